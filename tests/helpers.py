@@ -1,0 +1,63 @@
+"""Shared test helpers: fixture loading, tolerances, small nets rebuilt from fixtures."""
+import os
+
+import numpy as np
+import torch
+import torch.nn as nn
+
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+# Stated fp32 tolerances (BASELINE.json north_star / SURVEY.md section 8c)
+TOL_POSE = 1e-5      # absolute on R entries and t (both O(1) / O(0.1) quantities)
+TOL_SYS = 1e-4       # Frobenius-relative on J^T W J and J^T W r
+TOL_GRAD = 1e-3      # Frobenius-relative on gradients through the unrolled solve
+
+
+def load_golden(name):
+    z = np.load(os.path.join(GOLDEN, name + ".npz"))
+    return {k: torch.from_numpy(z[k]) for k in z.files}
+
+
+def frob_rel(a, b):
+    a = a.double().reshape(-1)
+    b = b.double().reshape(-1)
+    return ((a - b).norm() / b.norm().clamp_min(1e-30)).item()
+
+
+def level_inputs(g, prefix="in_"):
+    keys = ("x0", "x1", "s0", "s1", "invD0", "invD1", "K", "depth0", "depth1")
+    return {k: g[prefix + k] for k in keys if (prefix + k) in g}
+
+
+def damping_mlp(g):
+    """DirectSolverNet's 96->128->256->6 ReLU MLP (reference algorithms.py:1834-1842)."""
+    sd = {k[len("solver__"):]: v for k, v in g.items() if k.startswith("solver__")}
+    lin = [nn.Linear(96, 128), nn.Linear(128, 256), nn.Linear(256, 6)]
+    for i, l in enumerate(lin):
+        l.weight.data = sd[f"net.{i}.0.weight"].clone()
+        l.bias.data = sd[f"net.{i}.0.bias"].clone()
+    net = nn.Sequential(lin[0], nn.ReLU(), lin[1], nn.ReLU(), lin[2], nn.ReLU()).eval()
+    return net
+
+
+class ConvMEstimator(nn.Module):
+    """DeepRobustEstimator('MultiScale2w') (reference algorithms.py:1432-1478) rebuilt from a
+    fixture's state dict: 4 x (dilated conv + BN + ELU), sigmoid; input |r|, x0, x1, upsampled prior."""
+
+    def __init__(self, g):
+        super().__init__()
+        sd = {k[len("mest__net."):]: v for k, v in g.items() if k.startswith("mest__net.")}
+        layers = []
+        for i, (cin, cout, dil) in enumerate(((4, 16, 1), (16, 32, 2), (32, 64, 4), (64, 1, 1))):
+            conv = nn.Conv2d(cin, cout, 3, padding=dil, dilation=dil, bias=False)
+            bn = nn.BatchNorm2d(cout)
+            conv.weight.data = sd[f"{i}.0.weight"].clone()
+            for k in ("weight", "bias", "running_mean", "running_var"):
+                getattr(bn, k).data = sd[f"{i}.1.{k}"].clone()
+            layers += [conv, bn, nn.ELU()]
+        self.net = nn.Sequential(*layers, nn.Sigmoid()).eval()
+
+    def forward(self, residual, x0, x1, ws=None):
+        H, W = residual.shape[2:]
+        wl = nn.functional.interpolate(ws, (H, W), mode="bilinear", align_corners=True)
+        return self.net(torch.cat((residual.abs(), x0, x1, wl), dim=1))

@@ -1,0 +1,117 @@
+"""The CPU oracle against fixtures produced by the reference itself (tests/golden/make_golden.py).
+
+This is what pins the oracle: the reference ships no golden vectors of its own for this path.
+"""
+import pytest
+import torch
+
+from oracle import ic_oracle as O
+from helpers import (TOL_POSE, ConvMEstimator, damping_mlp, frob_rel, level_inputs, load_golden)
+
+UIC_CASES = ["uic_plain", "uic_trusigma", "uic_icp", "uic_masks", "uic_c8_wide"]
+
+
+def run_uic(g, sampler, trace=None):
+    f = g["flags"].tolist()
+    lv = level_inputs(g)
+    kw = {}
+    if f[2]:
+        kw = dict(obj_mask0=g["obj_mask0"].bool(), obj_mask1=g["obj_mask1"].bool())
+    return O.uic_level((g["R0"], g["t0"]), lv["x0"], lv["x1"], lv["invD0"], lv["invD1"], lv["K"], lv["s0"],
+                       lv["s1"], iters=f[3], remove_tru_sigma=bool(f[0]), combine_icp=bool(f[1]),
+                       depth0=lv.get("depth0"), depth1=lv.get("depth1"), uncer_prop=True, sampler=sampler,
+                       trace=trace, **kw), kw
+
+
+@pytest.mark.parametrize("name", UIC_CASES)
+@pytest.mark.parametrize("sampler", ["grid_sample", "explicit"])
+def test_uic_level_matches_reference(name, sampler):
+    g = load_golden(name)
+    trace = []
+    ((R, t), weights, A_last), kw = run_uic(g, sampler, trace)
+    for i, rec in enumerate(trace):
+        # validity masks: bit-exact, every iteration
+        assert torch.equal(rec["occ"].to(torch.uint8), g["it_occ"][i])
+        assert frob_rel(rec["A"], g["it_A"][i]) < 2e-6
+        assert frob_rel(rec["b"], g["it_b"][i]) < 2e-5
+    assert (R - g["R_out"]).abs().max() < 1e-6
+    assert (t - g["t_out"]).abs().max() < 1e-6
+    assert torch.allclose(weights, g["weights"])
+    assert frob_rel(A_last, g["A_last"]) < 2e-6
+
+
+@pytest.mark.parametrize("name", UIC_CASES)
+def test_uic_residual_loss_matches_reference(name):
+    g = load_golden(name)
+    f = g["flags"].tolist()
+    lv = level_inputs(g)
+    kw = {}
+    if f[2]:
+        kw = dict(obj_mask0=g["obj_mask0"].bool(), obj_mask1=g["obj_mask1"].bool())
+    loss = O.uic_residual_loss((g["R0"], g["t0"]), lv["x0"], lv["x1"], lv["invD0"], lv["invD1"], lv["K"],
+                               lv["s0"], lv["s1"], remove_tru_sigma=bool(f[0]), combine_icp=bool(f[1]),
+                               depth0=lv.get("depth0"), depth1=lv.get("depth1"), **kw)
+    assert frob_rel(loss, g["res_loss"]) < 1e-6
+
+
+@pytest.mark.parametrize("sampler", ["grid_sample", "explicit"])
+def test_uic_pyramid_chain_matches_reference(sampler):
+    g = load_golden("uic_pyramid")
+    f = g["flags"].tolist()
+    levels = [level_inputs(g, f"in{i}_") for i in range(4)]
+    B = levels[0]["x0"].shape[0]
+    trace = []
+    pose, per_level = O.track_pyramid(levels, (torch.eye(3).repeat(B, 1, 1), torch.zeros(B, 3)), iters=f[3],
+                                      remove_tru_sigma=bool(f[0]), sampler=sampler, trace=trace)
+    for i in range(4):
+        assert (per_level[i][0] - g[f"R_lvl{i}"]).abs().max() < 1e-6
+        assert (per_level[i][1] - g[f"t_lvl{i}"]).abs().max() < 1e-6
+        for j, rec in enumerate(trace[i]):
+            assert torch.equal(rec["occ"].to(torch.uint8), g[f"it{i}_occ"][j])
+    # the chain actually tracks: final error an order of magnitude below the initial one
+    assert (pose[1] - g["t_gt"]).abs().max() < 0.2 * g["t_gt"].abs().max()
+
+
+@pytest.mark.parametrize("name", ["uic_grad", "uic_grad_trusigma"])
+@pytest.mark.parametrize("sampler", ["grid_sample", "explicit"])
+def test_uic_autograd_matches_reference(name, sampler):
+    g = load_golden(name)
+    f = g["flags"].tolist()
+    lv = level_inputs(g)
+    leaves = {k: lv[k].clone().requires_grad_(True) for k in ("x0", "x1", "s0", "s1")}
+    R0 = g["R0"].clone().requires_grad_(True)
+    t0 = g["t0"].clone().requires_grad_(True)
+    (R, t), _, A = O.uic_level((R0, t0), leaves["x0"], leaves["x1"], lv["invD0"], lv["invD1"], lv["K"],
+                               leaves["s0"], leaves["s1"], iters=f[3], remove_tru_sigma=bool(f[0]),
+                               uncer_prop=True, sampler=sampler)
+    loss = (R * g["cR"]).sum() + (t * g["ct"]).sum() + (A * g["cA"]).sum()
+    loss.backward()
+    for k, v in leaves.items():
+        assert frob_rel(v.grad, g["g_" + k]) < 1e-5, k
+    assert frob_rel(R0.grad, g["g_R0"]) < 1e-5
+    assert frob_rel(t0.grad, g["g_t0"]) < 1e-5
+
+
+@pytest.mark.parametrize("name,solver", [("ic_plain", "Direct-Nodamping"), ("ic_resvol", "Direct-ResVol"),
+                                         ("ic_deepic", "Direct-ResVol")])
+@pytest.mark.parametrize("sampler", ["grid_sample", "explicit"])
+def test_ic_level_matches_reference(name, solver, sampler):
+    g = load_golden(name)
+    f = g["flags"].tolist()
+    lv = level_inputs(g)
+    net = damping_mlp(g) if solver == "Direct-ResVol" else None
+    mest = ConvMEstimator(g) if name == "ic_deepic" else None
+    trace = []
+    with torch.no_grad():
+        (R, t), w = O.ic_level((g["R0"], g["t0"]), lv["x0"], lv["x1"], lv["invD0"], lv["invD1"], lv["K"],
+                               iters=f[3], mest=mest, wPrior=g["wprior"], solver=solver, net=net,
+                               sampler=sampler, trace=trace)
+        loss = O.ic_residual_loss((g["R0"], g["t0"]), lv["x0"], lv["x1"], lv["invD0"], lv["invD1"], lv["K"],
+                                  mest=mest, wPrior=g["wprior"], sampler=sampler)
+    for j, rec in enumerate(trace):
+        assert frob_rel(rec["H"], g["it_H"][j]) < 1e-5
+        assert frob_rel(rec["b"], g["it_b"][j]) < 1e-4
+    assert (R - g["R_out"]).abs().max() < TOL_POSE
+    assert (t - g["t_out"]).abs().max() < TOL_POSE
+    assert frob_rel(w, g["weights"]) < 1e-5
+    assert frob_rel(loss, g["res_loss"]) < 1e-5
