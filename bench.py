@@ -1,0 +1,345 @@
+#!/usr/bin/env python
+"""Benchmark of the trust-region inverse-compositional solver path (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload tum|vga]
+
+A *step* is one coarse-to-fine solve (4 pyramid levels x 3 Gauss-Newton iterations, U_IC with
+--remove_tru_sigma as in every script the reference ships) of one batch of synthetic frame pairs.
+The metric is frame-pair GN solves per second; rank 0 prints ONE JSON line.
+
+  value      whole-job throughput with the inputs already in HBM (CUDA events, max over ranks)
+  e2e        same call made with HOST (pinned) buffers: host->device copy of the step's inputs and
+             device->host read of the poses inside the timed region
+  roofline   dominant kernel = the finest-level Gauss-Newton launch; algorithmic bytes per launch
+             (4C+2)*4*H*W*B  /  its average device time (events around every launch, separate pass)
+  cpu_baseline  the CPU port of the reference (oracle/) on this box's host cores, bounded sample
+
+N > 1 is launched by torchrun (one rank per GPU); frame pairs are independent, so every rank solves
+its own batch and there is no collective on the data path (weak scaling).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+
+WORKLOADS = {
+    # BASELINE.json configs[1]: TUM-shape 120x160, batch 64, C=8 features, 4 levels x 3 iterations
+    "tum": dict(name="tum120x160_b64_c8_uic_4lvl_x3it", B=64, C=8, H=120, W=160),
+    # BASELINE.json configs[2] per-GPU shard: 480x640, 128 pairs per GPU, processed 16 at a time
+    "vga": dict(name="vga480x640_b16_c8_uic_4lvl_x3it", B=16, C=8, H=480, W=640),
+}
+N_LEVELS, ITERS = 4, 3
+N_SETS = 4           # distinct input sets rotated between steps so no step finds its inputs in L2
+
+
+def algorithmic_bytes(B, C, H, W, levels=N_LEVELS, iters=ITERS):
+    """every iteration reads x0, x1, sigma0, sigma1 (C channels) and both inverse depths."""
+    per_level = [(4 * C + 2) * 4 * (H >> l) * (W >> l) * B for l in range(levels)]
+    return iters * sum(per_level), per_level[0]
+
+
+class ClockSampler:
+    """SM clock / throttle reasons sampled through NVML while the GPU is busy (same source as nvidia-smi)."""
+
+    def __init__(self, index: int, period: float = 0.01):
+        self.samples, self.reasons, self.max_mhz = [], set(), None
+        self._stop = threading.Event()
+        self._thr = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+        except Exception:   # pragma: no cover - NVML missing
+            self.nv = None
+        self.period = period
+
+    def _loop(self):
+        nv = self.nv
+        names = {
+            "hw_slowdown": getattr(nv, "nvmlClocksThrottleReasonHwSlowdown", 0x8),
+            "hw_thermal_slowdown": getattr(nv, "nvmlClocksThrottleReasonHwThermalSlowdown", 0x40),
+            "sw_thermal_slowdown": getattr(nv, "nvmlClocksThrottleReasonSwThermalSlowdown", 0x20),
+            "sw_power_cap": getattr(nv, "nvmlClocksThrottleReasonSwPowerCap", 0x4),
+        }
+        while not self._stop.is_set():
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for k, bit in names.items():
+                    if r & bit:
+                        self.reasons.add(k)
+            except Exception:
+                pass
+            time.sleep(self.period)
+
+    def __enter__(self):
+        if self.nv is not None:
+            self._thr = threading.Thread(target=self._loop, daemon=True)
+            self._thr.start()
+        return self
+
+    def __exit__(self, *exc):
+        self._stop.set()
+        if self._thr is not None:
+            self._thr.join()
+
+    def summary(self):
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons), "samples": 0}
+        return {"sm_mhz": statistics.median(self.samples), "sm_max_mhz": self.max_mhz,
+                "reasons": sorted(self.reasons), "samples": len(self.samples)}
+
+
+def pack_levels(levels, pin: bool):
+    """All tensors of a pyramid in ONE flat buffer (256-byte aligned pieces) so a step's input is one copy."""
+    layout, off = [], 0
+    for i, lv in enumerate(levels):
+        for k, v in lv.items():
+            layout.append((i, k, off, tuple(v.shape)))
+            off += (v.numel() + 63) // 64 * 64
+    flat = torch.empty(off, dtype=torch.float32, pin_memory=pin)
+    for (i, k, o, shape) in layout:
+        n = 1
+        for s in shape:
+            n *= s
+        flat[o:o + n].view(shape).copy_(levels[i][k])
+    return flat, layout
+
+
+def views(flat, layout, n_levels):
+    out = [dict() for _ in range(n_levels)]
+    for (i, k, o, shape) in layout:
+        n = 1
+        for s in shape:
+            n *= s
+        out[i][k] = flat[o:o + n].view(shape)
+    return out
+
+
+def cpu_sample(levels, R0, t0, n_pairs, min_seconds=8.0, max_reps=4):
+    """Time the oracle port (reference op chain: grid_sample + permute/bmm/sum) on the host cores."""
+    from oracle import ic_oracle as O
+    threads = os.cpu_count() or 1
+    torch.set_num_threads(threads)
+    sub = [{k: v[:n_pairs].contiguous() for k, v in lv.items()} for lv in levels]
+    pose = (R0[:n_pairs].contiguous(), t0[:n_pairs].contiguous())
+
+    def once():
+        with torch.no_grad():
+            return O.track_pyramid(sub, pose, iters=ITERS, remove_tru_sigma=True, sampler="grid_sample",
+                                   reduction="bmm")
+
+    small = [{k: v[:2].contiguous() for k, v in lv.items()} for lv in levels]
+    with torch.no_grad():
+        O.track_pyramid(small, (R0[:2], t0[:2]), iters=ITERS, remove_tru_sigma=True, sampler="grid_sample",
+                        reduction="bmm")
+    times = []
+    t_begin = time.perf_counter()
+    while len(times) < max_reps and (not times or time.perf_counter() - t_begin < min_seconds):
+        t = time.perf_counter()
+        once()
+        times.append(time.perf_counter() - t)
+    return n_pairs / min(times), threads, times
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=10)
+    ap.add_argument("--impl", default="ours", choices=("ours", "reference"))
+    ap.add_argument("--workload", default="tum", choices=tuple(WORKLOADS))
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-pdl", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3)
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    wl = WORKLOADS[args.workload]
+    B, C, H, W = wl["B"], wl["C"], wl["H"], wl["W"]
+    bytes_step, bytes_lvl0 = algorithmic_bytes(B, C, H, W)
+
+    from deep_prob_feature_track_b200.synthetic import make_frame_pairs
+
+    # ------------------------------------------------------------------ reference arm: CPU port, rank 0 only
+    if args.impl == "reference":
+        if rank != 0:
+            return
+        n_cpu = min(B, 16 if args.workload == "tum" else 1)
+        data = make_frame_pairs(n_cpu, C, H, W, seed=1234, n_levels=N_LEVELS)
+        from oracle import ic_oracle as O
+        threads = os.cpu_count() or 1
+        torch.set_num_threads(threads)
+
+        def step():
+            with torch.no_grad():
+                O.track_pyramid(data["levels"], (data["R0"], data["t0"]), iters=ITERS, remove_tru_sigma=True,
+                                sampler="grid_sample", reduction="bmm")
+
+        for _ in range(args.warmup):
+            step()
+        t = time.perf_counter()
+        for _ in range(args.steps):
+            step()
+        dt = time.perf_counter() - t
+        v = n_cpu * args.steps / dt
+        sample = f"{n_cpu} of the {B} pairs of a step, {args.steps} steps after {args.warmup} warm-up"
+        print(json.dumps({
+            "impl": "reference", "metric": "frame-pair GN solves/sec", "value": v, "unit": "pairs/s",
+            "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": wl["name"], "levels": N_LEVELS, "iters_per_level": ITERS, "variant": "U_IC",
+                       "remove_tru_sigma": True},
+            "cpu_baseline": {"value": v, "unit": "pairs/s", "cores": threads, "kind": "port", "sample": sample},
+            "e2e": {"value": v, "unit": "pairs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0,
+        }))
+        return
+
+    # ------------------------------------------------------------------ our arm
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py --impl ours needs a CUDA device (no CPU fallback exists)")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=dev)
+    from deep_prob_feature_track_b200 import algorithms as A
+
+    data = make_frame_pairs(B, C, H, W, seed=1234 + rank, n_levels=N_LEVELS)
+    host_flat, layout = pack_levels(data["levels"], pin=True)
+    dev_sets = []
+    for s in range(N_SETS):
+        # distinct allocations (distinct addresses) with the batch rolled by s: L2 can not serve step k+1 from step k
+        rolled = [{k: torch.roll(v, s, 0) for k, v in lv.items()} for lv in data["levels"]]
+        f, _ = pack_levels(rolled, pin=False)
+        dev_sets.append(views(f.to(dev), layout, N_LEVELS))
+    pose0 = (data["R0"].to(dev), data["t0"].to(dev))
+    set_bytes = host_flat.numel() * 4
+
+    def solve(levels, **kw):
+        return A.uic_solve(levels, pose0, iters=ITERS, remove_tru_sigma=True, pdl=not args.no_pdl, **kw)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    launches_per_step = 1 + N_LEVELS + N_LEVELS * ITERS     # init + sigma0 min/max per level + GN launches
+
+    with ClockSampler(local_rank) as clocks:
+        # ---- value: inputs resident in HBM
+        for i in range(args.warmup):
+            res = solve(dev_sets[i % N_SETS])
+        res.raise_if_bad()
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for i in range(args.steps):
+            res = solve(dev_sets[i % N_SETS])
+        e1.record()
+        barrier()
+        ms = e0.elapsed_time(e1)
+        res.raise_if_bad()
+        if world > 1:
+            t = torch.tensor([ms], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+
+        # ---- roofline: device time of every GN launch (events around each launch; separate pass)
+        lvl0 = []
+        per_launch = None
+        for i in range(max(3, min(args.steps, 20))):
+            r = solve(dev_sets[i % N_SETS], timed=True)
+            lvl0 += r.launch_ms[-ITERS:]
+            per_launch = r.launch_ms if per_launch is None else [a + b for a, b in zip(per_launch, r.launch_ms)]
+        n_timed = max(3, min(args.steps, 20))
+        per_launch = [x / n_timed for x in per_launch]
+        lvl0_ms = sum(lvl0) / len(lvl0)
+
+        # ---- e2e: host buffers in, poses out, every step
+        dev_flat = torch.empty_like(host_flat, device=dev)
+        dev_views = views(dev_flat, layout, N_LEVELS)
+        out_host = torch.empty((B, 12), dtype=torch.float32, pin_memory=True)
+
+        def e2e_step():
+            dev_flat.copy_(host_flat, non_blocking=True)
+            r = solve(dev_views)
+            out_host.copy_(r.pose_hist[-1], non_blocking=True)
+
+        n_e2e = max(3, min(args.steps, 30))
+        for _ in range(3):
+            e2e_step()
+        barrier()
+        e0.record()
+        for _ in range(n_e2e):
+            e2e_step()
+        e1.record()
+        barrier()
+        ms_e2e = e0.elapsed_time(e1)
+        if world > 1:
+            t = torch.tensor([ms_e2e], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms_e2e = float(t.item())
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    peak = float(peaks.get("hbm_gbs", 6650.0))
+    peak_src = "MEASURED_PEAKS.json hbm_gbs (measured copy bandwidth)" if peaks else "fallback 6650 GB/s"
+    achieved = bytes_lvl0 / (lvl0_ms * 1e-3) / 1e9
+    value = world * B * args.steps / (ms * 1e-3)
+    out = {
+        "metric": "frame-pair GN solves/sec", "value": value, "unit": "pairs/s", "n_gpus": world,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": wl["name"], "pairs_per_gpu_per_step": B, "feature_channels": C,
+                   "resolution": f"{H}x{W}", "levels": N_LEVELS, "iters_per_level": ITERS, "variant": "U_IC",
+                   "remove_tru_sigma": True, "pdl": not args.no_pdl,
+                   "l2": f"inputs rotate over {N_SETS} resident sets of {set_bytes / 1e6:.0f} MB each (> 126 MB L2)",
+                   "algorithmic_bytes_per_step": bytes_step},
+        "step_hbm_frac": bytes_step / (ms / args.steps * 1e-3) / 1e9 / peak,
+        "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                     "traffic": None, "kernel": "uic_iter_kernel<8,true> at the finest level",
+                     "algorithmic_bytes_per_launch": bytes_lvl0, "launch_ms": lvl0_ms,
+                     "all_launch_ms": [round(x, 4) for x in per_launch], "peak_source": peak_src,
+                     "how": "CUDA events around every launch (dpft_uic_forward_timed), separate pass after the timed region"},
+        "e2e": {"value": world * B * n_e2e / (ms_e2e * 1e-3), "unit": "pairs/s", "h2d_bytes_per_step": set_bytes,
+                "d2h_bytes_per_step": B * 12 * 4, "steps": n_e2e, "ms_per_step": ms_e2e / n_e2e},
+        "gpu_launches": launches_per_step * args.steps,
+        "clocks": clocks.summary(),
+    }
+    if not args.no_cpu_baseline:
+        n_cpu = min(B, 16 if args.workload == "tum" else 1)
+        v, threads, times = cpu_sample(data["levels"], data["R0"], data["t0"], n_cpu)
+        out["cpu_baseline"] = {"value": v, "unit": "pairs/s", "cores": threads, "kind": "port",
+                               "sample": f"first {n_cpu} pairs of the step's batch, best of {len(times)} runs "
+                                         f"({sum(times):.1f} s of CPU work)"}
+    print(json.dumps(out))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

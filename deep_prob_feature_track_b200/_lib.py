@@ -1,0 +1,121 @@
+"""ctypes binding of the C-ABI library (include/dpft.h) and its in-tree build.
+
+The library is built IN-TREE as ``deep_prob_feature_track_b200/libdpft.so`` by ``build()`` (called from
+``__graft_entry__.build()``): a plain ``nvcc -shared`` for sm_100a, no torch headers -- the ABI is plain
+pointers and sizes.  There is no fallback of any kind: if the library is missing or a CUDA device is not
+there, the calls raise.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+import shutil
+import subprocess
+from typing import List, Optional
+
+PKG_DIR = os.path.dirname(os.path.abspath(__file__))
+REPO_DIR = os.path.dirname(PKG_DIR)
+CSRC = os.path.join(PKG_DIR, "csrc")
+LIB_PATH = os.path.join(PKG_DIR, "libdpft.so")
+SOURCES = ["dpft_abi.cu", "uic_forward.cu"]
+NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
+              "-Xcompiler", "-fPIC", "-shared"]
+
+DPFT_ABI_VERSION = 1
+DPFT_MAX_LEVELS = 8
+DPFT_REMOVE_TRU_SIGMA = 0x01
+DPFT_COMBINE_ICP = 0x02
+DPFT_NO_PDL = 0x04
+DPFT_ST_NONFINITE = 0x01
+DPFT_ST_SINGULAR = 0x02
+
+c_float_p = ctypes.c_void_p   # device pointers travel as integers
+
+
+class DpftLevel(ctypes.Structure):
+    """struct dpft_level (include/dpft.h)."""
+    _fields_ = [
+        ("x0", c_float_p), ("x1", c_float_p),
+        ("sigma0", c_float_p), ("sigma1", c_float_p),
+        ("invd0", c_float_p), ("invd1", c_float_p),
+        ("depth0", c_float_p), ("depth1", c_float_p),
+        ("K", c_float_p),
+        ("obj_mask0", ctypes.c_void_p), ("obj_mask1", ctypes.c_void_p),
+        ("occ_out", ctypes.c_void_p),
+        ("H", ctypes.c_int32), ("W", ctypes.c_int32),
+    ]
+
+
+def _nvcc() -> str:
+    for cand in (os.environ.get("NVCC"), shutil.which("nvcc"), "/usr/local/cuda/bin/nvcc"):
+        if cand and os.path.exists(cand):
+            return cand
+    raise RuntimeError("nvcc not found; cannot build libdpft.so")
+
+
+def _stale() -> bool:
+    if not os.path.exists(LIB_PATH):
+        return True
+    t = os.path.getmtime(LIB_PATH)
+    deps = [os.path.join(CSRC, f) for f in os.listdir(CSRC)] + [os.path.join(REPO_DIR, "include", "dpft.h")]
+    return any(os.path.getmtime(d) > t for d in deps)
+
+
+def build(force: bool = False, verbose: bool = False) -> str:
+    """Compile csrc/*.cu into libdpft.so for sm_100a (cross-compiles without a GPU)."""
+    if not force and not _stale():
+        return LIB_PATH
+    cmd = [_nvcc(), *NVCC_FLAGS, "-I", os.path.join(REPO_DIR, "include"), "-I", CSRC,
+           "-o", LIB_PATH + ".tmp", *[os.path.join(CSRC, s) for s in SOURCES]]
+    if verbose:
+        cmd.insert(1, "-Xptxas=-v")
+    res = subprocess.run(cmd, capture_output=True, text=True)
+    if res.returncode != 0:
+        raise RuntimeError("nvcc failed:\n" + " ".join(cmd) + "\n" + res.stdout + res.stderr)
+    os.replace(LIB_PATH + ".tmp", LIB_PATH)
+    if verbose:
+        print(res.stderr)
+    return LIB_PATH
+
+
+_lib: Optional[ctypes.CDLL] = None
+
+
+def lib() -> ctypes.CDLL:
+    """The loaded library; raises if it has not been built (no fallback)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise RuntimeError(
+            f"{LIB_PATH} is missing: run `python -c 'import __graft_entry__ as g; g.build()'` "
+            "(the CUDA library is the only implementation of this path)")
+    L = ctypes.CDLL(LIB_PATH)
+    L.dpft_abi_version.restype = ctypes.c_int
+    L.dpft_last_error.restype = ctypes.c_char_p
+    L.dpft_uic_workspace_bytes.restype = ctypes.c_size_t
+    L.dpft_uic_workspace_bytes.argtypes = [ctypes.POINTER(DpftLevel), ctypes.c_int, ctypes.c_int, ctypes.c_int,
+                                           ctypes.c_int, ctypes.c_uint32]
+    L.dpft_uic_forward.restype = ctypes.c_int
+    L.dpft_uic_forward.argtypes = [ctypes.POINTER(DpftLevel), ctypes.c_int, ctypes.c_int, ctypes.c_int,
+                                   ctypes.c_int, ctypes.c_uint32, ctypes.c_float, ctypes.c_void_p,
+                                   ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p,
+                                   ctypes.c_size_t, ctypes.c_void_p]
+    L.dpft_uic_forward_timed.restype = ctypes.c_int
+    L.dpft_uic_forward_timed.argtypes = L.dpft_uic_forward.argtypes + [ctypes.POINTER(ctypes.c_float)]
+    if L.dpft_abi_version() != DPFT_ABI_VERSION:
+        raise RuntimeError("libdpft.so ABI version mismatch; rebuild")
+    _lib = L
+    return L
+
+
+def exported_symbols() -> List[str]:
+    """Entry points include/dpft.h declares (kept in sync by tests/test_abi.py)."""
+    return ["dpft_abi_version", "dpft_last_error", "dpft_uic_workspace_bytes", "dpft_uic_forward",
+            "dpft_uic_forward_timed"]
+
+
+def check(code: int, what: str) -> None:
+    if code != 0:
+        msg = lib().dpft_last_error().decode()
+        raise RuntimeError(f"{what} failed with code {code}: {msg}")

@@ -1,0 +1,210 @@
+"""Host-side mirror of the reference's solver modules, backed by the CUDA library.
+
+Class names, constructor arguments, ``forward`` signatures, return tuples and attribute names follow
+``/root/reference/code/models/algorithms.py`` (TrustRegionInverseWUncertainty :579-997, TrustRegionBase
+:23-139) so a ``LeastSquareTracking`` can have its ``tr_update0..3`` children swapped for these
+(``patch_tracker`` below) and keep loading its checkpoints.  All arithmetic happens in
+``libdpft.so`` (csrc/*.cu) through the C ABI of ``include/dpft.h``; there is no PyTorch fallback.
+"""
+from __future__ import annotations
+
+import ctypes
+from typing import Dict, List, Optional, Sequence, Tuple
+
+import torch
+import torch.nn as nn
+
+from . import _lib
+
+Pose = Tuple[torch.Tensor, torch.Tensor]
+
+
+# ----------------------------------------------------------------------------- plumbing
+def _dev_f32(t: torch.Tensor, name: str) -> torch.Tensor:
+    if not t.is_cuda:
+        raise RuntimeError(f"{name} must be a CUDA tensor: this path has no CPU implementation")
+    if t.dtype != torch.float32:
+        t = t.float()
+    return t.contiguous()
+
+
+def _dev_mask(t: Optional[torch.Tensor], name: str) -> Optional[torch.Tensor]:
+    if t is None:
+        return None
+    if not t.is_cuda:
+        raise RuntimeError(f"{name} must be a CUDA tensor")
+    return t.to(torch.uint8).contiguous() if t.dtype != torch.uint8 else t.contiguous()
+
+
+def pack_pose(pose: Pose) -> torch.Tensor:
+    """[R (B,3,3), t (B,3) | (B,3,1)] -> (B,12) rows R|t."""
+    R, t = pose
+    B = R.shape[0]
+    return torch.cat((R.reshape(B, 9), t.reshape(B, 3)), dim=1).float().contiguous()
+
+
+def unpack_pose(rows: torch.Tensor) -> Pose:
+    B = rows.shape[0]
+    return rows[:, :9].reshape(B, 3, 3), rows[:, 9:12]
+
+
+_TRI = [(i, j) for i in range(6) for j in range(i, 6)]
+
+
+def unpack_system(sys_rows: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
+    """(...,27) -> symmetric J^T W J (...,6,6) and J^T W r (...,6,1)."""
+    A = sys_rows.new_zeros(sys_rows.shape[:-1] + (6, 6))
+    for k, (i, j) in enumerate(_TRI):
+        A[..., i, j] = sys_rows[..., k]
+        A[..., j, i] = sys_rows[..., k]
+    return A, sys_rows[..., 21:27].unsqueeze(-1)
+
+
+class SolveResult:
+    """What one call into the library hands back (all device tensors, nothing synchronised)."""
+    __slots__ = ("pose_hist", "sys_hist", "status", "occ", "n_levels", "iters", "launch_ms")
+
+    def __init__(self, pose_hist, sys_hist, status, occ, n_levels, iters, launch_ms=None):
+        self.pose_hist, self.sys_hist, self.status, self.occ = pose_hist, sys_hist, status, occ
+        self.n_levels, self.iters, self.launch_ms = n_levels, iters, launch_ms
+
+    @property
+    def pose(self) -> Pose:
+        return unpack_pose(self.pose_hist[-1])
+
+    def level_pose(self, level: int) -> Pose:
+        """Pose after the ``level``-th solved level (0 = coarsest)."""
+        return unpack_pose(self.pose_hist[(level + 1) * self.iters])
+
+    def raise_if_bad(self) -> None:
+        """Host check of the device status word (one sync) -- the reference's check_nan asserts
+        (algorithms.py:886, :1988) raise AssertionError, so does this."""
+        st = int(self.status.item())
+        assert not (st & _lib.DPFT_ST_NONFINITE), "non-finite weighted residual / normal equations"
+        if st & _lib.DPFT_ST_SINGULAR:
+            raise RuntimeError("damped Gauss-Newton system is not positive definite")
+
+
+def uic_solve(levels: Sequence[Dict[str, torch.Tensor]], pose: Pose, *, iters: int = 3,
+              remove_tru_sigma: bool = False, want_occ: bool = False, pdl: bool = True, timed: bool = False,
+              obj_mask0: Optional[Sequence] = None, obj_mask1: Optional[Sequence] = None) -> SolveResult:
+    """Coarse-to-fine U_IC solve of a batch of frame pairs on the current CUDA stream.
+
+    ``levels`` is ordered coarse to fine; each dict holds x0, x1, s0, s1 (B,C,h,w), invD0, invD1 (B,1,h,w)
+    and K (B,4) already scaled to the level.  One entry == one TrustRegionInverseWUncertainty.forward.
+    """
+    L = _lib.lib()
+    n_levels = len(levels)
+    x0 = levels[0]["x0"]
+    B, C = int(x0.shape[0]), int(x0.shape[1])
+    dev = x0.device
+    keep = []   # keep converted tensors alive until the launches are queued
+    arr = (_lib.DpftLevel * n_levels)()
+    occ: List[Optional[torch.Tensor]] = []
+    for i, lv in enumerate(levels):
+        t = {k: _dev_f32(lv[k], k) for k in ("x0", "x1", "s0", "s1", "invD0", "invD1", "K")}
+        H, W = int(t["x0"].shape[2]), int(t["x0"].shape[3])
+        for k in ("x0", "x1", "s0", "s1"):
+            if tuple(t[k].shape) != (B, C, H, W):
+                raise ValueError(f"level {i}: {k} has shape {tuple(t[k].shape)}, expected {(B, C, H, W)}")
+        for k in ("invD0", "invD1"):
+            if t[k].numel() != B * H * W:
+                raise ValueError(f"level {i}: {k} must be (B,1,H,W)")
+        if tuple(t["K"].shape) != (B, 4):
+            raise ValueError(f"level {i}: K must be (B,4)")
+        m0 = _dev_mask(obj_mask0[i] if obj_mask0 is not None else None, "obj_mask0")
+        m1 = _dev_mask(obj_mask1[i] if obj_mask1 is not None else None, "obj_mask1")
+        o = torch.empty((iters, B, H, W), dtype=torch.uint8, device=dev) if want_occ else None
+        occ.append(o)
+        keep += [t, m0, m1]
+        a = arr[i]
+        a.x0, a.x1, a.sigma0, a.sigma1 = (t[k].data_ptr() for k in ("x0", "x1", "s0", "s1"))
+        a.invd0, a.invd1, a.K = t["invD0"].data_ptr(), t["invD1"].data_ptr(), t["K"].data_ptr()
+        a.depth0 = a.depth1 = None
+        a.obj_mask0 = m0.data_ptr() if m0 is not None else None
+        a.obj_mask1 = m1.data_ptr() if m1 is not None else None
+        a.occ_out = o.data_ptr() if o is not None else None
+        a.H, a.W = H, W
+    flags = (_lib.DPFT_REMOVE_TRU_SIGMA if remove_tru_sigma else 0) | (0 if pdl else _lib.DPFT_NO_PDL)
+    n_it = n_levels * iters
+    pose_in = pack_pose(pose).to(dev)
+    pose_hist = torch.empty((n_it + 1, B, 12), dtype=torch.float32, device=dev)
+    sys_hist = torch.empty((max(n_it, 1), B, 27), dtype=torch.float32, device=dev)
+    status = torch.zeros((1,), dtype=torch.int32, device=dev)
+    ws_bytes = L.dpft_uic_workspace_bytes(arr, n_levels, B, C, iters, flags)
+    if ws_bytes == 0:
+        raise RuntimeError("dpft_uic_workspace_bytes: " + L.dpft_last_error().decode())
+    ws = torch.empty((ws_bytes,), dtype=torch.uint8, device=dev)
+    stream = torch.cuda.current_stream(dev).cuda_stream
+    launch_ms = None
+    args = (arr, n_levels, B, C, iters, flags, ctypes.c_float(0.01), pose_in.data_ptr(), pose_hist.data_ptr(),
+            sys_hist.data_ptr(), status.data_ptr(), ws.data_ptr(), ws_bytes, stream)
+    with torch.cuda.device(dev):
+        if timed:   # measurement aid (bench.py): per-launch device times, synchronises the stream
+            buf = (ctypes.c_float * n_it)()
+            code = L.dpft_uic_forward_timed(*args, buf)
+            launch_ms = list(buf)
+        else:
+            code = L.dpft_uic_forward(*args)
+    _lib.check(code, "dpft_uic_forward")
+    del keep   # launches are queued on the allocating stream; the caching allocator orders reuse after them
+    return SolveResult(pose_hist, sys_hist[:n_it], status, occ, n_levels, iters, launch_ms)
+
+
+# ----------------------------------------------------------------------------- reference-shaped modules
+class TrustRegionInverseWUncertainty(nn.Module):
+    """Drop-in for reference algorithms.py:579-997 (track_type 'U_IC').
+
+    Same constructor and ``forward`` signature and return tuple.  ``mEst_func`` and ``solver_func`` are
+    accepted and stored under the reference's attribute names (``mEstimator``, ``directSolver``) because
+    checkpoints carry their parameters, but -- exactly as in the reference (:642-644, :836) -- never called.
+    ``vis_res`` is accepted and ignored (the reference opens OpenCV windows there).
+    """
+
+    def __init__(self, max_iter=3, mEst_func=None, solver_func=None, timers=None, uncer_prop=False,
+                 combine_icp=False, scale_func=None, remove_tru_sigma=False):
+        super().__init__()
+        self.max_iterations = max_iter
+        self.mEstimator = mEst_func
+        self.directSolver = solver_func
+        self.timers = timers
+        self.uncer_prop = uncer_prop
+        self.combine_icp = combine_icp
+        self.scale_func = scale_func
+        self.remove_tru_sigma = remove_tru_sigma
+        self.check_nan = True   # reference asserts after every iteration (host sync); one sync per call here
+
+    def forward(self, pose10, x0, x1, invD0, invD1, K, sigma0, sigma1, wPrior=None, depth0=None, depth1=None,
+                vis_res=True, obj_mask0=None, obj_mask1=None):
+        assert sigma0 is not None and sigma1 is not None
+        if self.combine_icp:
+            raise NotImplementedError("combine_icp: the ICP term is not built yet (DESIGN.md, 'next')")
+        if torch.is_grad_enabled() and any(t.requires_grad for t in (x0, x1, sigma0, sigma1, pose10[0], pose10[1])):
+            raise NotImplementedError("backward kernels are not built yet (DESIGN.md, 'next')")
+        if self.timers: self.timers.tic('trust-region level solve (fused CUDA)')
+        lv = dict(x0=x0, x1=x1, s0=sigma0, s1=sigma1, invD0=invD0, invD1=invD1, K=K)
+        res = uic_solve([lv], pose10, iters=self.max_iterations, remove_tru_sigma=self.remove_tru_sigma,
+                        obj_mask0=None if obj_mask0 is None else [obj_mask0],
+                        obj_mask1=None if obj_mask1 is None else [obj_mask1])
+        if self.check_nan:
+            res.raise_if_bad()
+        if self.timers: self.timers.toc('trust-region level solve (fused CUDA)')
+        weights = torch.ones((1, 1, 1, 1), dtype=x0.dtype, device=x0.device).expand(x0.shape)
+        if self.uncer_prop:
+            A, _ = unpack_system(res.sys_hist[-1])
+            return res.pose, weights, A
+        return res.pose, weights
+
+
+def patch_tracker(net: nn.Module) -> nn.Module:
+    """Swap the ``tr_update0..3`` children of a reference ``LeastSquareTracking`` (U_IC) for the CUDA-backed
+    modules, keeping their learned sub-modules so ``state_dict`` keys are unchanged."""
+    for i in range(4):
+        name = f"tr_update{i}"
+        old = getattr(net, name)
+        if type(old).__name__ != "TrustRegionInverseWUncertainty":
+            raise NotImplementedError(f"{name} is a {type(old).__name__}; only the U_IC tracker is built so far")
+        new = TrustRegionInverseWUncertainty(old.max_iterations, old.mEstimator, old.directSolver, old.timers,
+                                             old.uncer_prop, old.combine_icp, old.scale_func, old.remove_tru_sigma)
+        setattr(net, name, new)
+    return net

@@ -1,0 +1,252 @@
+// Device-side building blocks shared by the solver kernels (sm_100a).
+//
+// Arithmetic that feeds a validity mask is written with the *_rn intrinsics so that nvcc can not
+// contract it into FMAs: every product and sum is rounded on its own, in the order the oracle
+// (oracle/ic_oracle.py: project, _unnormalise, sample_border) spells out.  Everything else is
+// ordinary fp32 and free to fuse.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace dpft {
+
+__device__ __forceinline__ float xmul(float a, float b) { return __fmul_rn(a, b); }
+__device__ __forceinline__ float xadd(float a, float b) { return __fadd_rn(a, b); }
+__device__ __forceinline__ float xsub(float a, float b) { return __fsub_rn(a, b); }
+__device__ __forceinline__ float xdiv(float a, float b) { return __fdiv_rn(a, b); }
+
+// Order-preserving map float -> uint32 so atomicMin/atomicMax work on floats of either sign.
+__device__ __forceinline__ uint32_t f2ord(float f) {
+  uint32_t u = __float_as_uint(f);
+  return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+__device__ __forceinline__ float ord2f(uint32_t u) {
+  return __uint_as_float((u & 0x80000000u) ? (u & 0x7fffffffu) : ~u);
+}
+
+// Pose of one pair, held in registers.
+struct Pose {
+  float r[9];
+  float t[3];
+};
+
+__device__ __forceinline__ Pose load_pose(const float* __restrict__ row) {
+  Pose p;
+#pragma unroll
+  for (int i = 0; i < 9; ++i) p.r[i] = row[i];
+#pragma unroll
+  for (int i = 0; i < 3; ++i) p.t[i] = row[9 + i];
+  return p;
+}
+
+// SE(3) warp of the ray (x, y, 1) at inverse depth d (reference geometry.py:291-323).
+// w = ((r0*x + r1*y) + r2) + t*d, each step rounded; u = (w.x/w.z)*fx + cx; inv_z = d / w.z
+__device__ __forceinline__ void warp_pixel(const Pose& p, float x, float y, float d, float fx, float fy,
+                                           float cx, float cy, float& u, float& v, float& inv_z) {
+  float w[3];
+#pragma unroll
+  for (int i = 0; i < 3; ++i)
+    w[i] = xadd(xadd(xadd(xmul(p.r[3 * i], x), xmul(p.r[3 * i + 1], y)), p.r[3 * i + 2]), xmul(p.t[i], d));
+  u = xadd(xmul(xdiv(w[0], w[2]), fx), cx);
+  v = xadd(xmul(xdiv(w[1], w[2]), fy), cy);
+  inv_z = xdiv(d, w[2]);
+}
+
+// Bilinear footprint with border padding: warp_features (geometry.py:353-365) followed by torch's
+// grid_sampler_2d(align_corners=True, padding_mode='border') un-normalisation, clip and weights.
+struct Tap {
+  int o_nw, o_ne, o_sw, o_se;   // element offsets inside one (H,W) plane
+  float w_nw, w_ne, w_sw, w_se;
+};
+
+__device__ __forceinline__ float unnormalise(float coord, float half_span, float span) {
+  float g = xsub(xdiv(coord, half_span), 1.f);          // u / ((W-1)/2) - 1
+  float pix = xmul(xmul(xadd(g, 1.f), 0.5f), span);     // ((g+1)/2) * (W-1)
+  return fminf(fmaxf(pix, 0.f), span);                  // clip to [0, W-1]
+}
+
+__device__ __forceinline__ Tap make_tap(float u, float v, int H, int W) {
+  const float ix = unnormalise(u, 0.5f * (float)(W - 1), (float)(W - 1));
+  const float iy = unnormalise(v, 0.5f * (float)(H - 1), (float)(H - 1));
+  const float xw = floorf(ix), yn = floorf(iy);
+  const float tx1 = xsub(ix, xw), ty1 = xsub(iy, yn);
+  const float tx0 = xsub(xadd(xw, 1.f), ix), ty0 = xsub(xadd(yn, 1.f), iy);
+  Tap t;
+  t.w_nw = xmul(tx0, ty0);
+  t.w_ne = xmul(tx1, ty0);
+  t.w_sw = xmul(tx0, ty1);
+  t.w_se = xmul(tx1, ty1);
+  const int xi = min(max((int)xw, 0), W - 1), yi = min(max((int)yn, 0), H - 1);
+  const int xe = min(xi + 1, W - 1), ys = min(yi + 1, H - 1);   // weight is exactly 0 when these clamp
+  t.o_nw = yi * W + xi;
+  t.o_ne = yi * W + xe;
+  t.o_sw = ys * W + xi;
+  t.o_se = ys * W + xe;
+  return t;
+}
+
+// ((nw*w + ne*w) + sw*w) + se*w with every step rounded (mask-grade).
+__device__ __forceinline__ float blend_exact(float nw, float ne, float sw, float se, const Tap& t) {
+  return xadd(xadd(xadd(xmul(nw, t.w_nw), xmul(ne, t.w_ne)), xmul(sw, t.w_sw)), xmul(se, t.w_se));
+}
+__device__ __forceinline__ float blend_fast(float nw, float ne, float sw, float se, const Tap& t) {
+  return fmaf(se, t.w_se, fmaf(sw, t.w_sw, fmaf(ne, t.w_ne, nw * t.w_nw)));
+}
+__device__ __forceinline__ float sample_exact(const float* __restrict__ plane, const Tap& t) {
+  return blend_exact(__ldg(plane + t.o_nw), __ldg(plane + t.o_ne), __ldg(plane + t.o_sw), __ldg(plane + t.o_se), t);
+}
+__device__ __forceinline__ float sample_mask(const uint8_t* __restrict__ plane, const Tap& t) {
+  return blend_exact((float)__ldg(plane + t.o_nw), (float)__ldg(plane + t.o_ne), (float)__ldg(plane + t.o_sw),
+                     (float)__ldg(plane + t.o_se), t);
+}
+
+// z-buffer + in-view test (geometry.py:334-350). true = excluded.
+__device__ __forceinline__ bool occluded(float u, float v, float inv_z, float d1w, int H, int W) {
+  const bool ok = (inv_z > xsub(d1w, 0.1f)) && (u > 0.f) && (u < (float)W) && (v > 0.f) && (v < (float)H);
+  return !ok;
+}
+
+// Rows of d(u,v)/d(xi) at the identity (algorithms.py:1884-1917), twist = [rot, trs].
+// ju[4] and jv[3] are structurally zero and never touched by the callers.
+__device__ __forceinline__ void warp_rows(float x, float y, float d, float fx, float fy, float ju[6], float jv[6]) {
+  const float xy = x * y;
+  ju[0] = fx * (-xy);
+  ju[1] = fx * (1.f + x * x);
+  ju[2] = fx * (-y);
+  ju[3] = fx * d;
+  ju[4] = 0.f;
+  ju[5] = fx * (-d * x);
+  jv[0] = fy * (-1.f - y * y);
+  jv[1] = fy * xy;
+  jv[2] = fy * x;
+  jv[3] = 0.f;
+  jv[4] = fy * d;
+  jv[5] = fy * (-d * y);
+}
+
+// index of (i,j), i<=j, in the 21-entry row-major upper triangle of a symmetric 6x6
+__host__ __device__ constexpr int tri(int i, int j) { return i * 6 - (i * (i - 1)) / 2 + (j - i); }
+
+// A += sum over the pixel's channels of J_c J_c^T and b += sum J_c r_c, where J_c = a_c*ju + b_c*jv:
+// with saa = sum a^2, sab = sum a b, sbb = sum b^2, sar = sum a r, sbr = sum b r this is
+//   A += ju (saa ju + sab jv)^T + jv (sab ju + sbb jv)^T ,  b += sar ju + sbr jv
+// (the C x 6 Jacobian of algorithms.py:867-887 is never formed).
+__device__ __forceinline__ void accumulate_system(float acc[27], const float ju[6], const float jv[6], float saa,
+                                                  float sab, float sbb, float sar, float sbr) {
+  float P[6], Q[6];
+#pragma unroll
+  for (int j = 0; j < 6; ++j) {
+    if (j == 4) { P[j] = sab * jv[j]; Q[j] = sbb * jv[j]; }
+    else if (j == 3) { P[j] = saa * ju[j]; Q[j] = sab * ju[j]; }
+    else { P[j] = fmaf(saa, ju[j], sab * jv[j]); Q[j] = fmaf(sab, ju[j], sbb * jv[j]); }
+  }
+#pragma unroll
+  for (int i = 0; i < 6; ++i) {
+#pragma unroll
+    for (int j = i; j < 6; ++j) {
+      float a = acc[tri(i, j)];
+      if (i != 4) a = fmaf(ju[i], P[j], a);
+      if (i != 3) a = fmaf(jv[i], Q[j], a);
+      acc[tri(i, j)] = a;
+    }
+    float r = acc[21 + i];
+    if (i != 4) r = fmaf(sar, ju[i], r);
+    if (i != 3) r = fmaf(sbr, jv[i], r);
+    acc[21 + i] = r;
+  }
+}
+
+// ------------------------------------------------------------------ 6x6 solve and pose update (fp64)
+// H = A + 1e-6 trace(A) I (algorithms.py:2094-2103), xi = H^-1 b by Cholesky (H is SPD), then the
+// inverse-compositional update of algorithms.py:2035-2054 / geometry.py:105-123,163-185:
+//   dR = exp(-xi_w) (Rodrigues, no small-angle guard), dt = -dR xi_v, R <- R dR, t <- R dt + t.
+// A: 21 upper-triangular entries. Returns false if a pivot is not positive.
+__device__ inline bool solve_and_update(const double A[21], const double rhs[6], bool damp_trace,
+                                        const float* __restrict__ pose_in, float* __restrict__ pose_out,
+                                        double xi_out[6]) {
+  double L[6][6];
+  double tr = 0.0;
+#pragma unroll
+  for (int i = 0; i < 6; ++i) tr += A[tri(i, i)];
+  const double eps = damp_trace ? tr * 1e-6 : 0.0;
+  bool ok = true;
+#pragma unroll
+  for (int j = 0; j < 6; ++j) {
+    double s = A[tri(j, j)] + eps;
+#pragma unroll
+    for (int k = 0; k < j; ++k) s -= L[j][k] * L[j][k];
+    ok = ok && (s > 0.0);
+    const double d = sqrt(s);
+    L[j][j] = d;
+    const double inv = 1.0 / d;
+#pragma unroll
+    for (int i = j + 1; i < 6; ++i) {
+      double v = A[tri(j, i)];
+#pragma unroll
+      for (int k = 0; k < j; ++k) v -= L[i][k] * L[j][k];
+      L[i][j] = v * inv;
+    }
+  }
+  double z[6], xi[6];
+#pragma unroll
+  for (int i = 0; i < 6; ++i) {
+    double v = rhs[i];
+#pragma unroll
+    for (int k = 0; k < i; ++k) v -= L[i][k] * z[k];
+    z[i] = v / L[i][i];
+  }
+#pragma unroll
+  for (int i = 5; i >= 0; --i) {
+    double v = z[i];
+#pragma unroll
+    for (int k = i + 1; k < 6; ++k) v -= L[k][i] * xi[k];
+    xi[i] = v / L[i][i];
+  }
+#pragma unroll
+  for (int i = 0; i < 6; ++i) xi_out[i] = xi[i];
+
+  const double wx = -xi[0], wy = -xi[1], wz = -xi[2];
+  const double th = sqrt(wx * wx + wy * wy + wz * wz);
+  const double kx = wx / th, ky = wy / th, kz = wz / th;   // NaN at th == 0, as in the reference
+  const double s = sin(th), c1 = 1.0 - cos(th);
+  const double Kx[9] = {0, -kz, ky, kz, 0, -kx, -ky, kx, 0};
+  double dR[9];
+#pragma unroll
+  for (int i = 0; i < 3; ++i)
+#pragma unroll
+    for (int j = 0; j < 3; ++j) {
+      double kk = 0;
+#pragma unroll
+      for (int k = 0; k < 3; ++k) kk += Kx[3 * i + k] * Kx[3 * k + j];
+      dR[3 * i + j] = (i == j ? 1.0 : 0.0) + Kx[3 * i + j] * s + kk * c1;
+    }
+  double dt[3];
+#pragma unroll
+  for (int i = 0; i < 3; ++i) dt[i] = -(dR[3 * i] * xi[3] + dR[3 * i + 1] * xi[4] + dR[3 * i + 2] * xi[5]);
+  double R[9], t[3];
+#pragma unroll
+  for (int i = 0; i < 9; ++i) R[i] = (double)pose_in[i];
+#pragma unroll
+  for (int i = 0; i < 3; ++i) t[i] = (double)pose_in[9 + i];
+#pragma unroll
+  for (int i = 0; i < 3; ++i) {
+#pragma unroll
+    for (int j = 0; j < 3; ++j)
+      pose_out[3 * i + j] = (float)(R[3 * i] * dR[j] + R[3 * i + 1] * dR[3 + j] + R[3 * i + 2] * dR[6 + j]);
+    pose_out[9 + i] = (float)(R[3 * i] * dt[0] + R[3 * i + 1] * dt[1] + R[3 * i + 2] * dt[2] + t[i]);
+  }
+  return ok;
+}
+
+__device__ __forceinline__ float warp_min(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fminf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+
+}  // namespace dpft

@@ -1,0 +1,664 @@
+// U_IC forward: one Gauss-Newton iteration per launch, every launch fused end to end.
+//
+//   uic_iter_kernel    warp + bilinear lookup + validity mask + residual + Jacobian + J^T J / J^T r
+//                      partial sums, then (last CTA of a pair) the per-pair reduction and (last CTA
+//                      of the grid, or of the pair) the damped 6x6 solve and the pose update.
+//
+// Restates reference code/models/algorithms.py:611-723 (TrustRegionInverseWUncertainty.forward) with
+// the arithmetic of oracle/ic_oracle.py; see DESIGN.md for the data flow and the byte accounting.
+//
+// Thread mapping: a warp owns a tile of 30 output columns x TR rows of one frame pair.  Lanes 0 and
+// 31 are halo columns (clamped at the image border = replicate padding), so the horizontal Sobel
+// taps come from __shfl of the neighbouring lanes and the vertical taps from a 3-row register window
+// that slides down the tile: every x0 / sigma0 element is loaded once per tile (coalesced 128 B rows),
+// the unit Sobel gradients are recomputed instead of stored, and nothing per-pixel is written back.
+#include <cuda_runtime.h>
+#include <math_constants.h>
+#include <stdint.h>
+
+#include <algorithm>
+
+#include "dpft.h"
+#include "dpft_device.cuh"
+#include "dpft_host.h"
+
+namespace dpft {
+
+constexpr int kWarps = 4;
+constexpr int kThreads = kWarps * 32;
+constexpr int kCols = 30;          // output columns per warp tile
+constexpr int PS = 48;             // floats per partial record
+constexpr int NSUM = 39;           // 21 A + 6 b + 6 corr(min) + 6 corr(max)
+constexpr int E_VMIN = 27, E_VMAX = 28, E_CMIN = 29, E_CMAX = 35;
+
+struct UicIterParams {
+  const float *x0, *x1, *s0, *s1, *d0, *d1, *K;
+  const uint8_t *m0, *m1;
+  uint8_t* occ_out;      // (B,H,W) of this iteration or nullptr
+  float* sr0_dbg;        // (B,H,W) warped sigma channel 0 (only with occ_out + TRU)
+  int H, W, B, C;
+  int nseg, nrt, TR, ctas_per_pair;
+  const float* pose;     // (B,12) pose this iteration linearises at
+  float* pose_next;      // (B,12)
+  float* sys_out;        // (B,27)
+  float* partials;       // (B, ctas_per_pair, PS)
+  double* pairrec;       // (B, PS)
+  int* counters;         // [B] per pair, [B] = pairs done
+  const uint32_t* s0mm;  // order-encoded min, max of sigma0 over the whole level tensor
+  float* gmm;            // [2] batch-global min/max of the warped sigma (written for the debug pass)
+  int32_t* status;
+  uint32_t flags;
+};
+
+// Final step for one pair: corrections for the batch-global sigma extremes, damping, solve, update.
+template <bool TRU>
+__device__ void finalize_pair(const UicIterParams& p, int b, float gmin, float gmax) {
+  const double* rec = p.pairrec + (size_t)b * PS;
+  double A[21], rhs[6];
+#pragma unroll
+  for (int i = 0; i < 21; ++i) A[i] = __ldcg(rec + i);
+#pragma unroll
+  for (int i = 0; i < 6; ++i) rhs[i] = __ldcg(rec + 21 + i);
+  if (TRU) {
+    // pixels whose warped sigma (channel 0) equals the batch-global min or max are masked
+    // (algorithms.py:1976-1979): their weighted residual becomes 1e-6, i.e. subtract what they added.
+    const bool at_min = ((float)__ldcg(rec + E_VMIN) == gmin);
+    const bool at_max = ((float)__ldcg(rec + E_VMAX) == gmax) && (gmax != gmin);
+#pragma unroll
+    for (int i = 0; i < 6; ++i) {
+      if (at_min) rhs[i] -= __ldcg(rec + E_CMIN + i);
+      if (at_max) rhs[i] -= __ldcg(rec + E_CMAX + i);
+    }
+  }
+  bool finite = true;
+#pragma unroll
+  for (int i = 0; i < 21; ++i) finite = finite && isfinite(A[i]);
+#pragma unroll
+  for (int i = 0; i < 6; ++i) finite = finite && isfinite(rhs[i]);
+  float* sys = p.sys_out + (size_t)b * 27;
+#pragma unroll
+  for (int i = 0; i < 21; ++i) sys[i] = (float)A[i];
+#pragma unroll
+  for (int i = 0; i < 6; ++i) sys[21 + i] = (float)rhs[i];
+  double xi[6];
+  const bool ok = solve_and_update(A, rhs, true, p.pose + (size_t)b * 12, p.pose_next + (size_t)b * 12, xi);
+  int st = 0;
+  if (!finite) st |= DPFT_ST_NONFINITE;
+  if (!ok) st |= DPFT_ST_SINGULAR;
+  if (st) atomicOr(p.status, st);
+}
+
+template <int CH, bool TRU>
+__global__ void __launch_bounds__(kThreads) uic_iter_kernel(const UicIterParams p) {
+  __shared__ float red[kWarps][NSUM][33];
+  __shared__ double wsum[kWarps][NSUM + 1];
+  __shared__ float wvmin[kWarps], wvmax[kWarps];
+  __shared__ float s_pair_mm[2];
+  __shared__ int s_flag;
+
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int b = blockIdx.y;
+  const int H = p.H, W = p.W, C = p.C;
+  const size_t plane = (size_t)H * W;
+
+  const int wt = blockIdx.x * kWarps + warp;
+  const bool warp_on = wt < p.nseg * p.nrt;
+  const int seg = warp_on ? wt % p.nseg : 0;
+  const int rt = warp_on ? wt / p.nseg : 0;
+  const int x = seg * kCols - 1 + lane;
+  const int xc = min(max(x, 0), W - 1);
+  const bool col_out = warp_on && lane >= 1 && lane <= kCols && x < W;
+  const int y0 = rt * p.TR;
+  const int y1 = warp_on ? min(y0 + p.TR, H) : y0;
+
+  const float fx = __ldg(p.K + 4 * b), fy = __ldg(p.K + 4 * b + 1);
+  const float cx = __ldg(p.K + 4 * b + 2), cy = __ldg(p.K + 4 * b + 3);
+  const float px = xdiv(xsub((float)xc, cx), fx);
+
+  float acc[27];
+#pragma unroll
+  for (int i = 0; i < 27; ++i) acc[i] = 0.f;
+  float cmn[6], cmx[6];
+#pragma unroll
+  for (int i = 0; i < 6; ++i) cmn[i] = cmx[i] = 0.f;
+  float vmin = CUDART_INF_F, vmax = -CUDART_INF_F;
+
+  const float* d0p = p.d0 + (size_t)b * plane;
+  const float* d1p = p.d1 + (size_t)b * plane;
+  const uint8_t* m0p = p.m0 ? p.m0 + (size_t)b * plane : nullptr;
+  const uint8_t* m1p = p.m1 ? p.m1 + (size_t)b * plane : nullptr;
+  float s0lo = 0.f, s0hi = 0.f;
+  Pose pose;
+
+  // let the next iteration's launch become resident as soon as every CTA of this one has started
+  cudaTriggerProgrammaticLaunchCompletion();
+
+  for (int c0 = 0; c0 < C; c0 += CH) {
+    const float* X0 = p.x0 + ((size_t)b * C + c0) * plane;
+    const float* S0 = p.s0 + ((size_t)b * C + c0) * plane;
+    const float* X1 = p.x1 + ((size_t)b * C + c0) * plane;
+    const float* S1 = p.s1 + ((size_t)b * C + c0) * plane;
+
+    // 3-row sliding windows of the keyframe maps (own column): top / mid / (bot loaded per row)
+    float ft[CH], fm[CH], st[CH], sm[CH];
+    {
+      const int ot = max(y0 - 1, 0) * W + xc, om = min(y0, H - 1) * W + xc;
+#pragma unroll
+      for (int c = 0; c < CH; ++c) {
+        ft[c] = __ldg(X0 + c * plane + ot);
+        fm[c] = __ldg(X0 + c * plane + om);
+        st[c] = __ldg(S0 + c * plane + ot);
+        sm[c] = __ldg(S0 + c * plane + om);
+      }
+    }
+    if (c0 == 0) {
+      // everything above is independent of the previous launch: with programmatic dependent launch
+      // it overlaps that launch's tail.  The pose, sigma0's extremes and the scratch buffers are not.
+      cudaGridDependencySynchronize();
+      pose = load_pose(p.pose + (size_t)b * 12);
+      if (TRU) {
+        s0lo = ord2f(__ldcg(p.s0mm));
+        s0hi = ord2f(__ldcg(p.s0mm + 1));
+      }
+    }
+
+    for (int y = y0; y < y1; ++y) {
+      const int ob = min(y + 1, H - 1) * W + xc;
+      float fb[CH], sb[CH];
+#pragma unroll
+      for (int c = 0; c < CH; ++c) {
+        fb[c] = __ldg(X0 + c * plane + ob);
+        sb[c] = __ldg(S0 + c * plane + ob);
+      }
+      const int o = y * W + xc;
+      const float d0 = __ldg(d0p + o);
+      const float py = xdiv(xsub((float)y, cy), fy);
+
+      float u, v, inv_z;
+      warp_pixel(pose, px, py, d0, fx, fy, cx, cy, u, v, inv_z);
+      const Tap tap = make_tap(u, v, H, W);
+      const float d1w = sample_exact(d1p, tap);
+      bool occ = occluded(u, v, inv_z, d1w, H, W);
+      if (m0p) occ = occ || (__ldg(m0p + o) == 0);
+      if (m1p) occ = occ || !(sample_mask(m1p, tap) > 0.f);
+      float s0c0 = sm[0];
+      if (TRU) {
+        if (c0 != 0) s0c0 = __ldg(p.s0 + (size_t)b * C * plane + o);
+        occ = occ || (s0c0 == s0lo) || (s0c0 == s0hi);
+      }
+
+      float saa = 0.f, sab = 0.f, sbb = 0.f, sar = 0.f, sbr = 0.f, sca = 0.f, scb = 0.f;
+      float pmin = CUDART_INF_F, pmax = -CUDART_INF_F, sr0 = 0.f;
+#pragma unroll
+      for (int c = 0; c < CH; ++c) {
+        // unit Sobel gradient of x0 and sigma0 (algorithms.py:1844-1865), separable form:
+        // Sx = vs(x+1) - vs(x-1), Sy = vd(x-1) + 2 vd(x) + vd(x+1), vs = t+2m+b, vd = b-t
+        const float fvs = ft[c] + 2.f * fm[c] + fb[c], fvd = fb[c] - ft[c];
+        const float svs = st[c] + 2.f * sm[c] + sb[c], svd = sb[c] - st[c];
+        const float fSx = __shfl_down_sync(0xffffffffu, fvs, 1) - __shfl_up_sync(0xffffffffu, fvs, 1);
+        const float fSy = __shfl_up_sync(0xffffffffu, fvd, 1) + 2.f * fvd + __shfl_down_sync(0xffffffffu, fvd, 1);
+        const float sSx = __shfl_down_sync(0xffffffffu, svs, 1) - __shfl_up_sync(0xffffffffu, svs, 1);
+        const float sSy = __shfl_up_sync(0xffffffffu, svd, 1) + 2.f * svd + __shfl_down_sync(0xffffffffu, svd, 1);
+        const float fin = rsqrtf(fmaf(fSx, fSx, fmaf(fSy, fSy, 1e-8f)));
+        const float sin_ = rsqrtf(fmaf(sSx, sSx, fmaf(sSy, sSy, 1e-8f)));
+        const float gfx = fSx * fin, gfy = fSy * fin, gsx = sSx * sin_, gsy = sSy * sin_;
+
+        const float* x1c = X1 + c * plane;
+        const float* s1c = S1 + c * plane;
+        const float fr = blend_fast(__ldg(x1c + tap.o_nw), __ldg(x1c + tap.o_ne), __ldg(x1c + tap.o_sw),
+                                    __ldg(x1c + tap.o_se), tap);
+        float sr;
+        if (TRU) sr = sample_exact(s1c, tap);   // compared for equality against its batch extremes
+        else sr = blend_fast(__ldg(s1c + tap.o_nw), __ldg(s1c + tap.o_ne), __ldg(s1c + tap.o_sw),
+                             __ldg(s1c + tap.o_se), tap);
+
+        // residual, its uncertainty and the 2-vector d(wres)/d(u,v) (algorithms.py:1969-1972, :872)
+        const float res = fr - fm[c];
+        const float s0v = sm[c];
+        const float rs = rsqrtf(fmaf(sr, sr, s0v * s0v));   // 1 / sigma
+        const float wres = res * rs;
+        const float q = res * s0v * rs * rs * rs;
+        const float a = fmaf(gfx, rs, q * gsx);
+        const float bq = fmaf(gfy, rs, q * gsy);
+        const float wm = occ ? 1e-6f : wres;
+        saa = fmaf(a, a, saa);
+        sab = fmaf(a, bq, sab);
+        sbb = fmaf(bq, bq, sbb);
+        sar = fmaf(a, wm, sar);
+        sbr = fmaf(bq, wm, sbr);
+        if (TRU) {
+          const float dw = wres - 1e-6f;
+          sca = fmaf(a, dw, sca);
+          scb = fmaf(bq, dw, scb);
+          pmin = fminf(pmin, sr);
+          pmax = fmaxf(pmax, sr);
+          if (c == 0) sr0 = sr;
+        }
+      }
+      if (TRU && c0 != 0) sr0 = sample_exact(p.s1 + (size_t)b * C * plane, tap);
+
+      if (col_out) {
+        float ju[6], jv[6];
+        warp_rows(px, py, d0, fx, fy, ju, jv);
+        accumulate_system(acc, ju, jv, saa, sab, sbb, sar, sbr);
+        if (TRU) {
+          if (pmin < vmin) {
+            vmin = pmin;
+#pragma unroll
+            for (int i = 0; i < 6; ++i) cmn[i] = 0.f;
+          }
+          if (pmax > vmax) {
+            vmax = pmax;
+#pragma unroll
+            for (int i = 0; i < 6; ++i) cmx[i] = 0.f;
+          }
+          if (!occ) {
+            const bool tmin = (sr0 == vmin), tmax = (sr0 == vmax);
+#pragma unroll
+            for (int i = 0; i < 6; ++i) {
+              float cc = 0.f;
+              if (i != 4) cc = fmaf(sca, ju[i], cc);
+              if (i != 3) cc = fmaf(scb, jv[i], cc);
+              if (tmin) cmn[i] += cc;
+              if (tmax) cmx[i] += cc;
+            }
+          }
+        }
+        if (p.occ_out && c0 == 0) {
+          p.occ_out[(size_t)b * plane + (size_t)y * W + x] = occ ? 1 : 0;
+          if (TRU) p.sr0_dbg[(size_t)b * plane + (size_t)y * W + x] = sr0;
+        }
+      }
+#pragma unroll
+      for (int c = 0; c < CH; ++c) {
+        ft[c] = fm[c];
+        fm[c] = fb[c];
+        st[c] = sm[c];
+        sm[c] = sb[c];
+      }
+    }
+  }
+  // ---------------------------------------------------------------- CTA reduction
+  if (TRU) {
+    const float wmn = warp_min(vmin), wmx = warp_max(vmax);
+    if (vmin != wmn) {
+#pragma unroll
+      for (int i = 0; i < 6; ++i) cmn[i] = 0.f;
+    }
+    if (vmax != wmx) {
+#pragma unroll
+      for (int i = 0; i < 6; ++i) cmx[i] = 0.f;
+    }
+    if (lane == 0) {
+      wvmin[warp] = wmn;
+      wvmax[warp] = wmx;
+    }
+  }
+#pragma unroll
+  for (int e = 0; e < 27; ++e) red[warp][e][lane] = acc[e];
+  if (TRU) {
+#pragma unroll
+    for (int i = 0; i < 6; ++i) {
+      red[warp][27 + i][lane] = cmn[i];
+      red[warp][33 + i][lane] = cmx[i];
+    }
+  }
+  __syncwarp();
+  constexpr int NE = TRU ? NSUM : 27;
+  for (int e = lane; e < NE; e += 32) {
+    double s = 0.0;
+#pragma unroll 8
+    for (int j = 0; j < 32; ++j) s += (double)red[warp][e][j];
+    wsum[warp][e] = s;
+  }
+  __syncthreads();
+
+  float* part = p.partials + ((size_t)b * p.ctas_per_pair + blockIdx.x) * PS;
+  float cta_min = CUDART_INF_F, cta_max = -CUDART_INF_F;
+  if (TRU) {
+#pragma unroll
+    for (int w = 0; w < kWarps; ++w) {
+      cta_min = fminf(cta_min, wvmin[w]);
+      cta_max = fmaxf(cta_max, wvmax[w]);
+    }
+  }
+  if (threadIdx.x < NE) {
+    const int e = threadIdx.x;
+    double s = 0.0;
+#pragma unroll
+    for (int w = 0; w < kWarps; ++w) {
+      bool take = true;
+      if (TRU && e >= 27 && e < 33) take = (wvmin[w] == cta_min);
+      if (TRU && e >= 33) take = (wvmax[w] == cta_max);
+      if (take) s += wsum[w][e];
+    }
+    part[e < 27 ? e : e + 2] = (float)s;   // corr entries live at E_CMIN.. / E_CMAX..
+  }
+  if (TRU && threadIdx.x == 0) {
+    part[E_VMIN] = cta_min;
+    part[E_VMAX] = cta_max;
+  }
+
+  // ---------------------------------------------------------------- last CTA of the pair reduces it
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) s_flag = (atomicAdd(p.counters + b, 1) == p.ctas_per_pair - 1);
+  __syncthreads();
+  if (!s_flag) return;
+  __threadfence();
+
+  const float* pp = p.partials + (size_t)b * p.ctas_per_pair * PS;
+  const int n = p.ctas_per_pair;
+  float pair_min = CUDART_INF_F, pair_max = -CUDART_INF_F;
+  if (TRU) {
+    float a = CUDART_INF_F, c = -CUDART_INF_F;
+    for (int i = threadIdx.x; i < n; i += kThreads) {
+      a = fminf(a, __ldcg(pp + (size_t)i * PS + E_VMIN));
+      c = fmaxf(c, __ldcg(pp + (size_t)i * PS + E_VMAX));
+    }
+    a = warp_min(a);
+    c = warp_max(c);
+    __syncthreads();   // wvmin/wvmax reuse
+    if (lane == 0) {
+      wvmin[warp] = a;
+      wvmax[warp] = c;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int w = 0; w < kWarps; ++w) {
+      pair_min = fminf(pair_min, wvmin[w]);
+      pair_max = fmaxf(pair_max, wvmax[w]);
+    }
+  }
+  double* rec = p.pairrec + (size_t)b * PS;
+  if (threadIdx.x < NE) {
+    const int e = threadIdx.x;
+    const int slot = e < 27 ? e : e + 2;
+    double s = 0.0;
+    for (int i = 0; i < n; ++i) {
+      const float* q = pp + (size_t)i * PS;
+      bool take = true;
+      if (TRU && e >= 27 && e < 33) take = (__ldcg(q + E_VMIN) == pair_min);
+      if (TRU && e >= 33) take = (__ldcg(q + E_VMAX) == pair_max);
+      if (take) s += (double)__ldcg(q + slot);
+    }
+    rec[slot] = s;
+  }
+  if (TRU && threadIdx.x == 0) {
+    rec[E_VMIN] = (double)pair_min;
+    rec[E_VMAX] = (double)pair_max;
+  }
+  if (threadIdx.x == 0) p.counters[b] = 0;   // ready for the next launch
+  __threadfence();
+  __syncthreads();
+
+  if (!TRU) {
+    if (threadIdx.x == 0) finalize_pair<false>(p, b, 0.f, 0.f);
+    return;
+  }
+
+  // ---------------------------------------------------------------- last CTA of the grid: batch extremes + all solves
+  if (threadIdx.x == 0) s_flag = (atomicAdd(p.counters + p.B, 1) == p.B - 1);
+  __syncthreads();
+  if (!s_flag) return;
+  __threadfence();
+  {
+    float a = CUDART_INF_F, c = -CUDART_INF_F;
+    for (int i = threadIdx.x; i < p.B; i += kThreads) {
+      a = fminf(a, (float)__ldcg(p.pairrec + (size_t)i * PS + E_VMIN));
+      c = fmaxf(c, (float)__ldcg(p.pairrec + (size_t)i * PS + E_VMAX));
+    }
+    a = warp_min(a);
+    c = warp_max(c);
+    if (lane == 0) {
+      wvmin[warp] = a;
+      wvmax[warp] = c;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      float g0 = CUDART_INF_F, g1 = -CUDART_INF_F;
+#pragma unroll
+      for (int w = 0; w < kWarps; ++w) {
+        g0 = fminf(g0, wvmin[w]);
+        g1 = fmaxf(g1, wvmax[w]);
+      }
+      s_pair_mm[0] = g0;
+      s_pair_mm[1] = g1;
+      p.gmm[0] = g0;
+      p.gmm[1] = g1;
+      p.counters[p.B] = 0;
+    }
+    __syncthreads();
+  }
+  for (int i = threadIdx.x; i < p.B; i += kThreads) finalize_pair<true>(p, i, s_pair_mm[0], s_pair_mm[1]);
+}
+
+// --------------------------------------------------------------------------- small helper kernels
+__global__ void init_kernel(const float* __restrict__ pose_in, float* __restrict__ pose0, int n_pose,
+                            int* __restrict__ counters, int n_counters, uint32_t* __restrict__ mm, int n_levels) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n_pose) pose0[i] = pose_in[i];
+  if (i < n_counters) counters[i] = 0;
+  if (i < n_levels) {
+    mm[2 * i] = 0xffffffffu;   // running min
+    mm[2 * i + 1] = 0u;        // running max
+  }
+}
+
+// min / max of a whole tensor (torch's sigma0.min(), sigma0.max(): algorithms.py:1976-1977)
+__global__ void __launch_bounds__(256) minmax_kernel(const float* __restrict__ v, size_t n, uint32_t* __restrict__ mm) {
+  float lo = CUDART_INF_F, hi = -CUDART_INF_F;
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  const size_t n4 = ((reinterpret_cast<uintptr_t>(v) & 15) == 0) ? n / 4 : 0;
+  const float4* v4 = reinterpret_cast<const float4*>(v);
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
+    const float4 q = __ldg(v4 + i);
+    lo = fminf(fminf(lo, q.x), fminf(q.y, fminf(q.z, q.w)));
+    hi = fmaxf(fmaxf(hi, q.x), fmaxf(q.y, fmaxf(q.z, q.w)));
+  }
+  for (size_t i = n4 * 4 + (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+    const float q = __ldg(v + i);
+    lo = fminf(lo, q);
+    hi = fmaxf(hi, q);
+  }
+  lo = warp_min(lo);
+  hi = warp_max(hi);
+  if ((threadIdx.x & 31) == 0) {
+    atomicMin(mm, f2ord(lo));
+    atomicMax(mm + 1, f2ord(hi));
+  }
+}
+
+// debug only: OR the batch-global sigma test into the per-iteration mask
+__global__ void occ_fixup_kernel(uint8_t* __restrict__ occ, const float* __restrict__ sr0, const float* __restrict__ gmm,
+                                 size_t n) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n && (sr0[i] == gmm[0] || sr0[i] == gmm[1])) occ[i] = 1;
+}
+
+// --------------------------------------------------------------------------- host side
+struct Plan {
+  int nseg[DPFT_MAX_LEVELS], nrt[DPFT_MAX_LEVELS], TR[DPFT_MAX_LEVELS], ctas[DPFT_MAX_LEVELS];
+  int max_ctas;
+  size_t max_plane;
+  size_t off_partials, off_pairrec, off_counters, off_mm, off_gmm, off_sr0, total;
+};
+
+static int pick_tile_rows(int H) {
+  const int tiles = (H + 7) / 8;          // about 8 rows per tile
+  return (H + tiles - 1) / tiles;
+}
+
+static Plan make_plan(const dpft_level_t* lv, int n_levels, int B, uint32_t flags, bool any_occ) {
+  Plan pl{};
+  pl.max_ctas = 1;
+  pl.max_plane = 0;
+  for (int l = 0; l < n_levels; ++l) {
+    pl.nseg[l] = (lv[l].W + kCols - 1) / kCols;
+    pl.TR[l] = pick_tile_rows(lv[l].H);
+    pl.nrt[l] = (lv[l].H + pl.TR[l] - 1) / pl.TR[l];
+    pl.ctas[l] = (pl.nseg[l] * pl.nrt[l] + kWarps - 1) / kWarps;
+    if (pl.ctas[l] > pl.max_ctas) pl.max_ctas = pl.ctas[l];
+    const size_t plane = (size_t)lv[l].H * lv[l].W;
+    if (plane > pl.max_plane) pl.max_plane = plane;
+  }
+  size_t off = 0;
+  auto take = [&](size_t bytes) {
+    const size_t o = off;
+    off += (bytes + 255) & ~(size_t)255;
+    return o;
+  };
+  pl.off_partials = take((size_t)B * pl.max_ctas * PS * sizeof(float));
+  pl.off_pairrec = take((size_t)B * PS * sizeof(double));
+  pl.off_counters = take((size_t)(B + 1) * sizeof(int));
+  pl.off_mm = take((size_t)2 * DPFT_MAX_LEVELS * sizeof(uint32_t));
+  pl.off_gmm = take(2 * sizeof(float));
+  pl.off_sr0 = take(((flags & DPFT_REMOVE_TRU_SIGMA) && any_occ) ? (size_t)B * pl.max_plane * sizeof(float) : 0);
+  pl.total = off;
+  return pl;
+}
+
+static int check_args(const dpft_level_t* lv, int n_levels, int B, int C, int iters, uint32_t flags) {
+  if (!lv || n_levels < 1 || n_levels > DPFT_MAX_LEVELS) return set_error(DPFT_EINVAL, "n_levels must be 1..%d", DPFT_MAX_LEVELS);
+  if (B < 1 || B > 65535) return set_error(DPFT_EINVAL, "B must be 1..65535 (got %d)", B);
+  if (C < 1 || iters < 0) return set_error(DPFT_EINVAL, "C must be >= 1 and iters >= 0");
+  if (flags & DPFT_COMBINE_ICP) return set_error(DPFT_EINVAL, "DPFT_COMBINE_ICP is not available in this entry point yet");
+  for (int l = 0; l < n_levels; ++l) {
+    const dpft_level_t& L = lv[l];
+    if (L.H < 2 || L.W < 2) return set_error(DPFT_EINVAL, "level %d: H and W must be >= 2", l);
+    if (!L.x0 || !L.x1 || !L.sigma0 || !L.sigma1 || !L.invd0 || !L.invd1 || !L.K)
+      return set_error(DPFT_EINVAL, "level %d: x0, x1, sigma0, sigma1, invd0, invd1 and K are required", l);
+  }
+  return 0;
+}
+
+template <int CH>
+static cudaError_t launch_iter(const UicIterParams& prm, dim3 grid, bool tru, bool pdl, cudaStream_t stream) {
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = grid;
+  cfg.blockDim = dim3(kThreads);
+  cfg.dynamicSmemBytes = 0;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl ? 1 : 0;
+  if (tru) return cudaLaunchKernelEx(&cfg, uic_iter_kernel<CH, true>, prm);
+  return cudaLaunchKernelEx(&cfg, uic_iter_kernel<CH, false>, prm);
+}
+
+}  // namespace dpft
+
+using namespace dpft;
+
+extern "C" size_t dpft_uic_workspace_bytes(const dpft_level_t* levels, int n_levels, int B, int C, int iters,
+                                           uint32_t flags) {
+  if (check_args(levels, n_levels, B, C, iters, flags)) return 0;
+  bool any_occ = false;
+  for (int l = 0; l < n_levels; ++l) any_occ = any_occ || levels[l].occ_out;
+  return make_plan(levels, n_levels, B, flags, any_occ).total;
+}
+
+static int run_uic(const dpft_level_t* levels, int n_levels, int B, int C, int iters, uint32_t flags,
+                   float w_icp, const float* pose_in, float* pose_hist, float* sys_hist,
+                   int32_t* status, void* workspace, size_t workspace_bytes, void* stream_, cudaEvent_t* ev) {
+  (void)w_icp;
+  if (int e = check_args(levels, n_levels, B, C, iters, flags)) return e;
+  if (!pose_in || !pose_hist || !status || (iters > 0 && !sys_hist) || !workspace)
+    return set_error(DPFT_EINVAL, "pose_in, pose_hist, sys_hist, status and workspace are required");
+  bool any_occ = false;
+  for (int l = 0; l < n_levels; ++l) any_occ = any_occ || levels[l].occ_out;
+  const Plan pl = make_plan(levels, n_levels, B, flags, any_occ);
+  if (workspace_bytes < pl.total) return set_error(DPFT_ENOSPACE, "workspace has %zu bytes, %zu needed", workspace_bytes, pl.total);
+  cudaStream_t stream = (cudaStream_t)stream_;
+  char* ws = (char*)workspace;
+  float* partials = (float*)(ws + pl.off_partials);
+  double* pairrec = (double*)(ws + pl.off_pairrec);
+  int* counters = (int*)(ws + pl.off_counters);
+  uint32_t* mm = (uint32_t*)(ws + pl.off_mm);
+  float* gmm = (float*)(ws + pl.off_gmm);
+  float* sr0 = (float*)(ws + pl.off_sr0);
+  const bool tru = flags & DPFT_REMOVE_TRU_SIGMA;
+  const bool pdl = !(flags & DPFT_NO_PDL);
+
+  {
+    const int n = std::max(B * 12, B + 1);
+    init_kernel<<<(n + 255) / 256, 256, 0, stream>>>(pose_in, pose_hist, B * 12, counters, B + 1, mm, n_levels);
+  }
+  if (tru) {
+    for (int l = 0; l < n_levels; ++l) {
+      const size_t n = (size_t)B * C * levels[l].H * levels[l].W;
+      const int blocks = (int)std::min<size_t>((n / 4 + 255) / 256 + 1, 148 * 8);
+      minmax_kernel<<<blocks, 256, 0, stream>>>(levels[l].sigma0, n, mm + 2 * l);
+    }
+  }
+  const int CH = (C % 8 == 0) ? 8 : (C % 4 == 0) ? 4 : (C % 2 == 0) ? 2 : 1;
+  int k = 0;
+  for (int l = 0; l < n_levels; ++l) {
+    const dpft_level_t& L = levels[l];
+    const size_t plane = (size_t)L.H * L.W;
+    for (int it = 0; it < iters; ++it, ++k) {
+      UicIterParams prm{};
+      prm.x0 = L.x0; prm.x1 = L.x1; prm.s0 = L.sigma0; prm.s1 = L.sigma1;
+      prm.d0 = L.invd0; prm.d1 = L.invd1; prm.K = L.K;
+      prm.m0 = L.obj_mask0; prm.m1 = L.obj_mask1;
+      prm.occ_out = L.occ_out ? L.occ_out + (size_t)it * B * plane : nullptr;
+      prm.sr0_dbg = sr0;
+      prm.H = L.H; prm.W = L.W; prm.B = B; prm.C = C;
+      prm.nseg = pl.nseg[l]; prm.nrt = pl.nrt[l]; prm.TR = pl.TR[l]; prm.ctas_per_pair = pl.ctas[l];
+      prm.pose = pose_hist + (size_t)k * B * 12;
+      prm.pose_next = pose_hist + (size_t)(k + 1) * B * 12;
+      prm.sys_out = sys_hist + (size_t)k * B * 27;
+      prm.partials = partials; prm.pairrec = pairrec; prm.counters = counters;
+      prm.s0mm = mm + 2 * l; prm.gmm = gmm; prm.status = status; prm.flags = flags;
+      const dim3 grid(pl.ctas[l], B);
+      // the debug mask pass reads what this launch wrote, so keep plain stream order around it
+      const bool use_pdl = pdl && !any_occ && !ev;
+      cudaError_t err;
+      if (ev) cudaEventRecord(ev[k], stream);
+      switch (CH) {
+        case 8: err = launch_iter<8>(prm, grid, tru, use_pdl, stream); break;
+        case 4: err = launch_iter<4>(prm, grid, tru, use_pdl, stream); break;
+        case 2: err = launch_iter<2>(prm, grid, tru, use_pdl, stream); break;
+        default: err = launch_iter<1>(prm, grid, tru, use_pdl, stream); break;
+      }
+      if (err != cudaSuccess) return set_error((int)err, "uic_iter_kernel launch: %s", cudaGetErrorString(err));
+      if (tru && prm.occ_out) {
+        const size_t n = (size_t)B * plane;
+        occ_fixup_kernel<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(prm.occ_out, sr0, gmm, n);
+      }
+    }
+  }
+  if (ev) cudaEventRecord(ev[k], stream);
+  const cudaError_t err = cudaGetLastError();
+  if (err != cudaSuccess) return set_error((int)err, "launch: %s", cudaGetErrorString(err));
+  return 0;
+}
+
+extern "C" int dpft_uic_forward(const dpft_level_t* levels, int n_levels, int B, int C, int iters, uint32_t flags,
+                                float w_icp, const float* pose_in, float* pose_hist, float* sys_hist,
+                                int32_t* status, void* workspace, size_t workspace_bytes, void* stream) {
+  return run_uic(levels, n_levels, B, C, iters, flags, w_icp, pose_in, pose_hist, sys_hist, status, workspace,
+                 workspace_bytes, stream, nullptr);
+}
+
+extern "C" int dpft_uic_forward_timed(const dpft_level_t* levels, int n_levels, int B, int C, int iters,
+                                      uint32_t flags, float w_icp, const float* pose_in, float* pose_hist,
+                                      float* sys_hist, int32_t* status, void* workspace, size_t workspace_bytes,
+                                      void* stream, float* launch_ms) {
+  if (!launch_ms || n_levels < 1 || n_levels > DPFT_MAX_LEVELS || iters < 1 || iters > 64)
+    return set_error(DPFT_EINVAL, "launch_ms is required and iters must be 1..64");
+  const int n = n_levels * iters;
+  cudaEvent_t ev[DPFT_MAX_LEVELS * 64 + 1];
+  for (int i = 0; i <= n; ++i) cudaEventCreate(&ev[i]);
+  int rc = run_uic(levels, n_levels, B, C, iters, flags, w_icp, pose_in, pose_hist, sys_hist, status, workspace,
+                   workspace_bytes, stream, ev);
+  if (rc == 0) {
+    const cudaError_t err = cudaStreamSynchronize((cudaStream_t)stream);
+    if (err != cudaSuccess) rc = set_error((int)err, "sync: %s", cudaGetErrorString(err));
+  }
+  for (int i = 0; i < n && rc == 0; ++i) cudaEventElapsedTime(&launch_ms[i], ev[i], ev[i + 1]);
+  for (int i = 0; i <= n; ++i) cudaEventDestroy(ev[i]);
+  return rc;
+}

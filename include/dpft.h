@@ -1,0 +1,109 @@
+/*
+ * dpft.h -- C ABI of the B200-native trust-region inverse-compositional solver.
+ *
+ * This is the drop-in boundary for ONE path of smartroboticslab/deep_prob_feature_track:
+ * the per-pyramid-level Gauss-Newton solve that LeastSquareTracking.forward runs.  The
+ * reference has no FFI of its own (it is pure PyTorch); the interface it exposes for this
+ * path is the nn.Module surface
+ *
+ *   TrustRegionInverseWUncertainty.forward / .forward_residuals   code/models/algorithms.py:611, :725
+ *   TrustRegionBase.forward / .forward_residuals                  code/models/algorithms.py:45,  :123
+ *   DirectSolverNet.forward                                       code/models/algorithms.py:1604
+ *   LeastSquareTracking.forward (coarse-to-fine chain)            code/models/LeastSquareTracking.py:345-446
+ *
+ * and the Python modules in deep_prob_feature_track_b200/algorithms.py mirror it one to one
+ * and call the entry points below through ctypes (INTEGRATION.md shows the binding).
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer to contiguous fp32 (or uint8 for masks) unless noted;
+ *   - feature maps are NCHW: (B,C,H,W); depth / inverse-depth / masks are (B,1,H,W); K is (B,4)
+ *     = [fx, fy, cx, cy] ALREADY scaled to the level (the reference passes K / 2^level);
+ *   - poses are R (B,3,3) row-major and t (B,3); "pose rows" pack them as 12 floats R|t;
+ *   - `stream` is a cudaStream_t passed as void*; nothing here allocates or synchronises;
+ *   - every function returns 0 on success or a negative DPFT_E* / positive cudaError_t code.
+ *     dpft_last_error() gives a message for the calling thread.
+ *   - levels are listed in the order they are solved: COARSE FIRST.
+ */
+#ifndef DPFT_H_
+#define DPFT_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DPFT_ABI_VERSION 1
+#define DPFT_MAX_LEVELS 8
+
+/* error codes */
+#define DPFT_EINVAL   (-1)  /* bad argument (shape, NULL pointer, unsupported flag mix) */
+#define DPFT_ENOSPACE (-2)  /* workspace too small */
+
+/* flags */
+#define DPFT_REMOVE_TRU_SIGMA 0x01u /* alg:1974-1979  mask pixels whose sigma sits on the batch-global min/max */
+#define DPFT_COMBINE_ICP      0x02u /* alg:668-689    add the point-to-plane term (needs depth0/depth1)        */
+#define DPFT_NO_PDL           0x04u /* launch iterations without programmatic dependent launch (debug)        */
+
+/* status bits written to *status (device int32, OR-ed; zero it before the call) */
+#define DPFT_ST_NONFINITE 0x01 /* a weighted residual / normal-equation entry was NaN or Inf (alg:886,1988) */
+#define DPFT_ST_SINGULAR  0x02 /* a damped 6x6 system was not positive definite                              */
+
+/* One pyramid level of one batch of frame pairs. */
+typedef struct dpft_level {
+  const float *x0, *x1;         /* (B,C,H,W) keyframe / live feature maps                         */
+  const float *sigma0, *sigma1; /* (B,C,H,W) their uncertainty maps (U_IC only, else NULL)        */
+  const float *invd0, *invd1;   /* (B,1,H,W) inverse depth                                        */
+  const float *depth0, *depth1; /* (B,1,H,W) metric depth, only with DPFT_COMBINE_ICP, else NULL  */
+  const float *K;               /* (B,4) intrinsics at this level                                 */
+  const uint8_t *obj_mask0;     /* (B,1,H,W) optional object mask of the keyframe (1 = object)    */
+  const uint8_t *obj_mask1;     /* (B,1,H,W) optional object mask of the live frame               */
+  uint8_t *occ_out;             /* optional (iters,B,H,W): the validity mask of every iteration
+                                   (1 = excluded), exactly what compute_inverse_residuals returns */
+  int32_t H, W;
+} dpft_level_t;
+
+/* ABI version of the loaded library (== DPFT_ABI_VERSION). */
+int dpft_abi_version(void);
+
+/* Message of the last error on this thread ("" if none). */
+const char *dpft_last_error(void);
+
+/* Bytes of device scratch the calls below need for this problem (same arguments). */
+size_t dpft_uic_workspace_bytes(const dpft_level_t *levels, int n_levels, int B, int C, int iters,
+                                uint32_t flags);
+
+/*
+ * U_IC coarse-to-fine solve: for every level (coarse first) run `iters` Gauss-Newton iterations of
+ * TrustRegionInverseWUncertainty.forward (alg:611-723): SE(3) warp in inverse depth, bilinear lookup
+ * of x1 / sigma1 / invd1, validity mask, uncertainty-normalised residual, C x 6 Jacobian, J^T J and
+ * J^T r reduced over the pair, H = J^T J + 1e-6 tr I, xi = H^-1 b, inverse-compositional update.
+ * n_levels = 1 is exactly one module call; n_levels = 4 is the chain LeastSquareTracking.forward runs.
+ *
+ *   pose_in    (B,12)                       starting pose rows
+ *   pose_hist  (n_levels*iters + 1, B, 12)  OUT: pose before iteration k at row k; the result is the last row
+ *   sys_hist   (n_levels*iters, B, 27)      OUT: per iteration the 21 upper-triangular entries of J^T W J
+ *                                           (row-major i<=j) followed by the 6 entries of J^T W r
+ *   w_icp      scalar weight of the ICP term (the reference's ScaleNet('None') constant, 0.01)
+ *   status     device int32, OR-ed with DPFT_ST_* bits
+ */
+int dpft_uic_forward(const dpft_level_t *levels, int n_levels, int B, int C, int iters, uint32_t flags,
+                     float w_icp, const float *pose_in, float *pose_hist, float *sys_hist,
+                     int32_t *status, void *workspace, size_t workspace_bytes, void *stream);
+
+/*
+ * Measurement aid for bench.py: same work as dpft_uic_forward, but every Gauss-Newton launch is bracketed
+ * with CUDA events on `stream`, the stream is waited for, and the device time of launch k (milliseconds) is
+ * written to the HOST array launch_ms[n_levels*iters].  Events between launches switch their overlap off, so
+ * these are clean per-kernel durations, not a way to run the solver.
+ */
+int dpft_uic_forward_timed(const dpft_level_t *levels, int n_levels, int B, int C, int iters, uint32_t flags,
+                           float w_icp, const float *pose_in, float *pose_hist, float *sys_hist,
+                           int32_t *status, void *workspace, size_t workspace_bytes, void *stream,
+                           float *launch_ms);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DPFT_H_ */
