@@ -65,7 +65,8 @@ def build(force: bool = False, verbose: bool = False) -> str:
     """Compile csrc/*.cu into libdpft.so for sm_100a (cross-compiles without a GPU)."""
     if not force and not _stale():
         return LIB_PATH
-    cmd = [_nvcc(), *NVCC_FLAGS, "-I", os.path.join(REPO_DIR, "include"), "-I", CSRC,
+    extra = os.environ.get("DPFT_NVCC_EXTRA", "").split()   # e.g. -DDPFT_MIN_CTAS=4 for tuning sweeps
+    cmd = [_nvcc(), *NVCC_FLAGS, *extra, "-I", os.path.join(REPO_DIR, "include"), "-I", CSRC,
            "-o", LIB_PATH + ".tmp", *[os.path.join(CSRC, s) for s in SOURCES]]
     if verbose:
         cmd.insert(1, "-Xptxas=-v")

@@ -54,9 +54,14 @@ __device__ __forceinline__ void warp_pixel(const Pose& p, float x, float y, floa
 
 // Bilinear footprint with border padding: warp_features (geometry.py:353-365) followed by torch's
 // grid_sampler_2d(align_corners=True, padding_mode='border') un-normalisation, clip and weights.
+//
+// The four texels are addressed as o, o+1, o+W, o+W+1 with o = yi*W + xi, xi <= W-2, yi <= H-2.  torch
+// clamps the east/south index at the border instead (where its weight is exactly 0); here the footprint
+// is shifted one texel inwards and the two weights swap places, which gives the same sum bit for bit
+// (x*w + y*0 == y*0 + x*w up to the sign of a zero) and keeps every load at a fixed offset from one base.
 struct Tap {
-  int o_nw, o_ne, o_sw, o_se;   // element offsets inside one (H,W) plane
-  float w_nw, w_ne, w_sw, w_se;
+  int o;
+  float wa, wb, wc, wd;   // weights of texels o, o+1, o+W, o+W+1
 };
 
 __device__ __forceinline__ float unnormalise(float coord, float half_span, float span) {
@@ -69,35 +74,36 @@ __device__ __forceinline__ Tap make_tap(float u, float v, int H, int W) {
   const float ix = unnormalise(u, 0.5f * (float)(W - 1), (float)(W - 1));
   const float iy = unnormalise(v, 0.5f * (float)(H - 1), (float)(H - 1));
   const float xw = floorf(ix), yn = floorf(iy);
-  const float tx1 = xsub(ix, xw), ty1 = xsub(iy, yn);
-  const float tx0 = xsub(xadd(xw, 1.f), ix), ty0 = xsub(xadd(yn, 1.f), iy);
+  float txr = xsub(ix, xw), tys = xsub(iy, yn);                       // east / south weights
+  float txl = xsub(xadd(xw, 1.f), ix), tyn = xsub(xadd(yn, 1.f), iy); // west / north weights
+  int xi = (int)xw, yi = (int)yn;
+  if (xi > W - 2) { xi = W - 2; const float t = txl; txl = txr; txr = t; }
+  if (yi > H - 2) { yi = H - 2; const float t = tyn; tyn = tys; tys = t; }
+  xi = max(xi, 0);
+  yi = max(yi, 0);
   Tap t;
-  t.w_nw = xmul(tx0, ty0);
-  t.w_ne = xmul(tx1, ty0);
-  t.w_sw = xmul(tx0, ty1);
-  t.w_se = xmul(tx1, ty1);
-  const int xi = min(max((int)xw, 0), W - 1), yi = min(max((int)yn, 0), H - 1);
-  const int xe = min(xi + 1, W - 1), ys = min(yi + 1, H - 1);   // weight is exactly 0 when these clamp
-  t.o_nw = yi * W + xi;
-  t.o_ne = yi * W + xe;
-  t.o_sw = ys * W + xi;
-  t.o_se = ys * W + xe;
+  t.wa = xmul(txl, tyn);
+  t.wb = xmul(txr, tyn);
+  t.wc = xmul(txl, tys);
+  t.wd = xmul(txr, tys);
+  t.o = yi * W + xi;
   return t;
 }
 
-// ((nw*w + ne*w) + sw*w) + se*w with every step rounded (mask-grade).
-__device__ __forceinline__ float blend_exact(float nw, float ne, float sw, float se, const Tap& t) {
-  return xadd(xadd(xadd(xmul(nw, t.w_nw), xmul(ne, t.w_ne)), xmul(sw, t.w_sw)), xmul(se, t.w_se));
+// ((a*wa + b*wb) + c*wc) + d*wd with every step rounded (mask-grade).
+__device__ __forceinline__ float blend_exact(float a, float b, float c, float d, const Tap& t) {
+  return xadd(xadd(xadd(xmul(a, t.wa), xmul(b, t.wb)), xmul(c, t.wc)), xmul(d, t.wd));
 }
-__device__ __forceinline__ float blend_fast(float nw, float ne, float sw, float se, const Tap& t) {
-  return fmaf(se, t.w_se, fmaf(sw, t.w_sw, fmaf(ne, t.w_ne, nw * t.w_nw)));
+__device__ __forceinline__ float blend_fast(float a, float b, float c, float d, const Tap& t) {
+  return fmaf(d, t.wd, fmaf(c, t.wc, fmaf(b, t.wb, a * t.wa)));
 }
-__device__ __forceinline__ float sample_exact(const float* __restrict__ plane, const Tap& t) {
-  return blend_exact(__ldg(plane + t.o_nw), __ldg(plane + t.o_ne), __ldg(plane + t.o_sw), __ldg(plane + t.o_se), t);
+__device__ __forceinline__ float sample_exact(const float* __restrict__ plane, const Tap& t, int W) {
+  const float* q = plane + t.o;
+  return blend_exact(__ldg(q), __ldg(q + 1), __ldg(q + W), __ldg(q + W + 1), t);
 }
-__device__ __forceinline__ float sample_mask(const uint8_t* __restrict__ plane, const Tap& t) {
-  return blend_exact((float)__ldg(plane + t.o_nw), (float)__ldg(plane + t.o_ne), (float)__ldg(plane + t.o_sw),
-                     (float)__ldg(plane + t.o_se), t);
+__device__ __forceinline__ float sample_mask(const uint8_t* __restrict__ plane, const Tap& t, int W) {
+  const uint8_t* q = plane + t.o;
+  return blend_exact((float)__ldg(q), (float)__ldg(q + 1), (float)__ldg(q + W), (float)__ldg(q + W + 1), t);
 }
 
 // z-buffer + in-view test (geometry.py:334-350). true = excluded.

@@ -88,8 +88,12 @@ __device__ void finalize_pair(const UicIterParams& p, int b, float gmin, float g
   if (st) atomicOr(p.status, st);
 }
 
+#ifndef DPFT_MIN_CTAS
+#define DPFT_MIN_CTAS 4   // 128-thread CTAs per SM the register allocation must allow
+#endif
+
 template <int CH, bool TRU>
-__global__ void __launch_bounds__(kThreads) uic_iter_kernel(const UicIterParams p) {
+__global__ void __launch_bounds__(kThreads, DPFT_MIN_CTAS) uic_iter_kernel(const UicIterParams p) {
   __shared__ float red[kWarps][NSUM][33];
   __shared__ double wsum[kWarps][NSUM + 1];
   __shared__ float wvmin[kWarps], wvmax[kWarps];
@@ -100,6 +104,7 @@ __global__ void __launch_bounds__(kThreads) uic_iter_kernel(const UicIterParams 
   const int b = blockIdx.y;
   const int H = p.H, W = p.W, C = p.C;
   const size_t plane = (size_t)H * W;
+  const int iplane = H * W;
 
   const int wt = blockIdx.x * kWarps + warp;
   const bool warp_on = wt < p.nseg * p.nrt;
@@ -145,10 +150,10 @@ __global__ void __launch_bounds__(kThreads) uic_iter_kernel(const UicIterParams 
       const int ot = max(y0 - 1, 0) * W + xc, om = min(y0, H - 1) * W + xc;
 #pragma unroll
       for (int c = 0; c < CH; ++c) {
-        ft[c] = __ldg(X0 + c * plane + ot);
-        fm[c] = __ldg(X0 + c * plane + om);
-        st[c] = __ldg(S0 + c * plane + ot);
-        sm[c] = __ldg(S0 + c * plane + om);
+        ft[c] = __ldg(X0 + (ot + c * iplane));
+        fm[c] = __ldg(X0 + (om + c * iplane));
+        st[c] = __ldg(S0 + (ot + c * iplane));
+        sm[c] = __ldg(S0 + (om + c * iplane));
       }
     }
     if (c0 == 0) {
@@ -167,8 +172,8 @@ __global__ void __launch_bounds__(kThreads) uic_iter_kernel(const UicIterParams 
       float fb[CH], sb[CH];
 #pragma unroll
       for (int c = 0; c < CH; ++c) {
-        fb[c] = __ldg(X0 + c * plane + ob);
-        sb[c] = __ldg(S0 + c * plane + ob);
+        fb[c] = __ldg(X0 + (ob + c * iplane));
+        sb[c] = __ldg(S0 + (ob + c * iplane));
       }
       const int o = y * W + xc;
       const float d0 = __ldg(d0p + o);
@@ -177,97 +182,105 @@ __global__ void __launch_bounds__(kThreads) uic_iter_kernel(const UicIterParams 
       float u, v, inv_z;
       warp_pixel(pose, px, py, d0, fx, fy, cx, cy, u, v, inv_z);
       const Tap tap = make_tap(u, v, H, W);
-      const float d1w = sample_exact(d1p, tap);
+      const float d1w = sample_exact(d1p, tap, W);
       bool occ = occluded(u, v, inv_z, d1w, H, W);
       if (m0p) occ = occ || (__ldg(m0p + o) == 0);
-      if (m1p) occ = occ || !(sample_mask(m1p, tap) > 0.f);
-      float s0c0 = sm[0];
+      if (m1p) occ = occ || !(sample_mask(m1p, tap, W) > 0.f);
       if (TRU) {
-        if (c0 != 0) s0c0 = __ldg(p.s0 + (size_t)b * C * plane + o);
+        const float s0c0 = (c0 == 0) ? sm[0] : __ldg(p.s0 + (size_t)b * C * plane + o);
         occ = occ || (s0c0 == s0lo) || (s0c0 == s0hi);
       }
 
       float saa = 0.f, sab = 0.f, sbb = 0.f, sar = 0.f, sbr = 0.f, sca = 0.f, scb = 0.f;
       float pmin = CUDART_INF_F, pmax = -CUDART_INF_F, sr0 = 0.f;
+      constexpr int G = CH < 4 ? CH : 4;   // channels whose 8*G lookups are in flight together
 #pragma unroll
-      for (int c = 0; c < CH; ++c) {
-        // unit Sobel gradient of x0 and sigma0 (algorithms.py:1844-1865), separable form:
-        // Sx = vs(x+1) - vs(x-1), Sy = vd(x-1) + 2 vd(x) + vd(x+1), vs = t+2m+b, vd = b-t
-        const float fvs = ft[c] + 2.f * fm[c] + fb[c], fvd = fb[c] - ft[c];
-        const float svs = st[c] + 2.f * sm[c] + sb[c], svd = sb[c] - st[c];
-        const float fSx = __shfl_down_sync(0xffffffffu, fvs, 1) - __shfl_up_sync(0xffffffffu, fvs, 1);
-        const float fSy = __shfl_up_sync(0xffffffffu, fvd, 1) + 2.f * fvd + __shfl_down_sync(0xffffffffu, fvd, 1);
-        const float sSx = __shfl_down_sync(0xffffffffu, svs, 1) - __shfl_up_sync(0xffffffffu, svs, 1);
-        const float sSy = __shfl_up_sync(0xffffffffu, svd, 1) + 2.f * svd + __shfl_down_sync(0xffffffffu, svd, 1);
-        const float fin = rsqrtf(fmaf(fSx, fSx, fmaf(fSy, fSy, 1e-8f)));
-        const float sin_ = rsqrtf(fmaf(sSx, sSx, fmaf(sSy, sSy, 1e-8f)));
-        const float gfx = fSx * fin, gfy = fSy * fin, gsx = sSx * sin_, gsy = sSy * sin_;
-
-        const float* x1c = X1 + c * plane;
-        const float* s1c = S1 + c * plane;
-        const float fr = blend_fast(__ldg(x1c + tap.o_nw), __ldg(x1c + tap.o_ne), __ldg(x1c + tap.o_sw),
-                                    __ldg(x1c + tap.o_se), tap);
-        float sr;
-        if (TRU) sr = sample_exact(s1c, tap);   // compared for equality against its batch extremes
-        else sr = blend_fast(__ldg(s1c + tap.o_nw), __ldg(s1c + tap.o_ne), __ldg(s1c + tap.o_sw),
-                             __ldg(s1c + tap.o_se), tap);
-
-        // residual, its uncertainty and the 2-vector d(wres)/d(u,v) (algorithms.py:1969-1972, :872)
-        const float res = fr - fm[c];
-        const float s0v = sm[c];
-        const float rs = rsqrtf(fmaf(sr, sr, s0v * s0v));   // 1 / sigma
-        const float wres = res * rs;
-        const float q = res * s0v * rs * rs * rs;
-        const float a = fmaf(gfx, rs, q * gsx);
-        const float bq = fmaf(gfy, rs, q * gsy);
-        const float wm = occ ? 1e-6f : wres;
-        saa = fmaf(a, a, saa);
-        sab = fmaf(a, bq, sab);
-        sbb = fmaf(bq, bq, sbb);
-        sar = fmaf(a, wm, sar);
-        sbr = fmaf(bq, wm, sbr);
-        if (TRU) {
-          const float dw = wres - 1e-6f;
-          sca = fmaf(a, dw, sca);
-          scb = fmaf(bq, dw, scb);
-          pmin = fminf(pmin, sr);
-          pmax = fmaxf(pmax, sr);
-          if (c == 0) sr0 = sr;
+      for (int g0 = 0; g0 < CH; g0 += G) {
+        // all lookups of this channel group first (one base address per plane, fixed offsets) ...
+        float xa[G], xb[G], xc_[G], xd[G], za[G], zb[G], zc[G], zd[G];
+#pragma unroll
+        for (int c = 0; c < G; ++c) {
+          // 32-bit element index from one base per tensor: one IMAD.WIDE per row of the footprint
+          const int ia = tap.o + (g0 + c) * iplane, ic = ia + W;
+          xa[c] = __ldg(X1 + ia); xb[c] = __ldg(X1 + ia + 1); xc_[c] = __ldg(X1 + ic); xd[c] = __ldg(X1 + ic + 1);
+          za[c] = __ldg(S1 + ia); zb[c] = __ldg(S1 + ia + 1); zc[c] = __ldg(S1 + ic); zd[c] = __ldg(S1 + ic + 1);
+        }
+        // ... then the keyframe-side math of the group, which does not need them
+        float gfx[G], gfy[G], gsx[G], gsy[G];
+#pragma unroll
+        for (int c = 0; c < G; ++c) {
+          const int k = g0 + c;
+          // unit Sobel gradient of x0 and sigma0 (algorithms.py:1844-1865), separable form:
+          // Sx = vs(x+1) - vs(x-1), Sy = vd(x-1) + 2 vd(x) + vd(x+1), vs = t+2m+b, vd = b-t
+          const float fvs = ft[k] + 2.f * fm[k] + fb[k], fvd = fb[k] - ft[k];
+          const float svs = st[k] + 2.f * sm[k] + sb[k], svd = sb[k] - st[k];
+          const float fSx = __shfl_down_sync(0xffffffffu, fvs, 1) - __shfl_up_sync(0xffffffffu, fvs, 1);
+          const float fSy = __shfl_up_sync(0xffffffffu, fvd, 1) + 2.f * fvd + __shfl_down_sync(0xffffffffu, fvd, 1);
+          const float sSx = __shfl_down_sync(0xffffffffu, svs, 1) - __shfl_up_sync(0xffffffffu, svs, 1);
+          const float sSy = __shfl_up_sync(0xffffffffu, svd, 1) + 2.f * svd + __shfl_down_sync(0xffffffffu, svd, 1);
+          const float fin = rsqrtf(fmaf(fSx, fSx, fmaf(fSy, fSy, 1e-8f)));
+          const float sin_ = rsqrtf(fmaf(sSx, sSx, fmaf(sSy, sSy, 1e-8f)));
+          gfx[c] = fSx * fin; gfy[c] = fSy * fin; gsx[c] = sSx * sin_; gsy[c] = sSy * sin_;
+        }
+#pragma unroll
+        for (int c = 0; c < G; ++c) {
+          const int k = g0 + c;
+          const float fr = blend_fast(xa[c], xb[c], xc_[c], xd[c], tap);
+          // sigma is compared for equality against its batch extremes -> mask-grade arithmetic
+          const float sr = TRU ? blend_exact(za[c], zb[c], zc[c], zd[c], tap) : blend_fast(za[c], zb[c], zc[c], zd[c], tap);
+          // residual, its uncertainty and the 2-vector d(wres)/d(u,v) (algorithms.py:1969-1972, :872)
+          const float res = fr - fm[k];
+          const float s0v = sm[k];
+          const float rs = rsqrtf(fmaf(sr, sr, s0v * s0v));   // 1 / sigma
+          const float wres = res * rs;
+          const float q = wres * (s0v * (rs * rs));           // res * sigma0 / sigma^3
+          const float a = fmaf(gfx[c], rs, q * gsx[c]);
+          const float bq = fmaf(gfy[c], rs, q * gsy[c]);
+          const float wm = occ ? 1e-6f : wres;
+          saa = fmaf(a, a, saa);
+          sab = fmaf(a, bq, sab);
+          sbb = fmaf(bq, bq, sbb);
+          sar = fmaf(a, wm, sar);
+          sbr = fmaf(bq, wm, sbr);
+          if (TRU) {
+            const float dw = wres - 1e-6f;
+            sca = fmaf(a, dw, sca);
+            scb = fmaf(bq, dw, scb);
+            pmin = fminf(pmin, sr);
+            pmax = fmaxf(pmax, sr);
+            if (k == 0) sr0 = sr;
+          }
         }
       }
-      if (TRU && c0 != 0) sr0 = sample_exact(p.s1 + (size_t)b * C * plane, tap);
+      if (TRU && c0 != 0) sr0 = sample_exact(p.s1 + (size_t)b * C * plane, tap, W);
 
-      if (col_out) {
-        float ju[6], jv[6];
-        warp_rows(px, py, d0, fx, fy, ju, jv);
-        accumulate_system(acc, ju, jv, saa, sab, sbb, sar, sbr);
-        if (TRU) {
-          if (pmin < vmin) {
-            vmin = pmin;
+      // halo lanes and columns past the image contribute nothing
+      if (!col_out) { saa = sab = sbb = sar = sbr = 0.f; }
+      float ju[6], jv[6];
+      warp_rows(px, py, d0, fx, fy, ju, jv);
+      accumulate_system(acc, ju, jv, saa, sab, sbb, sar, sbr);
+      if (TRU) {
+        // running extremes of the warped sigma and what their pixels added to J^T r.  New extremes and
+        // ties are rare after the first rows, so the bookkeeping sits behind one warp-uniform branch.
+        const bool lo = col_out && (pmin < vmin), hi = col_out && (pmax > vmax);
+        const float nmin = lo ? pmin : vmin, nmax = hi ? pmax : vmax;
+        const bool tmin = col_out && !occ && (sr0 == nmin), tmax = col_out && !occ && (sr0 == nmax);
+        if (__any_sync(0xffffffffu, lo || hi || tmin || tmax)) {
+          vmin = nmin;
+          vmax = nmax;
 #pragma unroll
-            for (int i = 0; i < 6; ++i) cmn[i] = 0.f;
-          }
-          if (pmax > vmax) {
-            vmax = pmax;
-#pragma unroll
-            for (int i = 0; i < 6; ++i) cmx[i] = 0.f;
-          }
-          if (!occ) {
-            const bool tmin = (sr0 == vmin), tmax = (sr0 == vmax);
-#pragma unroll
-            for (int i = 0; i < 6; ++i) {
-              float cc = 0.f;
-              if (i != 4) cc = fmaf(sca, ju[i], cc);
-              if (i != 3) cc = fmaf(scb, jv[i], cc);
-              if (tmin) cmn[i] += cc;
-              if (tmax) cmx[i] += cc;
-            }
+          for (int i = 0; i < 6; ++i) {
+            float cc = 0.f;
+            if (i != 4) cc = fmaf(sca, ju[i], cc);
+            if (i != 3) cc = fmaf(scb, jv[i], cc);
+            cmn[i] = (lo ? 0.f : cmn[i]) + (tmin ? cc : 0.f);
+            cmx[i] = (hi ? 0.f : cmx[i]) + (tmax ? cc : 0.f);
           }
         }
-        if (p.occ_out && c0 == 0) {
-          p.occ_out[(size_t)b * plane + (size_t)y * W + x] = occ ? 1 : 0;
-          if (TRU) p.sr0_dbg[(size_t)b * plane + (size_t)y * W + x] = sr0;
-        }
+      }
+      if (p.occ_out && c0 == 0 && col_out) {
+        p.occ_out[(size_t)b * plane + (size_t)y * W + x] = occ ? 1 : 0;
+        if (TRU) p.sr0_dbg[(size_t)b * plane + (size_t)y * W + x] = sr0;
       }
 #pragma unroll
       for (int c = 0; c < CH; ++c) {
@@ -278,6 +291,7 @@ __global__ void __launch_bounds__(kThreads) uic_iter_kernel(const UicIterParams 
       }
     }
   }
+
   // ---------------------------------------------------------------- CTA reduction
   if (TRU) {
     const float wmn = warp_min(vmin), wmx = warp_max(vmax);
@@ -484,8 +498,13 @@ struct Plan {
   size_t off_partials, off_pairrec, off_counters, off_mm, off_gmm, off_sr0, total;
 };
 
-static int pick_tile_rows(int H) {
-  const int tiles = (H + 7) / 8;          // about 8 rows per tile
+// Rows per warp tile: tall tiles amortise the two halo rows, short tiles give a small level enough warps
+// to fill the machine (a tile is walked row by row by one warp, so its height is pure latency).
+static int pick_tile_rows(int H, int nseg, int B) {
+  const long target_warps = 148L * 16 * 2;
+  long tr = ((long)H * nseg * B + target_warps - 1) / target_warps;
+  tr = std::max(1L, std::min(tr, 12L));
+  const int tiles = (int)((H + tr - 1) / tr);
   return (H + tiles - 1) / tiles;
 }
 
@@ -495,7 +514,7 @@ static Plan make_plan(const dpft_level_t* lv, int n_levels, int B, uint32_t flag
   pl.max_plane = 0;
   for (int l = 0; l < n_levels; ++l) {
     pl.nseg[l] = (lv[l].W + kCols - 1) / kCols;
-    pl.TR[l] = pick_tile_rows(lv[l].H);
+    pl.TR[l] = pick_tile_rows(lv[l].H, pl.nseg[l], B);
     pl.nrt[l] = (lv[l].H + pl.TR[l] - 1) / pl.TR[l];
     pl.ctas[l] = (pl.nseg[l] * pl.nrt[l] + kWarps - 1) / kWarps;
     if (pl.ctas[l] > pl.max_ctas) pl.max_ctas = pl.ctas[l];

@@ -1,0 +1,14 @@
+#!/bin/bash
+# Tuning sweep on the GPU box: rebuild with each macro set, run the parity tests once and a short bench.
+# usage: profiles/sweep.sh "-DDPFT_MIN_CTAS=2" "-DDPFT_MIN_CTAS=3" ...
+for flags in "$@"; do
+  export DPFT_NVCC_EXTRA="$flags"
+  python -c "from deep_prob_feature_track_b200 import _lib; _lib.build(force=True)" || exit 1
+  echo "=== $flags"
+  python -m pytest tests -m gpu -x -q 2>&1 | tail -1
+  python bench.py --steps 100 --warmup 5 --no-cpu-baseline 2>/dev/null | python -c "
+import json,sys
+d=json.loads(sys.stdin.read()); r=d['roofline']
+print('pairs/s %.0f  ms/step %.3f  lvl0 launch %.1f us  frac %.3f  launches(us) %s' % (d['value'], d['ms_per_step'], r['launch_ms']*1e3, r['frac'], [round(x*1e3) for x in r['all_launch_ms']]))"
+done
+unset DPFT_NVCC_EXTRA
