@@ -163,6 +163,7 @@ def main():
     ap.add_argument("--workload", default="tum", choices=tuple(WORKLOADS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-pdl", action="store_true")
+    ap.add_argument("--fused-sobel", action="store_true", help="use the sliding-window kernel (DPFT_FUSED_SOBEL)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
 
@@ -232,14 +233,16 @@ def main():
     set_bytes = host_flat.numel() * 4
 
     def solve(levels, **kw):
-        return A.uic_solve(levels, pose0, iters=ITERS, remove_tru_sigma=True, pdl=not args.no_pdl, **kw)
+        return A.uic_solve(levels, pose0, iters=ITERS, remove_tru_sigma=True, pdl=not args.no_pdl, fused_sobel=args.fused_sobel,
+                           **kw)
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
-    launches_per_step = 1 + N_LEVELS + N_LEVELS * ITERS     # init + sigma0 min/max per level + GN launches
+    # init + sigma0 min/max per level + GN launches (+ 2 Sobel launches per level when gradients are materialised)
+    launches_per_step = 1 + N_LEVELS + N_LEVELS * ITERS + (0 if args.fused_sobel else 2 * N_LEVELS)
 
     with ClockSampler(local_rank) as clocks:
         # ---- value: inputs resident in HBM
@@ -317,6 +320,7 @@ def main():
         "config": {"workload": wl["name"], "pairs_per_gpu_per_step": B, "feature_channels": C,
                    "resolution": f"{H}x{W}", "levels": N_LEVELS, "iters_per_level": ITERS, "variant": "U_IC",
                    "remove_tru_sigma": True, "pdl": not args.no_pdl,
+                   "sobel": "fused" if args.fused_sobel else "materialised once per level",
                    "l2": f"inputs rotate over {N_SETS} resident sets of {set_bytes / 1e6:.0f} MB each (> 126 MB L2)",
                    "algorithmic_bytes_per_step": bytes_step},
         "step_hbm_frac": bytes_step / (ms / args.steps * 1e-3) / 1e9 / peak,

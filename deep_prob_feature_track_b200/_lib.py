@@ -26,6 +26,7 @@ DPFT_MAX_LEVELS = 8
 DPFT_REMOVE_TRU_SIGMA = 0x01
 DPFT_COMBINE_ICP = 0x02
 DPFT_NO_PDL = 0x04
+DPFT_FUSED_SOBEL = 0x08
 DPFT_ST_NONFINITE = 0x01
 DPFT_ST_SINGULAR = 0x02
 

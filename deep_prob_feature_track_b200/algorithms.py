@@ -86,7 +86,7 @@ class SolveResult:
 
 
 def uic_solve(levels: Sequence[Dict[str, torch.Tensor]], pose: Pose, *, iters: int = 3,
-              remove_tru_sigma: bool = False, want_occ: bool = False, pdl: bool = True, timed: bool = False,
+              remove_tru_sigma: bool = False, want_occ: bool = False, pdl: bool = True, timed: bool = False, fused_sobel: bool = False,
               obj_mask0: Optional[Sequence] = None, obj_mask1: Optional[Sequence] = None) -> SolveResult:
     """Coarse-to-fine U_IC solve of a batch of frame pairs on the current CUDA stream.
 
@@ -125,7 +125,8 @@ def uic_solve(levels: Sequence[Dict[str, torch.Tensor]], pose: Pose, *, iters: i
         a.obj_mask1 = m1.data_ptr() if m1 is not None else None
         a.occ_out = o.data_ptr() if o is not None else None
         a.H, a.W = H, W
-    flags = (_lib.DPFT_REMOVE_TRU_SIGMA if remove_tru_sigma else 0) | (0 if pdl else _lib.DPFT_NO_PDL)
+    flags = ((_lib.DPFT_REMOVE_TRU_SIGMA if remove_tru_sigma else 0) | (0 if pdl else _lib.DPFT_NO_PDL)
+             | (_lib.DPFT_FUSED_SOBEL if fused_sobel else 0))
     n_it = n_levels * iters
     pose_in = pack_pose(pose).to(dev)
     pose_hist = torch.empty((n_it + 1, B, 12), dtype=torch.float32, device=dev)

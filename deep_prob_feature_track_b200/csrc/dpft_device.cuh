@@ -99,7 +99,8 @@ __device__ __forceinline__ float blend_fast(float a, float b, float c, float d, 
 }
 __device__ __forceinline__ float sample_exact(const float* __restrict__ plane, const Tap& t, int W) {
   const float* q = plane + t.o;
-  return blend_exact(__ldg(q), __ldg(q + 1), __ldg(q + W), __ldg(q + W + 1), t);
+  const float* r = q + W;
+  return blend_exact(__ldg(q), __ldg(q + 1), __ldg(r), __ldg(r + 1), t);
 }
 __device__ __forceinline__ float sample_mask(const uint8_t* __restrict__ plane, const Tap& t, int W) {
   const uint8_t* q = plane + t.o;

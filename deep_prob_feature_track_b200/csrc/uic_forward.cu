@@ -88,17 +88,181 @@ __device__ void finalize_pair(const UicIterParams& p, int b, float gmin, float g
   if (st) atomicOr(p.status, st);
 }
 
+// Everything after the per-thread accumulation, shared by both iteration kernels: warp -> CTA sums
+// (fp64 once lanes are combined), one partial record per CTA, the last CTA of a pair folds its records in
+// a fixed order (deterministic), and the last CTA of the grid (or of the pair, when nothing couples the
+// pairs) damps, solves and updates the poses.
+template <bool TRU>
+__device__ __forceinline__ void reduce_and_finish(const UicIterParams& p, const int b, const float (&acc)[27],
+                                                  float (&cmn)[6], float (&cmx)[6], const float vmin,
+                                                  const float vmax) {
+  __shared__ float red[kWarps][NSUM][33];
+  __shared__ double wsum[kWarps][NSUM + 1];
+  __shared__ float wvmin[kWarps], wvmax[kWarps];
+  __shared__ float s_pair_mm[2];
+  __shared__ int s_flag;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  // ---------------------------------------------------------------- CTA reduction
+  if (TRU) {
+    const float wmn = warp_min(vmin), wmx = warp_max(vmax);
+    if (vmin != wmn) {
+#pragma unroll
+      for (int i = 0; i < 6; ++i) cmn[i] = 0.f;
+    }
+    if (vmax != wmx) {
+#pragma unroll
+      for (int i = 0; i < 6; ++i) cmx[i] = 0.f;
+    }
+    if (lane == 0) {
+      wvmin[warp] = wmn;
+      wvmax[warp] = wmx;
+    }
+  }
+#pragma unroll
+  for (int e = 0; e < 27; ++e) red[warp][e][lane] = acc[e];
+  if (TRU) {
+#pragma unroll
+    for (int i = 0; i < 6; ++i) {
+      red[warp][27 + i][lane] = cmn[i];
+      red[warp][33 + i][lane] = cmx[i];
+    }
+  }
+  __syncwarp();
+  constexpr int NE = TRU ? NSUM : 27;
+  for (int e = lane; e < NE; e += 32) {
+    double s = 0.0;
+#pragma unroll 8
+    for (int j = 0; j < 32; ++j) s += (double)red[warp][e][j];
+    wsum[warp][e] = s;
+  }
+  __syncthreads();
+
+  float* part = p.partials + ((size_t)b * p.ctas_per_pair + blockIdx.x) * PS;
+  float cta_min = CUDART_INF_F, cta_max = -CUDART_INF_F;
+  if (TRU) {
+#pragma unroll
+    for (int w = 0; w < kWarps; ++w) {
+      cta_min = fminf(cta_min, wvmin[w]);
+      cta_max = fmaxf(cta_max, wvmax[w]);
+    }
+  }
+  if (threadIdx.x < NE) {
+    const int e = threadIdx.x;
+    double s = 0.0;
+#pragma unroll
+    for (int w = 0; w < kWarps; ++w) {
+      bool take = true;
+      if (TRU && e >= 27 && e < 33) take = (wvmin[w] == cta_min);
+      if (TRU && e >= 33) take = (wvmax[w] == cta_max);
+      if (take) s += wsum[w][e];
+    }
+    part[e < 27 ? e : e + 2] = (float)s;   // corr entries live at E_CMIN.. / E_CMAX..
+  }
+  if (TRU && threadIdx.x == 0) {
+    part[E_VMIN] = cta_min;
+    part[E_VMAX] = cta_max;
+  }
+
+  // ---------------------------------------------------------------- last CTA of the pair reduces it
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) s_flag = (atomicAdd(p.counters + b, 1) == p.ctas_per_pair - 1);
+  __syncthreads();
+  if (!s_flag) return;
+  __threadfence();
+
+  const float* pp = p.partials + (size_t)b * p.ctas_per_pair * PS;
+  const int n = p.ctas_per_pair;
+  float pair_min = CUDART_INF_F, pair_max = -CUDART_INF_F;
+  if (TRU) {
+    float a = CUDART_INF_F, c = -CUDART_INF_F;
+    for (int i = threadIdx.x; i < n; i += kThreads) {
+      a = fminf(a, __ldcg(pp + (size_t)i * PS + E_VMIN));
+      c = fmaxf(c, __ldcg(pp + (size_t)i * PS + E_VMAX));
+    }
+    a = warp_min(a);
+    c = warp_max(c);
+    __syncthreads();   // wvmin/wvmax reuse
+    if (lane == 0) {
+      wvmin[warp] = a;
+      wvmax[warp] = c;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int w = 0; w < kWarps; ++w) {
+      pair_min = fminf(pair_min, wvmin[w]);
+      pair_max = fmaxf(pair_max, wvmax[w]);
+    }
+  }
+  double* rec = p.pairrec + (size_t)b * PS;
+  if (threadIdx.x < NE) {
+    const int e = threadIdx.x;
+    const int slot = e < 27 ? e : e + 2;
+    double s = 0.0;
+    for (int i = 0; i < n; ++i) {
+      const float* q = pp + (size_t)i * PS;
+      bool take = true;
+      if (TRU && e >= 27 && e < 33) take = (__ldcg(q + E_VMIN) == pair_min);
+      if (TRU && e >= 33) take = (__ldcg(q + E_VMAX) == pair_max);
+      if (take) s += (double)__ldcg(q + slot);
+    }
+    rec[slot] = s;
+  }
+  if (TRU && threadIdx.x == 0) {
+    rec[E_VMIN] = (double)pair_min;
+    rec[E_VMAX] = (double)pair_max;
+  }
+  if (threadIdx.x == 0) p.counters[b] = 0;   // ready for the next launch
+  __threadfence();
+  __syncthreads();
+
+  if (!TRU) {
+    if (threadIdx.x == 0) finalize_pair<false>(p, b, 0.f, 0.f);
+    return;
+  }
+
+  // ---------------------------------------------------------------- last CTA of the grid: batch extremes + all solves
+  if (threadIdx.x == 0) s_flag = (atomicAdd(p.counters + p.B, 1) == p.B - 1);
+  __syncthreads();
+  if (!s_flag) return;
+  __threadfence();
+  {
+    float a = CUDART_INF_F, c = -CUDART_INF_F;
+    for (int i = threadIdx.x; i < p.B; i += kThreads) {
+      a = fminf(a, (float)__ldcg(p.pairrec + (size_t)i * PS + E_VMIN));
+      c = fmaxf(c, (float)__ldcg(p.pairrec + (size_t)i * PS + E_VMAX));
+    }
+    a = warp_min(a);
+    c = warp_max(c);
+    if (lane == 0) {
+      wvmin[warp] = a;
+      wvmax[warp] = c;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      float g0 = CUDART_INF_F, g1 = -CUDART_INF_F;
+#pragma unroll
+      for (int w = 0; w < kWarps; ++w) {
+        g0 = fminf(g0, wvmin[w]);
+        g1 = fmaxf(g1, wvmax[w]);
+      }
+      s_pair_mm[0] = g0;
+      s_pair_mm[1] = g1;
+      p.gmm[0] = g0;
+      p.gmm[1] = g1;
+      p.counters[p.B] = 0;
+    }
+    __syncthreads();
+  }
+  for (int i = threadIdx.x; i < p.B; i += kThreads) finalize_pair<true>(p, i, s_pair_mm[0], s_pair_mm[1]);
+}
+
 #ifndef DPFT_MIN_CTAS
 #define DPFT_MIN_CTAS 4   // 128-thread CTAs per SM the register allocation must allow
 #endif
 
 template <int CH, bool TRU>
 __global__ void __launch_bounds__(kThreads, DPFT_MIN_CTAS) uic_iter_kernel(const UicIterParams p) {
-  __shared__ float red[kWarps][NSUM][33];
-  __shared__ double wsum[kWarps][NSUM + 1];
-  __shared__ float wvmin[kWarps], wvmax[kWarps];
-  __shared__ float s_pair_mm[2];
-  __shared__ int s_flag;
 
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int b = blockIdx.y;
@@ -292,159 +456,163 @@ __global__ void __launch_bounds__(kThreads, DPFT_MIN_CTAS) uic_iter_kernel(const
     }
   }
 
-  // ---------------------------------------------------------------- CTA reduction
+  reduce_and_finish<TRU>(p, b, acc, cmn, cmx, vmin, vmax);
+}
+
+// =========================================================================== materialised-gradient path
+// The unit Sobel gradients of x0 and sigma0 do not depend on the pose, so they can be formed once per level
+// (sobel_unit_kernel) and read back by the three iterations.  That costs HBM traffic (4C extra floats per
+// pixel and iteration) but turns the iteration into a pixel-parallel kernel with no register windows, no
+// halo lanes and every load of a pixel independent of the others -- which is what the latency-bound
+// fused kernel above lacks.  DESIGN.md carries the byte accounting of both.
+
+// g = S / sqrt(Sx^2 + Sy^2 + 1e-8), S the replicate-padded Sobel response (algorithms.py:1844-1865)
+__global__ void __launch_bounds__(256) sobel_unit_kernel(const float* __restrict__ img, float* __restrict__ gx,
+                                                         float* __restrict__ gy, int planes, int H, int W) {
+  const int x = blockIdx.x * 32 + (threadIdx.x & 31);
+  const int y = blockIdx.y * 8 + (threadIdx.x >> 5);
+  if (x >= W || y >= H) return;
+  const int xl = max(x - 1, 0), xr = min(x + 1, W - 1), yt = max(y - 1, 0) * W, ym = y * W, yb = min(y + 1, H - 1) * W;
+  for (int pl = blockIdx.z; pl < planes; pl += gridDim.z) {
+    const float* q = img + (size_t)pl * H * W;
+    const float a = __ldg(q + yt + xl), b = __ldg(q + yt + x), c = __ldg(q + yt + xr);
+    const float d = __ldg(q + ym + xl), f = __ldg(q + ym + xr);
+    const float g = __ldg(q + yb + xl), h = __ldg(q + yb + x), i = __ldg(q + yb + xr);
+    const float sx = (c - a) + 2.f * (f - d) + (i - g);
+    const float sy = (g - a) + 2.f * (h - b) + (i - c);
+    const float inv = rsqrtf(fmaf(sx, sx, fmaf(sy, sy, 1e-8f)));
+    gx[(size_t)pl * H * W + ym + x] = sx * inv;
+    gy[(size_t)pl * H * W + ym + x] = sy * inv;
+  }
+}
+
+struct PxExtra {
+  const float *gfx, *gfy, *gsx, *gsy;   // (B,C,H,W) unit gradients of x0 and sigma0
+  int ppt;                              // pixels per thread
+};
+
+template <int CH, bool TRU>
+__global__ void __launch_bounds__(kThreads, 4) uic_iter_px_kernel(const UicIterParams p, const PxExtra e) {
+  const int b = blockIdx.y;
+  const int H = p.H, W = p.W, C = p.C;
+  const int iplane = H * W;
+
+  float acc[27];
+#pragma unroll
+  for (int i = 0; i < 27; ++i) acc[i] = 0.f;
+  float cmn[6], cmx[6];
+#pragma unroll
+  for (int i = 0; i < 6; ++i) cmn[i] = cmx[i] = 0.f;
+  float vmin = CUDART_INF_F, vmax = -CUDART_INF_F;
+
+  const float fx = __ldg(p.K + 4 * b), fy = __ldg(p.K + 4 * b + 1);
+  const float cx = __ldg(p.K + 4 * b + 2), cy = __ldg(p.K + 4 * b + 3);
+  const size_t pair_off = (size_t)b * C * iplane;
+  const float* d0p = p.d0 + (size_t)b * iplane;
+  const float* d1p = p.d1 + (size_t)b * iplane;
+  const uint8_t* m0p = p.m0 ? p.m0 + (size_t)b * iplane : nullptr;
+  const uint8_t* m1p = p.m1 ? p.m1 + (size_t)b * iplane : nullptr;
+
+  cudaTriggerProgrammaticLaunchCompletion();
+  cudaGridDependencySynchronize();
+  const Pose pose = load_pose(p.pose + (size_t)b * 12);
+  float s0lo = 0.f, s0hi = 0.f;
   if (TRU) {
-    const float wmn = warp_min(vmin), wmx = warp_max(vmax);
-    if (vmin != wmn) {
-#pragma unroll
-      for (int i = 0; i < 6; ++i) cmn[i] = 0.f;
-    }
-    if (vmax != wmx) {
-#pragma unroll
-      for (int i = 0; i < 6; ++i) cmx[i] = 0.f;
-    }
-    if (lane == 0) {
-      wvmin[warp] = wmn;
-      wvmax[warp] = wmx;
-    }
-  }
-#pragma unroll
-  for (int e = 0; e < 27; ++e) red[warp][e][lane] = acc[e];
-  if (TRU) {
-#pragma unroll
-    for (int i = 0; i < 6; ++i) {
-      red[warp][27 + i][lane] = cmn[i];
-      red[warp][33 + i][lane] = cmx[i];
-    }
-  }
-  __syncwarp();
-  constexpr int NE = TRU ? NSUM : 27;
-  for (int e = lane; e < NE; e += 32) {
-    double s = 0.0;
-#pragma unroll 8
-    for (int j = 0; j < 32; ++j) s += (double)red[warp][e][j];
-    wsum[warp][e] = s;
-  }
-  __syncthreads();
-
-  float* part = p.partials + ((size_t)b * p.ctas_per_pair + blockIdx.x) * PS;
-  float cta_min = CUDART_INF_F, cta_max = -CUDART_INF_F;
-  if (TRU) {
-#pragma unroll
-    for (int w = 0; w < kWarps; ++w) {
-      cta_min = fminf(cta_min, wvmin[w]);
-      cta_max = fmaxf(cta_max, wvmax[w]);
-    }
-  }
-  if (threadIdx.x < NE) {
-    const int e = threadIdx.x;
-    double s = 0.0;
-#pragma unroll
-    for (int w = 0; w < kWarps; ++w) {
-      bool take = true;
-      if (TRU && e >= 27 && e < 33) take = (wvmin[w] == cta_min);
-      if (TRU && e >= 33) take = (wvmax[w] == cta_max);
-      if (take) s += wsum[w][e];
-    }
-    part[e < 27 ? e : e + 2] = (float)s;   // corr entries live at E_CMIN.. / E_CMAX..
-  }
-  if (TRU && threadIdx.x == 0) {
-    part[E_VMIN] = cta_min;
-    part[E_VMAX] = cta_max;
+    s0lo = ord2f(__ldcg(p.s0mm));
+    s0hi = ord2f(__ldcg(p.s0mm + 1));
   }
 
-  // ---------------------------------------------------------------- last CTA of the pair reduces it
-  __threadfence();
-  __syncthreads();
-  if (threadIdx.x == 0) s_flag = (atomicAdd(p.counters + b, 1) == p.ctas_per_pair - 1);
-  __syncthreads();
-  if (!s_flag) return;
-  __threadfence();
-
-  const float* pp = p.partials + (size_t)b * p.ctas_per_pair * PS;
-  const int n = p.ctas_per_pair;
-  float pair_min = CUDART_INF_F, pair_max = -CUDART_INF_F;
-  if (TRU) {
-    float a = CUDART_INF_F, c = -CUDART_INF_F;
-    for (int i = threadIdx.x; i < n; i += kThreads) {
-      a = fminf(a, __ldcg(pp + (size_t)i * PS + E_VMIN));
-      c = fmaxf(c, __ldcg(pp + (size_t)i * PS + E_VMAX));
+  for (int i = 0; i < e.ppt; ++i) {
+    const int pix = (blockIdx.x * e.ppt + i) * kThreads + threadIdx.x;
+    if (pix >= iplane) break;
+    const int y = pix / W, x = pix - y * W;
+    const float px = xdiv(xsub((float)x, cx), fx), py = xdiv(xsub((float)y, cy), fy);
+    const float d0 = __ldg(d0p + pix);
+    float u, v, inv_z;
+    warp_pixel(pose, px, py, d0, fx, fy, cx, cy, u, v, inv_z);
+    const Tap tap = make_tap(u, v, H, W);
+    const float d1w = sample_exact(d1p, tap, W);
+    bool occ = occluded(u, v, inv_z, d1w, H, W);
+    if (m0p) occ = occ || (__ldg(m0p + pix) == 0);
+    if (m1p) occ = occ || !(sample_mask(m1p, tap, W) > 0.f);
+    float sr0 = 0.f;
+    if (TRU) {
+      const float s0c0 = __ldg(p.s0 + pair_off + pix);
+      occ = occ || (s0c0 == s0lo) || (s0c0 == s0hi);
     }
-    a = warp_min(a);
-    c = warp_max(c);
-    __syncthreads();   // wvmin/wvmax reuse
-    if (lane == 0) {
-      wvmin[warp] = a;
-      wvmax[warp] = c;
-    }
-    __syncthreads();
+    float saa = 0.f, sab = 0.f, sbb = 0.f, sar = 0.f, sbr = 0.f, sca = 0.f, scb = 0.f;
+    float pmin = CUDART_INF_F, pmax = -CUDART_INF_F;
+    for (int c0 = 0; c0 < C; c0 += CH) {
+      const size_t o0 = pair_off + (size_t)c0 * iplane + pix;        // keyframe-side element
+      const size_t o1 = pair_off + (size_t)c0 * iplane + tap.o;      // north-west texel of the live frame
+      float f0[CH], s0v[CH], gfx[CH], gfy[CH], gsx[CH], gsy[CH];
+      float xa[CH], xb[CH], xc[CH], xd[CH], za[CH], zb[CH], zc[CH], zd[CH];
 #pragma unroll
-    for (int w = 0; w < kWarps; ++w) {
-      pair_min = fminf(pair_min, wvmin[w]);
-      pair_max = fmaxf(pair_max, wvmax[w]);
-    }
-  }
-  double* rec = p.pairrec + (size_t)b * PS;
-  if (threadIdx.x < NE) {
-    const int e = threadIdx.x;
-    const int slot = e < 27 ? e : e + 2;
-    double s = 0.0;
-    for (int i = 0; i < n; ++i) {
-      const float* q = pp + (size_t)i * PS;
-      bool take = true;
-      if (TRU && e >= 27 && e < 33) take = (__ldcg(q + E_VMIN) == pair_min);
-      if (TRU && e >= 33) take = (__ldcg(q + E_VMAX) == pair_max);
-      if (take) s += (double)__ldcg(q + slot);
-    }
-    rec[slot] = s;
-  }
-  if (TRU && threadIdx.x == 0) {
-    rec[E_VMIN] = (double)pair_min;
-    rec[E_VMAX] = (double)pair_max;
-  }
-  if (threadIdx.x == 0) p.counters[b] = 0;   // ready for the next launch
-  __threadfence();
-  __syncthreads();
-
-  if (!TRU) {
-    if (threadIdx.x == 0) finalize_pair<false>(p, b, 0.f, 0.f);
-    return;
-  }
-
-  // ---------------------------------------------------------------- last CTA of the grid: batch extremes + all solves
-  if (threadIdx.x == 0) s_flag = (atomicAdd(p.counters + p.B, 1) == p.B - 1);
-  __syncthreads();
-  if (!s_flag) return;
-  __threadfence();
-  {
-    float a = CUDART_INF_F, c = -CUDART_INF_F;
-    for (int i = threadIdx.x; i < p.B; i += kThreads) {
-      a = fminf(a, (float)__ldcg(p.pairrec + (size_t)i * PS + E_VMIN));
-      c = fmaxf(c, (float)__ldcg(p.pairrec + (size_t)i * PS + E_VMAX));
-    }
-    a = warp_min(a);
-    c = warp_max(c);
-    if (lane == 0) {
-      wvmin[warp] = a;
-      wvmax[warp] = c;
-    }
-    __syncthreads();
-    if (threadIdx.x == 0) {
-      float g0 = CUDART_INF_F, g1 = -CUDART_INF_F;
-#pragma unroll
-      for (int w = 0; w < kWarps; ++w) {
-        g0 = fminf(g0, wvmin[w]);
-        g1 = fmaxf(g1, wvmax[w]);
+      for (int c = 0; c < CH; ++c) {
+        const size_t k0 = o0 + (size_t)c * iplane, k1 = o1 + (size_t)c * iplane;
+        f0[c] = __ldg(p.x0 + k0); s0v[c] = __ldg(p.s0 + k0);
+        gfx[c] = __ldg(e.gfx + k0); gfy[c] = __ldg(e.gfy + k0);
+        gsx[c] = __ldg(e.gsx + k0); gsy[c] = __ldg(e.gsy + k0);
+        const float* q1 = p.x1 + k1;
+        const float* q2 = p.s1 + k1;
+        xa[c] = __ldg(q1); xb[c] = __ldg(q1 + 1); xc[c] = __ldg(q1 + W); xd[c] = __ldg(q1 + W + 1);
+        za[c] = __ldg(q2); zb[c] = __ldg(q2 + 1); zc[c] = __ldg(q2 + W); zd[c] = __ldg(q2 + W + 1);
       }
-      s_pair_mm[0] = g0;
-      s_pair_mm[1] = g1;
-      p.gmm[0] = g0;
-      p.gmm[1] = g1;
-      p.counters[p.B] = 0;
+#pragma unroll
+      for (int c = 0; c < CH; ++c) {
+        const float fr = blend_fast(xa[c], xb[c], xc[c], xd[c], tap);
+        // sigma is compared for equality against its batch extremes -> mask-grade arithmetic
+        const float sr = TRU ? blend_exact(za[c], zb[c], zc[c], zd[c], tap) : blend_fast(za[c], zb[c], zc[c], zd[c], tap);
+        // residual, its uncertainty and the 2-vector d(wres)/d(u,v) (algorithms.py:1969-1972, :872)
+        const float res = fr - f0[c];
+        const float rs = rsqrtf(fmaf(sr, sr, s0v[c] * s0v[c]));   // 1 / sigma
+        const float wres = res * rs;
+        const float q = wres * (s0v[c] * (rs * rs));              // res * sigma0 / sigma^3
+        const float a = fmaf(gfx[c], rs, q * gsx[c]);
+        const float bq = fmaf(gfy[c], rs, q * gsy[c]);
+        const float wm = occ ? 1e-6f : wres;
+        saa = fmaf(a, a, saa);
+        sab = fmaf(a, bq, sab);
+        sbb = fmaf(bq, bq, sbb);
+        sar = fmaf(a, wm, sar);
+        sbr = fmaf(bq, wm, sbr);
+        if (TRU) {
+          const float dw = wres - 1e-6f;
+          sca = fmaf(a, dw, sca);
+          scb = fmaf(bq, dw, scb);
+          pmin = fminf(pmin, sr);
+          pmax = fmaxf(pmax, sr);
+          if (c0 == 0 && c == 0) sr0 = sr;
+        }
+      }
     }
-    __syncthreads();
+    float ju[6], jv[6];
+    warp_rows(px, py, d0, fx, fy, ju, jv);
+    accumulate_system(acc, ju, jv, saa, sab, sbb, sar, sbr);
+    if (TRU) {
+      // running extremes of the warped sigma and what their pixels added to J^T r (rare -> one uniform branch)
+      const bool lo = pmin < vmin, hi = pmax > vmax;
+      const float nmin = lo ? pmin : vmin, nmax = hi ? pmax : vmax;
+      const bool tmin = !occ && (sr0 == nmin), tmax = !occ && (sr0 == nmax);
+      if (__any_sync(__activemask(), lo || hi || tmin || tmax)) {
+        vmin = nmin;
+        vmax = nmax;
+#pragma unroll
+        for (int k = 0; k < 6; ++k) {
+          float cc = 0.f;
+          if (k != 4) cc = fmaf(sca, ju[k], cc);
+          if (k != 3) cc = fmaf(scb, jv[k], cc);
+          cmn[k] = (lo ? 0.f : cmn[k]) + (tmin ? cc : 0.f);
+          cmx[k] = (hi ? 0.f : cmx[k]) + (tmax ? cc : 0.f);
+        }
+      }
+    }
+    if (p.occ_out) {
+      p.occ_out[(size_t)b * iplane + pix] = occ ? 1 : 0;
+      if (TRU) p.sr0_dbg[(size_t)b * iplane + pix] = sr0;
+    }
   }
-  for (int i = threadIdx.x; i < p.B; i += kThreads) finalize_pair<true>(p, i, s_pair_mm[0], s_pair_mm[1]);
+  reduce_and_finish<TRU>(p, b, acc, cmn, cmx, vmin, vmax);
 }
 
 // --------------------------------------------------------------------------- small helper kernels
@@ -493,9 +661,10 @@ __global__ void occ_fixup_kernel(uint8_t* __restrict__ occ, const float* __restr
 // --------------------------------------------------------------------------- host side
 struct Plan {
   int nseg[DPFT_MAX_LEVELS], nrt[DPFT_MAX_LEVELS], TR[DPFT_MAX_LEVELS], ctas[DPFT_MAX_LEVELS];
+  int ppt[DPFT_MAX_LEVELS], px_ctas[DPFT_MAX_LEVELS];   // materialised-gradient path: pixels per thread, CTAs per pair
   int max_ctas;
   size_t max_plane;
-  size_t off_partials, off_pairrec, off_counters, off_mm, off_gmm, off_sr0, total;
+  size_t off_partials, off_pairrec, off_counters, off_mm, off_gmm, off_sr0, off_grad, grad_elems, total;
 };
 
 // Rows per warp tile: tall tiles amortise the two halo rows, short tiles give a small level enough warps
@@ -508,7 +677,7 @@ static int pick_tile_rows(int H, int nseg, int B) {
   return (H + tiles - 1) / tiles;
 }
 
-static Plan make_plan(const dpft_level_t* lv, int n_levels, int B, uint32_t flags, bool any_occ) {
+static Plan make_plan(const dpft_level_t* lv, int n_levels, int B, int C, uint32_t flags, bool any_occ) {
   Plan pl{};
   pl.max_ctas = 1;
   pl.max_plane = 0;
@@ -519,6 +688,14 @@ static Plan make_plan(const dpft_level_t* lv, int n_levels, int B, uint32_t flag
     pl.ctas[l] = (pl.nseg[l] * pl.nrt[l] + kWarps - 1) / kWarps;
     if (pl.ctas[l] > pl.max_ctas) pl.max_ctas = pl.ctas[l];
     const size_t plane = (size_t)lv[l].H * lv[l].W;
+    {
+      const long want_threads = 148L * 2048 * 2;   // two full waves of resident threads
+      long ppt = ((long)B * (long)plane + want_threads - 1) / want_threads;
+      ppt = std::max(1L, std::min(ppt, 8L));
+      pl.ppt[l] = (int)ppt;
+      pl.px_ctas[l] = (int)((plane + (size_t)kThreads * ppt - 1) / ((size_t)kThreads * ppt));
+      if (pl.px_ctas[l] > pl.max_ctas) pl.max_ctas = pl.px_ctas[l];
+    }
     if (plane > pl.max_plane) pl.max_plane = plane;
   }
   size_t off = 0;
@@ -533,6 +710,8 @@ static Plan make_plan(const dpft_level_t* lv, int n_levels, int B, uint32_t flag
   pl.off_mm = take((size_t)2 * DPFT_MAX_LEVELS * sizeof(uint32_t));
   pl.off_gmm = take(2 * sizeof(float));
   pl.off_sr0 = take(((flags & DPFT_REMOVE_TRU_SIGMA) && any_occ) ? (size_t)B * pl.max_plane * sizeof(float) : 0);
+  pl.grad_elems = (flags & DPFT_FUSED_SOBEL) ? 0 : (size_t)B * C * pl.max_plane;
+  pl.off_grad = take(4 * pl.grad_elems * sizeof(float));
   pl.total = off;
   return pl;
 }
@@ -567,6 +746,23 @@ static cudaError_t launch_iter(const UicIterParams& prm, dim3 grid, bool tru, bo
   return cudaLaunchKernelEx(&cfg, uic_iter_kernel<CH, false>, prm);
 }
 
+template <int CH>
+static cudaError_t launch_px(const UicIterParams& prm, const PxExtra& ex, dim3 grid, bool tru, bool pdl,
+                             cudaStream_t stream) {
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = grid;
+  cfg.blockDim = dim3(kThreads);
+  cfg.dynamicSmemBytes = 0;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl ? 1 : 0;
+  if (tru) return cudaLaunchKernelEx(&cfg, uic_iter_px_kernel<CH, true>, prm, ex);
+  return cudaLaunchKernelEx(&cfg, uic_iter_px_kernel<CH, false>, prm, ex);
+}
+
 }  // namespace dpft
 
 using namespace dpft;
@@ -576,7 +772,7 @@ extern "C" size_t dpft_uic_workspace_bytes(const dpft_level_t* levels, int n_lev
   if (check_args(levels, n_levels, B, C, iters, flags)) return 0;
   bool any_occ = false;
   for (int l = 0; l < n_levels; ++l) any_occ = any_occ || levels[l].occ_out;
-  return make_plan(levels, n_levels, B, flags, any_occ).total;
+  return make_plan(levels, n_levels, B, C, flags, any_occ).total;
 }
 
 static int run_uic(const dpft_level_t* levels, int n_levels, int B, int C, int iters, uint32_t flags,
@@ -588,7 +784,7 @@ static int run_uic(const dpft_level_t* levels, int n_levels, int B, int C, int i
     return set_error(DPFT_EINVAL, "pose_in, pose_hist, sys_hist, status and workspace are required");
   bool any_occ = false;
   for (int l = 0; l < n_levels; ++l) any_occ = any_occ || levels[l].occ_out;
-  const Plan pl = make_plan(levels, n_levels, B, flags, any_occ);
+  const Plan pl = make_plan(levels, n_levels, B, C, flags, any_occ);
   if (workspace_bytes < pl.total) return set_error(DPFT_ENOSPACE, "workspace has %zu bytes, %zu needed", workspace_bytes, pl.total);
   cudaStream_t stream = (cudaStream_t)stream_;
   char* ws = (char*)workspace;
@@ -600,6 +796,8 @@ static int run_uic(const dpft_level_t* levels, int n_levels, int B, int C, int i
   float* sr0 = (float*)(ws + pl.off_sr0);
   const bool tru = flags & DPFT_REMOVE_TRU_SIGMA;
   const bool pdl = !(flags & DPFT_NO_PDL);
+  const bool fused = flags & DPFT_FUSED_SOBEL;
+  float* grad = (float*)(ws + pl.off_grad);
 
   {
     const int n = std::max(B * 12, B + 1);
@@ -617,6 +815,16 @@ static int run_uic(const dpft_level_t* levels, int n_levels, int B, int C, int i
   for (int l = 0; l < n_levels; ++l) {
     const dpft_level_t& L = levels[l];
     const size_t plane = (size_t)L.H * L.W;
+    PxExtra ex{};
+    if (!fused) {
+      // unit Sobel gradients of this level's keyframe maps, once for all its iterations
+      float* g = grad;
+      ex.gfx = g; ex.gfy = g + pl.grad_elems; ex.gsx = g + 2 * pl.grad_elems; ex.gsy = g + 3 * pl.grad_elems;
+      ex.ppt = pl.ppt[l];
+      const dim3 sg((L.W + 31) / 32, (L.H + 7) / 8, std::min(B * C, 4096));
+      sobel_unit_kernel<<<sg, 256, 0, stream>>>(L.x0, g, g + pl.grad_elems, B * C, L.H, L.W);
+      sobel_unit_kernel<<<sg, 256, 0, stream>>>(L.sigma0, g + 2 * pl.grad_elems, g + 3 * pl.grad_elems, B * C, L.H, L.W);
+    }
     for (int it = 0; it < iters; ++it, ++k) {
       UicIterParams prm{};
       prm.x0 = L.x0; prm.x1 = L.x1; prm.s0 = L.sigma0; prm.s1 = L.sigma1;
@@ -625,17 +833,26 @@ static int run_uic(const dpft_level_t* levels, int n_levels, int B, int C, int i
       prm.occ_out = L.occ_out ? L.occ_out + (size_t)it * B * plane : nullptr;
       prm.sr0_dbg = sr0;
       prm.H = L.H; prm.W = L.W; prm.B = B; prm.C = C;
-      prm.nseg = pl.nseg[l]; prm.nrt = pl.nrt[l]; prm.TR = pl.TR[l]; prm.ctas_per_pair = pl.ctas[l];
+      prm.nseg = pl.nseg[l]; prm.nrt = pl.nrt[l]; prm.TR = pl.TR[l];
+      prm.ctas_per_pair = fused ? pl.ctas[l] : pl.px_ctas[l];
       prm.pose = pose_hist + (size_t)k * B * 12;
       prm.pose_next = pose_hist + (size_t)(k + 1) * B * 12;
       prm.sys_out = sys_hist + (size_t)k * B * 27;
       prm.partials = partials; prm.pairrec = pairrec; prm.counters = counters;
       prm.s0mm = mm + 2 * l; prm.gmm = gmm; prm.status = status; prm.flags = flags;
-      const dim3 grid(pl.ctas[l], B);
+      const dim3 grid(prm.ctas_per_pair, B);
       // the debug mask pass reads what this launch wrote, so keep plain stream order around it
       const bool use_pdl = pdl && !any_occ && !ev;
       cudaError_t err;
       if (ev) cudaEventRecord(ev[k], stream);
+      if (!fused) {
+        switch (CH) {
+          case 8: err = launch_px<8>(prm, ex, grid, tru, use_pdl, stream); break;
+          case 4: err = launch_px<4>(prm, ex, grid, tru, use_pdl, stream); break;
+          case 2: err = launch_px<2>(prm, ex, grid, tru, use_pdl, stream); break;
+          default: err = launch_px<1>(prm, ex, grid, tru, use_pdl, stream); break;
+        }
+      } else
       switch (CH) {
         case 8: err = launch_iter<8>(prm, grid, tru, use_pdl, stream); break;
         case 4: err = launch_iter<4>(prm, grid, tru, use_pdl, stream); break;

@@ -45,6 +45,8 @@ extern "C" {
 #define DPFT_REMOVE_TRU_SIGMA 0x01u /* alg:1974-1979  mask pixels whose sigma sits on the batch-global min/max */
 #define DPFT_COMBINE_ICP      0x02u /* alg:668-689    add the point-to-plane term (needs depth0/depth1)        */
 #define DPFT_NO_PDL           0x04u /* launch iterations without programmatic dependent launch (debug)        */
+#define DPFT_FUSED_SOBEL      0x08u /* recompute the unit Sobel gradients inside every iteration (sliding register
+                                       window) instead of materialising them once per level                    */
 
 /* status bits written to *status (device int32, OR-ed; zero it before the call) */
 #define DPFT_ST_NONFINITE 0x01 /* a weighted residual / normal-equation entry was NaN or Inf (alg:886,1988) */

@@ -1,0 +1,10 @@
+#!/bin/bash
+# parity tests, then the bench on both forward paths
+python -m pytest tests -m gpu -x -q 2>&1 | tail -3
+for extra in "" "--fused-sobel"; do
+  echo "=== bench $extra"
+  python bench.py --steps 100 --warmup 5 --no-cpu-baseline $extra 2>/dev/null | python -c "
+import json,sys
+d=json.loads(sys.stdin.read()); r=d['roofline']
+print('pairs/s %.0f  ms/step %.3f  lvl0 launch %.1f us  frac %.3f  launches(us) %s' % (d['value'], d['ms_per_step'], r['launch_ms']*1e3, r['frac'], [round(x*1e3) for x in r['all_launch_ms']]))"
+done
