@@ -17,7 +17,7 @@ PKG_DIR = os.path.dirname(os.path.abspath(__file__))
 REPO_DIR = os.path.dirname(PKG_DIR)
 CSRC = os.path.join(PKG_DIR, "csrc")
 LIB_PATH = os.path.join(PKG_DIR, "libdpft.so")
-SOURCES = ["dpft_abi.cu", "uic_forward.cu"]
+SOURCES = ["dpft_abi.cu", "uic_forward.cu", "uic_backward.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "-Xcompiler", "-fPIC", "-shared"]
 
@@ -45,6 +45,11 @@ class DpftLevel(ctypes.Structure):
         ("occ_out", ctypes.c_void_p),
         ("H", ctypes.c_int32), ("W", ctypes.c_int32),
     ]
+
+
+class DpftLevelGrad(ctypes.Structure):
+    """struct dpft_level_grad (include/dpft.h)."""
+    _fields_ = [("g_x0", c_float_p), ("g_x1", c_float_p), ("g_sigma0", c_float_p), ("g_sigma1", c_float_p)]
 
 
 def _nvcc() -> str:
@@ -102,9 +107,16 @@ def lib() -> ctypes.CDLL:
     L.dpft_uic_forward.argtypes = [ctypes.POINTER(DpftLevel), ctypes.c_int, ctypes.c_int, ctypes.c_int,
                                    ctypes.c_int, ctypes.c_uint32, ctypes.c_float, ctypes.c_void_p,
                                    ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p,
-                                   ctypes.c_size_t, ctypes.c_void_p]
+                                   ctypes.c_void_p, ctypes.c_size_t, ctypes.c_void_p]
     L.dpft_uic_forward_timed.restype = ctypes.c_int
     L.dpft_uic_forward_timed.argtypes = L.dpft_uic_forward.argtypes + [ctypes.POINTER(ctypes.c_float)]
+    L.dpft_uic_backward_workspace_bytes.restype = ctypes.c_size_t
+    L.dpft_uic_backward_workspace_bytes.argtypes = L.dpft_uic_workspace_bytes.argtypes
+    L.dpft_uic_backward.restype = ctypes.c_int
+    L.dpft_uic_backward.argtypes = [ctypes.POINTER(DpftLevel), ctypes.POINTER(DpftLevelGrad), ctypes.c_int,
+                                    ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_uint32, ctypes.c_void_p,
+                                    ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p,
+                                    ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_void_p]
     if L.dpft_abi_version() != DPFT_ABI_VERSION:
         raise RuntimeError("libdpft.so ABI version mismatch; rebuild")
     _lib = L
@@ -114,7 +126,7 @@ def lib() -> ctypes.CDLL:
 def exported_symbols() -> List[str]:
     """Entry points include/dpft.h declares (kept in sync by tests/test_abi.py)."""
     return ["dpft_abi_version", "dpft_last_error", "dpft_uic_workspace_bytes", "dpft_uic_forward",
-            "dpft_uic_forward_timed"]
+            "dpft_uic_forward_timed", "dpft_uic_backward_workspace_bytes", "dpft_uic_backward"]
 
 
 def check(code: int, what: str) -> None:

@@ -62,10 +62,11 @@ def unpack_system(sys_rows: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
 
 class SolveResult:
     """What one call into the library hands back (all device tensors, nothing synchronised)."""
-    __slots__ = ("pose_hist", "sys_hist", "status", "occ", "n_levels", "iters", "launch_ms")
+    __slots__ = ("pose_hist", "sys_hist", "aux_hist", "status", "occ", "n_levels", "iters", "launch_ms")
 
-    def __init__(self, pose_hist, sys_hist, status, occ, n_levels, iters, launch_ms=None):
-        self.pose_hist, self.sys_hist, self.status, self.occ = pose_hist, sys_hist, status, occ
+    def __init__(self, pose_hist, sys_hist, aux_hist, status, occ, n_levels, iters, launch_ms=None):
+        self.pose_hist, self.sys_hist, self.aux_hist = pose_hist, sys_hist, aux_hist
+        self.status, self.occ = status, occ
         self.n_levels, self.iters, self.launch_ms = n_levels, iters, launch_ms
 
     @property
@@ -86,7 +87,7 @@ class SolveResult:
 
 
 def uic_solve(levels: Sequence[Dict[str, torch.Tensor]], pose: Pose, *, iters: int = 3,
-              remove_tru_sigma: bool = False, want_occ: bool = False, pdl: bool = True, timed: bool = False, fused_sobel: bool = False,
+              remove_tru_sigma: bool = False, want_occ: bool = False, pdl: bool = True, timed: bool = False, fused_sobel: bool = True,
               obj_mask0: Optional[Sequence] = None, obj_mask1: Optional[Sequence] = None) -> SolveResult:
     """Coarse-to-fine U_IC solve of a batch of frame pairs on the current CUDA stream.
 
@@ -131,6 +132,7 @@ def uic_solve(levels: Sequence[Dict[str, torch.Tensor]], pose: Pose, *, iters: i
     pose_in = pack_pose(pose).to(dev)
     pose_hist = torch.empty((n_it + 1, B, 12), dtype=torch.float32, device=dev)
     sys_hist = torch.empty((max(n_it, 1), B, 27), dtype=torch.float32, device=dev)
+    aux_hist = torch.zeros((max(n_it, 1), 4), dtype=torch.float32, device=dev)
     status = torch.zeros((1,), dtype=torch.int32, device=dev)
     ws_bytes = L.dpft_uic_workspace_bytes(arr, n_levels, B, C, iters, flags)
     if ws_bytes == 0:
@@ -139,7 +141,7 @@ def uic_solve(levels: Sequence[Dict[str, torch.Tensor]], pose: Pose, *, iters: i
     stream = torch.cuda.current_stream(dev).cuda_stream
     launch_ms = None
     args = (arr, n_levels, B, C, iters, flags, ctypes.c_float(0.01), pose_in.data_ptr(), pose_hist.data_ptr(),
-            sys_hist.data_ptr(), status.data_ptr(), ws.data_ptr(), ws_bytes, stream)
+            sys_hist.data_ptr(), aux_hist.data_ptr(), status.data_ptr(), ws.data_ptr(), ws_bytes, stream)
     with torch.cuda.device(dev):
         if timed:   # measurement aid (bench.py): per-launch device times, synchronises the stream
             buf = (ctypes.c_float * n_it)()
@@ -149,7 +151,107 @@ def uic_solve(levels: Sequence[Dict[str, torch.Tensor]], pose: Pose, *, iters: i
             code = L.dpft_uic_forward(*args)
     _lib.check(code, "dpft_uic_forward")
     del keep   # launches are queued on the allocating stream; the caching allocator orders reuse after them
-    return SolveResult(pose_hist, sys_hist[:n_it], status, occ, n_levels, iters, launch_ms)
+    return SolveResult(pose_hist, sys_hist[:n_it], aux_hist[:n_it], status, occ, n_levels, iters, launch_ms)
+
+
+# ----------------------------------------------------------------------------- autograd
+def _level_array(levels, B, C, obj_mask0=None, obj_mask1=None):
+    """ctypes array of dpft_level for already-converted device tensors; returns (array, keep-alive list)."""
+    arr = (_lib.DpftLevel * len(levels))()
+    keep = []
+    for i, lv in enumerate(levels):
+        t = {k: _dev_f32(lv[k], k) for k in ("x0", "x1", "s0", "s1", "invD0", "invD1", "K")}
+        m0 = _dev_mask(obj_mask0[i] if obj_mask0 is not None else None, "obj_mask0")
+        m1 = _dev_mask(obj_mask1[i] if obj_mask1 is not None else None, "obj_mask1")
+        keep += [t, m0, m1]
+        a = arr[i]
+        a.x0, a.x1, a.sigma0, a.sigma1 = (t[k].data_ptr() for k in ("x0", "x1", "s0", "s1"))
+        a.invd0, a.invd1, a.K = t["invD0"].data_ptr(), t["invD1"].data_ptr(), t["K"].data_ptr()
+        a.obj_mask0 = m0.data_ptr() if m0 is not None else None
+        a.obj_mask1 = m1.data_ptr() if m1 is not None else None
+        a.H, a.W = int(t["x0"].shape[2]), int(t["x0"].shape[3])
+    return arr, keep
+
+
+class _UicSolveFn(torch.autograd.Function):
+    """Differentiable coarse-to-fine U_IC solve.  Inputs: (cfg, R, t, x0_0, x1_0, s0_0, s1_0, x0_1, ...);
+    outputs: per level (R_l, t_l, JtWJ_l).  Backward calls dpft_uic_backward (recompute-based)."""
+
+    @staticmethod
+    def forward(ctx, cfg, R, t, *maps):
+        n_levels = len(cfg["static"])
+        levels = []
+        for i, st in enumerate(cfg["static"]):
+            x0, x1, s0, s1 = maps[4 * i:4 * i + 4]
+            levels.append(dict(x0=x0.detach(), x1=x1.detach(), s0=s0.detach(), s1=s1.detach(), **st))
+        res = uic_solve(levels, (R.detach(), t.detach()), iters=cfg["iters"], remove_tru_sigma=cfg["tru"],
+                        obj_mask0=cfg.get("obj_mask0"), obj_mask1=cfg.get("obj_mask1"))
+        if cfg.get("check", True):
+            res.raise_if_bad()
+        ctx.cfg, ctx.res, ctx.levels = cfg, res, levels
+        outs = []
+        for l in range(n_levels):
+            Rl, tl = res.level_pose(l)
+            A, _ = unpack_system(res.sys_hist[(l + 1) * cfg["iters"] - 1])
+            outs += [Rl.contiguous(), tl.contiguous(), A]
+        return tuple(outs)
+
+    @staticmethod
+    def backward(ctx, *gouts):
+        cfg, res, levels = ctx.cfg, ctx.res, ctx.levels
+        L = _lib.lib()
+        n_levels, iters = len(levels), cfg["iters"]
+        x0 = levels[0]["x0"]
+        B, C, dev = int(x0.shape[0]), int(x0.shape[1]), x0.device
+        n_it = n_levels * iters
+        gpose = torch.zeros((n_it + 1, B, 12), dtype=torch.float32, device=dev)
+        gA = None
+        for l in range(n_levels):
+            gR, gt, gAl = gouts[3 * l:3 * l + 3]
+            row = gpose[(l + 1) * iters]
+            if gR is not None:
+                row[:, :9] += gR.reshape(B, 9)
+            if gt is not None:
+                row[:, 9:] += gt.reshape(B, 3)
+            if gAl is not None:
+                if gA is None:
+                    gA = torch.zeros((n_levels, B, 36), dtype=torch.float32, device=dev)
+                gA[l] = gAl.reshape(B, 36)
+        arr, keep = _level_array(levels, B, C, cfg.get("obj_mask0"), cfg.get("obj_mask1"))
+        garr = (_lib.DpftLevelGrad * n_levels)()
+        gmaps = []
+        for i, lv in enumerate(levels):
+            g = [torch.zeros_like(lv["x0"], dtype=torch.float32, memory_format=torch.contiguous_format) for _ in range(4)]
+            gmaps += g
+            garr[i].g_x0, garr[i].g_x1, garr[i].g_sigma0, garr[i].g_sigma1 = (x.data_ptr() for x in g)
+        flags = _lib.DPFT_REMOVE_TRU_SIGMA if cfg["tru"] else 0
+        gin = torch.empty((B, 12), dtype=torch.float32, device=dev)
+        ws_bytes = L.dpft_uic_backward_workspace_bytes(arr, n_levels, B, C, iters, flags)
+        ws = torch.empty((ws_bytes,), dtype=torch.uint8, device=dev)
+        with torch.cuda.device(dev):
+            code = L.dpft_uic_backward(arr, garr, n_levels, B, C, iters, flags, res.pose_hist.data_ptr(),
+                                       res.sys_hist.data_ptr(), res.aux_hist.data_ptr(), gpose.data_ptr(),
+                                       gA.data_ptr() if gA is not None else None, gin.data_ptr(), ws.data_ptr(),
+                                       ws_bytes, torch.cuda.current_stream(dev).cuda_stream)
+        _lib.check(code, "dpft_uic_backward")
+        del keep
+        return (None, gin[:, :9].reshape(B, 3, 3), gin[:, 9:].contiguous(), *gmaps)
+
+
+def uic_track(levels: Sequence[Dict[str, torch.Tensor]], pose: Pose, *, iters: int = 3, remove_tru_sigma: bool = False,
+              obj_mask0=None, obj_mask1=None, check: bool = True):
+    """Differentiable coarse-to-fine solve: returns [(R_l, t_l, JtWJ_l) for every level], coarse first.
+    Gradients flow to x0, x1, s0, s1 of every level and to the starting pose (train.py's loss sums over the
+    per-level poses, criterions.py:101-136)."""
+    static = [dict(invD0=lv["invD0"], invD1=lv["invD1"], K=lv["K"]) for lv in levels]
+    cfg = dict(static=static, iters=iters, tru=remove_tru_sigma, obj_mask0=obj_mask0, obj_mask1=obj_mask1, check=check)
+    R, t = pose
+    B = R.shape[0]
+    maps = []
+    for lv in levels:
+        maps += [lv["x0"], lv["x1"], lv["s0"], lv["s1"]]
+    outs = _UicSolveFn.apply(cfg, R, t.reshape(B, 3), *maps)
+    return [tuple(outs[3 * l:3 * l + 3]) for l in range(len(levels))]
 
 
 # ----------------------------------------------------------------------------- reference-shaped modules
@@ -180,17 +282,23 @@ class TrustRegionInverseWUncertainty(nn.Module):
         assert sigma0 is not None and sigma1 is not None
         if self.combine_icp:
             raise NotImplementedError("combine_icp: the ICP term is not built yet (DESIGN.md, 'next')")
-        if torch.is_grad_enabled() and any(t.requires_grad for t in (x0, x1, sigma0, sigma1, pose10[0], pose10[1])):
-            raise NotImplementedError("backward kernels are not built yet (DESIGN.md, 'next')")
         if self.timers: self.timers.tic('trust-region level solve (fused CUDA)')
         lv = dict(x0=x0, x1=x1, s0=sigma0, s1=sigma1, invD0=invD0, invD1=invD1, K=K)
+        weights = torch.ones((1, 1, 1, 1), dtype=x0.dtype, device=x0.device).expand(x0.shape)
+        if torch.is_grad_enabled() and any(t.requires_grad for t in (x0, x1, sigma0, sigma1, pose10[0], pose10[1])):
+            # training: same kernels, recorded for autograd (backward = dpft_uic_backward)
+            (R, t, A), = uic_track([lv], (pose10[0], pose10[1]), iters=self.max_iterations,
+                                   remove_tru_sigma=self.remove_tru_sigma,
+                                   obj_mask0=None if obj_mask0 is None else [obj_mask0],
+                                   obj_mask1=None if obj_mask1 is None else [obj_mask1], check=self.check_nan)
+            if self.timers: self.timers.toc('trust-region level solve (fused CUDA)')
+            return ((R, t), weights, A) if self.uncer_prop else ((R, t), weights)
         res = uic_solve([lv], pose10, iters=self.max_iterations, remove_tru_sigma=self.remove_tru_sigma,
                         obj_mask0=None if obj_mask0 is None else [obj_mask0],
                         obj_mask1=None if obj_mask1 is None else [obj_mask1])
         if self.check_nan:
             res.raise_if_bad()
         if self.timers: self.timers.toc('trust-region level solve (fused CUDA)')
-        weights = torch.ones((1, 1, 1, 1), dtype=x0.dtype, device=x0.device).expand(x0.shape)
         if self.uncer_prop:
             A, _ = unpack_system(res.sys_hist[-1])
             return res.pose, weights, A

@@ -1,0 +1,499 @@
+// U_IC backward: reverse-mode through the unrolled Gauss-Newton iterations, recompute-based.
+//
+// The forward saves only the pose before every iteration (pose_hist), the reduced normal equations
+// (sys_hist) and the batch-global sigma extremes (aux_hist); everything per-pixel is recomputed here from
+// the inputs.  For iteration k, walking k = last .. 0:
+//
+//   pose_bwd_kernel   (one thread per pair, fp64)  d/d(pose_{k+1}) -> d/d(xi) through compose, Rodrigues
+//                     and the damped solve; emits lambda = H^-1 d(xi) and M = Abar + Abar^T with
+//                     Abar = -lambda xi^T + 1e-6 tr(.) I  (+ an external gradient on J^T W J), and the
+//                     part of d/d(pose_k) that flows through R <- R dR, t <- R dt + t.
+//   uic_bwd_px_kernel (one thread per pixel)       with J_c = a_c ju + b_c jv the gradient of the loss
+//                     w.r.t. (a_c, b_c, wres_c) needs only five per-pixel scalars of (M, lambda, ju, jv);
+//                     from there back through the residual / sigma / bilinear lookup into x0, sigma0,
+//                     their unit Sobel gradients (accumulated, turned into x0 / sigma0 gradients once per
+//                     level by sobel_unit_bwd_kernel), scattered into x1 / sigma1 (red.global.add), and
+//                     through (u,v) into the pose (12 sums per pair).
+//
+// Mirrors what torch.autograd derives from reference code/models/algorithms.py:611-723:
+// masks and the 1e-6 fill are stop-gradients (masked pixels pass nothing through wres but still through J).
+#include <cuda_runtime.h>
+#include <math_constants.h>
+#include <stdint.h>
+
+#include <algorithm>
+
+#include "dpft.h"
+#include "dpft_device.cuh"
+#include "dpft_host.h"
+#include "dpft_kernels.h"
+
+namespace dpft {
+
+constexpr int kBT = 128;   // threads per CTA of the pixel kernel
+
+struct BwdParams {
+  const float *x0, *x1, *s0, *s1, *d0, *d1, *K;
+  const uint8_t *m0, *m1;
+  const float *gfx, *gfy, *gsx, *gsy;        // unit Sobel gradients of x0 / sigma0 (recomputed per level)
+  float *g_x0, *g_x1, *g_s0, *g_s1;          // OUT (accumulated): gradients of the four maps
+  float *g_gfx, *g_gfy, *g_gsx, *g_gsy;      // accumulated gradients w.r.t. the unit Sobel gradients
+  int H, W, B, C, ppt;
+  const float* pose;     // (B,12) pose the iteration linearised at
+  const float* mlam;     // (B,27) 21 upper-triangular entries of M, then lambda
+  const float* aux;      // [4] gmin, gmax of the warped sigma, min, max of sigma0 (this iteration)
+  float* gpose;          // (B,12) accumulated d/d(pose_k)
+};
+
+template <int CH, bool TRU>
+__global__ void __launch_bounds__(kBT, 4) uic_bwd_px_kernel(const BwdParams p) {
+  __shared__ float s_red[kBT / 32][12];
+  const int b = blockIdx.y;
+  const int H = p.H, W = p.W, C = p.C;
+  const int iplane = H * W;
+  const float fx = __ldg(p.K + 4 * b), fy = __ldg(p.K + 4 * b + 1);
+  const float cx = __ldg(p.K + 4 * b + 2), cy = __ldg(p.K + 4 * b + 3);
+  const size_t pair_off = (size_t)b * C * iplane;
+  const float* d0p = p.d0 + (size_t)b * iplane;
+  const float* d1p = p.d1 + (size_t)b * iplane;
+  const uint8_t* m0p = p.m0 ? p.m0 + (size_t)b * iplane : nullptr;
+  const uint8_t* m1p = p.m1 ? p.m1 + (size_t)b * iplane : nullptr;
+  const Pose pose = load_pose(p.pose + (size_t)b * 12);
+  float M[21], lam[6];
+#pragma unroll
+  for (int i = 0; i < 21; ++i) M[i] = __ldg(p.mlam + (size_t)b * 27 + i);
+#pragma unroll
+  for (int i = 0; i < 6; ++i) lam[i] = __ldg(p.mlam + (size_t)b * 27 + 21 + i);
+  float gmin = 0.f, gmax = 0.f, s0lo = 0.f, s0hi = 0.f;
+  if (TRU) {
+    gmin = __ldg(p.aux);
+    gmax = __ldg(p.aux + 1);
+    s0lo = __ldg(p.aux + 2);
+    s0hi = __ldg(p.aux + 3);
+  }
+  float gR[9], gt[3];
+#pragma unroll
+  for (int i = 0; i < 9; ++i) gR[i] = 0.f;
+#pragma unroll
+  for (int i = 0; i < 3; ++i) gt[i] = 0.f;
+
+  for (int i = 0; i < p.ppt; ++i) {
+    const int pix = (blockIdx.x * p.ppt + i) * kBT + threadIdx.x;
+    if (pix >= iplane) break;
+    const int y = pix / W, x = pix - y * W;
+    const float px = xdiv(xsub((float)x, cx), fx), py = xdiv(xsub((float)y, cy), fy);
+    const float d0 = __ldg(d0p + pix);
+    // forward geometry, same arithmetic as the forward kernels (the mask must come out identical)
+    float w[3];
+#pragma unroll
+    for (int k = 0; k < 3; ++k)
+      w[k] = xadd(xadd(xadd(xmul(pose.r[3 * k], px), xmul(pose.r[3 * k + 1], py)), pose.r[3 * k + 2]), xmul(pose.t[k], d0));
+    const float u = xadd(xmul(xdiv(w[0], w[2]), fx), cx);
+    const float v = xadd(xmul(xdiv(w[1], w[2]), fy), cy);
+    const float inv_z = xdiv(d0, w[2]);
+    const Tap tap = make_tap(u, v, H, W);
+    const float d1w = sample_exact(d1p, tap, W);
+    bool occ = occluded(u, v, inv_z, d1w, H, W);
+    if (m0p) occ = occ || (__ldg(m0p + pix) == 0);
+    if (m1p) occ = occ || !(sample_mask(m1p, tap, W) > 0.f);
+    if (TRU) {
+      const float s0c0 = __ldg(p.s0 + pair_off + pix);
+      occ = occ || (s0c0 == s0lo) || (s0c0 == s0hi);
+      const float sr0 = sample_exact(p.s1 + pair_off, tap, W);
+      occ = occ || (sr0 == gmin) || (sr0 == gmax);
+    }
+    // five scalars carry (M, lambda) to the per-channel level: with J = a ju + b jv,
+    //   d/da = a ju'M ju + b ju'M jv + wm lambda.ju,  d/db = a ju'M jv + b jv'M jv + wm lambda.jv,
+    //   d/dwm = a lambda.ju + b lambda.jv
+    float ju[6], jv[6];
+    warp_rows(px, py, d0, fx, fy, ju, jv);
+    float Mu[6], Mv[6];
+#pragma unroll
+    for (int r = 0; r < 6; ++r) {
+      float su = 0.f, sv = 0.f;
+#pragma unroll
+      for (int c = 0; c < 6; ++c) {
+        const float m = M[r <= c ? tri(r, c) : tri(c, r)];
+        su = fmaf(m, ju[c], su);
+        sv = fmaf(m, jv[c], sv);
+      }
+      Mu[r] = su;
+      Mv[r] = sv;
+    }
+    float muu = 0.f, muv = 0.f, mvv = 0.f, lu = 0.f, lv = 0.f;
+#pragma unroll
+    for (int r = 0; r < 6; ++r) {
+      muu = fmaf(ju[r], Mu[r], muu);
+      muv = fmaf(ju[r], Mv[r], muv);
+      mvv = fmaf(jv[r], Mv[r], mvv);
+      lu = fmaf(lam[r], ju[r], lu);
+      lv = fmaf(lam[r], jv[r], lv);
+    }
+    // is the sample position strictly inside the clip range?  (grid_sampler gives zero coordinate
+    // gradient on and outside the border)
+    const float ixu = xmul(xmul(xadd(xsub(xdiv(u, 0.5f * (float)(W - 1)), 1.f), 1.f), 0.5f), (float)(W - 1));
+    const float iyu = xmul(xmul(xadd(xsub(xdiv(v, 0.5f * (float)(H - 1)), 1.f), 1.f), 0.5f), (float)(H - 1));
+    const bool in_x = ixu > 0.f && ixu < (float)(W - 1), in_y = iyu > 0.f && iyu < (float)(H - 1);
+    // fractional weights along each axis (wa = txl*tyn, wb = txr*tyn, wc = txl*tys, wd = txr*tys)
+    const float tyn = tap.wa + tap.wb, tys = tap.wc + tap.wd, txl = tap.wa + tap.wc, txr = tap.wb + tap.wd;
+    float g_ix = 0.f, g_iy = 0.f;
+
+    for (int c0 = 0; c0 < C; c0 += CH) {
+#pragma unroll
+      for (int c = 0; c < CH; ++c) {
+        const size_t k0 = pair_off + (size_t)(c0 + c) * iplane + pix;
+        const size_t k1 = pair_off + (size_t)(c0 + c) * iplane + tap.o;
+        const float f0 = __ldg(p.x0 + k0), s0v = __ldg(p.s0 + k0);
+        const float gfx = __ldg(p.gfx + k0), gfy = __ldg(p.gfy + k0), gsx = __ldg(p.gsx + k0), gsy = __ldg(p.gsy + k0);
+        const float xa = __ldg(p.x1 + k1), xb = __ldg(p.x1 + k1 + 1), xc = __ldg(p.x1 + k1 + W), xd = __ldg(p.x1 + k1 + W + 1);
+        const float za = __ldg(p.s1 + k1), zb = __ldg(p.s1 + k1 + 1), zc = __ldg(p.s1 + k1 + W), zd = __ldg(p.s1 + k1 + W + 1);
+        // forward quantities
+        const float fr = blend_fast(xa, xb, xc, xd, tap);
+        const float sr = TRU ? blend_exact(za, zb, zc, zd, tap) : blend_fast(za, zb, zc, zd, tap);
+        const float res = fr - f0;
+        const float rs = rsqrtf(fmaf(sr, sr, s0v * s0v));
+        const float rs3 = rs * rs * rs;
+        const float wres = res * rs;
+        const float q = res * s0v * rs3;
+        const float a = fmaf(gfx, rs, q * gsx);
+        const float bq = fmaf(gfy, rs, q * gsy);
+        const float wm = occ ? 1e-6f : wres;
+        // reverse
+        const float ga = fmaf(a, muu, fmaf(bq, muv, wm * lu));
+        const float gb = fmaf(a, muv, fmaf(bq, mvv, wm * lv));
+        const float gwres = occ ? 0.f : fmaf(a, lu, bq * lv);
+        const float gq = fmaf(ga, gsx, gb * gsy);
+        float grs = fmaf(ga, gfx, gb * gfy);                       // via a, b
+        float gres = fmaf(gq, s0v * rs3, gwres * rs);              // via q, wres
+        float gs0 = gq * res * rs3;                                // via q
+        grs = fmaf(3.f * gq, res * s0v * rs * rs, grs);            // q ~ rs^3
+        grs = fmaf(gwres, res, grs);                               // wres = res rs
+        const float gsr = -grs * rs3 * sr;                         // rs = (sr^2 + s0^2)^-1/2
+        gs0 = fmaf(-grs * rs3, s0v, gs0);
+        // own-pixel accumulations (this thread is the only writer of these elements in this launch)
+        p.g_gfx[k0] += ga * rs;
+        p.g_gfy[k0] += gb * rs;
+        p.g_gsx[k0] += ga * q;
+        p.g_gsy[k0] += gb * q;
+        p.g_x0[k0] -= gres;
+        p.g_s0[k0] += gs0;
+        // bilinear adjoint: scatter into the live frame's maps
+        atomicAdd(p.g_x1 + k1, tap.wa * gres);
+        atomicAdd(p.g_x1 + k1 + 1, tap.wb * gres);
+        atomicAdd(p.g_x1 + k1 + W, tap.wc * gres);
+        atomicAdd(p.g_x1 + k1 + W + 1, tap.wd * gres);
+        atomicAdd(p.g_s1 + k1, tap.wa * gsr);
+        atomicAdd(p.g_s1 + k1 + 1, tap.wb * gsr);
+        atomicAdd(p.g_s1 + k1 + W, tap.wc * gsr);
+        atomicAdd(p.g_s1 + k1 + W + 1, tap.wd * gsr);
+        // and into the sample position
+        g_ix = fmaf(gres, fmaf(xb - xa, tyn, (xd - xc) * tys), g_ix);
+        g_iy = fmaf(gres, fmaf(xc - xa, txl, (xd - xb) * txr), g_iy);
+        g_ix = fmaf(gsr, fmaf(zb - za, tyn, (zd - zc) * tys), g_ix);
+        g_iy = fmaf(gsr, fmaf(zc - za, txl, (zd - zb) * txr), g_iy);
+      }
+    }
+    // (u,v) -> w = R ray + t d0 -> pose
+    const float gu = in_x ? g_ix : 0.f, gv = in_y ? g_iy : 0.f;
+    const float iz = 1.f / w[2];
+    const float gw0 = gu * fx * iz, gw1 = gv * fy * iz;
+    const float gw2 = -(gw0 * w[0] + gw1 * w[1]) * iz;
+    const float gw[3] = {gw0, gw1, gw2};
+#pragma unroll
+    for (int r = 0; r < 3; ++r) {
+      gR[3 * r] = fmaf(gw[r], px, gR[3 * r]);
+      gR[3 * r + 1] = fmaf(gw[r], py, gR[3 * r + 1]);
+      gR[3 * r + 2] += gw[r];
+      gt[r] = fmaf(gw[r], d0, gt[r]);
+    }
+  }
+  // 12 pose-gradient sums: warp shuffle, then one atomic per CTA and entry
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+  for (int i = 0; i < 12; ++i) {
+    float s = i < 9 ? gR[i] : gt[i - 9];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if (lane == 0) s_red[warp][i] = s;
+  }
+  __syncthreads();
+  if (threadIdx.x < 12) {
+    float s = 0.f;
+#pragma unroll
+    for (int wq = 0; wq < kBT / 32; ++wq) s += s_red[wq][threadIdx.x];
+    atomicAdd(p.gpose + (size_t)b * 12 + threadIdx.x, s);
+  }
+}
+
+// d/d(pose_{k+1}) -> (M, lambda) of iteration k and the compose part of d/d(pose_k).  One thread per pair.
+__global__ void pose_bwd_kernel(const float* __restrict__ sys, const float* __restrict__ pose_k,
+                                const float* __restrict__ gpose_next, const float* __restrict__ gA_ext,
+                                float* __restrict__ gpose_k, float* __restrict__ mlam, int B) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= B) return;
+  double A[21], rhs[6];
+  for (int i = 0; i < 21; ++i) A[i] = (double)sys[(size_t)b * 27 + i];
+  for (int i = 0; i < 6; ++i) rhs[i] = (double)sys[(size_t)b * 27 + 21 + i];
+  double tr = 0.0;
+  for (int i = 0; i < 6; ++i) tr += A[tri(i, i)];
+  const double eps = tr * 1e-6;
+  double L[6][6];
+  for (int j = 0; j < 6; ++j) {
+    double s = A[tri(j, j)] + eps;
+    for (int k = 0; k < j; ++k) s -= L[j][k] * L[j][k];
+    const double d = sqrt(s);
+    L[j][j] = d;
+    for (int i = j + 1; i < 6; ++i) {
+      double v = A[tri(j, i)];
+      for (int k = 0; k < j; ++k) v -= L[i][k] * L[j][k];
+      L[i][j] = v / d;
+    }
+  }
+  auto chol_solve = [&](const double* r, double* out) {
+    double z[6];
+    for (int i = 0; i < 6; ++i) {
+      double v = r[i];
+      for (int k = 0; k < i; ++k) v -= L[i][k] * z[k];
+      z[i] = v / L[i][i];
+    }
+    for (int i = 5; i >= 0; --i) {
+      double v = z[i];
+      for (int k = i + 1; k < 6; ++k) v -= L[k][i] * out[k];
+      out[i] = v / L[i][i];
+    }
+  };
+  double xi[6];
+  chol_solve(rhs, xi);
+  // forward: w = -xi_w, theta = |w|, k = w/theta, dR = I + K s + K^2 c1, dt = -dR xi_v
+  const double w[3] = {-xi[0], -xi[1], -xi[2]};
+  const double th = sqrt(w[0] * w[0] + w[1] * w[1] + w[2] * w[2]);
+  const double kv[3] = {w[0] / th, w[1] / th, w[2] / th};
+  const double s = sin(th), c = cos(th), c1 = 1.0 - c;
+  const double Kx[9] = {0, -kv[2], kv[1], kv[2], 0, -kv[0], -kv[1], kv[0], 0};
+  double K2[9], dR[9];
+  for (int i = 0; i < 3; ++i)
+    for (int j = 0; j < 3; ++j) {
+      double kk = 0;
+      for (int m = 0; m < 3; ++m) kk += Kx[3 * i + m] * Kx[3 * m + j];
+      K2[3 * i + j] = kk;
+      dR[3 * i + j] = (i == j ? 1.0 : 0.0) + Kx[3 * i + j] * s + kk * c1;
+    }
+  double dt[3];
+  for (int i = 0; i < 3; ++i) dt[i] = -(dR[3 * i] * xi[3] + dR[3 * i + 1] * xi[4] + dR[3 * i + 2] * xi[5]);
+  double R[9], GR[9], Gt[3];
+  for (int i = 0; i < 9; ++i) {
+    R[i] = (double)pose_k[(size_t)b * 12 + i];
+    GR[i] = (double)gpose_next[(size_t)b * 12 + i];
+  }
+  for (int i = 0; i < 3; ++i) Gt[i] = (double)gpose_next[(size_t)b * 12 + 9 + i];
+  // R' = R dR, t' = R dt + t
+  double gRk[9], gdR[9], gdt[3];
+  for (int i = 0; i < 3; ++i)
+    for (int j = 0; j < 3; ++j) {
+      double a = 0, bb = 0;
+      for (int m = 0; m < 3; ++m) {
+        a += GR[3 * i + m] * dR[3 * j + m];      // GR dR^T
+        bb += R[3 * m + i] * GR[3 * m + j];      // R^T GR
+      }
+      gRk[3 * i + j] = a + Gt[i] * dt[j];
+      gdR[3 * i + j] = bb;
+    }
+  for (int i = 0; i < 3; ++i) gdt[i] = R[i] * Gt[0] + R[3 + i] * Gt[1] + R[6 + i] * Gt[2];
+  // dt = -dR xi_v
+  double gxi[6];
+  for (int i = 0; i < 3; ++i)
+    for (int j = 0; j < 3; ++j) gdR[3 * i + j] -= gdt[i] * xi[3 + j];
+  for (int j = 0; j < 3; ++j) gxi[3 + j] = -(dR[j] * gdt[0] + dR[3 + j] * gdt[1] + dR[6 + j] * gdt[2]);
+  // Rodrigues
+  double g_s = 0, g_c1 = 0, gK[9];
+  for (int i = 0; i < 9; ++i) {
+    g_s += gdR[i] * Kx[i];
+    g_c1 += gdR[i] * K2[i];
+  }
+  for (int i = 0; i < 3; ++i)
+    for (int j = 0; j < 3; ++j) {
+      double a = 0;
+      for (int m = 0; m < 3; ++m) a += gdR[3 * i + m] * Kx[3 * j + m] + Kx[3 * m + i] * gdR[3 * m + j];   // G K^T + K^T G
+      gK[3 * i + j] = gdR[3 * i + j] * s + c1 * a;
+    }
+  const double gk[3] = {gK[7] - gK[5], gK[2] - gK[6], gK[3] - gK[1]};
+  double g_th = g_s * c + g_c1 * s;
+  double gw[3];
+  const double kdotw = gk[0] * w[0] + gk[1] * w[1] + gk[2] * w[2];
+  g_th -= kdotw / (th * th);
+  for (int i = 0; i < 3; ++i) gw[i] = gk[i] / th + g_th * w[i] / th;
+  for (int i = 0; i < 3; ++i) gxi[i] = -gw[i];
+  // xi = H^-1 rhs:  lambda = H^-1 gxi, Hbar = -lambda xi^T;  H = A + 1e-6 tr(A) I
+  double lam[6];
+  chol_solve(gxi, lam);
+  double trH = 0;
+  for (int i = 0; i < 6; ++i) trH += -lam[i] * xi[i];
+  float* out = mlam + (size_t)b * 27;
+  for (int i = 0; i < 6; ++i)
+    for (int j = i; j < 6; ++j) {
+      double m = -(lam[i] * xi[j] + lam[j] * xi[i]);
+      if (i == j) m += 2.0 * 1e-6 * trH;
+      if (gA_ext) m += (double)gA_ext[(size_t)b * 36 + 6 * i + j] + (double)gA_ext[(size_t)b * 36 + 6 * j + i];
+      out[tri(i, j)] = (float)m;
+    }
+  for (int i = 0; i < 6; ++i) out[21 + i] = (float)lam[i];
+  for (int i = 0; i < 9; ++i) gpose_k[(size_t)b * 12 + i] += (float)gRk[i];
+  for (int i = 0; i < 3; ++i) gpose_k[(size_t)b * 12 + 9 + i] += (float)Gt[i];
+}
+
+// Adjoint of g = S / sqrt(|S|^2 + 1e-8), S = replicate-padded Sobel of img: scatters into g_img.
+__global__ void __launch_bounds__(256) sobel_unit_bwd_kernel(const float* __restrict__ img, const float* __restrict__ ggx,
+                                                             const float* __restrict__ ggy, float* __restrict__ g_img,
+                                                             int planes, int H, int W) {
+  const int x = blockIdx.x * 32 + (threadIdx.x & 31);
+  const int y = blockIdx.y * 8 + (threadIdx.x >> 5);
+  if (x >= W || y >= H) return;
+  const int xl = max(x - 1, 0), xr = min(x + 1, W - 1), yt = max(y - 1, 0) * W, ym = y * W, yb = min(y + 1, H - 1) * W;
+  for (int pl = blockIdx.z; pl < planes; pl += gridDim.z) {
+    const size_t base = (size_t)pl * H * W;
+    const float* q = img + base;
+    const float a = __ldg(q + yt + xl), b = __ldg(q + yt + x), c = __ldg(q + yt + xr);
+    const float d = __ldg(q + ym + xl), f = __ldg(q + ym + xr);
+    const float g = __ldg(q + yb + xl), h = __ldg(q + yb + x), i = __ldg(q + yb + xr);
+    const float sx = (c - a) + 2.f * (f - d) + (i - g);
+    const float sy = (g - a) + 2.f * (h - b) + (i - c);
+    const float n = rsqrtf(fmaf(sx, sx, fmaf(sy, sy, 1e-8f)));
+    const float gx = __ldg(ggx + base + ym + x), gy = __ldg(ggy + base + ym + x);
+    const float dot = (sx * gx + sy * gy) * n * n * n;
+    const float bsx = fmaf(-dot, sx, n * gx), bsy = fmaf(-dot, sy, n * gy);
+    if (bsx == 0.f && bsy == 0.f) continue;
+    float* o = g_img + base;
+    atomicAdd(o + yt + xl, -bsx - bsy);
+    atomicAdd(o + yt + x, -2.f * bsy);
+    atomicAdd(o + yt + xr, bsx - bsy);
+    atomicAdd(o + ym + xl, -2.f * bsx);
+    atomicAdd(o + ym + xr, 2.f * bsx);
+    atomicAdd(o + yb + xl, -bsx + bsy);
+    atomicAdd(o + yb + x, 2.f * bsy);
+    atomicAdd(o + yb + xr, bsx + bsy);
+  }
+}
+
+__global__ void copy_kernel(const float* __restrict__ src, float* __restrict__ dst, size_t n) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) dst[i] = src ? src[i] : 0.f;
+}
+
+struct BwdPlan {
+  size_t max_plane, grad_elems;
+  size_t off_unit, off_gunit, off_gpose, off_mlam, total;
+};
+
+static BwdPlan make_bwd_plan(const dpft_level_t* lv, int n_levels, int B, int C, int iters) {
+  BwdPlan pl{};
+  for (int l = 0; l < n_levels; ++l) pl.max_plane = std::max(pl.max_plane, (size_t)lv[l].H * lv[l].W);
+  pl.grad_elems = (size_t)B * C * pl.max_plane;
+  size_t off = 0;
+  auto take = [&](size_t bytes) {
+    const size_t o = off;
+    off += (bytes + 255) & ~(size_t)255;
+    return o;
+  };
+  pl.off_unit = take(4 * pl.grad_elems * sizeof(float));
+  pl.off_gunit = take(4 * pl.grad_elems * sizeof(float));
+  pl.off_gpose = take((size_t)(n_levels * iters + 1) * B * 12 * sizeof(float));
+  pl.off_mlam = take((size_t)B * 27 * sizeof(float));
+  pl.total = off;
+  return pl;
+}
+
+template <int CH>
+static void launch_bwd(const BwdParams& prm, dim3 grid, bool tru, cudaStream_t stream) {
+  if (tru) uic_bwd_px_kernel<CH, true><<<grid, kBT, 0, stream>>>(prm);
+  else uic_bwd_px_kernel<CH, false><<<grid, kBT, 0, stream>>>(prm);
+}
+
+}  // namespace dpft
+
+using namespace dpft;
+
+extern "C" size_t dpft_uic_backward_workspace_bytes(const dpft_level_t* levels, int n_levels, int B, int C,
+                                                    int iters, uint32_t flags) {
+  (void)flags;
+  if (!levels || n_levels < 1 || n_levels > DPFT_MAX_LEVELS || B < 1 || C < 1 || iters < 1) {
+    set_error(DPFT_EINVAL, "bad problem size");
+    return 0;
+  }
+  return make_bwd_plan(levels, n_levels, B, C, iters).total;
+}
+
+extern "C" int dpft_uic_backward(const dpft_level_t* levels, const dpft_level_grad_t* grads, int n_levels, int B,
+                                 int C, int iters, uint32_t flags, const float* pose_hist, const float* sys_hist,
+                                 const float* aux_hist, const float* grad_pose_hist, const float* grad_A,
+                                 float* grad_pose_in, void* workspace, size_t workspace_bytes, void* stream_) {
+  if (!levels || !grads || n_levels < 1 || n_levels > DPFT_MAX_LEVELS || B < 1 || B > 65535 || C < 1 || iters < 1)
+    return set_error(DPFT_EINVAL, "bad problem size");
+  if (!pose_hist || !sys_hist || !aux_hist || !grad_pose_hist || !grad_pose_in || !workspace)
+    return set_error(DPFT_EINVAL, "pose_hist, sys_hist, aux_hist, grad_pose_hist, grad_pose_in and workspace are required");
+  if (flags & DPFT_COMBINE_ICP) return set_error(DPFT_EINVAL, "DPFT_COMBINE_ICP has no backward yet");
+  for (int l = 0; l < n_levels; ++l)
+    if (!grads[l].g_x0 || !grads[l].g_x1 || !grads[l].g_sigma0 || !grads[l].g_sigma1)
+      return set_error(DPFT_EINVAL, "level %d: all four gradient maps are required", l);
+  const BwdPlan pl = make_bwd_plan(levels, n_levels, B, C, iters);
+  if (workspace_bytes < pl.total) return set_error(DPFT_ENOSPACE, "workspace has %zu bytes, %zu needed", workspace_bytes, pl.total);
+  cudaStream_t stream = (cudaStream_t)stream_;
+  char* ws = (char*)workspace;
+  float* unit = (float*)(ws + pl.off_unit);
+  float* gunit = (float*)(ws + pl.off_gunit);
+  float* gpose = (float*)(ws + pl.off_gpose);
+  float* mlam = (float*)(ws + pl.off_mlam);
+  const bool tru = flags & DPFT_REMOVE_TRU_SIGMA;
+  const int n_it = n_levels * iters;
+  const int CH = (C % 8 == 0) ? 8 : (C % 4 == 0) ? 4 : (C % 2 == 0) ? 2 : 1;
+  {
+    const size_t n = (size_t)(n_it + 1) * B * 12;
+    copy_kernel<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(grad_pose_hist, gpose, n);
+  }
+  for (int l = n_levels - 1; l >= 0; --l) {
+    const dpft_level_t& L = levels[l];
+    const size_t plane = (size_t)L.H * L.W;
+    const size_t ne = (size_t)B * C * plane;
+    float* u0 = unit; float* u1 = unit + pl.grad_elems; float* u2 = unit + 2 * pl.grad_elems; float* u3 = unit + 3 * pl.grad_elems;
+    float* g0 = gunit; float* g1 = gunit + pl.grad_elems; float* g2 = gunit + 2 * pl.grad_elems; float* g3 = gunit + 3 * pl.grad_elems;
+    launch_sobel_unit(L.x0, u0, u1, B * C, L.H, L.W, stream);
+    launch_sobel_unit(L.sigma0, u2, u3, B * C, L.H, L.W, stream);
+    cudaMemsetAsync(gunit, 0, 4 * pl.grad_elems * sizeof(float), stream);
+    const long want_threads = 148L * 2048 * 2;
+    long ppt = ((long)B * (long)plane + want_threads - 1) / want_threads;
+    ppt = std::max(1L, std::min(ppt, 8L));
+    const dim3 grid((unsigned)((plane + (size_t)kBT * ppt - 1) / ((size_t)kBT * ppt)), B);
+    for (int it = iters - 1; it >= 0; --it) {
+      const int k = l * iters + it;
+      const float* gA = (grad_A && it == iters - 1) ? grad_A + (size_t)l * B * 36 : nullptr;
+      pose_bwd_kernel<<<(B + 63) / 64, 64, 0, stream>>>(sys_hist + (size_t)k * B * 27, pose_hist + (size_t)k * B * 12,
+                                                         gpose + (size_t)(k + 1) * B * 12, gA,
+                                                         gpose + (size_t)k * B * 12, mlam, B);
+      BwdParams prm{};
+      prm.x0 = L.x0; prm.x1 = L.x1; prm.s0 = L.sigma0; prm.s1 = L.sigma1; prm.d0 = L.invd0; prm.d1 = L.invd1; prm.K = L.K;
+      prm.m0 = L.obj_mask0; prm.m1 = L.obj_mask1;
+      prm.gfx = u0; prm.gfy = u1; prm.gsx = u2; prm.gsy = u3;
+      prm.g_x0 = grads[l].g_x0; prm.g_x1 = grads[l].g_x1; prm.g_s0 = grads[l].g_sigma0; prm.g_s1 = grads[l].g_sigma1;
+      prm.g_gfx = g0; prm.g_gfy = g1; prm.g_gsx = g2; prm.g_gsy = g3;
+      prm.H = L.H; prm.W = L.W; prm.B = B; prm.C = C; prm.ppt = (int)ppt;
+      prm.pose = pose_hist + (size_t)k * B * 12;
+      prm.mlam = mlam;
+      prm.aux = aux_hist + 4 * k;
+      prm.gpose = gpose + (size_t)k * B * 12;
+      switch (CH) {
+        case 8: launch_bwd<8>(prm, grid, tru, stream); break;
+        case 4: launch_bwd<4>(prm, grid, tru, stream); break;
+        case 2: launch_bwd<2>(prm, grid, tru, stream); break;
+        default: launch_bwd<1>(prm, grid, tru, stream); break;
+      }
+    }
+    // unit-gradient adjoints of the level -> x0 / sigma0
+    const dim3 sg((L.W + 31) / 32, (L.H + 7) / 8, std::min(B * C, 4096));
+    sobel_unit_bwd_kernel<<<sg, 256, 0, stream>>>(L.x0, g0, g1, grads[l].g_x0, B * C, L.H, L.W);
+    sobel_unit_bwd_kernel<<<sg, 256, 0, stream>>>(L.sigma0, g2, g3, grads[l].g_sigma0, B * C, L.H, L.W);
+    (void)ne;
+  }
+  copy_kernel<<<(unsigned)(((size_t)B * 12 + 255) / 256), 256, 0, stream>>>(gpose, grad_pose_in, (size_t)B * 12);
+  const cudaError_t err = cudaGetLastError();
+  if (err != cudaSuccess) return set_error((int)err, "backward launch: %s", cudaGetErrorString(err));
+  return 0;
+}

@@ -21,6 +21,7 @@
 #include "dpft.h"
 #include "dpft_device.cuh"
 #include "dpft_host.h"
+#include "dpft_kernels.h"
 
 namespace dpft {
 
@@ -45,7 +46,7 @@ struct UicIterParams {
   double* pairrec;       // (B, PS)
   int* counters;         // [B] per pair, [B] = pairs done
   const uint32_t* s0mm;  // order-encoded min, max of sigma0 over the whole level tensor
-  float* gmm;            // [2] batch-global min/max of the warped sigma (written for the debug pass)
+  float* gmm;            // [4] batch-global min/max of the warped sigma of this iteration, min/max of sigma0
   int32_t* status;
   uint32_t flags;
 };
@@ -250,6 +251,8 @@ __device__ __forceinline__ void reduce_and_finish(const UicIterParams& p, const 
       s_pair_mm[1] = g1;
       p.gmm[0] = g0;
       p.gmm[1] = g1;
+      p.gmm[2] = ord2f(__ldcg(p.s0mm));
+      p.gmm[3] = ord2f(__ldcg(p.s0mm + 1));
       p.counters[p.B] = 0;
     }
     __syncthreads();
@@ -486,6 +489,11 @@ __global__ void __launch_bounds__(256) sobel_unit_kernel(const float* __restrict
   }
 }
 
+void launch_sobel_unit(const float* img, float* gx, float* gy, int planes, int H, int W, cudaStream_t stream) {
+  const dim3 grid((W + 31) / 32, (H + 7) / 8, std::min(planes, 4096));
+  sobel_unit_kernel<<<grid, 256, 0, stream>>>(img, gx, gy, planes, H, W);
+}
+
 struct PxExtra {
   const float *gfx, *gfy, *gsx, *gsy;   // (B,C,H,W) unit gradients of x0 and sigma0
   int ppt;                              // pixels per thread
@@ -708,7 +716,7 @@ static Plan make_plan(const dpft_level_t* lv, int n_levels, int B, int C, uint32
   pl.off_pairrec = take((size_t)B * PS * sizeof(double));
   pl.off_counters = take((size_t)(B + 1) * sizeof(int));
   pl.off_mm = take((size_t)2 * DPFT_MAX_LEVELS * sizeof(uint32_t));
-  pl.off_gmm = take(2 * sizeof(float));
+  pl.off_gmm = take(4 * sizeof(float) * DPFT_MAX_LEVELS * 64);
   pl.off_sr0 = take(((flags & DPFT_REMOVE_TRU_SIGMA) && any_occ) ? (size_t)B * pl.max_plane * sizeof(float) : 0);
   pl.grad_elems = (flags & DPFT_FUSED_SOBEL) ? 0 : (size_t)B * C * pl.max_plane;
   pl.off_grad = take(4 * pl.grad_elems * sizeof(float));
@@ -776,8 +784,9 @@ extern "C" size_t dpft_uic_workspace_bytes(const dpft_level_t* levels, int n_lev
 }
 
 static int run_uic(const dpft_level_t* levels, int n_levels, int B, int C, int iters, uint32_t flags,
-                   float w_icp, const float* pose_in, float* pose_hist, float* sys_hist,
+                   float w_icp, const float* pose_in, float* pose_hist, float* sys_hist, float* aux_hist,
                    int32_t* status, void* workspace, size_t workspace_bytes, void* stream_, cudaEvent_t* ev) {
+  if (iters > 64) return set_error(DPFT_EINVAL, "iters must be <= 64");
   (void)w_icp;
   if (int e = check_args(levels, n_levels, B, C, iters, flags)) return e;
   if (!pose_in || !pose_hist || !status || (iters > 0 && !sys_hist) || !workspace)
@@ -792,7 +801,7 @@ static int run_uic(const dpft_level_t* levels, int n_levels, int B, int C, int i
   double* pairrec = (double*)(ws + pl.off_pairrec);
   int* counters = (int*)(ws + pl.off_counters);
   uint32_t* mm = (uint32_t*)(ws + pl.off_mm);
-  float* gmm = (float*)(ws + pl.off_gmm);
+  float* gmm = aux_hist ? aux_hist : (float*)(ws + pl.off_gmm);   // 4 floats per iteration
   float* sr0 = (float*)(ws + pl.off_sr0);
   const bool tru = flags & DPFT_REMOVE_TRU_SIGMA;
   const bool pdl = !(flags & DPFT_NO_PDL);
@@ -821,9 +830,8 @@ static int run_uic(const dpft_level_t* levels, int n_levels, int B, int C, int i
       float* g = grad;
       ex.gfx = g; ex.gfy = g + pl.grad_elems; ex.gsx = g + 2 * pl.grad_elems; ex.gsy = g + 3 * pl.grad_elems;
       ex.ppt = pl.ppt[l];
-      const dim3 sg((L.W + 31) / 32, (L.H + 7) / 8, std::min(B * C, 4096));
-      sobel_unit_kernel<<<sg, 256, 0, stream>>>(L.x0, g, g + pl.grad_elems, B * C, L.H, L.W);
-      sobel_unit_kernel<<<sg, 256, 0, stream>>>(L.sigma0, g + 2 * pl.grad_elems, g + 3 * pl.grad_elems, B * C, L.H, L.W);
+      launch_sobel_unit(L.x0, g, g + pl.grad_elems, B * C, L.H, L.W, stream);
+      launch_sobel_unit(L.sigma0, g + 2 * pl.grad_elems, g + 3 * pl.grad_elems, B * C, L.H, L.W, stream);
     }
     for (int it = 0; it < iters; ++it, ++k) {
       UicIterParams prm{};
@@ -839,7 +847,7 @@ static int run_uic(const dpft_level_t* levels, int n_levels, int B, int C, int i
       prm.pose_next = pose_hist + (size_t)(k + 1) * B * 12;
       prm.sys_out = sys_hist + (size_t)k * B * 27;
       prm.partials = partials; prm.pairrec = pairrec; prm.counters = counters;
-      prm.s0mm = mm + 2 * l; prm.gmm = gmm; prm.status = status; prm.flags = flags;
+      prm.s0mm = mm + 2 * l; prm.gmm = gmm + 4 * k; prm.status = status; prm.flags = flags;
       const dim3 grid(prm.ctas_per_pair, B);
       // the debug mask pass reads what this launch wrote, so keep plain stream order around it
       const bool use_pdl = pdl && !any_occ && !ev;
@@ -862,7 +870,7 @@ static int run_uic(const dpft_level_t* levels, int n_levels, int B, int C, int i
       if (err != cudaSuccess) return set_error((int)err, "uic_iter_kernel launch: %s", cudaGetErrorString(err));
       if (tru && prm.occ_out) {
         const size_t n = (size_t)B * plane;
-        occ_fixup_kernel<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(prm.occ_out, sr0, gmm, n);
+        occ_fixup_kernel<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(prm.occ_out, sr0, prm.gmm, n);
       }
     }
   }
@@ -874,22 +882,23 @@ static int run_uic(const dpft_level_t* levels, int n_levels, int B, int C, int i
 
 extern "C" int dpft_uic_forward(const dpft_level_t* levels, int n_levels, int B, int C, int iters, uint32_t flags,
                                 float w_icp, const float* pose_in, float* pose_hist, float* sys_hist,
-                                int32_t* status, void* workspace, size_t workspace_bytes, void* stream) {
-  return run_uic(levels, n_levels, B, C, iters, flags, w_icp, pose_in, pose_hist, sys_hist, status, workspace,
-                 workspace_bytes, stream, nullptr);
+                                float* aux_hist, int32_t* status, void* workspace, size_t workspace_bytes,
+                                void* stream) {
+  return run_uic(levels, n_levels, B, C, iters, flags, w_icp, pose_in, pose_hist, sys_hist, aux_hist, status,
+                 workspace, workspace_bytes, stream, nullptr);
 }
 
 extern "C" int dpft_uic_forward_timed(const dpft_level_t* levels, int n_levels, int B, int C, int iters,
                                       uint32_t flags, float w_icp, const float* pose_in, float* pose_hist,
-                                      float* sys_hist, int32_t* status, void* workspace, size_t workspace_bytes,
-                                      void* stream, float* launch_ms) {
+                                      float* sys_hist, float* aux_hist, int32_t* status, void* workspace,
+                                      size_t workspace_bytes, void* stream, float* launch_ms) {
   if (!launch_ms || n_levels < 1 || n_levels > DPFT_MAX_LEVELS || iters < 1 || iters > 64)
     return set_error(DPFT_EINVAL, "launch_ms is required and iters must be 1..64");
   const int n = n_levels * iters;
   cudaEvent_t ev[DPFT_MAX_LEVELS * 64 + 1];
   for (int i = 0; i <= n; ++i) cudaEventCreate(&ev[i]);
-  int rc = run_uic(levels, n_levels, B, C, iters, flags, w_icp, pose_in, pose_hist, sys_hist, status, workspace,
-                   workspace_bytes, stream, ev);
+  int rc = run_uic(levels, n_levels, B, C, iters, flags, w_icp, pose_in, pose_hist, sys_hist, aux_hist, status,
+                   workspace, workspace_bytes, stream, ev);
   if (rc == 0) {
     const cudaError_t err = cudaStreamSynchronize((cudaStream_t)stream);
     if (err != cudaSuccess) rc = set_error((int)err, "sync: %s", cudaGetErrorString(err));

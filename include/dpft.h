@@ -87,12 +87,40 @@ size_t dpft_uic_workspace_bytes(const dpft_level_t *levels, int n_levels, int B,
  *   pose_hist  (n_levels*iters + 1, B, 12)  OUT: pose before iteration k at row k; the result is the last row
  *   sys_hist   (n_levels*iters, B, 27)      OUT: per iteration the 21 upper-triangular entries of J^T W J
  *                                           (row-major i<=j) followed by the 6 entries of J^T W r
+ *   aux_hist   (n_levels*iters, 4)          OUT, optional (NULL): with DPFT_REMOVE_TRU_SIGMA the batch-global
+ *                                           [min, max] of the warped sigma of that iteration and [min, max] of
+ *                                           sigma0 -- the values dpft_uic_backward needs to rebuild the masks
  *   w_icp      scalar weight of the ICP term (the reference's ScaleNet('None') constant, 0.01)
  *   status     device int32, OR-ed with DPFT_ST_* bits
  */
 int dpft_uic_forward(const dpft_level_t *levels, int n_levels, int B, int C, int iters, uint32_t flags,
-                     float w_icp, const float *pose_in, float *pose_hist, float *sys_hist,
+                     float w_icp, const float *pose_in, float *pose_hist, float *sys_hist, float *aux_hist,
                      int32_t *status, void *workspace, size_t workspace_bytes, void *stream);
+
+/* Gradient maps of one level, same shapes as the inputs; the backward ACCUMULATES into them (zero them first). */
+typedef struct dpft_level_grad {
+  float *g_x0, *g_x1;         /* (B,C,H,W) */
+  float *g_sigma0, *g_sigma1; /* (B,C,H,W) */
+} dpft_level_grad_t;
+
+size_t dpft_uic_backward_workspace_bytes(const dpft_level_t *levels, int n_levels, int B, int C, int iters,
+                                         uint32_t flags);
+
+/*
+ * Reverse-mode of dpft_uic_forward (what torch.autograd derives from alg:611-723):
+ * gradients w.r.t. x0, x1, sigma0, sigma1 of every level and w.r.t. the starting pose.  Masks, the 1e-6
+ * fill and the batch-global extremes are stop-gradients.  Recompute-based: takes the forward's inputs and
+ * its pose_hist / sys_hist / aux_hist, nothing per-pixel is saved.
+ *
+ *   grad_pose_hist (n_levels*iters + 1, B, 12)  IN: dL/d(pose row k); zero for rows that are not outputs
+ *                                               (the outputs are the rows (l+1)*iters, one per level)
+ *   grad_A         (n_levels, B, 36) or NULL    IN: dL/d(J^T W J of the last iteration of level l) (uncer_prop)
+ *   grad_pose_in   (B,12)                       OUT: dL/d(pose_in)
+ */
+int dpft_uic_backward(const dpft_level_t *levels, const dpft_level_grad_t *grads, int n_levels, int B, int C,
+                      int iters, uint32_t flags, const float *pose_hist, const float *sys_hist,
+                      const float *aux_hist, const float *grad_pose_hist, const float *grad_A,
+                      float *grad_pose_in, void *workspace, size_t workspace_bytes, void *stream);
 
 /*
  * Measurement aid for bench.py: same work as dpft_uic_forward, but every Gauss-Newton launch is bracketed
@@ -102,8 +130,8 @@ int dpft_uic_forward(const dpft_level_t *levels, int n_levels, int B, int C, int
  */
 int dpft_uic_forward_timed(const dpft_level_t *levels, int n_levels, int B, int C, int iters, uint32_t flags,
                            float w_icp, const float *pose_in, float *pose_hist, float *sys_hist,
-                           int32_t *status, void *workspace, size_t workspace_bytes, void *stream,
-                           float *launch_ms);
+                           float *aux_hist, int32_t *status, void *workspace, size_t workspace_bytes,
+                           void *stream, float *launch_ms);
 
 #ifdef __cplusplus
 }
