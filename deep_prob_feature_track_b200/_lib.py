@@ -17,7 +17,7 @@ PKG_DIR = os.path.dirname(os.path.abspath(__file__))
 REPO_DIR = os.path.dirname(PKG_DIR)
 CSRC = os.path.join(PKG_DIR, "csrc")
 LIB_PATH = os.path.join(PKG_DIR, "libdpft.so")
-SOURCES = ["dpft_abi.cu", "uic_forward.cu", "uic_backward.cu"]
+SOURCES = ["dpft_abi.cu", "uic_forward.cu", "uic_backward.cu", "icp_term.cu", "uic_residual.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "-Xcompiler", "-fPIC", "-shared"]
 
@@ -117,6 +117,13 @@ def lib() -> ctypes.CDLL:
                                     ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_uint32, ctypes.c_void_p,
                                     ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p,
                                     ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_void_p]
+    L.dpft_uic_residual_workspace_bytes.restype = ctypes.c_size_t
+    L.dpft_uic_residual_workspace_bytes.argtypes = [ctypes.POINTER(DpftLevel), ctypes.c_int, ctypes.c_int,
+                                                    ctypes.c_uint32]
+    L.dpft_uic_residual_loss.restype = ctypes.c_int
+    L.dpft_uic_residual_loss.argtypes = [ctypes.POINTER(DpftLevel), ctypes.c_int, ctypes.c_int, ctypes.c_uint32,
+                                         ctypes.c_float, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p,
+                                         ctypes.c_size_t, ctypes.c_void_p]
     if L.dpft_abi_version() != DPFT_ABI_VERSION:
         raise RuntimeError("libdpft.so ABI version mismatch; rebuild")
     _lib = L
@@ -126,7 +133,8 @@ def lib() -> ctypes.CDLL:
 def exported_symbols() -> List[str]:
     """Entry points include/dpft.h declares (kept in sync by tests/test_abi.py)."""
     return ["dpft_abi_version", "dpft_last_error", "dpft_uic_workspace_bytes", "dpft_uic_forward",
-            "dpft_uic_forward_timed", "dpft_uic_backward_workspace_bytes", "dpft_uic_backward"]
+            "dpft_uic_forward_timed", "dpft_uic_backward_workspace_bytes", "dpft_uic_backward",
+            "dpft_uic_residual_workspace_bytes", "dpft_uic_residual_loss"]
 
 
 def check(code: int, what: str) -> None:

@@ -87,7 +87,8 @@ class SolveResult:
 
 
 def uic_solve(levels: Sequence[Dict[str, torch.Tensor]], pose: Pose, *, iters: int = 3,
-              remove_tru_sigma: bool = False, want_occ: bool = False, pdl: bool = True, timed: bool = False, fused_sobel: bool = True,
+              remove_tru_sigma: bool = False, combine_icp: bool = False, w_icp: float = 0.01,
+              want_occ: bool = False, pdl: bool = True, timed: bool = False, fused_sobel: bool = True,
               obj_mask0: Optional[Sequence] = None, obj_mask1: Optional[Sequence] = None) -> SolveResult:
     """Coarse-to-fine U_IC solve of a batch of frame pairs on the current CUDA stream.
 
@@ -121,13 +122,18 @@ def uic_solve(levels: Sequence[Dict[str, torch.Tensor]], pose: Pose, *, iters: i
         a = arr[i]
         a.x0, a.x1, a.sigma0, a.sigma1 = (t[k].data_ptr() for k in ("x0", "x1", "s0", "s1"))
         a.invd0, a.invd1, a.K = t["invD0"].data_ptr(), t["invD1"].data_ptr(), t["K"].data_ptr()
-        a.depth0 = a.depth1 = None
+        if combine_icp:
+            dd = (_dev_f32(lv["depth0"], "depth0"), _dev_f32(lv["depth1"], "depth1"))
+            keep.append(dd)
+            a.depth0, a.depth1 = dd[0].data_ptr(), dd[1].data_ptr()
+        else:
+            a.depth0 = a.depth1 = None
         a.obj_mask0 = m0.data_ptr() if m0 is not None else None
         a.obj_mask1 = m1.data_ptr() if m1 is not None else None
         a.occ_out = o.data_ptr() if o is not None else None
         a.H, a.W = H, W
     flags = ((_lib.DPFT_REMOVE_TRU_SIGMA if remove_tru_sigma else 0) | (0 if pdl else _lib.DPFT_NO_PDL)
-             | (_lib.DPFT_FUSED_SOBEL if fused_sobel else 0))
+             | (_lib.DPFT_FUSED_SOBEL if fused_sobel else 0) | (_lib.DPFT_COMBINE_ICP if combine_icp else 0))
     n_it = n_levels * iters
     pose_in = pack_pose(pose).to(dev)
     pose_hist = torch.empty((n_it + 1, B, 12), dtype=torch.float32, device=dev)
@@ -140,7 +146,7 @@ def uic_solve(levels: Sequence[Dict[str, torch.Tensor]], pose: Pose, *, iters: i
     ws = torch.empty((ws_bytes,), dtype=torch.uint8, device=dev)
     stream = torch.cuda.current_stream(dev).cuda_stream
     launch_ms = None
-    args = (arr, n_levels, B, C, iters, flags, ctypes.c_float(0.01), pose_in.data_ptr(), pose_hist.data_ptr(),
+    args = (arr, n_levels, B, C, iters, flags, ctypes.c_float(w_icp), pose_in.data_ptr(), pose_hist.data_ptr(),
             sys_hist.data_ptr(), aux_hist.data_ptr(), status.data_ptr(), ws.data_ptr(), ws_bytes, stream)
     with torch.cuda.device(dev):
         if timed:   # measurement aid (bench.py): per-launch device times, synchronises the stream
@@ -155,7 +161,7 @@ def uic_solve(levels: Sequence[Dict[str, torch.Tensor]], pose: Pose, *, iters: i
 
 
 # ----------------------------------------------------------------------------- autograd
-def _level_array(levels, B, C, obj_mask0=None, obj_mask1=None):
+def _level_array(levels, B, C, obj_mask0=None, obj_mask1=None, with_depth=False):
     """ctypes array of dpft_level for already-converted device tensors; returns (array, keep-alive list)."""
     arr = (_lib.DpftLevel * len(levels))()
     keep = []
@@ -169,8 +175,33 @@ def _level_array(levels, B, C, obj_mask0=None, obj_mask1=None):
         a.invd0, a.invd1, a.K = t["invD0"].data_ptr(), t["invD1"].data_ptr(), t["K"].data_ptr()
         a.obj_mask0 = m0.data_ptr() if m0 is not None else None
         a.obj_mask1 = m1.data_ptr() if m1 is not None else None
+        if with_depth:
+            dd = (_dev_f32(lv["depth0"], "depth0"), _dev_f32(lv["depth1"], "depth1"))
+            keep.append(dd)
+            a.depth0, a.depth1 = dd[0].data_ptr(), dd[1].data_ptr()
         a.H, a.W = int(t["x0"].shape[2]), int(t["x0"].shape[3])
     return arr, keep
+
+
+def uic_residual_loss(level: Dict[str, torch.Tensor], pose: Pose, *, remove_tru_sigma: bool = False,
+                      combine_icp: bool = False, w_icp: float = 0.01, obj_mask0=None, obj_mask1=None) -> torch.Tensor:
+    """Per-pair average squared weighted residual at ``pose`` (reference forward_residuals, alg:725-786)."""
+    L = _lib.lib()
+    x0 = level["x0"]
+    B, C, dev = int(x0.shape[0]), int(x0.shape[1]), x0.device
+    arr, keep = _level_array([level], B, C, None if obj_mask0 is None else [obj_mask0],
+                             None if obj_mask1 is None else [obj_mask1], with_depth=combine_icp)
+    flags = (_lib.DPFT_REMOVE_TRU_SIGMA if remove_tru_sigma else 0) | (_lib.DPFT_COMBINE_ICP if combine_icp else 0)
+    pose_in = pack_pose(pose).to(dev)
+    loss = torch.empty((B,), dtype=torch.float32, device=dev)
+    ws_bytes = L.dpft_uic_residual_workspace_bytes(arr, B, C, flags)
+    ws = torch.empty((max(ws_bytes, 1),), dtype=torch.uint8, device=dev)
+    with torch.cuda.device(dev):
+        code = L.dpft_uic_residual_loss(arr, B, C, flags, ctypes.c_float(w_icp), pose_in.data_ptr(), loss.data_ptr(),
+                                        ws.data_ptr(), ws_bytes, torch.cuda.current_stream(dev).cuda_stream)
+    _lib.check(code, "dpft_uic_residual_loss")
+    del keep
+    return loss
 
 
 class _UicSolveFn(torch.autograd.Function):
@@ -280,12 +311,19 @@ class TrustRegionInverseWUncertainty(nn.Module):
     def forward(self, pose10, x0, x1, invD0, invD1, K, sigma0, sigma1, wPrior=None, depth0=None, depth1=None,
                 vis_res=True, obj_mask0=None, obj_mask1=None):
         assert sigma0 is not None and sigma1 is not None
+        w_icp = self._icp_weight()
         if self.combine_icp:
-            raise NotImplementedError("combine_icp: the ICP term is not built yet (DESIGN.md, 'next')")
+            assert depth0 is not None and depth1 is not None
         if self.timers: self.timers.tic('trust-region level solve (fused CUDA)')
         lv = dict(x0=x0, x1=x1, s0=sigma0, s1=sigma1, invD0=invD0, invD1=invD1, K=K)
         weights = torch.ones((1, 1, 1, 1), dtype=x0.dtype, device=x0.device).expand(x0.shape)
+        if self.combine_icp:
+            lv.update(depth0=depth0, depth1=depth1)
+            weights = torch.full((1, 1, 1, 1), w_icp, dtype=x0.dtype, device=x0.device).expand(
+                x0.shape[0], 1, x0.shape[2], x0.shape[3])
         if torch.is_grad_enabled() and any(t.requires_grad for t in (x0, x1, sigma0, sigma1, pose10[0], pose10[1])):
+            if self.combine_icp:
+                raise NotImplementedError("the ICP term has no backward kernel yet (DESIGN.md, 'next')")
             # training: same kernels, recorded for autograd (backward = dpft_uic_backward)
             (R, t, A), = uic_track([lv], (pose10[0], pose10[1]), iters=self.max_iterations,
                                    remove_tru_sigma=self.remove_tru_sigma,
@@ -294,6 +332,7 @@ class TrustRegionInverseWUncertainty(nn.Module):
             if self.timers: self.timers.toc('trust-region level solve (fused CUDA)')
             return ((R, t), weights, A) if self.uncer_prop else ((R, t), weights)
         res = uic_solve([lv], pose10, iters=self.max_iterations, remove_tru_sigma=self.remove_tru_sigma,
+                        combine_icp=self.combine_icp, w_icp=w_icp,
                         obj_mask0=None if obj_mask0 is None else [obj_mask0],
                         obj_mask1=None if obj_mask1 is None else [obj_mask1])
         if self.check_nan:
@@ -303,6 +342,29 @@ class TrustRegionInverseWUncertainty(nn.Module):
             A, _ = unpack_system(res.sys_hist[-1])
             return res.pose, weights, A
         return res.pose, weights
+
+
+    def _icp_weight(self) -> float:
+        """ScaleNet('None') is a constant (ones * scale, alg:1535,1563-1567); that is what every shipped
+        script uses.  A learned scaler would need the residual maps materialised for its CNN."""
+        if not self.combine_icp:
+            return 0.01
+        sf = self.scale_func
+        if sf is None:
+            return 0.01
+        if getattr(sf, "D", -1) > 0:
+            raise NotImplementedError("learned ICP scalers (ScaleNet with a CNN) are not built (DESIGN.md)")
+        return float(getattr(sf, "scale", 0.01))
+
+    def forward_residuals(self, pose10, x0, x1, invD0, invD1, K, sigma0, sigma1, wPrior=None, depth0=None,
+                          depth1=None, vis_res=True, obj_mask0=None, obj_mask1=None):
+        assert sigma0 is not None and sigma1 is not None
+        lv = dict(x0=x0, x1=x1, s0=sigma0, s1=sigma1, invD0=invD0, invD1=invD1, K=K)
+        if self.combine_icp:
+            assert depth0 is not None and depth1 is not None
+            lv.update(depth0=depth0, depth1=depth1)
+        return uic_residual_loss(lv, pose10, remove_tru_sigma=self.remove_tru_sigma, combine_icp=self.combine_icp,
+                                 w_icp=self._icp_weight(), obj_mask0=obj_mask0, obj_mask1=obj_mask1)
 
 
 def patch_tracker(net: nn.Module) -> nn.Module:

@@ -1,0 +1,172 @@
+// Point-to-plane ICP term of the U_IC tracker (reference code/models/algorithms.py:916-997, 2148-2171,
+// geometry.py:1129-1136), added to the feature-metric normal equations when combine_icp is on.
+//
+//   vertex_normal_kernel  once per level: V1 = [x, y, 1] depth1 and N1 = normalised cross product of the
+//                         (un-normalised, replicate-padded) Sobel responses of V1; zero where depth1 sits
+//                         on its batch-global extremes.
+//   icp_term_kernel       per iteration, one thread per pixel: P = R V0 + t, project, bilinear lookup of
+//                         V1 / N1, r = N1.(P - V1), J = -[ (N1^T R) x V0 , -(N1^T R) ] / sigma_icp,
+//                         accumulates sum J J^T and sum J r per pair.
+#include <cuda_runtime.h>
+#include <math_constants.h>
+#include <stdint.h>
+
+#include <algorithm>
+
+#include "dpft.h"
+#include "dpft_device.cuh"
+#include "dpft_kernels.h"
+
+namespace dpft {
+
+__global__ void __launch_bounds__(256) vertex_normal_kernel(const float* __restrict__ depth, const float* __restrict__ K,
+                                                            const uint32_t* __restrict__ dmm, float* __restrict__ V,
+                                                            float* __restrict__ N, int B, int H, int W) {
+  const int x = blockIdx.x * 32 + (threadIdx.x & 31);
+  const int y = blockIdx.y * 8 + (threadIdx.x >> 5);
+  const int b = blockIdx.z;
+  if (x >= W || y >= H) return;
+  const float fx = __ldg(K + 4 * b), fy = __ldg(K + 4 * b + 1), cx = __ldg(K + 4 * b + 2), cy = __ldg(K + 4 * b + 3);
+  const float* d = depth + (size_t)b * H * W;
+  const int xs[3] = {max(x - 1, 0), x, min(x + 1, W - 1)};
+  const int ys[3] = {max(y - 1, 0), y, min(y + 1, H - 1)};
+  float v[3][3][3];   // [row][col][component]
+#pragma unroll
+  for (int r = 0; r < 3; ++r)
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      const float z = __ldg(d + ys[r] * W + xs[c]);
+      const float px = xdiv(xsub((float)xs[c], cx), fx), py = xdiv(xsub((float)ys[r], cy), fy);
+      v[r][c][0] = px * z;
+      v[r][c][1] = py * z;
+      v[r][c][2] = z;
+    }
+  float sx[3], sy[3];
+#pragma unroll
+  for (int k = 0; k < 3; ++k) {
+    sx[k] = (v[0][2][k] - v[0][0][k]) + 2.f * (v[1][2][k] - v[1][0][k]) + (v[2][2][k] - v[2][0][k]);
+    sy[k] = (v[2][0][k] - v[0][0][k]) + 2.f * (v[2][1][k] - v[0][1][k]) + (v[2][2][k] - v[0][2][k]);
+  }
+  float n[3] = {sx[1] * sy[2] - sx[2] * sy[1], sx[2] * sy[0] - sx[0] * sy[2], sx[0] * sy[1] - sx[1] * sy[0]};
+  const float mag = sqrtf(n[0] * n[0] + n[1] * n[1] + n[2] * n[2]) + 1e-8f;
+  const float z = v[1][1][2];
+  const bool bad = (z == ord2f(dmm[0])) || (z == ord2f(dmm[1]));
+  const size_t plane = (size_t)H * W, o = (size_t)b * 3 * plane + (size_t)y * W + x;
+#pragma unroll
+  for (int k = 0; k < 3; ++k) {
+    V[o + k * plane] = v[1][1][k];
+    N[o + k * plane] = bad ? 0.f : n[k] / mag;
+  }
+}
+
+struct IcpParams {
+  const float *depth0, *K, *V1, *N1, *pose;
+  const uint8_t *m0, *m1;
+  float* rec;         // (B,28): 21 + 6 sums (atomically accumulated; zero before the launch)
+  uint8_t* occ_out;   // optional (B,H,W)
+  float* r_out;       // optional (B,H,W) weighted-by-sigma residual (1e-6 where masked)
+  int H, W, B, ppt;
+};
+
+__global__ void __launch_bounds__(128, 4) icp_term_kernel(const IcpParams p) {
+  __shared__ float s_red[4][27];
+  const int b = blockIdx.y;
+  const int H = p.H, W = p.W, plane = H * W;
+  const float fx = __ldg(p.K + 4 * b), fy = __ldg(p.K + 4 * b + 1), cx = __ldg(p.K + 4 * b + 2), cy = __ldg(p.K + 4 * b + 3);
+  const Pose pose = load_pose(p.pose + (size_t)b * 12);
+  const float* V1 = p.V1 + (size_t)b * 3 * plane;
+  const float* N1 = p.N1 + (size_t)b * 3 * plane;
+  float acc[27];
+#pragma unroll
+  for (int i = 0; i < 27; ++i) acc[i] = 0.f;
+  for (int i = 0; i < p.ppt; ++i) {
+    const int pix = (blockIdx.x * p.ppt + i) * 128 + threadIdx.x;
+    if (pix >= plane) break;
+    const int y = pix / W, x = pix - y * W;
+    const float px = xdiv(xsub((float)x, cx), fx), py = xdiv(xsub((float)y, cy), fy);
+    const float z = __ldg(p.depth0 + (size_t)b * plane + pix);
+    const float v0[3] = {xmul(px, z), xmul(py, z), z};
+    float P[3];
+#pragma unroll
+    for (int k = 0; k < 3; ++k)
+      P[k] = xadd(xadd(xadd(xmul(pose.r[3 * k], v0[0]), xmul(pose.r[3 * k + 1], v0[1])), xmul(pose.r[3 * k + 2], v0[2])),
+                  pose.t[k]);
+    const float u = xadd(xmul(xdiv(P[0], P[2]), fx), cx);
+    const float v = xadd(xmul(xdiv(P[1], P[2]), fy), cy);
+    const bool inview = (u > 0.f) && (u < (float)(W - 1)) && (v > 0.f) && (v < (float)(H - 1));
+    const Tap tap = make_tap(u, v, H, W);
+    float v1[3], n1[3], diff[3];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+      v1[k] = sample_exact(V1 + (size_t)k * plane, tap, W);
+      n1[k] = sample_exact(N1 + (size_t)k * plane, tap, W);
+      diff[k] = xsub(P[k], v1[k]);
+    }
+    const float dist = sqrtf(xadd(xadd(xmul(diff[0], diff[0]), xmul(diff[1], diff[1])), xmul(diff[2], diff[2])));
+    bool occ = !inview || (dist > 0.1f);
+    if (p.m0) occ = occ || (__ldg(p.m0 + (size_t)b * plane + pix) == 0);
+    if (p.m1) occ = occ || !(sample_mask(p.m1 + (size_t)b * plane, tap, W) > 0.f);
+    float r = n1[0] * diff[0] + n1[1] * diff[1] + n1[2] * diff[2];
+    float nr[3];   // N1^T R
+#pragma unroll
+    for (int j = 0; j < 3; ++j) nr[j] = n1[0] * pose.r[j] + n1[1] * pose.r[3 + j] + n1[2] * pose.r[6 + j];
+    // TUM stereo noise model projected on the rotated normal (algorithms.py:975-997)
+    const float s_lat = z / 525.f * 5.5f, s_z = z * z * 0.4f / (525.f * 1.2f);
+    const float sig = sqrtf((nr[0] * s_lat) * (nr[0] * s_lat) + (nr[1] * s_lat) * (nr[1] * s_lat) +
+                            (nr[2] * s_z) * (nr[2] * s_z) + 1e-8f);
+    const float inv = 1.f / (sig + 1e-8f);
+    r *= inv;
+    float J[6];
+    J[0] = -(nr[1] * v0[2] - nr[2] * v0[1]) * inv;
+    J[1] = -(nr[2] * v0[0] - nr[0] * v0[2]) * inv;
+    J[2] = -(nr[0] * v0[1] - nr[1] * v0[0]) * inv;
+    J[3] = nr[0] * inv;
+    J[4] = nr[1] * inv;
+    J[5] = nr[2] * inv;
+    const float rm = occ ? 1e-6f : r;
+#pragma unroll
+    for (int a = 0; a < 6; ++a) {
+#pragma unroll
+      for (int c = a; c < 6; ++c) acc[tri(a, c)] = fmaf(J[a], J[c], acc[tri(a, c)]);
+      acc[21 + a] = fmaf(J[a], rm, acc[21 + a]);
+    }
+    if (p.occ_out) p.occ_out[(size_t)b * plane + pix] = occ ? 1 : 0;
+    if (p.r_out) p.r_out[(size_t)b * plane + pix] = rm;
+  }
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+  for (int i = 0; i < 27; ++i) {
+    float s = acc[i];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if (lane == 0) s_red[warp][i] = s;
+  }
+  __syncthreads();
+  if (threadIdx.x < 27) {
+    const float s = s_red[0][threadIdx.x] + s_red[1][threadIdx.x] + s_red[2][threadIdx.x] + s_red[3][threadIdx.x];
+    atomicAdd(p.rec + (size_t)b * 28 + threadIdx.x, s);
+  }
+}
+
+void launch_vertex_normal(const float* depth, const float* K, const uint32_t* dmm, float* V, float* N, int B, int H,
+                          int W, cudaStream_t stream) {
+  const dim3 grid((W + 31) / 32, (H + 7) / 8, B);
+  vertex_normal_kernel<<<grid, 256, 0, stream>>>(depth, K, dmm, V, N, B, H, W);
+}
+
+void launch_icp_term(const float* depth0, const float* K, const float* V1, const float* N1, const float* pose,
+                     const uint8_t* m0, const uint8_t* m1, float* rec, uint8_t* occ_out, float* r_out, int B, int H,
+                     int W, cudaStream_t stream) {
+  IcpParams p{};
+  p.depth0 = depth0; p.K = K; p.V1 = V1; p.N1 = N1; p.pose = pose; p.m0 = m0; p.m1 = m1;
+  p.rec = rec; p.occ_out = occ_out; p.r_out = r_out; p.H = H; p.W = W; p.B = B;
+  const long plane = (long)H * W;
+  const long want_threads = 148L * 2048 * 2;
+  long ppt = ((long)B * plane + want_threads - 1) / want_threads;
+  p.ppt = (int)std::max(1L, std::min(ppt, 8L));
+  const dim3 grid((unsigned)((plane + 128L * p.ppt - 1) / (128L * p.ppt)), B);
+  cudaMemsetAsync(rec, 0, (size_t)B * 28 * sizeof(float), stream);
+  icp_term_kernel<<<grid, 128, 0, stream>>>(p);
+}
+
+}  // namespace dpft

@@ -49,6 +49,8 @@ struct UicIterParams {
   float* gmm;            // [4] batch-global min/max of the warped sigma of this iteration, min/max of sigma0
   int32_t* status;
   uint32_t flags;
+  const float* icp_rec;  // (B,28) sums of the point-to-plane term of this iteration, or nullptr
+  float icp_w2;          // its weight squared (w_icp scales both J and r)
 };
 
 // Final step for one pair: corrections for the batch-global sigma extremes, damping, solve, update.
@@ -70,6 +72,13 @@ __device__ void finalize_pair(const UicIterParams& p, int b, float gmin, float g
       if (at_min) rhs[i] -= __ldcg(rec + E_CMIN + i);
       if (at_max) rhs[i] -= __ldcg(rec + E_CMAX + i);
     }
+  }
+  if (p.icp_rec) {
+    // feature-metric and point-to-plane systems are simply added (algorithms.py:685-688)
+#pragma unroll
+    for (int i = 0; i < 21; ++i) A[i] += (double)p.icp_w2 * (double)__ldcg(p.icp_rec + (size_t)b * 28 + i);
+#pragma unroll
+    for (int i = 0; i < 6; ++i) rhs[i] += (double)p.icp_w2 * (double)__ldcg(p.icp_rec + (size_t)b * 28 + 21 + i);
   }
   bool finite = true;
 #pragma unroll
@@ -659,6 +668,11 @@ __global__ void __launch_bounds__(256) minmax_kernel(const float* __restrict__ v
   }
 }
 
+void launch_minmax(const float* v, size_t n, uint32_t* mm, cudaStream_t stream) {
+  const int blocks = (int)std::min<size_t>((n / 4 + 255) / 256 + 1, 148 * 8);
+  minmax_kernel<<<blocks, 256, 0, stream>>>(v, n, mm);
+}
+
 // debug only: OR the batch-global sigma test into the per-iteration mask
 __global__ void occ_fixup_kernel(uint8_t* __restrict__ occ, const float* __restrict__ sr0, const float* __restrict__ gmm,
                                  size_t n) {
@@ -672,7 +686,8 @@ struct Plan {
   int ppt[DPFT_MAX_LEVELS], px_ctas[DPFT_MAX_LEVELS];   // materialised-gradient path: pixels per thread, CTAs per pair
   int max_ctas;
   size_t max_plane;
-  size_t off_partials, off_pairrec, off_counters, off_mm, off_gmm, off_sr0, off_grad, grad_elems, total;
+  size_t off_partials, off_pairrec, off_counters, off_mm, off_gmm, off_sr0, off_grad, grad_elems;
+  size_t off_vn, off_icp, off_dmm, total;
 };
 
 // Rows per warp tile: tall tiles amortise the two halo rows, short tiles give a small level enough warps
@@ -720,6 +735,10 @@ static Plan make_plan(const dpft_level_t* lv, int n_levels, int B, int C, uint32
   pl.off_sr0 = take(((flags & DPFT_REMOVE_TRU_SIGMA) && any_occ) ? (size_t)B * pl.max_plane * sizeof(float) : 0);
   pl.grad_elems = (flags & DPFT_FUSED_SOBEL) ? 0 : (size_t)B * C * pl.max_plane;
   pl.off_grad = take(4 * pl.grad_elems * sizeof(float));
+  const bool icp = flags & DPFT_COMBINE_ICP;
+  pl.off_vn = take(icp ? 6 * (size_t)B * pl.max_plane * sizeof(float) : 0);
+  pl.off_icp = take(icp ? (size_t)B * 28 * sizeof(float) : 0);
+  pl.off_dmm = take(2 * DPFT_MAX_LEVELS * sizeof(uint32_t));
   pl.total = off;
   return pl;
 }
@@ -728,12 +747,13 @@ static int check_args(const dpft_level_t* lv, int n_levels, int B, int C, int it
   if (!lv || n_levels < 1 || n_levels > DPFT_MAX_LEVELS) return set_error(DPFT_EINVAL, "n_levels must be 1..%d", DPFT_MAX_LEVELS);
   if (B < 1 || B > 65535) return set_error(DPFT_EINVAL, "B must be 1..65535 (got %d)", B);
   if (C < 1 || iters < 0) return set_error(DPFT_EINVAL, "C must be >= 1 and iters >= 0");
-  if (flags & DPFT_COMBINE_ICP) return set_error(DPFT_EINVAL, "DPFT_COMBINE_ICP is not available in this entry point yet");
   for (int l = 0; l < n_levels; ++l) {
     const dpft_level_t& L = lv[l];
     if (L.H < 2 || L.W < 2) return set_error(DPFT_EINVAL, "level %d: H and W must be >= 2", l);
     if (!L.x0 || !L.x1 || !L.sigma0 || !L.sigma1 || !L.invd0 || !L.invd1 || !L.K)
       return set_error(DPFT_EINVAL, "level %d: x0, x1, sigma0, sigma1, invd0, invd1 and K are required", l);
+    if ((flags & DPFT_COMBINE_ICP) && (!L.depth0 || !L.depth1))
+      return set_error(DPFT_EINVAL, "level %d: DPFT_COMBINE_ICP needs depth0 and depth1", l);
   }
   return 0;
 }
@@ -787,7 +807,6 @@ static int run_uic(const dpft_level_t* levels, int n_levels, int B, int C, int i
                    float w_icp, const float* pose_in, float* pose_hist, float* sys_hist, float* aux_hist,
                    int32_t* status, void* workspace, size_t workspace_bytes, void* stream_, cudaEvent_t* ev) {
   if (iters > 64) return set_error(DPFT_EINVAL, "iters must be <= 64");
-  (void)w_icp;
   if (int e = check_args(levels, n_levels, B, C, iters, flags)) return e;
   if (!pose_in || !pose_hist || !status || (iters > 0 && !sys_hist) || !workspace)
     return set_error(DPFT_EINVAL, "pose_in, pose_hist, sys_hist, status and workspace are required");
@@ -806,11 +825,16 @@ static int run_uic(const dpft_level_t* levels, int n_levels, int B, int C, int i
   const bool tru = flags & DPFT_REMOVE_TRU_SIGMA;
   const bool pdl = !(flags & DPFT_NO_PDL);
   const bool fused = flags & DPFT_FUSED_SOBEL;
+  const bool icp = flags & DPFT_COMBINE_ICP;
   float* grad = (float*)(ws + pl.off_grad);
+  float* vn = (float*)(ws + pl.off_vn);
+  float* icp_rec = (float*)(ws + pl.off_icp);
+  uint32_t* dmm = (uint32_t*)(ws + pl.off_dmm);
 
   {
     const int n = std::max(B * 12, B + 1);
     init_kernel<<<(n + 255) / 256, 256, 0, stream>>>(pose_in, pose_hist, B * 12, counters, B + 1, mm, n_levels);
+    if (icp) init_kernel<<<1, 32, 0, stream>>>(pose_in, pose_hist, 0, counters, 0, dmm, n_levels);
   }
   if (tru) {
     for (int l = 0; l < n_levels; ++l) {
@@ -824,6 +848,13 @@ static int run_uic(const dpft_level_t* levels, int n_levels, int B, int C, int i
   for (int l = 0; l < n_levels; ++l) {
     const dpft_level_t& L = levels[l];
     const size_t plane = (size_t)L.H * L.W;
+    if (icp) {
+      // vertex and normal maps of the live frame; normals vanish on the batch-global depth extremes
+      const size_t n = (size_t)B * plane;
+      const int blocks = (int)std::min<size_t>((n / 4 + 255) / 256 + 1, 148 * 8);
+      minmax_kernel<<<blocks, 256, 0, stream>>>(L.depth1, n, dmm + 2 * l);
+      launch_vertex_normal(L.depth1, L.K, dmm + 2 * l, vn, vn + 3 * (size_t)B * plane, B, L.H, L.W, stream);
+    }
     PxExtra ex{};
     if (!fused) {
       // unit Sobel gradients of this level's keyframe maps, once for all its iterations
@@ -848,6 +879,12 @@ static int run_uic(const dpft_level_t* levels, int n_levels, int B, int C, int i
       prm.sys_out = sys_hist + (size_t)k * B * 27;
       prm.partials = partials; prm.pairrec = pairrec; prm.counters = counters;
       prm.s0mm = mm + 2 * l; prm.gmm = gmm + 4 * k; prm.status = status; prm.flags = flags;
+      if (icp) {
+        launch_icp_term(L.depth0, L.K, vn, vn + 3 * (size_t)B * plane, prm.pose, L.obj_mask0, L.obj_mask1, icp_rec,
+                        nullptr, nullptr, B, L.H, L.W, stream);
+        prm.icp_rec = icp_rec;
+        prm.icp_w2 = w_icp * w_icp;
+      }
       const dim3 grid(prm.ctas_per_pair, B);
       // the debug mask pass reads what this launch wrote, so keep plain stream order around it
       const bool use_pdl = pdl && !any_occ && !ev;

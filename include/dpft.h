@@ -97,6 +97,15 @@ int dpft_uic_forward(const dpft_level_t *levels, int n_levels, int B, int C, int
                      float w_icp, const float *pose_in, float *pose_hist, float *sys_hist, float *aux_hist,
                      int32_t *status, void *workspace, size_t workspace_bytes, void *stream);
 
+/*
+ * forward_residuals of the U_IC tracker (alg:725-786 with compute_avg_loss alg:2119-2137): per frame pair the
+ * sum over valid pixels of the squared uncertainty-weighted residuals (plus the squared weighted point-to-plane
+ * residual with DPFT_COMBINE_ICP) divided by the number of valid pixels, at the given pose.  loss: (B).
+ */
+size_t dpft_uic_residual_workspace_bytes(const dpft_level_t *level, int B, int C, uint32_t flags);
+int dpft_uic_residual_loss(const dpft_level_t *level, int B, int C, uint32_t flags, float w_icp,
+                           const float *pose, float *loss, void *workspace, size_t workspace_bytes, void *stream);
+
 /* Gradient maps of one level, same shapes as the inputs; the backward ACCUMULATES into them (zero them first). */
 typedef struct dpft_level_grad {
   float *g_x0, *g_x1;         /* (B,C,H,W) */

@@ -56,7 +56,7 @@ def compare_level(res, trace, k0, lvl, iters, *, exact_pose_inputs):
     return flips
 
 
-@pytest.mark.parametrize("name", ["uic_plain", "uic_trusigma", "uic_masks", "uic_c8_wide"])
+@pytest.mark.parametrize("name", ["uic_plain", "uic_trusigma", "uic_masks", "uic_c8_wide", "uic_icp"])
 def test_golden_single_level(name):
     """Inputs and expected outputs come from the reference itself (tests/golden/make_golden.py)."""
     g = load_golden(name)
@@ -67,8 +67,13 @@ def test_golden_single_level(name):
     if f[2]:
         kw = dict(obj_mask0=[g["obj_mask0"].to(DEV)], obj_mask1=[g["obj_mask1"].to(DEV)])
         okw = dict(obj_mask0=g["obj_mask0"].bool(), obj_mask1=g["obj_mask1"].bool())
-    res = run_cuda([lv], (g["R0"], g["t0"]), iters=f[3], remove_tru_sigma=bool(f[0]), **kw)
+    res = run_cuda([lv], (g["R0"], g["t0"]), iters=f[3], remove_tru_sigma=bool(f[0]), combine_icp=bool(f[1]), **kw)
     assert int(res.status.item()) == 0
+    # forward_residuals at the starting pose (reference alg:725-786)
+    loss = A.uic_residual_loss({k: v.to(DEV) for k, v in lv.items()}, (g["R0"].to(DEV), g["t0"].to(DEV)),
+                               remove_tru_sigma=bool(f[0]), combine_icp=bool(f[1]),
+                               obj_mask0=kw["obj_mask0"][0] if kw else None, obj_mask1=kw["obj_mask1"][0] if kw else None)
+    assert frob_rel(loss.cpu(), g["res_loss"]) < 1e-4, frob_rel(loss.cpu(), g["res_loss"])
     # against the reference's recorded iterations
     total_flips = 0
     for it in range(f[3]):
@@ -83,7 +88,8 @@ def test_golden_single_level(name):
     # and against the oracle, bit-exact masks
     trace = []
     O.uic_level((g["R0"], g["t0"]), lv["x0"], lv["x1"], lv["invD0"], lv["invD1"], lv["K"], lv["s0"], lv["s1"],
-                iters=f[3], remove_tru_sigma=bool(f[0]), trace=trace, **okw)
+                iters=f[3], remove_tru_sigma=bool(f[0]), combine_icp=bool(f[1]), depth0=lv.get("depth0"),
+                depth1=lv.get("depth1"), trace=trace, **okw)
     assert compare_level(res, trace, 0, 0, f[3], exact_pose_inputs=True) == 0
 
 
