@@ -17,7 +17,7 @@ PKG_DIR = os.path.dirname(os.path.abspath(__file__))
 REPO_DIR = os.path.dirname(PKG_DIR)
 CSRC = os.path.join(PKG_DIR, "csrc")
 LIB_PATH = os.path.join(PKG_DIR, "libdpft.so")
-SOURCES = ["dpft_abi.cu", "uic_forward.cu", "uic_backward.cu", "icp_term.cu", "uic_residual.cu"]
+SOURCES = ["dpft_abi.cu", "uic_forward.cu", "uic_backward.cu", "icp_term.cu", "uic_residual.cu", "ic_path.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "-Xcompiler", "-fPIC", "-shared"]
 
@@ -124,6 +124,16 @@ def lib() -> ctypes.CDLL:
     L.dpft_uic_residual_loss.argtypes = [ctypes.POINTER(DpftLevel), ctypes.c_int, ctypes.c_int, ctypes.c_uint32,
                                          ctypes.c_float, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p,
                                          ctypes.c_size_t, ctypes.c_void_p]
+    vp, ci = ctypes.c_void_p, ctypes.c_int
+    lp = ctypes.POINTER(DpftLevel)
+    for name, args in (("dpft_ic_gradients", [lp, ci, ci, vp, vp, vp]),
+                       ("dpft_ic_residual", [lp, ci, ci, vp, vp, vp, vp]),
+                       ("dpft_ic_normal_matrix", [lp, ci, ci, vp, vp, vp, vp, vp]),
+                       ("dpft_ic_rhs", [lp, ci, ci, vp, vp, vp, vp, ci, vp, vp]),
+                       ("dpft_ic_update", [ci, ci, ci, vp, vp, vp, vp, vp, vp, vp, vp, vp])):
+        fn = getattr(L, name)
+        fn.restype = ctypes.c_int
+        fn.argtypes = args
     if L.dpft_abi_version() != DPFT_ABI_VERSION:
         raise RuntimeError("libdpft.so ABI version mismatch; rebuild")
     _lib = L
@@ -134,7 +144,8 @@ def exported_symbols() -> List[str]:
     """Entry points include/dpft.h declares (kept in sync by tests/test_abi.py)."""
     return ["dpft_abi_version", "dpft_last_error", "dpft_uic_workspace_bytes", "dpft_uic_forward",
             "dpft_uic_forward_timed", "dpft_uic_backward_workspace_bytes", "dpft_uic_backward",
-            "dpft_uic_residual_workspace_bytes", "dpft_uic_residual_loss"]
+            "dpft_uic_residual_workspace_bytes", "dpft_uic_residual_loss", "dpft_ic_gradients", "dpft_ic_residual",
+            "dpft_ic_normal_matrix", "dpft_ic_rhs", "dpft_ic_update"]
 
 
 def check(code: int, what: str) -> None:

@@ -367,15 +367,197 @@ class TrustRegionInverseWUncertainty(nn.Module):
                                  w_icp=self._icp_weight(), obj_mask0=obj_mask0, obj_mask1=obj_mask1)
 
 
+# ----------------------------------------------------------------------------- IC tracker (DeepIC baseline)
+def _fc(n_in, n_out):
+    return nn.Sequential(nn.Linear(n_in, n_out, True), nn.ReLU(inplace=True))
+
+
+class DirectSolverNet(nn.Module):
+    """Mirror of reference algorithms.py:1583-1691: holds the solver type and, for 'Direct-ResVol', the damping
+    MLP (same layer layout, so state_dict keys match).  The solve itself runs in TrustRegionBase below, which
+    reads ``type`` / ``samples`` / ``net`` from whichever DirectSolverNet (this one or the reference's) it is given
+    -- the reference's ``forward`` wants the dense (B,6,C*H*W) Jacobian, which this implementation never forms."""
+    SOLVER_NO_DAMPING = 0
+    SOLVER_RESIDUAL_VOLUME = 1
+
+    def __init__(self, solver_type, samples=10, direction='inverse'):
+        super().__init__()
+        self.direction = direction
+        if solver_type == 'Direct-Nodamping':
+            self.net = None
+            self.type = self.SOLVER_NO_DAMPING
+        elif solver_type == 'Direct-ResVol':
+            self.samples = samples
+            self.net = nn.Sequential(_fc(6 * 6 + 6 * samples, 128), _fc(128, 256), _fc(256, 6))
+            self.type = self.SOLVER_RESIDUAL_VOLUME
+            for m in self.net.modules():
+                if isinstance(m, nn.Linear):
+                    nn.init.xavier_uniform_(m.weight)
+        else:
+            raise NotImplementedError()
+
+    def forward(self, *args, **kwargs):
+        raise NotImplementedError("called through TrustRegionBase, which never materialises the dense Jacobian")
+
+
+class _IcLevel:
+    """One pyramid level of the IC tracker on the device: converted inputs, the unit gradients of x0, and thin
+    wrappers of the dpft_ic_* entry points."""
+
+    def __init__(self, x0, x1, invD0, invD1, K, obj_mask0=None, obj_mask1=None):
+        self.L = _lib.lib()
+        self.t = {k: _dev_f32(v, k) for k, v in dict(x0=x0, x1=x1, invD0=invD0, invD1=invD1, K=K).items()}
+        self.B, self.C, self.H, self.W = (int(v) for v in self.t["x0"].shape)
+        self.dev = self.t["x0"].device
+        self.m0, self.m1 = _dev_mask(obj_mask0, "obj_mask0"), _dev_mask(obj_mask1, "obj_mask1")
+        self.gx = torch.empty_like(self.t["x0"])
+        self.gy = torch.empty_like(self.t["x0"])
+        self.status = torch.zeros((1,), dtype=torch.int32, device=self.dev)
+        self._call("dpft_ic_gradients", self._arr(False), self.B, self.C, self.gx.data_ptr(), self.gy.data_ptr())
+
+    def _arr(self, use_mask0):
+        arr = (_lib.DpftLevel * 1)()
+        a, t = arr[0], self.t
+        a.x0, a.x1, a.invd0, a.invd1, a.K = (t[k].data_ptr() for k in ("x0", "x1", "invD0", "invD1", "K"))
+        a.obj_mask0 = self.m0.data_ptr() if (use_mask0 and self.m0 is not None) else None
+        a.obj_mask1 = self.m1.data_ptr() if self.m1 is not None else None
+        a.H, a.W = self.H, self.W
+        return arr
+
+    def _call(self, name, *args):
+        with torch.cuda.device(self.dev):
+            code = getattr(self.L, name)(*args, torch.cuda.current_stream(self.dev).cuda_stream)
+        _lib.check(code, name)
+
+    def residual(self, pose_rows, first):
+        """(r (B,C,H,W), occ bool (B,1,H,W)); the keyframe object mask only counts on the first call (alg:65-66, 86-87)."""
+        r = torch.empty_like(self.t["x0"])
+        occ = torch.empty((self.B, 1, self.H, self.W), dtype=torch.uint8, device=self.dev)
+        self._call("dpft_ic_residual", self._arr(first), self.B, self.C, pose_rows.data_ptr(), r.data_ptr(), occ.data_ptr())
+        return r, occ.bool()
+
+    def _w(self, weights):
+        if weights is None:
+            return None
+        return _dev_f32(weights.expand(self.B, self.C, self.H, self.W), "weights")
+
+    def normal_matrix(self, weights):
+        A21 = torch.empty((self.B, 21), dtype=torch.float32, device=self.dev)
+        w = self._w(weights)
+        self._call("dpft_ic_normal_matrix", self._arr(False), self.B, self.C, self.gx.data_ptr(), self.gy.data_ptr(),
+                   w.data_ptr() if w is not None else None, A21.data_ptr())
+        return A21
+
+    def rhs(self, weights, poses):
+        S = int(poses.shape[0])
+        out = torch.empty((S, self.B, 6), dtype=torch.float32, device=self.dev)
+        w = self._w(weights)
+        self._call("dpft_ic_rhs", self._arr(False), self.B, self.C, self.gx.data_ptr(), self.gy.data_ptr(),
+                   w.data_ptr() if w is not None else None, poses.data_ptr(), S, out.data_ptr())
+        return out
+
+    def update(self, mode, A21, rhs, pose_rows, lambdas=None, damp=None):
+        S = int(lambdas.numel()) if mode == 1 else 1
+        out = torch.empty((S, self.B, 12), dtype=torch.float32, device=self.dev)
+        with torch.cuda.device(self.dev):
+            code = self.L.dpft_ic_update(self.B, S, mode, A21.data_ptr(), rhs.data_ptr(),
+                                         lambdas.data_ptr() if lambdas is not None else None,
+                                         damp.data_ptr() if damp is not None else None, pose_rows.data_ptr(),
+                                         out.data_ptr(), None, self.status.data_ptr(),
+                                         torch.cuda.current_stream(self.dev).cuda_stream)
+        _lib.check(code, "dpft_ic_update")
+        return out
+
+
+def _tri_to_full(A21: torch.Tensor) -> torch.Tensor:
+    A = A21.new_zeros(A21.shape[:-1] + (6, 6))
+    for k, (i, j) in enumerate(_TRI):
+        A[..., i, j] = A21[..., k]
+        A[..., j, i] = A21[..., k]
+    return A
+
+
+def _avg_loss(res_list, invalid):
+    """compute_avg_loss (alg:2119-2137) on device tensors."""
+    B, _, H, W = invalid.shape
+    n_valid = H * W - invalid.sum(dim=[2, 3]).squeeze()
+    tot = torch.zeros_like(invalid, dtype=torch.float32)
+    for r in res_list:
+        tot = tot + (torch.where(invalid, torch.zeros_like(r), r) ** 2).sum(dim=1, keepdim=True)
+    return tot.sum(dim=[2, 3], keepdim=True).squeeze() / n_valid
+
+
+class TrustRegionBase(nn.Module):
+    """Drop-in for reference algorithms.py:23-139 (track_type 'IC', the DeepIC baseline).  ``mEst_func`` is called
+    exactly as the reference calls it (a module taking the residual map, x0, x1 and the weight prior; ``None``
+    means constant ones); ``solver_func`` supplies type / samples / damping MLP (see DirectSolverNet)."""
+
+    def __init__(self, max_iter=3, mEst_func=None, solver_func=None, timers=None):
+        super().__init__()
+        self.max_iterations = max_iter
+        self.mEstimator = mEst_func
+        self.directSolver = solver_func
+        self.timers = timers
+
+    def _weights(self, r, x0, x1, wPrior):
+        if self.mEstimator is None:
+            return None
+        return self.mEstimator(r, x0, x1, wPrior)
+
+    def forward(self, pose, x0, x1, invD0, invD1, K, wPrior=None, vis_res=False, obj_mask0=None, obj_mask1=None):
+        if torch.is_grad_enabled() and any(t.requires_grad for t in (x0, x1, pose[0], pose[1])):
+            raise NotImplementedError("the IC tracker is forward-only here (DESIGN.md: backward exists for U_IC)")
+        solver = self.directSolver
+        if solver is not None and getattr(solver, "direction", "inverse") != "inverse":
+            raise NotImplementedError("pose updated should be inverse for this tracker")
+        lvl = _IcLevel(x0, x1, invD0, invD1, K, obj_mask0, obj_mask1)
+        rows = pack_pose(pose).to(lvl.dev)
+        if self.timers: self.timers.tic('compute warping residuals')
+        r, occ = lvl.residual(rows, first=True)
+        if self.timers: self.timers.toc('compute warping residuals')
+        weights = self._weights(r, lvl.t["x0"], lvl.t["x1"], wPrior)
+        A21 = lvl.normal_matrix(weights)
+        kind = getattr(solver, "type", 0) if solver is not None else 0
+        for _ in range(self.max_iterations):
+            if self.timers: self.timers.tic('solve x=A^{-1}b')
+            b0 = lvl.rhs(weights, rows.unsqueeze(0))[0]
+            if kind == 0:
+                rows = lvl.update(0, A21, b0, rows)[0]
+            else:
+                S = int(solver.samples)
+                lambdas = torch.logspace(-5, 5, S).to(device=lvl.dev, dtype=torch.float32)
+                trial = lvl.update(1, A21, b0, rows, lambdas=lambdas)              # (S,B,12)
+                vol = lvl.rhs(weights, trial)                                      # (S,B,6)
+                feat = torch.cat((vol.permute(1, 2, 0).reshape(lvl.B, 6 * S), _tri_to_full(A21).reshape(lvl.B, 36)), dim=1)
+                damp = solver.net(feat).float().contiguous()
+                rows = lvl.update(2, A21, b0, rows, damp=damp)[0]
+            if self.timers: self.timers.toc('solve x=A^{-1}b')
+        if weights is None:
+            weights = torch.ones((1, 1, 1, 1), dtype=torch.float32, device=lvl.dev).expand(x0.shape)
+        return unpack_pose(rows), weights
+
+    def forward_residuals(self, pose, x0, x1, invD0, invD1, K, wPrior=None, vis_res=False, obj_mask0=None,
+                          obj_mask1=None):
+        lvl = _IcLevel(x0, x1, invD0, invD1, K, obj_mask0, obj_mask1)
+        r, occ = lvl.residual(pack_pose(pose).to(lvl.dev), first=True)
+        w = self._weights(r, lvl.t["x0"], lvl.t["x1"], wPrior)
+        return _avg_loss([r if w is None else w * r], occ)
+
+
 def patch_tracker(net: nn.Module) -> nn.Module:
-    """Swap the ``tr_update0..3`` children of a reference ``LeastSquareTracking`` (U_IC) for the CUDA-backed
+    """Swap the ``tr_update0..3`` children of a reference ``LeastSquareTracking`` (U_IC or IC) for the CUDA-backed
     modules, keeping their learned sub-modules so ``state_dict`` keys are unchanged."""
     for i in range(4):
         name = f"tr_update{i}"
         old = getattr(net, name)
-        if type(old).__name__ != "TrustRegionInverseWUncertainty":
-            raise NotImplementedError(f"{name} is a {type(old).__name__}; only the U_IC tracker is built so far")
-        new = TrustRegionInverseWUncertainty(old.max_iterations, old.mEstimator, old.directSolver, old.timers,
-                                             old.uncer_prop, old.combine_icp, old.scale_func, old.remove_tru_sigma)
+        kind = type(old).__name__
+        if kind == "TrustRegionInverseWUncertainty":
+            new = TrustRegionInverseWUncertainty(old.max_iterations, old.mEstimator, old.directSolver, old.timers,
+                                                 old.uncer_prop, old.combine_icp, old.scale_func,
+                                                 old.remove_tru_sigma)
+        elif kind == "TrustRegionBase":
+            new = TrustRegionBase(old.max_iterations, old.mEstimator, old.directSolver, old.timers)
+        else:
+            raise NotImplementedError(f"{name} is a {kind}: only the U_IC and IC trackers are on this path")
         setattr(net, name, new)
     return net

@@ -98,6 +98,33 @@ int dpft_uic_forward(const dpft_level_t *levels, int n_levels, int B, int C, int
                      int32_t *status, void *workspace, size_t workspace_bytes, void *stream);
 
 /*
+ * IC tracker (TrustRegionBase alg:45-139 + DirectSolverNet alg:1604-1691), split around the learned networks
+ * the reference calls inside the loop.  `level` needs x0, x1, invd0, invd1, K (+ optional object masks).
+ *   dpft_ic_gradients      gx, gy (B,C,H,W) <- unit Sobel gradient of x0 (feature_gradient, alg:1844-1865)
+ *   dpft_ic_residual       r_out (B,C,H,W) <- x1(warp) - x0, 1e-3 where masked; occ_out (B,H,W) the mask
+ *                          (compute_warped_residual, alg:1919-1957)
+ *   dpft_ic_normal_matrix  A21 (B,21) <- upper triangle of sum w J J^T, J_c = gx_c du/dxi + gy_c dv/dxi;
+ *                          weights (B,C,H,W) or NULL for ones (alg:71-75)
+ *   dpft_ic_rhs            rhs (S,B,6) <- sum w J r(pose_s) for poses (S,B,12) (alg:1623-1624, 1682-1683)
+ *   dpft_ic_update         pose_out (S,B,12) <- inverse-compositional update of pose_in (B,12) with
+ *                          xi = H^-1 rhs (rhs: (B,6)), H = A + D + 1e-6 tr(A) I and
+ *                            mode 0: D = 0 (S = 1)                      lev_mar_H, alg:2094-2103
+ *                            mode 1: D = lambdas[s] diag(A)              residual-volume trials, alg:1676-1680
+ *                            mode 2: D = diag(damp[b]), damp (B,6), S=1  learned damping, alg:1688-1691
+ *                          H_out (S,B,21) optional.
+ */
+int dpft_ic_gradients(const dpft_level_t *level, int B, int C, float *gx, float *gy, void *stream);
+int dpft_ic_residual(const dpft_level_t *level, int B, int C, const float *pose, float *r_out, uint8_t *occ_out,
+                     void *stream);
+int dpft_ic_normal_matrix(const dpft_level_t *level, int B, int C, const float *gx, const float *gy,
+                          const float *weights, float *A21, void *stream);
+int dpft_ic_rhs(const dpft_level_t *level, int B, int C, const float *gx, const float *gy, const float *weights,
+                const float *poses, int S, float *rhs, void *stream);
+int dpft_ic_update(int B, int S, int mode, const float *A21, const float *rhs, const float *lambdas,
+                   const float *damp, const float *pose_in, float *pose_out, float *H_out, int32_t *status,
+                   void *stream);
+
+/*
  * forward_residuals of the U_IC tracker (alg:725-786 with compute_avg_loss alg:2119-2137): per frame pair the
  * sum over valid pixels of the squared uncertainty-weighted residuals (plus the squared weighted point-to-plane
  * residual with DPFT_COMBINE_ICP) divided by the number of valid pixels, at the given pose.  loss: (B).
