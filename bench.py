@@ -128,7 +128,7 @@ def views(flat, layout, n_levels):
     return out
 
 
-def cpu_sample(levels, R0, t0, n_pairs, min_seconds=8.0, max_reps=4):
+def cpu_sample(levels, R0, t0, n_pairs, min_seconds=10.0, max_reps=500):
     """Time the oracle port (reference op chain: grid_sample + permute/bmm/sum) on the host cores."""
     from oracle import ic_oracle as O
     threads = os.cpu_count() or 1
@@ -154,6 +154,72 @@ def cpu_sample(levels, R0, t0, n_pairs, min_seconds=8.0, max_reps=4):
     return n_pairs / min(times), threads, times
 
 
+def train_step_leg(A, dev_sets, pose0, B, steps, dev):
+    """Solver part of a training step (BASELINE config 4): forward + backward through all 12 iterations, loss =
+    a linear functional of every level's pose (what criterions.py:101-136 feeds back)."""
+    import torch
+    leaves = [[{k: (v.clone().requires_grad_(True) if k in ("x0", "x1", "s0", "s1") else v) for k, v in lv.items()}
+               for lv in s] for s in dev_sets[:2]]
+    R = pose0[0].clone().requires_grad_(True)
+    t = pose0[1].clone().requires_grad_(True)
+
+    def step(i):
+        for lv in leaves[i % 2]:
+            for k in ("x0", "x1", "s0", "s1"):
+                lv[k].grad = None
+        outs = A.uic_track(leaves[i % 2], (R, t), iters=ITERS, remove_tru_sigma=True, check=False)
+        loss = sum(Rl.sum() + tl.sum() for Rl, tl, _ in outs)
+        loss.backward()
+
+    for i in range(3):
+        step(i)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(steps):
+        step(i)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / steps
+    return {"what": "solver forward+backward (autograd through 4 levels x 3 iterations), per GPU", "ms_per_step": ms,
+            "pairs_per_s": B / (ms * 1e-3), "steps": steps}
+
+
+def vga_leg(A, rank, dev, args):
+    """BASELINE config 3 shape: 480x640 pairs, 16 per call (a 128-pair shard is 8 such calls)."""
+    import torch
+    from deep_prob_feature_track_b200.synthetic import make_frame_pairs
+    wl = WORKLOADS["vga"]
+    B, C, H, W = wl["B"], wl["C"], wl["H"], wl["W"]
+    data = make_frame_pairs(B, C, H, W, seed=99 + rank, n_levels=N_LEVELS)
+    sets = []
+    for s in range(2):
+        sets.append([{k: torch.roll(v, s, 0).to(dev) for k, v in lv.items()} for lv in data["levels"]])
+    pose0 = (data["R0"].to(dev), data["t0"].to(dev))
+
+    def solve(i, **kw):
+        return A.uic_solve(sets[i % 2], pose0, iters=ITERS, remove_tru_sigma=True, pdl=not args.no_pdl,
+                           fused_sobel=args.fused_sobel, **kw)
+
+    for i in range(3):
+        solve(i)
+    torch.cuda.synchronize()
+    n = 10
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(n):
+        solve(i)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / n
+    r = solve(0, timed=True)
+    bytes_step, bytes_lvl0 = algorithmic_bytes(B, C, H, W)
+    lvl0 = sum(r.launch_ms[-ITERS:]) / ITERS
+    return {"workload": wl["name"], "ms_per_step": ms, "pairs_per_s": B / (ms * 1e-3),
+            "lvl0_launch_ms": lvl0, "lvl0_algorithmic_GBps": bytes_lvl0 / (lvl0 * 1e-3) / 1e9,
+            "step_algorithmic_GBps": bytes_step / (ms * 1e-3) / 1e9}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -163,9 +229,12 @@ def main():
     ap.add_argument("--workload", default="tum", choices=tuple(WORKLOADS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-pdl", action="store_true")
-    ap.add_argument("--fused-sobel", action="store_true", help="use the sliding-window kernel (DPFT_FUSED_SOBEL)")
+    ap.add_argument("--materialised", action="store_true",
+                    help="materialise the unit Sobel gradients once per level instead of the fused sliding-window kernel")
+    ap.add_argument("--no-extras", action="store_true", help="skip the training-step and 480x640 side measurements")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
+    args.fused_sobel = not args.materialised
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -220,6 +289,7 @@ def main():
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=dev)
     from deep_prob_feature_track_b200 import algorithms as A
+    from deep_prob_feature_track_b200.sharding import max_over_ranks
 
     data = make_frame_pairs(B, C, H, W, seed=1234 + rank, n_levels=N_LEVELS)
     host_flat, layout = pack_levels(data["levels"], pin=True)
@@ -258,10 +328,7 @@ def main():
         barrier()
         ms = e0.elapsed_time(e1)
         res.raise_if_bad()
-        if world > 1:
-            t = torch.tensor([ms], device=dev)
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            ms = float(t.item())
+        ms = max_over_ranks(ms, dev)
 
         # ---- roofline: device time of every GN launch (events around each launch; separate pass)
         lvl0 = []
@@ -294,10 +361,15 @@ def main():
         e1.record()
         barrier()
         ms_e2e = e0.elapsed_time(e1)
-        if world > 1:
-            t = torch.tensor([ms_e2e], device=dev)
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            ms_e2e = float(t.item())
+        ms_e2e = max_over_ranks(ms_e2e, dev)
+
+        # ---- side measurements (not the headline): training step of the same workload, 480x640 pairs
+        extras = {}
+        if not args.no_extras:
+            extras["train_step"] = train_step_leg(A, dev_sets, pose0, B, max(3, min(args.steps, 20)), dev)
+            if args.workload == "tum":
+                del dev_flat, dev_views
+                extras["vga480x640"] = vga_leg(A, rank, dev, args)
 
     if rank != 0:
         if world > 1:
@@ -325,7 +397,9 @@ def main():
                    "algorithmic_bytes_per_step": bytes_step},
         "step_hbm_frac": bytes_step / (ms / args.steps * 1e-3) / 1e9 / peak,
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                     "traffic": None, "kernel": "uic_iter_kernel<8,true> at the finest level",
+                     "traffic": 170.7e6 if args.fused_sobel else 328.3e6,
+                     "traffic_source": "ncu --set full dram__bytes_read+write per launch, profiles/r1b_* (fused) / r1c_* (materialised)",
+                     "kernel": ("uic_iter_kernel<8,true>" if args.fused_sobel else "uic_iter_px_kernel<8,true>") + " at the finest level",
                      "algorithmic_bytes_per_launch": bytes_lvl0, "launch_ms": lvl0_ms,
                      "all_launch_ms": [round(x, 4) for x in per_launch], "peak_source": peak_src,
                      "how": "CUDA events around every launch (dpft_uic_forward_timed), separate pass after the timed region"},
@@ -333,6 +407,7 @@ def main():
                 "d2h_bytes_per_step": B * 12 * 4, "steps": n_e2e, "ms_per_step": ms_e2e / n_e2e},
         "gpu_launches": launches_per_step * args.steps,
         "clocks": clocks.summary(),
+        "extra": extras,
     }
     if not args.no_cpu_baseline:
         n_cpu = min(B, 16 if args.workload == "tum" else 1)

@@ -91,7 +91,12 @@ __device__ void finalize_pair(const UicIterParams& p, int b, float gmin, float g
 #pragma unroll
   for (int i = 0; i < 6; ++i) sys[21 + i] = (float)rhs[i];
   double xi[6];
+#ifdef DPFT_EXPERIMENT_SKIP_SOLVE
+  bool ok = true;
+  for (int i = 0; i < 12; ++i) p.pose_next[(size_t)b * 12 + i] = p.pose[(size_t)b * 12 + i];
+#else
   const bool ok = solve_and_update(A, rhs, true, p.pose + (size_t)b * 12, p.pose_next + (size_t)b * 12, xi);
+#endif
   int st = 0;
   if (!finite) st |= DPFT_ST_NONFINITE;
   if (!ok) st |= DPFT_ST_SINGULAR;
