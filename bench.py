@@ -199,7 +199,7 @@ def vga_leg(A, rank, dev, args):
 
     def solve(i, **kw):
         return A.uic_solve(sets[i % 2], pose0, iters=ITERS, remove_tru_sigma=True, pdl=not args.no_pdl,
-                           fused_sobel=args.fused_sobel, **kw)
+                           fused_sobel=args.fused_sobel, single_launch=not args.per_iteration, **kw)
 
     for i in range(3):
         solve(i)
@@ -231,6 +231,8 @@ def main():
     ap.add_argument("--no-pdl", action="store_true")
     ap.add_argument("--materialised", action="store_true",
                     help="materialise the unit Sobel gradients once per level instead of the fused sliding-window kernel")
+    ap.add_argument("--per-iteration", action="store_true",
+                    help="one launch per Gauss-Newton iteration instead of the single cooperative launch")
     ap.add_argument("--no-extras", action="store_true", help="skip the training-step and 480x640 side measurements")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
@@ -304,15 +306,17 @@ def main():
 
     def solve(levels, **kw):
         return A.uic_solve(levels, pose0, iters=ITERS, remove_tru_sigma=True, pdl=not args.no_pdl, fused_sobel=args.fused_sobel,
-                           **kw)
+                           single_launch=not args.per_iteration, **kw)
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
-    # init + sigma0 min/max per level + GN launches (+ 2 Sobel launches per level when gradients are materialised)
-    launches_per_step = 1 + N_LEVELS + N_LEVELS * ITERS + (0 if args.fused_sobel else 2 * N_LEVELS)
+    # init + sigma0 min/max per level, then either ONE cooperative launch for all 12 iterations (+ its init) or
+    # one launch per iteration (+ 2 Sobel launches per level when gradients are materialised)
+    single = args.fused_sobel and not args.per_iteration
+    launches_per_step = 1 + N_LEVELS + (2 if single else N_LEVELS * ITERS + (0 if args.fused_sobel else 2 * N_LEVELS))
 
     with ClockSampler(local_rank) as clocks:
         # ---- value: inputs resident in HBM
@@ -393,6 +397,7 @@ def main():
                    "resolution": f"{H}x{W}", "levels": N_LEVELS, "iters_per_level": ITERS, "variant": "U_IC",
                    "remove_tru_sigma": True, "pdl": not args.no_pdl,
                    "sobel": "fused" if args.fused_sobel else "materialised once per level",
+                   "launch": "single cooperative launch for all levels and iterations" if single else "one launch per iteration",
                    "l2": f"inputs rotate over {N_SETS} resident sets of {set_bytes / 1e6:.0f} MB each (> 126 MB L2)",
                    "algorithmic_bytes_per_step": bytes_step},
         "step_hbm_frac": bytes_step / (ms / args.steps * 1e-3) / 1e9 / peak,
@@ -402,7 +407,8 @@ def main():
                      "kernel": ("uic_iter_kernel<8,true>" if args.fused_sobel else "uic_iter_px_kernel<8,true>") + " at the finest level",
                      "algorithmic_bytes_per_launch": bytes_lvl0, "launch_ms": lvl0_ms,
                      "all_launch_ms": [round(x, 4) for x in per_launch], "peak_source": peak_src,
-                     "how": "CUDA events around every launch (dpft_uic_forward_timed), separate pass after the timed region"},
+                     "how": ("%globaltimer stamps at the iteration boundaries inside the single cooperative launch"
+                             if single else "CUDA events around every launch") + " (dpft_uic_forward_timed), separate pass after the timed region"},
         "e2e": {"value": world * B * n_e2e / (ms_e2e * 1e-3), "unit": "pairs/s", "h2d_bytes_per_step": set_bytes,
                 "d2h_bytes_per_step": B * 12 * 4, "steps": n_e2e, "ms_per_step": ms_e2e / n_e2e},
         "gpu_launches": launches_per_step * args.steps,

@@ -17,7 +17,7 @@ PKG_DIR = os.path.dirname(os.path.abspath(__file__))
 REPO_DIR = os.path.dirname(PKG_DIR)
 CSRC = os.path.join(PKG_DIR, "csrc")
 LIB_PATH = os.path.join(PKG_DIR, "libdpft.so")
-SOURCES = ["dpft_abi.cu", "uic_forward.cu", "uic_backward.cu", "icp_term.cu", "uic_residual.cu", "ic_path.cu"]
+SOURCES = ["dpft_abi.cu", "uic_forward.cu", "uic_backward.cu", "icp_term.cu", "uic_residual.cu", "ic_path.cu", "uic_persistent.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "-Xcompiler", "-fPIC", "-shared"]
 
@@ -27,6 +27,7 @@ DPFT_REMOVE_TRU_SIGMA = 0x01
 DPFT_COMBINE_ICP = 0x02
 DPFT_NO_PDL = 0x04
 DPFT_FUSED_SOBEL = 0x08
+DPFT_LAUNCH_PER_ITERATION = 0x10
 DPFT_ST_NONFINITE = 0x01
 DPFT_ST_SINGULAR = 0x02
 

@@ -18,4 +18,24 @@ void launch_icp_term(const float* depth0, const float* K, const float* V1, const
                      const uint8_t* m0, const uint8_t* m1, float* rec, uint8_t* occ_out, float* r_out, int B, int H,
                      int W, cudaStream_t stream);
 
+// ---- persistent (single cooperative launch) U_IC forward, uic_persistent.cu
+struct PLevel {
+  const float *x0, *x1, *s0, *s1, *d0, *d1, *K;
+  const uint8_t *m0, *m1;
+  int H, W, nseg, nrt, TR, tpp;   // tpp = warp tiles per pair
+};
+struct PersistParams {
+  PLevel lv[8];
+  int n_levels, iters, B, C, rcap;   // rcap = record slots per pair
+  float *pose_hist, *sys_hist, *aux;
+  float* records;                    // (B, rcap, PS)
+  double* pairrec;                   // (B, PS)
+  const uint32_t* s0mm;              // per level: order-encoded min, max of sigma0
+  uint32_t* gext;                    // per iteration: order-encoded min, max of the warped sigma (pre-initialised)
+  int32_t* status;
+  unsigned long long* clock_out;     // optional (n_it + 1) %globaltimer stamps at the iteration boundaries
+};
+int persistent_grid(int C, bool tru);   // CTAs that can be co-resident on the current device
+cudaError_t launch_persistent(const PersistParams& prm, int grid, bool tru, cudaStream_t stream);
+
 }  // namespace dpft

@@ -17,20 +17,25 @@
 #include <stdint.h>
 
 #include <algorithm>
+#include <cstdlib>
 
 #include "dpft.h"
 #include "dpft_device.cuh"
 #include "dpft_host.h"
 #include "dpft_kernels.h"
+#include "dpft_records.h"
+#include "uic_tile.cuh"
+
+#ifndef DPFT_MIN_CTAS
+#define DPFT_MIN_CTAS 4   // 128-thread CTAs per SM the register allocation must allow
+#endif
 
 namespace dpft {
 
 constexpr int kWarps = 4;
 constexpr int kThreads = kWarps * 32;
-constexpr int kCols = 30;          // output columns per warp tile
-constexpr int PS = 48;             // floats per partial record
-constexpr int NSUM = 39;           // 21 A + 6 b + 6 corr(min) + 6 corr(max)
-constexpr int E_VMIN = 27, E_VMAX = 28, E_CMIN = 29, E_CMAX = 35;
+constexpr int kCols = kTileCols;   // output columns per warp tile
+constexpr int kMaxTileRows = 24;
 
 struct UicIterParams {
   const float *x0, *x1, *s0, *s1, *d0, *d1, *K;
@@ -274,206 +279,43 @@ __device__ __forceinline__ void reduce_and_finish(const UicIterParams& p, const 
   for (int i = threadIdx.x; i < p.B; i += kThreads) finalize_pair<true>(p, i, s_pair_mm[0], s_pair_mm[1]);
 }
 
-#ifndef DPFT_MIN_CTAS
-#define DPFT_MIN_CTAS 4   // 128-thread CTAs per SM the register allocation must allow
-#endif
-
 template <int CH, bool TRU>
 __global__ void __launch_bounds__(kThreads, DPFT_MIN_CTAS) uic_iter_kernel(const UicIterParams p) {
-
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int b = blockIdx.y;
-  const int H = p.H, W = p.W, C = p.C;
-  const size_t plane = (size_t)H * W;
-  const int iplane = H * W;
-
+  const int plane = p.H * p.W;
   const int wt = blockIdx.x * kWarps + warp;
   const bool warp_on = wt < p.nseg * p.nrt;
   const int seg = warp_on ? wt % p.nseg : 0;
   const int rt = warp_on ? wt / p.nseg : 0;
-  const int x = seg * kCols - 1 + lane;
-  const int xc = min(max(x, 0), W - 1);
-  const bool col_out = warp_on && lane >= 1 && lane <= kCols && x < W;
   const int y0 = rt * p.TR;
-  const int y1 = warp_on ? min(y0 + p.TR, H) : y0;
+  const int y1 = warp_on ? min(y0 + p.TR, p.H) : y0;
 
-  const float fx = __ldg(p.K + 4 * b), fy = __ldg(p.K + 4 * b + 1);
-  const float cx = __ldg(p.K + 4 * b + 2), cy = __ldg(p.K + 4 * b + 3);
-  const float px = xdiv(xsub((float)xc, cx), fx);
+  PairView g;
+  const size_t po = (size_t)b * p.C * plane;
+  g.x0 = p.x0 + po; g.x1 = p.x1 + po; g.s0 = p.s0 + po; g.s1 = p.s1 + po;
+  g.d0 = p.d0 + (size_t)b * plane; g.d1 = p.d1 + (size_t)b * plane;
+  g.m0 = p.m0 ? p.m0 + (size_t)b * plane : nullptr;
+  g.m1 = p.m1 ? p.m1 + (size_t)b * plane : nullptr;
+  g.occ_out = p.occ_out ? p.occ_out + (size_t)b * plane : nullptr;
+  g.sr0_dbg = p.sr0_dbg ? p.sr0_dbg + (size_t)b * plane : nullptr;
+  g.H = p.H; g.W = p.W; g.C = p.C;
+  g.fx = __ldg(p.K + 4 * b); g.fy = __ldg(p.K + 4 * b + 1); g.cx = __ldg(p.K + 4 * b + 2); g.cy = __ldg(p.K + 4 * b + 3);
+  g.s0lo = g.s0hi = 0.f;
 
-  float acc[27];
-#pragma unroll
-  for (int i = 0; i < 27; ++i) acc[i] = 0.f;
-  float cmn[6], cmx[6];
-#pragma unroll
-  for (int i = 0; i < 6; ++i) cmn[i] = cmx[i] = 0.f;
-  float vmin = CUDART_INF_F, vmax = -CUDART_INF_F;
-
-  const float* d0p = p.d0 + (size_t)b * plane;
-  const float* d1p = p.d1 + (size_t)b * plane;
-  const uint8_t* m0p = p.m0 ? p.m0 + (size_t)b * plane : nullptr;
-  const uint8_t* m1p = p.m1 ? p.m1 + (size_t)b * plane : nullptr;
-  float s0lo = 0.f, s0hi = 0.f;
-  Pose pose;
-
-  // let the next iteration's launch become resident as soon as every CTA of this one has started
+  // let the next iteration's launch become resident as soon as every CTA of this one has started; nothing
+  // before the dependency sync touches what the previous launch writes
   cudaTriggerProgrammaticLaunchCompletion();
-
-  for (int c0 = 0; c0 < C; c0 += CH) {
-    const float* X0 = p.x0 + ((size_t)b * C + c0) * plane;
-    const float* S0 = p.s0 + ((size_t)b * C + c0) * plane;
-    const float* X1 = p.x1 + ((size_t)b * C + c0) * plane;
-    const float* S1 = p.s1 + ((size_t)b * C + c0) * plane;
-
-    // 3-row sliding windows of the keyframe maps (own column): top / mid / (bot loaded per row)
-    float ft[CH], fm[CH], st[CH], sm[CH];
-    {
-      const int ot = max(y0 - 1, 0) * W + xc, om = min(y0, H - 1) * W + xc;
-#pragma unroll
-      for (int c = 0; c < CH; ++c) {
-        ft[c] = __ldg(X0 + (ot + c * iplane));
-        fm[c] = __ldg(X0 + (om + c * iplane));
-        st[c] = __ldg(S0 + (ot + c * iplane));
-        sm[c] = __ldg(S0 + (om + c * iplane));
-      }
-    }
-    if (c0 == 0) {
-      // everything above is independent of the previous launch: with programmatic dependent launch
-      // it overlaps that launch's tail.  The pose, sigma0's extremes and the scratch buffers are not.
-      cudaGridDependencySynchronize();
-      pose = load_pose(p.pose + (size_t)b * 12);
-      if (TRU) {
-        s0lo = ord2f(__ldcg(p.s0mm));
-        s0hi = ord2f(__ldcg(p.s0mm + 1));
-      }
-    }
-
-    for (int y = y0; y < y1; ++y) {
-      const int ob = min(y + 1, H - 1) * W + xc;
-      float fb[CH], sb[CH];
-#pragma unroll
-      for (int c = 0; c < CH; ++c) {
-        fb[c] = __ldg(X0 + (ob + c * iplane));
-        sb[c] = __ldg(S0 + (ob + c * iplane));
-      }
-      const int o = y * W + xc;
-      const float d0 = __ldg(d0p + o);
-      const float py = xdiv(xsub((float)y, cy), fy);
-
-      float u, v, inv_z;
-      warp_pixel(pose, px, py, d0, fx, fy, cx, cy, u, v, inv_z);
-      const Tap tap = make_tap(u, v, H, W);
-      const float d1w = sample_exact(d1p, tap, W);
-      bool occ = occluded(u, v, inv_z, d1w, H, W);
-      if (m0p) occ = occ || (__ldg(m0p + o) == 0);
-      if (m1p) occ = occ || !(sample_mask(m1p, tap, W) > 0.f);
-      if (TRU) {
-        const float s0c0 = (c0 == 0) ? sm[0] : __ldg(p.s0 + (size_t)b * C * plane + o);
-        occ = occ || (s0c0 == s0lo) || (s0c0 == s0hi);
-      }
-
-      float saa = 0.f, sab = 0.f, sbb = 0.f, sar = 0.f, sbr = 0.f, sca = 0.f, scb = 0.f;
-      float pmin = CUDART_INF_F, pmax = -CUDART_INF_F, sr0 = 0.f;
-      constexpr int G = CH < 4 ? CH : 4;   // channels whose 8*G lookups are in flight together
-#pragma unroll
-      for (int g0 = 0; g0 < CH; g0 += G) {
-        // all lookups of this channel group first (one base address per plane, fixed offsets) ...
-        float xa[G], xb[G], xc_[G], xd[G], za[G], zb[G], zc[G], zd[G];
-#pragma unroll
-        for (int c = 0; c < G; ++c) {
-          // 32-bit element index from one base per tensor: one IMAD.WIDE per row of the footprint
-          const int ia = tap.o + (g0 + c) * iplane, ic = ia + W;
-          xa[c] = __ldg(X1 + ia); xb[c] = __ldg(X1 + ia + 1); xc_[c] = __ldg(X1 + ic); xd[c] = __ldg(X1 + ic + 1);
-          za[c] = __ldg(S1 + ia); zb[c] = __ldg(S1 + ia + 1); zc[c] = __ldg(S1 + ic); zd[c] = __ldg(S1 + ic + 1);
-        }
-        // ... then the keyframe-side math of the group, which does not need them
-        float gfx[G], gfy[G], gsx[G], gsy[G];
-#pragma unroll
-        for (int c = 0; c < G; ++c) {
-          const int k = g0 + c;
-          // unit Sobel gradient of x0 and sigma0 (algorithms.py:1844-1865), separable form:
-          // Sx = vs(x+1) - vs(x-1), Sy = vd(x-1) + 2 vd(x) + vd(x+1), vs = t+2m+b, vd = b-t
-          const float fvs = ft[k] + 2.f * fm[k] + fb[k], fvd = fb[k] - ft[k];
-          const float svs = st[k] + 2.f * sm[k] + sb[k], svd = sb[k] - st[k];
-          const float fSx = __shfl_down_sync(0xffffffffu, fvs, 1) - __shfl_up_sync(0xffffffffu, fvs, 1);
-          const float fSy = __shfl_up_sync(0xffffffffu, fvd, 1) + 2.f * fvd + __shfl_down_sync(0xffffffffu, fvd, 1);
-          const float sSx = __shfl_down_sync(0xffffffffu, svs, 1) - __shfl_up_sync(0xffffffffu, svs, 1);
-          const float sSy = __shfl_up_sync(0xffffffffu, svd, 1) + 2.f * svd + __shfl_down_sync(0xffffffffu, svd, 1);
-          const float fin = rsqrtf(fmaf(fSx, fSx, fmaf(fSy, fSy, 1e-8f)));
-          const float sin_ = rsqrtf(fmaf(sSx, sSx, fmaf(sSy, sSy, 1e-8f)));
-          gfx[c] = fSx * fin; gfy[c] = fSy * fin; gsx[c] = sSx * sin_; gsy[c] = sSy * sin_;
-        }
-#pragma unroll
-        for (int c = 0; c < G; ++c) {
-          const int k = g0 + c;
-          const float fr = blend_fast(xa[c], xb[c], xc_[c], xd[c], tap);
-          // sigma is compared for equality against its batch extremes -> mask-grade arithmetic
-          const float sr = TRU ? blend_exact(za[c], zb[c], zc[c], zd[c], tap) : blend_fast(za[c], zb[c], zc[c], zd[c], tap);
-          // residual, its uncertainty and the 2-vector d(wres)/d(u,v) (algorithms.py:1969-1972, :872)
-          const float res = fr - fm[k];
-          const float s0v = sm[k];
-          const float rs = rsqrtf(fmaf(sr, sr, s0v * s0v));   // 1 / sigma
-          const float wres = res * rs;
-          const float q = wres * (s0v * (rs * rs));           // res * sigma0 / sigma^3
-          const float a = fmaf(gfx[c], rs, q * gsx[c]);
-          const float bq = fmaf(gfy[c], rs, q * gsy[c]);
-          const float wm = occ ? 1e-6f : wres;
-          saa = fmaf(a, a, saa);
-          sab = fmaf(a, bq, sab);
-          sbb = fmaf(bq, bq, sbb);
-          sar = fmaf(a, wm, sar);
-          sbr = fmaf(bq, wm, sbr);
-          if (TRU) {
-            const float dw = wres - 1e-6f;
-            sca = fmaf(a, dw, sca);
-            scb = fmaf(bq, dw, scb);
-            pmin = fminf(pmin, sr);
-            pmax = fmaxf(pmax, sr);
-            if (k == 0) sr0 = sr;
-          }
-        }
-      }
-      if (TRU && c0 != 0) sr0 = sample_exact(p.s1 + (size_t)b * C * plane, tap, W);
-
-      // halo lanes and columns past the image contribute nothing
-      if (!col_out) { saa = sab = sbb = sar = sbr = 0.f; }
-      float ju[6], jv[6];
-      warp_rows(px, py, d0, fx, fy, ju, jv);
-      accumulate_system(acc, ju, jv, saa, sab, sbb, sar, sbr);
-      if (TRU) {
-        // running extremes of the warped sigma and what their pixels added to J^T r.  New extremes and
-        // ties are rare after the first rows, so the bookkeeping sits behind one warp-uniform branch.
-        const bool lo = col_out && (pmin < vmin), hi = col_out && (pmax > vmax);
-        const float nmin = lo ? pmin : vmin, nmax = hi ? pmax : vmax;
-        const bool tmin = col_out && !occ && (sr0 == nmin), tmax = col_out && !occ && (sr0 == nmax);
-        if (__any_sync(0xffffffffu, lo || hi || tmin || tmax)) {
-          vmin = nmin;
-          vmax = nmax;
-#pragma unroll
-          for (int i = 0; i < 6; ++i) {
-            float cc = 0.f;
-            if (i != 4) cc = fmaf(sca, ju[i], cc);
-            if (i != 3) cc = fmaf(scb, jv[i], cc);
-            cmn[i] = (lo ? 0.f : cmn[i]) + (tmin ? cc : 0.f);
-            cmx[i] = (hi ? 0.f : cmx[i]) + (tmax ? cc : 0.f);
-          }
-        }
-      }
-      if (p.occ_out && c0 == 0 && col_out) {
-        p.occ_out[(size_t)b * plane + (size_t)y * W + x] = occ ? 1 : 0;
-        if (TRU) p.sr0_dbg[(size_t)b * plane + (size_t)y * W + x] = sr0;
-      }
-#pragma unroll
-      for (int c = 0; c < CH; ++c) {
-        ft[c] = fm[c];
-        fm[c] = fb[c];
-        st[c] = sm[c];
-        sm[c] = sb[c];
-      }
-    }
+  cudaGridDependencySynchronize();
+  const Pose pose = load_pose(p.pose + (size_t)b * 12);
+  if (TRU) {
+    g.s0lo = ord2f(__ldcg(p.s0mm));
+    g.s0hi = ord2f(__ldcg(p.s0mm + 1));
   }
-
-  reduce_and_finish<TRU>(p, b, acc, cmn, cmx, vmin, vmax);
+  TileSums S;
+  S.reset();
+  process_tile<CH, TRU>(g, pose, seg, y0, y1, lane, S);
+  reduce_and_finish<TRU>(p, b, S.acc, S.cmn, S.cmx, S.vmin, S.vmax);
 }
 
 // =========================================================================== materialised-gradient path
@@ -693,19 +535,31 @@ struct Plan {
   size_t max_plane;
   size_t off_partials, off_pairrec, off_counters, off_mm, off_gmm, off_sr0, off_grad, grad_elems;
   size_t off_vn, off_icp, off_dmm, total;
+  // persistent (single cooperative launch) path
+  int p_grid, p_TR[DPFT_MAX_LEVELS], p_nrt[DPFT_MAX_LEVELS], p_rcap;
+  size_t off_records, off_gext, off_clock;
 };
 
-// Rows per warp tile: tall tiles amortise the two halo rows, short tiles give a small level enough warps
-// to fill the machine (a tile is walked row by row by one warp, so its height is pure latency).
+// Rows per warp tile.  A tile is walked row by row by one warp, so the time of a launch is about
+// (waves of CTAs) x (rows per tile + ~1.5 rows of window priming and reduction tail): pick the height that
+// minimises that, i.e. fill whole waves of the 148 x DPFT_MIN_CTAS resident CTAs.
 static int pick_tile_rows(int H, int nseg, int B) {
-  const long target_warps = 148L * 16 * 2;
-  long tr = ((long)H * nseg * B + target_warps - 1) / target_warps;
-  tr = std::max(1L, std::min(tr, 12L));
-  const int tiles = (int)((H + tr - 1) / tr);
-  return (H + tiles - 1) / tiles;
+  long slots = 148L * DPFT_MIN_CTAS;
+  if (const char* e = getenv("DPFT_CTA_SLOTS")) slots = std::max(1L, atol(e));   // tuning hook
+  int best_tr = 1;
+  double best = 1e30;
+  for (int tr = 1; tr <= kMaxTileRows; ++tr) {
+    const long nrt = (H + tr - 1) / tr;
+    const long ctas = ((nrt * nseg + kWarps - 1) / kWarps) * B;
+    const long waves = (ctas + slots - 1) / slots;
+    const double cost = (double)waves * (tr + 1.5);
+    if (cost < best - 1e-9) { best = cost; best_tr = tr; }
+  }
+  return best_tr;
 }
 
-static Plan make_plan(const dpft_level_t* lv, int n_levels, int B, int C, uint32_t flags, bool any_occ) {
+static Plan make_plan(const dpft_level_t* lv, int n_levels, int B, int C, uint32_t flags, bool any_occ,
+                      int p_grid) {
   Plan pl{};
   pl.max_ctas = 1;
   pl.max_plane = 0;
@@ -744,6 +598,28 @@ static Plan make_plan(const dpft_level_t* lv, int n_levels, int B, int C, uint32
   pl.off_vn = take(icp ? 6 * (size_t)B * pl.max_plane * sizeof(float) : 0);
   pl.off_icp = take(icp ? (size_t)B * 28 * sizeof(float) : 0);
   pl.off_dmm = take(2 * DPFT_MAX_LEVELS * sizeof(uint32_t));
+  // persistent path: tile height per level that minimises the rows the busiest warp walks (a tile costs its
+  // rows plus about one row of window priming), record slots per pair
+  pl.p_grid = p_grid;
+  pl.p_rcap = 1;
+  if (p_grid > 0) {
+    const long nw = (long)p_grid * kWarps;
+    for (int l = 0; l < n_levels; ++l) {
+      double best = 1e30;
+      for (int tr = 1; tr <= kMaxTileRows; ++tr) {
+        const long nrt = (lv[l].H + tr - 1) / tr, tiles = nrt * pl.nseg[l] * B;
+        const long T = (tiles + nw - 1) / nw;
+        const double cost = (double)T * (tr + 1.0);
+        if (cost < best - 1e-9) { best = cost; pl.p_TR[l] = tr; pl.p_nrt[l] = (int)nrt; }
+      }
+      const long tpp = (long)pl.p_nrt[l] * pl.nseg[l];
+      const long T = (tpp * B + nw - 1) / nw;
+      pl.p_rcap = std::max(pl.p_rcap, (int)((tpp + T - 1) / T + 1));
+    }
+  }
+  pl.off_records = take(p_grid > 0 ? (size_t)B * pl.p_rcap * PS * sizeof(float) : 0);
+  pl.off_gext = take(2 * DPFT_MAX_LEVELS * 64 * sizeof(uint32_t));
+  pl.off_clock = take((DPFT_MAX_LEVELS * 64 + 1) * sizeof(unsigned long long));
   pl.total = off;
   return pl;
 }
@@ -800,24 +676,42 @@ static cudaError_t launch_px(const UicIterParams& prm, const PxExtra& ex, dim3 g
 
 using namespace dpft;
 
+// The single-launch path serves the plain U_IC solve; the ICP term, the per-iteration mask output and the
+// materialised-gradient variant keep one launch per iteration.
+static bool persistent_ok(uint32_t flags, bool any_occ) {
+  return (flags & DPFT_FUSED_SOBEL) && !(flags & (DPFT_COMBINE_ICP | DPFT_LAUNCH_PER_ITERATION)) && !any_occ;
+}
+
+static int persistent_grid_cached(int C, bool tru) {
+  static int cache[2][4] = {{0, 0, 0, 0}, {0, 0, 0, 0}};
+  const int idx = (C % 8 == 0) ? 3 : (C % 4 == 0) ? 2 : (C % 2 == 0) ? 1 : 0;
+  if (!cache[tru][idx]) cache[tru][idx] = std::max(persistent_grid(C, tru), -1);
+  return cache[tru][idx];
+}
+
 extern "C" size_t dpft_uic_workspace_bytes(const dpft_level_t* levels, int n_levels, int B, int C, int iters,
                                            uint32_t flags) {
   if (check_args(levels, n_levels, B, C, iters, flags)) return 0;
   bool any_occ = false;
   for (int l = 0; l < n_levels; ++l) any_occ = any_occ || levels[l].occ_out;
-  return make_plan(levels, n_levels, B, C, flags, any_occ).total;
+  const int pg = persistent_ok(flags, any_occ) ? persistent_grid_cached(C, flags & DPFT_REMOVE_TRU_SIGMA) : 0;
+  return make_plan(levels, n_levels, B, C, flags, any_occ, std::max(pg, 0)).total;
 }
 
 static int run_uic(const dpft_level_t* levels, int n_levels, int B, int C, int iters, uint32_t flags,
                    float w_icp, const float* pose_in, float* pose_hist, float* sys_hist, float* aux_hist,
-                   int32_t* status, void* workspace, size_t workspace_bytes, void* stream_, cudaEvent_t* ev) {
+                   int32_t* status, void* workspace, size_t workspace_bytes, void* stream_, cudaEvent_t* ev,
+                   unsigned long long* clock_host) {
   if (iters > 64) return set_error(DPFT_EINVAL, "iters must be <= 64");
   if (int e = check_args(levels, n_levels, B, C, iters, flags)) return e;
   if (!pose_in || !pose_hist || !status || (iters > 0 && !sys_hist) || !workspace)
     return set_error(DPFT_EINVAL, "pose_in, pose_hist, sys_hist, status and workspace are required");
   bool any_occ = false;
   for (int l = 0; l < n_levels; ++l) any_occ = any_occ || levels[l].occ_out;
-  const Plan pl = make_plan(levels, n_levels, B, C, flags, any_occ);
+  if (ev && !clock_host) flags |= DPFT_LAUNCH_PER_ITERATION;   // event timing needs separate launches
+  const bool persist = persistent_ok(flags, any_occ) && persistent_grid_cached(C, flags & DPFT_REMOVE_TRU_SIGMA) > 0;
+  const Plan pl = make_plan(levels, n_levels, B, C, flags, any_occ,
+                            persist ? persistent_grid_cached(C, flags & DPFT_REMOVE_TRU_SIGMA) : 0);
   if (workspace_bytes < pl.total) return set_error(DPFT_ENOSPACE, "workspace has %zu bytes, %zu needed", workspace_bytes, pl.total);
   cudaStream_t stream = (cudaStream_t)stream_;
   char* ws = (char*)workspace;
@@ -848,7 +742,31 @@ static int run_uic(const dpft_level_t* levels, int n_levels, int B, int C, int i
       minmax_kernel<<<blocks, 256, 0, stream>>>(levels[l].sigma0, n, mm + 2 * l);
     }
   }
-  const int CH = (C % 8 == 0) ? 8 : (C % 4 == 0) ? 4 : (C % 2 == 0) ? 2 : 1;
+  if (persist) {
+    PersistParams pp{};
+    for (int l = 0; l < n_levels; ++l) {
+      const dpft_level_t& L = levels[l];
+      PLevel& q = pp.lv[l];
+      q.x0 = L.x0; q.x1 = L.x1; q.s0 = L.sigma0; q.s1 = L.sigma1; q.d0 = L.invd0; q.d1 = L.invd1; q.K = L.K;
+      q.m0 = L.obj_mask0; q.m1 = L.obj_mask1;
+      q.H = L.H; q.W = L.W; q.nseg = pl.nseg[l]; q.TR = pl.p_TR[l]; q.nrt = pl.p_nrt[l]; q.tpp = q.nseg * q.nrt;
+    }
+    pp.n_levels = n_levels; pp.iters = iters; pp.B = B; pp.C = C; pp.rcap = pl.p_rcap;
+    pp.pose_hist = pose_hist; pp.sys_hist = sys_hist; pp.aux = gmm;
+    pp.records = (float*)(ws + pl.off_records); pp.pairrec = pairrec; pp.s0mm = mm;
+    pp.gext = (uint32_t*)(ws + pl.off_gext); pp.status = status;
+    pp.clock_out = clock_host ? (unsigned long long*)(ws + pl.off_clock) : nullptr;
+    init_kernel<<<(n_levels * iters + 255) / 256, 256, 0, stream>>>(pose_in, pose_hist, 0, counters, 0, pp.gext, n_levels * iters);
+    const cudaError_t err = launch_persistent(pp, pl.p_grid, tru, stream);
+    if (err != cudaSuccess) return set_error((int)err, "cooperative launch: %s", cudaGetErrorString(err));
+    if (clock_host) {
+      const int n = n_levels * iters + 1;
+      cudaError_t e2 = cudaMemcpyAsync(clock_host, pp.clock_out, n * sizeof(unsigned long long), cudaMemcpyDeviceToHost, stream);
+      if (e2 == cudaSuccess) e2 = cudaStreamSynchronize(stream);
+      if (e2 != cudaSuccess) return set_error((int)e2, "clock read-back: %s", cudaGetErrorString(e2));
+    }
+    return 0;
+  }
   int k = 0;
   for (int l = 0; l < n_levels; ++l) {
     const dpft_level_t& L = levels[l];
@@ -869,6 +787,7 @@ static int run_uic(const dpft_level_t* levels, int n_levels, int B, int C, int i
       launch_sobel_unit(L.x0, g, g + pl.grad_elems, B * C, L.H, L.W, stream);
       launch_sobel_unit(L.sigma0, g + 2 * pl.grad_elems, g + 3 * pl.grad_elems, B * C, L.H, L.W, stream);
     }
+    const int CH = (C % 8 == 0) ? 8 : (C % 4 == 0) ? 4 : (C % 2 == 0) ? 2 : 1;
     for (int it = 0; it < iters; ++it, ++k) {
       UicIterParams prm{};
       prm.x0 = L.x0; prm.x1 = L.x1; prm.s0 = L.sigma0; prm.s1 = L.sigma1;
@@ -927,7 +846,7 @@ extern "C" int dpft_uic_forward(const dpft_level_t* levels, int n_levels, int B,
                                 float* aux_hist, int32_t* status, void* workspace, size_t workspace_bytes,
                                 void* stream) {
   return run_uic(levels, n_levels, B, C, iters, flags, w_icp, pose_in, pose_hist, sys_hist, aux_hist, status,
-                 workspace, workspace_bytes, stream, nullptr);
+                 workspace, workspace_bytes, stream, nullptr, nullptr);
 }
 
 extern "C" int dpft_uic_forward_timed(const dpft_level_t* levels, int n_levels, int B, int C, int iters,
@@ -937,10 +856,20 @@ extern "C" int dpft_uic_forward_timed(const dpft_level_t* levels, int n_levels, 
   if (!launch_ms || n_levels < 1 || n_levels > DPFT_MAX_LEVELS || iters < 1 || iters > 64)
     return set_error(DPFT_EINVAL, "launch_ms is required and iters must be 1..64");
   const int n = n_levels * iters;
+  bool any_occ = false;
+  for (int l = 0; l < n_levels; ++l) any_occ = any_occ || levels[l].occ_out;
+  if (persistent_ok(flags, any_occ) && persistent_grid_cached(C, flags & DPFT_REMOVE_TRU_SIGMA) > 0) {
+    // single cooperative launch: iteration boundaries are stamped on the device with %globaltimer
+    unsigned long long stamps[DPFT_MAX_LEVELS * 64 + 1];
+    const int rc = run_uic(levels, n_levels, B, C, iters, flags, w_icp, pose_in, pose_hist, sys_hist, aux_hist, status,
+                           workspace, workspace_bytes, stream, nullptr, stamps);
+    for (int i = 0; i < n && rc == 0; ++i) launch_ms[i] = (float)((double)(stamps[i + 1] - stamps[i]) * 1e-6);
+    return rc;
+  }
   cudaEvent_t ev[DPFT_MAX_LEVELS * 64 + 1];
   for (int i = 0; i <= n; ++i) cudaEventCreate(&ev[i]);
   int rc = run_uic(levels, n_levels, B, C, iters, flags, w_icp, pose_in, pose_hist, sys_hist, aux_hist, status,
-                   workspace, workspace_bytes, stream, ev);
+                   workspace, workspace_bytes, stream, ev, nullptr);
   if (rc == 0) {
     const cudaError_t err = cudaStreamSynchronize((cudaStream_t)stream);
     if (err != cudaSuccess) rc = set_error((int)err, "sync: %s", cudaGetErrorString(err));

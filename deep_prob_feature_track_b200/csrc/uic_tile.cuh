@@ -1,0 +1,231 @@
+// One warp tile of the fused U_IC iteration: 30 output columns x `rows` rows of one frame pair.
+//
+// Lanes 0 and 31 are halo columns (clamped at the image border = replicate padding), so the horizontal Sobel
+// taps come from __shfl of the neighbouring lanes and the vertical taps from a 3-row register window that
+// slides down the tile: every x0 / sigma0 element is loaded once per tile (coalesced rows), the unit Sobel
+// gradients are recomputed instead of stored, and nothing per-pixel is written back.
+// Restates reference code/models/algorithms.py:611-723 with the arithmetic of oracle/ic_oracle.py.
+#pragma once
+#include <cuda_runtime.h>
+#include <math_constants.h>
+
+#include "dpft_device.cuh"
+
+namespace dpft {
+
+constexpr int kTileCols = 30;   // output columns per warp tile
+
+struct PairView {               // one frame pair of one level, pointers already offset to the pair
+  const float *x0, *x1, *s0, *s1, *d0, *d1;
+  const uint8_t *m0, *m1;       // optional object masks
+  uint8_t* occ_out;             // optional debug outputs (per pair)
+  float* sr0_dbg;
+  int H, W, C;
+  float fx, fy, cx, cy;
+  float s0lo, s0hi;             // extremes of sigma0 over the whole level tensor (remove_tru_sigma)
+};
+
+struct TileSums {
+  float acc[27];                // 21 upper-triangular J^T J entries, 6 J^T r entries
+  float cmn[6], cmx[6];         // what the pixels on the running sigma extremes added to J^T r
+  float vmin, vmax;             // running extremes of the warped sigma
+  __device__ __forceinline__ void reset() {
+#pragma unroll
+    for (int i = 0; i < 27; ++i) acc[i] = 0.f;
+#pragma unroll
+    for (int i = 0; i < 6; ++i) cmn[i] = cmx[i] = 0.f;
+    vmin = CUDART_INF_F;
+    vmax = -CUDART_INF_F;
+  }
+};
+
+// base + idx (elements) as ONE IMAD.WIDE.U32: the base is made opaque (a per-thread 64-bit register pair) so
+// the compiler cannot fall back to uniform-register bases with 64-bit byte offsets per plane, which costs four
+// integer instructions per load
+__device__ __forceinline__ const float* opaque(const float* p) {
+  asm volatile("" : "+l"(p));
+  return p;
+}
+__device__ __forceinline__ float ldf(const float* __restrict__ base, unsigned idx) {
+  const float* q;
+  asm("mad.wide.u32 %0, %1, 4, %2;" : "=l"(q) : "r"(idx), "l"(base));
+  return __ldg(q);
+}
+__device__ __forceinline__ void ldf2(const float* __restrict__ base, unsigned idx, float& a, float& b) {
+  const float* q;
+  asm("mad.wide.u32 %0, %1, 4, %2;" : "=l"(q) : "r"(idx), "l"(base));
+  a = __ldg(q);
+  b = __ldg(q + 1);
+}
+
+template <int CH, bool TRU>
+__device__ __forceinline__ void process_tile(const PairView& g, const Pose& pose, const int seg, const int y0,
+                                             const int y1, const int lane, TileSums& S) {
+  const int H = g.H, W = g.W, C = g.C;
+  const unsigned iplane = (unsigned)(H * W), Wu = (unsigned)W;
+  const int x = seg * kTileCols - 1 + lane;
+  const int xc = min(max(x, 0), W - 1);
+  const bool col_out = lane >= 1 && lane <= kTileCols && x < W;
+  const float fx = g.fx, fy = g.fy, cx = g.cx, cy = g.cy;
+  const float px = xdiv(xsub((float)xc, cx), fx);
+
+  for (int c0 = 0; c0 < C; c0 += CH) {
+    const float* X0 = opaque(g.x0 + (size_t)c0 * iplane);
+    const float* S0 = opaque(g.s0 + (size_t)c0 * iplane);
+    const float* X1 = opaque(g.x1 + (size_t)c0 * iplane);
+    const float* S1 = opaque(g.s1 + (size_t)c0 * iplane);
+
+    // 3-row sliding windows of the keyframe maps (own column): top / mid / (bot loaded per row)
+    float ft[CH], fm[CH], st[CH], sm[CH];
+    {
+      const unsigned ot = (unsigned)(max(y0 - 1, 0) * W + xc), om = (unsigned)(min(y0, H - 1) * W + xc);
+#pragma unroll
+      for (int c = 0; c < CH; ++c) {
+        ft[c] = ldf(X0, ot + c * iplane);
+        fm[c] = ldf(X0, om + c * iplane);
+        st[c] = ldf(S0, ot + c * iplane);
+        sm[c] = ldf(S0, om + c * iplane);
+      }
+    }
+    for (int y = y0; y < y1; ++y) {
+      const unsigned ob = (unsigned)(min(y + 1, H - 1) * W + xc);
+      float fb[CH], sb[CH];
+#pragma unroll
+      for (int c = 0; c < CH; ++c) {
+        fb[c] = ldf(X0, ob + c * iplane);
+        sb[c] = ldf(S0, ob + c * iplane);
+      }
+      const unsigned o = (unsigned)(y * W + xc);
+      const float d0 = __ldg(g.d0 + o);
+      const float py = xdiv(xsub((float)y, cy), fy);
+
+      float u, v, inv_z;
+      warp_pixel(pose, px, py, d0, fx, fy, cx, cy, u, v, inv_z);
+      const Tap tap = make_tap(u, v, H, W);
+      const float d1w = sample_exact(g.d1, tap, W);
+      bool occ = occluded(u, v, inv_z, d1w, H, W);
+      if (g.m0) occ = occ || (__ldg(g.m0 + o) == 0);
+      if (g.m1) occ = occ || !(sample_mask(g.m1, tap, W) > 0.f);
+      if (TRU) {
+        const float s0c0 = (c0 == 0) ? sm[0] : __ldg(g.s0 + o);
+        occ = occ || (s0c0 == g.s0lo) || (s0c0 == g.s0hi);
+      }
+
+      float saa = 0.f, sab = 0.f, sbb = 0.f, sar = 0.f, sbr = 0.f, sca = 0.f, scb = 0.f;
+      float pmin = CUDART_INF_F, pmax = -CUDART_INF_F, sr0 = 0.f;
+      constexpr int G = CH < 4 ? CH : 4;   // channels whose 8*G lookups are in flight together
+#pragma unroll
+      for (int g0 = 0; g0 < CH; g0 += G) {
+        float xa[G], xb[G], xc_[G], xd[G], za[G], zb[G], zc[G], zd[G];
+#pragma unroll
+        for (int c = 0; c < G; ++c) {
+          const unsigned ia = (unsigned)tap.o + (unsigned)(g0 + c) * iplane, ic = ia + Wu;
+          ldf2(X1, ia, xa[c], xb[c]); ldf2(X1, ic, xc_[c], xd[c]);
+          ldf2(S1, ia, za[c], zb[c]); ldf2(S1, ic, zc[c], zd[c]);
+        }
+#ifdef DPFT_PREFETCH
+#pragma unroll
+        for (int c = 0; c < G; ++c) {
+          // the next tile row samples one footprint row further down: start pulling those lines in now
+          const unsigned ip = (unsigned)tap.o + (unsigned)(g0 + c) * iplane + 2u * Wu;
+          const float* q1; const float* q2;
+          asm("mad.wide.u32 %0, %1, 4, %2;" : "=l"(q1) : "r"(ip), "l"(X1));
+          asm("mad.wide.u32 %0, %1, 4, %2;" : "=l"(q2) : "r"(ip), "l"(S1));
+          if (y + 2 < H) {
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(q1));
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(q2));
+          }
+        }
+#endif
+        float gfx[G], gfy[G], gsx[G], gsy[G];
+#pragma unroll
+        for (int c = 0; c < G; ++c) {
+          const int k = g0 + c;
+          // unit Sobel gradient of x0 and sigma0 (algorithms.py:1844-1865), separable form:
+          // Sx = vs(x+1) - vs(x-1), Sy = vd(x-1) + 2 vd(x) + vd(x+1), vs = t+2m+b, vd = b-t
+          const float fvs = ft[k] + 2.f * fm[k] + fb[k], fvd = fb[k] - ft[k];
+          const float svs = st[k] + 2.f * sm[k] + sb[k], svd = sb[k] - st[k];
+          const float fSx = __shfl_down_sync(0xffffffffu, fvs, 1) - __shfl_up_sync(0xffffffffu, fvs, 1);
+          const float fSy = __shfl_up_sync(0xffffffffu, fvd, 1) + 2.f * fvd + __shfl_down_sync(0xffffffffu, fvd, 1);
+          const float sSx = __shfl_down_sync(0xffffffffu, svs, 1) - __shfl_up_sync(0xffffffffu, svs, 1);
+          const float sSy = __shfl_up_sync(0xffffffffu, svd, 1) + 2.f * svd + __shfl_down_sync(0xffffffffu, svd, 1);
+          const float fin = rsqrtf(fmaf(fSx, fSx, fmaf(fSy, fSy, 1e-8f)));
+          const float sin_ = rsqrtf(fmaf(sSx, sSx, fmaf(sSy, sSy, 1e-8f)));
+          gfx[c] = fSx * fin; gfy[c] = fSy * fin; gsx[c] = sSx * sin_; gsy[c] = sSy * sin_;
+        }
+#pragma unroll
+        for (int c = 0; c < G; ++c) {
+          const int k = g0 + c;
+          const float fr = blend_fast(xa[c], xb[c], xc_[c], xd[c], tap);
+          // sigma is compared for equality against its batch extremes -> mask-grade arithmetic
+          const float sr = TRU ? blend_exact(za[c], zb[c], zc[c], zd[c], tap) : blend_fast(za[c], zb[c], zc[c], zd[c], tap);
+          // residual, its uncertainty and the 2-vector d(wres)/d(u,v) (algorithms.py:1969-1972, :872)
+          const float res = fr - fm[k];
+          const float s0v = sm[k];
+          const float rs = rsqrtf(fmaf(sr, sr, s0v * s0v));   // 1 / sigma
+          const float wres = res * rs;
+          const float q = wres * (s0v * (rs * rs));           // res * sigma0 / sigma^3
+          const float a = fmaf(gfx[c], rs, q * gsx[c]);
+          const float bq = fmaf(gfy[c], rs, q * gsy[c]);
+          const float wm = occ ? 1e-6f : wres;
+          saa = fmaf(a, a, saa);
+          sab = fmaf(a, bq, sab);
+          sbb = fmaf(bq, bq, sbb);
+          sar = fmaf(a, wm, sar);
+          sbr = fmaf(bq, wm, sbr);
+          if (TRU) {
+            const float dw = wres - 1e-6f;
+            sca = fmaf(a, dw, sca);
+            scb = fmaf(bq, dw, scb);
+            pmin = fminf(pmin, sr);
+            pmax = fmaxf(pmax, sr);
+            if (c0 == 0 && k == 0) sr0 = sr;
+          }
+        }
+      }
+      if (TRU && c0 != 0) {
+        // channel 0 decides the mask; seeing it in every pass keeps the running extremes comparable
+        sr0 = sample_exact(g.s1, tap, W);
+        pmin = fminf(pmin, sr0);
+        pmax = fmaxf(pmax, sr0);
+      }
+      // halo lanes and columns past the image contribute nothing
+      if (!col_out) { saa = sab = sbb = sar = sbr = 0.f; }
+      float ju[6], jv[6];
+      warp_rows(px, py, d0, fx, fy, ju, jv);
+      accumulate_system(S.acc, ju, jv, saa, sab, sbb, sar, sbr);
+      if (TRU) {
+        // running extremes of the warped sigma and what their pixels added to J^T r.  New extremes and
+        // ties are rare after the first rows, so the bookkeeping sits behind one warp-uniform branch.
+        const bool lo = col_out && (pmin < S.vmin), hi = col_out && (pmax > S.vmax);
+        const float nmin = lo ? pmin : S.vmin, nmax = hi ? pmax : S.vmax;
+        const bool tmin = col_out && !occ && (sr0 == nmin), tmax = col_out && !occ && (sr0 == nmax);
+        if (__any_sync(0xffffffffu, lo || hi || tmin || tmax)) {
+          S.vmin = nmin;
+          S.vmax = nmax;
+#pragma unroll
+          for (int i = 0; i < 6; ++i) {
+            float cc = 0.f;
+            if (i != 4) cc = fmaf(sca, ju[i], cc);
+            if (i != 3) cc = fmaf(scb, jv[i], cc);
+            S.cmn[i] = (lo ? 0.f : S.cmn[i]) + (tmin ? cc : 0.f);
+            S.cmx[i] = (hi ? 0.f : S.cmx[i]) + (tmax ? cc : 0.f);
+          }
+        }
+      }
+      if (g.occ_out && c0 == 0 && col_out) {
+        g.occ_out[(size_t)y * W + x] = occ ? 1 : 0;
+        if (TRU) g.sr0_dbg[(size_t)y * W + x] = sr0;
+      }
+#pragma unroll
+      for (int c = 0; c < CH; ++c) {
+        ft[c] = fm[c];
+        fm[c] = fb[c];
+        st[c] = sm[c];
+        sm[c] = sb[c];
+      }
+    }
+  }
+}
+
+}  // namespace dpft

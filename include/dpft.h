@@ -45,6 +45,9 @@ extern "C" {
 #define DPFT_REMOVE_TRU_SIGMA 0x01u /* alg:1974-1979  mask pixels whose sigma sits on the batch-global min/max */
 #define DPFT_COMBINE_ICP      0x02u /* alg:668-689    add the point-to-plane term (needs depth0/depth1)        */
 #define DPFT_NO_PDL           0x04u /* launch iterations without programmatic dependent launch (debug)        */
+#define DPFT_LAUNCH_PER_ITERATION 0x10u /* one launch per Gauss-Newton iteration instead of the single
+                                          cooperative launch (the ICP term, occ_out and the materialised
+                                          gradients always use it)                                           */
 #define DPFT_FUSED_SOBEL      0x08u /* recompute the unit Sobel gradients inside every iteration (sliding register
                                        window) instead of materialising them once per level                    */
 
