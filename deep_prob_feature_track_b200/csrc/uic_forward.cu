@@ -113,10 +113,8 @@ __device__ void finalize_pair(const UicIterParams& p, int b, float gmin, float g
 // a fixed order (deterministic), and the last CTA of the grid (or of the pair, when nothing couples the
 // pairs) damps, solves and updates the poses.
 template <bool TRU>
-__device__ __forceinline__ void reduce_and_finish(const UicIterParams& p, const int b, const float (&acc)[27],
-                                                  float (&cmn)[6], float (&cmx)[6], const float vmin,
-                                                  const float vmax) {
-  __shared__ float red[kWarps][NSUM][33];
+__device__ __forceinline__ void reduce_and_finish(const UicIterParams& p, const int b, float (*red)[NSUM][33],
+                                                  const float (&acc)[27], const float vmin, const float vmax) {
   __shared__ double wsum[kWarps][NSUM + 1];
   __shared__ float wvmin[kWarps], wvmax[kWarps];
   __shared__ float s_pair_mm[2];
@@ -125,13 +123,14 @@ __device__ __forceinline__ void reduce_and_finish(const UicIterParams& p, const 
   // ---------------------------------------------------------------- CTA reduction
   if (TRU) {
     const float wmn = warp_min(vmin), wmx = warp_max(vmax);
+    // the corrections already sit in red[warp][27..38][lane]
     if (vmin != wmn) {
 #pragma unroll
-      for (int i = 0; i < 6; ++i) cmn[i] = 0.f;
+      for (int i = 0; i < 6; ++i) red[warp][27 + i][lane] = 0.f;
     }
     if (vmax != wmx) {
 #pragma unroll
-      for (int i = 0; i < 6; ++i) cmx[i] = 0.f;
+      for (int i = 0; i < 6; ++i) red[warp][33 + i][lane] = 0.f;
     }
     if (lane == 0) {
       wvmin[warp] = wmn;
@@ -140,13 +139,6 @@ __device__ __forceinline__ void reduce_and_finish(const UicIterParams& p, const 
   }
 #pragma unroll
   for (int e = 0; e < 27; ++e) red[warp][e][lane] = acc[e];
-  if (TRU) {
-#pragma unroll
-    for (int i = 0; i < 6; ++i) {
-      red[warp][27 + i][lane] = cmn[i];
-      red[warp][33 + i][lane] = cmx[i];
-    }
-  }
   __syncwarp();
   constexpr int NE = TRU ? NSUM : 27;
   for (int e = lane; e < NE; e += 32) {
@@ -305,17 +297,22 @@ __global__ void __launch_bounds__(kThreads, DPFT_MIN_CTAS) uic_iter_kernel(const
 
   // let the next iteration's launch become resident as soon as every CTA of this one has started; nothing
   // before the dependency sync touches what the previous launch writes
+  __shared__ float red[kWarps][NSUM][33];
+  __shared__ __align__(16) float s_pose[12];
   cudaTriggerProgrammaticLaunchCompletion();
   cudaGridDependencySynchronize();
-  const Pose pose = load_pose(p.pose + (size_t)b * 12);
+  if (threadIdx.x < 12) s_pose[threadIdx.x] = __ldcg(p.pose + (size_t)b * 12 + threadIdx.x);
   if (TRU) {
     g.s0lo = ord2f(__ldcg(p.s0mm));
     g.s0hi = ord2f(__ldcg(p.s0mm + 1));
+#pragma unroll
+    for (int i = 0; i < 12; ++i) red[warp][27 + i][lane] = 0.f;
   }
+  __syncthreads();
   TileSums S;
   S.reset();
-  process_tile<CH, TRU>(g, pose, seg, y0, y1, lane, S);
-  reduce_and_finish<TRU>(p, b, S.acc, S.cmn, S.cmx, S.vmin, S.vmax);
+  process_tile<CH, TRU>(g, s_pose, &red[warp][27], seg, y0, y1, lane, S);
+  reduce_and_finish<TRU>(p, b, red, S.acc, S.vmin, S.vmax);
 }
 
 // =========================================================================== materialised-gradient path
@@ -476,7 +473,16 @@ __global__ void __launch_bounds__(kThreads, 4) uic_iter_px_kernel(const UicIterP
       if (TRU) p.sr0_dbg[(size_t)b * iplane + pix] = sr0;
     }
   }
-  reduce_and_finish<TRU>(p, b, acc, cmn, cmx, vmin, vmax);
+  __shared__ float red[kWarps][NSUM][33];
+  if (TRU) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+    for (int i = 0; i < 6; ++i) {
+      red[warp][27 + i][lane] = cmn[i];
+      red[warp][33 + i][lane] = cmx[i];
+    }
+  }
+  reduce_and_finish<TRU>(p, b, red, acc, vmin, vmax);
 }
 
 // --------------------------------------------------------------------------- small helper kernels
@@ -787,7 +793,10 @@ static int run_uic(const dpft_level_t* levels, int n_levels, int B, int C, int i
       launch_sobel_unit(L.x0, g, g + pl.grad_elems, B * C, L.H, L.W, stream);
       launch_sobel_unit(L.sigma0, g + 2 * pl.grad_elems, g + 3 * pl.grad_elems, B * C, L.H, L.W, stream);
     }
-    const int CH = (C % 8 == 0) ? 8 : (C % 4 == 0) ? 4 : (C % 2 == 0) ? 2 : 1;
+#ifndef DPFT_MAX_CH
+#define DPFT_MAX_CH 8
+#endif
+    const int CH = (C % 8 == 0 && DPFT_MAX_CH >= 8) ? 8 : (C % 4 == 0) ? 4 : (C % 2 == 0) ? 2 : 1;
     for (int it = 0; it < iters; ++it, ++k) {
       UicIterParams prm{};
       prm.x0 = L.x0; prm.x1 = L.x1; prm.s0 = L.sigma0; prm.s1 = L.sigma1;

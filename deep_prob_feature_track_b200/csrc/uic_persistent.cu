@@ -47,22 +47,15 @@ __device__ __forceinline__ void flush_warp(TileSums& S, float (*red)[33], float*
     wmx = warp_max(S.vmax);
     if (S.vmin != wmn) {
 #pragma unroll
-      for (int i = 0; i < 6; ++i) S.cmn[i] = 0.f;
+      for (int i = 0; i < 6; ++i) red[27 + i][lane] = 0.f;
     }
     if (S.vmax != wmx) {
 #pragma unroll
-      for (int i = 0; i < 6; ++i) S.cmx[i] = 0.f;
+      for (int i = 0; i < 6; ++i) red[33 + i][lane] = 0.f;
     }
   }
 #pragma unroll
   for (int e = 0; e < 27; ++e) red[e][lane] = S.acc[e];
-  if (TRU) {
-#pragma unroll
-    for (int i = 0; i < 6; ++i) {
-      red[27 + i][lane] = S.cmn[i];
-      red[33 + i][lane] = S.cmx[i];
-    }
-  }
   __syncwarp();
   constexpr int NE = TRU ? NSUM : 27;
   for (int e = lane; e < NE; e += 32) {
@@ -83,6 +76,7 @@ __global__ void __launch_bounds__(kPT, DPFT_MIN_CTAS) uic_persistent_kernel(cons
   cg::grid_group grid = cg::this_grid();
   __shared__ float red[kPW][NSUM][33];
   __shared__ float s_mn[kPW], s_mx[kPW];
+  __shared__ __align__(16) float s_pose[kPW][12];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int gw = blockIdx.x * kPW + warp, nw = gridDim.x * kPW;
   const int B = p.B, C = p.C;
@@ -108,7 +102,6 @@ __global__ void __launch_bounds__(kPT, DPFT_MIN_CTAS) uic_persistent_kernel(cons
         int cur_b = -1;
         TileSums S;
         PairView g;
-        Pose pose;
         for (int t = t0; t < t1; ++t) {
           const int b = t / L.tpp, tl = t - b * L.tpp;
           if (b != cur_b) {
@@ -116,6 +109,10 @@ __global__ void __launch_bounds__(kPT, DPFT_MIN_CTAS) uic_persistent_kernel(cons
               flush_warp<TRU>(S, red[warp], p.records + ((size_t)cur_b * p.rcap + (gw - (cur_b * L.tpp) / T)) * PS, lane);
             cur_b = b;
             S.reset();
+            if (TRU) {
+#pragma unroll
+              for (int i = 0; i < 12; ++i) red[warp][27 + i][lane] = 0.f;
+            }
             const size_t po = (size_t)b * C * plane;
             g.x0 = L.x0 + po; g.x1 = L.x1 + po; g.s0 = L.s0 + po; g.s1 = L.s1 + po;
             g.d0 = L.d0 + (size_t)b * plane; g.d1 = L.d1 + (size_t)b * plane;
@@ -125,14 +122,13 @@ __global__ void __launch_bounds__(kPT, DPFT_MIN_CTAS) uic_persistent_kernel(cons
             g.H = L.H; g.W = L.W; g.C = C;
             g.fx = __ldg(L.K + 4 * b); g.fy = __ldg(L.K + 4 * b + 1); g.cx = __ldg(L.K + 4 * b + 2); g.cy = __ldg(L.K + 4 * b + 3);
             g.s0lo = s0lo; g.s0hi = s0hi;
-#pragma unroll
-            for (int i = 0; i < 9; ++i) pose.r[i] = __ldcg(pose_k + (size_t)b * 12 + i);
-#pragma unroll
-            for (int i = 0; i < 3; ++i) pose.t[i] = __ldcg(pose_k + (size_t)b * 12 + 9 + i);
+            __syncwarp();
+            if (lane < 12) s_pose[warp][lane] = __ldcg(pose_k + (size_t)b * 12 + lane);
+            __syncwarp();
           }
           const int seg = tl % L.nseg, rt = tl / L.nseg;
           const int y0 = rt * L.TR, y1 = min(y0 + L.TR, L.H);
-          process_tile<CH, TRU>(g, pose, seg, y0, y1, lane, S);
+          process_tile<CH, TRU>(g, s_pose[warp], &red[warp][27], seg, y0, y1, lane, S);
         }
         if (cur_b >= 0)
           flush_warp<TRU>(S, red[warp], p.records + ((size_t)cur_b * p.rcap + (gw - (cur_b * L.tpp) / T)) * PS, lane);

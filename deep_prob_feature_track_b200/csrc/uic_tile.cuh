@@ -27,13 +27,10 @@ struct PairView {               // one frame pair of one level, pointers already
 
 struct TileSums {
   float acc[27];                // 21 upper-triangular J^T J entries, 6 J^T r entries
-  float cmn[6], cmx[6];         // what the pixels on the running sigma extremes added to J^T r
-  float vmin, vmax;             // running extremes of the warped sigma
+  float vmin, vmax;             // running extremes of the warped sigma (their corrections live in shared memory)
   __device__ __forceinline__ void reset() {
 #pragma unroll
     for (int i = 0; i < 27; ++i) acc[i] = 0.f;
-#pragma unroll
-    for (int i = 0; i < 6; ++i) cmn[i] = cmx[i] = 0.f;
     vmin = CUDART_INF_F;
     vmax = -CUDART_INF_F;
   }
@@ -58,9 +55,23 @@ __device__ __forceinline__ void ldf2(const float* __restrict__ base, unsigned id
   b = __ldg(q + 1);
 }
 
+// 16-byte shared-memory load that the compiler may not hoist out of the row loop: the pose is read where it
+// is used instead of pinning 12 registers across the whole tile
+__device__ __forceinline__ float4 lds_v4(const float* p) {
+  float4 r;
+  asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];"
+               : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w)
+               : "r"((unsigned)__cvta_generic_to_shared(p)));
+  return r;
+}
+
+// `spose`: this warp's pose in SHARED memory, 12 floats R|t, 16-byte aligned.
+// `scorr`: this warp's [12][33] shared scratch for the sigma-extreme corrections (remove_tru_sigma), zeroed by
+//          the caller; row i < 6 belongs to the minimum, row 6 + i to the maximum, one column per lane.
 template <int CH, bool TRU>
-__device__ __forceinline__ void process_tile(const PairView& g, const Pose& pose, const int seg, const int y0,
-                                             const int y1, const int lane, TileSums& S) {
+__device__ __forceinline__ void process_tile(const PairView& g, const float* spose, float (*scorr)[33],
+                                             const int seg, const int y0, const int y1, const int lane,
+                                             TileSums& S) {
   const int H = g.H, W = g.W, C = g.C;
   const unsigned iplane = (unsigned)(H * W), Wu = (unsigned)W;
   const int x = seg * kTileCols - 1 + lane;
@@ -100,7 +111,16 @@ __device__ __forceinline__ void process_tile(const PairView& g, const Pose& pose
       const float py = xdiv(xsub((float)y, cy), fy);
 
       float u, v, inv_z;
-      warp_pixel(pose, px, py, d0, fx, fy, cx, cy, u, v, inv_z);
+      {
+        // SE(3) warp (geometry.py:291-323): w = ((r0 x + r1 y) + r2) + t d, every step rounded on its own
+        const float4 ra = lds_v4(spose), rb = lds_v4(spose + 4), rc = lds_v4(spose + 8);
+        const float wx = xadd(xadd(xadd(xmul(ra.x, px), xmul(ra.y, py)), ra.z), xmul(rc.y, d0));
+        const float wy = xadd(xadd(xadd(xmul(ra.w, px), xmul(rb.x, py)), rb.y), xmul(rc.z, d0));
+        const float wz = xadd(xadd(xadd(xmul(rb.z, px), xmul(rb.w, py)), rc.x), xmul(rc.w, d0));
+        u = xadd(xmul(xdiv(wx, wz), fx), cx);
+        v = xadd(xmul(xdiv(wy, wz), fy), cy);
+        inv_z = xdiv(d0, wz);
+      }
       const Tap tap = make_tap(u, v, H, W);
       const float d1w = sample_exact(g.d1, tap, W);
       bool occ = occluded(u, v, inv_z, d1w, H, W);
@@ -208,8 +228,8 @@ __device__ __forceinline__ void process_tile(const PairView& g, const Pose& pose
             float cc = 0.f;
             if (i != 4) cc = fmaf(sca, ju[i], cc);
             if (i != 3) cc = fmaf(scb, jv[i], cc);
-            S.cmn[i] = (lo ? 0.f : S.cmn[i]) + (tmin ? cc : 0.f);
-            S.cmx[i] = (hi ? 0.f : S.cmx[i]) + (tmax ? cc : 0.f);
+            if (lo || tmin) scorr[i][lane] = (lo ? 0.f : scorr[i][lane]) + (tmin ? cc : 0.f);
+            if (hi || tmax) scorr[6 + i][lane] = (hi ? 0.f : scorr[6 + i][lane]) + (tmax ? cc : 0.f);
           }
         }
       }
