@@ -199,7 +199,7 @@ def vga_leg(A, rank, dev, args):
 
     def solve(i, **kw):
         return A.uic_solve(sets[i % 2], pose0, iters=ITERS, remove_tru_sigma=True, pdl=not args.no_pdl,
-                           fused_sobel=args.fused_sobel, single_launch=not args.per_iteration, **kw)
+                           fused_sobel=args.fused_sobel, single_launch=args.single_launch, **kw)
 
     for i in range(3):
         solve(i)
@@ -231,8 +231,8 @@ def main():
     ap.add_argument("--no-pdl", action="store_true")
     ap.add_argument("--materialised", action="store_true",
                     help="materialise the unit Sobel gradients once per level instead of the fused sliding-window kernel")
-    ap.add_argument("--per-iteration", action="store_true",
-                    help="one launch per Gauss-Newton iteration instead of the single cooperative launch")
+    ap.add_argument("--single-launch", action="store_true",
+                    help="all levels and iterations in ONE cooperative launch instead of one launch per iteration")
     ap.add_argument("--no-extras", action="store_true", help="skip the training-step and 480x640 side measurements")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
@@ -306,7 +306,7 @@ def main():
 
     def solve(levels, **kw):
         return A.uic_solve(levels, pose0, iters=ITERS, remove_tru_sigma=True, pdl=not args.no_pdl, fused_sobel=args.fused_sobel,
-                           single_launch=not args.per_iteration, **kw)
+                           single_launch=args.single_launch, **kw)
 
     def barrier():
         if world > 1:
@@ -315,7 +315,7 @@ def main():
 
     # init + sigma0 min/max per level, then either ONE cooperative launch for all 12 iterations (+ its init) or
     # one launch per iteration (+ 2 Sobel launches per level when gradients are materialised)
-    single = args.fused_sobel and not args.per_iteration
+    single = args.fused_sobel and args.single_launch
     launches_per_step = 1 + N_LEVELS + (2 if single else N_LEVELS * ITERS + (0 if args.fused_sobel else 2 * N_LEVELS))
 
     with ClockSampler(local_rank) as clocks:

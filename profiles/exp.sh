@@ -1,7 +1,7 @@
 #!/bin/bash
 # one tuning experiment: parity subset, bench (both launch modes), dynamic instruction count of a level-0 launch
 python -m pytest tests/test_uic_forward_gpu.py -x -q -k "golden or full_size_vs_oracle or single_level" 2>&1 | tail -1
-for extra in "--per-iteration" ""; do
+for extra in "" "--single-launch"; do
 python bench.py --steps 100 --warmup 5 --no-cpu-baseline --no-extras $extra 2>/dev/null | python -c "
 import json,sys
 d=json.loads(sys.stdin.read()); r=d['roofline']

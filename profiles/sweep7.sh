@@ -2,7 +2,7 @@
 for tw in "$@"; do
   export DPFT_TARGET_WARPS=$tw
   echo "=== DPFT_TARGET_WARPS=$tw"
-  python bench.py --steps 100 --warmup 5 --no-cpu-baseline --no-extras --per-iteration 2>/dev/null | python -c "
+  python bench.py --steps 100 --warmup 5 --no-cpu-baseline --no-extras  2>/dev/null | python -c "
 import json,sys
 d=json.loads(sys.stdin.read()); r=d['roofline']
 print('pairs/s %.0f  ms/step %.3f  lvl0 launch %.1f us  frac %.3f  launches(us) %s' % (d['value'], d['ms_per_step'], r['launch_ms']*1e3, r['frac'], [round(x*1e3) for x in r['all_launch_ms']]))"
