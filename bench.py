@@ -402,8 +402,8 @@ def main():
                    "algorithmic_bytes_per_step": bytes_step},
         "step_hbm_frac": bytes_step / (ms / args.steps * 1e-3) / 1e9 / peak,
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                     "traffic": 170.7e6 if args.fused_sobel else 328.3e6,
-                     "traffic_source": "ncu --set full dram__bytes_read+write per launch, profiles/r1b_* (fused) / r1c_* (materialised)",
+                     "traffic": 183.8e6 if args.fused_sobel else 328.3e6,
+                     "traffic_source": "ncu --set full dram__bytes_read+write per launch, profiles/r1_uic_iter_kernel_level0.txt (fused) / r1c_* (materialised)",
                      "kernel": ("uic_iter_kernel<8,true>" if args.fused_sobel else "uic_iter_px_kernel<8,true>") + " at the finest level",
                      "algorithmic_bytes_per_launch": bytes_lvl0, "launch_ms": lvl0_ms,
                      "all_launch_ms": [round(x, 4) for x in per_launch], "peak_source": peak_src,

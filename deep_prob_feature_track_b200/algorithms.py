@@ -49,14 +49,20 @@ def unpack_pose(rows: torch.Tensor) -> Pose:
 
 
 _TRI = [(i, j) for i in range(6) for j in range(i, 6)]
+_TRI_OF = [[_TRI.index((min(i, j), max(i, j))) for j in range(6)] for i in range(6)]   # (i,j) -> packed index
+_TRI_GATHER: Dict = {}
+
+
+def _tri_gather(device) -> torch.Tensor:
+    g = _TRI_GATHER.get(device)
+    if g is None:
+        g = _TRI_GATHER[device] = torch.tensor(_TRI_OF, dtype=torch.long, device=device).reshape(36)
+    return g
 
 
 def unpack_system(sys_rows: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
-    """(...,27) -> symmetric J^T W J (...,6,6) and J^T W r (...,6,1)."""
-    A = sys_rows.new_zeros(sys_rows.shape[:-1] + (6, 6))
-    for k, (i, j) in enumerate(_TRI):
-        A[..., i, j] = sys_rows[..., k]
-        A[..., j, i] = sys_rows[..., k]
+    """(...,27) -> symmetric J^T W J (...,6,6) and J^T W r (...,6,1); one gather, no per-entry launches."""
+    A = sys_rows.index_select(-1, _tri_gather(sys_rows.device)).reshape(sys_rows.shape[:-1] + (6, 6))
     return A, sys_rows[..., 21:27].unsqueeze(-1)
 
 
@@ -471,11 +477,7 @@ class _IcLevel:
 
 
 def _tri_to_full(A21: torch.Tensor) -> torch.Tensor:
-    A = A21.new_zeros(A21.shape[:-1] + (6, 6))
-    for k, (i, j) in enumerate(_TRI):
-        A[..., i, j] = A21[..., k]
-        A[..., j, i] = A21[..., k]
-    return A
+    return A21.index_select(-1, _tri_gather(A21.device)).reshape(A21.shape[:-1] + (6, 6))
 
 
 def _avg_loss(res_list, invalid):
