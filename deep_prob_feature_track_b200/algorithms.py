@@ -94,7 +94,7 @@ class SolveResult:
 
 def uic_solve(levels: Sequence[Dict[str, torch.Tensor]], pose: Pose, *, iters: int = 3,
               remove_tru_sigma: bool = False, combine_icp: bool = False, w_icp: float = 0.01,
-              want_occ: bool = False, pdl: bool = True, timed: bool = False, fused_sobel: bool = True, single_launch: bool = False,
+              want_occ: bool = False, pdl: bool = True, timed: bool = False, fused_sobel: bool = True, single_launch: bool = False, async_gather: bool = False,
               obj_mask0: Optional[Sequence] = None, obj_mask1: Optional[Sequence] = None) -> SolveResult:
     """Coarse-to-fine U_IC solve of a batch of frame pairs on the current CUDA stream.
 
@@ -140,7 +140,8 @@ def uic_solve(levels: Sequence[Dict[str, torch.Tensor]], pose: Pose, *, iters: i
         a.H, a.W = H, W
     flags = ((_lib.DPFT_REMOVE_TRU_SIGMA if remove_tru_sigma else 0) | (0 if pdl else _lib.DPFT_NO_PDL)
              | (_lib.DPFT_FUSED_SOBEL if fused_sobel else 0) | (_lib.DPFT_COMBINE_ICP if combine_icp else 0)
-             | (0 if single_launch else _lib.DPFT_LAUNCH_PER_ITERATION))
+             | (0 if single_launch else _lib.DPFT_LAUNCH_PER_ITERATION)
+             | (_lib.DPFT_ASYNC_GATHER if async_gather else 0))
     n_it = n_levels * iters
     pose_in = pack_pose(pose).to(dev)
     pose_hist = torch.empty((n_it + 1, B, 12), dtype=torch.float32, device=dev)

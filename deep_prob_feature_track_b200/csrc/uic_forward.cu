@@ -25,6 +25,7 @@
 #include "dpft_kernels.h"
 #include "dpft_records.h"
 #include "uic_tile.cuh"
+#include "uic_tile_async.cuh"
 
 #ifndef DPFT_MIN_CTAS
 #define DPFT_MIN_CTAS 4   // 128-thread CTAs per SM the register allocation must allow
@@ -315,6 +316,55 @@ __global__ void __launch_bounds__(kThreads, DPFT_MIN_CTAS) uic_iter_kernel(const
   reduce_and_finish<TRU>(p, b, red, S.acc, S.vmin, S.vmax);
 }
 
+// Same launch structure as uic_iter_kernel, tile walked by the software-pipelined routine (cp.async lookups one
+// row ahead, two shared-memory stages per warp): 68 KB of dynamic shared memory, two CTAs per SM, no register cap.
+#ifndef DPFT_ASYNC_CTAS
+#define DPFT_ASYNC_CTAS 2
+#endif
+template <bool TRU>
+__global__ void __launch_bounds__(kThreads, DPFT_ASYNC_CTAS) uic_iter_async_kernel(const UicIterParams p) {
+  extern __shared__ __align__(16) float dyn_stage[];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int b = blockIdx.y;
+  const int plane = p.H * p.W;
+  const int wt = blockIdx.x * kWarps + warp;
+  const bool warp_on = wt < p.nseg * p.nrt;
+  const int seg = warp_on ? wt % p.nseg : 0;
+  const int rt = warp_on ? wt / p.nseg : 0;
+  const int y0 = rt * p.TR;
+  const int y1 = warp_on ? min(y0 + p.TR, p.H) : y0;
+
+  PairView g;
+  const size_t po = (size_t)b * p.C * plane;
+  g.x0 = p.x0 + po; g.x1 = p.x1 + po; g.s0 = p.s0 + po; g.s1 = p.s1 + po;
+  g.d0 = p.d0 + (size_t)b * plane; g.d1 = p.d1 + (size_t)b * plane;
+  g.m0 = p.m0 ? p.m0 + (size_t)b * plane : nullptr;
+  g.m1 = p.m1 ? p.m1 + (size_t)b * plane : nullptr;
+  g.occ_out = p.occ_out ? p.occ_out + (size_t)b * plane : nullptr;
+  g.sr0_dbg = p.sr0_dbg ? p.sr0_dbg + (size_t)b * plane : nullptr;
+  g.H = p.H; g.W = p.W; g.C = p.C;
+  g.fx = __ldg(p.K + 4 * b); g.fy = __ldg(p.K + 4 * b + 1); g.cx = __ldg(p.K + 4 * b + 2); g.cy = __ldg(p.K + 4 * b + 3);
+  g.s0lo = g.s0hi = 0.f;
+
+  __shared__ float red[kWarps][NSUM][33];
+  __shared__ __align__(16) float s_pose[12];
+  cudaTriggerProgrammaticLaunchCompletion();
+  cudaGridDependencySynchronize();
+  if (threadIdx.x < 12) s_pose[threadIdx.x] = __ldcg(p.pose + (size_t)b * 12 + threadIdx.x);
+  if (TRU) {
+    g.s0lo = ord2f(__ldcg(p.s0mm));
+    g.s0hi = ord2f(__ldcg(p.s0mm + 1));
+#pragma unroll
+    for (int i = 0; i < 12; ++i) red[warp][27 + i][lane] = 0.f;
+  }
+  __syncthreads();
+  TileSums S;
+  S.reset();
+  if (y1 > y0)
+    process_tile_async<TRU>(g, s_pose, &red[warp][27], dyn_stage + warp * kAsyncWarpFloats, seg, y0, y1, lane, S);
+  reduce_and_finish<TRU>(p, b, red, S.acc, S.vmin, S.vmax);
+}
+
 // =========================================================================== materialised-gradient path
 // The unit Sobel gradients of x0 and sigma0 do not depend on the pose, so they can be formed once per level
 // (sobel_unit_kernel) and read back by the three iterations.  That costs HBM traffic (4C extra floats per
@@ -549,8 +599,8 @@ struct Plan {
 // Rows per warp tile.  A tile is walked row by row by one warp, so the time of a launch is about
 // (waves of CTAs) x (rows per tile + ~1.5 rows of window priming and reduction tail): pick the height that
 // minimises that, i.e. fill whole waves of the 148 x DPFT_MIN_CTAS resident CTAs.
-static int pick_tile_rows(int H, int nseg, int B) {
-  long slots = 148L * DPFT_MIN_CTAS;
+static int pick_tile_rows(int H, int nseg, int B, int ctas_per_sm) {
+  long slots = 148L * ctas_per_sm;
   if (const char* e = getenv("DPFT_CTA_SLOTS")) slots = std::max(1L, atol(e));   // tuning hook
   int best_tr = 1;
   double best = 1e30;
@@ -571,7 +621,7 @@ static Plan make_plan(const dpft_level_t* lv, int n_levels, int B, int C, uint32
   pl.max_plane = 0;
   for (int l = 0; l < n_levels; ++l) {
     pl.nseg[l] = (lv[l].W + kCols - 1) / kCols;
-    pl.TR[l] = pick_tile_rows(lv[l].H, pl.nseg[l], B);
+    pl.TR[l] = pick_tile_rows(lv[l].H, pl.nseg[l], B, ((flags & DPFT_ASYNC_GATHER) && C % 8 == 0) ? DPFT_ASYNC_CTAS : DPFT_MIN_CTAS);
     pl.nrt[l] = (lv[l].H + pl.TR[l] - 1) / pl.TR[l];
     pl.ctas[l] = (pl.nseg[l] * pl.nrt[l] + kWarps - 1) / kWarps;
     if (pl.ctas[l] > pl.max_ctas) pl.max_ctas = pl.ctas[l];
@@ -659,6 +709,28 @@ static cudaError_t launch_iter(const UicIterParams& prm, dim3 grid, bool tru, bo
   cfg.numAttrs = pdl ? 1 : 0;
   if (tru) return cudaLaunchKernelEx(&cfg, uic_iter_kernel<CH, true>, prm);
   return cudaLaunchKernelEx(&cfg, uic_iter_kernel<CH, false>, prm);
+}
+
+static cudaError_t launch_async(const UicIterParams& prm, dim3 grid, bool tru, bool pdl, cudaStream_t stream) {
+  constexpr int smem = kWarps * kAsyncWarpFloats * (int)sizeof(float);
+  static bool configured = false;
+  if (!configured) {
+    cudaFuncSetAttribute(uic_iter_async_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    cudaFuncSetAttribute(uic_iter_async_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    configured = true;
+  }
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = grid;
+  cfg.blockDim = dim3(kThreads);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl ? 1 : 0;
+  if (tru) return cudaLaunchKernelEx(&cfg, uic_iter_async_kernel<true>, prm);
+  return cudaLaunchKernelEx(&cfg, uic_iter_async_kernel<false>, prm);
 }
 
 template <int CH>
@@ -830,6 +902,8 @@ static int run_uic(const dpft_level_t* levels, int n_levels, int B, int C, int i
           case 2: err = launch_px<2>(prm, ex, grid, tru, use_pdl, stream); break;
           default: err = launch_px<1>(prm, ex, grid, tru, use_pdl, stream); break;
         }
+      } else if ((flags & DPFT_ASYNC_GATHER) && C % 8 == 0) {
+        err = launch_async(prm, grid, tru, use_pdl, stream);
       } else
       switch (CH) {
         case 8: err = launch_iter<8>(prm, grid, tru, use_pdl, stream); break;

@@ -133,7 +133,10 @@ __device__ __forceinline__ void process_tile(const PairView& g, const float* spo
 
       float saa = 0.f, sab = 0.f, sbb = 0.f, sar = 0.f, sbr = 0.f, sca = 0.f, scb = 0.f;
       float pmin = CUDART_INF_F, pmax = -CUDART_INF_F, sr0 = 0.f;
-      constexpr int G = CH < 4 ? CH : 4;   // channels whose 8*G lookups are in flight together
+#ifndef DPFT_GATHER_GROUP
+#define DPFT_GATHER_GROUP 4
+#endif
+      constexpr int G = CH < DPFT_GATHER_GROUP ? CH : DPFT_GATHER_GROUP;   // channels whose 8*G lookups are in flight together
 #pragma unroll
       for (int g0 = 0; g0 < CH; g0 += G) {
         float xa[G], xb[G], xc_[G], xd[G], za[G], zb[G], zc[G], zd[G];

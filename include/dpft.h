@@ -48,6 +48,8 @@ extern "C" {
 #define DPFT_LAUNCH_PER_ITERATION 0x10u /* one launch per Gauss-Newton iteration instead of the single
                                           cooperative launch (the ICP term, occ_out and the materialised
                                           gradients always use it)                                           */
+#define DPFT_ASYNC_GATHER     0x20u /* fused kernel with the lookups issued by cp.async one tile row ahead
+                                       (C % 8 == 0; launch-per-iteration path)                                 */
 #define DPFT_FUSED_SOBEL      0x08u /* recompute the unit Sobel gradients inside every iteration (sliding register
                                        window) instead of materialising them once per level                    */
 
