@@ -17,7 +17,7 @@ PKG_DIR = os.path.dirname(os.path.abspath(__file__))
 REPO_DIR = os.path.dirname(PKG_DIR)
 CSRC = os.path.join(PKG_DIR, "csrc")
 LIB_PATH = os.path.join(PKG_DIR, "libdpft.so")
-SOURCES = ["dpft_abi.cu", "uic_forward.cu", "uic_backward.cu", "icp_term.cu", "uic_residual.cu", "ic_path.cu", "uic_persistent.cu"]
+SOURCES = ["dpft_abi.cu", "uic_forward.cu", "uic_backward.cu", "icp_term.cu", "uic_residual.cu", "ic_path.cu", "uic_persistent.cu", "preprocess.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "-Xcompiler", "-fPIC", "-shared"]
 
@@ -136,6 +136,9 @@ def lib() -> ctypes.CDLL:
         fn = getattr(L, name)
         fn.restype = ctypes.c_int
         fn.argtypes = args
+    L.dpft_preprocess_depth.restype = ctypes.c_int
+    L.dpft_preprocess_depth.argtypes = [vp, ci, ci, ci, ci, ctypes.POINTER(vp), ctypes.POINTER(vp), vp,
+                                        ctypes.c_size_t, vp]
     if L.dpft_abi_version() != DPFT_ABI_VERSION:
         raise RuntimeError("libdpft.so ABI version mismatch; rebuild")
     _lib = L
@@ -147,7 +150,7 @@ def exported_symbols() -> List[str]:
     return ["dpft_abi_version", "dpft_last_error", "dpft_uic_workspace_bytes", "dpft_uic_forward",
             "dpft_uic_forward_timed", "dpft_uic_backward_workspace_bytes", "dpft_uic_backward",
             "dpft_uic_residual_workspace_bytes", "dpft_uic_residual_loss", "dpft_ic_gradients", "dpft_ic_residual",
-            "dpft_ic_normal_matrix", "dpft_ic_rhs", "dpft_ic_update"]
+            "dpft_ic_normal_matrix", "dpft_ic_rhs", "dpft_ic_update", "dpft_preprocess_depth"]
 
 
 def check(code: int, what: str) -> None:

@@ -168,6 +168,26 @@ def uic_solve(levels: Sequence[Dict[str, torch.Tensor]], pose: Pose, *, iters: i
     return SolveResult(pose_hist, sys_hist[:n_it], aux_hist[:n_it], status, occ, n_levels, iters, launch_ms)
 
 
+def depth_pyramids(depth: torch.Tensor, n_levels: int = 4, with_depth: bool = False):
+    """Depth stage of LeastSquareTracking._preprocess (LeastSquareTracking.py:656-661, 668-674): returns the
+    inverse-depth pyramid [level 0 (finest), 1, ...] (clamp(1/d,0,10), batch-global min / max zeroed, max-pooled)
+    and, with ``with_depth``, the max-pooled depth pyramid the ICP term wants."""
+    L = _lib.lib()
+    d = _dev_f32(depth, "depth")
+    B, H, W = int(d.shape[0]), int(d.shape[-2]), int(d.shape[-1])
+    dev = d.device
+    inv = [torch.empty((B, 1, H >> l, W >> l), dtype=torch.float32, device=dev) for l in range(n_levels)]
+    dpt = [torch.empty_like(t) for t in inv] if with_depth else None
+    PtrArr = ctypes.c_void_p * n_levels
+    ws = torch.empty((8,), dtype=torch.uint8, device=dev)
+    with torch.cuda.device(dev):
+        code = L.dpft_preprocess_depth(d.data_ptr(), B, H, W, n_levels, PtrArr(*[t.data_ptr() for t in inv]),
+                                       PtrArr(*[t.data_ptr() for t in dpt]) if dpt else None, ws.data_ptr(), 8,
+                                       torch.cuda.current_stream(dev).cuda_stream)
+    _lib.check(code, "dpft_preprocess_depth")
+    return (inv, dpt) if with_depth else inv
+
+
 # ----------------------------------------------------------------------------- autograd
 def _level_array(levels, B, C, obj_mask0=None, obj_mask1=None, with_depth=False):
     """ctypes array of dpft_level for already-converted device tensors; returns (array, keep-alive list)."""

@@ -103,6 +103,16 @@ int dpft_uic_forward(const dpft_level_t *levels, int n_levels, int B, int C, int
                      int32_t *status, void *workspace, size_t workspace_bytes, void *stream);
 
 /*
+ * Depth stage of LeastSquareTracking._preprocess (LeastSquareTracking.py:656-661, 668-674; ImagePyramids
+ * alg:1201-1219): invd = clamp(1/depth, 0, 10) with the pixels on the batch-global minimum, then on the
+ * batch-global maximum, zeroed; max-pooled pyramids (kernel = stride = 2^l, floor sizes) of invd and, when
+ * depth_out is not NULL, of depth.  Outputs are listed FINE level first (level l has (H >> l) x (W >> l) pixels),
+ * each (B,1,h,w).  workspace: 8 bytes.
+ */
+int dpft_preprocess_depth(const float *depth, int B, int H, int W, int n_levels, float *const *invd_out,
+                          float *const *depth_out, void *workspace, size_t workspace_bytes, void *stream);
+
+/*
  * IC tracker (TrustRegionBase alg:45-139 + DirectSolverNet alg:1604-1691), split around the learned networks
  * the reference calls inside the loop.  `level` needs x0, x1, invd0, invd1, K (+ optional object masks).
  *   dpft_ic_gradients      gx, gy (B,C,H,W) <- unit Sobel gradient of x0 (feature_gradient, alg:1844-1865)
