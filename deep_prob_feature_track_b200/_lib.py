@@ -29,6 +29,8 @@ DPFT_NO_PDL = 0x04
 DPFT_FUSED_SOBEL = 0x08
 DPFT_LAUNCH_PER_ITERATION = 0x10
 DPFT_ASYNC_GATHER = 0x20
+DPFT_SHARED_KEYFRAME = 0x40
+DPFT_PAIRWISE_EXTREMES = 0x80
 DPFT_ST_NONFINITE = 0x01
 DPFT_ST_SINGULAR = 0x02
 

@@ -95,6 +95,7 @@ class SolveResult:
 def uic_solve(levels: Sequence[Dict[str, torch.Tensor]], pose: Pose, *, iters: int = 3,
               remove_tru_sigma: bool = False, combine_icp: bool = False, w_icp: float = 0.01,
               want_occ: bool = False, pdl: bool = True, timed: bool = False, fused_sobel: bool = True, single_launch: bool = False, async_gather: bool = False,
+              shared_keyframe: bool = False, pairwise_extremes: bool = False,
               obj_mask0: Optional[Sequence] = None, obj_mask1: Optional[Sequence] = None) -> SolveResult:
     """Coarse-to-fine U_IC solve of a batch of frame pairs on the current CUDA stream.
 
@@ -104,7 +105,8 @@ def uic_solve(levels: Sequence[Dict[str, torch.Tensor]], pose: Pose, *, iters: i
     L = _lib.lib()
     n_levels = len(levels)
     x0 = levels[0]["x0"]
-    B, C = int(x0.shape[0]), int(x0.shape[1])
+    B, C = int(levels[0]["x1"].shape[0]), int(x0.shape[1])
+    Bk = 1 if shared_keyframe else B     # batch size of the keyframe-side tensors
     dev = x0.device
     keep = []   # keep converted tensors alive until the launches are queued
     arr = (_lib.DpftLevel * n_levels)()
@@ -112,12 +114,12 @@ def uic_solve(levels: Sequence[Dict[str, torch.Tensor]], pose: Pose, *, iters: i
     for i, lv in enumerate(levels):
         t = {k: _dev_f32(lv[k], k) for k in ("x0", "x1", "s0", "s1", "invD0", "invD1", "K")}
         H, W = int(t["x0"].shape[2]), int(t["x0"].shape[3])
-        for k in ("x0", "x1", "s0", "s1"):
-            if tuple(t[k].shape) != (B, C, H, W):
-                raise ValueError(f"level {i}: {k} has shape {tuple(t[k].shape)}, expected {(B, C, H, W)}")
-        for k in ("invD0", "invD1"):
-            if t[k].numel() != B * H * W:
-                raise ValueError(f"level {i}: {k} must be (B,1,H,W)")
+        for k, nb in (("x0", Bk), ("x1", B), ("s0", Bk), ("s1", B)):
+            if tuple(t[k].shape) != (nb, C, H, W):
+                raise ValueError(f"level {i}: {k} has shape {tuple(t[k].shape)}, expected {(nb, C, H, W)}")
+        for k, nb in (("invD0", Bk), ("invD1", B)):
+            if t[k].numel() != nb * H * W:
+                raise ValueError(f"level {i}: {k} must be ({nb},1,H,W)")
         if tuple(t["K"].shape) != (B, 4):
             raise ValueError(f"level {i}: K must be (B,4)")
         m0 = _dev_mask(obj_mask0[i] if obj_mask0 is not None else None, "obj_mask0")
@@ -141,7 +143,11 @@ def uic_solve(levels: Sequence[Dict[str, torch.Tensor]], pose: Pose, *, iters: i
     flags = ((_lib.DPFT_REMOVE_TRU_SIGMA if remove_tru_sigma else 0) | (0 if pdl else _lib.DPFT_NO_PDL)
              | (_lib.DPFT_FUSED_SOBEL if fused_sobel else 0) | (_lib.DPFT_COMBINE_ICP if combine_icp else 0)
              | (0 if single_launch else _lib.DPFT_LAUNCH_PER_ITERATION)
-             | (_lib.DPFT_ASYNC_GATHER if async_gather else 0))
+             | (_lib.DPFT_ASYNC_GATHER if async_gather else 0)
+             | (_lib.DPFT_SHARED_KEYFRAME if shared_keyframe else 0)
+             | (_lib.DPFT_PAIRWISE_EXTREMES if pairwise_extremes else 0))
+    if (shared_keyframe or pairwise_extremes) and (combine_icp or not fused_sobel):
+        raise NotImplementedError("shared_keyframe / pairwise_extremes are served by the fused U_IC kernel only")
     n_it = n_levels * iters
     pose_in = pack_pose(pose).to(dev)
     pose_hist = torch.empty((n_it + 1, B, 12), dtype=torch.float32, device=dev)
@@ -566,6 +572,26 @@ class TrustRegionBase(nn.Module):
         r, occ = lvl.residual(pack_pose(pose).to(lvl.dev), first=True)
         w = self._weights(r, lvl.t["x0"], lvl.t["x1"], wPrior)
         return _avg_loss([r if w is None else w * r], occ)
+
+
+class KeyframeTracker:
+    """Keyframe-mode tracking as experiments/kf_vo.py does it (TUM_RGBD.py:334-340: every live frame against
+    one fixed keyframe), but batched: the keyframe side (x0, sigma0, inverse depth per level) is uploaded once
+    and any number of live frames are solved against it in one call.  Every frame keeps the semantics of a
+    B = 1 call of the reference (sigma extremes per pair)."""
+
+    def __init__(self, key_levels: Sequence[Dict[str, torch.Tensor]], iters: int = 3, remove_tru_sigma: bool = True):
+        self.key = [{k: _dev_f32(lv[k], k) for k in ("x0", "s0", "invD0")} for lv in key_levels]
+        for lv in self.key:
+            if lv["x0"].shape[0] != 1:
+                raise ValueError("a keyframe has batch size 1")
+        self.iters, self.tru = iters, remove_tru_sigma
+
+    def track(self, live_levels: Sequence[Dict[str, torch.Tensor]], pose: Pose) -> SolveResult:
+        """live_levels: per level x1, s1 (B,C,h,w), invD1 (B,1,h,w), K (B,4); pose: starting poses of the B frames."""
+        levels = [dict(kf, x1=lv["x1"], s1=lv["s1"], invD1=lv["invD1"], K=lv["K"]) for kf, lv in zip(self.key, live_levels)]
+        return uic_solve(levels, pose, iters=self.iters, remove_tru_sigma=self.tru, shared_keyframe=True,
+                         pairwise_extremes=True)
 
 
 def patch_tracker(net: nn.Module) -> nn.Module:

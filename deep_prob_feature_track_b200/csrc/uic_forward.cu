@@ -55,6 +55,8 @@ struct UicIterParams {
   float* gmm;            // [4] batch-global min/max of the warped sigma of this iteration, min/max of sigma0
   int32_t* status;
   uint32_t flags;
+  int kf_shared;         // keyframe-side tensors (x0, sigma0, invd0, obj_mask0) have batch size 1
+  int pairwise;          // sigma extremes per pair instead of per batch (each pair its own batch of one)
   const float* icp_rec;  // (B,28) sums of the point-to-plane term of this iteration, or nullptr
   float icp_w2;          // its weight squared (w_icp scales both J and r)
 };
@@ -233,6 +235,11 @@ __device__ __forceinline__ void reduce_and_finish(const UicIterParams& p, const 
     if (threadIdx.x == 0) finalize_pair<false>(p, b, 0.f, 0.f);
     return;
   }
+  if (p.pairwise) {
+    // every pair is its own batch: its extremes are "the batch extremes", nothing couples the pairs
+    if (threadIdx.x == 0) finalize_pair<true>(p, b, pair_min, pair_max);
+    return;
+  }
 
   // ---------------------------------------------------------------- last CTA of the grid: batch extremes + all solves
   if (threadIdx.x == 0) s_flag = (atomicAdd(p.counters + p.B, 1) == p.B - 1);
@@ -286,9 +293,10 @@ __global__ void __launch_bounds__(kThreads, DPFT_MIN_CTAS) uic_iter_kernel(const
 
   PairView g;
   const size_t po = (size_t)b * p.C * plane;
-  g.x0 = p.x0 + po; g.x1 = p.x1 + po; g.s0 = p.s0 + po; g.s1 = p.s1 + po;
-  g.d0 = p.d0 + (size_t)b * plane; g.d1 = p.d1 + (size_t)b * plane;
-  g.m0 = p.m0 ? p.m0 + (size_t)b * plane : nullptr;
+  const size_t b0 = p.kf_shared ? 0 : (size_t)b;      // one keyframe for the whole batch (kf_vo-style tracking)
+  g.x0 = p.x0 + b0 * p.C * plane; g.x1 = p.x1 + po; g.s0 = p.s0 + b0 * p.C * plane; g.s1 = p.s1 + po;
+  g.d0 = p.d0 + b0 * plane; g.d1 = p.d1 + (size_t)b * plane;
+  g.m0 = p.m0 ? p.m0 + b0 * plane : nullptr;
   g.m1 = p.m1 ? p.m1 + (size_t)b * plane : nullptr;
   g.occ_out = p.occ_out ? p.occ_out + (size_t)b * plane : nullptr;
   g.sr0_dbg = p.sr0_dbg ? p.sr0_dbg + (size_t)b * plane : nullptr;
@@ -304,8 +312,9 @@ __global__ void __launch_bounds__(kThreads, DPFT_MIN_CTAS) uic_iter_kernel(const
   cudaGridDependencySynchronize();
   if (threadIdx.x < 12) s_pose[threadIdx.x] = __ldcg(p.pose + (size_t)b * 12 + threadIdx.x);
   if (TRU) {
-    g.s0lo = ord2f(__ldcg(p.s0mm));
-    g.s0hi = ord2f(__ldcg(p.s0mm + 1));
+    const uint32_t* mm = p.s0mm + ((p.pairwise && !p.kf_shared) ? 2 * b : 0);
+    g.s0lo = ord2f(__ldcg(mm));
+    g.s0hi = ord2f(__ldcg(mm + 1));
 #pragma unroll
     for (int i = 0; i < 12; ++i) red[warp][27 + i][lane] = 0.f;
   }
@@ -336,9 +345,10 @@ __global__ void __launch_bounds__(kThreads, DPFT_ASYNC_CTAS) uic_iter_async_kern
 
   PairView g;
   const size_t po = (size_t)b * p.C * plane;
-  g.x0 = p.x0 + po; g.x1 = p.x1 + po; g.s0 = p.s0 + po; g.s1 = p.s1 + po;
-  g.d0 = p.d0 + (size_t)b * plane; g.d1 = p.d1 + (size_t)b * plane;
-  g.m0 = p.m0 ? p.m0 + (size_t)b * plane : nullptr;
+  const size_t b0 = p.kf_shared ? 0 : (size_t)b;      // one keyframe for the whole batch (kf_vo-style tracking)
+  g.x0 = p.x0 + b0 * p.C * plane; g.x1 = p.x1 + po; g.s0 = p.s0 + b0 * p.C * plane; g.s1 = p.s1 + po;
+  g.d0 = p.d0 + b0 * plane; g.d1 = p.d1 + (size_t)b * plane;
+  g.m0 = p.m0 ? p.m0 + b0 * plane : nullptr;
   g.m1 = p.m1 ? p.m1 + (size_t)b * plane : nullptr;
   g.occ_out = p.occ_out ? p.occ_out + (size_t)b * plane : nullptr;
   g.sr0_dbg = p.sr0_dbg ? p.sr0_dbg + (size_t)b * plane : nullptr;
@@ -352,8 +362,9 @@ __global__ void __launch_bounds__(kThreads, DPFT_ASYNC_CTAS) uic_iter_async_kern
   cudaGridDependencySynchronize();
   if (threadIdx.x < 12) s_pose[threadIdx.x] = __ldcg(p.pose + (size_t)b * 12 + threadIdx.x);
   if (TRU) {
-    g.s0lo = ord2f(__ldcg(p.s0mm));
-    g.s0hi = ord2f(__ldcg(p.s0mm + 1));
+    const uint32_t* mm = p.s0mm + ((p.pairwise && !p.kf_shared) ? 2 * b : 0);
+    g.s0lo = ord2f(__ldcg(mm));
+    g.s0hi = ord2f(__ldcg(mm + 1));
 #pragma unroll
     for (int i = 0; i < 12; ++i) red[warp][27 + i][lane] = 0.f;
   }
@@ -571,6 +582,24 @@ __global__ void __launch_bounds__(256) minmax_kernel(const float* __restrict__ v
   }
 }
 
+// per-pair variant: blockIdx.y = pair, extremes of v[b, :] into mm[2b], mm[2b+1]
+__global__ void __launch_bounds__(256) minmax_pairs_kernel(const float* __restrict__ v, size_t per_pair,
+                                                           uint32_t* __restrict__ mm) {
+  const float* q = v + (size_t)blockIdx.y * per_pair;
+  float lo = CUDART_INF_F, hi = -CUDART_INF_F;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < per_pair; i += (size_t)gridDim.x * blockDim.x) {
+    const float x = __ldg(q + i);
+    lo = fminf(lo, x);
+    hi = fmaxf(hi, x);
+  }
+  lo = warp_min(lo);
+  hi = warp_max(hi);
+  if ((threadIdx.x & 31) == 0) {
+    atomicMin(mm + 2 * blockIdx.y, f2ord(lo));
+    atomicMax(mm + 2 * blockIdx.y + 1, f2ord(hi));
+  }
+}
+
 void launch_minmax(const float* v, size_t n, uint32_t* mm, cudaStream_t stream) {
   const int blocks = (int)std::min<size_t>((n / 4 + 255) / 256 + 1, 148 * 8);
   minmax_kernel<<<blocks, 256, 0, stream>>>(v, n, mm);
@@ -645,7 +674,7 @@ static Plan make_plan(const dpft_level_t* lv, int n_levels, int B, int C, uint32
   pl.off_partials = take((size_t)B * pl.max_ctas * PS * sizeof(float));
   pl.off_pairrec = take((size_t)B * PS * sizeof(double));
   pl.off_counters = take((size_t)(B + 1) * sizeof(int));
-  pl.off_mm = take((size_t)2 * DPFT_MAX_LEVELS * sizeof(uint32_t));
+  pl.off_mm = take((size_t)2 * DPFT_MAX_LEVELS * sizeof(uint32_t) * ((flags & DPFT_PAIRWISE_EXTREMES) ? B : 1));
   pl.off_gmm = take(4 * sizeof(float) * DPFT_MAX_LEVELS * 64);
   pl.off_sr0 = take(((flags & DPFT_REMOVE_TRU_SIGMA) && any_occ) ? (size_t)B * pl.max_plane * sizeof(float) : 0);
   pl.grad_elems = (flags & DPFT_FUSED_SOBEL) ? 0 : (size_t)B * C * pl.max_plane;
@@ -757,7 +786,8 @@ using namespace dpft;
 // The single-launch path serves the plain U_IC solve; the ICP term, the per-iteration mask output and the
 // materialised-gradient variant keep one launch per iteration.
 static bool persistent_ok(uint32_t flags, bool any_occ) {
-  return (flags & DPFT_FUSED_SOBEL) && !(flags & (DPFT_COMBINE_ICP | DPFT_LAUNCH_PER_ITERATION)) && !any_occ;
+  return (flags & DPFT_FUSED_SOBEL) && !any_occ &&
+         !(flags & (DPFT_COMBINE_ICP | DPFT_LAUNCH_PER_ITERATION | DPFT_SHARED_KEYFRAME | DPFT_PAIRWISE_EXTREMES));
 }
 
 static int persistent_grid_cached(int C, bool tru) {
@@ -809,15 +839,24 @@ static int run_uic(const dpft_level_t* levels, int n_levels, int B, int C, int i
   uint32_t* dmm = (uint32_t*)(ws + pl.off_dmm);
 
   {
-    const int n = std::max(B * 12, B + 1);
-    init_kernel<<<(n + 255) / 256, 256, 0, stream>>>(pose_in, pose_hist, B * 12, counters, B + 1, mm, n_levels);
+    const int n_mm = n_levels * (((flags & DPFT_PAIRWISE_EXTREMES) && !(flags & DPFT_SHARED_KEYFRAME)) ? B : 1);
+    const int n = std::max(std::max(B * 12, B + 1), n_mm);
+    init_kernel<<<(n + 255) / 256, 256, 0, stream>>>(pose_in, pose_hist, B * 12, counters, B + 1, mm, n_mm);
     if (icp) init_kernel<<<1, 32, 0, stream>>>(pose_in, pose_hist, 0, counters, 0, dmm, n_levels);
   }
+  const bool shared_kf = flags & DPFT_SHARED_KEYFRAME, pairwise = flags & DPFT_PAIRWISE_EXTREMES;
+  const int mm_per_level = (pairwise && !shared_kf) ? B : 1;
   if (tru) {
     for (int l = 0; l < n_levels; ++l) {
-      const size_t n = (size_t)B * C * levels[l].H * levels[l].W;
-      const int blocks = (int)std::min<size_t>((n / 4 + 255) / 256 + 1, 148 * 8);
-      minmax_kernel<<<blocks, 256, 0, stream>>>(levels[l].sigma0, n, mm + 2 * l);
+      const size_t per_pair = (size_t)C * levels[l].H * levels[l].W;
+      const size_t n = per_pair * (shared_kf ? 1 : B);
+      if (mm_per_level == 1) {
+        const int blocks = (int)std::min<size_t>((n / 4 + 255) / 256 + 1, 148 * 8);
+        minmax_kernel<<<blocks, 256, 0, stream>>>(levels[l].sigma0, n, mm + 2 * l);
+      } else {
+        const dim3 g((unsigned)std::min<size_t>((per_pair + 255) / 256, 64), B);
+        minmax_pairs_kernel<<<g, 256, 0, stream>>>(levels[l].sigma0, per_pair, mm + 2 * (size_t)l * B);
+      }
     }
   }
   if (persist) {
@@ -883,7 +922,8 @@ static int run_uic(const dpft_level_t* levels, int n_levels, int B, int C, int i
       prm.pose_next = pose_hist + (size_t)(k + 1) * B * 12;
       prm.sys_out = sys_hist + (size_t)k * B * 27;
       prm.partials = partials; prm.pairrec = pairrec; prm.counters = counters;
-      prm.s0mm = mm + 2 * l; prm.gmm = gmm + 4 * k; prm.status = status; prm.flags = flags;
+      prm.s0mm = mm + 2 * (size_t)l * mm_per_level; prm.gmm = gmm + 4 * k;
+      prm.kf_shared = shared_kf; prm.pairwise = pairwise; prm.status = status; prm.flags = flags;
       if (icp) {
         launch_icp_term(L.depth0, L.K, vn, vn + 3 * (size_t)B * plane, prm.pose, L.obj_mask0, L.obj_mask1, icp_rec,
                         nullptr, nullptr, B, L.H, L.W, stream);

@@ -50,6 +50,10 @@ extern "C" {
                                           gradients always use it)                                           */
 #define DPFT_ASYNC_GATHER     0x20u /* fused kernel with the lookups issued by cp.async one tile row ahead
                                        (C % 8 == 0; launch-per-iteration path)                                 */
+#define DPFT_SHARED_KEYFRAME  0x40u /* x0, sigma0, invd0 (and obj_mask0) have batch size 1: every pair of the
+                                       batch tracks against the same keyframe (kf_vo.py keyframe mode); forward only */
+#define DPFT_PAIRWISE_EXTREMES 0x80u /* with DPFT_REMOVE_TRU_SIGMA: sigma extremes per pair, i.e. the semantics of
+                                        calling the reference once per pair with B = 1 (kf_vo.py:156-166); forward only */
 #define DPFT_FUSED_SOBEL      0x08u /* recompute the unit Sobel gradients inside every iteration (sliding register
                                        window) instead of materialising them once per level                    */
 
