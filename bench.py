@@ -102,32 +102,6 @@ class ClockSampler:
                 "reasons": sorted(self.reasons), "samples": len(self.samples)}
 
 
-def pack_levels(levels, pin: bool):
-    """All tensors of a pyramid in ONE flat buffer (256-byte aligned pieces) so a step's input is one copy."""
-    layout, off = [], 0
-    for i, lv in enumerate(levels):
-        for k, v in lv.items():
-            layout.append((i, k, off, tuple(v.shape)))
-            off += (v.numel() + 63) // 64 * 64
-    flat = torch.empty(off, dtype=torch.float32, pin_memory=pin)
-    for (i, k, o, shape) in layout:
-        n = 1
-        for s in shape:
-            n *= s
-        flat[o:o + n].view(shape).copy_(levels[i][k])
-    return flat, layout
-
-
-def views(flat, layout, n_levels):
-    out = [dict() for _ in range(n_levels)]
-    for (i, k, o, shape) in layout:
-        n = 1
-        for s in shape:
-            n *= s
-        out[i][k] = flat[o:o + n].view(shape)
-    return out
-
-
 def cpu_sample(levels, R0, t0, n_pairs, min_seconds=10.0, max_reps=500):
     """Time the oracle port (reference op chain: grid_sample + permute/bmm/sum) on the host cores."""
     from oracle import ic_oracle as O
@@ -309,6 +283,7 @@ def main():
         dist.init_process_group("nccl", device_id=dev)
     from deep_prob_feature_track_b200 import algorithms as A
     from deep_prob_feature_track_b200.sharding import max_over_ranks
+    from deep_prob_feature_track_b200.streaming import StreamingSolver, pack_levels, views
 
     data = make_frame_pairs(B, C, H, W, seed=1234 + rank, n_levels=N_LEVELS)
     host_flat, layout = pack_levels(data["levels"], pin=True)
@@ -362,23 +337,19 @@ def main():
         per_launch = [x / n_timed for x in per_launch]
         lvl0_ms = sum(lvl0) / len(lvl0)
 
-        # ---- e2e: host buffers in, poses out, every step
-        dev_flat = torch.empty_like(host_flat, device=dev)
-        dev_views = views(dev_flat, layout, N_LEVELS)
-        out_host = torch.empty((B, 12), dtype=torch.float32, pin_memory=True)
+        # ---- e2e: host buffers in, poses out, every step.  Two device buffers and a copy stream: the upload of
+        # step k+1 runs while step k is solved (the upload is ~5x the solve, so the link sets the pace); every
+        # step still uploads all of its inputs from pinned memory and reads its poses back.
+        streamer = StreamingSolver(layout, host_flat.numel(), N_LEVELS, B, dev, solve)
 
-        def e2e_step():
-            dev_flat.copy_(host_flat, non_blocking=True)
-            r = solve(dev_views)
-            out_host.copy_(r.pose_hist[-1], non_blocking=True)
+        def e2e_run(n):
+            streamer.run([host_flat] * n)
 
         n_e2e = max(3, min(args.steps, 30))
-        for _ in range(3):
-            e2e_step()
+        e2e_run(3)
         barrier()
         e0.record()
-        for _ in range(n_e2e):
-            e2e_step()
+        e2e_run(n_e2e)
         e1.record()
         barrier()
         ms_e2e = e0.elapsed_time(e1)
@@ -389,7 +360,7 @@ def main():
         if not args.no_extras:
             extras["train_step"] = train_step_leg(A, dev_sets, pose0, B, max(3, min(args.steps, 20)), dev)
             if args.workload == "tum":
-                del dev_flat, dev_views
+                del streamer
                 extras["vga480x640"] = vga_leg(A, rank, dev, args)
 
     if rank != 0:
