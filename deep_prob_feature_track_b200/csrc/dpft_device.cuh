@@ -13,7 +13,11 @@ namespace dpft {
 __device__ __forceinline__ float xmul(float a, float b) { return __fmul_rn(a, b); }
 __device__ __forceinline__ float xadd(float a, float b) { return __fadd_rn(a, b); }
 __device__ __forceinline__ float xsub(float a, float b) { return __fsub_rn(a, b); }
+#ifdef DPFT_EXPERIMENT_FAST_DIV   // timing experiment only: NOT mask-exact
+__device__ __forceinline__ float xdiv(float a, float b) { return __fdividef(a, b); }
+#else
 __device__ __forceinline__ float xdiv(float a, float b) { return __fdiv_rn(a, b); }
+#endif
 
 // Order-preserving map float -> uint32 so atomicMin/atomicMax work on floats of either sign.
 __device__ __forceinline__ uint32_t f2ord(float f) {

@@ -1,0 +1,12 @@
+#!/bin/bash
+for flags in "$@"; do
+  export DPFT_NVCC_EXTRA="$flags"
+  python -c "from deep_prob_feature_track_b200 import _lib; _lib.build(force=True)" || exit 1
+  echo "=== $flags"
+  python -m pytest tests/test_uic_forward_gpu.py -x -q -k "launch-per-iteration" 2>&1 | tail -1
+  python bench.py --steps 100 --warmup 5 --no-cpu-baseline --no-extras 2>/dev/null | python -c "
+import json,sys
+d=json.loads(sys.stdin.read()); r=d['roofline']
+print('pairs/s %.0f  ms/step %.3f  lvl0 launch %.1f us  frac %.3f  launches(us) %s' % (d['value'], d['ms_per_step'], r['launch_ms']*1e3, r['frac'], [round(x*1e3) for x in r['all_launch_ms']]))"
+  python profiles/prof_target2.py > /dev/null 2>&1 && ncu --metrics smsp__inst_executed.sum,gpu__time_duration.sum --clock-control none -k regex:uic_iter_kernel -s 21 -c 1 --csv python profiles/prof_target2.py 2>/dev/null | grep -E "inst_executed|time_duration" | awk -F'","' '{print $(NF-2), $NF}'
+done
