@@ -79,6 +79,9 @@ __device__ __forceinline__ void process_tile(const PairView& g, const float* spo
   const bool col_out = lane >= 1 && lane <= kTileCols && x < W;
   const float fx = g.fx, fy = g.fy, cx = g.cx, cy = g.cy;
   const float px = xdiv(xsub((float)xc, cx), fx);
+  // reciprocals of the divisors that do not change over the tile (see div_by)
+  const float rcp_fy = __frcp_rn(fy);
+  const float rcp_hw = __frcp_rn(0.5f * (float)(W - 1)), rcp_hh = __frcp_rn(0.5f * (float)(H - 1));
 
   for (int c0 = 0; c0 < C; c0 += CH) {
     const float* X0 = opaque(g.x0 + (size_t)c0 * iplane);
@@ -108,7 +111,7 @@ __device__ __forceinline__ void process_tile(const PairView& g, const float* spo
       }
       const unsigned o = (unsigned)(y * W + xc);
       const float d0 = __ldg(g.d0 + o);
-      const float py = xdiv(xsub((float)y, cy), fy);
+      const float py = div_by(xsub((float)y, cy), fy, rcp_fy);
 
       float u, v, inv_z;
       {
@@ -117,11 +120,12 @@ __device__ __forceinline__ void process_tile(const PairView& g, const float* spo
         const float wx = xadd(xadd(xadd(xmul(ra.x, px), xmul(ra.y, py)), ra.z), xmul(rc.y, d0));
         const float wy = xadd(xadd(xadd(xmul(ra.w, px), xmul(rb.x, py)), rb.y), xmul(rc.z, d0));
         const float wz = xadd(xadd(xadd(xmul(rb.z, px), xmul(rb.w, py)), rc.x), xmul(rc.w, d0));
-        u = xadd(xmul(xdiv(wx, wz), fx), cx);
-        v = xadd(xmul(xdiv(wy, wz), fy), cy);
-        inv_z = xdiv(d0, wz);
+        const float rz = __frcp_rn(wz);
+        u = xadd(xmul(div_by(wx, wz, rz), fx), cx);
+        v = xadd(xmul(div_by(wy, wz, rz), fy), cy);
+        inv_z = div_by(d0, wz, rz);
       }
-      const Tap tap = make_tap(u, v, H, W);
+      const Tap tap = make_tap_r(u, v, H, W, rcp_hw, rcp_hh);
       const float d1w = sample_exact(g.d1, tap, W);
       bool occ = occluded(u, v, inv_z, d1w, H, W);
       if (g.m0) occ = occ || (__ldg(g.m0 + o) == 0);
