@@ -176,8 +176,8 @@ __device__ __forceinline__ void process_tile(const PairView& g, const float* spo
           const float fSy = __shfl_up_sync(0xffffffffu, fvd, 1) + 2.f * fvd + __shfl_down_sync(0xffffffffu, fvd, 1);
           const float sSx = __shfl_down_sync(0xffffffffu, svs, 1) - __shfl_up_sync(0xffffffffu, svs, 1);
           const float sSy = __shfl_up_sync(0xffffffffu, svd, 1) + 2.f * svd + __shfl_down_sync(0xffffffffu, svd, 1);
-          const float fin = rsqrtf(fmaf(fSx, fSx, fmaf(fSy, fSy, 1e-8f)));
-          const float sin_ = rsqrtf(fmaf(sSx, sSx, fmaf(sSy, sSy, 1e-8f)));
+          const float fin = rsqrt_fast(fmaf(fSx, fSx, fmaf(fSy, fSy, 1e-8f)));
+          const float sin_ = rsqrt_fast(fmaf(sSx, sSx, fmaf(sSy, sSy, 1e-8f)));
           gfx[c] = fSx * fin; gfy[c] = fSy * fin; gsx[c] = sSx * sin_; gsy[c] = sSy * sin_;
         }
 #pragma unroll
@@ -189,7 +189,7 @@ __device__ __forceinline__ void process_tile(const PairView& g, const float* spo
           // residual, its uncertainty and the 2-vector d(wres)/d(u,v) (algorithms.py:1969-1972, :872)
           const float res = fr - fm[k];
           const float s0v = sm[k];
-          const float rs = rsqrtf(fmaf(sr, sr, s0v * s0v));   // 1 / sigma
+          const float rs = rsqrt_fast(fmaf(sr, sr, s0v * s0v));   // 1 / sigma
           const float wres = res * rs;
           const float q = wres * (s0v * (rs * rs));           // res * sigma0 / sigma^3
           const float a = fmaf(gfx[c], rs, q * gsx[c]);

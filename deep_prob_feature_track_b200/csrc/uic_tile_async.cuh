@@ -164,8 +164,8 @@ __device__ __forceinline__ void process_tile_async(const PairView& g, const floa
         const float fSy = __shfl_up_sync(0xffffffffu, fvd, 1) + 2.f * fvd + __shfl_down_sync(0xffffffffu, fvd, 1);
         const float sSx = __shfl_down_sync(0xffffffffu, svs, 1) - __shfl_up_sync(0xffffffffu, svs, 1);
         const float sSy = __shfl_up_sync(0xffffffffu, svd, 1) + 2.f * svd + __shfl_down_sync(0xffffffffu, svd, 1);
-        const float fin = rsqrtf(fmaf(fSx, fSx, fmaf(fSy, fSy, 1e-8f)));
-        const float sin_ = rsqrtf(fmaf(sSx, sSx, fmaf(sSy, sSy, 1e-8f)));
+        const float fin = rsqrt_fast(fmaf(fSx, fSx, fmaf(fSy, fSy, 1e-8f)));
+        const float sin_ = rsqrt_fast(fmaf(sSx, sSx, fmaf(sSy, sSy, 1e-8f)));
         const float gfx = fSx * fin, gfy = fSy * fin, gsx = sSx * sin_, gsy = sSy * sin_;
 
         const float* q = sl + (4 * k) * 32;
@@ -174,7 +174,7 @@ __device__ __forceinline__ void process_tile_async(const PairView& g, const floa
         const float sr = TRU ? blend_exact(z[0], z[32], z[64], z[96], tap) : blend_fast(z[0], z[32], z[64], z[96], tap);
         const float res = fr - fm[k];
         const float s0v = sm[k];
-        const float rs = rsqrtf(fmaf(sr, sr, s0v * s0v));
+        const float rs = rsqrt_fast(fmaf(sr, sr, s0v * s0v));
         const float wres = res * rs;
         const float qq = wres * (s0v * (rs * rs));
         const float a = fmaf(gfx, rs, qq * gsx);
