@@ -7,7 +7,9 @@ A *step* is one coarse-to-fine solve (4 pyramid levels x 3 Gauss-Newton iteratio
 --remove_tru_sigma as in every script the reference ships) of one batch of synthetic frame pairs.
 The metric is frame-pair GN solves per second; rank 0 prints ONE JSON line.
 
-  value      whole-job throughput with the inputs already in HBM (CUDA events, max over ranks)
+  value      whole-job throughput with the inputs already in HBM (CUDA events, max over ranks); independent
+             batches are issued round-robin on --streams CUDA streams (default 8) so the latency-bound coarse
+             levels of one batch overlap the finest level of another; --streams 1 gives the latency of one solve
   e2e        same call made with HOST (pinned) buffers: host->device copy of the step's inputs and
              device->host read of the poses inside the timed region
   roofline   dominant kernel = the finest-level Gauss-Newton launch; algorithmic bytes per launch
@@ -224,6 +226,7 @@ def main():
     ap.add_argument("--single-launch", action="store_true",
                     help="all levels and iterations in ONE cooperative launch instead of one launch per iteration")
     ap.add_argument("--async-gather", action="store_true", help="cp.async-pipelined tile routine (DPFT_ASYNC_GATHER)")
+    ap.add_argument("--streams", type=int, default=8, help="CUDA streams the timed steps are spread over")
     ap.add_argument("--no-extras", action="store_true", help="skip the training-step and 480x640 side measurements")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
@@ -311,16 +314,37 @@ def main():
     launches_per_step = 1 + N_LEVELS + (2 if single else N_LEVELS * ITERS + (0 if args.fused_sobel else 2 * N_LEVELS))
 
     with ClockSampler(local_rank) as clocks:
-        # ---- value: inputs resident in HBM
-        for i in range(args.warmup):
-            res = solve(dev_sets[i % N_SETS])
+        # ---- value: inputs resident in HBM.  Batches are independent, so consecutive steps are issued round-robin
+        # on `--streams` CUDA streams: the latency-bound coarse levels of one batch overlap the bandwidth-heavy
+        # finest level of another.  Timed with events on the launching (default) stream, which every worker
+        # stream waits for at the start and which waits for every worker stream at the end.
+        main_stream = torch.cuda.current_stream(dev)
+        workers = [torch.cuda.Stream(device=dev) for _ in range(max(1, args.streams))]
+
+        def run_steps(n):
+            last = None
+            for i in range(n):
+                with torch.cuda.stream(workers[i % len(workers)]):
+                    last = solve(dev_sets[i % N_SETS])
+            return last
+
+        def timed(n):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(main_stream)
+            for w in workers:
+                w.wait_event(e0)
+            out = run_steps(n)
+            for w in workers:
+                done = torch.cuda.Event()
+                done.record(w)
+                main_stream.wait_event(done)
+            e1.record(main_stream)
+            return out, e0, e1
+
+        res, _, _ = timed(args.warmup)
         res.raise_if_bad()
         barrier()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        for i in range(args.steps):
-            res = solve(dev_sets[i % N_SETS])
-        e1.record()
+        res, e0, e1 = timed(args.steps)
         barrier()
         ms = e0.elapsed_time(e1)
         res.raise_if_bad()
@@ -383,7 +407,7 @@ def main():
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": wl["name"], "pairs_per_gpu_per_step": B, "feature_channels": C,
                    "resolution": f"{H}x{W}", "levels": N_LEVELS, "iters_per_level": ITERS, "variant": "U_IC",
-                   "remove_tru_sigma": True, "pdl": not args.no_pdl,
+                   "remove_tru_sigma": True, "pdl": not args.no_pdl, "streams": max(1, args.streams),
                    "sobel": "fused" if args.fused_sobel else "materialised once per level",
                    "launch": "single cooperative launch for all levels and iterations" if single else "one launch per iteration",
                    "l2": f"inputs rotate over {N_SETS} resident sets of {set_bytes / 1e6:.0f} MB each (> 126 MB L2)",
