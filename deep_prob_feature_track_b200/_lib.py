@@ -118,9 +118,10 @@ def lib() -> ctypes.CDLL:
     L.dpft_uic_backward_workspace_bytes.argtypes = L.dpft_uic_workspace_bytes.argtypes
     L.dpft_uic_backward.restype = ctypes.c_int
     L.dpft_uic_backward.argtypes = [ctypes.POINTER(DpftLevel), ctypes.POINTER(DpftLevelGrad), ctypes.c_int,
-                                    ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_uint32, ctypes.c_void_p,
+                                    ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_uint32, ctypes.c_float,
                                     ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p,
-                                    ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_void_p]
+                                    ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t,
+                                    ctypes.c_void_p]
     L.dpft_uic_residual_workspace_bytes.restype = ctypes.c_size_t
     L.dpft_uic_residual_workspace_bytes.argtypes = [ctypes.POINTER(DpftLevel), ctypes.c_int, ctypes.c_int,
                                                     ctypes.c_uint32]

@@ -250,6 +250,7 @@ class _UicSolveFn(torch.autograd.Function):
             x0, x1, s0, s1 = maps[4 * i:4 * i + 4]
             levels.append(dict(x0=x0.detach(), x1=x1.detach(), s0=s0.detach(), s1=s1.detach(), **st))
         res = uic_solve(levels, (R.detach(), t.detach()), iters=cfg["iters"], remove_tru_sigma=cfg["tru"],
+                        combine_icp=cfg.get("icp", False), w_icp=cfg.get("w_icp", 0.01),
                         obj_mask0=cfg.get("obj_mask0"), obj_mask1=cfg.get("obj_mask1"))
         if cfg.get("check", True):
             res.raise_if_bad()
@@ -282,19 +283,21 @@ class _UicSolveFn(torch.autograd.Function):
                 if gA is None:
                     gA = torch.zeros((n_levels, B, 36), dtype=torch.float32, device=dev)
                 gA[l] = gAl.reshape(B, 36)
-        arr, keep = _level_array(levels, B, C, cfg.get("obj_mask0"), cfg.get("obj_mask1"))
+        icp = bool(cfg.get("icp", False))
+        arr, keep = _level_array(levels, B, C, cfg.get("obj_mask0"), cfg.get("obj_mask1"), with_depth=icp)
         garr = (_lib.DpftLevelGrad * n_levels)()
         gmaps = []
         for i, lv in enumerate(levels):
             g = [torch.zeros_like(lv["x0"], dtype=torch.float32, memory_format=torch.contiguous_format) for _ in range(4)]
             gmaps += g
             garr[i].g_x0, garr[i].g_x1, garr[i].g_sigma0, garr[i].g_sigma1 = (x.data_ptr() for x in g)
-        flags = _lib.DPFT_REMOVE_TRU_SIGMA if cfg["tru"] else 0
+        flags = (_lib.DPFT_REMOVE_TRU_SIGMA if cfg["tru"] else 0) | (_lib.DPFT_COMBINE_ICP if icp else 0)
         gin = torch.empty((B, 12), dtype=torch.float32, device=dev)
         ws_bytes = L.dpft_uic_backward_workspace_bytes(arr, n_levels, B, C, iters, flags)
         ws = torch.empty((ws_bytes,), dtype=torch.uint8, device=dev)
         with torch.cuda.device(dev):
-            code = L.dpft_uic_backward(arr, garr, n_levels, B, C, iters, flags, res.pose_hist.data_ptr(),
+            code = L.dpft_uic_backward(arr, garr, n_levels, B, C, iters, flags,
+                                       ctypes.c_float(cfg.get("w_icp", 0.01)), res.pose_hist.data_ptr(),
                                        res.sys_hist.data_ptr(), res.aux_hist.data_ptr(), gpose.data_ptr(),
                                        gA.data_ptr() if gA is not None else None, gin.data_ptr(), ws.data_ptr(),
                                        ws_bytes, torch.cuda.current_stream(dev).cuda_stream)
@@ -304,12 +307,16 @@ class _UicSolveFn(torch.autograd.Function):
 
 
 def uic_track(levels: Sequence[Dict[str, torch.Tensor]], pose: Pose, *, iters: int = 3, remove_tru_sigma: bool = False,
-              obj_mask0=None, obj_mask1=None, check: bool = True):
+              combine_icp: bool = False, w_icp: float = 0.01, obj_mask0=None, obj_mask1=None, check: bool = True):
     """Differentiable coarse-to-fine solve: returns [(R_l, t_l, JtWJ_l) for every level], coarse first.
     Gradients flow to x0, x1, s0, s1 of every level and to the starting pose (train.py's loss sums over the
     per-level poses, criterions.py:101-136)."""
     static = [dict(invD0=lv["invD0"], invD1=lv["invD1"], K=lv["K"]) for lv in levels]
-    cfg = dict(static=static, iters=iters, tru=remove_tru_sigma, obj_mask0=obj_mask0, obj_mask1=obj_mask1, check=check)
+    if combine_icp:
+        for st, lv in zip(static, levels):
+            st.update(depth0=lv["depth0"], depth1=lv["depth1"])
+    cfg = dict(static=static, iters=iters, tru=remove_tru_sigma, icp=combine_icp, w_icp=w_icp, obj_mask0=obj_mask0,
+               obj_mask1=obj_mask1, check=check)
     R, t = pose
     B = R.shape[0]
     maps = []
@@ -356,11 +363,9 @@ class TrustRegionInverseWUncertainty(nn.Module):
             weights = torch.full((1, 1, 1, 1), w_icp, dtype=x0.dtype, device=x0.device).expand(
                 x0.shape[0], 1, x0.shape[2], x0.shape[3])
         if torch.is_grad_enabled() and any(t.requires_grad for t in (x0, x1, sigma0, sigma1, pose10[0], pose10[1])):
-            if self.combine_icp:
-                raise NotImplementedError("the ICP term has no backward kernel yet (DESIGN.md, 'next')")
             # training: same kernels, recorded for autograd (backward = dpft_uic_backward)
             (R, t, A), = uic_track([lv], (pose10[0], pose10[1]), iters=self.max_iterations,
-                                   remove_tru_sigma=self.remove_tru_sigma,
+                                   remove_tru_sigma=self.remove_tru_sigma, combine_icp=self.combine_icp, w_icp=w_icp,
                                    obj_mask0=None if obj_mask0 is None else [obj_mask0],
                                    obj_mask1=None if obj_mask1 is None else [obj_mask1], check=self.check_nan)
             if self.timers: self.timers.toc('trust-region level solve (fused CUDA)')

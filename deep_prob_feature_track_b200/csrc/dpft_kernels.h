@@ -18,6 +18,12 @@ void launch_icp_term(const float* depth0, const float* K, const float* V1, const
                      const uint8_t* m0, const uint8_t* m1, float* rec, uint8_t* occ_out, float* r_out, int B, int H,
                      int W, cudaStream_t stream);
 
+// Pose gradient of the point-to-plane term of one iteration, accumulated into gpose (B,12)
+void launch_icp_bwd(const float* depth0, const float* K, const float* V1, const float* N1, const float* pose,
+                    const float* mlam, const uint8_t* m0, const uint8_t* m1, float* gpose, float w2, int B, int H, int W,
+                    cudaStream_t stream);
+void launch_minmax(const float* v, size_t n, uint32_t* mm, cudaStream_t stream);
+
 // ---- persistent (single cooperative launch) U_IC forward, uic_persistent.cu
 struct PLevel {
   const float *x0, *x1, *s0, *s1, *d0, *d1, *K;

@@ -374,6 +374,11 @@ __global__ void __launch_bounds__(256) sobel_unit_bwd_kernel(const float* __rest
   }
 }
 
+__global__ void bwd_mm_init_kernel(uint32_t* mm) {
+  mm[0] = 0xffffffffu;
+  mm[1] = 0u;
+}
+
 __global__ void copy_kernel(const float* __restrict__ src, float* __restrict__ dst, size_t n) {
   const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) dst[i] = src ? src[i] : 0.f;
@@ -381,10 +386,10 @@ __global__ void copy_kernel(const float* __restrict__ src, float* __restrict__ d
 
 struct BwdPlan {
   size_t max_plane, grad_elems;
-  size_t off_unit, off_gunit, off_gpose, off_mlam, total;
+  size_t off_unit, off_gunit, off_gpose, off_mlam, off_vn, off_dmm, total;
 };
 
-static BwdPlan make_bwd_plan(const dpft_level_t* lv, int n_levels, int B, int C, int iters) {
+static BwdPlan make_bwd_plan(const dpft_level_t* lv, int n_levels, int B, int C, int iters, bool icp = false) {
   BwdPlan pl{};
   for (int l = 0; l < n_levels; ++l) pl.max_plane = std::max(pl.max_plane, (size_t)lv[l].H * lv[l].W);
   pl.grad_elems = (size_t)B * C * pl.max_plane;
@@ -398,6 +403,8 @@ static BwdPlan make_bwd_plan(const dpft_level_t* lv, int n_levels, int B, int C,
   pl.off_gunit = take(4 * pl.grad_elems * sizeof(float));
   pl.off_gpose = take((size_t)(n_levels * iters + 1) * B * 12 * sizeof(float));
   pl.off_mlam = take((size_t)B * 27 * sizeof(float));
+  pl.off_vn = take(icp ? 6 * (size_t)B * pl.max_plane * sizeof(float) : 0);
+  pl.off_dmm = take(2 * sizeof(uint32_t));
   pl.total = off;
   return pl;
 }
@@ -414,27 +421,29 @@ using namespace dpft;
 
 extern "C" size_t dpft_uic_backward_workspace_bytes(const dpft_level_t* levels, int n_levels, int B, int C,
                                                     int iters, uint32_t flags) {
-  (void)flags;
   if (!levels || n_levels < 1 || n_levels > DPFT_MAX_LEVELS || B < 1 || C < 1 || iters < 1) {
     set_error(DPFT_EINVAL, "bad problem size");
     return 0;
   }
-  return make_bwd_plan(levels, n_levels, B, C, iters).total;
+  return make_bwd_plan(levels, n_levels, B, C, iters, flags & DPFT_COMBINE_ICP).total;
 }
 
 extern "C" int dpft_uic_backward(const dpft_level_t* levels, const dpft_level_grad_t* grads, int n_levels, int B,
-                                 int C, int iters, uint32_t flags, const float* pose_hist, const float* sys_hist,
+                                 int C, int iters, uint32_t flags, float w_icp, const float* pose_hist, const float* sys_hist,
                                  const float* aux_hist, const float* grad_pose_hist, const float* grad_A,
                                  float* grad_pose_in, void* workspace, size_t workspace_bytes, void* stream_) {
   if (!levels || !grads || n_levels < 1 || n_levels > DPFT_MAX_LEVELS || B < 1 || B > 65535 || C < 1 || iters < 1)
     return set_error(DPFT_EINVAL, "bad problem size");
   if (!pose_hist || !sys_hist || !aux_hist || !grad_pose_hist || !grad_pose_in || !workspace)
     return set_error(DPFT_EINVAL, "pose_hist, sys_hist, aux_hist, grad_pose_hist, grad_pose_in and workspace are required");
-  if (flags & DPFT_COMBINE_ICP) return set_error(DPFT_EINVAL, "DPFT_COMBINE_ICP has no backward yet");
+  const bool icp = flags & DPFT_COMBINE_ICP;
+  if (icp)
+    for (int l = 0; l < n_levels; ++l)
+      if (!levels[l].depth0 || !levels[l].depth1) return set_error(DPFT_EINVAL, "level %d: DPFT_COMBINE_ICP needs depth0 and depth1", l);
   for (int l = 0; l < n_levels; ++l)
     if (!grads[l].g_x0 || !grads[l].g_x1 || !grads[l].g_sigma0 || !grads[l].g_sigma1)
       return set_error(DPFT_EINVAL, "level %d: all four gradient maps are required", l);
-  const BwdPlan pl = make_bwd_plan(levels, n_levels, B, C, iters);
+  const BwdPlan pl = make_bwd_plan(levels, n_levels, B, C, iters, icp);
   if (workspace_bytes < pl.total) return set_error(DPFT_ENOSPACE, "workspace has %zu bytes, %zu needed", workspace_bytes, pl.total);
   cudaStream_t stream = (cudaStream_t)stream_;
   char* ws = (char*)workspace;
@@ -442,6 +451,8 @@ extern "C" int dpft_uic_backward(const dpft_level_t* levels, const dpft_level_gr
   float* gunit = (float*)(ws + pl.off_gunit);
   float* gpose = (float*)(ws + pl.off_gpose);
   float* mlam = (float*)(ws + pl.off_mlam);
+  float* vn = (float*)(ws + pl.off_vn);
+  uint32_t* dmm = (uint32_t*)(ws + pl.off_dmm);
   const bool tru = flags & DPFT_REMOVE_TRU_SIGMA;
   const int n_it = n_levels * iters;
   const int CH = (C % 8 == 0) ? 8 : (C % 4 == 0) ? 4 : (C % 2 == 0) ? 2 : 1;
@@ -458,6 +469,11 @@ extern "C" int dpft_uic_backward(const dpft_level_t* levels, const dpft_level_gr
     launch_sobel_unit(L.x0, u0, u1, B * C, L.H, L.W, stream);
     launch_sobel_unit(L.sigma0, u2, u3, B * C, L.H, L.W, stream);
     cudaMemsetAsync(gunit, 0, 4 * pl.grad_elems * sizeof(float), stream);
+    if (icp) {
+      bwd_mm_init_kernel<<<1, 1, 0, stream>>>(dmm);
+      launch_minmax(L.depth1, (size_t)B * plane, dmm, stream);
+      launch_vertex_normal(L.depth1, L.K, dmm, vn, vn + 3 * (size_t)B * plane, B, L.H, L.W, stream);
+    }
     const long want_threads = 148L * 2048 * 2;
     long ppt = ((long)B * (long)plane + want_threads - 1) / want_threads;
     ppt = std::max(1L, std::min(ppt, 8L));
@@ -479,6 +495,9 @@ extern "C" int dpft_uic_backward(const dpft_level_t* levels, const dpft_level_gr
       prm.mlam = mlam;
       prm.aux = aux_hist + 4 * k;
       prm.gpose = gpose + (size_t)k * B * 12;
+      if (icp)
+        launch_icp_bwd(L.depth0, L.K, vn, vn + 3 * (size_t)B * plane, prm.pose, mlam, L.obj_mask0, L.obj_mask1,
+                       prm.gpose, w_icp * w_icp, B, L.H, L.W, stream);
       switch (CH) {
         case 8: launch_bwd<8>(prm, grid, tru, stream); break;
         case 4: launch_bwd<4>(prm, grid, tru, stream); break;

@@ -173,7 +173,7 @@ size_t dpft_uic_backward_workspace_bytes(const dpft_level_t *levels, int n_level
  *   grad_pose_in   (B,12)                       OUT: dL/d(pose_in)
  */
 int dpft_uic_backward(const dpft_level_t *levels, const dpft_level_grad_t *grads, int n_levels, int B, int C,
-                      int iters, uint32_t flags, const float *pose_hist, const float *sys_hist,
+                      int iters, uint32_t flags, float w_icp, const float *pose_hist, const float *sys_hist,
                       const float *aux_hist, const float *grad_pose_hist, const float *grad_A,
                       float *grad_pose_in, void *workspace, size_t workspace_bytes, void *stream);
 

@@ -13,7 +13,7 @@ pytestmark = pytest.mark.gpu
 DEV = "cuda:0"
 
 
-def cuda_grads(levels, R0, t0, iters, tru, loss_fn):
+def cuda_grads(levels, R0, t0, iters, tru, loss_fn, icp=False, w_icp=0.01):
     lv_dev = []
     leaves = []
     for lv in levels:
@@ -24,7 +24,7 @@ def cuda_grads(levels, R0, t0, iters, tru, loss_fn):
         leaves.append({k: d[k] for k in ("x0", "x1", "s0", "s1")})
     R = R0.to(DEV).clone().requires_grad_(True)
     t = t0.to(DEV).clone().requires_grad_(True)
-    outs = A.uic_track(lv_dev, (R, t), iters=iters, remove_tru_sigma=tru)
+    outs = A.uic_track(lv_dev, (R, t), iters=iters, remove_tru_sigma=tru, combine_icp=icp, w_icp=w_icp)
     loss = loss_fn(outs)
     loss.backward()
     torch.cuda.synchronize()
@@ -99,3 +99,37 @@ def test_module_trains_like_the_reference_module():
     loss.backward()
     assert frob_rel(lv["x1"].grad.cpu(), g["g_x1"]) < TOL_GRAD
     assert frob_rel(t0.grad.cpu().view(-1, 3), g["g_t0"]) < TOL_GRAD
+
+
+@pytest.mark.parametrize("n_levels,w_icp", [(1, 0.01), (2, 0.01), (1, 1.0)])
+def test_icp_term_backward_against_oracle_autograd(n_levels, w_icp):
+    """combine_icp in training (train_tum_feature_icp.sh): the point-to-plane term adds a pose-gradient path."""
+    B, C, H, W = 2, 4, 32, 44
+    data = make_frame_pairs(B, C, H, W, seed=60 + n_levels, n_levels=n_levels, with_depth=True)
+    gen = torch.Generator().manual_seed(3)
+    R0, t0 = _twist_to_pose((torch.rand((B, 6), generator=gen) * 2 - 1) * 0.01)
+    cs = [(torch.randn((B, 3, 3), generator=gen), torch.randn((B, 3), generator=gen)) for _ in range(n_levels)]
+
+    def loss_cuda(outs):
+        return sum((R * c[0].to(DEV)).sum() + (t * c[1].to(DEV)).sum() for (R, t, _), c in zip(outs, cs))
+
+    loss, leaves, gR, gt, _ = cuda_grads(data["levels"], R0, t0, 2, True, loss_cuda, icp=True, w_icp=w_icp)
+    o_levels = []
+    for lv in data["levels"]:
+        d = dict(lv)
+        for k in ("x0", "x1", "s0", "s1"):
+            d[k] = lv[k].clone().requires_grad_(True)
+        o_levels.append(d)
+    Ro, to = R0.clone().requires_grad_(True), t0.clone().requires_grad_(True)
+    # w_icp = 1 makes the point-to-plane term dominate the system, so its gradient path is really exercised
+    _, per_level = O.track_pyramid(o_levels, (Ro, to), iters=2, remove_tru_sigma=True, combine_icp=True,
+                                   scale_func=lambda r, w, prior: torch.ones_like(r) * w_icp, reduction="einsum")
+    loss_o = sum((R * c[0]).sum() + (t * c[1]).sum() for (R, t), c in zip(per_level, cs))
+    loss_o.backward()
+    assert abs(loss - loss_o.item()) < 1e-4 * max(1.0, abs(loss_o.item()))
+    for l in range(n_levels):
+        for k in ("x0", "x1", "s0", "s1"):
+            e = frob_rel(leaves[l][k].grad.cpu(), o_levels[l][k].grad)
+            assert e < TOL_GRAD, (l, k, e)
+    assert frob_rel(gR, Ro.grad) < TOL_GRAD, frob_rel(gR, Ro.grad)
+    assert frob_rel(gt, to.grad) < TOL_GRAD, frob_rel(gt, to.grad)
