@@ -17,7 +17,7 @@ PKG_DIR = os.path.dirname(os.path.abspath(__file__))
 REPO_DIR = os.path.dirname(PKG_DIR)
 CSRC = os.path.join(PKG_DIR, "csrc")
 LIB_PATH = os.path.join(PKG_DIR, "libdpft.so")
-SOURCES = ["dpft_abi.cu", "uic_forward.cu", "uic_backward.cu", "icp_term.cu", "uic_residual.cu", "ic_path.cu", "uic_persistent.cu", "preprocess.cu"]
+SOURCES = ["dpft_abi.cu", "uic_forward.cu", "uic_backward.cu", "icp_term.cu", "uic_residual.cu", "ic_path.cu", "ic_backward.cu", "uic_persistent.cu", "preprocess.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "-Xcompiler", "-fPIC", "-shared"]
 
@@ -135,7 +135,12 @@ def lib() -> ctypes.CDLL:
                        ("dpft_ic_residual", [lp, ci, ci, vp, vp, vp, vp]),
                        ("dpft_ic_normal_matrix", [lp, ci, ci, vp, vp, vp, vp, vp]),
                        ("dpft_ic_rhs", [lp, ci, ci, vp, vp, vp, vp, ci, vp, vp]),
-                       ("dpft_ic_update", [ci, ci, ci, vp, vp, vp, vp, vp, vp, vp, vp, vp])):
+                       ("dpft_ic_update", [ci, ci, ci, vp, vp, vp, vp, vp, vp, vp, vp, vp]),
+                       ("dpft_ic_gradients_backward", [lp, ci, ci, vp, vp, vp, vp]),
+                       ("dpft_ic_residual_backward", [lp, ci, ci, vp, vp, vp, vp, vp, vp]),
+                       ("dpft_ic_normal_matrix_backward", [lp, ci, ci, vp, vp, vp, vp, vp, vp, vp, vp]),
+                       ("dpft_ic_rhs_backward", [lp, ci, ci, vp, vp, vp, vp, ci, vp, vp, vp, vp, vp, vp, vp, vp]),
+                       ("dpft_ic_update_backward", [ci, ci, ci, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp])):
         fn = getattr(L, name)
         fn.restype = ctypes.c_int
         fn.argtypes = args
@@ -153,7 +158,9 @@ def exported_symbols() -> List[str]:
     return ["dpft_abi_version", "dpft_last_error", "dpft_uic_workspace_bytes", "dpft_uic_forward",
             "dpft_uic_forward_timed", "dpft_uic_backward_workspace_bytes", "dpft_uic_backward",
             "dpft_uic_residual_workspace_bytes", "dpft_uic_residual_loss", "dpft_ic_gradients", "dpft_ic_residual",
-            "dpft_ic_normal_matrix", "dpft_ic_rhs", "dpft_ic_update", "dpft_preprocess_depth"]
+            "dpft_ic_normal_matrix", "dpft_ic_rhs", "dpft_ic_update", "dpft_ic_gradients_backward",
+            "dpft_ic_residual_backward", "dpft_ic_normal_matrix_backward", "dpft_ic_rhs_backward",
+            "dpft_ic_update_backward", "dpft_preprocess_depth"]
 
 
 def check(code: int, what: str) -> None:

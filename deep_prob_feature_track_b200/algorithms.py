@@ -441,7 +441,8 @@ class DirectSolverNet(nn.Module):
 
 class _IcLevel:
     """One pyramid level of the IC tracker on the device: converted inputs, the unit gradients of x0, and thin
-    wrappers of the dpft_ic_* entry points."""
+    differentiable wrappers of the dpft_ic_* entry points (each a torch.autograd.Function whose backward is the
+    matching dpft_ic_*_backward call, so autograd can chain them around the M-estimator and the damping MLP)."""
 
     def __init__(self, x0, x1, invD0, invD1, K, obj_mask0=None, obj_mask1=None):
         self.L = _lib.lib()
@@ -449,10 +450,8 @@ class _IcLevel:
         self.B, self.C, self.H, self.W = (int(v) for v in self.t["x0"].shape)
         self.dev = self.t["x0"].device
         self.m0, self.m1 = _dev_mask(obj_mask0, "obj_mask0"), _dev_mask(obj_mask1, "obj_mask1")
-        self.gx = torch.empty_like(self.t["x0"])
-        self.gy = torch.empty_like(self.t["x0"])
         self.status = torch.zeros((1,), dtype=torch.int32, device=self.dev)
-        self._call("dpft_ic_gradients", self._arr(False), self.B, self.C, self.gx.data_ptr(), self.gy.data_ptr())
+        self.gx, self.gy = _IcGradFn.apply(self, self.t["x0"])
 
     def _arr(self, use_mask0):
         arr = (_lib.DpftLevel * 1)()
@@ -470,9 +469,7 @@ class _IcLevel:
 
     def residual(self, pose_rows, first):
         """(r (B,C,H,W), occ bool (B,1,H,W)); the keyframe object mask only counts on the first call (alg:65-66, 86-87)."""
-        r = torch.empty_like(self.t["x0"])
-        occ = torch.empty((self.B, 1, self.H, self.W), dtype=torch.uint8, device=self.dev)
-        self._call("dpft_ic_residual", self._arr(first), self.B, self.C, pose_rows.data_ptr(), r.data_ptr(), occ.data_ptr())
+        r, occ = _IcResidualFn.apply(self, first, pose_rows, self.t["x0"], self.t["x1"])
         return r, occ.bool()
 
     def _w(self, weights):
@@ -481,31 +478,156 @@ class _IcLevel:
         return _dev_f32(weights.expand(self.B, self.C, self.H, self.W), "weights")
 
     def normal_matrix(self, weights):
-        A21 = torch.empty((self.B, 21), dtype=torch.float32, device=self.dev)
-        w = self._w(weights)
-        self._call("dpft_ic_normal_matrix", self._arr(False), self.B, self.C, self.gx.data_ptr(), self.gy.data_ptr(),
-                   w.data_ptr() if w is not None else None, A21.data_ptr())
-        return A21
+        return _IcNormalFn.apply(self, self.gx, self.gy, self._w(weights))
 
-    def rhs(self, weights, poses):
-        S = int(poses.shape[0])
-        out = torch.empty((S, self.B, 6), dtype=torch.float32, device=self.dev)
-        w = self._w(weights)
-        self._call("dpft_ic_rhs", self._arr(False), self.B, self.C, self.gx.data_ptr(), self.gy.data_ptr(),
-                   w.data_ptr() if w is not None else None, poses.data_ptr(), S, out.data_ptr())
-        return out
+    def rhs(self, weights, poses, first=False):
+        """(S,B,6) J^T W r at S poses; ``first``: the residual of the level's first warp, which also honours the
+        keyframe object mask (alg:63-66 feeds it to the first solve)."""
+        return _IcRhsFn.apply(self, first, self.gx, self.gy, self._w(weights), poses, self.t["x0"], self.t["x1"])
 
     def update(self, mode, A21, rhs, pose_rows, lambdas=None, damp=None):
-        S = int(lambdas.numel()) if mode == 1 else 1
-        out = torch.empty((S, self.B, 12), dtype=torch.float32, device=self.dev)
-        with torch.cuda.device(self.dev):
-            code = self.L.dpft_ic_update(self.B, S, mode, A21.data_ptr(), rhs.data_ptr(),
-                                         lambdas.data_ptr() if lambdas is not None else None,
-                                         damp.data_ptr() if damp is not None else None, pose_rows.data_ptr(),
-                                         out.data_ptr(), None, self.status.data_ptr(),
-                                         torch.cuda.current_stream(self.dev).cuda_stream)
-        _lib.check(code, "dpft_ic_update")
+        return _IcUpdateFn.apply(self, mode, A21, rhs, pose_rows, lambdas, damp)
+
+
+def _ptr(t: Optional[torch.Tensor]):
+    return None if t is None else t.data_ptr()
+
+
+class _IcGradFn(torch.autograd.Function):
+    """dpft_ic_gradients / dpft_ic_gradients_backward."""
+
+    @staticmethod
+    def forward(ctx, lvl, x0):
+        gx, gy = torch.empty_like(x0), torch.empty_like(x0)
+        lvl._call("dpft_ic_gradients", lvl._arr(False), lvl.B, lvl.C, gx.data_ptr(), gy.data_ptr())
+        ctx.lvl = lvl
+        return gx, gy
+
+    @staticmethod
+    def backward(ctx, g_gx, g_gy):
+        lvl = ctx.lvl
+        g_gx, g_gy = g_gx.contiguous(), g_gy.contiguous()
+        g_x0 = torch.zeros_like(lvl.t["x0"])
+        lvl._call("dpft_ic_gradients_backward", lvl._arr(False), lvl.B, lvl.C, g_gx.data_ptr(), g_gy.data_ptr(),
+                  g_x0.data_ptr())
+        return None, g_x0
+
+
+class _IcResidualFn(torch.autograd.Function):
+    """dpft_ic_residual / dpft_ic_residual_backward."""
+
+    @staticmethod
+    def forward(ctx, lvl, first, rows, x0, x1):
+        rows = rows.contiguous()
+        r = torch.empty_like(x0)
+        occ = torch.empty((lvl.B, 1, lvl.H, lvl.W), dtype=torch.uint8, device=lvl.dev)
+        lvl._call("dpft_ic_residual", lvl._arr(first), lvl.B, lvl.C, rows.data_ptr(), r.data_ptr(), occ.data_ptr())
+        ctx.lvl, ctx.first = lvl, first
+        ctx.save_for_backward(rows)
+        ctx.mark_non_differentiable(occ)
+        return r, occ
+
+    @staticmethod
+    def backward(ctx, g_r, _g_occ):
+        lvl = ctx.lvl
+        rows, = ctx.saved_tensors
+        g_r = g_r.contiguous()
+        g_x0, g_x1 = torch.zeros_like(lvl.t["x0"]), torch.zeros_like(lvl.t["x1"])
+        g_rows = torch.zeros_like(rows)
+        lvl._call("dpft_ic_residual_backward", lvl._arr(ctx.first), lvl.B, lvl.C, rows.data_ptr(), g_r.data_ptr(),
+                  g_x0.data_ptr(), g_x1.data_ptr(), g_rows.data_ptr())
+        return None, None, g_rows, g_x0, g_x1
+
+
+class _IcNormalFn(torch.autograd.Function):
+    """dpft_ic_normal_matrix / dpft_ic_normal_matrix_backward."""
+
+    @staticmethod
+    def forward(ctx, lvl, gx, gy, w):
+        A21 = torch.empty((lvl.B, 21), dtype=torch.float32, device=lvl.dev)
+        lvl._call("dpft_ic_normal_matrix", lvl._arr(False), lvl.B, lvl.C, gx.data_ptr(), gy.data_ptr(), _ptr(w),
+                  A21.data_ptr())
+        ctx.lvl, ctx.has_w = lvl, w is not None
+        ctx.save_for_backward(gx, gy, *([w] if w is not None else []))
+        return A21
+
+    @staticmethod
+    def backward(ctx, g_A21):
+        lvl = ctx.lvl
+        gx, gy = ctx.saved_tensors[:2]
+        w = ctx.saved_tensors[2] if ctx.has_w else None
+        g_A21 = g_A21.contiguous()
+        g_gx, g_gy = torch.empty_like(gx), torch.empty_like(gy)
+        g_w = torch.empty_like(w) if w is not None else None
+        lvl._call("dpft_ic_normal_matrix_backward", lvl._arr(False), lvl.B, lvl.C, gx.data_ptr(), gy.data_ptr(), _ptr(w),
+                  g_A21.data_ptr(), g_gx.data_ptr(), g_gy.data_ptr(), _ptr(g_w))
+        return None, g_gx, g_gy, g_w
+
+
+class _IcRhsFn(torch.autograd.Function):
+    """dpft_ic_rhs / dpft_ic_rhs_backward (the residual is recomputed inside both)."""
+
+    @staticmethod
+    def forward(ctx, lvl, first, gx, gy, w, poses, x0, x1):
+        poses = poses.contiguous()
+        S = int(poses.shape[0])
+        out = torch.empty((S, lvl.B, 6), dtype=torch.float32, device=lvl.dev)
+        lvl._call("dpft_ic_rhs", lvl._arr(first), lvl.B, lvl.C, gx.data_ptr(), gy.data_ptr(), _ptr(w), poses.data_ptr(),
+                  S, out.data_ptr())
+        ctx.lvl, ctx.first, ctx.has_w = lvl, first, w is not None
+        ctx.save_for_backward(gx, gy, poses, *([w] if w is not None else []))
         return out
+
+    @staticmethod
+    def backward(ctx, g_rhs):
+        lvl = ctx.lvl
+        gx, gy, poses = ctx.saved_tensors[:3]
+        w = ctx.saved_tensors[3] if ctx.has_w else None
+        g_rhs = g_rhs.contiguous()
+        g_gx, g_gy = torch.zeros_like(gx), torch.zeros_like(gy)
+        g_w = torch.zeros_like(w) if w is not None else None
+        g_x0, g_x1 = torch.zeros_like(lvl.t["x0"]), torch.zeros_like(lvl.t["x1"])
+        g_poses = torch.zeros_like(poses)
+        lvl._call("dpft_ic_rhs_backward", lvl._arr(ctx.first), lvl.B, lvl.C, gx.data_ptr(), gy.data_ptr(), _ptr(w),
+                  poses.data_ptr(), int(poses.shape[0]), g_rhs.data_ptr(), g_gx.data_ptr(), g_gy.data_ptr(), _ptr(g_w),
+                  g_x0.data_ptr(), g_x1.data_ptr(), g_poses.data_ptr())
+        return None, None, g_gx, g_gy, g_w, g_poses, g_x0, g_x1
+
+
+class _IcUpdateFn(torch.autograd.Function):
+    """dpft_ic_update / dpft_ic_update_backward."""
+
+    @staticmethod
+    def forward(ctx, lvl, mode, A21, rhs, rows, lambdas, damp):
+        A21, rhs, rows = A21.contiguous(), rhs.contiguous(), rows.contiguous()
+        damp = damp.contiguous() if damp is not None else None
+        S = int(lambdas.numel()) if mode == 1 else 1
+        out = torch.empty((S, lvl.B, 12), dtype=torch.float32, device=lvl.dev)
+        with torch.cuda.device(lvl.dev):
+            code = lvl.L.dpft_ic_update(lvl.B, S, mode, A21.data_ptr(), rhs.data_ptr(), _ptr(lambdas), _ptr(damp),
+                                        rows.data_ptr(), out.data_ptr(), None, lvl.status.data_ptr(),
+                                        torch.cuda.current_stream(lvl.dev).cuda_stream)
+        _lib.check(code, "dpft_ic_update")
+        ctx.lvl, ctx.mode, ctx.S, ctx.lambdas = lvl, mode, S, lambdas
+        ctx.has_damp = damp is not None
+        ctx.save_for_backward(A21, rhs, rows, *([damp] if damp is not None else []))
+        return out
+
+    @staticmethod
+    def backward(ctx, g_out):
+        lvl = ctx.lvl
+        A21, rhs, rows = ctx.saved_tensors[:3]
+        damp = ctx.saved_tensors[3] if ctx.has_damp else None
+        g_out = g_out.contiguous()
+        g_A21, g_rhs, g_rows = torch.empty_like(A21), torch.empty_like(rhs), torch.empty_like(rows)
+        g_damp = torch.empty_like(damp) if damp is not None else None
+        with torch.cuda.device(lvl.dev):
+            code = lvl.L.dpft_ic_update_backward(lvl.B, ctx.S, ctx.mode, A21.data_ptr(), rhs.data_ptr(), _ptr(ctx.lambdas),
+                                                 _ptr(damp), rows.data_ptr(), g_out.data_ptr(), g_A21.data_ptr(),
+                                                 g_rhs.data_ptr(), _ptr(g_damp), g_rows.data_ptr(),
+                                                 torch.cuda.current_stream(lvl.dev).cuda_stream)
+        _lib.check(code, "dpft_ic_update_backward")
+        return None, None, g_A21, g_rhs, g_rows, None, g_damp
 
 
 def _tri_to_full(A21: torch.Tensor) -> torch.Tensor:
@@ -540,8 +662,6 @@ class TrustRegionBase(nn.Module):
         return self.mEstimator(r, x0, x1, wPrior)
 
     def forward(self, pose, x0, x1, invD0, invD1, K, wPrior=None, vis_res=False, obj_mask0=None, obj_mask1=None):
-        if torch.is_grad_enabled() and any(t.requires_grad for t in (x0, x1, pose[0], pose[1])):
-            raise NotImplementedError("the IC tracker is forward-only here (DESIGN.md: backward exists for U_IC)")
         solver = self.directSolver
         if solver is not None and getattr(solver, "direction", "inverse") != "inverse":
             raise NotImplementedError("pose updated should be inverse for this tracker")
@@ -553,9 +673,9 @@ class TrustRegionBase(nn.Module):
         weights = self._weights(r, lvl.t["x0"], lvl.t["x1"], wPrior)
         A21 = lvl.normal_matrix(weights)
         kind = getattr(solver, "type", 0) if solver is not None else 0
-        for _ in range(self.max_iterations):
+        for it in range(self.max_iterations):
             if self.timers: self.timers.tic('solve x=A^{-1}b')
-            b0 = lvl.rhs(weights, rows.unsqueeze(0))[0]
+            b0 = lvl.rhs(weights, rows.unsqueeze(0), first=(it == 0))[0]
             if kind == 0:
                 rows = lvl.update(0, A21, b0, rows)[0]
             else:

@@ -8,6 +8,10 @@ namespace dpft {
 // gx, gy <- unit Sobel gradient of `planes` images of H x W (reference algorithms.py:1844-1865)
 void launch_sobel_unit(const float* img, float* gx, float* gy, int planes, int H, int W, cudaStream_t stream);
 
+// adjoint of launch_sobel_unit: g_img (accumulated) <- d/d(gx), d/d(gy)
+void launch_sobel_unit_bwd(const float* img, const float* ggx, const float* ggy, float* g_img, int planes, int H, int W,
+                           cudaStream_t stream);
+
 // V (B,3,H,W) = [x,y,1] depth and N (B,3,H,W) its unit normals (algorithms.py:2148-2171); dmm = order-encoded
 // min / max of the whole depth tensor
 void launch_vertex_normal(const float* depth, const float* K, const uint32_t* dmm, float* V, float* N, int B, int H,

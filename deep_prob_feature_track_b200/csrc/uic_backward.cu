@@ -27,6 +27,7 @@
 #include "dpft_device.cuh"
 #include "dpft_host.h"
 #include "dpft_kernels.h"
+#include "pose_adjoint.cuh"
 
 namespace dpft {
 
@@ -236,96 +237,11 @@ __global__ void pose_bwd_kernel(const float* __restrict__ sys, const float* __re
   for (int i = 0; i < 6; ++i) rhs[i] = (double)sys[(size_t)b * 27 + 21 + i];
   double tr = 0.0;
   for (int i = 0; i < 6; ++i) tr += A[tri(i, i)];
-  const double eps = tr * 1e-6;
-  double L[6][6];
-  for (int j = 0; j < 6; ++j) {
-    double s = A[tri(j, j)] + eps;
-    for (int k = 0; k < j; ++k) s -= L[j][k] * L[j][k];
-    const double d = sqrt(s);
-    L[j][j] = d;
-    for (int i = j + 1; i < 6; ++i) {
-      double v = A[tri(j, i)];
-      for (int k = 0; k < j; ++k) v -= L[i][k] * L[j][k];
-      L[i][j] = v / d;
-    }
-  }
-  auto chol_solve = [&](const double* r, double* out) {
-    double z[6];
-    for (int i = 0; i < 6; ++i) {
-      double v = r[i];
-      for (int k = 0; k < i; ++k) v -= L[i][k] * z[k];
-      z[i] = v / L[i][i];
-    }
-    for (int i = 5; i >= 0; --i) {
-      double v = z[i];
-      for (int k = i + 1; k < 6; ++k) v -= L[k][i] * out[k];
-      out[i] = v / L[i][i];
-    }
-  };
-  double xi[6];
-  chol_solve(rhs, xi);
-  // forward: w = -xi_w, theta = |w|, k = w/theta, dR = I + K s + K^2 c1, dt = -dR xi_v
-  const double w[3] = {-xi[0], -xi[1], -xi[2]};
-  const double th = sqrt(w[0] * w[0] + w[1] * w[1] + w[2] * w[2]);
-  const double kv[3] = {w[0] / th, w[1] / th, w[2] / th};
-  const double s = sin(th), c = cos(th), c1 = 1.0 - c;
-  const double Kx[9] = {0, -kv[2], kv[1], kv[2], 0, -kv[0], -kv[1], kv[0], 0};
-  double K2[9], dR[9];
-  for (int i = 0; i < 3; ++i)
-    for (int j = 0; j < 3; ++j) {
-      double kk = 0;
-      for (int m = 0; m < 3; ++m) kk += Kx[3 * i + m] * Kx[3 * m + j];
-      K2[3 * i + j] = kk;
-      dR[3 * i + j] = (i == j ? 1.0 : 0.0) + Kx[3 * i + j] * s + kk * c1;
-    }
-  double dt[3];
-  for (int i = 0; i < 3; ++i) dt[i] = -(dR[3 * i] * xi[3] + dR[3 * i + 1] * xi[4] + dR[3 * i + 2] * xi[5]);
-  double R[9], GR[9], Gt[3];
-  for (int i = 0; i < 9; ++i) {
-    R[i] = (double)pose_k[(size_t)b * 12 + i];
-    GR[i] = (double)gpose_next[(size_t)b * 12 + i];
-  }
-  for (int i = 0; i < 3; ++i) Gt[i] = (double)gpose_next[(size_t)b * 12 + 9 + i];
-  // R' = R dR, t' = R dt + t
-  double gRk[9], gdR[9], gdt[3];
-  for (int i = 0; i < 3; ++i)
-    for (int j = 0; j < 3; ++j) {
-      double a = 0, bb = 0;
-      for (int m = 0; m < 3; ++m) {
-        a += GR[3 * i + m] * dR[3 * j + m];      // GR dR^T
-        bb += R[3 * m + i] * GR[3 * m + j];      // R^T GR
-      }
-      gRk[3 * i + j] = a + Gt[i] * dt[j];
-      gdR[3 * i + j] = bb;
-    }
-  for (int i = 0; i < 3; ++i) gdt[i] = R[i] * Gt[0] + R[3 + i] * Gt[1] + R[6 + i] * Gt[2];
-  // dt = -dR xi_v
-  double gxi[6];
-  for (int i = 0; i < 3; ++i)
-    for (int j = 0; j < 3; ++j) gdR[3 * i + j] -= gdt[i] * xi[3 + j];
-  for (int j = 0; j < 3; ++j) gxi[3 + j] = -(dR[j] * gdt[0] + dR[3 + j] * gdt[1] + dR[6 + j] * gdt[2]);
-  // Rodrigues
-  double g_s = 0, g_c1 = 0, gK[9];
-  for (int i = 0; i < 9; ++i) {
-    g_s += gdR[i] * Kx[i];
-    g_c1 += gdR[i] * K2[i];
-  }
-  for (int i = 0; i < 3; ++i)
-    for (int j = 0; j < 3; ++j) {
-      double a = 0;
-      for (int m = 0; m < 3; ++m) a += gdR[3 * i + m] * Kx[3 * j + m] + Kx[3 * m + i] * gdR[3 * m + j];   // G K^T + K^T G
-      gK[3 * i + j] = gdR[3 * i + j] * s + c1 * a;
-    }
-  const double gk[3] = {gK[7] - gK[5], gK[2] - gK[6], gK[3] - gK[1]};
-  double g_th = g_s * c + g_c1 * s;
-  double gw[3];
-  const double kdotw = gk[0] * w[0] + gk[1] * w[1] + gk[2] * w[2];
-  g_th -= kdotw / (th * th);
-  for (int i = 0; i < 3; ++i) gw[i] = gk[i] / th + g_th * w[i] / th;
-  for (int i = 0; i < 3; ++i) gxi[i] = -gw[i];
-  // xi = H^-1 rhs:  lambda = H^-1 gxi, Hbar = -lambda xi^T;  H = A + 1e-6 tr(A) I
-  double lam[6];
-  chol_solve(gxi, lam);
+  for (int i = 0; i < 6; ++i) A[tri(i, i)] += tr * 1e-6;
+  double xi[6], lam[6], gk[12];
+  for (int i = 0; i < 12; ++i) gk[i] = 0.0;
+  solve_update_adjoint(A, rhs, pose_k + (size_t)b * 12, gpose_next + (size_t)b * 12, xi, lam, gk);
+  // xi = H^-1 rhs:  Hbar = -lambda xi^T;  H = A + 1e-6 tr(A) I
   double trH = 0;
   for (int i = 0; i < 6; ++i) trH += -lam[i] * xi[i];
   float* out = mlam + (size_t)b * 27;
@@ -337,8 +253,7 @@ __global__ void pose_bwd_kernel(const float* __restrict__ sys, const float* __re
       out[tri(i, j)] = (float)m;
     }
   for (int i = 0; i < 6; ++i) out[21 + i] = (float)lam[i];
-  for (int i = 0; i < 9; ++i) gpose_k[(size_t)b * 12 + i] += (float)gRk[i];
-  for (int i = 0; i < 3; ++i) gpose_k[(size_t)b * 12 + 9 + i] += (float)Gt[i];
+  for (int i = 0; i < 12; ++i) gpose_k[(size_t)b * 12 + i] += (float)gk[i];
 }
 
 // Adjoint of g = S / sqrt(|S|^2 + 1e-8), S = replicate-padded Sobel of img: scatters into g_img.
@@ -372,6 +287,12 @@ __global__ void __launch_bounds__(256) sobel_unit_bwd_kernel(const float* __rest
     atomicAdd(o + yb + x, 2.f * bsy);
     atomicAdd(o + yb + xr, bsx + bsy);
   }
+}
+
+void launch_sobel_unit_bwd(const float* img, const float* ggx, const float* ggy, float* g_img, int planes, int H, int W,
+                           cudaStream_t stream) {
+  const dim3 sg((W + 31) / 32, (H + 7) / 8, std::min(planes, 4096));
+  sobel_unit_bwd_kernel<<<sg, 256, 0, stream>>>(img, ggx, ggy, g_img, planes, H, W);
 }
 
 __global__ void bwd_mm_init_kernel(uint32_t* mm) {
@@ -506,9 +427,8 @@ extern "C" int dpft_uic_backward(const dpft_level_t* levels, const dpft_level_gr
       }
     }
     // unit-gradient adjoints of the level -> x0 / sigma0
-    const dim3 sg((L.W + 31) / 32, (L.H + 7) / 8, std::min(B * C, 4096));
-    sobel_unit_bwd_kernel<<<sg, 256, 0, stream>>>(L.x0, g0, g1, grads[l].g_x0, B * C, L.H, L.W);
-    sobel_unit_bwd_kernel<<<sg, 256, 0, stream>>>(L.sigma0, g2, g3, grads[l].g_sigma0, B * C, L.H, L.W);
+    launch_sobel_unit_bwd(L.x0, g0, g1, grads[l].g_x0, B * C, L.H, L.W, stream);
+    launch_sobel_unit_bwd(L.sigma0, g2, g3, grads[l].g_sigma0, B * C, L.H, L.W, stream);
     (void)ne;
   }
   copy_kernel<<<(unsigned)(((size_t)B * 12 + 255) / 256), 256, 0, stream>>>(gpose, grad_pose_in, (size_t)B * 12);

@@ -144,6 +144,32 @@ int dpft_ic_update(int B, int S, int mode, const float *A21, const float *rhs, c
                    void *stream);
 
 /*
+ * Adjoints of the five entry points above, for training the IC tracker (reference: torch.autograd over
+ * alg:45-121, 1604-1691, 1919-1957).  g_* inputs are gradients w.r.t. the matching forward output; outputs
+ * marked (+=) are accumulated with atomics and must be zeroed (or hold a running sum) before the call, the
+ * others are overwritten.  Masks and the 1e-3 fill are stop-gradients.
+ *   dpft_ic_gradients_backward      g_x0 (+=)  <- g_gx, g_gy
+ *   dpft_ic_residual_backward       g_x0, g_x1 (+=), g_pose (B,12) (+=)  <- g_r; pose as in the forward call
+ *   dpft_ic_normal_matrix_backward  g_gx, g_gy, g_weights (NULL if weights NULL)  <- g_A21 (B,21)
+ *   dpft_ic_rhs_backward            g_gx, g_gy, g_weights, g_x0, g_x1 (+=), g_poses (S,B,12) (+=)  <- g_rhs (S,B,6)
+ *   dpft_ic_update_backward         g_A21 (B,21), g_rhs (B,6), g_damp (B,6; mode 2, may be NULL),
+ *                                   g_pose_in (B,12)  <- g_pose_out (S,B,12)
+ */
+int dpft_ic_gradients_backward(const dpft_level_t *level, int B, int C, const float *g_gx, const float *g_gy,
+                               float *g_x0, void *stream);
+int dpft_ic_residual_backward(const dpft_level_t *level, int B, int C, const float *pose, const float *g_r,
+                              float *g_x0, float *g_x1, float *g_pose, void *stream);
+int dpft_ic_normal_matrix_backward(const dpft_level_t *level, int B, int C, const float *gx, const float *gy,
+                                   const float *weights, const float *g_A21, float *g_gx, float *g_gy,
+                                   float *g_weights, void *stream);
+int dpft_ic_rhs_backward(const dpft_level_t *level, int B, int C, const float *gx, const float *gy,
+                         const float *weights, const float *poses, int S, const float *g_rhs, float *g_gx,
+                         float *g_gy, float *g_weights, float *g_x0, float *g_x1, float *g_poses, void *stream);
+int dpft_ic_update_backward(int B, int S, int mode, const float *A21, const float *rhs, const float *lambdas,
+                            const float *damp, const float *pose_in, const float *g_pose_out, float *g_A21,
+                            float *g_rhs, float *g_damp, float *g_pose_in, void *stream);
+
+/*
  * forward_residuals of the U_IC tracker (alg:725-786 with compute_avg_loss alg:2119-2137): per frame pair the
  * sum over valid pixels of the squared uncertainty-weighted residuals (plus the squared weighted point-to-plane
  * residual with DPFT_COMBINE_ICP) divided by the number of valid pixels, at the given pose.  loss: (B).

@@ -222,6 +222,43 @@ def ic_single_level(name, *, seed, B=2, C=4, H=24, W=32, solver="Direct-Nodampin
          flags=np.array([0, 0, 0, iters], dtype=np.int32))
 
 
+def ic_gradients(name, *, seed, B=2, C=1, H=20, W=28, iters=2):
+    """Reference autograd through one DeepIC level (conv M-estimator + residual-volume damping MLP, eval-mode
+    batch norm): gradients of a fixed linear functional of the pose w.r.t. the maps, the start pose and the
+    first layer of each network."""
+    data = make_frame_pairs(B, C, H, W, seed=seed, n_levels=1)
+    lv = data["levels"][0]
+    R0, t0 = perturbed_pose(B, seed + 1)
+    torch.manual_seed(seed + 5)
+    mest_net = alg.DeepRobustEstimator("MultiScale2w").eval()
+    solver_net = alg.DirectSolverNet("Direct-ResVol", samples=10).eval()
+    with torch.no_grad():
+        solver_net.net[-1][0].bias.fill_(0.05)
+    mod = alg.TrustRegionBase(max_iter=iters, mEst_func=mest_net, solver_func=solver_net).eval()
+    wprior = torch.ones(B, 1, max(H // 2, 1), max(W // 2, 1)) * 0.001
+    leaves = {k: lv[k].clone().requires_grad_(True) for k in ("x0", "x1")}
+    R0 = R0.clone().requires_grad_(True)
+    t0 = t0.clone().requires_grad_(True)
+    g = torch.Generator().manual_seed(seed + 3)
+    cR = torch.randn((B, 3, 3), generator=g)
+    ct = torch.randn((B, 3), generator=g)
+    with split_clones():
+        (R, t), weights = mod([R0, t0], leaves["x0"], leaves["x1"], lv["invD0"], lv["invD1"], lv["K"], wPrior=wprior)
+        loss = (R * cR).sum() + (t * ct).sum()
+        loss.backward()
+    nets = {}
+    for prefix, net in (("mest", mest_net), ("solver", solver_net)):
+        for k, v in net.state_dict().items():
+            nets[f"{prefix}__{k}"] = v.numpy()
+    save(name, **{f"in_{k}": v for k, v in np_level(lv).items()}, R0=R0.detach().numpy(), t0=t0.detach().numpy(),
+         wprior=wprior.numpy(), cR=cR.numpy(), ct=ct.numpy(), loss=loss.detach().numpy(),
+         R_out=R.detach().numpy(), t_out=t.detach().numpy(),
+         **{f"g_{k}": v.grad.numpy() for k, v in leaves.items()}, g_R0=R0.grad.numpy(), g_t0=t0.grad.numpy(),
+         g_mest_conv0=mest_net.net[0][0].weight.grad.numpy(), g_solver_fc0=solver_net.net[0][0].weight.grad.numpy(),
+         g_solver_fc2_bias=solver_net.net[2][0].bias.grad.numpy(), **nets,
+         flags=np.array([0, 0, 0, iters], dtype=np.int32))
+
+
 def main():
     torch.set_num_threads(4)
     uic_single_level("uic_plain", seed=11)
@@ -235,6 +272,7 @@ def main():
     ic_single_level("ic_plain", seed=41)
     ic_single_level("ic_resvol", seed=42, solver="Direct-ResVol")
     ic_single_level("ic_deepic", seed=43, solver="Direct-ResVol", mest="MultiScale2w")
+    ic_gradients("ic_grad", seed=51)
 
 
 if __name__ == "__main__":

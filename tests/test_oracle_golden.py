@@ -115,3 +115,28 @@ def test_ic_level_matches_reference(name, solver, sampler):
     assert (t - g["t_out"]).abs().max() < TOL_POSE
     assert frob_rel(w, g["weights"]) < 1e-5
     assert frob_rel(loss, g["res_loss"]) < 1e-5
+
+
+@pytest.mark.parametrize("sampler", ["grid_sample", "explicit"])
+def test_ic_autograd_matches_reference(sampler):
+    """Oracle autograd through a DeepIC level (conv M-estimator + residual-volume damping MLP) against the
+    reference's own autograd."""
+    g = load_golden("ic_grad")
+    lv = level_inputs(g)
+    net, mest = damping_mlp(g), ConvMEstimator(g)
+    leaves = {k: lv[k].clone().requires_grad_(True) for k in ("x0", "x1")}
+    R0 = g["R0"].clone().requires_grad_(True)
+    t0 = g["t0"].clone().requires_grad_(True)
+    (R, t), _ = O.ic_level((R0, t0), leaves["x0"], leaves["x1"], lv["invD0"], lv["invD1"], lv["K"],
+                           iters=int(g["flags"][3]), mest=mest, wPrior=g["wprior"], solver="Direct-ResVol", net=net,
+                           sampler=sampler)
+    loss = (R * g["cR"]).sum() + (t * g["ct"]).sum()
+    loss.backward()
+    assert abs(loss.item() - g["loss"].item()) < 1e-5
+    for k, v in leaves.items():
+        assert frob_rel(v.grad, g["g_" + k]) < 1e-3, k
+    assert frob_rel(R0.grad, g["g_R0"]) < 1e-3
+    assert frob_rel(t0.grad, g["g_t0"]) < 1e-3
+    assert frob_rel(mest.net[0].weight.grad, g["g_mest_conv0"]) < 1e-3
+    assert frob_rel(net[0].weight.grad, g["g_solver_fc0"]) < 1e-3
+    assert frob_rel(net[4].bias.grad, g["g_solver_fc2_bias"]) < 1e-3
