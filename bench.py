@@ -175,7 +175,7 @@ def vga_leg(A, rank, dev, args):
 
     def solve(i, **kw):
         return A.uic_solve(sets[i % 2], pose0, iters=ITERS, remove_tru_sigma=True, pdl=not args.no_pdl,
-                           fused_sobel=args.fused_sobel, single_launch=args.single_launch, async_gather=args.async_gather, **kw)
+                           fused_sobel=args.fused_sobel, single_launch=args.single_launch, staged_footprint=not args.no_staged, **kw)
 
     for i in range(3):
         solve(i)
@@ -225,7 +225,7 @@ def main():
                     help="materialise the unit Sobel gradients once per level instead of the fused sliding-window kernel")
     ap.add_argument("--single-launch", action="store_true",
                     help="all levels and iterations in ONE cooperative launch instead of one launch per iteration")
-    ap.add_argument("--async-gather", action="store_true", help="cp.async-pipelined tile routine (DPFT_ASYNC_GATHER)")
+    ap.add_argument("--no-staged", action="store_true", help="plain fused kernel instead of the staged-footprint one (DPFT_STAGED_FOOTPRINT off)")
     ap.add_argument("--streams", type=int, default=8, help="CUDA streams the timed steps are spread over")
     ap.add_argument("--no-extras", action="store_true", help="skip the training-step and 480x640 side measurements")
     args = ap.parse_args()
@@ -301,7 +301,7 @@ def main():
 
     def solve(levels, **kw):
         return A.uic_solve(levels, pose0, iters=ITERS, remove_tru_sigma=True, pdl=not args.no_pdl, fused_sobel=args.fused_sobel,
-                           single_launch=args.single_launch, async_gather=args.async_gather, **kw)
+                           single_launch=args.single_launch, staged_footprint=not args.no_staged, **kw)
 
     def barrier():
         if world > 1:

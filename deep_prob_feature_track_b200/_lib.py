@@ -28,7 +28,7 @@ DPFT_COMBINE_ICP = 0x02
 DPFT_NO_PDL = 0x04
 DPFT_FUSED_SOBEL = 0x08
 DPFT_LAUNCH_PER_ITERATION = 0x10
-DPFT_ASYNC_GATHER = 0x20
+DPFT_STAGED_FOOTPRINT = 0x20
 DPFT_SHARED_KEYFRAME = 0x40
 DPFT_PAIRWISE_EXTREMES = 0x80
 DPFT_ST_NONFINITE = 0x01

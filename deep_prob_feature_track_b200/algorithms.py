@@ -94,7 +94,7 @@ class SolveResult:
 
 def uic_solve(levels: Sequence[Dict[str, torch.Tensor]], pose: Pose, *, iters: int = 3,
               remove_tru_sigma: bool = False, combine_icp: bool = False, w_icp: float = 0.01,
-              want_occ: bool = False, pdl: bool = True, timed: bool = False, fused_sobel: bool = True, single_launch: bool = False, async_gather: bool = False,
+              want_occ: bool = False, pdl: bool = True, timed: bool = False, fused_sobel: bool = True, single_launch: bool = False, staged_footprint: bool = True,
               shared_keyframe: bool = False, pairwise_extremes: bool = False,
               obj_mask0: Optional[Sequence] = None, obj_mask1: Optional[Sequence] = None) -> SolveResult:
     """Coarse-to-fine U_IC solve of a batch of frame pairs on the current CUDA stream.
@@ -143,7 +143,7 @@ def uic_solve(levels: Sequence[Dict[str, torch.Tensor]], pose: Pose, *, iters: i
     flags = ((_lib.DPFT_REMOVE_TRU_SIGMA if remove_tru_sigma else 0) | (0 if pdl else _lib.DPFT_NO_PDL)
              | (_lib.DPFT_FUSED_SOBEL if fused_sobel else 0) | (_lib.DPFT_COMBINE_ICP if combine_icp else 0)
              | (0 if single_launch else _lib.DPFT_LAUNCH_PER_ITERATION)
-             | (_lib.DPFT_ASYNC_GATHER if async_gather else 0)
+             | (_lib.DPFT_STAGED_FOOTPRINT if staged_footprint else 0)
              | (_lib.DPFT_SHARED_KEYFRAME if shared_keyframe else 0)
              | (_lib.DPFT_PAIRWISE_EXTREMES if pairwise_extremes else 0))
     if (shared_keyframe or pairwise_extremes) and (combine_icp or not fused_sobel):

@@ -25,7 +25,7 @@
 #include "dpft_kernels.h"
 #include "dpft_records.h"
 #include "uic_tile.cuh"
-#include "uic_tile_async.cuh"
+#include "uic_tile_staged.cuh"
 
 #ifndef DPFT_MIN_CTAS
 #define DPFT_MIN_CTAS 4   // 128-thread CTAs per SM the register allocation must allow
@@ -36,7 +36,7 @@ namespace dpft {
 constexpr int kWarps = 4;
 constexpr int kThreads = kWarps * 32;
 constexpr int kCols = kTileCols;   // output columns per warp tile
-constexpr int kMaxTileRows = 24;
+constexpr int kMaxTileRows = 40;
 
 struct UicIterParams {
   const float *x0, *x1, *s0, *s1, *d0, *d1, *K;
@@ -116,7 +116,7 @@ __device__ void finalize_pair(const UicIterParams& p, int b, float gmin, float g
 // a fixed order (deterministic), and the last CTA of the grid (or of the pair, when nothing couples the
 // pairs) damps, solves and updates the poses.
 template <bool TRU>
-__device__ __forceinline__ void reduce_and_finish(const UicIterParams& p, const int b, float (*red)[NSUM][33],
+__device__ __forceinline__ void reduce_and_finish(const UicIterParams& p, const int b, float (*redw)[33] /* this warp's [NSUM][33] */,
                                                   const float (&acc)[27], const float vmin, const float vmax) {
   __shared__ double wsum[kWarps][NSUM + 1];
   __shared__ float wvmin[kWarps], wvmax[kWarps];
@@ -126,14 +126,14 @@ __device__ __forceinline__ void reduce_and_finish(const UicIterParams& p, const 
   // ---------------------------------------------------------------- CTA reduction
   if (TRU) {
     const float wmn = warp_min(vmin), wmx = warp_max(vmax);
-    // the corrections already sit in red[warp][27..38][lane]
+    // the corrections already sit in redw[27..38][lane]
     if (vmin != wmn) {
 #pragma unroll
-      for (int i = 0; i < 6; ++i) red[warp][27 + i][lane] = 0.f;
+      for (int i = 0; i < 6; ++i) redw[27 + i][lane] = 0.f;
     }
     if (vmax != wmx) {
 #pragma unroll
-      for (int i = 0; i < 6; ++i) red[warp][33 + i][lane] = 0.f;
+      for (int i = 0; i < 6; ++i) redw[33 + i][lane] = 0.f;
     }
     if (lane == 0) {
       wvmin[warp] = wmn;
@@ -141,13 +141,13 @@ __device__ __forceinline__ void reduce_and_finish(const UicIterParams& p, const 
     }
   }
 #pragma unroll
-  for (int e = 0; e < 27; ++e) red[warp][e][lane] = acc[e];
+  for (int e = 0; e < 27; ++e) redw[e][lane] = acc[e];
   __syncwarp();
   constexpr int NE = TRU ? NSUM : 27;
   for (int e = lane; e < NE; e += 32) {
     double s = 0.0;
 #pragma unroll 8
-    for (int j = 0; j < 32; ++j) s += (double)red[warp][e][j];
+    for (int j = 0; j < 32; ++j) s += (double)redw[e][j];
     wsum[warp][e] = s;
   }
   __syncthreads();
@@ -279,11 +279,11 @@ __device__ __forceinline__ void reduce_and_finish(const UicIterParams& p, const 
   for (int i = threadIdx.x; i < p.B; i += kThreads) finalize_pair<true>(p, i, s_pair_mm[0], s_pair_mm[1]);
 }
 
-template <int CH, bool TRU>
+template <int CH, bool TRU, int GW = 0, int GH = 0>
 __global__ void __launch_bounds__(kThreads, DPFT_MIN_CTAS) uic_iter_kernel(const UicIterParams p) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int b = blockIdx.y;
-  const int plane = p.H * p.W;
+  const int plane = (GW > 0) ? GW * GH : p.H * p.W;
   const int wt = blockIdx.x * kWarps + warp;
   const bool warp_on = wt < p.nseg * p.nrt;
   const int seg = warp_on ? wt % p.nseg : 0;
@@ -321,21 +321,24 @@ __global__ void __launch_bounds__(kThreads, DPFT_MIN_CTAS) uic_iter_kernel(const
   __syncthreads();
   TileSums S;
   S.reset();
-  process_tile<CH, TRU>(g, s_pose, &red[warp][27], seg, y0, y1, lane, S);
-  reduce_and_finish<TRU>(p, b, red, S.acc, S.vmin, S.vmax);
+  process_tile<CH, TRU, GW, GH>(g, s_pose, &red[warp][27], seg, y0, y1, lane, S);
+  reduce_and_finish<TRU>(p, b, red[warp], S.acc, S.vmin, S.vmax);
 }
 
-// Same launch structure as uic_iter_kernel, tile walked by the software-pipelined routine (cp.async lookups one
-// row ahead, two shared-memory stages per warp): 68 KB of dynamic shared memory, two CTAs per SM, no register cap.
-#ifndef DPFT_ASYNC_CTAS
-#define DPFT_ASYNC_CTAS 2
+// Same launch structure as uic_iter_kernel, tile walked by the staged-footprint routine (uic_tile_staged.cuh):
+// every warp owns kStageAreaFloats of dynamic shared memory: its ring of source rows, then the 12 correction
+// rows of remove_tru_sigma; the 27 rows of the final reduction overlay the tail of the ring once the tile is done.
+#ifndef DPFT_STAGED_CTAS
+#define DPFT_STAGED_CTAS 3
 #endif
-template <bool TRU>
-__global__ void __launch_bounds__(kThreads, DPFT_ASYNC_CTAS) uic_iter_async_kernel(const UicIterParams p) {
+constexpr int kStageAreaFloats = (kStageWarpFloats + 12 * 33 + 3) / 4 * 4;
+static_assert(kStageWarpFloats >= 27 * 33, "the reduction rows overlay the ring");
+template <bool TRU, int GW = 0, int GH = 0>
+__global__ void __launch_bounds__(kThreads, DPFT_STAGED_CTAS) uic_iter_staged_kernel(const UicIterParams p) {
   extern __shared__ __align__(16) float dyn_stage[];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int b = blockIdx.y;
-  const int plane = p.H * p.W;
+  const int plane = (GW > 0) ? GW * GH : p.H * p.W;
   const int wt = blockIdx.x * kWarps + warp;
   const bool warp_on = wt < p.nseg * p.nrt;
   const int seg = warp_on ? wt % p.nseg : 0;
@@ -356,7 +359,8 @@ __global__ void __launch_bounds__(kThreads, DPFT_ASYNC_CTAS) uic_iter_async_kern
   g.fx = __ldg(p.K + 4 * b); g.fy = __ldg(p.K + 4 * b + 1); g.cx = __ldg(p.K + 4 * b + 2); g.cy = __ldg(p.K + 4 * b + 3);
   g.s0lo = g.s0hi = 0.f;
 
-  __shared__ float red[kWarps][NSUM][33];
+  float* area = dyn_stage + warp * kStageAreaFloats;
+  float (*redw)[33] = reinterpret_cast<float (*)[33]>(area + kStageWarpFloats - 27 * 33);   // rows 27.. start at the ring's end
   __shared__ __align__(16) float s_pose[12];
   cudaTriggerProgrammaticLaunchCompletion();
   cudaGridDependencySynchronize();
@@ -366,14 +370,14 @@ __global__ void __launch_bounds__(kThreads, DPFT_ASYNC_CTAS) uic_iter_async_kern
     g.s0lo = ord2f(__ldcg(mm));
     g.s0hi = ord2f(__ldcg(mm + 1));
 #pragma unroll
-    for (int i = 0; i < 12; ++i) red[warp][27 + i][lane] = 0.f;
+    for (int i = 0; i < 12; ++i) redw[27 + i][lane] = 0.f;
   }
   __syncthreads();
   TileSums S;
   S.reset();
-  if (y1 > y0)
-    process_tile_async<TRU>(g, s_pose, &red[warp][27], dyn_stage + warp * kAsyncWarpFloats, seg, y0, y1, lane, S);
-  reduce_and_finish<TRU>(p, b, red, S.acc, S.vmin, S.vmax);
+  if (y1 > y0) process_tile_staged<TRU, GW, GH>(g, s_pose, redw + 27, area, seg, y0, y1, lane, S);
+  __syncwarp();
+  reduce_and_finish<TRU>(p, b, redw, S.acc, S.vmin, S.vmax);
 }
 
 // =========================================================================== materialised-gradient path
@@ -543,7 +547,7 @@ __global__ void __launch_bounds__(kThreads, 4) uic_iter_px_kernel(const UicIterP
       red[warp][33 + i][lane] = cmx[i];
     }
   }
-  reduce_and_finish<TRU>(p, b, red, acc, vmin, vmax);
+  reduce_and_finish<TRU>(p, b, red[threadIdx.x >> 5], acc, vmin, vmax);
 }
 
 // --------------------------------------------------------------------------- small helper kernels
@@ -643,6 +647,12 @@ static int pick_tile_rows(int H, int nseg, int B, int ctas_per_sm) {
   return best_tr;
 }
 
+// can this level run the staged-footprint kernel?  (16-byte cp.async rows, one 8-channel pass)
+static bool staged_ok(const dpft_level_t& L, int C) {
+  auto al = [](const void* q) { return ((uintptr_t)q & 15u) == 0; };
+  return C == 8 && L.W % 4 == 0 && L.W >= 2 * kTileCols && L.H >= kStageRows && al(L.x1) && al(L.sigma1) && al(L.invd1);
+}
+
 static Plan make_plan(const dpft_level_t* lv, int n_levels, int B, int C, uint32_t flags, bool any_occ,
                       int p_grid) {
   Plan pl{};
@@ -650,7 +660,7 @@ static Plan make_plan(const dpft_level_t* lv, int n_levels, int B, int C, uint32
   pl.max_plane = 0;
   for (int l = 0; l < n_levels; ++l) {
     pl.nseg[l] = (lv[l].W + kCols - 1) / kCols;
-    pl.TR[l] = pick_tile_rows(lv[l].H, pl.nseg[l], B, ((flags & DPFT_ASYNC_GATHER) && C % 8 == 0) ? DPFT_ASYNC_CTAS : DPFT_MIN_CTAS);
+    pl.TR[l] = pick_tile_rows(lv[l].H, pl.nseg[l], B, ((flags & DPFT_STAGED_FOOTPRINT) && staged_ok(lv[l], C)) ? DPFT_STAGED_CTAS : DPFT_MIN_CTAS);
     pl.nrt[l] = (lv[l].H + pl.TR[l] - 1) / pl.TR[l];
     pl.ctas[l] = (pl.nseg[l] * pl.nrt[l] + kWarps - 1) / kWarps;
     if (pl.ctas[l] > pl.max_ctas) pl.max_ctas = pl.ctas[l];
@@ -736,18 +746,22 @@ static cudaError_t launch_iter(const UicIterParams& prm, dim3 grid, bool tru, bo
   attr[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
   cfg.numAttrs = pdl ? 1 : 0;
+  // the reference's pyramid sizes (TUM 160x120 ... and 640x480 ...) run geometry-specialised instantiations
+  if (CH == 8 && !getenv("DPFT_GENERIC_GEOMETRY")) {
+#define DPFT_FIXED(w, h)                                                                     \
+    if (prm.W == w && prm.H == h)                                                            \
+      return tru ? cudaLaunchKernelEx(&cfg, uic_iter_kernel<8, true, w, h>, prm)             \
+                 : cudaLaunchKernelEx(&cfg, uic_iter_kernel<8, false, w, h>, prm);
+    DPFT_FIXED(160, 120)
+    DPFT_FIXED(80, 60)
+#undef DPFT_FIXED
+  }
   if (tru) return cudaLaunchKernelEx(&cfg, uic_iter_kernel<CH, true>, prm);
   return cudaLaunchKernelEx(&cfg, uic_iter_kernel<CH, false>, prm);
 }
 
-static cudaError_t launch_async(const UicIterParams& prm, dim3 grid, bool tru, bool pdl, cudaStream_t stream) {
-  constexpr int smem = kWarps * kAsyncWarpFloats * (int)sizeof(float);
-  static bool configured = false;
-  if (!configured) {
-    cudaFuncSetAttribute(uic_iter_async_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-    cudaFuncSetAttribute(uic_iter_async_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-    configured = true;
-  }
+static cudaError_t launch_staged(const UicIterParams& prm, dim3 grid, bool tru, bool pdl, cudaStream_t stream) {
+  constexpr int smem = kWarps * kStageAreaFloats * (int)sizeof(float);
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = grid;
   cfg.blockDim = dim3(kThreads);
@@ -758,8 +772,20 @@ static cudaError_t launch_async(const UicIterParams& prm, dim3 grid, bool tru, b
   attr[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
   cfg.numAttrs = pdl ? 1 : 0;
-  if (tru) return cudaLaunchKernelEx(&cfg, uic_iter_async_kernel<true>, prm);
-  return cudaLaunchKernelEx(&cfg, uic_iter_async_kernel<false>, prm);
+  // (cudaFuncSetAttribute is per device and cheap: set it on every launch rather than caching per process)
+#define DPFT_STAGED(TRUV, w, h)                                                                              \
+  do {                                                                                                       \
+    auto* fn = uic_iter_staged_kernel<TRUV, w, h>;                                                           \
+    cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);                             \
+    return cudaLaunchKernelEx(&cfg, fn, prm);                                                                \
+  } while (0)
+  if (!getenv("DPFT_GENERIC_GEOMETRY")) {
+    if (prm.W == 160 && prm.H == 120) { if (tru) DPFT_STAGED(true, 160, 120); else DPFT_STAGED(false, 160, 120); }
+    if (prm.W == 80 && prm.H == 60) { if (tru) DPFT_STAGED(true, 80, 60); else DPFT_STAGED(false, 80, 60); }
+  }
+  if (tru) DPFT_STAGED(true, 0, 0);
+  DPFT_STAGED(false, 0, 0);
+#undef DPFT_STAGED
 }
 
 template <int CH>
@@ -942,8 +968,8 @@ static int run_uic(const dpft_level_t* levels, int n_levels, int B, int C, int i
           case 2: err = launch_px<2>(prm, ex, grid, tru, use_pdl, stream); break;
           default: err = launch_px<1>(prm, ex, grid, tru, use_pdl, stream); break;
         }
-      } else if ((flags & DPFT_ASYNC_GATHER) && C % 8 == 0) {
-        err = launch_async(prm, grid, tru, use_pdl, stream);
+      } else if ((flags & DPFT_STAGED_FOOTPRINT) && staged_ok(L, C)) {
+        err = launch_staged(prm, grid, tru, use_pdl, stream);
       } else
       switch (CH) {
         case 8: err = launch_iter<8>(prm, grid, tru, use_pdl, stream); break;

@@ -68,11 +68,17 @@ __device__ __forceinline__ float4 lds_v4(const float* p) {
 // `spose`: this warp's pose in SHARED memory, 12 floats R|t, 16-byte aligned.
 // `scorr`: this warp's [12][33] shared scratch for the sigma-extreme corrections (remove_tru_sigma), zeroed by
 //          the caller; row i < 6 belongs to the minimum, row 6 + i to the maximum, one column per lane.
-template <int CH, bool TRU>
+//
+// GW, GH > 0: the level's width and height are compile-time constants (the reference's pyramid sizes get their
+// own instantiations).  Every channel plane and footprint tap is then an immediate offset from ONE address
+// register per map and row, instead of a 64-bit multiply-add per load; GW = GH = 0 is the generic routine.
+template <int CH, bool TRU, int GW = 0, int GH = 0>
 __device__ __forceinline__ void process_tile(const PairView& g, const float* spose, float (*scorr)[33],
                                              const int seg, const int y0, const int y1, const int lane,
                                              TileSums& S) {
-  const int H = g.H, W = g.W, C = g.C;
+  constexpr bool FIXED = GW > 0 && GH > 0;
+  constexpr int PLANE = GW * GH;
+  const int H = FIXED ? GH : g.H, W = FIXED ? GW : g.W, C = g.C;
   const unsigned iplane = (unsigned)(H * W), Wu = (unsigned)W;
   const int x = seg * kTileCols - 1 + lane;
   const int xc = min(max(x, 0), W - 1);
@@ -84,30 +90,51 @@ __device__ __forceinline__ void process_tile(const PairView& g, const float* spo
   const float rcp_hw = __frcp_rn(0.5f * (float)(W - 1)), rcp_hh = __frcp_rn(0.5f * (float)(H - 1));
 
   for (int c0 = 0; c0 < C; c0 += CH) {
-    const float* X0 = opaque(g.x0 + (size_t)c0 * iplane);
-    const float* S0 = opaque(g.s0 + (size_t)c0 * iplane);
-    const float* X1 = opaque(g.x1 + (size_t)c0 * iplane);
-    const float* S1 = opaque(g.s1 + (size_t)c0 * iplane);
+    const float* X0 = g.x0 + (size_t)c0 * iplane;
+    const float* S0 = g.s0 + (size_t)c0 * iplane;
+    const float* X1 = g.x1 + (size_t)c0 * iplane;
+    const float* S1 = g.s1 + (size_t)c0 * iplane;
+    if (!FIXED) { X0 = opaque(X0); S0 = opaque(S0); X1 = opaque(X1); S1 = opaque(S1); }
 
     // 3-row sliding windows of the keyframe maps (own column): top / mid / (bot loaded per row)
     float ft[CH], fm[CH], st[CH], sm[CH];
     {
       const unsigned ot = (unsigned)(max(y0 - 1, 0) * W + xc), om = (unsigned)(min(y0, H - 1) * W + xc);
+      if (FIXED) {
+        const float *xt = X0 + ot, *xm = X0 + om, *zt = S0 + ot, *zm = S0 + om;
 #pragma unroll
-      for (int c = 0; c < CH; ++c) {
-        ft[c] = ldf(X0, ot + c * iplane);
-        fm[c] = ldf(X0, om + c * iplane);
-        st[c] = ldf(S0, ot + c * iplane);
-        sm[c] = ldf(S0, om + c * iplane);
+        for (int c = 0; c < CH; ++c) {
+          ft[c] = __ldg(xt + c * PLANE);
+          fm[c] = __ldg(xm + c * PLANE);
+          st[c] = __ldg(zt + c * PLANE);
+          sm[c] = __ldg(zm + c * PLANE);
+        }
+      } else {
+#pragma unroll
+        for (int c = 0; c < CH; ++c) {
+          ft[c] = ldf(X0, ot + c * iplane);
+          fm[c] = ldf(X0, om + c * iplane);
+          st[c] = ldf(S0, ot + c * iplane);
+          sm[c] = ldf(S0, om + c * iplane);
+        }
       }
     }
     for (int y = y0; y < y1; ++y) {
       const unsigned ob = (unsigned)(min(y + 1, H - 1) * W + xc);
       float fb[CH], sb[CH];
+      if (FIXED) {
+        const float *xr = X0 + ob, *zr = S0 + ob;
 #pragma unroll
-      for (int c = 0; c < CH; ++c) {
-        fb[c] = ldf(X0, ob + c * iplane);
-        sb[c] = ldf(S0, ob + c * iplane);
+        for (int c = 0; c < CH; ++c) {
+          fb[c] = __ldg(xr + c * PLANE);
+          sb[c] = __ldg(zr + c * PLANE);
+        }
+      } else {
+#pragma unroll
+        for (int c = 0; c < CH; ++c) {
+          fb[c] = ldf(X0, ob + c * iplane);
+          sb[c] = ldf(S0, ob + c * iplane);
+        }
       }
       const unsigned o = (unsigned)(y * W + xc);
       const float d0 = __ldg(g.d0 + o);
@@ -144,11 +171,21 @@ __device__ __forceinline__ void process_tile(const PairView& g, const float* spo
 #pragma unroll
       for (int g0 = 0; g0 < CH; g0 += G) {
         float xa[G], xb[G], xc_[G], xd[G], za[G], zb[G], zc[G], zd[G];
+        if (FIXED) {
+          const float *xq = X1 + tap.o, *zq = S1 + tap.o;
 #pragma unroll
-        for (int c = 0; c < G; ++c) {
-          const unsigned ia = (unsigned)tap.o + (unsigned)(g0 + c) * iplane, ic = ia + Wu;
-          ldf2(X1, ia, xa[c], xb[c]); ldf2(X1, ic, xc_[c], xd[c]);
-          ldf2(S1, ia, za[c], zb[c]); ldf2(S1, ic, zc[c], zd[c]);
+          for (int c = 0; c < G; ++c) {
+            const int k = (g0 + c) * PLANE;
+            xa[c] = __ldg(xq + k); xb[c] = __ldg(xq + k + 1); xc_[c] = __ldg(xq + k + GW); xd[c] = __ldg(xq + k + GW + 1);
+            za[c] = __ldg(zq + k); zb[c] = __ldg(zq + k + 1); zc[c] = __ldg(zq + k + GW); zd[c] = __ldg(zq + k + GW + 1);
+          }
+        } else {
+#pragma unroll
+          for (int c = 0; c < G; ++c) {
+            const unsigned ia = (unsigned)tap.o + (unsigned)(g0 + c) * iplane, ic = ia + Wu;
+            ldf2(X1, ia, xa[c], xb[c]); ldf2(X1, ic, xc_[c], xd[c]);
+            ldf2(S1, ia, za[c], zb[c]); ldf2(S1, ic, zc[c], zd[c]);
+          }
         }
 #ifdef DPFT_PREFETCH
 #pragma unroll

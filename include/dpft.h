@@ -48,8 +48,9 @@ extern "C" {
 #define DPFT_LAUNCH_PER_ITERATION 0x10u /* one launch per Gauss-Newton iteration instead of the single
                                           cooperative launch (the ICP term, occ_out and the materialised
                                           gradients always use it)                                           */
-#define DPFT_ASYNC_GATHER     0x20u /* fused kernel with the lookups issued by cp.async one tile row ahead
-                                       (C % 8 == 0; launch-per-iteration path)                                 */
+#define DPFT_STAGED_FOOTPRINT 0x20u /* launch-per-iteration path: levels with C == 8, W % 4 == 0, W >= 60 and 16-byte
+                                       aligned x1 / sigma1 / invd1 run the kernel that stages the lookup footprint
+                                       in shared memory (cp.async rows); other levels are unaffected              */
 #define DPFT_SHARED_KEYFRAME  0x40u /* x0, sigma0, invd0 (and obj_mask0) have batch size 1: every pair of the
                                        batch tracks against the same keyframe (kf_vo.py keyframe mode); forward only */
 #define DPFT_PAIRWISE_EXTREMES 0x80u /* with DPFT_REMOVE_TRU_SIGMA: sigma extremes per pair, i.e. the semantics of

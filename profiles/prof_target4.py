@@ -1,4 +1,4 @@
-"""ncu target: two solves with the cp.async-pipelined kernel, one launch per iteration."""
+"""ncu target: two solves with the staged-footprint kernel, one launch per iteration."""
 import os
 import sys
 
@@ -12,7 +12,7 @@ data = make_frame_pairs(64, 8, 120, 160, seed=1234, n_levels=4)
 lv = levels_to(data["levels"], "cuda:0")
 pose = (data["R0"].cuda(), data["t0"].cuda())
 for _ in range(2):
-    res = A.uic_solve(lv, pose, iters=3, remove_tru_sigma=True, async_gather=True)
+    res = A.uic_solve(lv, pose, iters=3, remove_tru_sigma=True, staged_footprint=True)
 torch.cuda.synchronize()
 res.raise_if_bad()
 print("ok")

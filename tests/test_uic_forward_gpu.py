@@ -15,18 +15,19 @@ pytestmark = pytest.mark.gpu
 DEV = "cuda:0"
 FUSED = True
 SINGLE = True
-ASYNC = False
+STAGED = False
 
 
 @pytest.fixture(autouse=True, params=[(True, True, False), (True, False, False), (False, False, False), (True, False, True)],
-                ids=["single-launch", "launch-per-iteration", "materialised-gradients", "async-gather"])
+                ids=["single-launch", "launch-per-iteration", "materialised-gradients", "staged-footprint"])
 def forward_path(request, monkeypatch):
-    """Every test runs on the three forward paths: the single cooperative launch (default), the same fused
-    kernel launched once per iteration, and the variant with gradients materialised once per level."""
+    """Every test runs on the four forward paths: the single cooperative launch, the same fused kernel
+    launched once per iteration, the variant with gradients materialised once per level, and the fused kernel
+    with the lookup footprint staged in shared memory (levels that qualify: C == 8, W % 4 == 0, W >= 48)."""
     import sys
     monkeypatch.setattr(sys.modules[__name__], "FUSED", request.param[0])
     monkeypatch.setattr(sys.modules[__name__], "SINGLE", request.param[1])
-    monkeypatch.setattr(sys.modules[__name__], "ASYNC", request.param[2])
+    monkeypatch.setattr(sys.modules[__name__], "STAGED", request.param[2])
 
 
 def perturbed(B, seed, scale=0.01):
@@ -38,7 +39,7 @@ def perturbed(B, seed, scale=0.01):
 def run_cuda(levels, pose, **kw):
     kw.setdefault("fused_sobel", FUSED)
     kw.setdefault("single_launch", SINGLE)
-    kw.setdefault("async_gather", ASYNC)
+    kw.setdefault("staged_footprint", STAGED)
     res = A.uic_solve(levels_to(levels, DEV), (pose[0].to(DEV), pose[1].to(DEV)), want_occ=True, **kw)
     torch.cuda.synchronize()
     return res
@@ -164,6 +165,25 @@ def test_masks_bit_exact_over_many_poses():
         assert torch.equal(res.occ[0][0].cpu(), trace[0]["occ"][:, 0].to(torch.uint8)), scale
 
 
+@pytest.mark.parametrize("scale", [0.005, 0.05, 0.15, 0.4])
+def test_eight_channel_level_under_small_and_large_motion(scale):
+    """C = 8, W % 4 == 0: the shape the staged-footprint kernel takes.  Large motions spread the lookups of a
+    warp row over more source rows / columns than its shared-memory ring holds and push them against the image
+    border, so the per-lane direct loads and the ring restarts are exercised; results must not depend on it."""
+    B, C, H, W = 4, 8, 44, 64
+    data = make_frame_pairs(B, C, H, W, seed=31, n_levels=1)
+    lv = data["levels"][0]
+    pose = perturbed(B, 11, scale)
+    res = run_cuda([lv], pose, iters=2, remove_tru_sigma=True)
+    trace = []
+    O.uic_level(pose, lv["x0"], lv["x1"], lv["invD0"], lv["invD1"], lv["K"], lv["s0"], lv["s1"], iters=2,
+                remove_tru_sigma=True, trace=trace)
+    assert torch.equal(res.occ[0][0].cpu(), trace[0]["occ"][:, 0].to(torch.uint8))
+    for it in range(2):
+        Ac, bc = A.unpack_system(res.sys_hist[it].cpu())
+        assert frob_rel(Ac, trace[it]["A"]) < TOL_SYS and frob_rel(bc, trace[it]["b"]) < TOL_SYS, (scale, it)
+
+
 def test_saturated_sigma_masks():
     """sigma clamped like the reference's laplacian head (exp(clamp(.,-3,3))): whole regions sit on the
     batch extremes and must be masked exactly as the oracle masks them."""
@@ -188,8 +208,8 @@ def test_full_size_batch_properties():
     data = make_frame_pairs(B, C, H, W, seed=1234, n_levels=4)
     levels = levels_to(data["levels"], DEV)
     pose = (data["R0"].to(DEV), data["t0"].to(DEV))
-    r1 = A.uic_solve(levels, pose, iters=3, remove_tru_sigma=True, fused_sobel=FUSED, single_launch=SINGLE, async_gather=ASYNC)
-    r2 = A.uic_solve(levels, pose, iters=3, remove_tru_sigma=True, fused_sobel=FUSED, single_launch=SINGLE, async_gather=ASYNC)
+    r1 = A.uic_solve(levels, pose, iters=3, remove_tru_sigma=True, fused_sobel=FUSED, single_launch=SINGLE, staged_footprint=STAGED)
+    r2 = A.uic_solve(levels, pose, iters=3, remove_tru_sigma=True, fused_sobel=FUSED, single_launch=SINGLE, staged_footprint=STAGED)
     torch.cuda.synchronize()
     assert int(r1.status.item()) == 0
     assert torch.equal(r1.pose_hist, r2.pose_hist) and torch.equal(r1.sys_hist, r2.sys_hist)
@@ -200,20 +220,20 @@ def test_full_size_batch_properties():
     # permuting the batch permutes the result (bitwise)
     perm = torch.randperm(B, generator=torch.Generator().manual_seed(0)).to(DEV)
     lv_p = [{k: v[perm].contiguous() for k, v in lv.items()} for lv in levels]
-    r3 = A.uic_solve(lv_p, (pose[0][perm], pose[1][perm]), iters=3, remove_tru_sigma=True, fused_sobel=FUSED, single_launch=SINGLE, async_gather=ASYNC)
+    r3 = A.uic_solve(lv_p, (pose[0][perm], pose[1][perm]), iters=3, remove_tru_sigma=True, fused_sobel=FUSED, single_launch=SINGLE, staged_footprint=STAGED)
     assert torch.equal(r3.pose_hist, r1.pose_hist[:, perm])
     # no batch coupling without remove_tru_sigma: swapping the batch-mates of the first five pairs for
     # other data leaves their rows bitwise unchanged, and a smaller batch (different tiling, so a
     # different summation order) agrees to rounding
-    r4 = A.uic_solve(levels, pose, iters=3, remove_tru_sigma=False, fused_sobel=FUSED, single_launch=SINGLE, async_gather=ASYNC)
+    r4 = A.uic_solve(levels, pose, iters=3, remove_tru_sigma=False, fused_sobel=FUSED, single_launch=SINGLE, staged_footprint=STAGED)
     mixed = [{k: torch.cat((v[:5], v[5:].flip(0))).contiguous() for k, v in lv.items()} for lv in levels]
-    r5 = A.uic_solve(mixed, pose, iters=3, remove_tru_sigma=False, fused_sobel=FUSED, single_launch=SINGLE, async_gather=ASYNC)
+    r5 = A.uic_solve(mixed, pose, iters=3, remove_tru_sigma=False, fused_sobel=FUSED, single_launch=SINGLE, staged_footprint=STAGED)
     assert torch.equal(r5.pose_hist[:, :5], r4.pose_hist[:, :5])
     sub = [{k: v[:5].contiguous() for k, v in lv.items()} for lv in levels]
-    r7 = A.uic_solve(sub, (pose[0][:5], pose[1][:5]), iters=3, remove_tru_sigma=False, fused_sobel=FUSED, single_launch=SINGLE, async_gather=ASYNC)
+    r7 = A.uic_solve(sub, (pose[0][:5], pose[1][:5]), iters=3, remove_tru_sigma=False, fused_sobel=FUSED, single_launch=SINGLE, staged_footprint=STAGED)
     assert (r7.pose_hist - r4.pose_hist[:, :5]).abs().max() < 1e-6
     # PDL on/off is only a scheduling difference
-    r6 = A.uic_solve(levels, pose, iters=3, remove_tru_sigma=True, pdl=False, fused_sobel=FUSED, single_launch=SINGLE, async_gather=ASYNC)
+    r6 = A.uic_solve(levels, pose, iters=3, remove_tru_sigma=True, pdl=False, fused_sobel=FUSED, single_launch=SINGLE, staged_footprint=STAGED)
     assert torch.equal(r6.pose_hist, r1.pose_hist)
 
 
@@ -221,7 +241,7 @@ def test_full_size_vs_oracle():
     """The whole B=64 120x160 4-level solve against the oracle (a few seconds of CPU)."""
     B, C, H, W = 64, 8, 120, 160
     data = make_frame_pairs(B, C, H, W, seed=4321, n_levels=4)
-    res = run_cuda(data["levels"], (data["R0"], data["t0"]), iters=3, remove_tru_sigma=True, fused_sobel=FUSED, single_launch=SINGLE, async_gather=ASYNC)
+    res = run_cuda(data["levels"], (data["R0"], data["t0"]), iters=3, remove_tru_sigma=True, fused_sobel=FUSED, single_launch=SINGLE, staged_footprint=STAGED)
     trace = []
     with torch.no_grad():
         pose, per_level = O.track_pyramid(data["levels"], (data["R0"], data["t0"]), iters=3,
