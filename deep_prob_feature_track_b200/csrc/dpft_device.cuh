@@ -210,7 +210,9 @@ __device__ __forceinline__ void accumulate_system(float acc[27], const float ju[
 __device__ inline bool solve_and_update(const double A[21], const double rhs[6], bool damp_trace,
                                         const float* __restrict__ pose_in, float* __restrict__ pose_out,
                                         double xi_out[6]) {
-  double L[6][6];
+  // Cholesky with the reciprocal pivots kept (one rsqrt per column, no division, no sqrt: the solve sits on the
+  // serial tail of every launch and fp64 sqrt / div are long dependent sequences)
+  double L[6][6], invd[6];
   double tr = 0.0;
 #pragma unroll
   for (int i = 0; i < 6; ++i) tr += A[tri(i, i)];
@@ -222,9 +224,8 @@ __device__ inline bool solve_and_update(const double A[21], const double rhs[6],
 #pragma unroll
     for (int k = 0; k < j; ++k) s -= L[j][k] * L[j][k];
     ok = ok && (s > 0.0);
-    const double d = sqrt(s);
-    L[j][j] = d;
-    const double inv = 1.0 / d;
+    const double inv = rsqrt(s);
+    invd[j] = inv;
 #pragma unroll
     for (int i = j + 1; i < 6; ++i) {
       double v = A[tri(j, i)];
@@ -239,22 +240,25 @@ __device__ inline bool solve_and_update(const double A[21], const double rhs[6],
     double v = rhs[i];
 #pragma unroll
     for (int k = 0; k < i; ++k) v -= L[i][k] * z[k];
-    z[i] = v / L[i][i];
+    z[i] = v * invd[i];
   }
 #pragma unroll
   for (int i = 5; i >= 0; --i) {
     double v = z[i];
 #pragma unroll
     for (int k = i + 1; k < 6; ++k) v -= L[k][i] * xi[k];
-    xi[i] = v / L[i][i];
+    xi[i] = v * invd[i];
   }
 #pragma unroll
   for (int i = 0; i < 6; ++i) xi_out[i] = xi[i];
 
   const double wx = -xi[0], wy = -xi[1], wz = -xi[2];
   const double th = sqrt(wx * wx + wy * wy + wz * wz);
-  const double kx = wx / th, ky = wy / th, kz = wz / th;   // NaN at th == 0, as in the reference
-  const double s = sin(th), c1 = 1.0 - cos(th);
+  const double ith = 1.0 / th;
+  const double kx = wx * ith, ky = wy * ith, kz = wz * ith;   // NaN at th == 0, as in the reference
+  double s, c;
+  sincos(th, &s, &c);
+  const double c1 = 1.0 - c;
   const double Kx[9] = {0, -kz, ky, kz, 0, -kx, -ky, kx, 0};
   double dR[9];
 #pragma unroll

@@ -115,6 +115,20 @@ __device__ void finalize_pair(const UicIterParams& p, int b, float gmin, float g
 // (fp64 once lanes are combined), one partial record per CTA, the last CTA of a pair folds its records in
 // a fixed order (deterministic), and the last CTA of the grid (or of the pair, when nothing couples the
 // pairs) damps, solves and updates the poses.
+// Optional in-kernel timeline (compile with -DDPFT_DEBUG_STAMPS): %globaltimer at a few points of the LAST launch,
+// read back with dpft_debug_read_stamps.  Not part of the ABI; absent from normal builds.
+#ifdef DPFT_DEBUG_STAMPS
+__device__ unsigned long long g_stamps[16];
+__device__ __forceinline__ void stamp(int i) {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  g_stamps[i] = t;
+}
+#define DPFT_STAMP(i, cond) do { if (cond) stamp(i); } while (0)
+#else
+#define DPFT_STAMP(i, cond) do { } while (0)
+#endif
+
 template <bool TRU>
 __device__ __forceinline__ void reduce_and_finish(const UicIterParams& p, const int b, float (*redw)[33] /* this warp's [NSUM][33] */,
                                                   const float (&acc)[27], const float vmin, const float vmax) {
@@ -152,6 +166,7 @@ __device__ __forceinline__ void reduce_and_finish(const UicIterParams& p, const 
   }
   __syncthreads();
 
+  DPFT_STAMP(3, threadIdx.x == 0 && blockIdx.x == 0 && b == 0);   // CTA reduction done
   float* part = p.partials + ((size_t)b * p.ctas_per_pair + blockIdx.x) * PS;
   float cta_min = CUDART_INF_F, cta_max = -CUDART_INF_F;
   if (TRU) {
@@ -185,6 +200,7 @@ __device__ __forceinline__ void reduce_and_finish(const UicIterParams& p, const 
   __syncthreads();
   if (!s_flag) return;
   __threadfence();
+  DPFT_STAMP(4, threadIdx.x == 0 && b == 0);                      // last CTA of pair 0 starts the pair reduction
 
   const float* pp = p.partials + (size_t)b * p.ctas_per_pair * PS;
   const int n = p.ctas_per_pair;
@@ -213,13 +229,22 @@ __device__ __forceinline__ void reduce_and_finish(const UicIterParams& p, const 
   if (threadIdx.x < NE) {
     const int e = threadIdx.x;
     const int slot = e < 27 ? e : e + 2;
+    // eight records in flight at a time (the loads are L2 round trips), summed in record order
+    const bool corr = TRU && e >= 27;
+    const int key_at = e < 33 ? E_VMIN : E_VMAX;
+    const float key_want = e < 33 ? pair_min : pair_max;
     double s = 0.0;
-    for (int i = 0; i < n; ++i) {
-      const float* q = pp + (size_t)i * PS;
-      bool take = true;
-      if (TRU && e >= 27 && e < 33) take = (__ldcg(q + E_VMIN) == pair_min);
-      if (TRU && e >= 33) take = (__ldcg(q + E_VMAX) == pair_max);
-      if (take) s += (double)__ldcg(q + slot);
+    for (int i0 = 0; i0 < n; i0 += 8) {
+      float v[8], key[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float* q = pp + (size_t)min(i0 + j, n - 1) * PS;
+        v[j] = __ldcg(q + slot);
+        key[j] = corr ? __ldcg(q + key_at) : 0.f;
+      }
+#pragma unroll
+      for (int j = 0; j < 8; ++j)
+        if (i0 + j < n && (!corr || key[j] == key_want)) s += (double)v[j];
     }
     rec[slot] = s;
   }
@@ -242,6 +267,7 @@ __device__ __forceinline__ void reduce_and_finish(const UicIterParams& p, const 
   }
 
   // ---------------------------------------------------------------- last CTA of the grid: batch extremes + all solves
+  DPFT_STAMP(5, threadIdx.x == 0 && b == 0);                      // pair 0 reduced
   if (threadIdx.x == 0) s_flag = (atomicAdd(p.counters + p.B, 1) == p.B - 1);
   __syncthreads();
   if (!s_flag) return;
@@ -276,7 +302,9 @@ __device__ __forceinline__ void reduce_and_finish(const UicIterParams& p, const 
     }
     __syncthreads();
   }
+  DPFT_STAMP(6, threadIdx.x == 0);                                // grid-last CTA: extremes known
   for (int i = threadIdx.x; i < p.B; i += kThreads) finalize_pair<true>(p, i, s_pair_mm[0], s_pair_mm[1]);
+  DPFT_STAMP(7, threadIdx.x == 0);                                // all solves written
 }
 
 template <int CH, bool TRU, int GW = 0, int GH = 0>
@@ -362,8 +390,10 @@ __global__ void __launch_bounds__(kThreads, DPFT_STAGED_CTAS) uic_iter_staged_ke
   float* area = dyn_stage + warp * kStageAreaFloats;
   float (*redw)[33] = reinterpret_cast<float (*)[33]>(area + kStageWarpFloats - 27 * 33);   // rows 27.. start at the ring's end
   __shared__ __align__(16) float s_pose[12];
+  DPFT_STAMP(0, threadIdx.x == 0 && blockIdx.x == 0 && b == 0);   // CTA resident
   cudaTriggerProgrammaticLaunchCompletion();
   cudaGridDependencySynchronize();
+  DPFT_STAMP(1, threadIdx.x == 0 && blockIdx.x == 0 && b == 0);   // previous launch complete
   if (threadIdx.x < 12) s_pose[threadIdx.x] = __ldcg(p.pose + (size_t)b * 12 + threadIdx.x);
   if (TRU) {
     const uint32_t* mm = p.s0mm + ((p.pairwise && !p.kf_shared) ? 2 * b : 0);
@@ -377,6 +407,7 @@ __global__ void __launch_bounds__(kThreads, DPFT_STAGED_CTAS) uic_iter_staged_ke
   S.reset();
   if (y1 > y0) process_tile_staged<TRU, GW, GH>(g, s_pose, redw + 27, area, seg, y0, y1, lane, S);
   __syncwarp();
+  DPFT_STAMP(2, threadIdx.x == 0 && blockIdx.x == 0 && b == 0);   // tile walked
   reduce_and_finish<TRU>(p, b, redw, S.acc, S.vmin, S.vmax);
 }
 
@@ -1027,3 +1058,9 @@ extern "C" int dpft_uic_forward_timed(const dpft_level_t* levels, int n_levels, 
   for (int i = 0; i <= n; ++i) cudaEventDestroy(ev[i]);
   return rc;
 }
+
+#ifdef DPFT_DEBUG_STAMPS
+extern "C" int dpft_debug_read_stamps(unsigned long long* host16) {
+  return (int)cudaMemcpyFromSymbol(host16, dpft::g_stamps, sizeof(unsigned long long) * 16);
+}
+#endif

@@ -77,7 +77,7 @@ __device__ __forceinline__ void process_tile_staged(const PairView& g, const flo
   constexpr int CH = 8;
   constexpr bool FIXED = GW > 0 && GH > 0;
   constexpr int PLANE = GW * GH;
-  constexpr int SW = kStageWidth, NM = kStageMaps, CPR = SW / 4;   // 16-byte chunks per staged map row
+  constexpr int SW = kStageWidth, CPR = SW / 4;   // 16-byte chunks per staged map row
   const int H = FIXED ? GH : g.H, W = FIXED ? GW : g.W;
   const unsigned iplane = (unsigned)(H * W), Wu = (unsigned)W;
   const int x = seg * kTileCols - 1 + lane;
@@ -96,46 +96,57 @@ __device__ __forceinline__ void process_tile_staged(const PairView& g, const flo
   const float* S1 = g.s1;
   if (!FIXED) { X0 = opaque(X0); S0 = opaque(S0); X1 = opaque(X1); S1 = opaque(S1); }
 
-  // one source row of all 17 maps -> ring slot (row & 3), columns [xs, xs + SW)
-  auto stage_row = [&](const int row, const int xs) {
-    const unsigned slot_s = ring_s + (unsigned)((row & (kStageRows - 1)) * kStageSlotFloats) * 4u;
-    const unsigned src_off = (unsigned)(row * W + xs);
+  // one source row of all 17 maps -> ring slot (row & 3), columns [xs, xs + SW).  A map row is CPR 16-byte
+  // chunks and SW = 4 CPR, so chunk i = 11 m + ch of a tensor lands at float 4 i of the slot: the destination is
+  // 16 lane + an immediate, and the source offsets of this lane's three chunks are fixed for the whole tile.
+  static_assert(SW == 4 * CPR, "chunk i of a tensor sits at float 4 i of the slot");
+  unsigned soff[3];
 #pragma unroll
-    for (int k = 0; k < (NM * CPR + 31) / 32; ++k) {
-      const int i = lane + 32 * k;
-      if (i < NM * CPR) {
-        const int m = i / CPR, ch = i - m * CPR;
-        const float* base = (m < CH) ? X1 : (m < 2 * CH) ? S1 : g.d1;
-        const unsigned plane_off = (m < 2 * CH) ? (unsigned)(m & (CH - 1)) * iplane : 0u;
-        const float* src;
-        asm("mad.wide.u32 %0, %1, 4, %2;" : "=l"(src) : "r"(src_off + plane_off + 4u * ch), "l"(base));
-        cp_async16(slot_s + (unsigned)(m * SW + 4 * ch) * 4u, src);
+  for (int k = 0; k < 3; ++k) {
+    const int i = lane + 32 * k, m = i / CPR, ch = i - m * CPR;
+    soff[k] = (unsigned)m * iplane + 4u * (unsigned)ch;
+  }
+  auto stage_row = [&](const int row, const int xs) {
+    const unsigned dst = ring_s + (unsigned)((row & (kStageRows - 1)) * kStageSlotFloats) * 4u + 16u * (unsigned)lane;
+    const unsigned row_off = (unsigned)(row * W + xs);
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+      if (k < 2 || lane + 64 < CH * CPR) {
+        const float *sx, *sz;
+        asm("mad.wide.u32 %0, %1, 4, %2;" : "=l"(sx) : "r"(row_off + soff[k]), "l"(X1));
+        asm("mad.wide.u32 %0, %1, 4, %2;" : "=l"(sz) : "r"(row_off + soff[k]), "l"(S1));
+        cp_async16(dst + 512u * k, sx);
+        cp_async16(dst + 512u * k + 4u * (CH * SW), sz);
       }
     }
+    if (lane < CPR) cp_async16(dst + 4u * (2 * CH * SW), g.d1 + row_off + 4 * lane);
     if (lane == 0) slot_xs[row & (kStageRows - 1)] = xs;
     stage_commit();
   };
 
-  float ft[CH], fm[CH], st[CH], sm[CH];
+  // channel PAIRS travel together as float2 so the per-channel arithmetic issues as packed FFMA2 / FMUL2 / FADD2
+  constexpr int NP = CH / 2;
+  float2 ft[NP], fm[NP], st[NP], sm[NP];
+  auto load_pair = [&](const float* base, const unsigned idx, const int p) {
+    float2 r;
+    if (FIXED) {
+      const float* q = base + idx;
+      r.x = __ldg(q + (2 * p) * PLANE);
+      r.y = __ldg(q + (2 * p + 1) * PLANE);
+    } else {
+      r.x = ldf(base, idx + (2 * p) * iplane);
+      r.y = ldf(base, idx + (2 * p + 1) * iplane);
+    }
+    return r;
+  };
   {
     const unsigned ot = (unsigned)(max(y0 - 1, 0) * W + xc), om = (unsigned)(min(y0, H - 1) * W + xc);
-    if (FIXED) {
-      const float *xt = X0 + ot, *xm = X0 + om, *zt = S0 + ot, *zm = S0 + om;
 #pragma unroll
-      for (int c = 0; c < CH; ++c) {
-        ft[c] = __ldg(xt + c * PLANE);
-        fm[c] = __ldg(xm + c * PLANE);
-        st[c] = __ldg(zt + c * PLANE);
-        sm[c] = __ldg(zm + c * PLANE);
-      }
-    } else {
-#pragma unroll
-      for (int c = 0; c < CH; ++c) {
-        ft[c] = ldf(X0, ot + c * iplane);
-        fm[c] = ldf(X0, om + c * iplane);
-        st[c] = ldf(S0, ot + c * iplane);
-        sm[c] = ldf(S0, om + c * iplane);
-      }
+    for (int p = 0; p < NP; ++p) {
+      ft[p] = load_pair(X0, ot, p);
+      fm[p] = load_pair(X0, om, p);
+      st[p] = load_pair(S0, ot, p);
+      sm[p] = load_pair(S0, om, p);
     }
   }
   // the ring holds source rows max(base, top - 3) .. top; base = first row requested since the last restart
@@ -144,20 +155,11 @@ __device__ __forceinline__ void process_tile_staged(const PairView& g, const flo
 
   for (int y = y0; y < y1; ++y) {
     const unsigned ob = (unsigned)(min(y + 1, H - 1) * W + xc);
-    float fb[CH], sb[CH];
-    if (FIXED) {
-      const float *xr = X0 + ob, *zr = S0 + ob;
+    float2 fb[NP], sb[NP];
 #pragma unroll
-      for (int c = 0; c < CH; ++c) {
-        fb[c] = __ldg(xr + c * PLANE);
-        sb[c] = __ldg(zr + c * PLANE);
-      }
-    } else {
-#pragma unroll
-      for (int c = 0; c < CH; ++c) {
-        fb[c] = ldf(X0, ob + c * iplane);
-        sb[c] = ldf(S0, ob + c * iplane);
-      }
+    for (int p = 0; p < NP; ++p) {
+      fb[p] = load_pair(X0, ob, p);
+      sb[p] = load_pair(S0, ob, p);
     }
     const unsigned o = (unsigned)(y * W + xc);
     const float d0 = d0_next;
@@ -192,6 +194,7 @@ __device__ __forceinline__ void process_tile_staged(const PairView& g, const flo
       const int target = min(min(yhi + kStageLookahead, keep + kStageRows - 1), H - 1);
       const int xs = min(max((xlo - (SW - 32) / 2) & ~3, 0), W - SW);
       __syncwarp();                                                      // every lane is done with the old slots
+#pragma unroll 1
       while (top < target) stage_row(++top, xs);
       ready_top = min(yhi, top);
       stage_wait(top - ready_top);
@@ -220,83 +223,108 @@ __device__ __forceinline__ void process_tile_staged(const PairView& g, const flo
     bool occ = occluded(u, v, inv_z, d1w, H, W);
     if (g.m0) occ = occ || (__ldg(g.m0 + o) == 0);
     if (g.m1) occ = occ || !(sample_mask(g.m1, tap, W) > 0.f);
-    if (TRU) occ = occ || (sm[0] == g.s0lo) || (sm[0] == g.s0hi);
+    if (TRU) occ = occ || (sm[0].x == g.s0lo) || (sm[0].x == g.s0hi);
 
-    float saa = 0.f, sab = 0.f, sbb = 0.f, sar = 0.f, sbr = 0.f, sca = 0.f, scb = 0.f;
+    const float2 zero2 = make_float2(0.f, 0.f), two2 = make_float2(2.f, 2.f), neg1 = make_float2(-1.f, -1.f);
+    const float2 wa2 = make_float2(tap.wa, tap.wa), wb2 = make_float2(tap.wb, tap.wb);
+    const float2 wc2 = make_float2(tap.wc, tap.wc), wd2 = make_float2(tap.wd, tap.wd);
+    float2 saa2 = zero2, sab2 = zero2, sbb2 = zero2, sar2 = zero2, sbr2 = zero2, sca2 = zero2, scb2 = zero2;
     float pmin = CUDART_INF_F, pmax = -CUDART_INF_F, sr0 = 0.f;
-    constexpr int G = DPFT_GATHER_GROUP;
+    auto shfl2 = [](const float2 v, const bool down) {
+      float2 r;
+      r.x = down ? __shfl_down_sync(0xffffffffu, v.x, 1) : __shfl_up_sync(0xffffffffu, v.x, 1);
+      r.y = down ? __shfl_down_sync(0xffffffffu, v.y, 1) : __shfl_up_sync(0xffffffffu, v.y, 1);
+      return r;
+    };
+    // unit Sobel gradient of a map pair (algorithms.py:1844-1865), separable: Sx = vs(x+1) - vs(x-1),
+    // Sy = vd(x-1) + 2 vd(x) + vd(x+1), vs = t + 2 m + b, vd = b - t
+    auto unit_sobel = [&](const float2 t, const float2 m, const float2 b, float2& gx, float2& gy) {
+      const float2 vs = __ffma2_rn(m, two2, __fadd2_rn(t, b)), vd = __ffma2_rn(t, neg1, b);
+      const float2 Sx = __ffma2_rn(shfl2(vs, false), neg1, shfl2(vs, true));
+      const float2 Sy = __ffma2_rn(vd, two2, __fadd2_rn(shfl2(vd, false), shfl2(vd, true)));
+      const float2 n = __ffma2_rn(Sx, Sx, __ffma2_rn(Sy, Sy, make_float2(1e-8f, 1e-8f)));
+      const float2 inv = make_float2(rsqrt_fast(n.x), rsqrt_fast(n.y));
+      gx = __fmul2_rn(Sx, inv);
+      gy = __fmul2_rn(Sy, inv);
+    };
+    constexpr int GP = DPFT_GATHER_GROUP / 2;      // channel pairs whose lookups are in flight together
 #pragma unroll
-    for (int g0 = 0; g0 < CH; g0 += G) {
-      float xa[G], xb[G], xc_[G], xd[G], za[G], zb[G], zc[G], zd[G];
+    for (int p0 = 0; p0 < NP; p0 += GP) {
+      float2 xa[GP], xb[GP], xc_[GP], xd[GP], za[GP], zb[GP], zc[GP], zd[GP];
 #pragma unroll
-      for (int c = 0; c < G; ++c) {
-        const int kx = (g0 + c) * SW, kz = (CH + g0 + c) * SW;
-        xa[c] = a0[kx]; xb[c] = a0[kx + 1]; xc_[c] = a1[kx]; xd[c] = a1[kx + 1];
-        za[c] = a0[kz]; zb[c] = a0[kz + 1]; zc[c] = a1[kz]; zd[c] = a1[kz + 1];
+      for (int j = 0; j < GP; ++j) {
+        const int kx = 2 * (p0 + j) * SW, kz = (CH + 2 * (p0 + j)) * SW;
+        xa[j] = make_float2(a0[kx], a0[kx + SW]); xb[j] = make_float2(a0[kx + 1], a0[kx + SW + 1]);
+        xc_[j] = make_float2(a1[kx], a1[kx + SW]); xd[j] = make_float2(a1[kx + 1], a1[kx + SW + 1]);
+        za[j] = make_float2(a0[kz], a0[kz + SW]); zb[j] = make_float2(a0[kz + 1], a0[kz + SW + 1]);
+        zc[j] = make_float2(a1[kz], a1[kz + SW]); zd[j] = make_float2(a1[kz + 1], a1[kz + SW + 1]);
       }
       if (any_direct && !resident) {
 #pragma unroll
-        for (int c = 0; c < G; ++c) {
-          const unsigned ia = (unsigned)tap.o + (unsigned)(g0 + c) * iplane, ic = ia + Wu;
-          ldf2(X1, ia, xa[c], xb[c]); ldf2(X1, ic, xc_[c], xd[c]);
-          ldf2(S1, ia, za[c], zb[c]); ldf2(S1, ic, zc[c], zd[c]);
+        for (int j = 0; j < GP; ++j) {
+          const unsigned ia = (unsigned)tap.o + (unsigned)(2 * (p0 + j)) * iplane, ic = ia + Wu;
+          ldf2(X1, ia, xa[j].x, xb[j].x); ldf2(X1, ic, xc_[j].x, xd[j].x);
+          ldf2(S1, ia, za[j].x, zb[j].x); ldf2(S1, ic, zc[j].x, zd[j].x);
+          ldf2(X1, ia + iplane, xa[j].y, xb[j].y); ldf2(X1, ic + iplane, xc_[j].y, xd[j].y);
+          ldf2(S1, ia + iplane, za[j].y, zb[j].y); ldf2(S1, ic + iplane, zc[j].y, zd[j].y);
         }
       }
-      float gfx[G], gfy[G], gsx[G], gsy[G];
+      float2 gfx[GP], gfy[GP], gsx[GP], gsy[GP];
 #pragma unroll
-      for (int c = 0; c < G; ++c) {
-        const int k = g0 + c;
-#ifdef DPFT_EXPERIMENT_NO_SOBEL   // timing experiment only: wrong results
-        gfx[c] = ft[k]; gfy[c] = fb[k]; gsx[c] = st[k]; gsy[c] = sb[k];
-        continue;
-#endif
-        const float fvs = ft[k] + 2.f * fm[k] + fb[k], fvd = fb[k] - ft[k];
-        const float svs = st[k] + 2.f * sm[k] + sb[k], svd = sb[k] - st[k];
-        const float fSx = __shfl_down_sync(0xffffffffu, fvs, 1) - __shfl_up_sync(0xffffffffu, fvs, 1);
-        const float fSy = __shfl_up_sync(0xffffffffu, fvd, 1) + 2.f * fvd + __shfl_down_sync(0xffffffffu, fvd, 1);
-        const float sSx = __shfl_down_sync(0xffffffffu, svs, 1) - __shfl_up_sync(0xffffffffu, svs, 1);
-        const float sSy = __shfl_up_sync(0xffffffffu, svd, 1) + 2.f * svd + __shfl_down_sync(0xffffffffu, svd, 1);
-        const float fin = rsqrt_fast(fmaf(fSx, fSx, fmaf(fSy, fSy, 1e-8f)));
-        const float sin_ = rsqrt_fast(fmaf(sSx, sSx, fmaf(sSy, sSy, 1e-8f)));
-        gfx[c] = fSx * fin; gfy[c] = fSy * fin; gsx[c] = sSx * sin_; gsy[c] = sSy * sin_;
+      for (int j = 0; j < GP; ++j) {
+        unit_sobel(ft[p0 + j], fm[p0 + j], fb[p0 + j], gfx[j], gfy[j]);
+        unit_sobel(st[p0 + j], sm[p0 + j], sb[p0 + j], gsx[j], gsy[j]);
       }
 #pragma unroll
-      for (int c = 0; c < G; ++c) {
-        const int k = g0 + c;
-        const float fr = blend_fast(xa[c], xb[c], xc_[c], xd[c], tap);
-        const float sr = TRU ? blend_exact(za[c], zb[c], zc[c], zd[c], tap) : blend_fast(za[c], zb[c], zc[c], zd[c], tap);
-        const float res = fr - fm[k];
-        const float s0v = sm[k];
-        const float rs = rsqrt_fast(fmaf(sr, sr, s0v * s0v));
-        const float wres = res * rs;
-        const float q = wres * (s0v * (rs * rs));
-        const float a = fmaf(gfx[c], rs, q * gsx[c]);
-        const float bq = fmaf(gfy[c], rs, q * gsy[c]);
-        const float wm = occ ? 1e-6f : wres;
-        saa = fmaf(a, a, saa);
-        sab = fmaf(a, bq, sab);
-        sbb = fmaf(bq, bq, sbb);
-        sar = fmaf(a, wm, sar);
-        sbr = fmaf(bq, wm, sbr);
+      for (int j = 0; j < GP; ++j) {
+        const int p = p0 + j;
+        const float2 fr = __ffma2_rn(xd[j], wd2, __ffma2_rn(xc_[j], wc2, __ffma2_rn(xb[j], wb2, __fmul2_rn(xa[j], wa2))));
+        // sigma is compared for equality against its batch extremes -> every product and sum rounded on its own,
+        // in blend_exact's order
+        const float2 sr = TRU ? __fadd2_rn(__fadd2_rn(__fadd2_rn(__fmul2_rn(za[j], wa2), __fmul2_rn(zb[j], wb2)),
+                                                     __fmul2_rn(zc[j], wc2)), __fmul2_rn(zd[j], wd2))
+                              : __ffma2_rn(zd[j], wd2, __ffma2_rn(zc[j], wc2, __ffma2_rn(zb[j], wb2, __fmul2_rn(za[j], wa2))));
+        // residual, its uncertainty and the 2-vector d(wres)/d(u,v) (algorithms.py:1969-1972, :872)
+        const float2 res = __ffma2_rn(fm[p], neg1, fr);
+        const float2 s0v = sm[p];
+        const float2 ss = __ffma2_rn(sr, sr, __fmul2_rn(s0v, s0v));
+        const float2 rs = make_float2(rsqrt_fast(ss.x), rsqrt_fast(ss.y));       // 1 / sigma
+        const float2 wres = __fmul2_rn(res, rs);
+        const float2 q = __fmul2_rn(wres, __fmul2_rn(s0v, __fmul2_rn(rs, rs)));   // res * sigma0 / sigma^3
+        const float2 a = __ffma2_rn(gfx[j], rs, __fmul2_rn(q, gsx[j]));
+        const float2 bq = __ffma2_rn(gfy[j], rs, __fmul2_rn(q, gsy[j]));
+        const float2 wm = occ ? make_float2(1e-6f, 1e-6f) : wres;
+        saa2 = __ffma2_rn(a, a, saa2);
+        sab2 = __ffma2_rn(a, bq, sab2);
+        sbb2 = __ffma2_rn(bq, bq, sbb2);
+        sar2 = __ffma2_rn(a, wm, sar2);
+        sbr2 = __ffma2_rn(bq, wm, sbr2);
         if (TRU) {
-          const float dw = wres - 1e-6f;
-          sca = fmaf(a, dw, sca);
-          scb = fmaf(bq, dw, scb);
-          pmin = fminf(pmin, sr);
-          pmax = fmaxf(pmax, sr);
-          if (k == 0) sr0 = sr;
+          const float2 dw = __fadd2_rn(wres, make_float2(-1e-6f, -1e-6f));
+          sca2 = __ffma2_rn(a, dw, sca2);
+          scb2 = __ffma2_rn(bq, dw, scb2);
+          pmin = fminf(pmin, fminf(sr.x, sr.y));
+          pmax = fmaxf(pmax, fmaxf(sr.x, sr.y));
+          if (p == 0) sr0 = sr.x;
         }
       }
     }
+    float saa = saa2.x + saa2.y, sab = sab2.x + sab2.y, sbb = sbb2.x + sbb2.y, sar = sar2.x + sar2.y, sbr = sbr2.x + sbr2.y;
+    const float sca = sca2.x + sca2.y, scb = scb2.x + scb2.y;
     if (!col_out) { saa = sab = sbb = sar = sbr = 0.f; }
     float ju[6], jv[6];
     warp_rows(px, py, d0, fx, fy, ju, jv);
     accumulate_system(S.acc, ju, jv, saa, sab, sbb, sar, sbr);
     if (TRU) {
-      const bool lo = col_out && (pmin < S.vmin), hi = col_out && (pmax > S.vmax);
-      const float nmin = lo ? pmin : S.vmin, nmax = hi ? pmax : S.vmax;
+      // running extremes of the warped sigma over the WARP's pixels and what the pixels sitting on them added to
+      // J^T r.  A new extreme of the warp is rare after the first rows (~ log of the pixels seen), so the
+      // bookkeeping sits behind one warp-uniform branch; ties (saturated sigma maps) take it every time.
+      const float wmin = ord2f(__reduce_min_sync(0xffffffffu, f2ord(col_out ? pmin : CUDART_INF_F)));
+      const float wmax = ord2f(__reduce_max_sync(0xffffffffu, f2ord(col_out ? pmax : -CUDART_INF_F)));
+      const bool lo = wmin < S.vmin, hi = wmax > S.vmax;
+      const float nmin = lo ? wmin : S.vmin, nmax = hi ? wmax : S.vmax;
       const bool tmin = col_out && !occ && (sr0 == nmin), tmax = col_out && !occ && (sr0 == nmax);
-      if (__any_sync(0xffffffffu, lo || hi || tmin || tmax)) {
+      if (lo || hi || __any_sync(0xffffffffu, tmin || tmax)) {
         S.vmin = nmin;
         S.vmax = nmax;
 #pragma unroll
@@ -314,11 +342,11 @@ __device__ __forceinline__ void process_tile_staged(const PairView& g, const flo
       if (TRU) g.sr0_dbg[(size_t)y * W + x] = sr0;
     }
 #pragma unroll
-    for (int c = 0; c < CH; ++c) {
-      ft[c] = fm[c];
-      fm[c] = fb[c];
-      st[c] = sm[c];
-      sm[c] = sb[c];
+    for (int p = 0; p < NP; ++p) {
+      ft[p] = fm[p];
+      fm[p] = fb[p];
+      st[p] = sm[p];
+      sm[p] = sb[p];
     }
   }
   asm volatile("cp.async.wait_group 0;" ::: "memory");   // nothing of this warp may still land in the ring
