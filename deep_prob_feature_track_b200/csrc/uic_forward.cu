@@ -33,7 +33,10 @@
 
 namespace dpft {
 
-constexpr int kWarps = 4;
+#ifndef DPFT_WARPS
+#define DPFT_WARPS 4
+#endif
+constexpr int kWarps = DPFT_WARPS;   // warps per CTA of the iteration kernels
 constexpr int kThreads = kWarps * 32;
 constexpr int kCols = kTileCols;   // output columns per warp tile
 constexpr int kMaxTileRows = 40;

@@ -22,7 +22,10 @@
 namespace dpft {
 
 constexpr int kStageRows = 4;        // ring depth (power of two: slot = source row & 3)
-constexpr int kStageWidth = 44;      // texels per staged row segment (30 output columns + margin)
+#ifndef DPFT_STAGE_WIDTH
+#define DPFT_STAGE_WIDTH 44     // tuning hook; 4 * (chunks per map row)
+#endif
+constexpr int kStageWidth = DPFT_STAGE_WIDTH;      // texels per staged row segment (30 output columns + margin)
 constexpr int kStageMaps = 17;       // x1[0..7], sigma1[0..7], invd1
 constexpr int kStageLookahead = 2;   // source rows requested ahead of the row being computed
 // slot stride = 0 mod 32 banks: lanes of one warp row that sit on different source rows (same map, distinct

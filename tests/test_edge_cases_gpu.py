@@ -107,3 +107,41 @@ def test_bad_shapes_and_cpu_tensors_are_rejected():
     mod = A.TrustRegionInverseWUncertainty(combine_icp=True)
     with pytest.raises(AssertionError):
         mod(list(pose), lv["x0"], lv["x1"], lv["invD0"], lv["invD1"], lv["K"], lv["s0"], lv["s1"])   # no depth given
+
+
+def test_staged_kernel_with_depth_holes_and_out_of_view_motion():
+    """The shape the staged-footprint kernel takes (C = 8, W % 4 == 0, W >= 60) with a third of the keyframe
+    depth missing and a motion that pushes most lookups against the border: ring restarts, lanes outside
+    the staged window and clamped footprints, all against the oracle with the mask bit-exact."""
+    data = make_frame_pairs(3, 8, 36, 72, seed=18, n_levels=1)
+    lv = data["levels"][0]
+    hole = torch.rand(lv["invD0"].shape, generator=torch.Generator().manual_seed(2)) < 0.3
+    lv["invD0"] = torch.where(hole, torch.zeros_like(lv["invD0"]), lv["invD0"]).contiguous()
+    pose = _twist_to_pose(torch.tensor([[0.0, 0.35, 0.0, 0.4, 0.1, 0.0], [0.2, 0.0, 0.3, -0.3, 0.2, 0.1],
+                                        [0.0, 0.0, 1.2, 0.0, 0.0, 0.0]]))      # the last one: 70 degrees in-plane
+    res, trace = both(lv, pose, iters=2)
+    assert trace[0]["occ"].float().mean() > 0.3
+    check(res, trace, mask_slack=3)
+
+
+def test_staged_and_plain_kernels_agree_and_misaligned_maps_fall_back():
+    """staged_footprint only changes how the lookups are fetched: same masks, sums to rounding.  Maps that are
+    not 16-byte aligned cannot be staged with 16-byte cp.async; the level then runs the plain kernel."""
+    B, C, H, W = 4, 8, 60, 80
+    data = make_frame_pairs(B, C, H, W, seed=44, n_levels=1)
+    lv = levels_to(data["levels"], DEV)[0]
+    pose = (data["R0"].to(DEV), data["t0"].to(DEV))
+    a = A.uic_solve([lv], pose, iters=3, remove_tru_sigma=True, want_occ=True, staged_footprint=True)
+    b = A.uic_solve([lv], pose, iters=3, remove_tru_sigma=True, want_occ=True, staged_footprint=False)
+    # shift x1 / s1 by one float inside a larger allocation: still contiguous, no longer 16-byte aligned
+    shifted = dict(lv)
+    for k in ("x1", "s1"):
+        buf = torch.empty(lv[k].numel() + 1, device=DEV)
+        buf[1:] = lv[k].reshape(-1)
+        shifted[k] = buf[1:].view_as(lv[k])
+        assert shifted[k].data_ptr() % 16 != 0 and shifted[k].is_contiguous()
+    c = A.uic_solve([shifted], pose, iters=3, remove_tru_sigma=True, want_occ=True, staged_footprint=True)
+    torch.cuda.synchronize()
+    assert torch.equal(a.occ[0], b.occ[0]) and torch.equal(c.occ[0], b.occ[0])
+    assert (a.pose_hist - b.pose_hist).abs().max() < 1e-6
+    assert torch.equal(c.sys_hist, b.sys_hist)          # the fallback IS the plain kernel
