@@ -382,6 +382,41 @@ def main():
         # ---- side measurements (not the headline): training step of the same workload, 480x640 pairs
         extras = {}
         if not args.no_extras:
+            # the same workload with the uncertainty passed as the ONE map per frame the reference's encoder emits
+            # (it repeats it to C channels, alg:1425-1427; the headline above moves and reads the repeated tensors)
+            one_sets = [[dict(lv, s0=lv["s0"][:, :1].contiguous(), s1=lv["s1"][:, :1].contiguous()) for lv in st]
+                        for st in dev_sets]
+
+            def run_one(n):
+                for i in range(n):
+                    with torch.cuda.stream(workers[i % len(workers)]):
+                        solve(one_sets[i % N_SETS])
+
+            e0.record(main_stream)
+            for w in workers:
+                w.wait_event(e0)
+            run_one(args.warmup)
+            torch.cuda.synchronize()
+            e0.record(main_stream)
+            for w in workers:
+                w.wait_event(e0)
+            run_one(args.steps)
+            for w in workers:
+                done = torch.cuda.Event()
+                done.record(w)
+                main_stream.wait_event(done)
+            e1.record(main_stream)
+            torch.cuda.synchronize()
+            ms_one = e0.elapsed_time(e1) / args.steps
+            r = solve(one_sets[0], timed=True)
+            lvl0_one = sum(r.launch_ms[-ITERS:]) / ITERS
+            bytes_lvl0_one = (2 * C + 4) * 4 * H * W * B
+            extras["single_sigma_map"] = {
+                "what": "sigma0 / sigma1 given as (B,1,h,w) instead of repeated to C channels (DPFT_SIGMA_BROADCAST); "
+                        "same results", "ms_per_step": ms_one, "pairs_per_s": B / (ms_one * 1e-3),
+                "lvl0_launch_ms": lvl0_one, "lvl0_bytes_read_per_launch": bytes_lvl0_one,
+                "lvl0_GBps_of_bytes_read": bytes_lvl0_one / (lvl0_one * 1e-3) / 1e9}
+            del one_sets
             extras["train_step"] = train_step_leg(A, dev_sets, pose0, B, max(3, min(args.steps, 20)), dev)
             if args.workload == "tum":
                 del streamer

@@ -31,6 +31,7 @@ DPFT_LAUNCH_PER_ITERATION = 0x10
 DPFT_STAGED_FOOTPRINT = 0x20
 DPFT_SHARED_KEYFRAME = 0x40
 DPFT_PAIRWISE_EXTREMES = 0x80
+DPFT_SIGMA_BROADCAST = 0x100
 DPFT_ST_NONFINITE = 0x01
 DPFT_ST_SINGULAR = 0x02
 

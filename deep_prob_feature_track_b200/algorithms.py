@@ -101,22 +101,31 @@ def uic_solve(levels: Sequence[Dict[str, torch.Tensor]], pose: Pose, *, iters: i
 
     ``levels`` is ordered coarse to fine; each dict holds x0, x1, s0, s1 (B,C,h,w), invD0, invD1 (B,1,h,w)
     and K (B,4) already scaled to the level.  One entry == one TrustRegionInverseWUncertainty.forward.
+
+    s0 / s1 may also be (B,1,h,w): the single uncertainty map the reference's encoder produces before repeating
+    it to C channels (algorithms.py:1425-1427).  The fused launch-per-iteration kernels then read it once per
+    pixel (DPFT_SIGMA_BROADCAST); every other path gets the repeated tensor, so results never depend on it.
     """
     L = _lib.lib()
     n_levels = len(levels)
     x0 = levels[0]["x0"]
     B, C = int(levels[0]["x1"].shape[0]), int(x0.shape[1])
     Bk = 1 if shared_keyframe else B     # batch size of the keyframe-side tensors
+    one_sigma = C > 1 and all(int(lv[k].shape[1]) == 1 for lv in levels for k in ("s0", "s1"))
+    sigma_broadcast = one_sigma and fused_sobel and not single_launch
+    SC = 1 if sigma_broadcast else C
     dev = x0.device
     keep = []   # keep converted tensors alive until the launches are queued
     arr = (_lib.DpftLevel * n_levels)()
     occ: List[Optional[torch.Tensor]] = []
     for i, lv in enumerate(levels):
-        t = {k: _dev_f32(lv[k], k) for k in ("x0", "x1", "s0", "s1", "invD0", "invD1", "K")}
+        t = {k: _dev_f32(lv[k], k) for k in ("x0", "x1", "invD0", "invD1", "K")}
+        for k in ("s0", "s1"):
+            t[k] = _dev_f32(lv[k].expand(-1, C, -1, -1) if (one_sigma and not sigma_broadcast) else lv[k], k)
         H, W = int(t["x0"].shape[2]), int(t["x0"].shape[3])
-        for k, nb in (("x0", Bk), ("x1", B), ("s0", Bk), ("s1", B)):
-            if tuple(t[k].shape) != (nb, C, H, W):
-                raise ValueError(f"level {i}: {k} has shape {tuple(t[k].shape)}, expected {(nb, C, H, W)}")
+        for k, nb, nc in (("x0", Bk, C), ("x1", B, C), ("s0", Bk, SC), ("s1", B, SC)):
+            if tuple(t[k].shape) != (nb, nc, H, W):
+                raise ValueError(f"level {i}: {k} has shape {tuple(t[k].shape)}, expected {(nb, nc, H, W)}")
         for k, nb in (("invD0", Bk), ("invD1", B)):
             if t[k].numel() != nb * H * W:
                 raise ValueError(f"level {i}: {k} must be ({nb},1,H,W)")
@@ -145,7 +154,8 @@ def uic_solve(levels: Sequence[Dict[str, torch.Tensor]], pose: Pose, *, iters: i
              | (0 if single_launch else _lib.DPFT_LAUNCH_PER_ITERATION)
              | (_lib.DPFT_STAGED_FOOTPRINT if staged_footprint else 0)
              | (_lib.DPFT_SHARED_KEYFRAME if shared_keyframe else 0)
-             | (_lib.DPFT_PAIRWISE_EXTREMES if pairwise_extremes else 0))
+             | (_lib.DPFT_PAIRWISE_EXTREMES if pairwise_extremes else 0)
+             | (_lib.DPFT_SIGMA_BROADCAST if sigma_broadcast else 0))
     if (shared_keyframe or pairwise_extremes) and (combine_icp or not fused_sobel):
         raise NotImplementedError("shared_keyframe / pairwise_extremes are served by the fused U_IC kernel only")
     n_it = n_levels * iters
@@ -223,6 +233,7 @@ def uic_residual_loss(level: Dict[str, torch.Tensor], pose: Pose, *, remove_tru_
     L = _lib.lib()
     x0 = level["x0"]
     B, C, dev = int(x0.shape[0]), int(x0.shape[1]), x0.device
+    level = dict(level, s0=level["s0"].expand(-1, C, -1, -1), s1=level["s1"].expand(-1, C, -1, -1))
     arr, keep = _level_array([level], B, C, None if obj_mask0 is None else [obj_mask0],
                              None if obj_mask1 is None else [obj_mask1], with_depth=combine_icp)
     flags = (_lib.DPFT_REMOVE_TRU_SIGMA if remove_tru_sigma else 0) | (_lib.DPFT_COMBINE_ICP if combine_icp else 0)
@@ -321,7 +332,9 @@ def uic_track(levels: Sequence[Dict[str, torch.Tensor]], pose: Pose, *, iters: i
     B = R.shape[0]
     maps = []
     for lv in levels:
-        maps += [lv["x0"], lv["x1"], lv["s0"], lv["s1"]]
+        C = lv["x0"].shape[1]
+        # a single-channel uncertainty map trains as the repeated tensor (autograd sums its gradient over channels)
+        maps += [lv["x0"], lv["x1"], lv["s0"].expand(-1, C, -1, -1), lv["s1"].expand(-1, C, -1, -1)]
     outs = _UicSolveFn.apply(cfg, R, t.reshape(B, 3), *maps)
     return [tuple(outs[3 * l:3 * l + 3]) for l in range(len(levels))]
 

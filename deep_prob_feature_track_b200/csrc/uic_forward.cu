@@ -54,6 +54,7 @@ struct UicIterParams {
   float* partials;       // (B, ctas_per_pair, PS)
   double* pairrec;       // (B, PS)
   int* counters;         // [B] per pair, [B] = pairs done
+  int SC;                // channels of sigma0 / sigma1: C, or 1 (DPFT_SIGMA_BROADCAST)
   const uint32_t* s0mm;  // order-encoded min, max of sigma0 over the whole level tensor
   float* gmm;            // [4] batch-global min/max of the warped sigma of this iteration, min/max of sigma0
   int32_t* status;
@@ -325,7 +326,9 @@ __global__ void __launch_bounds__(kThreads, DPFT_MIN_CTAS) uic_iter_kernel(const
   PairView g;
   const size_t po = (size_t)b * p.C * plane;
   const size_t b0 = p.kf_shared ? 0 : (size_t)b;      // one keyframe for the whole batch (kf_vo-style tracking)
-  g.x0 = p.x0 + b0 * p.C * plane; g.x1 = p.x1 + po; g.s0 = p.s0 + b0 * p.C * plane; g.s1 = p.s1 + po;
+  g.x0 = p.x0 + b0 * p.C * plane; g.x1 = p.x1 + po;
+  g.s0 = p.s0 + b0 * p.SC * plane; g.s1 = p.s1 + (size_t)b * p.SC * plane;
+  g.splane = (p.SC == p.C) ? (unsigned)plane : 0u;
   g.d0 = p.d0 + b0 * plane; g.d1 = p.d1 + (size_t)b * plane;
   g.m0 = p.m0 ? p.m0 + b0 * plane : nullptr;
   g.m1 = p.m1 ? p.m1 + (size_t)b * plane : nullptr;
@@ -364,7 +367,7 @@ __global__ void __launch_bounds__(kThreads, DPFT_MIN_CTAS) uic_iter_kernel(const
 #endif
 constexpr int kStageAreaFloats = (kStageWarpFloats + 12 * 33 + 3) / 4 * 4;
 static_assert(kStageWarpFloats >= 27 * 33, "the reduction rows overlay the ring");
-template <bool TRU, int GW = 0, int GH = 0>
+template <bool TRU, bool SB = false, int GW = 0, int GH = 0>
 __global__ void __launch_bounds__(kThreads, DPFT_STAGED_CTAS) uic_iter_staged_kernel(const UicIterParams p) {
   extern __shared__ __align__(16) float dyn_stage[];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -380,7 +383,9 @@ __global__ void __launch_bounds__(kThreads, DPFT_STAGED_CTAS) uic_iter_staged_ke
   PairView g;
   const size_t po = (size_t)b * p.C * plane;
   const size_t b0 = p.kf_shared ? 0 : (size_t)b;      // one keyframe for the whole batch (kf_vo-style tracking)
-  g.x0 = p.x0 + b0 * p.C * plane; g.x1 = p.x1 + po; g.s0 = p.s0 + b0 * p.C * plane; g.s1 = p.s1 + po;
+  g.x0 = p.x0 + b0 * p.C * plane; g.x1 = p.x1 + po;
+  g.s0 = p.s0 + b0 * p.SC * plane; g.s1 = p.s1 + (size_t)b * p.SC * plane;
+  g.splane = (p.SC == p.C) ? (unsigned)plane : 0u;
   g.d0 = p.d0 + b0 * plane; g.d1 = p.d1 + (size_t)b * plane;
   g.m0 = p.m0 ? p.m0 + b0 * plane : nullptr;
   g.m1 = p.m1 ? p.m1 + (size_t)b * plane : nullptr;
@@ -408,7 +413,7 @@ __global__ void __launch_bounds__(kThreads, DPFT_STAGED_CTAS) uic_iter_staged_ke
   __syncthreads();
   TileSums S;
   S.reset();
-  if (y1 > y0) process_tile_staged<TRU, GW, GH>(g, s_pose, redw + 27, area, seg, y0, y1, lane, S);
+  if (y1 > y0) process_tile_staged<TRU, SB, GW, GH>(g, s_pose, redw + 27, area, seg, y0, y1, lane, S);
   __syncwarp();
   DPFT_STAMP(2, threadIdx.x == 0 && blockIdx.x == 0 && b == 0);   // tile walked
   reduce_and_finish<TRU>(p, b, redw, S.acc, S.vmin, S.vmax);
@@ -807,18 +812,23 @@ static cudaError_t launch_staged(const UicIterParams& prm, dim3 grid, bool tru, 
   cfg.attrs = attr;
   cfg.numAttrs = pdl ? 1 : 0;
   // (cudaFuncSetAttribute is per device and cheap: set it on every launch rather than caching per process)
-#define DPFT_STAGED(TRUV, w, h)                                                                              \
+#define DPFT_STAGED(TRUV, SBV, w, h)                                                                         \
   do {                                                                                                       \
-    auto* fn = uic_iter_staged_kernel<TRUV, w, h>;                                                           \
+    auto* fn = uic_iter_staged_kernel<TRUV, SBV, w, h>;                                                      \
     cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);                             \
     return cudaLaunchKernelEx(&cfg, fn, prm);                                                                \
   } while (0)
+  const bool sb = prm.SC != prm.C;
   if (!getenv("DPFT_GENERIC_GEOMETRY")) {
-    if (prm.W == 160 && prm.H == 120) { if (tru) DPFT_STAGED(true, 160, 120); else DPFT_STAGED(false, 160, 120); }
-    if (prm.W == 80 && prm.H == 60) { if (tru) DPFT_STAGED(true, 80, 60); else DPFT_STAGED(false, 80, 60); }
+    if (prm.W == 160 && prm.H == 120) {
+      if (sb) { if (tru) DPFT_STAGED(true, true, 160, 120); else DPFT_STAGED(false, true, 160, 120); }
+      if (tru) DPFT_STAGED(true, false, 160, 120); else DPFT_STAGED(false, false, 160, 120);
+    }
+    if (prm.W == 80 && prm.H == 60 && !sb) { if (tru) DPFT_STAGED(true, false, 80, 60); else DPFT_STAGED(false, false, 80, 60); }
   }
-  if (tru) DPFT_STAGED(true, 0, 0);
-  DPFT_STAGED(false, 0, 0);
+  if (sb) { if (tru) DPFT_STAGED(true, true, 0, 0); else DPFT_STAGED(false, true, 0, 0); }
+  if (tru) DPFT_STAGED(true, false, 0, 0);
+  DPFT_STAGED(false, false, 0, 0);
 #undef DPFT_STAGED
 }
 
@@ -847,7 +857,8 @@ using namespace dpft;
 // materialised-gradient variant keep one launch per iteration.
 static bool persistent_ok(uint32_t flags, bool any_occ) {
   return (flags & DPFT_FUSED_SOBEL) && !any_occ &&
-         !(flags & (DPFT_COMBINE_ICP | DPFT_LAUNCH_PER_ITERATION | DPFT_SHARED_KEYFRAME | DPFT_PAIRWISE_EXTREMES));
+         !(flags & (DPFT_COMBINE_ICP | DPFT_LAUNCH_PER_ITERATION | DPFT_SHARED_KEYFRAME | DPFT_PAIRWISE_EXTREMES |
+                    DPFT_SIGMA_BROADCAST));
 }
 
 static int persistent_grid_cached(int C, bool tru) {
@@ -893,6 +904,9 @@ static int run_uic(const dpft_level_t* levels, int n_levels, int B, int C, int i
   const bool pdl = !(flags & DPFT_NO_PDL);
   const bool fused = flags & DPFT_FUSED_SOBEL;
   const bool icp = flags & DPFT_COMBINE_ICP;
+  const int SC = (flags & DPFT_SIGMA_BROADCAST) ? 1 : C;     // channels of the sigma maps
+  if (SC != C && !fused)
+    return set_error(DPFT_EINVAL, "DPFT_SIGMA_BROADCAST needs the fused kernels (DPFT_FUSED_SOBEL)");
   float* grad = (float*)(ws + pl.off_grad);
   float* vn = (float*)(ws + pl.off_vn);
   float* icp_rec = (float*)(ws + pl.off_icp);
@@ -908,7 +922,7 @@ static int run_uic(const dpft_level_t* levels, int n_levels, int B, int C, int i
   const int mm_per_level = (pairwise && !shared_kf) ? B : 1;
   if (tru) {
     for (int l = 0; l < n_levels; ++l) {
-      const size_t per_pair = (size_t)C * levels[l].H * levels[l].W;
+      const size_t per_pair = (size_t)SC * levels[l].H * levels[l].W;
       const size_t n = per_pair * (shared_kf ? 1 : B);
       if (mm_per_level == 1) {
         const int blocks = (int)std::min<size_t>((n / 4 + 255) / 256 + 1, 148 * 8);
@@ -975,7 +989,7 @@ static int run_uic(const dpft_level_t* levels, int n_levels, int B, int C, int i
       prm.m0 = L.obj_mask0; prm.m1 = L.obj_mask1;
       prm.occ_out = L.occ_out ? L.occ_out + (size_t)it * B * plane : nullptr;
       prm.sr0_dbg = sr0;
-      prm.H = L.H; prm.W = L.W; prm.B = B; prm.C = C;
+      prm.H = L.H; prm.W = L.W; prm.B = B; prm.C = C; prm.SC = SC;
       prm.nseg = pl.nseg[l]; prm.nrt = pl.nrt[l]; prm.TR = pl.TR[l];
       prm.ctas_per_pair = fused ? pl.ctas[l] : pl.px_ctas[l];
       prm.pose = pose_hist + (size_t)k * B * 12;

@@ -119,7 +119,7 @@ __global__ void __launch_bounds__(kPT, DPFT_MIN_CTAS) uic_persistent_kernel(cons
             g.m0 = L.m0 ? L.m0 + (size_t)b * plane : nullptr;
             g.m1 = L.m1 ? L.m1 + (size_t)b * plane : nullptr;
             g.occ_out = nullptr; g.sr0_dbg = nullptr;
-            g.H = L.H; g.W = L.W; g.C = C;
+            g.H = L.H; g.W = L.W; g.C = C; g.splane = (unsigned)plane;
             g.fx = __ldg(L.K + 4 * b); g.fy = __ldg(L.K + 4 * b + 1); g.cx = __ldg(L.K + 4 * b + 2); g.cy = __ldg(L.K + 4 * b + 3);
             g.s0lo = s0lo; g.s0hi = s0hi;
             __syncwarp();

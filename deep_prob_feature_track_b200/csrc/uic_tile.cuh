@@ -21,6 +21,8 @@ struct PairView {               // one frame pair of one level, pointers already
   uint8_t* occ_out;             // optional debug outputs (per pair)
   float* sr0_dbg;
   int H, W, C;
+  unsigned splane;              // channel stride of sigma0 / sigma1 in elements: H*W, or 0 when the uncertainty is ONE
+                                // map per frame that the reference would have repeated to C channels (alg:1425-1427)
   float fx, fy, cx, cy;
   float s0lo, s0hi;             // extremes of sigma0 over the whole level tensor (remove_tru_sigma)
 };
@@ -91,9 +93,10 @@ __device__ __forceinline__ void process_tile(const PairView& g, const float* spo
 
   for (int c0 = 0; c0 < C; c0 += CH) {
     const float* X0 = g.x0 + (size_t)c0 * iplane;
-    const float* S0 = g.s0 + (size_t)c0 * iplane;
+    const unsigned splane = g.splane;
+    const float* S0 = g.s0 + (size_t)c0 * splane;
     const float* X1 = g.x1 + (size_t)c0 * iplane;
-    const float* S1 = g.s1 + (size_t)c0 * iplane;
+    const float* S1 = g.s1 + (size_t)c0 * splane;
     if (!FIXED) { X0 = opaque(X0); S0 = opaque(S0); X1 = opaque(X1); S1 = opaque(S1); }
 
     // 3-row sliding windows of the keyframe maps (own column): top / mid / (bot loaded per row)
@@ -106,16 +109,16 @@ __device__ __forceinline__ void process_tile(const PairView& g, const float* spo
         for (int c = 0; c < CH; ++c) {
           ft[c] = __ldg(xt + c * PLANE);
           fm[c] = __ldg(xm + c * PLANE);
-          st[c] = __ldg(zt + c * PLANE);
-          sm[c] = __ldg(zm + c * PLANE);
+          st[c] = __ldg(zt + c * splane);
+          sm[c] = __ldg(zm + c * splane);
         }
       } else {
 #pragma unroll
         for (int c = 0; c < CH; ++c) {
           ft[c] = ldf(X0, ot + c * iplane);
           fm[c] = ldf(X0, om + c * iplane);
-          st[c] = ldf(S0, ot + c * iplane);
-          sm[c] = ldf(S0, om + c * iplane);
+          st[c] = ldf(S0, ot + c * splane);
+          sm[c] = ldf(S0, om + c * splane);
         }
       }
     }
@@ -127,13 +130,13 @@ __device__ __forceinline__ void process_tile(const PairView& g, const float* spo
 #pragma unroll
         for (int c = 0; c < CH; ++c) {
           fb[c] = __ldg(xr + c * PLANE);
-          sb[c] = __ldg(zr + c * PLANE);
+          sb[c] = __ldg(zr + c * splane);
         }
       } else {
 #pragma unroll
         for (int c = 0; c < CH; ++c) {
           fb[c] = ldf(X0, ob + c * iplane);
-          sb[c] = ldf(S0, ob + c * iplane);
+          sb[c] = ldf(S0, ob + c * splane);
         }
       }
       const unsigned o = (unsigned)(y * W + xc);
@@ -176,31 +179,19 @@ __device__ __forceinline__ void process_tile(const PairView& g, const float* spo
 #pragma unroll
           for (int c = 0; c < G; ++c) {
             const int k = (g0 + c) * PLANE;
+            const unsigned kz = (unsigned)(g0 + c) * splane;
             xa[c] = __ldg(xq + k); xb[c] = __ldg(xq + k + 1); xc_[c] = __ldg(xq + k + GW); xd[c] = __ldg(xq + k + GW + 1);
-            za[c] = __ldg(zq + k); zb[c] = __ldg(zq + k + 1); zc[c] = __ldg(zq + k + GW); zd[c] = __ldg(zq + k + GW + 1);
+            za[c] = __ldg(zq + kz); zb[c] = __ldg(zq + kz + 1); zc[c] = __ldg(zq + kz + GW); zd[c] = __ldg(zq + kz + GW + 1);
           }
         } else {
 #pragma unroll
           for (int c = 0; c < G; ++c) {
             const unsigned ia = (unsigned)tap.o + (unsigned)(g0 + c) * iplane, ic = ia + Wu;
+            const unsigned ja = (unsigned)tap.o + (unsigned)(g0 + c) * splane, jc = ja + Wu;
             ldf2(X1, ia, xa[c], xb[c]); ldf2(X1, ic, xc_[c], xd[c]);
-            ldf2(S1, ia, za[c], zb[c]); ldf2(S1, ic, zc[c], zd[c]);
+            ldf2(S1, ja, za[c], zb[c]); ldf2(S1, jc, zc[c], zd[c]);
           }
         }
-#ifdef DPFT_PREFETCH
-#pragma unroll
-        for (int c = 0; c < G; ++c) {
-          // the next tile row samples one footprint row further down: start pulling those lines in now
-          const unsigned ip = (unsigned)tap.o + (unsigned)(g0 + c) * iplane + 2u * Wu;
-          const float* q1; const float* q2;
-          asm("mad.wide.u32 %0, %1, 4, %2;" : "=l"(q1) : "r"(ip), "l"(X1));
-          asm("mad.wide.u32 %0, %1, 4, %2;" : "=l"(q2) : "r"(ip), "l"(S1));
-          if (y + 2 < H) {
-            asm volatile("prefetch.global.L2 [%0];" ::"l"(q1));
-            asm volatile("prefetch.global.L2 [%0];" ::"l"(q2));
-          }
-        }
-#endif
         float gfx[G], gfy[G], gsx[G], gsy[G];
 #pragma unroll
         for (int c = 0; c < G; ++c) {

@@ -73,7 +73,11 @@ __device__ __forceinline__ TapXY make_tap_xy(float u, float v, int H, int W, flo
   return r;
 }
 
-template <bool TRU, int GW = 0, int GH = 0>
+// SB ("sigma broadcast"): sigma0 / sigma1 are ONE map per frame -- what the reference's encoder emits before it
+// repeats it to C channels (algorithms.py:1425-1427, uncertainty_channel = 1 in every shipped configuration).  The
+// map is staged, looked up, blended and differentiated once per pixel instead of once per channel; the results
+// are those of the repeated tensor.
+template <bool TRU, bool SB = false, int GW = 0, int GH = 0>
 __device__ __forceinline__ void process_tile_staged(const PairView& g, const float* spose, float (*scorr)[33],
                                                     float* ring /* kStageWarpFloats of this warp */, const int seg,
                                                     const int y0, const int y1, const int lane, TileSums& S) {
@@ -115,21 +119,28 @@ __device__ __forceinline__ void process_tile_staged(const PairView& g, const flo
 #pragma unroll
     for (int k = 0; k < 3; ++k) {
       if (k < 2 || lane + 64 < CH * CPR) {
-        const float *sx, *sz;
+        const float* sx;
         asm("mad.wide.u32 %0, %1, 4, %2;" : "=l"(sx) : "r"(row_off + soff[k]), "l"(X1));
-        asm("mad.wide.u32 %0, %1, 4, %2;" : "=l"(sz) : "r"(row_off + soff[k]), "l"(S1));
         cp_async16(dst + 512u * k, sx);
-        cp_async16(dst + 512u * k + 4u * (CH * SW), sz);
+        if (!SB) {
+          const float* sz;
+          asm("mad.wide.u32 %0, %1, 4, %2;" : "=l"(sz) : "r"(row_off + soff[k]), "l"(S1));
+          cp_async16(dst + 512u * k + 4u * (CH * SW), sz);
+        }
       }
     }
-    if (lane < CPR) cp_async16(dst + 4u * (2 * CH * SW), g.d1 + row_off + 4 * lane);
+    if (lane < CPR) {
+      cp_async16(dst + 4u * (2 * CH * SW), g.d1 + row_off + 4 * lane);
+      if (SB) cp_async16(dst + 4u * (CH * SW), S1 + row_off + 4 * lane);     // the one sigma map, in map slot CH
+    }
     if (lane == 0) slot_xs[row & (kStageRows - 1)] = xs;
     stage_commit();
   };
 
   // channel PAIRS travel together as float2 so the per-channel arithmetic issues as packed FFMA2 / FMUL2 / FADD2
   constexpr int NP = CH / 2;
-  float2 ft[NP], fm[NP], st[NP], sm[NP];
+  constexpr int NSP = SB ? 1 : NP;        // sigma windows: one map (its .x half) or one per channel pair
+  float2 ft[NP], fm[NP], st[NSP], sm[NSP];
   auto load_pair = [&](const float* base, const unsigned idx, const int p) {
     float2 r;
     if (FIXED) {
@@ -148,8 +159,16 @@ __device__ __forceinline__ void process_tile_staged(const PairView& g, const flo
     for (int p = 0; p < NP; ++p) {
       ft[p] = load_pair(X0, ot, p);
       fm[p] = load_pair(X0, om, p);
-      st[p] = load_pair(S0, ot, p);
-      sm[p] = load_pair(S0, om, p);
+    }
+    if (SB) {
+      st[0] = make_float2(__ldg(S0 + ot), 0.f);
+      sm[0] = make_float2(__ldg(S0 + om), 0.f);
+    } else {
+#pragma unroll
+      for (int p = 0; p < NSP; ++p) {
+        st[p] = load_pair(S0, ot, p);
+        sm[p] = load_pair(S0, om, p);
+      }
     }
   }
   // the ring holds source rows max(base, top - 3) .. top; base = first row requested since the last restart
@@ -158,11 +177,14 @@ __device__ __forceinline__ void process_tile_staged(const PairView& g, const flo
 
   for (int y = y0; y < y1; ++y) {
     const unsigned ob = (unsigned)(min(y + 1, H - 1) * W + xc);
-    float2 fb[NP], sb[NP];
+    float2 fb[NP], sb[NSP];
 #pragma unroll
-    for (int p = 0; p < NP; ++p) {
-      fb[p] = load_pair(X0, ob, p);
-      sb[p] = load_pair(S0, ob, p);
+    for (int p = 0; p < NP; ++p) fb[p] = load_pair(X0, ob, p);
+    if (SB) {
+      sb[0] = make_float2(__ldg(S0 + ob), 0.f);
+    } else {
+#pragma unroll
+      for (int p = 0; p < NSP; ++p) sb[p] = load_pair(S0, ob, p);
     }
     const unsigned o = (unsigned)(y * W + xc);
     const float d0 = d0_next;
@@ -250,7 +272,25 @@ __device__ __forceinline__ void process_tile_staged(const PairView& g, const flo
       gx = __fmul2_rn(Sx, inv);
       gy = __fmul2_rn(Sy, inv);
     };
-    constexpr int GP = DPFT_GATHER_GROUP / 2;      // channel pairs whose lookups are in flight together
+    // one sigma map per frame: its gradient, warped value and 1 / sigma once per pixel, shared by all channels
+    float2 sb_gsx = zero2, sb_gsy = zero2, sb_rs = zero2, sb_k = zero2;
+    if (SB) {
+      float2 gx1, gy1;
+      unit_sobel(st[0], sm[0], sb[0], gx1, gy1);
+      float za = a0[CH * SW], zb = a0[CH * SW + 1], zc = a1[CH * SW], zd = a1[CH * SW + 1];
+      if (any_direct && !resident) {
+        const float* q = S1 + tap.o;
+        za = __ldg(q); zb = __ldg(q + 1); zc = __ldg(q + W); zd = __ldg(q + W + 1);
+      }
+      const float sr = TRU ? blend_exact(za, zb, zc, zd, tap) : blend_fast(za, zb, zc, zd, tap);
+      const float s0v = sm[0].x;
+      const float rs = rsqrt_fast(fmaf(sr, sr, s0v * s0v));
+      const float k3 = s0v * (rs * rs);
+      sb_gsx = make_float2(gx1.x, gx1.x); sb_gsy = make_float2(gy1.x, gy1.x);
+      sb_rs = make_float2(rs, rs); sb_k = make_float2(k3, k3);
+      pmin = pmax = sr0 = sr;
+    }
+    constexpr int GP = SB ? NP : DPFT_GATHER_GROUP / 2;      // channel pairs whose lookups are in flight together
 #pragma unroll
     for (int p0 = 0; p0 < NP; p0 += GP) {
       float2 xa[GP], xb[GP], xc_[GP], xd[GP], za[GP], zb[GP], zc[GP], zd[GP];
@@ -259,41 +299,53 @@ __device__ __forceinline__ void process_tile_staged(const PairView& g, const flo
         const int kx = 2 * (p0 + j) * SW, kz = (CH + 2 * (p0 + j)) * SW;
         xa[j] = make_float2(a0[kx], a0[kx + SW]); xb[j] = make_float2(a0[kx + 1], a0[kx + SW + 1]);
         xc_[j] = make_float2(a1[kx], a1[kx + SW]); xd[j] = make_float2(a1[kx + 1], a1[kx + SW + 1]);
-        za[j] = make_float2(a0[kz], a0[kz + SW]); zb[j] = make_float2(a0[kz + 1], a0[kz + SW + 1]);
-        zc[j] = make_float2(a1[kz], a1[kz + SW]); zd[j] = make_float2(a1[kz + 1], a1[kz + SW + 1]);
+        if (!SB) {
+          za[j] = make_float2(a0[kz], a0[kz + SW]); zb[j] = make_float2(a0[kz + 1], a0[kz + SW + 1]);
+          zc[j] = make_float2(a1[kz], a1[kz + SW]); zd[j] = make_float2(a1[kz + 1], a1[kz + SW + 1]);
+        }
       }
       if (any_direct && !resident) {
 #pragma unroll
         for (int j = 0; j < GP; ++j) {
           const unsigned ia = (unsigned)tap.o + (unsigned)(2 * (p0 + j)) * iplane, ic = ia + Wu;
           ldf2(X1, ia, xa[j].x, xb[j].x); ldf2(X1, ic, xc_[j].x, xd[j].x);
-          ldf2(S1, ia, za[j].x, zb[j].x); ldf2(S1, ic, zc[j].x, zd[j].x);
           ldf2(X1, ia + iplane, xa[j].y, xb[j].y); ldf2(X1, ic + iplane, xc_[j].y, xd[j].y);
-          ldf2(S1, ia + iplane, za[j].y, zb[j].y); ldf2(S1, ic + iplane, zc[j].y, zd[j].y);
+          if (!SB) {
+            ldf2(S1, ia, za[j].x, zb[j].x); ldf2(S1, ic, zc[j].x, zd[j].x);
+            ldf2(S1, ia + iplane, za[j].y, zb[j].y); ldf2(S1, ic + iplane, zc[j].y, zd[j].y);
+          }
         }
       }
       float2 gfx[GP], gfy[GP], gsx[GP], gsy[GP];
 #pragma unroll
       for (int j = 0; j < GP; ++j) {
         unit_sobel(ft[p0 + j], fm[p0 + j], fb[p0 + j], gfx[j], gfy[j]);
-        unit_sobel(st[p0 + j], sm[p0 + j], sb[p0 + j], gsx[j], gsy[j]);
+        if (SB) { gsx[j] = sb_gsx; gsy[j] = sb_gsy; }
+        else unit_sobel(st[SB ? 0 : p0 + j], sm[SB ? 0 : p0 + j], sb[SB ? 0 : p0 + j], gsx[j], gsy[j]);
       }
 #pragma unroll
       for (int j = 0; j < GP; ++j) {
         const int p = p0 + j;
         const float2 fr = __ffma2_rn(xd[j], wd2, __ffma2_rn(xc_[j], wc2, __ffma2_rn(xb[j], wb2, __fmul2_rn(xa[j], wa2))));
-        // sigma is compared for equality against its batch extremes -> every product and sum rounded on its own,
-        // in blend_exact's order
-        const float2 sr = TRU ? __fadd2_rn(__fadd2_rn(__fadd2_rn(__fmul2_rn(za[j], wa2), __fmul2_rn(zb[j], wb2)),
-                                                     __fmul2_rn(zc[j], wc2)), __fmul2_rn(zd[j], wd2))
-                              : __ffma2_rn(zd[j], wd2, __ffma2_rn(zc[j], wc2, __ffma2_rn(zb[j], wb2, __fmul2_rn(za[j], wa2))));
         // residual, its uncertainty and the 2-vector d(wres)/d(u,v) (algorithms.py:1969-1972, :872)
         const float2 res = __ffma2_rn(fm[p], neg1, fr);
-        const float2 s0v = sm[p];
-        const float2 ss = __ffma2_rn(sr, sr, __fmul2_rn(s0v, s0v));
-        const float2 rs = make_float2(rsqrt_fast(ss.x), rsqrt_fast(ss.y));       // 1 / sigma
+        float2 sr = zero2, rs, k3;
+        if (SB) {
+          rs = sb_rs;
+          k3 = sb_k;
+        } else {
+          // sigma is compared for equality against its batch extremes -> every product and sum rounded on its own,
+          // in blend_exact's order
+          sr = TRU ? __fadd2_rn(__fadd2_rn(__fadd2_rn(__fmul2_rn(za[j], wa2), __fmul2_rn(zb[j], wb2)),
+                                           __fmul2_rn(zc[j], wc2)), __fmul2_rn(zd[j], wd2))
+                   : __ffma2_rn(zd[j], wd2, __ffma2_rn(zc[j], wc2, __ffma2_rn(zb[j], wb2, __fmul2_rn(za[j], wa2))));
+          const float2 s0v = sm[SB ? 0 : p];
+          const float2 ss = __ffma2_rn(sr, sr, __fmul2_rn(s0v, s0v));
+          rs = make_float2(rsqrt_fast(ss.x), rsqrt_fast(ss.y));                  // 1 / sigma
+          k3 = __fmul2_rn(s0v, __fmul2_rn(rs, rs));                              // sigma0 / sigma^2
+        }
         const float2 wres = __fmul2_rn(res, rs);
-        const float2 q = __fmul2_rn(wres, __fmul2_rn(s0v, __fmul2_rn(rs, rs)));   // res * sigma0 / sigma^3
+        const float2 q = __fmul2_rn(wres, k3);                                   // res * sigma0 / sigma^3
         const float2 a = __ffma2_rn(gfx[j], rs, __fmul2_rn(q, gsx[j]));
         const float2 bq = __ffma2_rn(gfy[j], rs, __fmul2_rn(q, gsy[j]));
         const float2 wm = occ ? make_float2(1e-6f, 1e-6f) : wres;
@@ -306,9 +358,11 @@ __device__ __forceinline__ void process_tile_staged(const PairView& g, const flo
           const float2 dw = __fadd2_rn(wres, make_float2(-1e-6f, -1e-6f));
           sca2 = __ffma2_rn(a, dw, sca2);
           scb2 = __ffma2_rn(bq, dw, scb2);
-          pmin = fminf(pmin, fminf(sr.x, sr.y));
-          pmax = fmaxf(pmax, fmaxf(sr.x, sr.y));
-          if (p == 0) sr0 = sr.x;
+          if (!SB) {
+            pmin = fminf(pmin, fminf(sr.x, sr.y));
+            pmax = fmaxf(pmax, fmaxf(sr.x, sr.y));
+            if (p == 0) sr0 = sr.x;
+          }
         }
       }
     }

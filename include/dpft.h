@@ -51,6 +51,11 @@ extern "C" {
 #define DPFT_STAGED_FOOTPRINT 0x20u /* launch-per-iteration path: levels with C == 8, W % 4 == 0, W >= 60 and 16-byte
                                        aligned x1 / sigma1 / invd1 run the kernel that stages the lookup footprint
                                        in shared memory (cp.async rows); other levels are unaffected              */
+#define DPFT_SIGMA_BROADCAST  0x100u /* dpft_uic_forward: sigma0 / sigma1 are (B,1,H,W) -- the ONE uncertainty map per
+                                        frame that the reference's encoder emits and then repeats to C channels
+                                        (alg:1425-1427, uncertainty_channel = 1); results are those of the repeated
+                                        tensors, the map is read, warped and differentiated once per pixel.
+                                        Fused launch-per-iteration kernels only.                               */
 #define DPFT_SHARED_KEYFRAME  0x40u /* x0, sigma0, invd0 (and obj_mask0) have batch size 1: every pair of the
                                        batch tracks against the same keyframe (kf_vo.py keyframe mode); forward only */
 #define DPFT_PAIRWISE_EXTREMES 0x80u /* with DPFT_REMOVE_TRU_SIGMA: sigma extremes per pair, i.e. the semantics of

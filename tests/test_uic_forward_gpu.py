@@ -272,3 +272,26 @@ def test_module_surface_matches_reference_signature():
         assert hasattr(mod, name)
     with pytest.raises(RuntimeError):
         mod([g["R0"], g["t0"]], *(level_inputs(g)[k] for k in ("x0", "x1", "invD0", "invD1", "K", "s0", "s1")))
+
+
+@pytest.mark.parametrize("shape", [(3, 8, 60, 80), (2, 8, 120, 160), (2, 4, 24, 32), (2, 3, 16, 31)])
+def test_single_uncertainty_map_equals_the_repeated_tensor(shape):
+    """sigma given as (B,1,h,w) -- what the reference's encoder emits before `repeat` (alg:1425-1427) -- against
+    the same map repeated to C channels and against the oracle: masks identical, sums to rounding."""
+    B, C, H, W = shape
+    data = make_frame_pairs(B, C, H, W, seed=61, n_levels=1)
+    lv = dict(data["levels"][0])
+    lv["s0"] = lv["s0"][:, :1].repeat(1, C, 1, 1).contiguous()
+    lv["s1"] = lv["s1"][:, :1].repeat(1, C, 1, 1).contiguous()
+    one = dict(lv, s0=lv["s0"][:, :1].contiguous(), s1=lv["s1"][:, :1].contiguous())
+    pose = perturbed(B, 5, 0.02)
+    full = run_cuda([lv], pose, iters=3, remove_tru_sigma=True)
+    bc = run_cuda([one], pose, iters=3, remove_tru_sigma=True)
+    assert int(bc.status.item()) == 0
+    assert torch.equal(bc.occ[0], full.occ[0])
+    assert frob_rel(bc.sys_hist.cpu(), full.sys_hist.cpu()) < 1e-5
+    assert (bc.pose_hist - full.pose_hist).abs().max() < 1e-6
+    trace = []
+    O.uic_level(pose, lv["x0"], lv["x1"], lv["invD0"], lv["invD1"], lv["K"], lv["s0"], lv["s1"], iters=3,
+                remove_tru_sigma=True, trace=trace)
+    compare_level(bc, trace, 0, 0, 3, exact_pose_inputs=True)
