@@ -11,16 +11,17 @@ namespace dpft {
 __device__ inline void solve_update_adjoint(const double* Hd /*21, upper triangle, damping included*/, const double* rhs,
                                             const float* pose_k /*12*/, const float* gpose_next /*12*/, double* xi,
                                             double* lam, double* gpose_k /*12, accumulated*/) {
-  double L[6][6];
+  // Cholesky with reciprocal pivots (one rsqrt per column, no division): this runs serially, one thread per pair
+  double L[6][6], invd[6];
   for (int j = 0; j < 6; ++j) {
     double s = Hd[tri(j, j)];
     for (int k = 0; k < j; ++k) s -= L[j][k] * L[j][k];
-    const double d = sqrt(s);
-    L[j][j] = d;
+    const double inv = rsqrt(s);
+    invd[j] = inv;
     for (int i = j + 1; i < 6; ++i) {
       double v = Hd[tri(j, i)];
       for (int k = 0; k < j; ++k) v -= L[i][k] * L[j][k];
-      L[i][j] = v / d;
+      L[i][j] = v * inv;
     }
   }
   auto chol_solve = [&](const double* r, double* out) {
@@ -28,20 +29,23 @@ __device__ inline void solve_update_adjoint(const double* Hd /*21, upper triangl
     for (int i = 0; i < 6; ++i) {
       double v = r[i];
       for (int k = 0; k < i; ++k) v -= L[i][k] * z[k];
-      z[i] = v / L[i][i];
+      z[i] = v * invd[i];
     }
     for (int i = 5; i >= 0; --i) {
       double v = z[i];
       for (int k = i + 1; k < 6; ++k) v -= L[k][i] * out[k];
-      out[i] = v / L[i][i];
+      out[i] = v * invd[i];
     }
   };
   chol_solve(rhs, xi);
   // forward: w = -xi_w, theta = |w|, k = w/theta, dR = I + K s + K^2 c1, dt = -dR xi_v
   const double w[3] = {-xi[0], -xi[1], -xi[2]};
   const double th = sqrt(w[0] * w[0] + w[1] * w[1] + w[2] * w[2]);
-  const double kv[3] = {w[0] / th, w[1] / th, w[2] / th};
-  const double s = sin(th), c = cos(th), c1 = 1.0 - c;
+  const double ith = 1.0 / th;
+  const double kv[3] = {w[0] * ith, w[1] * ith, w[2] * ith};
+  double s, c;
+  sincos(th, &s, &c);
+  const double c1 = 1.0 - c;
   const double Kx[9] = {0, -kv[2], kv[1], kv[2], 0, -kv[0], -kv[1], kv[0], 0};
   double K2[9], dR[9];
   for (int i = 0; i < 3; ++i)
@@ -95,8 +99,8 @@ __device__ inline void solve_update_adjoint(const double* Hd /*21, upper triangl
   const double gk[3] = {gK[7] - gK[5], gK[2] - gK[6], gK[3] - gK[1]};
   double g_th = g_s * c + g_c1 * s;
   const double kdotw = gk[0] * w[0] + gk[1] * w[1] + gk[2] * w[2];
-  g_th -= kdotw / (th * th);
-  for (int i = 0; i < 3; ++i) gxi[i] = -(gk[i] / th + g_th * w[i] / th);
+  g_th -= kdotw * ith * ith;
+  for (int i = 0; i < 3; ++i) gxi[i] = -(gk[i] * ith + g_th * w[i] * ith);
   chol_solve(gxi, lam);
 }
 

@@ -46,8 +46,11 @@ struct BwdParams {
   float* gpose;          // (B,12) accumulated d/d(pose_k)
 };
 
+#ifndef DPFT_BWD_CTAS
+#define DPFT_BWD_CTAS 4
+#endif
 template <int CH, bool TRU>
-__global__ void __launch_bounds__(kBT, 4) uic_bwd_px_kernel(const BwdParams p) {
+__global__ void __launch_bounds__(kBT, DPFT_BWD_CTAS) uic_bwd_px_kernel(const BwdParams p) {
   __shared__ float s_red[kBT / 32][12];
   const int b = blockIdx.y;
   const int H = p.H, W = p.W, C = p.C;
@@ -139,45 +142,62 @@ __global__ void __launch_bounds__(kBT, 4) uic_bwd_px_kernel(const BwdParams p) {
     const float tyn = tap.wa + tap.wb, tys = tap.wc + tap.wd, txl = tap.wa + tap.wc, txr = tap.wb + tap.wd;
     float g_ix = 0.f, g_iy = 0.f;
 
-    for (int c0 = 0; c0 < C; c0 += CH) {
+    // Channels go in groups of G: every load of the group (keyframe maps, unit gradients, the eight lookups AND the
+    // running sums that are about to be updated) is issued before the first dependent instruction, so a thread has
+    // 20 G independent loads in flight per round trip instead of one channel's worth -- the kernel is bound by
+    // the latency of exactly these loads (ncu: 88 % of the stall samples are long-scoreboard waits).
+#ifndef DPFT_BWD_GROUP
+#define DPFT_BWD_GROUP 2
+#endif
+    constexpr int G = CH >= DPFT_BWD_GROUP ? DPFT_BWD_GROUP : (CH >= 2 ? 2 : 1);
+    for (int c0 = 0; c0 < C; c0 += G) {
+      float f0[G], s0v[G], gfx[G], gfy[G], gsx[G], gsy[G], xa[G], xb[G], xc[G], xd[G], za[G], zb[G], zc[G], zd[G];
+      float o_gfx[G], o_gfy[G], o_gsx[G], o_gsy[G], o_x0[G], o_s0[G];
 #pragma unroll
-      for (int c = 0; c < CH; ++c) {
+      for (int c = 0; c < G; ++c) {
         const size_t k0 = pair_off + (size_t)(c0 + c) * iplane + pix;
         const size_t k1 = pair_off + (size_t)(c0 + c) * iplane + tap.o;
-        const float f0 = __ldg(p.x0 + k0), s0v = __ldg(p.s0 + k0);
-        const float gfx = __ldg(p.gfx + k0), gfy = __ldg(p.gfy + k0), gsx = __ldg(p.gsx + k0), gsy = __ldg(p.gsy + k0);
-        const float xa = __ldg(p.x1 + k1), xb = __ldg(p.x1 + k1 + 1), xc = __ldg(p.x1 + k1 + W), xd = __ldg(p.x1 + k1 + W + 1);
-        const float za = __ldg(p.s1 + k1), zb = __ldg(p.s1 + k1 + 1), zc = __ldg(p.s1 + k1 + W), zd = __ldg(p.s1 + k1 + W + 1);
+        f0[c] = __ldg(p.x0 + k0); s0v[c] = __ldg(p.s0 + k0);
+        gfx[c] = __ldg(p.gfx + k0); gfy[c] = __ldg(p.gfy + k0); gsx[c] = __ldg(p.gsx + k0); gsy[c] = __ldg(p.gsy + k0);
+        xa[c] = __ldg(p.x1 + k1); xb[c] = __ldg(p.x1 + k1 + 1); xc[c] = __ldg(p.x1 + k1 + W); xd[c] = __ldg(p.x1 + k1 + W + 1);
+        za[c] = __ldg(p.s1 + k1); zb[c] = __ldg(p.s1 + k1 + 1); zc[c] = __ldg(p.s1 + k1 + W); zd[c] = __ldg(p.s1 + k1 + W + 1);
+        o_gfx[c] = p.g_gfx[k0]; o_gfy[c] = p.g_gfy[k0]; o_gsx[c] = p.g_gsx[k0]; o_gsy[c] = p.g_gsy[k0];
+        o_x0[c] = p.g_x0[k0]; o_s0[c] = p.g_s0[k0];
+      }
+#pragma unroll
+      for (int c = 0; c < G; ++c) {
+        const size_t k0 = pair_off + (size_t)(c0 + c) * iplane + pix;
+        const size_t k1 = pair_off + (size_t)(c0 + c) * iplane + tap.o;
         // forward quantities
-        const float fr = blend_fast(xa, xb, xc, xd, tap);
-        const float sr = TRU ? blend_exact(za, zb, zc, zd, tap) : blend_fast(za, zb, zc, zd, tap);
-        const float res = fr - f0;
-        const float rs = rsqrtf(fmaf(sr, sr, s0v * s0v));
+        const float fr = blend_fast(xa[c], xb[c], xc[c], xd[c], tap);
+        const float sr = TRU ? blend_exact(za[c], zb[c], zc[c], zd[c], tap) : blend_fast(za[c], zb[c], zc[c], zd[c], tap);
+        const float res = fr - f0[c];
+        const float rs = rsqrtf(fmaf(sr, sr, s0v[c] * s0v[c]));
         const float rs3 = rs * rs * rs;
         const float wres = res * rs;
-        const float q = res * s0v * rs3;
-        const float a = fmaf(gfx, rs, q * gsx);
-        const float bq = fmaf(gfy, rs, q * gsy);
+        const float q = res * s0v[c] * rs3;
+        const float a = fmaf(gfx[c], rs, q * gsx[c]);
+        const float bq = fmaf(gfy[c], rs, q * gsy[c]);
         const float wm = occ ? 1e-6f : wres;
         // reverse
         const float ga = fmaf(a, muu, fmaf(bq, muv, wm * lu));
         const float gb = fmaf(a, muv, fmaf(bq, mvv, wm * lv));
         const float gwres = occ ? 0.f : fmaf(a, lu, bq * lv);
-        const float gq = fmaf(ga, gsx, gb * gsy);
-        float grs = fmaf(ga, gfx, gb * gfy);                       // via a, b
-        float gres = fmaf(gq, s0v * rs3, gwres * rs);              // via q, wres
-        float gs0 = gq * res * rs3;                                // via q
-        grs = fmaf(3.f * gq, res * s0v * rs * rs, grs);            // q ~ rs^3
-        grs = fmaf(gwres, res, grs);                               // wres = res rs
-        const float gsr = -grs * rs3 * sr;                         // rs = (sr^2 + s0^2)^-1/2
-        gs0 = fmaf(-grs * rs3, s0v, gs0);
+        const float gq = fmaf(ga, gsx[c], gb * gsy[c]);
+        float grs = fmaf(ga, gfx[c], gb * gfy[c]);                    // via a, b
+        float gres = fmaf(gq, s0v[c] * rs3, gwres * rs);              // via q, wres
+        float gs0 = gq * res * rs3;                                   // via q
+        grs = fmaf(3.f * gq, res * s0v[c] * rs * rs, grs);            // q ~ rs^3
+        grs = fmaf(gwres, res, grs);                                  // wres = res rs
+        const float gsr = -grs * rs3 * sr;                            // rs = (sr^2 + s0^2)^-1/2
+        gs0 = fmaf(-grs * rs3, s0v[c], gs0);
         // own-pixel accumulations (this thread is the only writer of these elements in this launch)
-        p.g_gfx[k0] += ga * rs;
-        p.g_gfy[k0] += gb * rs;
-        p.g_gsx[k0] += ga * q;
-        p.g_gsy[k0] += gb * q;
-        p.g_x0[k0] -= gres;
-        p.g_s0[k0] += gs0;
+        p.g_gfx[k0] = fmaf(ga, rs, o_gfx[c]);
+        p.g_gfy[k0] = fmaf(gb, rs, o_gfy[c]);
+        p.g_gsx[k0] = fmaf(ga, q, o_gsx[c]);
+        p.g_gsy[k0] = fmaf(gb, q, o_gsy[c]);
+        p.g_x0[k0] = o_x0[c] - gres;
+        p.g_s0[k0] = o_s0[c] + gs0;
         // bilinear adjoint: scatter into the live frame's maps
         atomicAdd(p.g_x1 + k1, tap.wa * gres);
         atomicAdd(p.g_x1 + k1 + 1, tap.wb * gres);
@@ -188,10 +208,10 @@ __global__ void __launch_bounds__(kBT, 4) uic_bwd_px_kernel(const BwdParams p) {
         atomicAdd(p.g_s1 + k1 + W, tap.wc * gsr);
         atomicAdd(p.g_s1 + k1 + W + 1, tap.wd * gsr);
         // and into the sample position
-        g_ix = fmaf(gres, fmaf(xb - xa, tyn, (xd - xc) * tys), g_ix);
-        g_iy = fmaf(gres, fmaf(xc - xa, txl, (xd - xb) * txr), g_iy);
-        g_ix = fmaf(gsr, fmaf(zb - za, tyn, (zd - zc) * tys), g_ix);
-        g_iy = fmaf(gsr, fmaf(zc - za, txl, (zd - zb) * txr), g_iy);
+        g_ix = fmaf(gres, fmaf(xb[c] - xa[c], tyn, (xd[c] - xc[c]) * tys), g_ix);
+        g_iy = fmaf(gres, fmaf(xc[c] - xa[c], txl, (xd[c] - xb[c]) * txr), g_iy);
+        g_ix = fmaf(gsr, fmaf(zb[c] - za[c], tyn, (zd[c] - zc[c]) * tys), g_ix);
+        g_iy = fmaf(gsr, fmaf(zc[c] - za[c], txl, (zd[c] - zb[c]) * txr), g_iy);
       }
     }
     // (u,v) -> w = R ray + t d0 -> pose
