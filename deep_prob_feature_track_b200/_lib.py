@@ -17,7 +17,7 @@ PKG_DIR = os.path.dirname(os.path.abspath(__file__))
 REPO_DIR = os.path.dirname(PKG_DIR)
 CSRC = os.path.join(PKG_DIR, "csrc")
 LIB_PATH = os.path.join(PKG_DIR, "libdpft.so")
-SOURCES = ["dpft_abi.cu", "uic_forward.cu", "uic_backward.cu", "icp_term.cu", "uic_residual.cu", "ic_path.cu", "ic_backward.cu", "uic_persistent.cu", "preprocess.cu"]
+SOURCES = ["dpft_abi.cu", "uic_forward.cu", "uic_backward.cu", "icp_term.cu", "uic_residual.cu", "ic_path.cu", "ic_backward.cu", "uic_persistent.cu", "preprocess.cu", "pose_loss.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "-Xcompiler", "-fPIC", "-shared"]
 
@@ -145,6 +145,10 @@ def lib() -> ctypes.CDLL:
         fn = getattr(L, name)
         fn.restype = ctypes.c_int
         fn.argtypes = args
+    L.dpft_pose_epe_loss.restype = ctypes.c_int
+    L.dpft_pose_epe_loss.argtypes = [vp] * 7 + [ci] * 4 + [vp, vp]
+    L.dpft_pose_epe_loss_backward.restype = ctypes.c_int
+    L.dpft_pose_epe_loss_backward.argtypes = [vp] * 7 + [ci] * 4 + [vp, vp, vp, vp]
     L.dpft_preprocess_depth.restype = ctypes.c_int
     L.dpft_preprocess_depth.argtypes = [vp, ci, ci, ci, ci, ctypes.POINTER(vp), ctypes.POINTER(vp), vp,
                                         ctypes.c_size_t, vp]
@@ -161,7 +165,7 @@ def exported_symbols() -> List[str]:
             "dpft_uic_residual_workspace_bytes", "dpft_uic_residual_loss", "dpft_ic_gradients", "dpft_ic_residual",
             "dpft_ic_normal_matrix", "dpft_ic_rhs", "dpft_ic_update", "dpft_ic_gradients_backward",
             "dpft_ic_residual_backward", "dpft_ic_normal_matrix_backward", "dpft_ic_rhs_backward",
-            "dpft_ic_update_backward", "dpft_preprocess_depth"]
+            "dpft_ic_update_backward", "dpft_preprocess_depth", "dpft_pose_epe_loss", "dpft_pose_epe_loss_backward"]
 
 
 def check(code: int, what: str) -> None:

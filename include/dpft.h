@@ -220,6 +220,20 @@ int dpft_uic_forward_timed(const dpft_level_t *levels, int n_levels, int B, int 
                            float *aux_hist, int32_t *status, void *workspace, size_t workspace_bytes,
                            void *stream, float *launch_ms);
 
+/*
+ * 3D end-point-error loss on the pose pyramid (criterions.py:101-136 compute_RT_EPE_loss, EPE3D_loss :22-46):
+ *   loss[b] = sum_n mean over valid pixels of || (R_est[b,n] p + t_est[b,n]) - (R_gt[b] p + t_gt[b]) ||,
+ *   p = [(u - cx)/fx, (v - cy)/fy, 1] * depth[b,v,u];  a pixel is valid when the target point has no NaN and
+ *   invalid[b,v,u] <= 0 (invalid may be NULL); a sample without valid pixels gives 0.
+ * depth, invalid: (B,h,w); K: (B,4) already scaled to (h,w); R_est (B,N,3,3), t_est (B,N,3), N <= 8.
+ * The backward writes d loss / d R_est and d t_est scaled by g_loss (B); the target is a constant, as in the reference.
+ */
+int dpft_pose_epe_loss(const float *depth, const float *invalid, const float *K, const float *R_gt, const float *t_gt,
+                       const float *R_est, const float *t_est, int B, int N, int h, int w, float *loss, void *stream);
+int dpft_pose_epe_loss_backward(const float *depth, const float *invalid, const float *K, const float *R_gt,
+                                const float *t_gt, const float *R_est, const float *t_est, int B, int N, int h, int w,
+                                const float *g_loss, float *g_R_est, float *g_t_est, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

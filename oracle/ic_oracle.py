@@ -511,3 +511,28 @@ def track_pyramid(levels: Sequence[Dict], pose: Pose, *, variant: str = "U_IC", 
         if trace is not None:
             trace.append(tr)
     return pose, per_level
+
+
+def pose_epe_loss(R_est, t_est, R_gt, t_gt, depth, K, invalid=None) -> torch.Tensor:
+    """compute_RT_EPE_loss (criterions.py:101-136) on maps that are already at the loss resolution: back-project
+    (geometry.py:429-445), transform by the target and by each of the N estimated poses (geometry.py:376-399),
+    per-sample mean point distance over the valid pixels (EPE3D_loss, criterions.py:22-46), summed over the poses.
+    R_est (B,N,3,3), t_est (B,N,3), depth (B,1,h,w), invalid (B,1,h,w) or None -> (B,)."""
+    B, _, H, W = depth.shape
+    px, py = pixel_rays(K, H, W)
+    xyz = torch.cat((px * depth, py * depth, depth), dim=1).reshape(B, 3, -1)
+    target = (t_gt.reshape(B, 3, 1) + torch.bmm(R_gt, xyz)).detach()
+    mask = torch.isnan(target).any(dim=1)
+    if invalid is not None:
+        mask = mask | (invalid.reshape(B, -1) > 0)
+    total = torch.zeros((B,), dtype=depth.dtype)
+    for n in range(R_est.shape[1]):
+        est = t_est[:, n].reshape(B, 3, 1) + torch.bmm(R_est[:, n], xyz)
+        epe = torch.norm(target - est, p=2, dim=1)
+        per = []
+        for b in range(B):
+            v = epe[b][~mask[b]]
+            per.append(v.mean() if v.numel() else torch.zeros((), dtype=depth.dtype))
+        total = total + torch.stack(per)
+    return total
+

@@ -259,6 +259,30 @@ def ic_gradients(name, *, seed, B=2, C=1, H=20, W=28, iters=2):
          flags=np.array([0, 0, 0, iters], dtype=np.int32))
 
 
+def pose_loss(name, *, seed, B=3, N=4, H=120, W=160):
+    """Reference compute_RT_EPE_loss (criterions.py:101-136), training and evaluation calls, with autograd."""
+    import models.criterions as crit
+    g = torch.Generator().manual_seed(seed)
+    depth = torch.rand((B, 1, H, W), generator=g) * 2.0 + 0.5
+    invalid = torch.rand((B, 1, H, W), generator=g) < 0.15
+    invalid[B - 1] = True                                   # one sample without a valid pixel
+    K = torch.tensor([[131.25, 131.25, 79.875, 59.875]]).repeat(B, 1) * (W / 160.0)
+    R_gt, t_gt = perturbed_pose(B, seed + 1, 0.05)
+    R_est = torch.stack([perturbed_pose(B, seed + 2 + n, 0.05)[0] for n in range(N)], dim=1).requires_grad_(True)
+    t_est = torch.stack([perturbed_pose(B, seed + 2 + n, 0.05)[1] for n in range(N)], dim=1).requires_grad_(True)
+    w = torch.rand((B,), generator=g) + 0.5
+    loss = crit.compute_RT_EPE_loss(R_est, t_est, R_gt, t_gt, depth, K, invalid=invalid)
+    (loss * w).sum().backward()
+    with torch.no_grad():
+        loss_eval = crit.compute_RT_EPE_loss(R_est[:, 0], t_est[:, 0], R_gt, t_gt, depth, K, invalid=invalid)
+        rdepth = torch.nn.functional.interpolate(depth, size=(60, 80), mode='bilinear')
+        rinvalid = torch.nn.functional.interpolate(invalid.float(), size=(60, 80), mode='bilinear')
+    save(name, depth=depth.numpy(), invalid=invalid.numpy().astype(np.uint8), K=K.numpy(), R_gt=R_gt.numpy(),
+         t_gt=t_gt.numpy(), R_est=R_est.detach().numpy(), t_est=t_est.detach().numpy(), w=w.numpy(),
+         loss=loss.detach().numpy(), loss_eval=loss_eval.numpy(), g_R_est=R_est.grad.numpy(), g_t_est=t_est.grad.numpy(),
+         rdepth=rdepth.numpy(), rinvalid=rinvalid.numpy())
+
+
 def main():
     torch.set_num_threads(4)
     uic_single_level("uic_plain", seed=11)
@@ -273,6 +297,7 @@ def main():
     ic_single_level("ic_resvol", seed=42, solver="Direct-ResVol")
     ic_single_level("ic_deepic", seed=43, solver="Direct-ResVol", mest="MultiScale2w")
     ic_gradients("ic_grad", seed=51)
+    pose_loss("pose_loss", seed=61)
 
 
 if __name__ == "__main__":

@@ -140,3 +140,21 @@ def test_ic_autograd_matches_reference(sampler):
     assert frob_rel(mest.net[0].weight.grad, g["g_mest_conv0"]) < 1e-3
     assert frob_rel(net[0].weight.grad, g["g_solver_fc0"]) < 1e-3
     assert frob_rel(net[4].bias.grad, g["g_solver_fc2_bias"]) < 1e-3
+
+
+def test_pose_epe_loss_matches_reference():
+    """Oracle pose-pyramid loss (and its autograd) against the reference's compute_RT_EPE_loss, training call
+    (60x80 resize, N poses) and evaluation call (full resolution, one pose)."""
+    g = load_golden("pose_loss")
+    B, _, H, W = g["depth"].shape
+    rK = g["K"].clone() * torch.tensor([80.0 / W, 60.0 / H, 80.0 / W, 60.0 / H])
+    R_est = g["R_est"].clone().requires_grad_(True)
+    t_est = g["t_est"].clone().requires_grad_(True)
+    loss = O.pose_epe_loss(R_est, t_est, g["R_gt"], g["t_gt"], g["rdepth"], rK, g["rinvalid"])
+    (loss * g["w"]).sum().backward()
+    assert frob_rel(loss, g["loss"]) < 1e-5 and loss[B - 1] == 0
+    assert frob_rel(R_est.grad, g["g_R_est"]) < 1e-4 and frob_rel(t_est.grad, g["g_t_est"]) < 1e-4
+    with torch.no_grad():
+        ev = O.pose_epe_loss(g["R_est"][:, :1], g["t_est"][:, :1], g["R_gt"], g["t_gt"], g["depth"], g["K"],
+                             g["invalid"].float())
+    assert frob_rel(ev, g["loss_eval"]) < 1e-5
