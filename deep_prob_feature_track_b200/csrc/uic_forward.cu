@@ -603,23 +603,42 @@ __global__ void init_kernel(const float* __restrict__ pose_in, float* __restrict
 
 // min / max of a whole tensor (torch's sigma0.min(), sigma0.max(): algorithms.py:1976-1977)
 __global__ void __launch_bounds__(256) minmax_kernel(const float* __restrict__ v, size_t n, uint32_t* __restrict__ mm) {
+  __shared__ float s_lo[8], s_hi[8];
   float lo = CUDART_INF_F, hi = -CUDART_INF_F;
   const size_t stride = (size_t)gridDim.x * blockDim.x;
   const size_t n4 = ((reinterpret_cast<uintptr_t>(v) & 15) == 0) ? n / 4 : 0;
   const float4* v4 = reinterpret_cast<const float4*>(v);
-  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  for (; i + 3 * stride < n4; i += 4 * stride) {       // four independent 16-byte loads in flight per thread
+    const float4 a = __ldg(v4 + i), b = __ldg(v4 + i + stride), c = __ldg(v4 + i + 2 * stride), d = __ldg(v4 + i + 3 * stride);
+    lo = fminf(fminf(fminf(lo, fminf(a.x, a.y)), fminf(fminf(a.z, a.w), fminf(b.x, b.y))),
+               fminf(fminf(fminf(b.z, b.w), fminf(c.x, c.y)), fminf(fminf(c.z, c.w), fminf(fminf(d.x, d.y), fminf(d.z, d.w)))));
+    hi = fmaxf(fmaxf(fmaxf(hi, fmaxf(a.x, a.y)), fmaxf(fmaxf(a.z, a.w), fmaxf(b.x, b.y))),
+               fmaxf(fmaxf(fmaxf(b.z, b.w), fmaxf(c.x, c.y)), fmaxf(fmaxf(c.z, c.w), fmaxf(fmaxf(d.x, d.y), fmaxf(d.z, d.w)))));
+  }
+  for (; i < n4; i += stride) {
     const float4 q = __ldg(v4 + i);
     lo = fminf(fminf(lo, q.x), fminf(q.y, fminf(q.z, q.w)));
     hi = fmaxf(fmaxf(hi, q.x), fmaxf(q.y, fmaxf(q.z, q.w)));
   }
-  for (size_t i = n4 * 4 + (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
-    const float q = __ldg(v + i);
+  for (size_t j = n4 * 4 + (size_t)blockIdx.x * blockDim.x + threadIdx.x; j < n; j += stride) {
+    const float q = __ldg(v + j);
     lo = fminf(lo, q);
     hi = fmaxf(hi, q);
   }
   lo = warp_min(lo);
   hi = warp_max(hi);
   if ((threadIdx.x & 31) == 0) {
+    s_lo[threadIdx.x >> 5] = lo;
+    s_hi[threadIdx.x >> 5] = hi;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {                               // one atomic pair per CTA on the two shared words
+#pragma unroll
+    for (int w = 1; w < 8; ++w) {
+      lo = fminf(lo, s_lo[w]);
+      hi = fmaxf(hi, s_hi[w]);
+    }
     atomicMin(mm, f2ord(lo));
     atomicMax(mm + 1, f2ord(hi));
   }
