@@ -41,6 +41,21 @@ constexpr int kThreads = kWarps * 32;
 constexpr int kCols = kTileCols;   // output columns per warp tile
 constexpr int kMaxTileRows = 40;
 
+// Balanced tiling of the staged kernel.  With one rectangular tiling for every pair the CTA count is a multiple of
+// B and rarely matches the resident CTA slots (64 pairs x 6 CTAs = 384 of 444: 60 SMs run two CTAs, 88 run three,
+// and the launch lasts as long as the three-CTA SMs).  So the pairs come in two kinds: `n_more` of them (spread
+// evenly over the batch) get one CTA more than the others, and the warp tiles of a kind are listed explicitly --
+// segments split into a different number of row tiles, dealt to the CTAs so that every CTA walks about the same
+// number of rows.  Every slot is filled and every SM gets the same work to within a few rows.
+constexpr int kTabCtas = 8;
+struct TileTab {
+  int on;                          // 0: rectangular tiling (nseg x nrt tiles of TR rows)
+  int n_more;                      // pairs of kind 1
+  int ctas[2];                     // CTAs per pair of kind 0 / 1
+  unsigned char seg[2][kTabCtas][4];
+  short y0[2][kTabCtas][4], y1[2][kTabCtas][4];
+};
+
 struct UicIterParams {
   const float *x0, *x1, *s0, *s1, *d0, *d1, *K;
   const uint8_t *m0, *m1;
@@ -63,6 +78,7 @@ struct UicIterParams {
   int pairwise;          // sigma extremes per pair instead of per batch (each pair its own batch of one)
   const float* icp_rec;  // (B,28) sums of the point-to-plane term of this iteration, or nullptr
   float icp_w2;          // its weight squared (w_icp scales both J and r)
+  TileTab tab;           // staged kernel only
 };
 
 // Final step for one pair: corrections for the batch-global sigma extremes, damping, solve, update.
@@ -135,7 +151,8 @@ __device__ __forceinline__ void stamp(int i) {
 
 template <bool TRU>
 __device__ __forceinline__ void reduce_and_finish(const UicIterParams& p, const int b, float (*redw)[33] /* this warp's [NSUM][33] */,
-                                                  const float (&acc)[27], const float vmin, const float vmax) {
+                                                  const float (&acc)[27], const float vmin, const float vmax,
+                                                  const int n_ctas /* CTAs of THIS pair; records are spaced by p.ctas_per_pair */) {
   __shared__ double wsum[kWarps][NSUM + 1];
   __shared__ float wvmin[kWarps], wvmax[kWarps];
   __shared__ float s_pair_mm[2];
@@ -200,14 +217,14 @@ __device__ __forceinline__ void reduce_and_finish(const UicIterParams& p, const 
   // ---------------------------------------------------------------- last CTA of the pair reduces it
   __threadfence();
   __syncthreads();
-  if (threadIdx.x == 0) s_flag = (atomicAdd(p.counters + b, 1) == p.ctas_per_pair - 1);
+  if (threadIdx.x == 0) s_flag = (atomicAdd(p.counters + b, 1) == n_ctas - 1);
   __syncthreads();
   if (!s_flag) return;
   __threadfence();
   DPFT_STAMP(4, threadIdx.x == 0 && b == 0);                      // last CTA of pair 0 starts the pair reduction
 
   const float* pp = p.partials + (size_t)b * p.ctas_per_pair * PS;
-  const int n = p.ctas_per_pair;
+  const int n = n_ctas;
   float pair_min = CUDART_INF_F, pair_max = -CUDART_INF_F;
   if (TRU) {
     float a = CUDART_INF_F, c = -CUDART_INF_F;
@@ -356,7 +373,7 @@ __global__ void __launch_bounds__(kThreads, DPFT_MIN_CTAS) uic_iter_kernel(const
   TileSums S;
   S.reset();
   process_tile<CH, TRU, GW, GH>(g, s_pose, &red[warp][27], seg, y0, y1, lane, S);
-  reduce_and_finish<TRU>(p, b, red[warp], S.acc, S.vmin, S.vmax);
+  reduce_and_finish<TRU>(p, b, red[warp], S.acc, S.vmin, S.vmax, p.ctas_per_pair);
 }
 
 // Same launch structure as uic_iter_kernel, tile walked by the staged-footprint routine (uic_tile_staged.cuh):
@@ -373,12 +390,23 @@ __global__ void __launch_bounds__(kThreads, DPFT_STAGED_CTAS) uic_iter_staged_ke
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int b = blockIdx.y;
   const int plane = (GW > 0) ? GW * GH : p.H * p.W;
-  const int wt = blockIdx.x * kWarps + warp;
-  const bool warp_on = wt < p.nseg * p.nrt;
-  const int seg = warp_on ? wt % p.nseg : 0;
-  const int rt = warp_on ? wt / p.nseg : 0;
-  const int y0 = rt * p.TR;
-  const int y1 = warp_on ? min(y0 + p.TR, p.H) : y0;
+  int seg, y0, y1, n_ctas = p.ctas_per_pair;
+  if (p.tab.on) {
+    // kind 1 pairs are spread evenly over the batch (Bresenham)
+    const int kind = (int)(((long)(b + 1) * p.tab.n_more) / p.B - ((long)b * p.tab.n_more) / p.B);
+    n_ctas = p.tab.ctas[kind];
+    if ((int)blockIdx.x >= n_ctas) return;
+    seg = p.tab.seg[kind][blockIdx.x][warp];
+    y0 = p.tab.y0[kind][blockIdx.x][warp];
+    y1 = p.tab.y1[kind][blockIdx.x][warp];
+  } else {
+    const int wt = blockIdx.x * kWarps + warp;
+    const bool warp_on = wt < p.nseg * p.nrt;
+    seg = warp_on ? wt % p.nseg : 0;
+    const int rt = warp_on ? wt / p.nseg : 0;
+    y0 = rt * p.TR;
+    y1 = warp_on ? min(y0 + p.TR, p.H) : y0;
+  }
 
   PairView g;
   const size_t po = (size_t)b * p.C * plane;
@@ -416,7 +444,7 @@ __global__ void __launch_bounds__(kThreads, DPFT_STAGED_CTAS) uic_iter_staged_ke
   if (y1 > y0) process_tile_staged<TRU, SB, GW, GH>(g, s_pose, redw + 27, area, seg, y0, y1, lane, S);
   __syncwarp();
   DPFT_STAMP(2, threadIdx.x == 0 && blockIdx.x == 0 && b == 0);   // tile walked
-  reduce_and_finish<TRU>(p, b, redw, S.acc, S.vmin, S.vmax);
+  reduce_and_finish<TRU>(p, b, redw, S.acc, S.vmin, S.vmax, n_ctas);
 }
 
 // =========================================================================== materialised-gradient path
@@ -586,7 +614,7 @@ __global__ void __launch_bounds__(kThreads, 4) uic_iter_px_kernel(const UicIterP
       red[warp][33 + i][lane] = cmx[i];
     }
   }
-  reduce_and_finish<TRU>(p, b, red[threadIdx.x >> 5], acc, vmin, vmax);
+  reduce_and_finish<TRU>(p, b, red[threadIdx.x >> 5], acc, vmin, vmax, p.ctas_per_pair);
 }
 
 // --------------------------------------------------------------------------- small helper kernels
@@ -679,6 +707,7 @@ struct Plan {
   int nseg[DPFT_MAX_LEVELS], nrt[DPFT_MAX_LEVELS], TR[DPFT_MAX_LEVELS], ctas[DPFT_MAX_LEVELS];
   int ppt[DPFT_MAX_LEVELS], px_ctas[DPFT_MAX_LEVELS];   // materialised-gradient path: pixels per thread, CTAs per pair
   int max_ctas;
+  TileTab tab[DPFT_MAX_LEVELS];   // balanced tiling of the levels the staged kernel takes
   size_t max_plane;
   size_t off_partials, off_pairrec, off_counters, off_mm, off_gmm, off_sr0, off_grad, grad_elems;
   size_t off_vn, off_icp, off_dmm, total;
@@ -711,6 +740,46 @@ static bool staged_ok(const dpft_level_t& L, int C) {
   return C == 8 && L.W % 4 == 0 && L.W >= 2 * kTileCols && L.H >= kStageRows && al(L.x1) && al(L.sigma1) && al(L.invd1);
 }
 
+// Balanced tile table of one level (see TileTab).  Returns false when the rectangular tiling should stay (the
+// table holds at most kTabCtas CTAs per pair, and a pair needs at least one tile per segment).
+static bool make_tile_tab(int H, int nseg, int B, TileTab& tab) {
+  tab = TileTab{};
+  if (kWarps != 4) return false;
+  // 420 of the 444 resident slots: filling every slot makes a lone launch ~3 % shorter still, but then the small
+  // launches of OTHER streams (coarse levels of independent batches) find no free slot and the multi-stream
+  // throughput drops by 5 % (profiles/exp9.sh)
+  long slots = 148L * DPFT_STAGED_CTAS * 35 / 37;
+  if (const char* e = getenv("DPFT_CTA_SLOTS")) slots = std::max(1L, atol(e));
+  if (getenv("DPFT_RECT_TILES")) return false;
+  const int c0 = (int)(slots / B);               // CTAs per pair of kind 0; kind 1 has one more
+  const int n_more = (int)(slots - (long)c0 * B);
+  if (c0 < 1 || c0 + 1 > kTabCtas || 4 * c0 < nseg) return false;
+  for (int kind = 0; kind < 2; ++kind) {
+    const int ctas = c0 + kind, tiles = 4 * ctas;
+    const int base = tiles / nseg, extra = tiles - base * nseg;     // `extra` segments get base + 1 row tiles
+    if (base + 1 > H) return false;
+    struct T { int seg, y0, y1; } list[4 * kTabCtas];
+    int n = 0;
+    // taller tiles first, then deal round-robin: every CTA gets the same mix of heights
+    for (int pass = 0; pass < 2; ++pass)
+      for (int sg = 0; sg < nseg; ++sg) {
+        const int nt = base + (sg < extra ? 1 : 0);
+        if ((nt == base) != (pass == 0)) continue;
+        for (int k = 0; k < nt; ++k) list[n++] = T{sg, (int)((long)H * k / nt), (int)((long)H * (k + 1) / nt)};
+      }
+    tab.ctas[kind] = ctas;
+    for (int i = 0; i < n; ++i) {
+      const int cta = i % ctas, w = i / ctas;
+      tab.seg[kind][cta][w] = (unsigned char)list[i].seg;
+      tab.y0[kind][cta][w] = (short)list[i].y0;
+      tab.y1[kind][cta][w] = (short)list[i].y1;
+    }
+  }
+  tab.n_more = n_more;
+  tab.on = 1;
+  return true;
+}
+
 static Plan make_plan(const dpft_level_t* lv, int n_levels, int B, int C, uint32_t flags, bool any_occ,
                       int p_grid) {
   Plan pl{};
@@ -721,6 +790,10 @@ static Plan make_plan(const dpft_level_t* lv, int n_levels, int B, int C, uint32
     pl.TR[l] = pick_tile_rows(lv[l].H, pl.nseg[l], B, ((flags & DPFT_STAGED_FOOTPRINT) && staged_ok(lv[l], C)) ? DPFT_STAGED_CTAS : DPFT_MIN_CTAS);
     pl.nrt[l] = (lv[l].H + pl.TR[l] - 1) / pl.TR[l];
     pl.ctas[l] = (pl.nseg[l] * pl.nrt[l] + kWarps - 1) / kWarps;
+    pl.tab[l].on = 0;
+    if ((flags & DPFT_STAGED_FOOTPRINT) && (flags & DPFT_FUSED_SOBEL) && staged_ok(lv[l], C) && lv[l].H < 32768 &&
+        make_tile_tab(lv[l].H, pl.nseg[l], B, pl.tab[l]))
+      pl.ctas[l] = pl.tab[l].ctas[1];   // grid.x and the record stride
     if (pl.ctas[l] > pl.max_ctas) pl.max_ctas = pl.ctas[l];
     const size_t plane = (size_t)lv[l].H * lv[l].W;
     {
@@ -1011,6 +1084,7 @@ static int run_uic(const dpft_level_t* levels, int n_levels, int B, int C, int i
       prm.H = L.H; prm.W = L.W; prm.B = B; prm.C = C; prm.SC = SC;
       prm.nseg = pl.nseg[l]; prm.nrt = pl.nrt[l]; prm.TR = pl.TR[l];
       prm.ctas_per_pair = fused ? pl.ctas[l] : pl.px_ctas[l];
+      prm.tab = pl.tab[l];
       prm.pose = pose_hist + (size_t)k * B * 12;
       prm.pose_next = pose_hist + (size_t)(k + 1) * B * 12;
       prm.sys_out = sys_hist + (size_t)k * B * 27;

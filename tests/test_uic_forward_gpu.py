@@ -221,7 +221,12 @@ def test_full_size_batch_properties():
     perm = torch.randperm(B, generator=torch.Generator().manual_seed(0)).to(DEV)
     lv_p = [{k: v[perm].contiguous() for k, v in lv.items()} for lv in levels]
     r3 = A.uic_solve(lv_p, (pose[0][perm], pose[1][perm]), iters=3, remove_tru_sigma=True, fused_sobel=FUSED, single_launch=SINGLE, staged_footprint=STAGED)
-    assert torch.equal(r3.pose_hist, r1.pose_hist[:, perm])
+    if STAGED:
+        # the balanced tiling gives some pairs one CTA more than others depending on their position in the batch, so
+        # a permuted pair is summed in a different order: equal to rounding instead of bitwise
+        assert (r3.pose_hist - r1.pose_hist[:, perm]).abs().max() < 1e-6
+    else:
+        assert torch.equal(r3.pose_hist, r1.pose_hist[:, perm])
     # no batch coupling without remove_tru_sigma: swapping the batch-mates of the first five pairs for
     # other data leaves their rows bitwise unchanged, and a smaller batch (different tiling, so a
     # different summation order) agrees to rounding
