@@ -444,14 +444,18 @@ def main():
                    "resolution": f"{H}x{W}", "levels": N_LEVELS, "iters_per_level": ITERS, "variant": "U_IC",
                    "remove_tru_sigma": True, "pdl": not args.no_pdl, "streams": max(1, args.streams),
                    "sobel": "fused" if args.fused_sobel else "materialised once per level",
+                   "lookups": "plain loads" if (args.no_staged or not args.fused_sobel) else "footprint staged in shared memory (cp.async ring)",
                    "launch": "single cooperative launch for all levels and iterations" if single else "one launch per iteration",
                    "l2": f"inputs rotate over {N_SETS} resident sets of {set_bytes / 1e6:.0f} MB each (> 126 MB L2)",
                    "algorithmic_bytes_per_step": bytes_step},
         "step_hbm_frac": bytes_step / (ms / args.steps * 1e-3) / 1e9 / peak,
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                     "traffic": 183.8e6 if args.fused_sobel else 328.3e6,
-                     "traffic_source": "ncu --set full dram__bytes_read+write per launch, profiles/r1_uic_iter_kernel_level0.txt (fused) / r1c_* (materialised)",
-                     "kernel": ("uic_iter_kernel<8,true>" if args.fused_sobel else "uic_iter_px_kernel<8,true>") + " at the finest level",
+                     "traffic": (328.3e6 if not args.fused_sobel else 184.0e6 if args.no_staged else 184.1e6)
+                     if args.workload == "tum" else None,
+                     "traffic_source": "ncu --set full dram__bytes_read+write per launch: profiles/r1f_uic_iter_staged_kernel_level0.txt "
+                                       "(staged, default) / r1_uic_iter_kernel_level0.txt (--no-staged) / r1c_* (--materialised)",
+                     "kernel": ("uic_iter_px_kernel<8,true>" if not args.fused_sobel else "uic_iter_kernel<8,true>" if args.no_staged
+                                else "uic_iter_staged_kernel<true,false,160,120>") + " at the finest level",
                      "algorithmic_bytes_per_launch": bytes_lvl0, "launch_ms": lvl0_ms,
                      "all_launch_ms": [round(x, 4) for x in per_launch], "peak_source": peak_src,
                      "how": ("%globaltimer stamps at the iteration boundaries inside the single cooperative launch"
