@@ -402,6 +402,9 @@ __device__ __forceinline__ void process_tile_staged(const PairView& g, const flo
     for (int p = 0; p < NP; ++p) {
       ft[p] = fm[p];
       fm[p] = fb[p];
+    }
+#pragma unroll
+    for (int p = 0; p < NSP; ++p) {
       st[p] = sm[p];
       sm[p] = sb[p];
     }

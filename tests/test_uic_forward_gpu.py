@@ -258,6 +258,16 @@ def test_full_size_vs_oracle():
     assert flips <= total * 1e-5, (flips, total)
     R, t = (x.cpu() for x in res.pose)
     assert (R - pose[0]).abs().max() < TOL_POSE and (t - pose[1]).abs().max() < TOL_POSE
+    # the generator repeats ONE uncertainty map to the C channels, like the reference's encoder: handing that map over
+    # un-repeated (DPFT_SIGMA_BROADCAST) must give the same solve at the full size and with the balanced tiling
+    one = [dict(lv, s0=lv["s0"][:, :1].contiguous(), s1=lv["s1"][:, :1].contiguous()) for lv in data["levels"]]
+    assert all(torch.equal(lv["s0"], o["s0"].expand_as(lv["s0"])) for lv, o in zip(data["levels"], one))
+    res1 = run_cuda(one, (data["R0"], data["t0"]), iters=3, remove_tru_sigma=True)
+    assert torch.equal(res1.occ[0][0], res.occ[0][0])            # same starting pose: bit for bit
+    for i in range(1, 4):                                        # later levels start from poses equal to rounding
+        assert int((res1.occ[i] != res.occ[i]).sum()) <= 5e-5 * res.occ[i].numel(), i
+    assert (res1.pose_hist - res.pose_hist).abs().max() < 1e-6
+    assert frob_rel(res1.sys_hist.cpu(), res.sys_hist.cpu()) < 1e-5
 
 
 def test_module_surface_matches_reference_signature():
