@@ -359,8 +359,10 @@ __global__ void __launch_bounds__(kThreads, DPFT_MIN_CTAS) uic_iter_kernel(const
   // before the dependency sync touches what the previous launch writes
   __shared__ float red[kWarps][NSUM][33];
   __shared__ __align__(16) float s_pose[12];
+  DPFT_STAMP(0, threadIdx.x == 0 && blockIdx.x == 0 && b == 0);
   cudaTriggerProgrammaticLaunchCompletion();
   cudaGridDependencySynchronize();
+  DPFT_STAMP(1, threadIdx.x == 0 && blockIdx.x == 0 && b == 0);
   if (threadIdx.x < 12) s_pose[threadIdx.x] = __ldcg(p.pose + (size_t)b * 12 + threadIdx.x);
   if (TRU) {
     const uint32_t* mm = p.s0mm + ((p.pairwise && !p.kf_shared) ? 2 * b : 0);
@@ -373,6 +375,7 @@ __global__ void __launch_bounds__(kThreads, DPFT_MIN_CTAS) uic_iter_kernel(const
   TileSums S;
   S.reset();
   process_tile<CH, TRU, GW, GH>(g, s_pose, &red[warp][27], seg, y0, y1, lane, S);
+  DPFT_STAMP(2, threadIdx.x == 0 && blockIdx.x == 0 && b == 0);
   reduce_and_finish<TRU>(p, b, red[warp], S.acc, S.vmin, S.vmax, p.ctas_per_pair);
 }
 
