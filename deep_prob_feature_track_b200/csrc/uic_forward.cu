@@ -41,19 +41,27 @@ constexpr int kThreads = kWarps * 32;
 constexpr int kCols = kTileCols;   // output columns per warp tile
 constexpr int kMaxTileRows = 40;
 
+// Warps per CTA of the staged kernel (a tuning hook: 2-warp CTAs make the two kinds of pairs of the balanced tiling
+// differ by 1/13 of their work instead of 1/6, but measured slower).
+#ifndef DPFT_STAGED_WARPS
+#define DPFT_STAGED_WARPS 4
+#endif
+constexpr int kSW = DPFT_STAGED_WARPS;   // warps per CTA of the staged kernel
+constexpr int kSThreads = kSW * 32;
+
 // Balanced tiling of the staged kernel.  With one rectangular tiling for every pair the CTA count is a multiple of
-// B and rarely matches the resident CTA slots (64 pairs x 6 CTAs = 384 of 444: 60 SMs run two CTAs, 88 run three,
-// and the launch lasts as long as the three-CTA SMs).  So the pairs come in two kinds: `n_more` of them (spread
-// evenly over the batch) get one CTA more than the others, and the warp tiles of a kind are listed explicitly --
-// segments split into a different number of row tiles, dealt to the CTAs so that every CTA walks about the same
-// number of rows.  Every slot is filled and every SM gets the same work to within a few rows.
-constexpr int kTabCtas = 8;
+// B and rarely matches the resident CTA slots, and tiles of whole rows per segment rarely divide evenly among the
+// warps.  So (1) the pairs come in two kinds: `n_more` of them (spread evenly over the batch) get one CTA more than
+// the others, and (2) the warp-rows of a pair (segment-major: segment 0 top to bottom, then segment 1, ...) are
+// cut into one contiguous range per warp, every range the same length to within a row.  A range that crosses a
+// segment boundary is walked as two sub-tiles (the second one re-primes its windows and its ring).
+constexpr int kTabWarps = 40;
 struct TileTab {
   int on;                          // 0: rectangular tiling (nseg x nrt tiles of TR rows)
   int n_more;                      // pairs of kind 1
   int ctas[2];                     // CTAs per pair of kind 0 / 1
-  unsigned char seg[2][kTabCtas][4];
-  short y0[2][kTabCtas][4], y1[2][kTabCtas][4];
+  unsigned char seg[2][kTabWarps][2];
+  short y0[2][kTabWarps][2], y1[2][kTabWarps][2];
 };
 
 struct UicIterParams {
@@ -145,16 +153,25 @@ __device__ __forceinline__ void stamp(int i) {
   g_stamps[i] = t;
 }
 #define DPFT_STAMP(i, cond) do { if (cond) stamp(i); } while (0)
+// per-warp timeline of the staged kernel: SM id, start of the tile walk, its end, rows walked
+constexpr int kTimelineWarps = 8192;
+__device__ unsigned long long g_wtl[kTimelineWarps * 4];
+__device__ unsigned long long g_wtl2[kTimelineWarps * 4];
+__device__ __forceinline__ unsigned long long gtimer() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
 #else
 #define DPFT_STAMP(i, cond) do { } while (0)
 #endif
 
-template <bool TRU>
+template <bool TRU, int NW = kWarps>
 __device__ __forceinline__ void reduce_and_finish(const UicIterParams& p, const int b, float (*redw)[33] /* this warp's [NSUM][33] */,
                                                   const float (&acc)[27], const float vmin, const float vmax,
                                                   const int n_ctas /* CTAs of THIS pair; records are spaced by p.ctas_per_pair */) {
-  __shared__ double wsum[kWarps][NSUM + 1];
-  __shared__ float wvmin[kWarps], wvmax[kWarps];
+  __shared__ double wsum[NW][NSUM + 1];
+  __shared__ float wvmin[NW], wvmax[NW];
   __shared__ float s_pair_mm[2];
   __shared__ int s_flag;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -192,7 +209,7 @@ __device__ __forceinline__ void reduce_and_finish(const UicIterParams& p, const 
   float cta_min = CUDART_INF_F, cta_max = -CUDART_INF_F;
   if (TRU) {
 #pragma unroll
-    for (int w = 0; w < kWarps; ++w) {
+    for (int w = 0; w < NW; ++w) {
       cta_min = fminf(cta_min, wvmin[w]);
       cta_max = fmaxf(cta_max, wvmax[w]);
     }
@@ -201,7 +218,7 @@ __device__ __forceinline__ void reduce_and_finish(const UicIterParams& p, const 
     const int e = threadIdx.x;
     double s = 0.0;
 #pragma unroll
-    for (int w = 0; w < kWarps; ++w) {
+    for (int w = 0; w < NW; ++w) {
       bool take = true;
       if (TRU && e >= 27 && e < 33) take = (wvmin[w] == cta_min);
       if (TRU && e >= 33) take = (wvmax[w] == cta_max);
@@ -228,7 +245,7 @@ __device__ __forceinline__ void reduce_and_finish(const UicIterParams& p, const 
   float pair_min = CUDART_INF_F, pair_max = -CUDART_INF_F;
   if (TRU) {
     float a = CUDART_INF_F, c = -CUDART_INF_F;
-    for (int i = threadIdx.x; i < n; i += kThreads) {
+    for (int i = threadIdx.x; i < n; i += (NW * 32)) {
       a = fminf(a, __ldcg(pp + (size_t)i * PS + E_VMIN));
       c = fmaxf(c, __ldcg(pp + (size_t)i * PS + E_VMAX));
     }
@@ -241,7 +258,7 @@ __device__ __forceinline__ void reduce_and_finish(const UicIterParams& p, const 
     }
     __syncthreads();
 #pragma unroll
-    for (int w = 0; w < kWarps; ++w) {
+    for (int w = 0; w < NW; ++w) {
       pair_min = fminf(pair_min, wvmin[w]);
       pair_max = fmaxf(pair_max, wvmax[w]);
     }
@@ -295,7 +312,7 @@ __device__ __forceinline__ void reduce_and_finish(const UicIterParams& p, const 
   __threadfence();
   {
     float a = CUDART_INF_F, c = -CUDART_INF_F;
-    for (int i = threadIdx.x; i < p.B; i += kThreads) {
+    for (int i = threadIdx.x; i < p.B; i += (NW * 32)) {
       a = fminf(a, (float)__ldcg(p.pairrec + (size_t)i * PS + E_VMIN));
       c = fmaxf(c, (float)__ldcg(p.pairrec + (size_t)i * PS + E_VMAX));
     }
@@ -309,7 +326,7 @@ __device__ __forceinline__ void reduce_and_finish(const UicIterParams& p, const 
     if (threadIdx.x == 0) {
       float g0 = CUDART_INF_F, g1 = -CUDART_INF_F;
 #pragma unroll
-      for (int w = 0; w < kWarps; ++w) {
+      for (int w = 0; w < NW; ++w) {
         g0 = fminf(g0, wvmin[w]);
         g1 = fmaxf(g1, wvmax[w]);
       }
@@ -324,12 +341,12 @@ __device__ __forceinline__ void reduce_and_finish(const UicIterParams& p, const 
     __syncthreads();
   }
   DPFT_STAMP(6, threadIdx.x == 0);                                // grid-last CTA: extremes known
-  for (int i = threadIdx.x; i < p.B; i += kThreads) finalize_pair<true>(p, i, s_pair_mm[0], s_pair_mm[1]);
+  for (int i = threadIdx.x; i < p.B; i += (NW * 32)) finalize_pair<true>(p, i, s_pair_mm[0], s_pair_mm[1]);
   DPFT_STAMP(7, threadIdx.x == 0);                                // all solves written
 }
 
 template <int CH, bool TRU, int GW = 0, int GH = 0>
-__global__ void __launch_bounds__(kThreads, DPFT_MIN_CTAS) uic_iter_kernel(const UicIterParams p) {
+__global__ void __launch_bounds__(kThreads, DPFT_MIN_CTAS) uic_iter_kernel(const __grid_constant__ UicIterParams p) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int b = blockIdx.y;
   const int plane = (GW > 0) ? GW * GH : p.H * p.W;
@@ -383,32 +400,37 @@ __global__ void __launch_bounds__(kThreads, DPFT_MIN_CTAS) uic_iter_kernel(const
 // every warp owns kStageAreaFloats of dynamic shared memory: its ring of source rows, then the 12 correction
 // rows of remove_tru_sigma; the 27 rows of the final reduction overlay the tail of the ring once the tile is done.
 #ifndef DPFT_STAGED_CTAS
-#define DPFT_STAGED_CTAS 3
+#define DPFT_STAGED_CTAS (12 / DPFT_STAGED_WARPS)
 #endif
-constexpr int kStageAreaFloats = (kStageWarpFloats + 12 * 33 + 3) / 4 * 4;
+constexpr int kStageAreaFloats = (kStageWarpFloats + 12 * 33 + kOutFloats + 3) / 4 * 4;   // ring | corrections | outlier taps
 static_assert(kStageWarpFloats >= 27 * 33, "the reduction rows overlay the ring");
-template <bool TRU, bool SB = false, int GW = 0, int GH = 0>
-__global__ void __launch_bounds__(kThreads, DPFT_STAGED_CTAS) uic_iter_staged_kernel(const UicIterParams p) {
+template <bool TRU, bool SB = false, int GW = 0, int GH = 0, bool AUX = true>
+__global__ void __launch_bounds__(kSThreads, DPFT_STAGED_CTAS) uic_iter_staged_kernel(const __grid_constant__ UicIterParams p) {
   extern __shared__ __align__(16) float dyn_stage[];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int b = blockIdx.y;
   const int plane = (GW > 0) ? GW * GH : p.H * p.W;
-  int seg, y0, y1, n_ctas = p.ctas_per_pair;
+  int seg[2], y0[2], y1[2], n_ctas = p.ctas_per_pair;
   if (p.tab.on) {
     // kind 1 pairs are spread evenly over the batch (Bresenham)
     const int kind = (int)(((long)(b + 1) * p.tab.n_more) / p.B - ((long)b * p.tab.n_more) / p.B);
     n_ctas = p.tab.ctas[kind];
     if ((int)blockIdx.x >= n_ctas) return;
-    seg = p.tab.seg[kind][blockIdx.x][warp];
-    y0 = p.tab.y0[kind][blockIdx.x][warp];
-    y1 = p.tab.y1[kind][blockIdx.x][warp];
+    const int w = blockIdx.x * kSW + warp;
+#pragma unroll
+    for (int k = 0; k < 2; ++k) {
+      seg[k] = p.tab.seg[kind][w][k];
+      y0[k] = p.tab.y0[kind][w][k];
+      y1[k] = p.tab.y1[kind][w][k];
+    }
   } else {
-    const int wt = blockIdx.x * kWarps + warp;
+    const int wt = blockIdx.x * kSW + warp;
     const bool warp_on = wt < p.nseg * p.nrt;
-    seg = warp_on ? wt % p.nseg : 0;
+    seg[0] = warp_on ? wt % p.nseg : 0;
     const int rt = warp_on ? wt / p.nseg : 0;
-    y0 = rt * p.TR;
-    y1 = warp_on ? min(y0 + p.TR, p.H) : y0;
+    y0[0] = rt * p.TR;
+    y1[0] = warp_on ? min(y0[0] + p.TR, p.H) : y0[0];
+    seg[1] = y0[1] = y1[1] = 0;
   }
 
   PairView g;
@@ -444,10 +466,36 @@ __global__ void __launch_bounds__(kThreads, DPFT_STAGED_CTAS) uic_iter_staged_ke
   __syncthreads();
   TileSums S;
   S.reset();
-  if (y1 > y0) process_tile_staged<TRU, SB, GW, GH>(g, s_pose, redw + 27, area, seg, y0, y1, lane, S);
+#ifdef DPFT_DEBUG_STAMPS
+  const unsigned long long wt0 = gtimer();
+#endif
+#pragma unroll 1
+  for (int k = 0; k < 2; ++k) {
+    const int sg = k ? seg[1] : seg[0], ya = k ? y0[1] : y0[0], yb = k ? y1[1] : y1[0];
+    if (yb > ya) process_tile_staged<TRU, SB, GW, GH, AUX>(g, s_pose, redw + 27, area, area + kStageWarpFloats + 12 * 33, sg, ya, yb, lane, S);
+  }
   __syncwarp();
+#ifdef DPFT_DEBUG_STAMPS
+  {
+    const int wi = (b * (int)gridDim.x + (int)blockIdx.x) * kSW + warp;
+    if (lane == 0 && wi < kTimelineWarps) {
+      unsigned smid;
+      asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+      g_wtl[4 * wi] = smid | ((unsigned long long)S.nrestart << 32) | ((unsigned long long)S.nlanes << 40);
+      g_wtl[4 * wi + 1] = wt0;
+      g_wtl[4 * wi + 2] = gtimer();
+      g_wtl2[4 * wi] = (unsigned long long)S.c_front;
+      g_wtl2[4 * wi + 1] = (unsigned long long)S.c_wait;
+      g_wtl2[4 * wi + 2] = (unsigned long long)S.c_body;
+      g_wtl2[4 * wi + 3] = (unsigned long long)S.nstaged | ((unsigned long long)S.ntru << 32);
+      g_wtl[4 * wi + 3] = (unsigned long long)((y1[0] - y0[0]) + (y1[1] - y0[1])) | ((unsigned long long)(y1[1] > y0[1]) << 16) |
+                          ((unsigned long long)seg[0] << 24) | ((unsigned long long)y0[0] << 32) |
+                          ((unsigned long long)S.ndirect << 48);
+    }
+  }
+#endif
   DPFT_STAMP(2, threadIdx.x == 0 && blockIdx.x == 0 && b == 0);   // tile walked
-  reduce_and_finish<TRU>(p, b, redw, S.acc, S.vmin, S.vmax, n_ctas);
+  reduce_and_finish<TRU, kSW>(p, b, redw, S.acc, S.vmin, S.vmax, n_ctas);
 }
 
 // =========================================================================== materialised-gradient path
@@ -488,7 +536,7 @@ struct PxExtra {
 };
 
 template <int CH, bool TRU>
-__global__ void __launch_bounds__(kThreads, 4) uic_iter_px_kernel(const UicIterParams p, const PxExtra e) {
+__global__ void __launch_bounds__(kThreads, 4) uic_iter_px_kernel(const __grid_constant__ UicIterParams p, const PxExtra e) {
   const int b = blockIdx.y;
   const int H = p.H, W = p.W, C = p.C;
   const int iplane = H * W;
@@ -722,14 +770,14 @@ struct Plan {
 // Rows per warp tile.  A tile is walked row by row by one warp, so the time of a launch is about
 // (waves of CTAs) x (rows per tile + ~1.5 rows of window priming and reduction tail): pick the height that
 // minimises that, i.e. fill whole waves of the 148 x DPFT_MIN_CTAS resident CTAs.
-static int pick_tile_rows(int H, int nseg, int B, int ctas_per_sm) {
+static int pick_tile_rows(int H, int nseg, int B, int ctas_per_sm, int warps) {
   long slots = 148L * ctas_per_sm;
   if (const char* e = getenv("DPFT_CTA_SLOTS")) slots = std::max(1L, atol(e));   // tuning hook
   int best_tr = 1;
   double best = 1e30;
   for (int tr = 1; tr <= kMaxTileRows; ++tr) {
     const long nrt = (H + tr - 1) / tr;
-    const long ctas = ((nrt * nseg + kWarps - 1) / kWarps) * B;
+    const long ctas = ((nrt * nseg + warps - 1) / warps) * B;
     const long waves = (ctas + slots - 1) / slots;
     const double cost = (double)waves * (tr + 1.5);
     if (cost < best - 1e-9) { best = cost; best_tr = tr; }
@@ -743,11 +791,54 @@ static bool staged_ok(const dpft_level_t& L, int C) {
   return C == 8 && L.W % 4 == 0 && L.W >= 2 * kTileCols && L.H >= kStageRows && al(L.x1) && al(L.sigma1) && al(L.invd1);
 }
 
-// Balanced tile table of one level (see TileTab).  Returns false when the rectangular tiling should stay (the
-// table holds at most kTabCtas CTAs per pair, and a pair needs at least one tile per segment).
-static bool make_tile_tab(int H, int nseg, int B, TileTab& tab) {
+// Linear variant of the balanced tile table (DPFT_LINEAR_TILES=1; see TileTab).  Returns false when the rectangular tiling should stay (the
+// table holds at most kTabWarps warps per pair, and a warp's range may cross one segment boundary at most).
+static bool make_tile_tab_linear(int H, int nseg, int B, TileTab& tab) {
   tab = TileTab{};
-  if (kWarps != 4) return false;
+  // 35/37 of the resident slots: filling every slot makes a lone launch ~3 % shorter still, but then the small
+  // launches of OTHER streams (coarse levels of independent batches) find no free slot and the multi-stream
+  // throughput drops by 5 % (profiles/exp9.sh)
+  long slots = 148L * DPFT_STAGED_CTAS * 35 / 37;
+  if (const char* e = getenv("DPFT_CTA_SLOTS")) slots = std::max(1L, atol(e));
+  if (getenv("DPFT_RECT_TILES")) return false;
+  const int c0 = (int)(slots / B);               // CTAs per pair of kind 0; kind 1 has one more
+  const int n_more = (int)(slots - (long)c0 * B);
+  if (c0 < 1 || (c0 + 1) * kSW > kTabWarps || c0 * kSW < nseg + 1) return false;
+  const long R = (long)nseg * H;                 // warp-rows of a pair
+  for (int kind = 0; kind < 2; ++kind) {
+    const int ctas = c0 + kind, nw = ctas * kSW;
+    // range ends, snapped to a segment boundary when they fall within two rows of one (no 1- or 2-row sub-tiles)
+    auto bound = [&](int w) {
+      long e = R * w / nw;
+      const long r = e % H;
+      if (r <= 2) e -= r;
+      else if (r >= H - 2) e += H - r;
+      return e;
+    };
+    tab.ctas[kind] = ctas;
+    for (int w = 0; w < nw; ++w) {
+      const long s = bound(w), e = bound(w + 1);
+      const long sa = s / H, cut = std::min(e, (sa + 1) * H);
+      if (e > (sa + 2) * H) return false;
+      tab.seg[kind][w][0] = (unsigned char)sa;
+      tab.y0[kind][w][0] = (short)(s - sa * H);
+      tab.y1[kind][w][0] = (short)(cut - sa * H);
+      tab.seg[kind][w][1] = (unsigned char)std::min<long>(sa + 1, nseg - 1);
+      tab.y0[kind][w][1] = 0;
+      tab.y1[kind][w][1] = (short)(e - cut);
+    }
+  }
+  tab.n_more = n_more;
+  tab.on = 1;
+  return true;
+}
+
+// Balanced tile table of one level (see TileTab), the default: every segment is cut into whole row tiles (some
+// segments into one tile more than the others), taller tiles first, dealt round-robin to the CTAs so that every CTA
+// gets the same mix of heights.  Returns false when the rectangular tiling should stay.
+static bool make_tile_tab(int H, int nseg, int B, TileTab& tab) {
+  if (getenv("DPFT_LINEAR_TILES") || kSW != 4) return make_tile_tab_linear(H, nseg, B, tab);
+  tab = TileTab{};
   // 420 of the 444 resident slots: filling every slot makes a lone launch ~3 % shorter still, but then the small
   // launches of OTHER streams (coarse levels of independent batches) find no free slot and the multi-stream
   // throughput drops by 5 % (profiles/exp9.sh)
@@ -756,12 +847,12 @@ static bool make_tile_tab(int H, int nseg, int B, TileTab& tab) {
   if (getenv("DPFT_RECT_TILES")) return false;
   const int c0 = (int)(slots / B);               // CTAs per pair of kind 0; kind 1 has one more
   const int n_more = (int)(slots - (long)c0 * B);
-  if (c0 < 1 || c0 + 1 > kTabCtas || 4 * c0 < nseg) return false;
+  if (c0 < 1 || (c0 + 1) * kSW > kTabWarps || kSW * c0 < nseg) return false;
   for (int kind = 0; kind < 2; ++kind) {
-    const int ctas = c0 + kind, tiles = 4 * ctas;
+    const int ctas = c0 + kind, tiles = kSW * ctas;
     const int base = tiles / nseg, extra = tiles - base * nseg;     // `extra` segments get base + 1 row tiles
     if (base + 1 > H) return false;
-    struct T { int seg, y0, y1; } list[4 * kTabCtas];
+    struct T { int seg, y0, y1; } list[kTabWarps];
     int n = 0;
     // taller tiles first, then deal round-robin: every CTA gets the same mix of heights
     for (int pass = 0; pass < 2; ++pass)
@@ -772,10 +863,10 @@ static bool make_tile_tab(int H, int nseg, int B, TileTab& tab) {
       }
     tab.ctas[kind] = ctas;
     for (int i = 0; i < n; ++i) {
-      const int cta = i % ctas, w = i / ctas;
-      tab.seg[kind][cta][w] = (unsigned char)list[i].seg;
-      tab.y0[kind][cta][w] = (short)list[i].y0;
-      tab.y1[kind][cta][w] = (short)list[i].y1;
+      const int w = (i % ctas) * kSW + i / ctas;       // CTA i % ctas, warp i / ctas
+      tab.seg[kind][w][0] = (unsigned char)list[i].seg;
+      tab.y0[kind][w][0] = (short)list[i].y0;
+      tab.y1[kind][w][0] = (short)list[i].y1;
     }
   }
   tab.n_more = n_more;
@@ -790,9 +881,11 @@ static Plan make_plan(const dpft_level_t* lv, int n_levels, int B, int C, uint32
   pl.max_plane = 0;
   for (int l = 0; l < n_levels; ++l) {
     pl.nseg[l] = (lv[l].W + kCols - 1) / kCols;
-    pl.TR[l] = pick_tile_rows(lv[l].H, pl.nseg[l], B, ((flags & DPFT_STAGED_FOOTPRINT) && staged_ok(lv[l], C)) ? DPFT_STAGED_CTAS : DPFT_MIN_CTAS);
+    const bool staged = (flags & DPFT_STAGED_FOOTPRINT) && (flags & DPFT_FUSED_SOBEL) && staged_ok(lv[l], C);
+    const int cta_warps = staged ? kSW : kWarps;
+    pl.TR[l] = pick_tile_rows(lv[l].H, pl.nseg[l], B, staged ? DPFT_STAGED_CTAS : DPFT_MIN_CTAS, cta_warps);
     pl.nrt[l] = (lv[l].H + pl.TR[l] - 1) / pl.TR[l];
-    pl.ctas[l] = (pl.nseg[l] * pl.nrt[l] + kWarps - 1) / kWarps;
+    pl.ctas[l] = (pl.nseg[l] * pl.nrt[l] + cta_warps - 1) / cta_warps;
     pl.tab[l].on = 0;
     if ((flags & DPFT_STAGED_FOOTPRINT) && (flags & DPFT_FUSED_SOBEL) && staged_ok(lv[l], C) && lv[l].H < 32768 &&
         make_tile_tab(lv[l].H, pl.nseg[l], B, pl.tab[l]))
@@ -895,10 +988,10 @@ static cudaError_t launch_iter(const UicIterParams& prm, dim3 grid, bool tru, bo
 }
 
 static cudaError_t launch_staged(const UicIterParams& prm, dim3 grid, bool tru, bool pdl, cudaStream_t stream) {
-  constexpr int smem = kWarps * kStageAreaFloats * (int)sizeof(float);
+  constexpr int smem = kSW * kStageAreaFloats * (int)sizeof(float);
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = grid;
-  cfg.blockDim = dim3(kThreads);
+  cfg.blockDim = dim3(kSThreads);
   cfg.dynamicSmemBytes = smem;
   cfg.stream = stream;
   cudaLaunchAttribute attr[1];
@@ -907,12 +1000,19 @@ static cudaError_t launch_staged(const UicIterParams& prm, dim3 grid, bool tru, 
   cfg.attrs = attr;
   cfg.numAttrs = pdl ? 1 : 0;
   // (cudaFuncSetAttribute is per device and cheap: set it on every launch rather than caching per process)
-#define DPFT_STAGED(TRUV, SBV, w, h)                                                                         \
+#define DPFT_STAGED_A(TRUV, SBV, w, h, AUXV)                                                                 \
   do {                                                                                                       \
-    auto* fn = uic_iter_staged_kernel<TRUV, SBV, w, h>;                                                      \
+    auto* fn = uic_iter_staged_kernel<TRUV, SBV, w, h, AUXV>;                                                \
     cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);                             \
     return cudaLaunchKernelEx(&cfg, fn, prm);                                                                \
   } while (0)
+  // object masks and per-pixel debug outputs are compiled out of the instantiations that run without them
+#define DPFT_STAGED(TRUV, SBV, w, h)                                                                         \
+  do {                                                                                                       \
+    if (aux) DPFT_STAGED_A(TRUV, SBV, w, h, true);                                                           \
+    DPFT_STAGED_A(TRUV, SBV, w, h, false);                                                                   \
+  } while (0)
+  const bool aux = prm.m0 || prm.m1 || prm.occ_out;
   const bool sb = prm.SC != prm.C;
   if (!getenv("DPFT_GENERIC_GEOMETRY")) {
     if (prm.W == 160 && prm.H == 120) {
@@ -924,6 +1024,7 @@ static cudaError_t launch_staged(const UicIterParams& prm, dim3 grid, bool tru, 
   if (sb) { if (tru) DPFT_STAGED(true, true, 0, 0); else DPFT_STAGED(false, true, 0, 0); }
   if (tru) DPFT_STAGED(true, false, 0, 0);
   DPFT_STAGED(false, false, 0, 0);
+#undef DPFT_STAGED_A
 #undef DPFT_STAGED
 }
 
@@ -1173,6 +1274,12 @@ extern "C" int dpft_uic_forward_timed(const dpft_level_t* levels, int n_levels, 
 }
 
 #ifdef DPFT_DEBUG_STAMPS
+extern "C" int dpft_debug_read_phases(unsigned long long* host, int n_warps) {
+  return (int)cudaMemcpyFromSymbol(host, dpft::g_wtl2, sizeof(unsigned long long) * 4 * (size_t)n_warps);
+}
+extern "C" int dpft_debug_read_timeline(unsigned long long* host, int n_warps) {
+  return (int)cudaMemcpyFromSymbol(host, dpft::g_wtl, sizeof(unsigned long long) * 4 * (size_t)n_warps);
+}
 extern "C" int dpft_debug_read_stamps(unsigned long long* host16) {
   return (int)cudaMemcpyFromSymbol(host16, dpft::g_stamps, sizeof(unsigned long long) * 16);
 }

@@ -30,6 +30,12 @@ struct PairView {               // one frame pair of one level, pointers already
 struct TileSums {
   float acc[27];                // 21 upper-triangular J^T J entries, 6 J^T r entries
   float vmin, vmax;             // running extremes of the warped sigma (their corrections live in shared memory)
+#ifdef DPFT_DEBUG_STAMPS
+  int ndirect = 0;              // rows of the staged routine that took the direct-load body
+  int nrestart = 0, nlanes = 0; // ring restarts; lanes (summed over rows) whose footprint was not resident
+  int nstaged = 0, ntru = 0;    // source rows staged; rows that took the sigma-extreme bookkeeping branch
+  long long c_front = 0, c_wait = 0, c_body = 0;   // clock cycles: geometry + ring logic | waiting for the ring | the rest of the row
+#endif
   __device__ __forceinline__ void reset() {
 #pragma unroll
     for (int i = 0; i < 27; ++i) acc[i] = 0.f;

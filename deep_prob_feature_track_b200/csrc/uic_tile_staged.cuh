@@ -32,9 +32,15 @@ constexpr int kStageLookahead = 2;   // source rows requested ahead of the row b
 // columns) then never share a bank
 constexpr int kStageSlotFloats = (kStageMaps * kStageWidth + 31) / 32 * 32;
 constexpr int kStageWarpFloats = kStageRows * kStageSlotFloats + 32;   // + x origin of each slot (as int)
+// lanes of a row whose footprint is not resident park their own 17 x 4 taps here (see the direct-load body)
+constexpr int kOutLanes = 4;
+constexpr int kOutFloats = kOutLanes * kStageMaps * 4;
 
 __device__ __forceinline__ void cp_async16(unsigned smem_addr, const float* g) {
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_addr), "l"(g) : "memory");
+}
+__device__ __forceinline__ void cp_async4(unsigned smem_addr, const float* g) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_addr), "l"(g) : "memory");
 }
 __device__ __forceinline__ void stage_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void stage_wait(int pending) {
@@ -77,9 +83,11 @@ __device__ __forceinline__ TapXY make_tap_xy(float u, float v, int H, int W, flo
 // repeats it to C channels (algorithms.py:1425-1427, uncertainty_channel = 1 in every shipped configuration).  The
 // map is staged, looked up, blended and differentiated once per pixel instead of once per channel; the results
 // are those of the repeated tensor.
-template <bool TRU, bool SB = false, int GW = 0, int GH = 0>
+// AUX: object masks and / or the per-pixel debug outputs may be present (their tests are compiled out otherwise).
+template <bool TRU, bool SB = false, int GW = 0, int GH = 0, bool AUX = true>
 __device__ __forceinline__ void process_tile_staged(const PairView& g, const float* spose, float (*scorr)[33],
-                                                    float* ring /* kStageWarpFloats of this warp */, const int seg,
+                                                    float* ring /* kStageWarpFloats of this warp */,
+                                                    float* outl /* kOutFloats of this warp */, const int seg,
                                                     const int y0, const int y1, const int lane, TileSums& S) {
   constexpr int CH = 8;
   constexpr bool FIXED = GW > 0 && GH > 0;
@@ -176,6 +184,10 @@ __device__ __forceinline__ void process_tile_staged(const PairView& g, const flo
   float d0_next = (y0 < y1) ? __ldg(g.d0 + (unsigned)(y0 * W + xc)) : 0.f;
 
   for (int y = y0; y < y1; ++y) {
+#ifdef DPFT_DEBUG_STAMPS
+    const long long ck0 = clock64();
+    long long ck1 = ck0, ck2 = ck0;
+#endif
     const unsigned ob = (unsigned)(min(y + 1, H - 1) * W + xc);
     float2 fb[NP], sb[NSP];
 #pragma unroll
@@ -212,6 +224,9 @@ __device__ __forceinline__ void process_tile_staged(const PairView& g, const flo
     int ready_top = top;
     if (yhi >= 0) {
       if (ylo > top + 1 || ylo < base - 2) {            // a jump in the warp field: restart the ring at ylo
+#ifdef DPFT_DEBUG_STAMPS
+        S.nrestart += 1;
+#endif
         top = ylo - 1;
         base = ylo;
       }
@@ -220,10 +235,21 @@ __device__ __forceinline__ void process_tile_staged(const PairView& g, const flo
       const int xs = min(max((xlo - (SW - 32) / 2) & ~3, 0), W - SW);
       __syncwarp();                                                      // every lane is done with the old slots
 #pragma unroll 1
-      while (top < target) stage_row(++top, xs);
+      while (top < target) {
+        stage_row(++top, xs);
+#ifdef DPFT_DEBUG_STAMPS
+        S.nstaged += 1;
+#endif
+      }
       ready_top = min(yhi, top);
+#ifdef DPFT_DEBUG_STAMPS
+      ck1 = clock64();
+#endif
       stage_wait(top - ready_top);
       __syncwarp();
+#ifdef DPFT_DEBUG_STAMPS
+      ck2 = clock64();
+#endif
     }
     const int lowest = max(base, top - (kStageRows - 1));
     const int s0i = txy.yi & (kStageRows - 1), s1i = (txy.yi + 1) & (kStageRows - 1);
@@ -231,23 +257,77 @@ __device__ __forceinline__ void process_tile_staged(const PairView& g, const flo
     const bool resident = txy.yi >= lowest && txy.yi + 1 <= ready_top && txy.xi >= xs0 && txy.xi + 1 < xs0 + SW &&
                           txy.xi >= xs1 && txy.xi + 1 < xs1 + SW;
     const bool any_direct = __any_sync(0xffffffffu, col_out && !resident);
+#ifdef DPFT_DEBUG_STAMPS
+    S.ndirect += any_direct ? 1 : 0;
+    S.nlanes += __popc(__ballot_sync(0xffffffffu, col_out && !resident));
+#endif
     // north-west / south-west texel of map 0 in the ring (kept in range for lanes that are not resident)
     const float* a0 = ring + s0i * kStageSlotFloats + min(max(txy.xi - xs0, 0), SW - 2);
     const float* a1 = ring + s1i * kStageSlotFloats + min(max(txy.xi - xs1, 0), SW - 2);
 
+    // The rest of the row exists twice: the copy that runs when every lane's footprint is resident has no
+    // lane-divergent code at all (one basic block from the first tap to the accumulation, which is what lets the
+    // scheduler interleave the channel groups), the other one adds the per-lane direct loads.
+#ifdef DPFT_STAGED_ONE_BODY
+    constexpr int kBodies = 1;
+#else
+    constexpr int kBodies = 2;
+#endif
+#pragma unroll
+    for (int body = 0; body < kBodies; ++body) {
+    if (kBodies == 2 && (body == 1) != any_direct) continue;
+    const bool DIRECT = kBodies == 1 ? any_direct : (body == 1);
+    // A lane whose footprint is not resident (a pixel whose depth differs from its neighbours': a hole, an object
+    // edge) reads its 68 taps from global memory.  Read as they are needed they cost three dependent round trips
+    // (depth, channels 0-3, channels 4-7), and the warps that meet many such pixels were the stragglers every
+    // launch waited for.  So the first kOutLanes such lanes of a row copy all their taps into a small scratch area
+    // with 4-byte cp.async -- no registers, everything in flight at once, one round trip -- and then read them
+    // like everybody else, through a per-lane base and map stride; only the overflow takes the dependent loads.
+    // Lanes outside the tile's columns never need real values (their sums are discarded): they read the ring
+    // wherever their clamped offsets point.
+    const float *b0 = a0, *b1 = a1;     // north / south texel row of map 0 for this lane
+    int ms = SW;                        // floats between maps
+    bool slow = false;                  // overflow: dependent direct loads
+    if (DIRECT) {
+      const bool need = col_out && !resident;
+      const int rank = __popc(__ballot_sync(0xffffffffu, need) & ((1u << lane) - 1u));
+      const bool parked = need && rank < kOutLanes;
+      slow = need && !parked;
+      if (parked) {
+        float* sc = outl + rank * (kStageMaps * 4);
+        const unsigned sc_s = (unsigned)__cvta_generic_to_shared(sc);
+#pragma unroll
+        for (int m = 0; m < kStageMaps; ++m) {
+          if (SB && m > CH && m < 2 * CH) continue;      // one sigma map: slot CH
+          const float* src = (m < CH) ? X1 + (unsigned)tap.o + (unsigned)m * iplane
+                           : (m < 2 * CH) ? S1 + (unsigned)tap.o + (SB ? 0u : (unsigned)(m - CH) * iplane)
+                                          : g.d1 + tap.o;
+          cp_async4(sc_s + 16u * m, src);
+          cp_async4(sc_s + 16u * m + 4u, src + 1);
+          cp_async4(sc_s + 16u * m + 8u, src + W);
+          cp_async4(sc_s + 16u * m + 12u, src + W + 1);
+        }
+        b0 = sc;
+        b1 = sc + 2;
+        ms = 4;
+      }
+      stage_commit();
+      stage_wait(0);
+      __syncwarp();
+    }
     float d1w;
     {
-      float da = a0[2 * CH * SW], db = a0[2 * CH * SW + 1];
-      float dc = a1[2 * CH * SW], dd = a1[2 * CH * SW + 1];
-      if (any_direct && !resident) {
+      float da = b0[2 * CH * ms], db = b0[2 * CH * ms + 1];
+      float dc = b1[2 * CH * ms], dd = b1[2 * CH * ms + 1];
+      if (DIRECT && slow) {
         const float* q = g.d1 + tap.o;
         da = __ldg(q); db = __ldg(q + 1); dc = __ldg(q + W); dd = __ldg(q + W + 1);
       }
       d1w = blend_exact(da, db, dc, dd, tap);
     }
     bool occ = occluded(u, v, inv_z, d1w, H, W);
-    if (g.m0) occ = occ || (__ldg(g.m0 + o) == 0);
-    if (g.m1) occ = occ || !(sample_mask(g.m1, tap, W) > 0.f);
+    if (AUX && g.m0) occ = occ || (__ldg(g.m0 + o) == 0);
+    if (AUX && g.m1) occ = occ || !(sample_mask(g.m1, tap, W) > 0.f);
     if (TRU) occ = occ || (sm[0].x == g.s0lo) || (sm[0].x == g.s0hi);
 
     const float2 zero2 = make_float2(0.f, 0.f), two2 = make_float2(2.f, 2.f), neg1 = make_float2(-1.f, -1.f);
@@ -277,8 +357,8 @@ __device__ __forceinline__ void process_tile_staged(const PairView& g, const flo
     if (SB) {
       float2 gx1, gy1;
       unit_sobel(st[0], sm[0], sb[0], gx1, gy1);
-      float za = a0[CH * SW], zb = a0[CH * SW + 1], zc = a1[CH * SW], zd = a1[CH * SW + 1];
-      if (any_direct && !resident) {
+      float za = b0[CH * ms], zb = b0[CH * ms + 1], zc = b1[CH * ms], zd = b1[CH * ms + 1];
+      if (DIRECT && slow) {
         const float* q = S1 + tap.o;
         za = __ldg(q); zb = __ldg(q + 1); zc = __ldg(q + W); zd = __ldg(q + W + 1);
       }
@@ -296,15 +376,15 @@ __device__ __forceinline__ void process_tile_staged(const PairView& g, const flo
       float2 xa[GP], xb[GP], xc_[GP], xd[GP], za[GP], zb[GP], zc[GP], zd[GP];
 #pragma unroll
       for (int j = 0; j < GP; ++j) {
-        const int kx = 2 * (p0 + j) * SW, kz = (CH + 2 * (p0 + j)) * SW;
-        xa[j] = make_float2(a0[kx], a0[kx + SW]); xb[j] = make_float2(a0[kx + 1], a0[kx + SW + 1]);
-        xc_[j] = make_float2(a1[kx], a1[kx + SW]); xd[j] = make_float2(a1[kx + 1], a1[kx + SW + 1]);
+        const int kx = 2 * (p0 + j) * ms, kz = (CH + 2 * (p0 + j)) * ms;
+        xa[j] = make_float2(b0[kx], b0[kx + ms]); xb[j] = make_float2(b0[kx + 1], b0[kx + ms + 1]);
+        xc_[j] = make_float2(b1[kx], b1[kx + ms]); xd[j] = make_float2(b1[kx + 1], b1[kx + ms + 1]);
         if (!SB) {
-          za[j] = make_float2(a0[kz], a0[kz + SW]); zb[j] = make_float2(a0[kz + 1], a0[kz + SW + 1]);
-          zc[j] = make_float2(a1[kz], a1[kz + SW]); zd[j] = make_float2(a1[kz + 1], a1[kz + SW + 1]);
+          za[j] = make_float2(b0[kz], b0[kz + ms]); zb[j] = make_float2(b0[kz + 1], b0[kz + ms + 1]);
+          zc[j] = make_float2(b1[kz], b1[kz + ms]); zd[j] = make_float2(b1[kz + 1], b1[kz + ms + 1]);
         }
       }
-      if (any_direct && !resident) {
+      if (DIRECT && slow) {
 #pragma unroll
         for (int j = 0; j < GP; ++j) {
           const unsigned ia = (unsigned)tap.o + (unsigned)(2 * (p0 + j)) * iplane, ic = ia + Wu;
@@ -381,23 +461,44 @@ __device__ __forceinline__ void process_tile_staged(const PairView& g, const flo
       const bool lo = wmin < S.vmin, hi = wmax > S.vmax;
       const float nmin = lo ? wmin : S.vmin, nmax = hi ? wmax : S.vmax;
       const bool tmin = col_out && !occ && (sr0 == nmin), tmax = col_out && !occ && (sr0 == nmax);
-      if (lo || hi || __any_sync(0xffffffffu, tmin || tmax)) {
+      const bool any_min = lo || __any_sync(0xffffffffu, tmin), any_max = hi || __any_sync(0xffffffffu, tmax);
+      if (any_min || any_max) {
+#ifdef DPFT_DEBUG_STAMPS
+        S.ntru += 1;
+#endif
         S.vmin = nmin;
         S.vmax = nmax;
+        float cc[6];
 #pragma unroll
         for (int i = 0; i < 6; ++i) {
-          float cc = 0.f;
-          if (i != 4) cc = fmaf(sca, ju[i], cc);
-          if (i != 3) cc = fmaf(scb, jv[i], cc);
-          if (lo || tmin) scorr[i][lane] = (lo ? 0.f : scorr[i][lane]) + (tmin ? cc : 0.f);
-          if (hi || tmax) scorr[6 + i][lane] = (hi ? 0.f : scorr[6 + i][lane]) + (tmax ? cc : 0.f);
+          cc[i] = 0.f;
+          if (i != 4) cc[i] = fmaf(sca, ju[i], cc[i]);
+          if (i != 3) cc[i] = fmaf(scb, jv[i], cc[i]);
+        }
+        // every lane rewrites its column (no per-lane branches): a new extreme restarts the sums
+        if (any_min) {
+#pragma unroll
+          for (int i = 0; i < 6; ++i) scorr[i][lane] = (lo ? 0.f : scorr[i][lane]) + (tmin ? cc[i] : 0.f);
+        }
+        if (any_max) {
+#pragma unroll
+          for (int i = 0; i < 6; ++i) scorr[6 + i][lane] = (hi ? 0.f : scorr[6 + i][lane]) + (tmax ? cc[i] : 0.f);
         }
       }
     }
-    if (g.occ_out && col_out) {
+    if (AUX && g.occ_out && col_out) {
       g.occ_out[(size_t)y * W + x] = occ ? 1 : 0;
       if (TRU) g.sr0_dbg[(size_t)y * W + x] = sr0;
     }
+    }   // body
+#ifdef DPFT_DEBUG_STAMPS
+    {
+      const long long ck3 = clock64();
+      S.c_front += ck1 - ck0;
+      S.c_wait += ck2 - ck1;
+      S.c_body += ck3 - ck2;
+    }
+#endif
 #pragma unroll
     for (int p = 0; p < NP; ++p) {
       ft[p] = fm[p];
