@@ -402,7 +402,8 @@ __global__ void __launch_bounds__(kThreads, DPFT_MIN_CTAS) uic_iter_kernel(const
 #ifndef DPFT_STAGED_CTAS
 #define DPFT_STAGED_CTAS (12 / DPFT_STAGED_WARPS)
 #endif
-constexpr int kStageAreaFloats = (kStageWarpFloats + 12 * 33 + kOutFloats + 3) / 4 * 4;   // ring | corrections | outlier taps
+constexpr int kStageAreaFloats = (kStageWarpFloats + 12 * 33 + kOutFloats + kHaloFloats + 3) / 4 * 4;   // ring | corrections | outlier taps | halo sums
+static_assert((kStageWarpFloats + 12 * 33 + kOutFloats) % 4 == 0, "the halo sums are read as float4");
 static_assert(kStageWarpFloats >= 27 * 33, "the reduction rows overlay the ring");
 template <bool TRU, bool SB = false, int GW = 0, int GH = 0, bool AUX = true>
 __global__ void __launch_bounds__(kSThreads, DPFT_STAGED_CTAS) uic_iter_staged_kernel(const __grid_constant__ UicIterParams p) {
@@ -880,8 +881,9 @@ static Plan make_plan(const dpft_level_t* lv, int n_levels, int B, int C, uint32
   pl.max_ctas = 1;
   pl.max_plane = 0;
   for (int l = 0; l < n_levels; ++l) {
-    pl.nseg[l] = (lv[l].W + kCols - 1) / kCols;
     const bool staged = (flags & DPFT_STAGED_FOOTPRINT) && (flags & DPFT_FUSED_SOBEL) && staged_ok(lv[l], C);
+    const int cols = staged ? kStagedCols : kCols;
+    pl.nseg[l] = (lv[l].W + cols - 1) / cols;
     const int cta_warps = staged ? kSW : kWarps;
     pl.TR[l] = pick_tile_rows(lv[l].H, pl.nseg[l], B, staged ? DPFT_STAGED_CTAS : DPFT_MIN_CTAS, cta_warps);
     pl.nrt[l] = (lv[l].H + pl.TR[l] - 1) / pl.TR[l];

@@ -22,9 +22,19 @@
 namespace dpft {
 
 constexpr int kStageRows = 4;        // ring depth (power of two: slot = source row & 3)
-#ifndef DPFT_STAGE_WIDTH
-#define DPFT_STAGE_WIDTH 44     // tuning hook; 4 * (chunks per map row)
+// Output columns per warp row: 30 (lanes 0 and 31 are halo columns of the horizontal Sobel taps, as in the plain
+// kernel) or 32 (every lane is an output column; the two halo columns' vertical Sobel sums are formed by the lanes
+// in turn -- one map and one side each -- a row ahead, handed over in shared memory and applied as corrections on
+// lanes 0 and 31).  32 columns walk a 160-wide row in 5 segments instead of 6.
+#ifndef DPFT_STAGED_COLS
+#define DPFT_STAGED_COLS 30
 #endif
+constexpr int kStagedCols = DPFT_STAGED_COLS;
+static_assert(kStagedCols == 30 || kStagedCols == 32, "30 or 32 output columns per warp row");
+#ifndef DPFT_STAGE_WIDTH
+#define DPFT_STAGE_WIDTH (DPFT_STAGED_COLS == 32 ? 48 : 44)     // tuning hook; 4 * (chunks per map row)
+#endif
+constexpr int kHaloFloats = kStagedCols == 32 ? 128 : 0;        // [row parity][side][16 maps: vs, vs, vd, vd per pair]
 constexpr int kStageWidth = DPFT_STAGE_WIDTH;      // texels per staged row segment (30 output columns + margin)
 constexpr int kStageMaps = 17;       // x1[0..7], sigma1[0..7], invd1
 constexpr int kStageLookahead = 2;   // source rows requested ahead of the row being computed
@@ -87,7 +97,7 @@ __device__ __forceinline__ TapXY make_tap_xy(float u, float v, int H, int W, flo
 template <bool TRU, bool SB = false, int GW = 0, int GH = 0, bool AUX = true>
 __device__ __forceinline__ void process_tile_staged(const PairView& g, const float* spose, float (*scorr)[33],
                                                     float* ring /* kStageWarpFloats of this warp */,
-                                                    float* outl /* kOutFloats of this warp */, const int seg,
+                                                    float* outl /* kOutFloats (+ kHaloFloats) of this warp */, const int seg,
                                                     const int y0, const int y1, const int lane, TileSums& S) {
   constexpr int CH = 8;
   constexpr bool FIXED = GW > 0 && GH > 0;
@@ -95,9 +105,10 @@ __device__ __forceinline__ void process_tile_staged(const PairView& g, const flo
   constexpr int SW = kStageWidth, CPR = SW / 4;   // 16-byte chunks per staged map row
   const int H = FIXED ? GH : g.H, W = FIXED ? GW : g.W;
   const unsigned iplane = (unsigned)(H * W), Wu = (unsigned)W;
-  const int x = seg * kTileCols - 1 + lane;
+  constexpr bool WIDE = kStagedCols == 32;
+  const int x = WIDE ? seg * 32 + lane : seg * kTileCols - 1 + lane;
   const int xc = min(max(x, 0), W - 1);
-  const bool col_out = lane >= 1 && lane <= kTileCols && x < W;
+  const bool col_out = WIDE ? (x < W) : (lane >= 1 && lane <= kTileCols && x < W);
   const float fx = g.fx, fy = g.fy, cx = g.cx, cy = g.cy;
   const float px = xdiv(xsub((float)xc, cx), fx);
   const float rcp_fy = __frcp_rn(fy);
@@ -179,6 +190,36 @@ __device__ __forceinline__ void process_tile_staged(const PairView& g, const flo
       }
     }
   }
+  // 32 output columns: lane l forms the vertical Sobel sums of map l & 15 (x0 channels, then sigma0 channels) in the
+  // halo column left (l < 16) or right (l >= 16) of the segment, one row AHEAD of the row loop (the hand-over through
+  // shared memory then needs no synchronisation of its own).  Clamped columns reproduce the replicate padding: at
+  // the image border the halo column IS the lane's own column and the correction below vanishes exactly.
+  float* hbuf = outl + kOutFloats;
+  const float* hsrc = nullptr;      // halo column of this lane's map, row 0
+  float ht = 0.f, hm = 0.f;
+  float2 msgn2 = make_float2(0.f, 0.f), mabs2 = make_float2(0.f, 0.f);
+  auto halo_store = [&](const int row, const float hb) {
+    // same expressions as unit_sobel's vs / vd, so a halo sum equals what the neighbouring segment's lane forms
+    const int hmap = lane & 15;
+    float* q = hbuf + (row & 1) * 64 + (lane >> 4) * 32 + 4 * (hmap >> 1) + (hmap & 1);
+    q[0] = fmaf(hm, 2.f, ht + hb);
+    q[2] = fmaf(ht, -1.f, hb);
+  };
+  if (WIDE) {
+    const int hmap = lane & 15;
+    const int hcol = (lane >> 4) ? min(seg * 32 + 32, W - 1) : max(seg * 32 - 1, 0);
+    hsrc = (hmap < CH ? X0 + (unsigned)hmap * iplane : S0 + (SB ? 0u : (unsigned)(hmap - CH) * iplane)) + hcol;
+    ht = __ldg(hsrc + max(y0 - 1, 0) * W);
+    hm = __ldg(hsrc + min(y0, H - 1) * W);
+    const float hb = __ldg(hsrc + min(y0 + 1, H - 1) * W);
+    halo_store(y0, hb);
+    ht = hm;
+    hm = hb;
+    const float sg = lane == 0 ? 1.f : lane == 31 ? -1.f : 0.f;
+    msgn2 = make_float2(sg, sg);
+    mabs2 = make_float2(fabsf(sg), fabsf(sg));
+    __syncwarp();
+  }
   // the ring holds source rows max(base, top - 3) .. top; base = first row requested since the last restart
   int top = -0x40000000, base = 0x40000000;
   float d0_next = (y0 < y1) ? __ldg(g.d0 + (unsigned)(y0 * W + xc)) : 0.f;
@@ -198,6 +239,8 @@ __device__ __forceinline__ void process_tile_staged(const PairView& g, const flo
 #pragma unroll
       for (int p = 0; p < NSP; ++p) sb[p] = load_pair(S0, ob, p);
     }
+    float hnext = 0.f;
+    if (WIDE) hnext = __ldg(hsrc + min(y + 2, H - 1) * W);
     const unsigned o = (unsigned)(y * W + xc);
     const float d0 = d0_next;
     if (y + 1 < y1) d0_next = __ldg(g.d0 + o + Wu);
@@ -234,6 +277,11 @@ __device__ __forceinline__ void process_tile_staged(const PairView& g, const flo
       const int target = min(min(yhi + kStageLookahead, keep + kStageRows - 1), H - 1);
       const int xs = min(max((xlo - (SW - 32) / 2) & ~3, 0), W - SW);
       __syncwarp();                                                      // every lane is done with the old slots
+      if (WIDE) {                                                        // ... and with the halo sums of row y - 1
+        halo_store(y + 1, hnext);
+        ht = hm;
+        hm = hnext;
+      }
 #pragma unroll 1
       while (top < target) {
         stage_row(++top, xs);
@@ -343,10 +391,17 @@ __device__ __forceinline__ void process_tile_staged(const PairView& g, const flo
     };
     // unit Sobel gradient of a map pair (algorithms.py:1844-1865), separable: Sx = vs(x+1) - vs(x-1),
     // Sy = vd(x-1) + 2 vd(x) + vd(x+1), vs = t + 2 m + b, vd = b - t
-    auto unit_sobel = [&](const float2 t, const float2 m, const float2 b, float2& gx, float2& gy) {
+    const float* hrow = hbuf + (y & 1) * 64 + (lane >> 4) * 32;
+    auto unit_sobel = [&](const float2 t, const float2 m, const float2 b, float2& gx, float2& gy, const int hpair) {
       const float2 vs = __ffma2_rn(m, two2, __fadd2_rn(t, b)), vd = __ffma2_rn(t, neg1, b);
-      const float2 Sx = __ffma2_rn(shfl2(vs, false), neg1, shfl2(vs, true));
-      const float2 Sy = __ffma2_rn(vd, two2, __fadd2_rn(shfl2(vd, false), shfl2(vd, true)));
+      float2 Sx = __ffma2_rn(shfl2(vs, false), neg1, shfl2(vs, true));
+      float2 Sy = __ffma2_rn(vd, two2, __fadd2_rn(shfl2(vd, false), shfl2(vd, true)));
+      if (WIDE) {
+        // lanes 0 / 31 received their OWN sums from the shuffle that has no neighbour: swap them for the halo's
+        const float4 hv = *reinterpret_cast<const float4*>(hrow + 4 * hpair);
+        Sx = __ffma2_rn(__ffma2_rn(make_float2(hv.x, hv.y), neg1, vs), msgn2, Sx);
+        Sy = __ffma2_rn(__ffma2_rn(vd, neg1, make_float2(hv.z, hv.w)), mabs2, Sy);
+      }
       const float2 n = __ffma2_rn(Sx, Sx, __ffma2_rn(Sy, Sy, make_float2(1e-8f, 1e-8f)));
       const float2 inv = make_float2(rsqrt_fast(n.x), rsqrt_fast(n.y));
       gx = __fmul2_rn(Sx, inv);
@@ -356,7 +411,7 @@ __device__ __forceinline__ void process_tile_staged(const PairView& g, const flo
     float2 sb_gsx = zero2, sb_gsy = zero2, sb_rs = zero2, sb_k = zero2;
     if (SB) {
       float2 gx1, gy1;
-      unit_sobel(st[0], sm[0], sb[0], gx1, gy1);
+      unit_sobel(st[0], sm[0], sb[0], gx1, gy1, CH / 2);
       float za = b0[CH * ms], zb = b0[CH * ms + 1], zc = b1[CH * ms], zd = b1[CH * ms + 1];
       if (DIRECT && slow) {
         const float* q = S1 + tap.o;
@@ -399,9 +454,9 @@ __device__ __forceinline__ void process_tile_staged(const PairView& g, const flo
       float2 gfx[GP], gfy[GP], gsx[GP], gsy[GP];
 #pragma unroll
       for (int j = 0; j < GP; ++j) {
-        unit_sobel(ft[p0 + j], fm[p0 + j], fb[p0 + j], gfx[j], gfy[j]);
+        unit_sobel(ft[p0 + j], fm[p0 + j], fb[p0 + j], gfx[j], gfy[j], p0 + j);
         if (SB) { gsx[j] = sb_gsx; gsy[j] = sb_gsy; }
-        else unit_sobel(st[SB ? 0 : p0 + j], sm[SB ? 0 : p0 + j], sb[SB ? 0 : p0 + j], gsx[j], gsy[j]);
+        else unit_sobel(st[SB ? 0 : p0 + j], sm[SB ? 0 : p0 + j], sb[SB ? 0 : p0 + j], gsx[j], gsy[j], CH / 2 + p0 + j);
       }
 #pragma unroll
       for (int j = 0; j < GP; ++j) {
