@@ -120,7 +120,14 @@ __device__ __forceinline__ void process_tile_staged(const PairView& g, const flo
   const float* S0 = g.s0;
   const float* X1 = g.x1;
   const float* S1 = g.s1;
-  if (!FIXED) { X0 = opaque(X0); S0 = opaque(S0); X1 = opaque(X1); S1 = opaque(S1); }
+  if (!FIXED) { X0 = opaque(X0); S0 = opaque(S0); }
+  // the live frame's bases stay in registers: left to itself ptxas re-derives them from the kernel parameters in
+  // every row, and the constant load it uses for that ends up sharing a scoreboard with the sixteen window loads
+  // issued next to it -- the first staging address of the row then waits for all of them (a DRAM round trip in
+  // the serial part of every row; 18 % of the stall samples in profiles/r1h_uic_iter_staged_kernel_level0.txt)
+  X1 = opaque(X1);
+  S1 = opaque(S1);
+  const float* D1 = opaque(g.d1);
 
   // one source row of all 17 maps -> ring slot (row & 3), columns [xs, xs + SW).  A map row is CPR 16-byte
   // chunks and SW = 4 CPR, so chunk i = 11 m + ch of a tensor lands at float 4 i of the slot: the destination is
@@ -149,7 +156,7 @@ __device__ __forceinline__ void process_tile_staged(const PairView& g, const flo
       }
     }
     if (lane < CPR) {
-      cp_async16(dst + 4u * (2 * CH * SW), g.d1 + row_off + 4 * lane);
+      cp_async16(dst + 4u * (2 * CH * SW), D1 + row_off + 4 * lane);
       if (SB) cp_async16(dst + 4u * (CH * SW), S1 + row_off + 4 * lane);     // the one sigma map, in map slot CH
     }
     if (lane == 0) slot_xs[row & (kStageRows - 1)] = xs;
@@ -299,6 +306,16 @@ __device__ __forceinline__ void process_tile_staged(const PairView& g, const flo
       ck2 = clock64();
 #endif
     }
+    // The sixteen window loads issued at the top of the row land in scratch registers, and ptxas copies them into
+    // the register PAIRS the packed arithmetic wants as early as it can -- a hundred instructions after the loads,
+    // in the serial part of the row, where the copies then wait a DRAM round trip (17 % of the stall samples in the
+    // first r1h capture).  Adding a zero that is only known after the ring logic turns each copy into an FADD that
+    // cannot be scheduled before this point, by which time the loads have landed.
+    const float late0 = (top == 0x7ffffff0) ? 1.f : 0.f;       // always 0.f (top is a row index), opaque to the compiler
+#pragma unroll
+    for (int p = 0; p < NP; ++p) { fb[p].x += late0; fb[p].y += late0; }
+#pragma unroll
+    for (int p = 0; p < NSP; ++p) { sb[p].x += late0; if (!SB) sb[p].y += late0; }
     const int lowest = max(base, top - (kStageRows - 1));
     const int s0i = txy.yi & (kStageRows - 1), s1i = (txy.yi + 1) & (kStageRows - 1);
     const int xs0 = slot_xs[s0i], xs1 = slot_xs[s1i];
@@ -349,7 +366,7 @@ __device__ __forceinline__ void process_tile_staged(const PairView& g, const flo
           if (SB && m > CH && m < 2 * CH) continue;      // one sigma map: slot CH
           const float* src = (m < CH) ? X1 + (unsigned)tap.o + (unsigned)m * iplane
                            : (m < 2 * CH) ? S1 + (unsigned)tap.o + (SB ? 0u : (unsigned)(m - CH) * iplane)
-                                          : g.d1 + tap.o;
+                                          : D1 + tap.o;
           cp_async4(sc_s + 16u * m, src);
           cp_async4(sc_s + 16u * m + 4u, src + 1);
           cp_async4(sc_s + 16u * m + 8u, src + W);
@@ -368,7 +385,7 @@ __device__ __forceinline__ void process_tile_staged(const PairView& g, const flo
       float da = b0[2 * CH * ms], db = b0[2 * CH * ms + 1];
       float dc = b1[2 * CH * ms], dd = b1[2 * CH * ms + 1];
       if (DIRECT && slow) {
-        const float* q = g.d1 + tap.o;
+        const float* q = D1 + tap.o;
         da = __ldg(q); db = __ldg(q + 1); dc = __ldg(q + W); dd = __ldg(q + W + 1);
       }
       d1w = blend_exact(da, db, dc, dd, tap);
