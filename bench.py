@@ -450,12 +450,12 @@ def main():
                    "algorithmic_bytes_per_step": bytes_step},
         "step_hbm_frac": bytes_step / (ms / args.steps * 1e-3) / 1e9 / peak,
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                     "traffic": (328.3e6 if not args.fused_sobel else 184.0e6 if args.no_staged else 188.2e6)
+                     "traffic": (328.3e6 if not args.fused_sobel else 184.0e6 if args.no_staged else 187.6e6)
                      if args.workload == "tum" else None,
-                     "traffic_source": "ncu --set full dram__bytes_read+write per launch: profiles/r1g_uic_iter_staged_kernel_level0.txt "
+                     "traffic_source": "ncu --set full dram__bytes_read+write per launch: profiles/r1h_uic_iter_staged_kernel_level0.txt "
                                        "(staged, default) / r1_uic_iter_kernel_level0.txt (--no-staged) / r1c_* (--materialised)",
                      "kernel": ("uic_iter_px_kernel<8,true>" if not args.fused_sobel else "uic_iter_kernel<8,true>" if args.no_staged
-                                else "uic_iter_staged_kernel<true,false,160,120>") + " at the finest level",
+                                else "uic_iter_staged_kernel<true,false,160,120,false>") + " at the finest level",
                      "algorithmic_bytes_per_launch": bytes_lvl0, "launch_ms": lvl0_ms,
                      "all_launch_ms": [round(x, 4) for x in per_launch], "peak_source": peak_src,
                      "how": ("%globaltimer stamps at the iteration boundaries inside the single cooperative launch"
