@@ -1275,6 +1275,31 @@ extern "C" int dpft_uic_forward_timed(const dpft_level_t* levels, int n_levels, 
   return rc;
 }
 
+// Host-side view of the balanced tile table of one level (test hook, not part of the ABI): returns 1 and fills
+// `tiles` ([2 kinds][max_warps][2 sub-tiles][seg, y0, y1]), `ctas` (CTAs per pair of kind 0 / 1), `n_more` (pairs of
+// kind 1), `nseg` and `warps_per_cta` when a table is used for (H, W, B), 0 when the rectangular tiling stays.
+extern "C" int dpft_debug_tile_table(int H, int W, int B, int linear, int max_warps, int* tiles, int* ctas,
+                                     int* n_more, int* nseg, int* warps_per_cta) {
+  TileTab tab;
+  const int ns = (W + kStagedCols - 1) / kStagedCols;
+  const bool on = linear ? make_tile_tab_linear(H, ns, B, tab) : make_tile_tab(H, ns, B, tab);
+  *nseg = ns;
+  *warps_per_cta = kSW;
+  if (!on) return 0;
+  ctas[0] = tab.ctas[0];
+  ctas[1] = tab.ctas[1];
+  *n_more = tab.n_more;
+  for (int kind = 0; kind < 2; ++kind)
+    for (int w = 0; w < max_warps && w < kTabWarps; ++w)
+      for (int k = 0; k < 2; ++k) {
+        int* t = tiles + ((kind * max_warps + w) * 2 + k) * 3;
+        t[0] = tab.seg[kind][w][k];
+        t[1] = tab.y0[kind][w][k];
+        t[2] = tab.y1[kind][w][k];
+      }
+  return 1;
+}
+
 #ifdef DPFT_DEBUG_STAMPS
 extern "C" int dpft_debug_read_phases(unsigned long long* host, int n_warps) {
   return (int)cudaMemcpyFromSymbol(host, dpft::g_wtl2, sizeof(unsigned long long) * 4 * (size_t)n_warps);
