@@ -12,6 +12,7 @@
 // taps come from __shfl of the neighbouring lanes and the vertical taps from a 3-row register window
 // that slides down the tile: every x0 / sigma0 element is loaded once per tile (coalesced 128 B rows),
 // the unit Sobel gradients are recomputed instead of stored, and nothing per-pixel is written back.
+#include <cuda.h>
 #include <cuda_runtime.h>
 #include <math_constants.h>
 #include <stdint.h>
@@ -87,6 +88,9 @@ struct UicIterParams {
   const float* icp_rec;  // (B,28) sums of the point-to-plane term of this iteration, or nullptr
   float icp_w2;          // its weight squared (w_icp scales both J and r)
   TileTab tab;           // staged kernel only
+#if DPFT_STAGED_TMA
+  CUtensorMap tm_x1, tm_s1, tm_d1;   // (W, H, C | SC | 1, B) maps of x1 / sigma1 / invd1, box = stage width x 1 x channels x 1
+#endif
 };
 
 // Final step for one pair: corrections for the batch-global sigma extremes, damping, solve, update.
@@ -402,12 +406,14 @@ __global__ void __launch_bounds__(kThreads, DPFT_MIN_CTAS) uic_iter_kernel(const
 #ifndef DPFT_STAGED_CTAS
 #define DPFT_STAGED_CTAS (12 / DPFT_STAGED_WARPS)
 #endif
-constexpr int kStageAreaFloats = (kStageWarpFloats + 12 * 33 + kOutFloats + kHaloFloats + 3) / 4 * 4;   // ring | corrections | outlier taps | halo sums
+// ring | corrections | outlier taps | halo sums; a multiple of 128 bytes so that every ring slot is 128-byte aligned
+// (what the tensor-map copies of DPFT_STAGED_TMA=1 require of their destination)
+constexpr int kStageAreaFloats = (kStageWarpFloats + 12 * 33 + kOutFloats + kHaloFloats + 31) / 32 * 32;
 static_assert((kStageWarpFloats + 12 * 33 + kOutFloats) % 4 == 0, "the halo sums are read as float4");
 static_assert(kStageWarpFloats >= 27 * 33, "the reduction rows overlay the ring");
 template <bool TRU, bool SB = false, int GW = 0, int GH = 0, bool AUX = true>
 __global__ void __launch_bounds__(kSThreads, DPFT_STAGED_CTAS) uic_iter_staged_kernel(const __grid_constant__ UicIterParams p) {
-  extern __shared__ __align__(16) float dyn_stage[];
+  extern __shared__ __align__(128) float dyn_stage[];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int b = blockIdx.y;
   const int plane = (GW > 0) ? GW * GH : p.H * p.W;
@@ -448,6 +454,12 @@ __global__ void __launch_bounds__(kSThreads, DPFT_STAGED_CTAS) uic_iter_staged_k
   g.H = p.H; g.W = p.W; g.C = p.C;
   g.fx = __ldg(p.K + 4 * b); g.fy = __ldg(p.K + 4 * b + 1); g.cx = __ldg(p.K + 4 * b + 2); g.cy = __ldg(p.K + 4 * b + 3);
   g.s0lo = g.s0hi = 0.f;
+  g.b = b;
+#if DPFT_STAGED_TMA
+  g.tm_x1 = &p.tm_x1; g.tm_s1 = &p.tm_s1; g.tm_d1 = &p.tm_d1;
+#else
+  g.tm_x1 = g.tm_s1 = g.tm_d1 = nullptr;
+#endif
 
   float* area = dyn_stage + warp * kStageAreaFloats;
   float (*redw)[33] = reinterpret_cast<float (*)[33]>(area + kStageWarpFloats - 27 * 33);   // rows 27.. start at the ring's end
@@ -989,7 +1001,36 @@ static cudaError_t launch_iter(const UicIterParams& prm, dim3 grid, bool tru, bo
   return cudaLaunchKernelEx(&cfg, uic_iter_kernel<CH, false>, prm);
 }
 
-static cudaError_t launch_staged(const UicIterParams& prm, dim3 grid, bool tru, bool pdl, cudaStream_t stream) {
+#if DPFT_STAGED_TMA
+// Tensor map of a contiguous (B, C, H, W) fp32 tensor whose box is one staged row of all its channel planes.
+static bool encode_row_map(CUtensorMap* tm, const float* base, int W, int H, int C, int B) {
+  typedef CUresult (*encode_fn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+  static encode_fn fn = nullptr;
+  if (!fn) {
+    void* q = nullptr;
+    cudaDriverEntryPointQueryResult qr;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &q, cudaEnableDefault, &qr) != cudaSuccess || !q) return false;
+    fn = (encode_fn)q;
+  }
+  const cuuint64_t dims[4] = {(cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)C, (cuuint64_t)B};
+  const cuuint64_t strides[3] = {(cuuint64_t)W * 4, (cuuint64_t)W * H * 4, (cuuint64_t)W * H * C * 4};
+  const cuuint32_t box[4] = {(cuuint32_t)kStageWidth, 1, (cuuint32_t)C, 1};
+  const cuuint32_t estr[4] = {1, 1, 1, 1};
+  return fn(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, (void*)base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+            CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+#endif
+
+static cudaError_t launch_staged(const UicIterParams& prm_in, dim3 grid, bool tru, bool pdl, cudaStream_t stream) {
+  UicIterParams prm = prm_in;
+#if DPFT_STAGED_TMA
+  if (!encode_row_map(&prm.tm_x1, prm.x1, prm.W, prm.H, prm.C, prm.B) ||
+      !encode_row_map(&prm.tm_s1, prm.s1, prm.W, prm.H, prm.SC, prm.B) ||
+      !encode_row_map(&prm.tm_d1, prm.d1, prm.W, prm.H, 1, prm.B))
+    return cudaErrorInvalidValue;
+#endif
   constexpr int smem = kSW * kStageAreaFloats * (int)sizeof(float);
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = grid;

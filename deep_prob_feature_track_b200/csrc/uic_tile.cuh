@@ -25,6 +25,8 @@ struct PairView {               // one frame pair of one level, pointers already
                                 // map per frame that the reference would have repeated to C channels (alg:1425-1427)
   float fx, fy, cx, cy;
   float s0lo, s0hi;             // extremes of sigma0 over the whole level tensor (remove_tru_sigma)
+  const void *tm_x1, *tm_s1, *tm_d1;   // tensor maps of the live frame's level tensors (TMA ring staging only)
+  int b;                        // pair index (the maps cover the whole batch)
 };
 
 struct TileSums {

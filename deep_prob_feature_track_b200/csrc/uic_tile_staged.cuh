@@ -53,6 +53,41 @@ __device__ __forceinline__ void cp_async4(unsigned smem_addr, const float* g) {
   asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_addr), "l"(g) : "memory");
 }
 __device__ __forceinline__ void stage_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+
+// TMA variant of the ring (-DDPFT_STAGED_TMA=1): a staged source row is three tensor-map copies issued by ONE lane
+// (all x1 planes, all sigma1 planes, the inverse depth; box = stage width x 1 row x channels) and completion is
+// tracked by one mbarrier per ring slot instead of cp.async groups.  Parity-green, measured slower than the cp.async
+// ring (92 vs 87 us per level-0 launch, profiles/r1h_sweep_tma.txt), so it is off by default.
+#ifndef DPFT_STAGED_TMA
+#define DPFT_STAGED_TMA 0
+#endif
+__device__ __forceinline__ void mbar_init(unsigned mbar, unsigned count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(mbar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_inval(unsigned mbar) {
+  asm volatile("mbarrier.inval.shared::cta.b64 [%0];" ::"r"(mbar) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned mbar, unsigned bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(mbar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(unsigned mbar, unsigned parity) {
+  unsigned ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(mbar), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+// one box {SW texels, 1 row, nc channel planes, 1 pair} of a (W, H, C, B) tensor -> shared memory, [channel][texel]
+__device__ __forceinline__ void tma_row_g2s(unsigned dst, const void* tmap, int x, int y, int b, unsigned mbar) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5}], [%6];" ::"r"(dst),
+      "l"(tmap), "r"(x), "r"(y), "r"(0), "r"(b), "r"(mbar)
+      : "memory");
+}
 __device__ __forceinline__ void stage_wait(int pending) {
   // cp.async groups complete in order; `pending` newest groups may stay in flight
   if (pending <= 0) asm volatile("cp.async.wait_group 0;" ::: "memory");
@@ -115,6 +150,12 @@ __device__ __forceinline__ void process_tile_staged(const PairView& g, const flo
   const float rcp_hw = __frcp_rn(0.5f * (float)(W - 1)), rcp_hh = __frcp_rn(0.5f * (float)(H - 1));
   const unsigned ring_s = (unsigned)__cvta_generic_to_shared(ring);
   int* slot_xs = reinterpret_cast<int*>(ring + kStageRows * kStageSlotFloats);
+  // TMA variant: four mbarriers behind the slot origins; `par` holds the phase parity to wait for per slot,
+  // `inflight` the slots whose copy has not been confirmed yet (both warp-uniform)
+#if DPFT_STAGED_TMA
+  const unsigned mbar0 = ring_s + (unsigned)(kStageRows * kStageSlotFloats + 8) * 4u;
+  unsigned par = 0u, inflight = 0u;
+#endif
 
   const float* X0 = g.x0;
   const float* S0 = g.s0;
@@ -133,6 +174,42 @@ __device__ __forceinline__ void process_tile_staged(const PairView& g, const flo
   // chunks and SW = 4 CPR, so chunk i = 11 m + ch of a tensor lands at float 4 i of the slot: the destination is
   // 16 lane + an immediate, and the source offsets of this lane's three chunks are fixed for the whole tile.
   static_assert(SW == 4 * CPR, "chunk i of a tensor sits at float 4 i of the slot");
+#if DPFT_STAGED_TMA
+  // map rows per staged source row: x1 channels in map slots 0..7, sigma1 in 8..15 (one map in slot 8 with SB),
+  // the inverse depth in slot 16
+  constexpr int kBulkMaps = SB ? CH + 2 : kStageMaps;
+  auto wait_slot = [&](const int sl) {
+    const unsigned mb = mbar0 + 8u * (unsigned)sl;
+    int spins = 0;
+    while (!mbar_try_wait(mb, (par >> sl) & 1u)) {
+      if (++spins > (1 << 24)) __trap();               // a copy that never lands must not hang the device
+    }
+    par ^= 1u << sl;
+    inflight &= ~(1u << sl);
+  };
+  if (lane == 0) {
+#pragma unroll
+    for (int sl = 0; sl < kStageRows; ++sl) mbar_init(mbar0 + 8u * sl, 1u);
+  }
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  __syncwarp();
+  auto stage_row = [&](const int row, const int xs) {
+    const int sl = row & (kStageRows - 1);
+    if ((inflight >> sl) & 1u) wait_slot(sl);          // a staged row nobody waited for (lookahead past a restart)
+    const unsigned mb = mbar0 + 8u * (unsigned)sl;
+    // three tensor copies by one lane: the eight x1 planes, the sigma1 planes, the inverse depth (tensor maps of
+    // the level's (W, H, C, B) tensors travel as kernel parameters; box = SW texels x 1 row x all channels)
+    if (lane == 0) {
+      slot_xs[sl] = xs;
+      mbar_expect_tx(mb, (unsigned)(kBulkMaps * SW * 4));
+      const unsigned dst = ring_s + (unsigned)(sl * kStageSlotFloats) * 4u;
+      tma_row_g2s(dst, g.tm_x1, xs, row, g.b, mb);
+      tma_row_g2s(dst + 4u * (CH * SW), g.tm_s1, xs, row, g.b, mb);
+      tma_row_g2s(dst + 4u * (2 * CH * SW), g.tm_d1, xs, row, g.b, mb);
+    }
+    inflight |= 1u << sl;
+  };
+#else
   unsigned soff[3];
 #pragma unroll
   for (int k = 0; k < 3; ++k) {
@@ -162,6 +239,7 @@ __device__ __forceinline__ void process_tile_staged(const PairView& g, const flo
     if (lane == 0) slot_xs[row & (kStageRows - 1)] = xs;
     stage_commit();
   };
+#endif
 
   // channel PAIRS travel together as float2 so the per-channel arithmetic issues as packed FFMA2 / FMUL2 / FADD2
   constexpr int NP = CH / 2;
@@ -300,7 +378,18 @@ __device__ __forceinline__ void process_tile_staged(const PairView& g, const flo
 #ifdef DPFT_DEBUG_STAMPS
       ck1 = clock64();
 #endif
+#if DPFT_STAGED_TMA
+      {
+        // rows keep .. ready_top are read by this warp row: confirm the ones still in flight (usually the newest)
+#pragma unroll 1
+        for (int r = max(keep, top - (kStageRows - 1)); r <= ready_top; ++r) {
+          const int sl = r & (kStageRows - 1);
+          if ((inflight >> sl) & 1u) wait_slot(sl);
+        }
+      }
+#else
       stage_wait(top - ready_top);
+#endif
       __syncwarp();
 #ifdef DPFT_DEBUG_STAMPS
       ck2 = clock64();
@@ -583,6 +672,17 @@ __device__ __forceinline__ void process_tile_staged(const PairView& g, const flo
     }
   }
   asm volatile("cp.async.wait_group 0;" ::: "memory");   // nothing of this warp may still land in the ring
+#if DPFT_STAGED_TMA
+#pragma unroll
+  for (int sl = 0; sl < kStageRows; ++sl)
+    if ((inflight >> sl) & 1u) wait_slot(sl);
+  __syncwarp();
+  if (lane == 0) {
+#pragma unroll
+    for (int sl = 0; sl < kStageRows; ++sl) mbar_inval(mbar0 + 8u * sl);
+  }
+  __syncwarp();
+#endif
 }
 
 }  // namespace dpft
