@@ -161,7 +161,8 @@ __device__ __forceinline__ void process_tile_staged(const PairView& g, const flo
   const float* S0 = g.s0;
   const float* X1 = g.x1;
   const float* S1 = g.s1;
-  if (!FIXED) { X0 = opaque(X0); S0 = opaque(S0); }
+  X0 = opaque(X0);
+  S0 = opaque(S0);
   // the live frame's bases stay in registers: left to itself ptxas re-derives them from the kernel parameters in
   // every row, and the constant load it uses for that ends up sharing a scoreboard with the sixteen window loads
   // issued next to it -- the first staging address of the row then waits for all of them (a DRAM round trip in
@@ -169,6 +170,7 @@ __device__ __forceinline__ void process_tile_staged(const PairView& g, const flo
   X1 = opaque(X1);
   S1 = opaque(S1);
   const float* D1 = opaque(g.d1);
+  const float* D0 = opaque(g.d0);
 
   // one source row of all 17 maps -> ring slot (row & 3), columns [xs, xs + SW).  A map row is CPR 16-byte
   // chunks and SW = 4 CPR, so chunk i = 11 m + ch of a tensor lands at float 4 i of the slot: the destination is
@@ -307,7 +309,7 @@ __device__ __forceinline__ void process_tile_staged(const PairView& g, const flo
   }
   // the ring holds source rows max(base, top - 3) .. top; base = first row requested since the last restart
   int top = -0x40000000, base = 0x40000000;
-  float d0_next = (y0 < y1) ? __ldg(g.d0 + (unsigned)(y0 * W + xc)) : 0.f;
+  float d0_next = (y0 < y1) ? __ldg(D0 + (unsigned)(y0 * W + xc)) : 0.f;
 
   for (int y = y0; y < y1; ++y) {
 #ifdef DPFT_DEBUG_STAMPS
@@ -328,7 +330,7 @@ __device__ __forceinline__ void process_tile_staged(const PairView& g, const flo
     if (WIDE) hnext = __ldg(hsrc + min(y + 2, H - 1) * W);
     const unsigned o = (unsigned)(y * W + xc);
     const float d0 = d0_next;
-    if (y + 1 < y1) d0_next = __ldg(g.d0 + o + Wu);
+    if (y + 1 < y1) d0_next = __ldg(D0 + o + Wu);
     const float py = div_by(xsub((float)y, cy), fy, rcp_fy);
 
     float u, v, inv_z;
