@@ -43,7 +43,10 @@ constexpr int kStageLookahead = 2;   // source rows requested ahead of the row b
 constexpr int kStageSlotFloats = (kStageMaps * kStageWidth + 31) / 32 * 32;
 constexpr int kStageWarpFloats = kStageRows * kStageSlotFloats + 32;   // + x origin of each slot (as int)
 // lanes of a row whose footprint is not resident park their own 17 x 4 taps here (see the direct-load body)
-constexpr int kOutLanes = 4;
+#ifndef DPFT_OUT_LANES
+#define DPFT_OUT_LANES 4
+#endif
+constexpr int kOutLanes = DPFT_OUT_LANES;     // tuning hook
 constexpr int kOutFloats = kOutLanes * kStageMaps * 4;
 
 __device__ __forceinline__ void cp_async16(unsigned smem_addr, const float* g) {
