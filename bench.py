@@ -228,6 +228,8 @@ def main():
     ap.add_argument("--no-staged", action="store_true", help="plain fused kernel instead of the staged-footprint one (DPFT_STAGED_FOOTPRINT off)")
     ap.add_argument("--streams", type=int, default=8, help="CUDA streams the timed steps are spread over")
     ap.add_argument("--no-extras", action="store_true", help="skip the training-step and 480x640 side measurements")
+    ap.add_argument("--no-graphs", action="store_true",
+                    help="issue every launch from the host instead of replaying one CUDA graph per solve")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
     args.fused_sobel = not args.materialised
@@ -321,11 +323,39 @@ def main():
         main_stream = torch.cuda.current_stream(dev)
         workers = [torch.cuda.Stream(device=dev) for _ in range(max(1, args.streams))]
 
+        # One solve is 17 launches (~0.18 ms of host time) for ~0.3 ms of device time; with several ranks on one host
+        # the issue rate, not the GPU, set the pace (4 GPUs: 0.56 ms per step).  So a solve is captured ONCE per
+        # (worker stream, input set) into a CUDA graph -- same C-ABI call, same launches, PDL edges included -- and the
+        # timed steps replay the graphs.  --no-graphs restores host-issued launches; a failed capture falls back to them.
+        graphs = {}
+        if not args.no_graphs and not args.single_launch:
+            try:
+                combos = sorted({(i % len(workers), i % N_SETS) for i in range(len(workers) * N_SETS)})
+                for w, k in combos:
+                    with torch.cuda.stream(workers[w]):
+                        solve(dev_sets[k])                      # scratch pools, function attributes
+                torch.cuda.synchronize()
+                for w, k in combos:
+                    g = torch.cuda.CUDAGraph()
+                    with torch.cuda.graph(g, stream=workers[w]):
+                        out = solve(dev_sets[k])
+                    graphs[(w, k)] = (g, out)
+                torch.cuda.synchronize()
+            except Exception as exc:   # pragma: no cover - depends on the driver
+                print(f"[bench] CUDA graph capture failed ({exc!r}); issuing launches from the host", file=sys.stderr)
+                graphs = {}
+                torch.cuda.synchronize()
+
         def run_steps(n):
             last = None
             for i in range(n):
-                with torch.cuda.stream(workers[i % len(workers)]):
-                    last = solve(dev_sets[i % N_SETS])
+                w, k = i % len(workers), i % N_SETS
+                with torch.cuda.stream(workers[w]):
+                    if graphs:
+                        graphs[(w, k)][0].replay()
+                        last = graphs[(w, k)][1]
+                    else:
+                        last = solve(dev_sets[k])
             return last
 
         def timed(n):
@@ -341,6 +371,7 @@ def main():
             e1.record(main_stream)
             return out, e0, e1
 
+        use_graphs = bool(graphs)
         res, _, _ = timed(args.warmup)
         res.raise_if_bad()
         barrier()
@@ -445,7 +476,8 @@ def main():
                    "remove_tru_sigma": True, "pdl": not args.no_pdl, "streams": max(1, args.streams),
                    "sobel": "fused" if args.fused_sobel else "materialised once per level",
                    "lookups": "plain loads" if (args.no_staged or not args.fused_sobel) else "footprint staged in shared memory (cp.async ring)",
-                   "launch": "single cooperative launch for all levels and iterations" if single else "one launch per iteration",
+                   "launch": "single cooperative launch for all levels and iterations" if single else
+                             ("one launch per iteration, each solve replayed from a CUDA graph" if use_graphs else "one launch per iteration"),
                    "l2": f"inputs rotate over {N_SETS} resident sets of {set_bytes / 1e6:.0f} MB each (> 126 MB L2)",
                    "algorithmic_bytes_per_step": bytes_step},
         "step_hbm_frac": bytes_step / (ms / args.steps * 1e-3) / 1e9 / peak,
