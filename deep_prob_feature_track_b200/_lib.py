@@ -17,9 +17,11 @@ PKG_DIR = os.path.dirname(os.path.abspath(__file__))
 REPO_DIR = os.path.dirname(PKG_DIR)
 CSRC = os.path.join(PKG_DIR, "csrc")
 LIB_PATH = os.path.join(PKG_DIR, "libdpft.so")
-SOURCES = ["dpft_abi.cu", "uic_forward.cu", "uic_backward.cu", "icp_term.cu", "uic_residual.cu", "ic_path.cu", "ic_backward.cu", "uic_persistent.cu", "preprocess.cu", "pose_loss.cu"]
+SOURCES = ["dpft_abi.cu", "uic_forward.cu", "uic_queue.cu", "uic_backward.cu", "icp_term.cu", "uic_residual.cu",
+           "ic_path.cu", "ic_backward.cu", "uic_persistent.cu", "preprocess.cu", "pose_loss.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
-              "-Xcompiler", "-fPIC", "-shared"]
+              "-Xcompiler", "-fPIC"]
+OBJ_DIR = os.path.join(PKG_DIR, "build")
 
 DPFT_ABI_VERSION = 1
 DPFT_MAX_LEVELS = 8
@@ -32,6 +34,7 @@ DPFT_STAGED_FOOTPRINT = 0x20
 DPFT_SHARED_KEYFRAME = 0x40
 DPFT_PAIRWISE_EXTREMES = 0x80
 DPFT_SIGMA_BROADCAST = 0x100
+DPFT_QUEUE = 0x200
 DPFT_ST_NONFINITE = 0x01
 DPFT_ST_SINGULAR = 0x02
 
@@ -52,6 +55,26 @@ class DpftLevel(ctypes.Structure):
     ]
 
 
+class DpftUicOptions(ctypes.Structure):
+    """struct dpft_uic_options (include/dpft.h); zero fields mean "default"."""
+    _fields_ = [
+        ("struct_bytes", ctypes.c_uint32), ("group", ctypes.c_int32),
+        ("tile_rows", ctypes.c_int32 * DPFT_MAX_LEVELS),
+        ("queue_ctas", ctypes.c_int32), ("cta_slots", ctypes.c_int32), ("tiling", ctypes.c_int32),
+        ("generic_geometry", ctypes.c_int32),
+        ("launch_ms", ctypes.POINTER(ctypes.c_float)),
+    ]
+
+    def __init__(self, **kw):
+        super().__init__()
+        self.struct_bytes = ctypes.sizeof(DpftUicOptions)
+        tile_rows = kw.pop("tile_rows", None)
+        for i, v in enumerate(tile_rows or ()):
+            self.tile_rows[i] = int(v)
+        for k, v in kw.items():
+            setattr(self, k, v)
+
+
 class DpftLevelGrad(ctypes.Structure):
     """struct dpft_level_grad (include/dpft.h)."""
     _fields_ = [("g_x0", c_float_p), ("g_x1", c_float_p), ("g_sigma0", c_float_p), ("g_sigma1", c_float_p)]
@@ -64,6 +87,11 @@ def _nvcc() -> str:
     raise RuntimeError("nvcc not found; cannot build libdpft.so")
 
 
+def _headers() -> List[str]:
+    return ([os.path.join(CSRC, f) for f in os.listdir(CSRC) if not f.endswith(".cu")]
+            + [os.path.join(REPO_DIR, "include", "dpft.h")])
+
+
 def _stale() -> bool:
     if not os.path.exists(LIB_PATH):
         return True
@@ -73,20 +101,48 @@ def _stale() -> bool:
 
 
 def build(force: bool = False, verbose: bool = False) -> str:
-    """Compile csrc/*.cu into libdpft.so for sm_100a (cross-compiles without a GPU)."""
+    """Compile csrc/*.cu for sm_100a (cross-compiles without a GPU) and link libdpft.so.  Every translation unit
+    becomes an object file under build/ (compiled in parallel, recompiled only when it or a header changed);
+    temporary names carry the pid so that several ranks building at once cannot install a truncated file."""
     if not force and not _stale():
         return LIB_PATH
-    extra = os.environ.get("DPFT_NVCC_EXTRA", "").split()   # e.g. -DDPFT_MIN_CTAS=4 for tuning sweeps
-    cmd = [_nvcc(), *NVCC_FLAGS, *extra, "-I", os.path.join(REPO_DIR, "include"), "-I", CSRC,
-           "-o", LIB_PATH + ".tmp", *[os.path.join(CSRC, s) for s in SOURCES]]
-    if verbose:
-        cmd.insert(1, "-Xptxas=-v")
+    from concurrent.futures import ThreadPoolExecutor
+    os.makedirs(OBJ_DIR, exist_ok=True)
+    extra = os.environ.get("DPFT_NVCC_EXTRA", "").split()   # e.g. -DDPFT_STAGED_COLS=32 for tuning sweeps
+    tag_path = os.path.join(OBJ_DIR, "flags.txt")
+    tag = " ".join(NVCC_FLAGS + extra)
+    if not os.path.exists(tag_path) or open(tag_path).read() != tag:
+        force = True
+    hdr_t = max(os.path.getmtime(h) for h in _headers())
+    pid = os.getpid()
+
+    def compile_one(src: str):
+        obj = os.path.join(OBJ_DIR, src[:-3] + ".o")
+        path = os.path.join(CSRC, src)
+        if not force and os.path.exists(obj) and os.path.getmtime(obj) >= max(hdr_t, os.path.getmtime(path)):
+            return obj, ""
+        tmp = f"{obj}.{pid}.tmp"
+        cmd = [_nvcc(), *NVCC_FLAGS, *extra, "-I", os.path.join(REPO_DIR, "include"), "-I", CSRC, "-c", "-o", tmp, path]
+        if verbose:
+            cmd.insert(1, "-Xptxas=-v")
+        res = subprocess.run(cmd, capture_output=True, text=True)
+        if res.returncode != 0:
+            raise RuntimeError("nvcc failed:\n" + " ".join(cmd) + "\n" + res.stdout + res.stderr)
+        os.replace(tmp, obj)
+        return obj, res.stderr
+
+    with ThreadPoolExecutor(max_workers=min(len(SOURCES), os.cpu_count() or 1)) as pool:
+        results = list(pool.map(compile_one, SOURCES))
+    tmp = f"{LIB_PATH}.{pid}.tmp"
+    cmd = [_nvcc(), "-gencode", "arch=compute_100a,code=sm_100a", "-shared", "-o", tmp, *[o for o, _ in results]]
     res = subprocess.run(cmd, capture_output=True, text=True)
     if res.returncode != 0:
-        raise RuntimeError("nvcc failed:\n" + " ".join(cmd) + "\n" + res.stdout + res.stderr)
-    os.replace(LIB_PATH + ".tmp", LIB_PATH)
+        raise RuntimeError("link failed:\n" + " ".join(cmd) + "\n" + res.stdout + res.stderr)
+    os.replace(tmp, LIB_PATH)
+    with open(tag_path, "w") as f:
+        f.write(tag)
     if verbose:
-        print(res.stderr)
+        print("".join(err for _, err in results))
     return LIB_PATH
 
 
@@ -115,6 +171,10 @@ def lib() -> ctypes.CDLL:
                                    ctypes.c_void_p, ctypes.c_size_t, ctypes.c_void_p]
     L.dpft_uic_forward_timed.restype = ctypes.c_int
     L.dpft_uic_forward_timed.argtypes = L.dpft_uic_forward.argtypes + [ctypes.POINTER(ctypes.c_float)]
+    L.dpft_uic_workspace_bytes_ex.restype = ctypes.c_size_t
+    L.dpft_uic_workspace_bytes_ex.argtypes = L.dpft_uic_workspace_bytes.argtypes + [ctypes.POINTER(DpftUicOptions)]
+    L.dpft_uic_forward_ex.restype = ctypes.c_int
+    L.dpft_uic_forward_ex.argtypes = L.dpft_uic_forward.argtypes + [ctypes.POINTER(DpftUicOptions)]
     L.dpft_uic_backward_workspace_bytes.restype = ctypes.c_size_t
     L.dpft_uic_backward_workspace_bytes.argtypes = L.dpft_uic_workspace_bytes.argtypes
     L.dpft_uic_backward.restype = ctypes.c_int
@@ -161,7 +221,7 @@ def lib() -> ctypes.CDLL:
 def exported_symbols() -> List[str]:
     """Entry points include/dpft.h declares (kept in sync by tests/test_abi.py)."""
     return ["dpft_abi_version", "dpft_last_error", "dpft_uic_workspace_bytes", "dpft_uic_forward",
-            "dpft_uic_forward_timed", "dpft_uic_backward_workspace_bytes", "dpft_uic_backward",
+            "dpft_uic_workspace_bytes_ex", "dpft_uic_forward_ex", "dpft_uic_forward_timed", "dpft_uic_backward_workspace_bytes", "dpft_uic_backward",
             "dpft_uic_residual_workspace_bytes", "dpft_uic_residual_loss", "dpft_ic_gradients", "dpft_ic_residual",
             "dpft_ic_normal_matrix", "dpft_ic_rhs", "dpft_ic_update", "dpft_ic_gradients_backward",
             "dpft_ic_residual_backward", "dpft_ic_normal_matrix_backward", "dpft_ic_rhs_backward",

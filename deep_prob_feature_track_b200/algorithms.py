@@ -96,7 +96,9 @@ def uic_solve(levels: Sequence[Dict[str, torch.Tensor]], pose: Pose, *, iters: i
               remove_tru_sigma: bool = False, combine_icp: bool = False, w_icp: float = 0.01,
               want_occ: bool = False, pdl: bool = True, timed: bool = False, fused_sobel: bool = True, single_launch: bool = False, staged_footprint: bool = True,
               shared_keyframe: bool = False, pairwise_extremes: bool = False,
-              obj_mask0: Optional[Sequence] = None, obj_mask1: Optional[Sequence] = None) -> SolveResult:
+              obj_mask0: Optional[Sequence] = None, obj_mask1: Optional[Sequence] = None,
+              queue: bool = True, group: int = 0, tile_rows: Optional[Sequence[int]] = None, queue_ctas: int = 0,
+              tuning: Optional[Dict[str, int]] = None) -> SolveResult:
     """Coarse-to-fine U_IC solve of a batch of frame pairs on the current CUDA stream.
 
     ``levels`` is ordered coarse to fine; each dict holds x0, x1, s0, s1 (B,C,h,w), invD0, invD1 (B,1,h,w)
@@ -105,6 +107,13 @@ def uic_solve(levels: Sequence[Dict[str, torch.Tensor]], pose: Pose, *, iters: i
     s0 / s1 may also be (B,1,h,w): the single uncertainty map the reference's encoder produces before repeating
     it to C channels (algorithms.py:1425-1427).  The fused launch-per-iteration kernels then read it once per
     pixel (DPFT_SIGMA_BROADCAST); every other path gets the repeated tensor, so results never depend on it.
+
+    ``queue`` (default): the whole solve is ONE launch whose warps take tiles from a work queue with per-pair
+    dependencies (csrc/uic_queue.cu) whenever the problem qualifies (C == 8, fused Sobel, no ICP term, no
+    ``want_occ``); otherwise -- and with ``queue=False`` -- one launch per Gauss-Newton iteration.  ``group``: the B
+    pairs are B / group independent batches of ``group`` consecutive pairs, each with its own batch-global sigma
+    extremes (what B / group separate calls would give, from one launch; queue path only).  ``tile_rows`` (per level,
+    coarse first), ``queue_ctas`` and ``tuning`` (cta_slots, tiling, generic_geometry) are measurement knobs.
     """
     L = _lib.lib()
     n_levels = len(levels)
@@ -113,6 +122,13 @@ def uic_solve(levels: Sequence[Dict[str, torch.Tensor]], pose: Pose, *, iters: i
     Bk = 1 if shared_keyframe else B     # batch size of the keyframe-side tensors
     one_sigma = C > 1 and all(int(lv[k].shape[1]) == 1 for lv in levels for k in ("s0", "s1"))
     sigma_broadcast = one_sigma and fused_sobel and not single_launch
+    use_queue = queue and fused_sobel and not single_launch and not combine_icp and not want_occ and C == 8 and iters >= 1
+    if group not in (0, B) and not use_queue and not (group == 1 and pairwise_extremes):
+        raise NotImplementedError("sigma-extreme groups other than the whole batch need the work-queue path")
+    eff_group = group if group > 0 else (1 if pairwise_extremes else B)
+    if B % eff_group:
+        raise ValueError(f"group ({eff_group}) must divide the batch size ({B})")
+    n_groups = B // eff_group if use_queue else 1
     SC = 1 if sigma_broadcast else C
     dev = x0.device
     keep = []   # keep converted tensors alive until the launches are queued
@@ -155,31 +171,33 @@ def uic_solve(levels: Sequence[Dict[str, torch.Tensor]], pose: Pose, *, iters: i
              | (_lib.DPFT_STAGED_FOOTPRINT if staged_footprint else 0)
              | (_lib.DPFT_SHARED_KEYFRAME if shared_keyframe else 0)
              | (_lib.DPFT_PAIRWISE_EXTREMES if pairwise_extremes else 0)
-             | (_lib.DPFT_SIGMA_BROADCAST if sigma_broadcast else 0))
+             | (_lib.DPFT_SIGMA_BROADCAST if sigma_broadcast else 0)
+             | (_lib.DPFT_QUEUE if use_queue else 0))
     if (shared_keyframe or pairwise_extremes) and (combine_icp or not fused_sobel):
         raise NotImplementedError("shared_keyframe / pairwise_extremes are served by the fused U_IC kernel only")
     n_it = n_levels * iters
     pose_in = pack_pose(pose).to(dev)
     pose_hist = torch.empty((n_it + 1, B, 12), dtype=torch.float32, device=dev)
     sys_hist = torch.empty((max(n_it, 1), B, 27), dtype=torch.float32, device=dev)
-    aux_hist = torch.zeros((max(n_it, 1), 4), dtype=torch.float32, device=dev)
+    aux_shape = (max(n_it, 1), 4) if n_groups == 1 else (max(n_it, 1), n_groups, 4)
+    aux_hist = torch.zeros(aux_shape, dtype=torch.float32, device=dev)
     status = torch.zeros((1,), dtype=torch.int32, device=dev)
-    ws_bytes = L.dpft_uic_workspace_bytes(arr, n_levels, B, C, iters, flags)
+    buf = (ctypes.c_float * max(n_it, 1))() if timed else None
+    opt = _lib.DpftUicOptions(group=(eff_group if use_queue else 0), tile_rows=tile_rows, queue_ctas=queue_ctas,
+                              **(tuning or {}))
+    if timed:   # measurement aid (bench.py): per-iteration device times, synchronises the stream
+        opt.launch_ms = ctypes.cast(buf, ctypes.POINTER(ctypes.c_float))
+    ws_bytes = L.dpft_uic_workspace_bytes_ex(arr, n_levels, B, C, iters, flags, ctypes.byref(opt))
     if ws_bytes == 0:
         raise RuntimeError("dpft_uic_workspace_bytes: " + L.dpft_last_error().decode())
     ws = torch.empty((ws_bytes,), dtype=torch.uint8, device=dev)
     stream = torch.cuda.current_stream(dev).cuda_stream
-    launch_ms = None
-    args = (arr, n_levels, B, C, iters, flags, ctypes.c_float(w_icp), pose_in.data_ptr(), pose_hist.data_ptr(),
-            sys_hist.data_ptr(), aux_hist.data_ptr(), status.data_ptr(), ws.data_ptr(), ws_bytes, stream)
     with torch.cuda.device(dev):
-        if timed:   # measurement aid (bench.py): per-launch device times, synchronises the stream
-            buf = (ctypes.c_float * n_it)()
-            code = L.dpft_uic_forward_timed(*args, buf)
-            launch_ms = list(buf)
-        else:
-            code = L.dpft_uic_forward(*args)
+        code = L.dpft_uic_forward_ex(arr, n_levels, B, C, iters, flags, ctypes.c_float(w_icp), pose_in.data_ptr(),
+                                     pose_hist.data_ptr(), sys_hist.data_ptr(), aux_hist.data_ptr(), status.data_ptr(),
+                                     ws.data_ptr(), ws_bytes, stream, ctypes.byref(opt))
     _lib.check(code, "dpft_uic_forward")
+    launch_ms = list(buf) if timed else None
     del keep   # launches are queued on the allocating stream; the caching allocator orders reuse after them
     return SolveResult(pose_hist, sys_hist[:n_it], aux_hist[:n_it], status, occ, n_levels, iters, launch_ms)
 

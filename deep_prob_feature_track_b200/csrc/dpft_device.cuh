@@ -275,9 +275,9 @@ __device__ inline bool solve_and_update(const double A[21], const double rhs[6],
   for (int i = 0; i < 3; ++i) dt[i] = -(dR[3 * i] * xi[3] + dR[3 * i + 1] * xi[4] + dR[3 * i + 2] * xi[5]);
   double R[9], t[3];
 #pragma unroll
-  for (int i = 0; i < 9; ++i) R[i] = (double)pose_in[i];
+  for (int i = 0; i < 9; ++i) R[i] = (double)__ldcg(pose_in + i);   // L2: in the persistent kernels another SM wrote it
 #pragma unroll
-  for (int i = 0; i < 3; ++i) t[i] = (double)pose_in[9 + i];
+  for (int i = 0; i < 3; ++i) t[i] = (double)__ldcg(pose_in + 9 + i);
 #pragma unroll
   for (int i = 0; i < 3; ++i) {
 #pragma unroll

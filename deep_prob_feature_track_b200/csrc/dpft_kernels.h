@@ -48,4 +48,35 @@ struct PersistParams {
 int persistent_grid(int C, bool tru);   // CTAs that can be co-resident on the current device
 cudaError_t launch_persistent(const PersistParams& prm, int grid, bool tru, cudaStream_t stream);
 
+// ---- queue-driven single launch (uic_queue.cu): per-pair dependencies, any number of sigma-extreme groups
+struct QLevel {
+  const float *x0, *x1, *s0, *s1, *d0, *d1, *K;
+  const uint8_t *m0, *m1;
+  int H, W, nseg, TR, nrt, tpp;      // TR rows per tile, tpp = tiles per pair
+  int kind;                          // tile routine: 0 plain, 1 staged footprint (2: its geometry-specialised copy)
+};
+struct QueueParams {
+  QLevel lv[8];
+  int n_levels, iters, B, C, SC;
+  int group, n_groups;               // pairs per sigma-extreme group (the reference's batch), groups in this call
+  int n_mm_groups;                   // groups of the sigma0 extremes per level (1 with a shared keyframe)
+  int max_tiles, kf_shared;
+  unsigned total_items;
+  float *pose_hist, *sys_hist, *aux; // aux: (n_it, n_groups, 4) or nullptr
+  float* records;                    // (B, max_tiles, PS)
+  double* pairrec;                   // (B, PS) parked sums of the candidates
+  unsigned long long* fifo;          // (total_items)
+  unsigned* qctl;                    // [0] head (claims), [1] tail (reservations)
+  int *tiles_done, *cand;            // (B)
+  int *pairs_done, *groups_done;     // (n_it, n_groups), (n_it)
+  uint32_t* gext;                    // (n_it, n_groups, 2) running extremes of the warped sigma, order-encoded
+  const uint32_t* s0mm;              // (n_levels, n_mm_groups, 2) extremes of sigma0, order-encoded
+  uint32_t* s0mm_rw;                 // the same buffer (written by the launcher's helper kernels)
+  int32_t* status;
+  unsigned long long* t_done;        // optional (n_it + 1) %globaltimer stamps: start, then every iteration complete
+};
+int queue_tiles_per_sm();            // resident workers (warps) per SM
+cudaError_t launch_queue(const QueueParams& prm, const float* pose_in, bool tru, int grid, cudaStream_t stream,
+                         bool allow_fixed_geometry);
+
 }  // namespace dpft

@@ -406,11 +406,6 @@ __global__ void __launch_bounds__(kThreads, DPFT_MIN_CTAS) uic_iter_kernel(const
 #ifndef DPFT_STAGED_CTAS
 #define DPFT_STAGED_CTAS (12 / DPFT_STAGED_WARPS)
 #endif
-// ring | corrections | outlier taps | halo sums; a multiple of 128 bytes so that every ring slot is 128-byte aligned
-// (what the tensor-map copies of DPFT_STAGED_TMA=1 require of their destination)
-constexpr int kStageAreaFloats = (kStageWarpFloats + 12 * 33 + kOutFloats + kHaloFloats + 31) / 32 * 32;
-static_assert((kStageWarpFloats + 12 * 33 + kOutFloats) % 4 == 0, "the halo sums are read as float4");
-static_assert(kStageWarpFloats >= 27 * 33, "the reduction rows overlay the ring");
 template <bool TRU, bool SB = false, int GW = 0, int GH = 0, bool AUX = true>
 __global__ void __launch_bounds__(kSThreads, DPFT_STAGED_CTAS) uic_iter_staged_kernel(const __grid_constant__ UicIterParams p) {
   extern __shared__ __align__(128) float dyn_stage[];
@@ -767,6 +762,30 @@ __global__ void occ_fixup_kernel(uint8_t* __restrict__ occ, const float* __restr
 }
 
 // --------------------------------------------------------------------------- host side
+// What dpft_uic_options_t carries, with the defaults filled in (no environment variables, no process state).
+struct Tuning {
+  int group = 0;                          // pairs per sigma-extreme group (queue path); 0 = B
+  int tile_rows[DPFT_MAX_LEVELS] = {};    // queue path: rows per tile, 0 = chosen
+  int queue_ctas = 0;
+  long cta_slots = 0;                     // 0 = 148 x resident CTAs
+  int tiling = 0;                         // 0 dealt, 1 rectangular, 2 linear
+  bool generic_geometry = false;
+  float* launch_ms = nullptr;
+};
+
+static Tuning tuning_of(const dpft_uic_options_t* o) {
+  Tuning t;
+  if (!o || o->struct_bytes < sizeof(dpft_uic_options_t)) return t;
+  t.group = o->group;
+  for (int l = 0; l < DPFT_MAX_LEVELS; ++l) t.tile_rows[l] = o->tile_rows[l];
+  t.queue_ctas = o->queue_ctas;
+  t.cta_slots = o->cta_slots;
+  t.tiling = o->tiling;
+  t.generic_geometry = o->generic_geometry != 0;
+  t.launch_ms = o->launch_ms;
+  return t;
+}
+
 struct Plan {
   int nseg[DPFT_MAX_LEVELS], nrt[DPFT_MAX_LEVELS], TR[DPFT_MAX_LEVELS], ctas[DPFT_MAX_LEVELS];
   int ppt[DPFT_MAX_LEVELS], px_ctas[DPFT_MAX_LEVELS];   // materialised-gradient path: pixels per thread, CTAs per pair
@@ -783,9 +802,9 @@ struct Plan {
 // Rows per warp tile.  A tile is walked row by row by one warp, so the time of a launch is about
 // (waves of CTAs) x (rows per tile + ~1.5 rows of window priming and reduction tail): pick the height that
 // minimises that, i.e. fill whole waves of the 148 x DPFT_MIN_CTAS resident CTAs.
-static int pick_tile_rows(int H, int nseg, int B, int ctas_per_sm, int warps) {
+static int pick_tile_rows(int H, int nseg, int B, int ctas_per_sm, int warps, const Tuning& tun) {
   long slots = 148L * ctas_per_sm;
-  if (const char* e = getenv("DPFT_CTA_SLOTS")) slots = std::max(1L, atol(e));   // tuning hook
+  if (tun.cta_slots > 0) slots = tun.cta_slots;
   int best_tr = 1;
   double best = 1e30;
   for (int tr = 1; tr <= kMaxTileRows; ++tr) {
@@ -806,14 +825,14 @@ static bool staged_ok(const dpft_level_t& L, int C) {
 
 // Linear variant of the balanced tile table (DPFT_LINEAR_TILES=1; see TileTab).  Returns false when the rectangular tiling should stay (the
 // table holds at most kTabWarps warps per pair, and a warp's range may cross one segment boundary at most).
-static bool make_tile_tab_linear(int H, int nseg, int B, TileTab& tab) {
+static bool make_tile_tab_linear(int H, int nseg, int B, TileTab& tab, const Tuning& tun) {
   tab = TileTab{};
   // 35/37 of the resident slots: filling every slot makes a lone launch ~3 % shorter still, but then the small
   // launches of OTHER streams (coarse levels of independent batches) find no free slot and the multi-stream
   // throughput drops by 5 % (profiles/exp9.sh)
   long slots = 148L * DPFT_STAGED_CTAS * 35 / 37;
-  if (const char* e = getenv("DPFT_CTA_SLOTS")) slots = std::max(1L, atol(e));
-  if (getenv("DPFT_RECT_TILES")) return false;
+  if (tun.cta_slots > 0) slots = tun.cta_slots;
+  if (tun.tiling == 1) return false;
   const int c0 = (int)(slots / B);               // CTAs per pair of kind 0; kind 1 has one more
   const int n_more = (int)(slots - (long)c0 * B);
   if (c0 < 1 || (c0 + 1) * kSW > kTabWarps || c0 * kSW < nseg + 1) return false;
@@ -849,15 +868,15 @@ static bool make_tile_tab_linear(int H, int nseg, int B, TileTab& tab) {
 // Balanced tile table of one level (see TileTab), the default: every segment is cut into whole row tiles (some
 // segments into one tile more than the others), taller tiles first, dealt round-robin to the CTAs so that every CTA
 // gets the same mix of heights.  Returns false when the rectangular tiling should stay.
-static bool make_tile_tab(int H, int nseg, int B, TileTab& tab) {
-  if (getenv("DPFT_LINEAR_TILES") || kSW != 4) return make_tile_tab_linear(H, nseg, B, tab);
+static bool make_tile_tab(int H, int nseg, int B, TileTab& tab, const Tuning& tun) {
+  if (tun.tiling == 2 || kSW != 4) return make_tile_tab_linear(H, nseg, B, tab, tun);
   tab = TileTab{};
   // 420 of the 444 resident slots: filling every slot makes a lone launch ~3 % shorter still, but then the small
   // launches of OTHER streams (coarse levels of independent batches) find no free slot and the multi-stream
   // throughput drops by 5 % (profiles/exp9.sh)
   long slots = 148L * DPFT_STAGED_CTAS * 35 / 37;
-  if (const char* e = getenv("DPFT_CTA_SLOTS")) slots = std::max(1L, atol(e));
-  if (getenv("DPFT_RECT_TILES")) return false;
+  if (tun.cta_slots > 0) slots = tun.cta_slots;
+  if (tun.tiling == 1) return false;
   const int c0 = (int)(slots / B);               // CTAs per pair of kind 0; kind 1 has one more
   const int n_more = (int)(slots - (long)c0 * B);
   if (c0 < 1 || (c0 + 1) * kSW > kTabWarps || kSW * c0 < nseg) return false;
@@ -888,7 +907,7 @@ static bool make_tile_tab(int H, int nseg, int B, TileTab& tab) {
 }
 
 static Plan make_plan(const dpft_level_t* lv, int n_levels, int B, int C, uint32_t flags, bool any_occ,
-                      int p_grid) {
+                      int p_grid, const Tuning& tun) {
   Plan pl{};
   pl.max_ctas = 1;
   pl.max_plane = 0;
@@ -897,12 +916,12 @@ static Plan make_plan(const dpft_level_t* lv, int n_levels, int B, int C, uint32
     const int cols = staged ? kStagedCols : kCols;
     pl.nseg[l] = (lv[l].W + cols - 1) / cols;
     const int cta_warps = staged ? kSW : kWarps;
-    pl.TR[l] = pick_tile_rows(lv[l].H, pl.nseg[l], B, staged ? DPFT_STAGED_CTAS : DPFT_MIN_CTAS, cta_warps);
+    pl.TR[l] = pick_tile_rows(lv[l].H, pl.nseg[l], B, staged ? DPFT_STAGED_CTAS : DPFT_MIN_CTAS, cta_warps, tun);
     pl.nrt[l] = (lv[l].H + pl.TR[l] - 1) / pl.TR[l];
     pl.ctas[l] = (pl.nseg[l] * pl.nrt[l] + cta_warps - 1) / cta_warps;
     pl.tab[l].on = 0;
     if ((flags & DPFT_STAGED_FOOTPRINT) && (flags & DPFT_FUSED_SOBEL) && staged_ok(lv[l], C) && lv[l].H < 32768 &&
-        make_tile_tab(lv[l].H, pl.nseg[l], B, pl.tab[l]))
+        make_tile_tab(lv[l].H, pl.nseg[l], B, pl.tab[l], tun))
       pl.ctas[l] = pl.tab[l].ctas[1];   // grid.x and the record stride
     if (pl.ctas[l] > pl.max_ctas) pl.max_ctas = pl.ctas[l];
     const size_t plane = (size_t)lv[l].H * lv[l].W;
@@ -971,12 +990,30 @@ static int check_args(const dpft_level_t* lv, int n_levels, int B, int C, int it
       return set_error(DPFT_EINVAL, "level %d: x0, x1, sigma0, sigma1, invd0, invd1 and K are required", l);
     if ((flags & DPFT_COMBINE_ICP) && (!L.depth0 || !L.depth1))
       return set_error(DPFT_EINVAL, "level %d: DPFT_COMBINE_ICP needs depth0 and depth1", l);
+    if ((flags & DPFT_PAIRWISE_EXTREMES) && (flags & DPFT_REMOVE_TRU_SIGMA) && L.occ_out)
+      return set_error(DPFT_EINVAL, "level %d: occ_out is not produced with DPFT_PAIRWISE_EXTREMES", l);
   }
+  // Flag mixes no kernel serves.  The keyframe-side tensors of DPFT_SHARED_KEYFRAME have batch size 1, which only
+  // the fused U_IC kernels index accordingly: the materialised-gradient pass and the ICP term would read past them.
+  if ((flags & (DPFT_SHARED_KEYFRAME | DPFT_PAIRWISE_EXTREMES)) && ((flags & DPFT_COMBINE_ICP) || !(flags & DPFT_FUSED_SOBEL)))
+    return set_error(DPFT_EINVAL, "DPFT_SHARED_KEYFRAME / DPFT_PAIRWISE_EXTREMES need DPFT_FUSED_SOBEL and exclude DPFT_COMBINE_ICP");
+  if ((flags & DPFT_SIGMA_BROADCAST) && !(flags & DPFT_FUSED_SOBEL))
+    return set_error(DPFT_EINVAL, "DPFT_SIGMA_BROADCAST needs the fused kernels (DPFT_FUSED_SOBEL)");
+  return 0;
+}
+
+// the sigma-extreme group of the options: a divisor of B, and only the queue path knows groups other than B and 1
+static int check_group(int B, uint32_t flags, const Tuning& tun, bool queue) {
+  if (tun.group < 0 || (tun.group > 0 && B % tun.group != 0))
+    return set_error(DPFT_EINVAL, "options.group (%d) must divide B (%d)", tun.group, B);
+  if (tun.group > 0 && tun.group != B && !queue && !(tun.group == 1 && (flags & DPFT_PAIRWISE_EXTREMES)))
+    return set_error(DPFT_EINVAL, "options.group = %d needs the work-queue path (DPFT_QUEUE, C == 8, fused, no ICP, no occ_out)", tun.group);
   return 0;
 }
 
 template <int CH>
-static cudaError_t launch_iter(const UicIterParams& prm, dim3 grid, bool tru, bool pdl, cudaStream_t stream) {
+static cudaError_t launch_iter(const UicIterParams& prm, dim3 grid, bool tru, bool pdl, cudaStream_t stream,
+                               const Tuning& tun) {
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = grid;
   cfg.blockDim = dim3(kThreads);
@@ -988,7 +1025,7 @@ static cudaError_t launch_iter(const UicIterParams& prm, dim3 grid, bool tru, bo
   cfg.attrs = attr;
   cfg.numAttrs = pdl ? 1 : 0;
   // the reference's pyramid sizes (TUM 160x120 ... and 640x480 ...) run geometry-specialised instantiations
-  if (CH == 8 && !getenv("DPFT_GENERIC_GEOMETRY")) {
+  if (CH == 8 && !tun.generic_geometry) {
 #define DPFT_FIXED(w, h)                                                                     \
     if (prm.W == w && prm.H == h)                                                            \
       return tru ? cudaLaunchKernelEx(&cfg, uic_iter_kernel<8, true, w, h>, prm)             \
@@ -1023,7 +1060,8 @@ static bool encode_row_map(CUtensorMap* tm, const float* base, int W, int H, int
 }
 #endif
 
-static cudaError_t launch_staged(const UicIterParams& prm_in, dim3 grid, bool tru, bool pdl, cudaStream_t stream) {
+static cudaError_t launch_staged(const UicIterParams& prm_in, dim3 grid, bool tru, bool pdl, cudaStream_t stream,
+                                 const Tuning& tun) {
   UicIterParams prm = prm_in;
 #if DPFT_STAGED_TMA
   if (!encode_row_map(&prm.tm_x1, prm.x1, prm.W, prm.H, prm.C, prm.B) ||
@@ -1057,7 +1095,7 @@ static cudaError_t launch_staged(const UicIterParams& prm_in, dim3 grid, bool tr
   } while (0)
   const bool aux = prm.m0 || prm.m1 || prm.occ_out;
   const bool sb = prm.SC != prm.C;
-  if (!getenv("DPFT_GENERIC_GEOMETRY")) {
+  if (!tun.generic_geometry) {
     if (prm.W == 160 && prm.H == 120) {
       if (sb) { if (tru) DPFT_STAGED(true, true, 160, 120); else DPFT_STAGED(false, true, 160, 120); }
       if (tru) DPFT_STAGED(true, false, 160, 120); else DPFT_STAGED(false, false, 160, 120);
@@ -1100,36 +1138,192 @@ static bool persistent_ok(uint32_t flags, bool any_occ) {
                     DPFT_SIGMA_BROADCAST));
 }
 
+// co-resident CTAs of the cooperative kernel: an occupancy query per (device, instantiation), remembered (the answer
+// is a property of the device and the binary; racing first calls compute the same value)
 static int persistent_grid_cached(int C, bool tru) {
-  static int cache[2][4] = {{0, 0, 0, 0}, {0, 0, 0, 0}};
+  constexpr int kMaxDev = 64;
+  static int cache[kMaxDev][2][4] = {};
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= kMaxDev) return std::max(persistent_grid(C, tru), -1);
   const int idx = (C % 8 == 0) ? 3 : (C % 4 == 0) ? 2 : (C % 2 == 0) ? 1 : 0;
-  if (!cache[tru][idx]) cache[tru][idx] = std::max(persistent_grid(C, tru), -1);
-  return cache[tru][idx];
+  if (!cache[dev][tru][idx]) cache[dev][tru][idx] = std::max(persistent_grid(C, tru), -1);
+  return cache[dev][tru][idx];
+}
+
+// ------------------------------------------------------------------------------------------- queue path (uic_queue.cu)
+struct QPlan {
+  bool on = false;
+  int nseg[DPFT_MAX_LEVELS], TR[DPFT_MAX_LEVELS], nrt[DPFT_MAX_LEVELS], tpp[DPFT_MAX_LEVELS], kind[DPFT_MAX_LEVELS];
+  int group = 0, n_groups = 0, n_mm_groups = 0, max_tiles = 0, grid = 0;
+  size_t total_items = 0;
+  size_t off_fifo, off_qctl, off_tiles_done, off_cand, off_pairs_done, off_groups_done, off_gext, off_mm, off_records,
+      off_pairrec, off_tdone, off_aux, total = 0;
+};
+
+static int device_sms() {
+  int dev = 0, sms = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess ||
+      sms < 1)
+    sms = 148;
+  return sms;
+}
+
+// Rows per tile of the queue path.  Workers are warps; an iteration of a level offers B * nseg * ceil(H / TR) tiles.
+// A tile costs its rows plus ~3 rows of fixed work (claim, pose, window and ring priming, record, counters) and a
+// pair's iteration is over when its last tile is, so: as few waves of tiles as possible, and within that small tiles.
+static int queue_tile_rows(int H, int nseg, int B, long workers) {
+  int best_tr = 1;
+  double best = 1e30;
+  for (int tr = 1; tr <= std::min(H, 64); ++tr) {
+    const long nrt = (H + tr - 1) / tr;
+    const int tr_eff = (int)((H + nrt - 1) / nrt);          // equal tiles: ceil(H / nrt) rows
+    const long tiles = nrt * nseg * B;
+    const long waves = (tiles + workers - 1) / workers;
+    const double cost = (double)waves * (tr_eff + 3.0) + 0.25 * (double)((nrt * nseg + 7) / 8);
+    if (cost < best - 1e-9) { best = cost; best_tr = tr_eff; }
+  }
+  return best_tr;
+}
+
+static bool queue_wanted(int C, int iters, uint32_t flags, bool any_occ) {
+  return (flags & DPFT_QUEUE) && (flags & DPFT_FUSED_SOBEL) && !(flags & DPFT_COMBINE_ICP) && !any_occ && C == 8 && iters >= 1;
+}
+
+static QPlan make_qplan(const dpft_level_t* lv, int n_levels, int B, int C, int iters, uint32_t flags, const Tuning& tun) {
+  QPlan q;
+  q.on = true;
+  q.group = tun.group > 0 ? tun.group : ((flags & DPFT_PAIRWISE_EXTREMES) ? 1 : B);
+  q.n_groups = B / q.group;
+  q.n_mm_groups = (flags & DPFT_SHARED_KEYFRAME) ? 1 : q.n_groups;
+  const int sms = device_sms();
+  const long workers = (long)sms * queue_tiles_per_sm();
+  long widest = 1;
+  for (int l = 0; l < n_levels; ++l) {
+    const bool staged = (flags & DPFT_STAGED_FOOTPRINT) && staged_ok(lv[l], C);
+    q.kind[l] = staged ? 1 : 0;
+    q.nseg[l] = (lv[l].W + kCols - 1) / kCols;
+    int tr = tun.tile_rows[l] > 0 ? std::min(tun.tile_rows[l], (int)lv[l].H) : queue_tile_rows(lv[l].H, q.nseg[l], B, workers);
+    if (staged) tr = std::max(tr, 1);
+    q.nrt[l] = (lv[l].H + tr - 1) / tr;
+    q.TR[l] = (lv[l].H + q.nrt[l] - 1) / q.nrt[l];
+    q.nrt[l] = (lv[l].H + q.TR[l] - 1) / q.TR[l];
+    q.tpp[l] = q.nseg[l] * q.nrt[l];
+    q.max_tiles = std::max(q.max_tiles, q.tpp[l]);
+    q.total_items += (size_t)iters * B * q.tpp[l];
+    widest = std::max(widest, (long)B * q.tpp[l]);
+  }
+  const int full = sms * 3;
+  q.grid = tun.queue_ctas > 0 ? tun.queue_ctas : (int)std::min<long>(full, (widest + 3) / 4);
+  const int n_it = n_levels * iters;
+  size_t off = 0;
+  auto take = [&](size_t bytes) {
+    const size_t o = off;
+    off += (bytes + 255) & ~(size_t)255;
+    return o;
+  };
+  q.off_fifo = take(q.total_items * sizeof(unsigned long long));
+  q.off_qctl = take(2 * sizeof(unsigned));
+  q.off_tiles_done = take((size_t)B * sizeof(int));
+  q.off_cand = take((size_t)B * sizeof(int));
+  q.off_pairs_done = take((size_t)n_it * q.n_groups * sizeof(int));
+  q.off_groups_done = take((size_t)n_it * sizeof(int));
+  q.off_gext = take((size_t)n_it * q.n_groups * 2 * sizeof(uint32_t));
+  q.off_mm = take((size_t)n_levels * q.n_mm_groups * 2 * sizeof(uint32_t));
+  q.off_records = take((size_t)B * q.max_tiles * PS * sizeof(float));
+  q.off_pairrec = take((size_t)B * PS * sizeof(double));
+  q.off_tdone = take((size_t)(n_it + 1) * sizeof(unsigned long long));
+  q.off_aux = take((size_t)n_it * q.n_groups * 4 * sizeof(float));
+  q.total = off;
+  return q;
+}
+
+static int run_queue(const dpft_level_t* levels, int n_levels, int B, int C, int iters, uint32_t flags,
+                     const float* pose_in, float* pose_hist, float* sys_hist, float* aux_hist, int32_t* status,
+                     void* workspace, size_t workspace_bytes, cudaStream_t stream, const Tuning& tun) {
+  const QPlan q = make_qplan(levels, n_levels, B, C, iters, flags, tun);
+  if (workspace_bytes < q.total) return set_error(DPFT_ENOSPACE, "workspace has %zu bytes, %zu needed", workspace_bytes, q.total);
+  if (q.total_items >= (1ull << 32) || q.max_tiles >= (1 << 20) || n_levels * iters >= (1 << 19))
+    return set_error(DPFT_EINVAL, "problem too large for the work queue's item encoding");
+  char* ws = (char*)workspace;
+  QueueParams prm{};
+  for (int l = 0; l < n_levels; ++l) {
+    const dpft_level_t& L = levels[l];
+    QLevel& v = prm.lv[l];
+    v.x0 = L.x0; v.x1 = L.x1; v.s0 = L.sigma0; v.s1 = L.sigma1; v.d0 = L.invd0; v.d1 = L.invd1; v.K = L.K;
+    v.m0 = L.obj_mask0; v.m1 = L.obj_mask1;
+    v.H = L.H; v.W = L.W; v.nseg = q.nseg[l]; v.TR = q.TR[l]; v.nrt = q.nrt[l]; v.tpp = q.tpp[l]; v.kind = q.kind[l];
+  }
+  prm.n_levels = n_levels; prm.iters = iters; prm.B = B; prm.C = C;
+  prm.SC = (flags & DPFT_SIGMA_BROADCAST) ? 1 : C;
+  prm.group = q.group; prm.n_groups = q.n_groups; prm.n_mm_groups = q.n_mm_groups;
+  prm.max_tiles = q.max_tiles; prm.kf_shared = (flags & DPFT_SHARED_KEYFRAME) ? 1 : 0;
+  prm.total_items = (unsigned)q.total_items;
+  prm.pose_hist = pose_hist; prm.sys_hist = sys_hist;
+  prm.aux = aux_hist ? aux_hist : (float*)(ws + q.off_aux);
+  prm.records = (float*)(ws + q.off_records);
+  prm.pairrec = (double*)(ws + q.off_pairrec);
+  prm.fifo = (unsigned long long*)(ws + q.off_fifo);
+  prm.qctl = (unsigned*)(ws + q.off_qctl);
+  prm.tiles_done = (int*)(ws + q.off_tiles_done);
+  prm.cand = (int*)(ws + q.off_cand);
+  prm.pairs_done = (int*)(ws + q.off_pairs_done);
+  prm.groups_done = (int*)(ws + q.off_groups_done);
+  prm.gext = (uint32_t*)(ws + q.off_gext);
+  prm.s0mm = prm.s0mm_rw = (uint32_t*)(ws + q.off_mm);
+  prm.status = status;
+  prm.t_done = tun.launch_ms ? (unsigned long long*)(ws + q.off_tdone) : nullptr;
+  if (tun.generic_geometry)
+    for (int l = 0; l < n_levels; ++l) prm.lv[l].kind = std::min(prm.lv[l].kind, 1);
+  cudaError_t err = launch_queue(prm, pose_in, flags & DPFT_REMOVE_TRU_SIGMA, q.grid, stream, !tun.generic_geometry);
+  if (err != cudaSuccess) return set_error((int)err, "work-queue launch: %s", cudaGetErrorString(err));
+  if (tun.launch_ms) {
+    const int n = n_levels * iters;
+    unsigned long long stamps[DPFT_MAX_LEVELS * 64 + 1];
+    err = cudaMemcpyAsync(stamps, prm.t_done, (n + 1) * sizeof(unsigned long long), cudaMemcpyDeviceToHost, stream);
+    if (err == cudaSuccess) err = cudaStreamSynchronize(stream);
+    if (err != cudaSuccess) return set_error((int)err, "stamp read-back: %s", cudaGetErrorString(err));
+    for (int i = 0; i < n; ++i) tun.launch_ms[i] = (float)((double)(stamps[i + 1] - stamps[i]) * 1e-6);
+  }
+  return 0;
+}
+
+extern "C" size_t dpft_uic_workspace_bytes_ex(const dpft_level_t* levels, int n_levels, int B, int C, int iters,
+                                              uint32_t flags, const dpft_uic_options_t* opt) {
+  if (check_args(levels, n_levels, B, C, iters, flags)) return 0;
+  const Tuning tun = tuning_of(opt);
+  bool any_occ = false;
+  for (int l = 0; l < n_levels; ++l) any_occ = any_occ || levels[l].occ_out;
+  const bool queue = queue_wanted(C, iters, flags, any_occ);
+  if (check_group(B, flags, tun, queue)) return 0;
+  if (queue) return make_qplan(levels, n_levels, B, C, iters, flags, tun).total;
+  const int pg = persistent_ok(flags, any_occ) ? persistent_grid_cached(C, flags & DPFT_REMOVE_TRU_SIGMA) : 0;
+  return make_plan(levels, n_levels, B, C, flags, any_occ, std::max(pg, 0), tun).total;
 }
 
 extern "C" size_t dpft_uic_workspace_bytes(const dpft_level_t* levels, int n_levels, int B, int C, int iters,
                                            uint32_t flags) {
-  if (check_args(levels, n_levels, B, C, iters, flags)) return 0;
-  bool any_occ = false;
-  for (int l = 0; l < n_levels; ++l) any_occ = any_occ || levels[l].occ_out;
-  const int pg = persistent_ok(flags, any_occ) ? persistent_grid_cached(C, flags & DPFT_REMOVE_TRU_SIGMA) : 0;
-  return make_plan(levels, n_levels, B, C, flags, any_occ, std::max(pg, 0)).total;
+  return dpft_uic_workspace_bytes_ex(levels, n_levels, B, C, iters, flags, nullptr);
 }
 
 static int run_uic(const dpft_level_t* levels, int n_levels, int B, int C, int iters, uint32_t flags,
                    float w_icp, const float* pose_in, float* pose_hist, float* sys_hist, float* aux_hist,
                    int32_t* status, void* workspace, size_t workspace_bytes, void* stream_, cudaEvent_t* ev,
-                   unsigned long long* clock_host) {
+                   unsigned long long* clock_host, const Tuning& tun) {
   if (iters > 64) return set_error(DPFT_EINVAL, "iters must be <= 64");
   if (int e = check_args(levels, n_levels, B, C, iters, flags)) return e;
   if (!pose_in || !pose_hist || !status || (iters > 0 && !sys_hist) || !workspace)
     return set_error(DPFT_EINVAL, "pose_in, pose_hist, sys_hist, status and workspace are required");
   bool any_occ = false;
   for (int l = 0; l < n_levels; ++l) any_occ = any_occ || levels[l].occ_out;
+  const bool queue = queue_wanted(C, iters, flags, any_occ);
+  if (int e = check_group(B, flags, tun, queue)) return e;
+  if (queue)
+    return run_queue(levels, n_levels, B, C, iters, flags, pose_in, pose_hist, sys_hist, aux_hist, status, workspace,
+                     workspace_bytes, (cudaStream_t)stream_, tun);
   if (ev && !clock_host) flags |= DPFT_LAUNCH_PER_ITERATION;   // event timing needs separate launches
   const bool persist = persistent_ok(flags, any_occ) && persistent_grid_cached(C, flags & DPFT_REMOVE_TRU_SIGMA) > 0;
   const Plan pl = make_plan(levels, n_levels, B, C, flags, any_occ,
-                            persist ? persistent_grid_cached(C, flags & DPFT_REMOVE_TRU_SIGMA) : 0);
+                            persist ? persistent_grid_cached(C, flags & DPFT_REMOVE_TRU_SIGMA) : 0, tun);
   if (workspace_bytes < pl.total) return set_error(DPFT_ENOSPACE, "workspace has %zu bytes, %zu needed", workspace_bytes, pl.total);
   cudaStream_t stream = (cudaStream_t)stream_;
   char* ws = (char*)workspace;
@@ -1144,8 +1338,6 @@ static int run_uic(const dpft_level_t* levels, int n_levels, int B, int C, int i
   const bool fused = flags & DPFT_FUSED_SOBEL;
   const bool icp = flags & DPFT_COMBINE_ICP;
   const int SC = (flags & DPFT_SIGMA_BROADCAST) ? 1 : C;     // channels of the sigma maps
-  if (SC != C && !fused)
-    return set_error(DPFT_EINVAL, "DPFT_SIGMA_BROADCAST needs the fused kernels (DPFT_FUSED_SOBEL)");
   float* grad = (float*)(ws + pl.off_grad);
   float* vn = (float*)(ws + pl.off_vn);
   float* icp_rec = (float*)(ws + pl.off_icp);
@@ -1257,13 +1449,13 @@ static int run_uic(const dpft_level_t* levels, int n_levels, int B, int C, int i
           default: err = launch_px<1>(prm, ex, grid, tru, use_pdl, stream); break;
         }
       } else if ((flags & DPFT_STAGED_FOOTPRINT) && staged_ok(L, C)) {
-        err = launch_staged(prm, grid, tru, use_pdl, stream);
+        err = launch_staged(prm, grid, tru, use_pdl, stream, tun);
       } else
       switch (CH) {
-        case 8: err = launch_iter<8>(prm, grid, tru, use_pdl, stream); break;
-        case 4: err = launch_iter<4>(prm, grid, tru, use_pdl, stream); break;
-        case 2: err = launch_iter<2>(prm, grid, tru, use_pdl, stream); break;
-        default: err = launch_iter<1>(prm, grid, tru, use_pdl, stream); break;
+        case 8: err = launch_iter<8>(prm, grid, tru, use_pdl, stream, tun); break;
+        case 4: err = launch_iter<4>(prm, grid, tru, use_pdl, stream, tun); break;
+        case 2: err = launch_iter<2>(prm, grid, tru, use_pdl, stream, tun); break;
+        default: err = launch_iter<1>(prm, grid, tru, use_pdl, stream, tun); break;
       }
       if (err != cudaSuccess) return set_error((int)err, "uic_iter_kernel launch: %s", cudaGetErrorString(err));
       if (tru && prm.occ_out) {
@@ -1278,35 +1470,32 @@ static int run_uic(const dpft_level_t* levels, int n_levels, int B, int C, int i
   return 0;
 }
 
-extern "C" int dpft_uic_forward(const dpft_level_t* levels, int n_levels, int B, int C, int iters, uint32_t flags,
-                                float w_icp, const float* pose_in, float* pose_hist, float* sys_hist,
-                                float* aux_hist, int32_t* status, void* workspace, size_t workspace_bytes,
-                                void* stream) {
-  return run_uic(levels, n_levels, B, C, iters, flags, w_icp, pose_in, pose_hist, sys_hist, aux_hist, status,
-                 workspace, workspace_bytes, stream, nullptr, nullptr);
-}
-
-extern "C" int dpft_uic_forward_timed(const dpft_level_t* levels, int n_levels, int B, int C, int iters,
-                                      uint32_t flags, float w_icp, const float* pose_in, float* pose_hist,
-                                      float* sys_hist, float* aux_hist, int32_t* status, void* workspace,
-                                      size_t workspace_bytes, void* stream, float* launch_ms) {
-  if (!launch_ms || n_levels < 1 || n_levels > DPFT_MAX_LEVELS || iters < 1 || iters > 64)
-    return set_error(DPFT_EINVAL, "launch_ms is required and iters must be 1..64");
+static int forward_timed(const dpft_level_t* levels, int n_levels, int B, int C, int iters, uint32_t flags, float w_icp,
+                         const float* pose_in, float* pose_hist, float* sys_hist, float* aux_hist, int32_t* status,
+                         void* workspace, size_t workspace_bytes, void* stream, const Tuning& tun) {
+  float* launch_ms = tun.launch_ms;
+  if (n_levels < 1 || n_levels > DPFT_MAX_LEVELS || iters < 1 || iters > 64)
+    return set_error(DPFT_EINVAL, "timing needs 1..%d levels and 1..64 iterations", DPFT_MAX_LEVELS);
   const int n = n_levels * iters;
   bool any_occ = false;
   for (int l = 0; l < n_levels; ++l) any_occ = any_occ || levels[l].occ_out;
+  if (queue_wanted(C, iters, flags, any_occ))   // one launch: iteration completions are stamped on the device
+    return run_uic(levels, n_levels, B, C, iters, flags, w_icp, pose_in, pose_hist, sys_hist, aux_hist, status, workspace,
+                   workspace_bytes, stream, nullptr, nullptr, tun);
+  Tuning plain = tun;
+  plain.launch_ms = nullptr;
   if (persistent_ok(flags, any_occ) && persistent_grid_cached(C, flags & DPFT_REMOVE_TRU_SIGMA) > 0) {
     // single cooperative launch: iteration boundaries are stamped on the device with %globaltimer
     unsigned long long stamps[DPFT_MAX_LEVELS * 64 + 1];
     const int rc = run_uic(levels, n_levels, B, C, iters, flags, w_icp, pose_in, pose_hist, sys_hist, aux_hist, status,
-                           workspace, workspace_bytes, stream, nullptr, stamps);
+                           workspace, workspace_bytes, stream, nullptr, stamps, plain);
     for (int i = 0; i < n && rc == 0; ++i) launch_ms[i] = (float)((double)(stamps[i + 1] - stamps[i]) * 1e-6);
     return rc;
   }
   cudaEvent_t ev[DPFT_MAX_LEVELS * 64 + 1];
   for (int i = 0; i <= n; ++i) cudaEventCreate(&ev[i]);
   int rc = run_uic(levels, n_levels, B, C, iters, flags, w_icp, pose_in, pose_hist, sys_hist, aux_hist, status,
-                   workspace, workspace_bytes, stream, ev, nullptr);
+                   workspace, workspace_bytes, stream, ev, nullptr, plain);
   if (rc == 0) {
     const cudaError_t err = cudaStreamSynchronize((cudaStream_t)stream);
     if (err != cudaSuccess) rc = set_error((int)err, "sync: %s", cudaGetErrorString(err));
@@ -1316,6 +1505,37 @@ extern "C" int dpft_uic_forward_timed(const dpft_level_t* levels, int n_levels, 
   return rc;
 }
 
+extern "C" int dpft_uic_forward_ex(const dpft_level_t* levels, int n_levels, int B, int C, int iters, uint32_t flags,
+                                   float w_icp, const float* pose_in, float* pose_hist, float* sys_hist,
+                                   float* aux_hist, int32_t* status, void* workspace, size_t workspace_bytes,
+                                   void* stream, const dpft_uic_options_t* opt) {
+  const Tuning tun = tuning_of(opt);
+  if (tun.launch_ms)
+    return forward_timed(levels, n_levels, B, C, iters, flags, w_icp, pose_in, pose_hist, sys_hist, aux_hist, status,
+                         workspace, workspace_bytes, stream, tun);
+  return run_uic(levels, n_levels, B, C, iters, flags, w_icp, pose_in, pose_hist, sys_hist, aux_hist, status,
+                 workspace, workspace_bytes, stream, nullptr, nullptr, tun);
+}
+
+extern "C" int dpft_uic_forward(const dpft_level_t* levels, int n_levels, int B, int C, int iters, uint32_t flags,
+                                float w_icp, const float* pose_in, float* pose_hist, float* sys_hist,
+                                float* aux_hist, int32_t* status, void* workspace, size_t workspace_bytes,
+                                void* stream) {
+  return dpft_uic_forward_ex(levels, n_levels, B, C, iters, flags, w_icp, pose_in, pose_hist, sys_hist, aux_hist, status,
+                             workspace, workspace_bytes, stream, nullptr);
+}
+
+extern "C" int dpft_uic_forward_timed(const dpft_level_t* levels, int n_levels, int B, int C, int iters,
+                                      uint32_t flags, float w_icp, const float* pose_in, float* pose_hist,
+                                      float* sys_hist, float* aux_hist, int32_t* status, void* workspace,
+                                      size_t workspace_bytes, void* stream, float* launch_ms) {
+  if (!launch_ms) return set_error(DPFT_EINVAL, "launch_ms is required");
+  Tuning tun;
+  tun.launch_ms = launch_ms;
+  return forward_timed(levels, n_levels, B, C, iters, flags, w_icp, pose_in, pose_hist, sys_hist, aux_hist, status,
+                       workspace, workspace_bytes, stream, tun);
+}
+
 // Host-side view of the balanced tile table of one level (test hook, not part of the ABI): returns 1 and fills
 // `tiles` ([2 kinds][max_warps][2 sub-tiles][seg, y0, y1]), `ctas` (CTAs per pair of kind 0 / 1), `n_more` (pairs of
 // kind 1), `nseg` and `warps_per_cta` when a table is used for (H, W, B), 0 when the rectangular tiling stays.
@@ -1323,7 +1543,8 @@ extern "C" int dpft_debug_tile_table(int H, int W, int B, int linear, int max_wa
                                      int* n_more, int* nseg, int* warps_per_cta) {
   TileTab tab;
   const int ns = (W + kStagedCols - 1) / kStagedCols;
-  const bool on = linear ? make_tile_tab_linear(H, ns, B, tab) : make_tile_tab(H, ns, B, tab);
+  const Tuning tun;
+  const bool on = linear ? make_tile_tab_linear(H, ns, B, tab, tun) : make_tile_tab(H, ns, B, tab, tun);
   *nseg = ns;
   *warps_per_cta = kSW;
   if (!on) return 0;

@@ -21,6 +21,7 @@
 #include "dpft_host.h"
 #include "dpft_kernels.h"
 #include "dpft_records.h"
+#include "uic_reduce.cuh"
 #include "uic_tile.cuh"
 
 namespace cg = cooperative_groups;
@@ -31,44 +32,16 @@ namespace dpft {
 #define DPFT_MIN_CTAS 4
 #endif
 
-constexpr int kPT = 128, kPW = kPT / 32;
+#ifndef DPFT_WARPS
+#define DPFT_WARPS 4
+#endif
+// the plan (make_plan in uic_forward.cu) sizes the record slots with DPFT_WARPS warps per CTA: one constant for both
+constexpr int kPW = DPFT_WARPS, kPT = kPW * 32;
 
 __device__ __forceinline__ unsigned long long global_ns() {
   unsigned long long t;
   asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
   return t;
-}
-
-template <bool TRU>
-__device__ __forceinline__ void flush_warp(TileSums& S, float (*red)[33], float* __restrict__ rec, const int lane) {
-  float wmn = 0.f, wmx = 0.f;
-  if (TRU) {
-    wmn = warp_min(S.vmin);
-    wmx = warp_max(S.vmax);
-    if (S.vmin != wmn) {
-#pragma unroll
-      for (int i = 0; i < 6; ++i) red[27 + i][lane] = 0.f;
-    }
-    if (S.vmax != wmx) {
-#pragma unroll
-      for (int i = 0; i < 6; ++i) red[33 + i][lane] = 0.f;
-    }
-  }
-#pragma unroll
-  for (int e = 0; e < 27; ++e) red[e][lane] = S.acc[e];
-  __syncwarp();
-  constexpr int NE = TRU ? NSUM : 27;
-  for (int e = lane; e < NE; e += 32) {
-    double s = 0.0;
-#pragma unroll 8
-    for (int j = 0; j < 32; ++j) s += (double)red[e][j];
-    rec[e < 27 ? e : e + 2] = (float)s;
-  }
-  if (TRU && lane == 0) {
-    rec[E_VMIN] = wmn;
-    rec[E_VMAX] = wmx;
-  }
-  __syncwarp();
 }
 
 template <int CH, bool TRU>

@@ -1,0 +1,502 @@
+// U_IC forward as ONE launch driven by a work queue: every pyramid level and every Gauss-Newton iteration of every
+// frame pair, with the dependencies of the algorithm expressed per PAIR instead of per launch.
+//
+// Why.  With one launch per iteration (uic_forward.cu) every iteration of every level ends in a drain: the launch is as
+// long as its slowest warp, then a chain of hand-offs (CTA sums -> pair sums -> batch extremes -> 64 solves) runs on a
+// nearly idle machine, then the next launch starts.  The in-kernel timeline of round 1 put a third of a finest-level
+// launch into that drain, and a coarse-level launch is little else.  But the algorithm only orders the iterations of ONE
+// pair (iteration k+1 of a pair needs the pose iteration k gave it); pairs do not wait for each other -- with one
+// exception, the batch-global sigma extremes of remove_tru_sigma (algorithms.py:1976-1979), handled below.
+//
+// How.  A unit of work is a warp tile (30 columns x TR rows of one pair at one iteration), the same tile routines as
+// the launch-per-iteration kernels walk it (uic_tile.cuh / uic_tile_staged.cuh).  Warps are workers: a worker takes
+// the next slot of a FIFO in global memory (one atomicAdd), waits until the slot holds an item, walks the tile and
+// writes one record.  The worker that completes the LAST tile of a pair-iteration folds the pair's records in tile
+// order (fp64, deterministic whoever ran which tile), damps and solves the 6x6 system, writes the pose of iteration
+// k+1 and appends that iteration's tiles to the FIFO.  Nothing ever waits for a launch boundary; pairs drift apart and
+// the drain of one is hidden behind the tiles of the others.  Several independent batches ("groups") may share a
+// launch, which is what keeps the machine full while a batch is in its small coarse levels.
+//
+// Batch-global sigma extremes without a barrier.  A pixel is masked when its warped sigma equals the minimum or the
+// maximum over the whole batch (group).  The mask only moves J^T r, and every record carries what its extreme pixels
+// added (uic_forward.cu: finalize_pair), so a pair only has to know whether ITS extreme is the group's.  When a pair
+// is folded it merges its extremes into the group's running extremes with atomicMin / atomicMax: if the running value
+// was already beyond the pair's, the pair can never be the group's extreme (the running value only moves outwards)
+// and it is solved at once.  Otherwise it is a candidate: its sums are parked and the LAST pair of the group to be
+// folded -- which sees the final extremes -- solves the candidates.  Typically two pairs of 64 wait; with saturated
+// sigma maps (ties) all of them do, which degrades to the barrier the reference has, never to a wrong mask.
+//
+// Progress.  Slots are claimed in order and an item is only ever waited for by a worker that holds no other item, so
+// every claimed item is being walked by a resident warp and the item a waiting worker needs is produced by them: no
+// co-residency guarantee (cooperative launch) is needed.  A wait that exceeds kWaitLimitNs traps instead of hanging.
+#include <cuda_runtime.h>
+#include <math_constants.h>
+#include <stdint.h>
+
+#include <algorithm>
+
+#include "dpft.h"
+#include "dpft_device.cuh"
+#include "dpft_host.h"
+#include "dpft_kernels.h"
+#include "dpft_records.h"
+#include "uic_reduce.cuh"
+#include "uic_tile.cuh"
+#include "uic_tile_staged.cuh"
+
+namespace dpft {
+
+constexpr int kQW = 4;                 // warps (workers) per CTA
+constexpr int kQThreads = kQW * 32;
+constexpr int kQCtasPerSm = 3;
+// per-worker shared memory: the staged routine's area (ring | corrections | outlier taps | halo sums), then the pose
+constexpr int kQAreaFloats = kStageAreaFloats + 32;
+constexpr unsigned long long kWaitLimitNs = 4000000000ull;   // a worker that waits this long for an item traps
+constexpr unsigned long long kItemValid = 1ull << 63;
+
+static_assert(kStageWarpFloats - 27 * 33 >= 2 * PS, "the fold's fp64 scratch sits in front of the reduction rows");
+
+__device__ __forceinline__ unsigned long long q_encode(int k, int b, int t) {
+  return kItemValid | ((unsigned long long)k << 44) | ((unsigned long long)b << 20) | (unsigned long long)t;
+}
+__device__ __forceinline__ int q_item_k(unsigned long long it) { return (int)((it >> 44) & 0x7ffffu); }
+__device__ __forceinline__ int q_item_b(unsigned long long it) { return (int)((it >> 20) & 0xffffffu); }
+__device__ __forceinline__ int q_item_t(unsigned long long it) { return (int)(it & 0xfffffu); }
+__device__ __forceinline__ unsigned long long ld_acquire_u64(const unsigned long long* q) {
+  unsigned long long v;
+  asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(q) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_release_u64(unsigned long long* q, unsigned long long v) {
+  asm volatile("st.release.gpu.global.u64 [%0], %1;" ::"l"(q), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long q_now_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+
+// lane 0: wait until the slot holds an item (the producer may still be folding the pair that feeds it)
+__device__ __forceinline__ unsigned long long q_wait_item(const unsigned long long* slot) {
+  unsigned long long v = ld_acquire_u64(slot);
+  if (v) return v;
+  const unsigned long long t0 = q_now_ns();
+  unsigned ns = 64;
+  while (true) {
+    __nanosleep(ns);
+    v = ld_acquire_u64(slot);
+    if (v) return v;
+    if (ns < 1024) ns *= 2;
+    if (q_now_ns() - t0 > kWaitLimitNs) __trap();   // a lost item must not hang the device
+  }
+}
+
+// Damp, solve, update one pair (algorithms.py:2017-2054, 2094-2103) from its 39 folded sums.
+template <bool TRU, bool GLOBAL>
+__device__ __forceinline__ void q_finalize(const QueueParams& p, const int k, const int b, const double* rec,
+                                           const bool at_min, const bool at_max) {
+  auto ld = [&](int i) { return GLOBAL ? __ldcg(rec + i) : rec[i]; };
+  double A[21], rhs[6];
+#pragma unroll
+  for (int i = 0; i < 21; ++i) A[i] = ld(i);
+#pragma unroll
+  for (int i = 0; i < 6; ++i) rhs[i] = ld(21 + i);
+  if (TRU) {
+    // pixels whose warped sigma (channel 0) sits on the group's extreme are masked: their weighted residual becomes
+    // 1e-6, i.e. subtract what they added beyond that
+#pragma unroll
+    for (int i = 0; i < 6; ++i) {
+      if (at_min) rhs[i] -= ld(E_CMIN + i);
+      if (at_max) rhs[i] -= ld(E_CMAX + i);
+    }
+  }
+  bool finite = true;
+#pragma unroll
+  for (int i = 0; i < 21; ++i) finite = finite && isfinite(A[i]);
+#pragma unroll
+  for (int i = 0; i < 6; ++i) finite = finite && isfinite(rhs[i]);
+  float* sys = p.sys_hist + ((size_t)k * p.B + b) * 27;
+#pragma unroll
+  for (int i = 0; i < 21; ++i) sys[i] = (float)A[i];
+#pragma unroll
+  for (int i = 0; i < 6; ++i) sys[21 + i] = (float)rhs[i];
+  double xi[6];
+  const bool ok = solve_and_update(A, rhs, true, p.pose_hist + ((size_t)k * p.B + b) * 12,
+                                   p.pose_hist + ((size_t)(k + 1) * p.B + b) * 12, xi);
+  int st = 0;
+  if (!finite) st |= DPFT_ST_NONFINITE;
+  if (!ok) st |= DPFT_ST_SINGULAR;
+  if (st) atomicOr(p.status, st);
+}
+
+// Append the tiles of iteration k+1 of pair b (its pose has been written by this warp's lane 0).
+__device__ __forceinline__ void q_push_next(const QueueParams& p, const int k, const int b, const int lane) {
+  if (k + 1 >= p.n_levels * p.iters) return;
+  const int n = p.lv[(k + 1) / p.iters].tpp;
+  __threadfence();                       // the pose (lane 0) and everything before it, ahead of the items
+  __syncwarp();
+  unsigned pos = 0;
+  if (lane == 0) pos = atomicAdd(p.qctl + 1, (unsigned)n);
+  pos = __shfl_sync(0xffffffffu, pos, 0);
+  for (int i = lane; i < n; i += 32) st_release_u64(p.fifo + pos + i, q_encode(k + 1, b, i));
+}
+
+// One item: walk the tile, write its record, count it.  Returns true for the worker that completed the pair-iteration.
+// Not inlined on purpose: the tile routines want every register the launch bounds allow, and inside the worker loop
+// the loop's own state (item, level, queue pointers) pushed accumulators of the row loop out to local memory.
+template <bool TRU, bool SB, bool AUX, int GW, int GH>
+__device__ __noinline__ bool q_walk_item(const QueueParams& p, float* area, const unsigned long long item) {
+  const int lane = threadIdx.x & 31;
+  float (*redw)[33] = reinterpret_cast<float (*)[33]>(area + kStageWarpFloats - 27 * 33);   // rows 27.. follow the ring
+  float* spose = area + kStageAreaFloats;
+  // what the epilogue needs is parked in shared memory for the length of the tile walk (registers are what the row
+  // loop is short of) and decoded again afterwards
+  volatile unsigned long long* sitem = reinterpret_cast<volatile unsigned long long*>(spose + 16);
+  if (lane == 0) *sitem = item;
+  const int k = q_item_k(item), b = q_item_b(item), t = q_item_t(item);
+  const int B = p.B, C = p.C;
+  const int l = k / p.iters;
+  const QLevel& L = p.lv[l];
+  const int plane = L.H * L.W;
+
+  PairView g;
+  {
+    const size_t b0 = p.kf_shared ? 0 : (size_t)b;      // one keyframe for every pair (kf_vo-style tracking)
+    g.x0 = L.x0 + b0 * C * plane; g.x1 = L.x1 + (size_t)b * C * plane;
+    g.s0 = L.s0 + b0 * p.SC * plane; g.s1 = L.s1 + (size_t)b * p.SC * plane;
+    g.splane = (p.SC == C) ? (unsigned)plane : 0u;
+    g.d0 = L.d0 + b0 * plane; g.d1 = L.d1 + (size_t)b * plane;
+    g.m0 = (AUX && L.m0) ? L.m0 + b0 * plane : nullptr;
+    g.m1 = (AUX && L.m1) ? L.m1 + (size_t)b * plane : nullptr;
+    g.occ_out = nullptr; g.sr0_dbg = nullptr;
+    g.H = L.H; g.W = L.W; g.C = C;
+    g.fx = __ldg(L.K + 4 * b); g.fy = __ldg(L.K + 4 * b + 1); g.cx = __ldg(L.K + 4 * b + 2); g.cy = __ldg(L.K + 4 * b + 3);
+    g.s0lo = g.s0hi = 0.f;
+    g.b = b;
+    g.tm_x1 = g.tm_s1 = g.tm_d1 = nullptr;
+    if (TRU) {
+      const uint32_t* mm = p.s0mm + 2 * ((size_t)l * p.n_mm_groups + (p.n_mm_groups > 1 ? b / p.group : 0));
+      g.s0lo = ord2f(__ldcg(mm));
+      g.s0hi = ord2f(__ldcg(mm + 1));
+    }
+  }
+  __syncwarp();
+  if (lane < 12) spose[lane] = __ldcg(p.pose_hist + ((size_t)k * B + b) * 12 + lane);
+  if (TRU) {
+#pragma unroll
+    for (int i = 0; i < 12; ++i) redw[27 + i][lane] = 0.f;
+  }
+  __syncwarp();
+
+  TileSums S;
+  S.reset();
+  {
+    const int seg = t % L.nseg, rt = t / L.nseg;
+    const int y0 = rt * L.TR, y1 = min(y0 + L.TR, L.H);
+    const int kind = L.kind;
+    float* outl = area + kStageWarpFloats + 12 * 33;
+    if (GW > 0 && kind == 2)
+      process_tile_staged<TRU, SB, GW, GH, AUX>(g, spose, redw + 27, area, outl, seg, y0, y1, lane, S);
+    else if (kind >= 1)
+      process_tile_staged<TRU, SB, 0, 0, AUX>(g, spose, redw + 27, area, outl, seg, y0, y1, lane, S);
+    else
+      process_tile<8, TRU>(g, spose, redw + 27, seg, y0, y1, lane, S);
+  }
+  __syncwarp();
+  const unsigned long long it2 = *sitem;
+  const int b2 = q_item_b(it2);
+  flush_warp<TRU>(S, redw, p.records + ((size_t)b2 * p.max_tiles + q_item_t(it2)) * PS, lane);
+
+  __threadfence();
+  __syncwarp();
+  int last = 0;
+  if (lane == 0) last = (atomicAdd(p.tiles_done + b2, 1) == p.lv[q_item_k(it2) / p.iters].tpp - 1);
+  return __shfl_sync(0xffffffffu, last, 0) != 0;
+}
+
+// The worker that completed the last tile of (iteration k, pair b): fold, solve (or park), append the next tiles.
+template <bool TRU>
+__device__ __noinline__ void q_finish_pair(const QueueParams& p, float* area, const int k, const int b) {
+  const int lane = threadIdx.x & 31;
+  constexpr int NE = TRU ? NSUM : 27;
+  double* sdbl = reinterpret_cast<double*>(area);        // PS doubles, free between two tile walks
+  const int B = p.B;
+  const QLevel& L = p.lv[k / p.iters];
+  const int grp = b / p.group;
+  __threadfence();
+
+  // ---------------------------------------------------------------- fold the pair's records in tile order
+  const float* recs = p.records + (size_t)b * p.max_tiles * PS;
+  const int n = L.tpp;
+  float pair_min = CUDART_INF_F, pair_max = -CUDART_INF_F;
+  if (TRU) {
+    for (int i = lane; i < n; i += 32) {
+      pair_min = fminf(pair_min, __ldcg(recs + (size_t)i * PS + E_VMIN));
+      pair_max = fmaxf(pair_max, __ldcg(recs + (size_t)i * PS + E_VMAX));
+    }
+    pair_min = warp_min(pair_min);
+    pair_max = warp_max(pair_max);
+  }
+#pragma unroll 1
+  for (int e = lane; e < NE; e += 32) {
+    const int sl = e < 27 ? e : e + 2;
+    // eight records in flight at a time (L2 round trips), summed in record order
+    const bool corr = TRU && e >= 27;
+    const int key_at = e < 33 ? E_VMIN : E_VMAX;
+    const float key_want = e < 33 ? pair_min : pair_max;
+    double s = 0.0;
+    for (int i0 = 0; i0 < n; i0 += 8) {
+      float v[8], key[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float* q = recs + (size_t)min(i0 + j, n - 1) * PS;
+        v[j] = __ldcg(q + sl);
+        key[j] = corr ? __ldcg(q + key_at) : 0.f;
+      }
+#pragma unroll
+      for (int j = 0; j < 8; ++j)
+        if (i0 + j < n && (!corr || key[j] == key_want)) s += (double)v[j];
+    }
+    sdbl[sl] = s;
+  }
+  float s0lo = 0.f, s0hi = 0.f;
+  if (lane == 0) {
+    sdbl[E_VMIN] = (double)pair_min;
+    sdbl[E_VMAX] = (double)pair_max;
+    p.tiles_done[b] = 0;               // ready for the pair's next iteration
+    if (TRU && p.aux) {
+      const uint32_t* mm = p.s0mm + 2 * ((size_t)(k / p.iters) * p.n_mm_groups + (p.n_mm_groups > 1 ? grp : 0));
+      s0lo = ord2f(__ldcg(mm));
+      s0hi = ord2f(__ldcg(mm + 1));
+    }
+  }
+  __syncwarp();
+
+  if (!TRU || p.group == 1) {
+    // nothing couples the pairs (a group of one is its own batch: its extremes are the batch extremes)
+    if (lane == 0) {
+      q_finalize<TRU, false>(p, k, b, sdbl, TRU, TRU && (pair_max != pair_min));
+      if (TRU && p.aux) {
+        float* a = p.aux + ((size_t)k * p.n_groups + grp) * 4;
+        a[0] = pair_min; a[1] = pair_max; a[2] = s0lo; a[3] = s0hi;
+      }
+    }
+    q_push_next(p, k, b, lane);
+    if (p.t_done && lane == 0) {
+      if (atomicAdd(p.groups_done + k, 1) == B - 1) p.t_done[k + 1] = q_now_ns();
+    }
+    return;
+  }
+
+  // ---------------------------------------------------------------- group extremes: solve now, or park as a candidate
+  uint32_t* gx = p.gext + 2 * ((size_t)k * p.n_groups + grp);
+  int cand = 0;
+  if (lane == 0) {
+    const uint32_t emin = f2ord(pair_min), emax = f2ord(pair_max);
+    const uint32_t old_min = atomicMin(gx, emin), old_max = atomicMax(gx + 1, emax);
+    cand = (emin <= old_min) || (emax >= old_max);
+  }
+  cand = __shfl_sync(0xffffffffu, cand, 0);
+  if (cand) {
+    double* rec = p.pairrec + (size_t)b * PS;
+    for (int i = lane; i < PS; i += 32) rec[i] = sdbl[i];
+    if (lane == 0) p.cand[b] = k + 1;
+  } else {
+    if (lane == 0) q_finalize<TRU, false>(p, k, b, sdbl, false, false);
+    q_push_next(p, k, b, lane);
+  }
+  __threadfence();
+  __syncwarp();
+  int group_done = 0;
+  if (lane == 0) group_done = (atomicAdd(p.pairs_done + (size_t)k * p.n_groups + grp, 1) == p.group - 1);
+  group_done = __shfl_sync(0xffffffffu, group_done, 0);
+  if (!group_done) return;
+  __threadfence();
+
+  // ---------------------------------------------------------------- last pair of the group: the extremes are final
+  const float gmin = ord2f(__ldcg(gx)), gmax = ord2f(__ldcg(gx + 1));
+  if (lane == 0 && p.aux) {
+    float* a = p.aux + ((size_t)k * p.n_groups + grp) * 4;
+    a[0] = gmin; a[1] = gmax; a[2] = s0lo; a[3] = s0hi;
+  }
+  const int b_lo = grp * p.group, b_hi = b_lo + p.group;
+  for (int base = b_lo; base < b_hi; base += 32) {
+    const int bb = base + lane;
+    const bool mine = bb < b_hi && __ldcg(p.cand + bb) == k + 1;
+    if (mine) {
+      const double* rec = p.pairrec + (size_t)bb * PS;
+      const bool at_min = ((float)__ldcg(rec + E_VMIN) == gmin);
+      const bool at_max = ((float)__ldcg(rec + E_VMAX) == gmax) && (gmax != gmin);
+      q_finalize<TRU, true>(p, k, bb, rec, at_min, at_max);
+    }
+    unsigned m = __ballot_sync(0xffffffffu, mine);
+    while (m) {
+      const int j = __ffs(m) - 1;
+      m &= m - 1;
+      q_push_next(p, k, base + j, lane);
+    }
+  }
+  if (p.t_done && lane == 0) {
+    if (atomicAdd(p.groups_done + k, 1) == p.n_groups - 1) p.t_done[k + 1] = q_now_ns();
+  }
+}
+
+template <bool TRU, bool SB, bool AUX, int GW, int GH>
+__global__ void __launch_bounds__(kQThreads, kQCtasPerSm) uic_queue_kernel(const __grid_constant__ QueueParams p) {
+  extern __shared__ __align__(128) float q_dyn[];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  float* area = q_dyn + warp * kQAreaFloats;
+  while (true) {
+    unsigned slot = 0;
+    if (lane == 0) slot = atomicAdd(p.qctl, 1u);
+    slot = __shfl_sync(0xffffffffu, slot, 0);
+    if (slot >= p.total_items) break;
+    unsigned long long item = 0;
+    if (lane == 0) {
+      item = q_wait_item(p.fifo + slot);
+      if (p.t_done && slot == 0) p.t_done[0] = q_now_ns();
+    }
+    item = __shfl_sync(0xffffffffu, item, 0);
+    if (q_walk_item<TRU, SB, AUX, GW, GH>(p, area, item)) q_finish_pair<TRU>(p, area, q_item_k(item), q_item_b(item));
+  }
+}
+
+// head / tail, counters, running extremes, candidate marks, the FIFO with the coarsest level's first iteration in it
+__global__ void __launch_bounds__(256) queue_init_kernel(const QueueParams p, const float* __restrict__ pose_in,
+                                                         const int n_mm) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int n_it = p.n_levels * p.iters;
+  const unsigned n0 = (unsigned)p.B * (unsigned)p.lv[0].tpp;
+  if (i < p.total_items) {
+    unsigned long long v = 0;
+    if (i < n0) v = q_encode(0, (int)(i / p.lv[0].tpp), (int)(i % p.lv[0].tpp));
+    p.fifo[i] = v;
+  }
+  if (i == 0) {
+    p.qctl[0] = 0u;
+    p.qctl[1] = n0;
+  }
+  if (i < (size_t)p.B * 12) p.pose_hist[i] = pose_in[i];
+  if (i < (size_t)p.B) {
+    p.tiles_done[i] = 0;
+    p.cand[i] = 0;
+  }
+  if (i < (size_t)n_it * p.n_groups) {
+    p.pairs_done[i] = 0;
+    p.gext[2 * i] = 0xffffffffu;
+    p.gext[2 * i + 1] = 0u;
+  }
+  if (i < (size_t)n_it) p.groups_done[i] = 0;
+  if (i < (size_t)n_mm) {
+    p.s0mm_rw[2 * i] = 0xffffffffu;
+    p.s0mm_rw[2 * i + 1] = 0u;
+  }
+}
+
+// extremes of sigma0 per (level, group): blockIdx.z = level, blockIdx.y = group
+struct MmLevels {
+  const float* v[DPFT_MAX_LEVELS];
+  size_t per_group[DPFT_MAX_LEVELS];     // elements of one group's slice
+};
+__global__ void __launch_bounds__(256) minmax_levels_kernel(const MmLevels q, uint32_t* __restrict__ mm, const int n_groups) {
+  __shared__ float s_lo[8], s_hi[8];
+  const int l = blockIdx.z, grp = blockIdx.y;
+  const size_t n = q.per_group[l];
+  const float* v = q.v[l] + (size_t)grp * n;
+  float lo = CUDART_INF_F, hi = -CUDART_INF_F;
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  const size_t n4 = ((reinterpret_cast<uintptr_t>(v) & 15) == 0) ? n / 4 : 0;
+  const float4* v4 = reinterpret_cast<const float4*>(v);
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  for (; i + 3 * stride < n4; i += 4 * stride) {       // four independent 16-byte loads in flight per thread
+    const float4 a = __ldg(v4 + i), b = __ldg(v4 + i + stride), c = __ldg(v4 + i + 2 * stride), d = __ldg(v4 + i + 3 * stride);
+    lo = fminf(fminf(fminf(lo, fminf(a.x, a.y)), fminf(fminf(a.z, a.w), fminf(b.x, b.y))),
+               fminf(fminf(fminf(b.z, b.w), fminf(c.x, c.y)), fminf(fminf(c.z, c.w), fminf(fminf(d.x, d.y), fminf(d.z, d.w)))));
+    hi = fmaxf(fmaxf(fmaxf(hi, fmaxf(a.x, a.y)), fmaxf(fmaxf(a.z, a.w), fmaxf(b.x, b.y))),
+               fmaxf(fmaxf(fmaxf(b.z, b.w), fmaxf(c.x, c.y)), fmaxf(fmaxf(c.z, c.w), fmaxf(fmaxf(d.x, d.y), fmaxf(d.z, d.w)))));
+  }
+  for (; i < n4; i += stride) {
+    const float4 a = __ldg(v4 + i);
+    lo = fminf(fminf(lo, a.x), fminf(a.y, fminf(a.z, a.w)));
+    hi = fmaxf(fmaxf(hi, a.x), fmaxf(a.y, fmaxf(a.z, a.w)));
+  }
+  for (size_t j = n4 * 4 + (size_t)blockIdx.x * blockDim.x + threadIdx.x; j < n; j += stride) {
+    const float a = __ldg(v + j);
+    lo = fminf(lo, a);
+    hi = fmaxf(hi, a);
+  }
+  lo = warp_min(lo);
+  hi = warp_max(hi);
+  if ((threadIdx.x & 31) == 0) {
+    s_lo[threadIdx.x >> 5] = lo;
+    s_hi[threadIdx.x >> 5] = hi;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+#pragma unroll
+    for (int w = 1; w < 8; ++w) {
+      lo = fminf(lo, s_lo[w]);
+      hi = fmaxf(hi, s_hi[w]);
+    }
+    uint32_t* out = mm + 2 * ((size_t)l * n_groups + grp);
+    atomicMin(out, f2ord(lo));
+    atomicMax(out + 1, f2ord(hi));
+  }
+}
+
+template <bool TRU, bool SB, bool AUX, int GW, int GH>
+static cudaError_t launch_q(const QueueParams& prm, int grid, cudaStream_t stream) {
+  constexpr int smem = kQW * kQAreaFloats * (int)sizeof(float);
+  auto* fn = uic_queue_kernel<TRU, SB, AUX, GW, GH>;
+  // (cudaFuncSetAttribute is per device and cheap: set it on every launch rather than caching per process)
+  cudaError_t err = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+  if (err != cudaSuccess) return err;
+  fn<<<grid, kQThreads, smem, stream>>>(prm);
+  return cudaGetLastError();
+}
+
+int queue_tiles_per_sm() { return kQCtasPerSm * kQW; }
+
+cudaError_t launch_queue(const QueueParams& prm_in, const float* pose_in, bool tru, int grid, cudaStream_t stream,
+                         bool allow_fixed_geometry) {
+  QueueParams prm = prm_in;
+  const int n_it = prm.n_levels * prm.iters;
+  const int n_mm = prm.n_levels * prm.n_mm_groups;
+  {
+    const size_t n = std::max<size_t>(std::max<size_t>(prm.total_items, (size_t)prm.B * 12),
+                                      std::max<size_t>((size_t)n_it * prm.n_groups, (size_t)n_mm));
+    queue_init_kernel<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(prm, pose_in, n_mm);
+  }
+  if (tru) {
+    MmLevels q{};
+    size_t widest = 0;
+    for (int l = 0; l < prm.n_levels; ++l) {
+      const size_t per_pair = (size_t)prm.SC * prm.lv[l].H * prm.lv[l].W;
+      q.v[l] = prm.lv[l].s0;
+      q.per_group[l] = prm.n_mm_groups > 1 ? per_pair * prm.group : per_pair * (prm.kf_shared ? 1 : prm.B);
+      widest = std::max(widest, q.per_group[l]);
+    }
+    const unsigned bx = (unsigned)std::max<size_t>(1, std::min<size_t>((widest / 4 + 255) / 256, (148 * 8) / std::max(1, prm.n_mm_groups) + 1));
+    minmax_levels_kernel<<<dim3(bx, prm.n_mm_groups, prm.n_levels), 256, 0, stream>>>(q, prm.s0mm_rw, prm.n_mm_groups);
+  }
+  const bool sb = prm.SC != prm.C;
+  bool aux = false;
+  for (int l = 0; l < prm.n_levels; ++l) aux = aux || prm.lv[l].m0 || prm.lv[l].m1;
+  // the reference's TUM pyramid (160x120 at the finest level) runs a geometry-specialised tile routine there
+  const QLevel& fine = prm.lv[prm.n_levels - 1];
+  if (allow_fixed_geometry && !sb && !aux && fine.kind >= 1 && fine.W == 160 && fine.H == 120) {
+    for (int l = 0; l < prm.n_levels; ++l)
+      if (prm.lv[l].kind >= 1 && prm.lv[l].W == 160 && prm.lv[l].H == 120) prm.lv[l].kind = 2;
+    return tru ? launch_q<true, false, false, 160, 120>(prm, grid, stream) : launch_q<false, false, false, 160, 120>(prm, grid, stream);
+  }
+#define DPFT_Q(TRUV, SBV, AUXV) launch_q<TRUV, SBV, AUXV, 0, 0>(prm, grid, stream)
+  if (tru) {
+    if (sb) return aux ? DPFT_Q(true, true, true) : DPFT_Q(true, true, false);
+    return aux ? DPFT_Q(true, false, true) : DPFT_Q(true, false, false);
+  }
+  if (sb) return aux ? DPFT_Q(false, true, true) : DPFT_Q(false, true, false);
+  return aux ? DPFT_Q(false, false, true) : DPFT_Q(false, false, false);
+#undef DPFT_Q
+}
+
+}  // namespace dpft

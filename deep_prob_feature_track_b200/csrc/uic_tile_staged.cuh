@@ -48,6 +48,12 @@ constexpr int kStageWarpFloats = kStageRows * kStageSlotFloats + 32;   // + x or
 #endif
 constexpr int kOutLanes = DPFT_OUT_LANES;     // tuning hook
 constexpr int kOutFloats = kOutLanes * kStageMaps * 4;
+// shared memory of one warp: ring | corrections of remove_tru_sigma | outlier taps | halo sums; a multiple of 128
+// bytes so that every ring slot is 128-byte aligned (what the tensor-map copies of DPFT_STAGED_TMA=1 require of their
+// destination).  The 27 rows of the final reduction overlay the tail of the ring once the tile is done.
+constexpr int kStageAreaFloats = (kStageWarpFloats + 12 * 33 + kOutFloats + kHaloFloats + 31) / 32 * 32;
+static_assert((kStageWarpFloats + 12 * 33 + kOutFloats) % 4 == 0, "the halo sums are read as float4");
+static_assert(kStageWarpFloats >= 27 * 33, "the reduction rows overlay the ring");
 
 __device__ __forceinline__ void cp_async16(unsigned smem_addr, const float* g) {
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_addr), "l"(g) : "memory");

@@ -38,7 +38,9 @@ extern "C" {
 #define DPFT_MAX_LEVELS 8
 
 /* error codes */
-#define DPFT_EINVAL   (-1)  /* bad argument (shape, NULL pointer, unsupported flag mix) */
+#define DPFT_EINVAL   (-1)  /* bad argument (shape, NULL pointer, unsupported flag mix: DPFT_SHARED_KEYFRAME or
+                               DPFT_PAIRWISE_EXTREMES with DPFT_COMBINE_ICP or without DPFT_FUSED_SOBEL;
+                               DPFT_SIGMA_BROADCAST without DPFT_FUSED_SOBEL; occ_out with DPFT_PAIRWISE_EXTREMES) */
 #define DPFT_ENOSPACE (-2)  /* workspace too small */
 
 /* flags */
@@ -60,6 +62,11 @@ extern "C" {
                                        batch tracks against the same keyframe (kf_vo.py keyframe mode); forward only */
 #define DPFT_PAIRWISE_EXTREMES 0x80u /* with DPFT_REMOVE_TRU_SIGMA: sigma extremes per pair, i.e. the semantics of
                                         calling the reference once per pair with B = 1 (kf_vo.py:156-166); forward only */
+#define DPFT_QUEUE            0x200u /* dpft_uic_forward: the whole solve (every level, every iteration) as ONE launch
+                                        whose warps take warp tiles from a work queue; dependencies are per frame pair,
+                                        not per launch (csrc/uic_queue.cu).  Taken when the problem qualifies (C == 8,
+                                        DPFT_FUSED_SOBEL, no DPFT_COMBINE_ICP, no occ_out, iters >= 1), ignored otherwise.
+                                        Same results as the launch-per-iteration path up to summation order.          */
 #define DPFT_FUSED_SOBEL      0x08u /* recompute the unit Sobel gradients inside every iteration (sliding register
                                        window) instead of materialising them once per level                    */
 
@@ -80,6 +87,28 @@ typedef struct dpft_level {
                                    (1 = excluded), exactly what compute_inverse_residuals returns */
   int32_t H, W;
 } dpft_level_t;
+
+/*
+ * Optional knobs of dpft_uic_forward_ex / dpft_uic_workspace_bytes_ex.  Zero-initialise, set struct_bytes =
+ * sizeof(dpft_uic_options_t), then the fields you want; a zero field means "default".  The library keeps no copy.
+ */
+typedef struct dpft_uic_options {
+  uint32_t struct_bytes;
+  int32_t group;          /* DPFT_QUEUE + DPFT_REMOVE_TRU_SIGMA: pairs per sigma-extreme group.  The B pairs of the
+                             call are `B / group` independent batches of `group` consecutive pairs, each with the
+                             reference's batch-global extremes (alg:1976-1979) -- the results of B / group separate
+                             calls, from one launch.  0 = B (one batch); 1 = DPFT_PAIRWISE_EXTREMES.  B % group == 0.
+                             aux_hist then has (n_levels*iters, B / group, 4) entries.                            */
+  int32_t tile_rows[DPFT_MAX_LEVELS]; /* DPFT_QUEUE: rows per warp tile at level l (coarse first); 0 = chosen   */
+  int32_t queue_ctas;     /* DPFT_QUEUE: CTAs (4 worker warps each) to launch; 0 = what the device holds        */
+  int32_t cta_slots;      /* launch-per-iteration kernels: resident CTA slots the tile heights are planned for  */
+  int32_t tiling;         /* staged kernel: 0 balanced dealt tiles, 1 rectangular, 2 balanced linear ranges     */
+  int32_t generic_geometry; /* 1: never pick the instantiations specialised for 160x120 / 80x60 levels          */
+  float *launch_ms;       /* HOST array (n_levels*iters) or NULL.  When set, the call measures the device time of every
+                             Gauss-Newton iteration (CUDA events around every launch, or %globaltimer stamps of the
+                             iteration completions inside a single launch), WAITS for the stream and fills the array:
+                             a measurement aid, not a way to run the solver.                                      */
+} dpft_uic_options_t;
 
 /* ABI version of the loaded library (== DPFT_ABI_VERSION). */
 int dpft_abi_version(void);
@@ -111,6 +140,14 @@ size_t dpft_uic_workspace_bytes(const dpft_level_t *levels, int n_levels, int B,
 int dpft_uic_forward(const dpft_level_t *levels, int n_levels, int B, int C, int iters, uint32_t flags,
                      float w_icp, const float *pose_in, float *pose_hist, float *sys_hist, float *aux_hist,
                      int32_t *status, void *workspace, size_t workspace_bytes, void *stream);
+
+/* dpft_uic_workspace_bytes / dpft_uic_forward with options (opt may be NULL: identical to the plain calls). */
+size_t dpft_uic_workspace_bytes_ex(const dpft_level_t *levels, int n_levels, int B, int C, int iters,
+                                   uint32_t flags, const dpft_uic_options_t *opt);
+int dpft_uic_forward_ex(const dpft_level_t *levels, int n_levels, int B, int C, int iters, uint32_t flags,
+                        float w_icp, const float *pose_in, float *pose_hist, float *sys_hist, float *aux_hist,
+                        int32_t *status, void *workspace, size_t workspace_bytes, void *stream,
+                        const dpft_uic_options_t *opt);
 
 /*
  * Depth stage of LeastSquareTracking._preprocess (LeastSquareTracking.py:656-661, 668-674; ImagePyramids

@@ -8,7 +8,9 @@ import torch.nn as nn
 GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 
 # Stated fp32 tolerances (BASELINE.json north_star / SURVEY.md section 8c)
-TOL_POSE = 1e-5      # absolute on R entries and t (both O(1) / O(0.1) quantities)
+TOL_POSE = 2e-6      # absolute on R entries and t ("abs 1e-6 on t, R entries"; measured ~1e-7, and the
+                     # fp32-vs-fp64 gap of the reference itself is 1e-7, so 2e-6 leaves no room for a real regression)
+TOL_TWIST_REL = 1e-5 # north_star: <= 1e-5 relative on the twist of the estimated motion
 TOL_SYS = 1e-4       # Frobenius-relative on J^T W J and J^T W r
 TOL_GRAD = 1e-3      # Frobenius-relative on gradients through the unrolled solve
 
@@ -22,6 +24,22 @@ def frob_rel(a, b):
     a = a.double().reshape(-1)
     b = b.double().reshape(-1)
     return ((a - b).norm() / b.norm().clamp_min(1e-30)).item()
+
+
+def twist_of(R, t):
+    """(B,6) twist [rotation vector, translation] of poses R (B,3,3), t (B,3) (fp64 log map)."""
+    R = R.double()
+    cos = ((R.diagonal(dim1=1, dim2=2).sum(-1) - 1) / 2).clamp(-1, 1)
+    th = torch.acos(cos)
+    w = torch.stack((R[:, 2, 1] - R[:, 1, 2], R[:, 0, 2] - R[:, 2, 0], R[:, 1, 0] - R[:, 0, 1]), dim=1) / 2
+    scale = torch.where(th > 1e-8, th / torch.sin(th).clamp_min(1e-30), torch.ones_like(th))
+    return torch.cat((w * scale[:, None], t.double().reshape(-1, 3)), dim=1)
+
+
+def twist_rel_err(R, t, R_ref, t_ref):
+    """max over the batch of |xi - xi_ref| / |xi_ref| (the north_star's "relative on twist")."""
+    a, b = twist_of(R, t), twist_of(R_ref, t_ref)
+    return ((a - b).norm(dim=1) / b.norm(dim=1).clamp_min(1e-12)).max().item()
 
 
 def level_inputs(g, prefix="in_"):

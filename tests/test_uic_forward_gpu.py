@@ -40,6 +40,7 @@ def run_cuda(levels, pose, **kw):
     kw.setdefault("fused_sobel", FUSED)
     kw.setdefault("single_launch", SINGLE)
     kw.setdefault("staged_footprint", STAGED)
+    kw.setdefault("queue", False)      # the work-queue path has its own file (test_uic_queue_gpu.py)
     res = A.uic_solve(levels_to(levels, DEV), (pose[0].to(DEV), pose[1].to(DEV)), want_occ=True, **kw)
     torch.cuda.synchronize()
     return res
@@ -208,8 +209,8 @@ def test_full_size_batch_properties():
     data = make_frame_pairs(B, C, H, W, seed=1234, n_levels=4)
     levels = levels_to(data["levels"], DEV)
     pose = (data["R0"].to(DEV), data["t0"].to(DEV))
-    r1 = A.uic_solve(levels, pose, iters=3, remove_tru_sigma=True, fused_sobel=FUSED, single_launch=SINGLE, staged_footprint=STAGED)
-    r2 = A.uic_solve(levels, pose, iters=3, remove_tru_sigma=True, fused_sobel=FUSED, single_launch=SINGLE, staged_footprint=STAGED)
+    r1 = A.uic_solve(levels, pose, iters=3, remove_tru_sigma=True, fused_sobel=FUSED, single_launch=SINGLE, staged_footprint=STAGED, queue=False)
+    r2 = A.uic_solve(levels, pose, iters=3, remove_tru_sigma=True, fused_sobel=FUSED, single_launch=SINGLE, staged_footprint=STAGED, queue=False)
     torch.cuda.synchronize()
     assert int(r1.status.item()) == 0
     assert torch.equal(r1.pose_hist, r2.pose_hist) and torch.equal(r1.sys_hist, r2.sys_hist)
@@ -220,7 +221,7 @@ def test_full_size_batch_properties():
     # permuting the batch permutes the result (bitwise)
     perm = torch.randperm(B, generator=torch.Generator().manual_seed(0)).to(DEV)
     lv_p = [{k: v[perm].contiguous() for k, v in lv.items()} for lv in levels]
-    r3 = A.uic_solve(lv_p, (pose[0][perm], pose[1][perm]), iters=3, remove_tru_sigma=True, fused_sobel=FUSED, single_launch=SINGLE, staged_footprint=STAGED)
+    r3 = A.uic_solve(lv_p, (pose[0][perm], pose[1][perm]), iters=3, remove_tru_sigma=True, fused_sobel=FUSED, single_launch=SINGLE, staged_footprint=STAGED, queue=False)
     if STAGED:
         # the balanced tiling gives some pairs one CTA more than others depending on their position in the batch, so
         # a permuted pair is summed in a different order: equal to rounding instead of bitwise
@@ -230,15 +231,15 @@ def test_full_size_batch_properties():
     # no batch coupling without remove_tru_sigma: swapping the batch-mates of the first five pairs for
     # other data leaves their rows bitwise unchanged, and a smaller batch (different tiling, so a
     # different summation order) agrees to rounding
-    r4 = A.uic_solve(levels, pose, iters=3, remove_tru_sigma=False, fused_sobel=FUSED, single_launch=SINGLE, staged_footprint=STAGED)
+    r4 = A.uic_solve(levels, pose, iters=3, remove_tru_sigma=False, fused_sobel=FUSED, single_launch=SINGLE, staged_footprint=STAGED, queue=False)
     mixed = [{k: torch.cat((v[:5], v[5:].flip(0))).contiguous() for k, v in lv.items()} for lv in levels]
-    r5 = A.uic_solve(mixed, pose, iters=3, remove_tru_sigma=False, fused_sobel=FUSED, single_launch=SINGLE, staged_footprint=STAGED)
+    r5 = A.uic_solve(mixed, pose, iters=3, remove_tru_sigma=False, fused_sobel=FUSED, single_launch=SINGLE, staged_footprint=STAGED, queue=False)
     assert torch.equal(r5.pose_hist[:, :5], r4.pose_hist[:, :5])
     sub = [{k: v[:5].contiguous() for k, v in lv.items()} for lv in levels]
-    r7 = A.uic_solve(sub, (pose[0][:5], pose[1][:5]), iters=3, remove_tru_sigma=False, fused_sobel=FUSED, single_launch=SINGLE, staged_footprint=STAGED)
+    r7 = A.uic_solve(sub, (pose[0][:5], pose[1][:5]), iters=3, remove_tru_sigma=False, fused_sobel=FUSED, single_launch=SINGLE, staged_footprint=STAGED, queue=False)
     assert (r7.pose_hist - r4.pose_hist[:, :5]).abs().max() < 1e-6
     # PDL on/off is only a scheduling difference
-    r6 = A.uic_solve(levels, pose, iters=3, remove_tru_sigma=True, pdl=False, fused_sobel=FUSED, single_launch=SINGLE, staged_footprint=STAGED)
+    r6 = A.uic_solve(levels, pose, iters=3, remove_tru_sigma=True, pdl=False, fused_sobel=FUSED, single_launch=SINGLE, staged_footprint=STAGED, queue=False)
     assert torch.equal(r6.pose_hist, r1.pose_hist)
 
 
@@ -246,7 +247,7 @@ def test_full_size_vs_oracle():
     """The whole B=64 120x160 4-level solve against the oracle (a few seconds of CPU)."""
     B, C, H, W = 64, 8, 120, 160
     data = make_frame_pairs(B, C, H, W, seed=4321, n_levels=4)
-    res = run_cuda(data["levels"], (data["R0"], data["t0"]), iters=3, remove_tru_sigma=True, fused_sobel=FUSED, single_launch=SINGLE, staged_footprint=STAGED)
+    res = run_cuda(data["levels"], (data["R0"], data["t0"]), iters=3, remove_tru_sigma=True, fused_sobel=FUSED, single_launch=SINGLE, staged_footprint=STAGED, queue=False)
     trace = []
     with torch.no_grad():
         pose, per_level = O.track_pyramid(data["levels"], (data["R0"], data["t0"]), iters=3,

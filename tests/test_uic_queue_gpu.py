@@ -1,0 +1,248 @@
+"""The work-queue solve (csrc/uic_queue.cu: one launch, per-pair dependencies, sigma-extreme groups) against the
+CPU oracle, the reference-generated fixtures and the launch-per-iteration kernels.
+
+This is also the parity gate of the configuration bench.py times: B = 64, 120x160, 4 levels x 3 iterations,
+remove_tru_sigma, NO per-iteration mask output (so the kernels run the instantiations without the debug outputs).
+Tolerances: twist <= 1e-5 relative (north_star), J^T W J / J^T W r <= 1e-4 Frobenius-relative.
+"""
+import pytest
+import torch
+
+from deep_prob_feature_track_b200 import algorithms as A
+from deep_prob_feature_track_b200.synthetic import levels_to, make_frame_pairs
+from helpers import TOL_POSE, TOL_SYS, TOL_TWIST_REL, frob_rel, level_inputs, load_golden, twist_rel_err
+from oracle import ic_oracle as O
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+
+
+def solve(levels, pose, **kw):
+    res = A.uic_solve(levels_to(levels, DEV), (pose[0].to(DEV), pose[1].to(DEV)), **kw)
+    torch.cuda.synchronize()
+    return res
+
+
+def check_against_trace(res, trace, iters, tol_sys=TOL_SYS):
+    """pose_hist / sys_hist of a whole solve against the oracle's per-level traces."""
+    for i, tr in enumerate(trace):
+        for it, rec in enumerate(tr):
+            k = i * iters + it
+            Ac, bc = A.unpack_system(res.sys_hist[k].cpu())
+            assert frob_rel(Ac, rec["A"]) < tol_sys, (i, it, frob_rel(Ac, rec["A"]))
+            assert frob_rel(bc, rec["b"]) < tol_sys, (i, it, frob_rel(bc, rec["b"]))
+            Rc, tc = A.unpack_pose(res.pose_hist[k].cpu())
+            assert (Rc - rec["R"]).abs().max() < TOL_POSE and (tc - rec["t"]).abs().max() < TOL_POSE, (i, it)
+
+
+def test_bench_configuration_vs_oracle():
+    """bench.py's exact flag set at its exact size against the oracle, and against the launch-per-iteration kernels
+    (with and without the debug outputs compiled in)."""
+    B, C, H, W = 64, 8, 120, 160
+    data = make_frame_pairs(B, C, H, W, seed=1234, n_levels=4)
+    pose0 = (data["R0"], data["t0"])
+    res = solve(data["levels"], pose0, iters=3, remove_tru_sigma=True)
+    assert int(res.status.item()) == 0
+    trace = []
+    with torch.no_grad():
+        pose, _ = O.track_pyramid(data["levels"], pose0, iters=3, remove_tru_sigma=True, trace=trace, reduction="einsum")
+    check_against_trace(res, trace, 3)
+    R, t = (x.cpu() for x in res.pose)
+    assert twist_rel_err(R, t, pose[0], pose[1]) < TOL_TWIST_REL, twist_rel_err(R, t, pose[0], pose[1])
+    # the batch extremes the backward needs are the oracle's
+    for i, tr in enumerate(trace):
+        for it, rec in enumerate(tr):
+            if "sr_min" in rec:
+                a = res.aux_hist[i * 3 + it].cpu()
+                assert a[0].item() == rec["sr_min"] and a[1].item() == rec["sr_max"], (i, it)
+    # launch-per-iteration kernels, no mask output (AUX = false instantiation) and with it (AUX = true): same solve
+    lp = solve(data["levels"], pose0, iters=3, remove_tru_sigma=True, queue=False)
+    lp_occ = solve(data["levels"], pose0, iters=3, remove_tru_sigma=True, queue=False, want_occ=True)
+    assert torch.equal(lp.pose_hist, lp_occ.pose_hist) and torch.equal(lp.sys_hist, lp_occ.sys_hist)
+    check_against_trace(lp, trace, 3)
+    assert (lp.pose_hist - res.pose_hist).abs().max() < 2e-6
+    assert frob_rel(lp.sys_hist.cpu(), res.sys_hist.cpu()) < 1e-5
+    # same starting pose at k = 0: the warped-sigma extremes are bit-exact; later iterations start from poses equal to rounding
+    assert torch.equal(lp.aux_hist[0], res.aux_hist[0])
+    assert (lp.aux_hist - res.aux_hist).abs().max() < 1e-5
+
+
+def test_deterministic_and_independent_of_worker_count():
+    """Records are folded in tile order: the result does not depend on which worker ran which tile, nor on how many
+    workers there are."""
+    B, C, H, W = 16, 8, 60, 80
+    data = make_frame_pairs(B, C, H, W, seed=5, n_levels=3)
+    pose0 = (data["R0"], data["t0"])
+    kw = dict(iters=3, remove_tru_sigma=True, tile_rows=[4, 6, 10])
+    a = solve(data["levels"], pose0, **kw)
+    b = solve(data["levels"], pose0, **kw)
+    c = solve(data["levels"], pose0, queue_ctas=7, **kw)
+    d = solve(data["levels"], pose0, queue_ctas=1, **kw)
+    for o in (b, c, d):
+        assert torch.equal(a.pose_hist, o.pose_hist) and torch.equal(a.sys_hist, o.sys_hist)
+        assert torch.equal(a.aux_hist, o.aux_hist)
+
+
+@pytest.mark.parametrize("tru", [True, False])
+def test_groups_equal_separate_calls(tru):
+    """B pairs as B / group independent batches in ONE launch == B / group calls (each with its own batch-global
+    sigma extremes, alg:1976-1979) -- bitwise, given the same tile heights."""
+    B, G, C, H, W = 24, 6, 8, 60, 80
+    data = make_frame_pairs(B, C, H, W, seed=9, n_levels=3)
+    pose0 = (data["R0"], data["t0"])
+    kw = dict(iters=3, remove_tru_sigma=tru, tile_rows=[5, 10, 15])
+    whole = solve(data["levels"], pose0, group=G, **kw)
+    assert int(whole.status.item()) == 0
+    for g in range(B // G):
+        sl = slice(g * G, (g + 1) * G)
+        sub = [{k: v[sl].contiguous() for k, v in lv.items()} for lv in data["levels"]]
+        part = solve(sub, (pose0[0][sl], pose0[1][sl]), **kw)
+        assert torch.equal(part.pose_hist, whole.pose_hist[:, sl]), g
+        assert torch.equal(part.sys_hist, whole.sys_hist[:, sl]), g
+        if tru:
+            assert torch.equal(part.aux_hist, whole.aux_hist[:, g]), g
+    if tru:   # and the groups really differ from one batch of B
+        one = solve(data["levels"], pose0, **kw)
+        assert not torch.equal(one.aux_hist[:, :2], whole.aux_hist[:, 0, :2])
+
+
+def test_saturated_sigma_every_pair_is_a_candidate():
+    """Clamped uncertainty maps: every pair sits on the batch extremes (ties), so every pair waits for the last one
+    of its group -- the barrier the reference has; masks and sums as the oracle's."""
+    B, C, H, W = 6, 8, 40, 64
+    data = make_frame_pairs(B, C, H, W, seed=77, n_levels=1)
+    lv = data["levels"][0]
+    for k in ("s0", "s1"):
+        lv[k] = lv[k].clamp(0.8, 1.25).contiguous()
+    pose0 = (data["R0"], data["t0"])
+    res = solve([lv], pose0, iters=3, remove_tru_sigma=True, tile_rows=[7])
+    trace = []
+    O.uic_level(pose0, lv["x0"], lv["x1"], lv["invD0"], lv["invD1"], lv["K"], lv["s0"], lv["s1"], iters=3,
+                remove_tru_sigma=True, trace=trace)
+    assert trace[0]["occ"].float().mean() > 0.15
+    check_against_trace(res, [trace], 3)
+
+
+@pytest.mark.parametrize("name", ["uic_plain", "uic_trusigma", "uic_masks", "uic_c8_wide"])
+def test_golden_single_level(name):
+    """Reference-generated fixtures (tests/golden/make_golden.py); C != 8 ones fall back to launch-per-iteration."""
+    g = load_golden(name)
+    f = g["flags"].tolist()
+    lv = level_inputs(g)
+    kw = {}
+    if f[2]:
+        kw = dict(obj_mask0=[g["obj_mask0"].to(DEV)], obj_mask1=[g["obj_mask1"].to(DEV)])
+    res = solve([lv], (g["R0"], g["t0"]), iters=f[3], remove_tru_sigma=bool(f[0]), **kw)
+    assert int(res.status.item()) == 0
+    for it in range(f[3]):
+        Ac, bc = A.unpack_system(res.sys_hist[it].cpu())
+        assert frob_rel(Ac, g["it_A"][it]) < TOL_SYS and frob_rel(bc, g["it_b"][it]) < TOL_SYS
+    R, t = (x.cpu() for x in res.pose)
+    assert (R - g["R_out"]).abs().max() < TOL_POSE and (t - g["t_out"]).abs().max() < TOL_POSE
+
+
+def test_golden_pyramid_chain():
+    g = load_golden("uic_pyramid")
+    f = g["flags"].tolist()
+    levels = [level_inputs(g, f"in{i}_") for i in range(4)]
+    B = levels[0]["x0"].shape[0]
+    res = solve(levels, (torch.eye(3).repeat(B, 1, 1), torch.zeros(B, 3)), iters=f[3], remove_tru_sigma=bool(f[0]))
+    assert int(res.status.item()) == 0
+    for i in range(4):
+        R, t = (x.cpu() for x in res.level_pose(i))
+        assert (R - g[f"R_lvl{i}"]).abs().max() < TOL_POSE and (t - g[f"t_lvl{i}"]).abs().max() < TOL_POSE
+        for it in range(f[3]):
+            Ac, bc = A.unpack_system(res.sys_hist[i * f[3] + it].cpu())
+            assert frob_rel(Ac, g[f"it{i}_A"][it]) < TOL_SYS and frob_rel(bc, g[f"it{i}_b"][it]) < TOL_SYS
+
+
+def test_object_masks_and_single_sigma_map():
+    """AUX (object masks) and SB (one uncertainty map per frame) instantiations of the queue kernel against the
+    launch-per-iteration kernels."""
+    B, C, H, W = 4, 8, 60, 80
+    data = make_frame_pairs(B, C, H, W, seed=21, n_levels=2)
+    pose0 = (data["R0"], data["t0"])
+    gen = torch.Generator().manual_seed(3)
+    m0 = [(torch.rand((B, 1, lv["x0"].shape[2], lv["x0"].shape[3]), generator=gen) > 0.2).to(DEV) for lv in data["levels"]]
+    m1 = [(torch.rand((B, 1, lv["x0"].shape[2], lv["x0"].shape[3]), generator=gen) > 0.2).to(DEV) for lv in data["levels"]]
+    one = [dict(lv, s0=lv["s0"][:, :1].contiguous(), s1=lv["s1"][:, :1].contiguous()) for lv in data["levels"]]
+    for levels, kw in ((data["levels"], dict(obj_mask0=m0, obj_mask1=m1)), (one, {}), (one, dict(obj_mask0=m0, obj_mask1=m1))):
+        q = solve(levels, pose0, iters=3, remove_tru_sigma=True, **kw)
+        lp = solve(levels, pose0, iters=3, remove_tru_sigma=True, queue=False, **kw)
+        assert int(q.status.item()) == 0
+        assert (q.pose_hist - lp.pose_hist).abs().max() < 2e-6
+        assert frob_rel(q.sys_hist.cpu(), lp.sys_hist.cpu()) < 1e-5
+        assert torch.equal(q.aux_hist[0], lp.aux_hist[0]) and (q.aux_hist - lp.aux_hist).abs().max() < 1e-5
+
+
+def test_vga_resolution_vs_oracle():
+    """480x640 (BASELINE config 3 size), two pairs, 4 levels: generic-geometry staged routine, 22 segments per row."""
+    B, C, H, W = 2, 8, 480, 640
+    data = make_frame_pairs(B, C, H, W, seed=11, n_levels=4)
+    pose0 = (data["R0"], data["t0"])
+    res = solve(data["levels"], pose0, iters=3, remove_tru_sigma=True)
+    assert int(res.status.item()) == 0
+    trace = []
+    with torch.no_grad():
+        pose, _ = O.track_pyramid(data["levels"], pose0, iters=3, remove_tru_sigma=True, trace=trace, reduction="einsum")
+    check_against_trace(res, trace, 3)
+    R, t = (x.cpu() for x in res.pose)
+    assert twist_rel_err(R, t, pose[0], pose[1]) < TOL_TWIST_REL
+    lp = solve(data["levels"], pose0, iters=3, remove_tru_sigma=True, queue=False, want_occ=True)
+    flips = int((lp.occ[3][0].cpu() != trace[3][0]["occ"][:, 0].to(torch.uint8)).sum())
+    assert flips <= 3, flips      # level 3 starts from a pose equal to rounding, not bitwise
+    assert torch.equal(lp.occ[0][0].cpu(), trace[0][0]["occ"][:, 0].to(torch.uint8))
+    assert (lp.pose_hist - res.pose_hist).abs().max() < 2e-6
+
+
+def test_keyframe_mode_on_the_queue():
+    """Shared keyframe + per-pair extremes (kf_vo keyframe mode) equals per-frame B = 1 oracle calls."""
+    B, C, H, W = 5, 8, 60, 80
+    data = make_frame_pairs(B, C, H, W, seed=13, n_levels=2)
+    key = [{k: lv[k][:1].contiguous() for k in ("x0", "s0", "invD0")} for lv in data["levels"]]
+    live = [{k: lv[k] for k in ("x1", "s1", "invD1", "K")} for lv in data["levels"]]
+    tracker = A.KeyframeTracker(levels_to(key, DEV), iters=3, remove_tru_sigma=True)
+    res = tracker.track(levels_to(live, DEV), (data["R0"].to(DEV), data["t0"].to(DEV)))
+    torch.cuda.synchronize()
+    assert int(res.status.item()) == 0
+    for b in range(B):
+        lv1 = [dict(kf, **{k: v[b:b + 1] for k, v in lv.items()}) for kf, lv in zip(key, live)]
+        with torch.no_grad():
+            (R, t), _ = O.track_pyramid(lv1, (data["R0"][b:b + 1], data["t0"][b:b + 1]), iters=3, remove_tru_sigma=True)
+        Rc, tc = (x.cpu() for x in res.pose)
+        assert (Rc[b] - R[0]).abs().max() < TOL_POSE and (tc[b] - t[0]).abs().max() < TOL_POSE, b
+
+
+def test_abi_rejects_unsupported_flag_mixes():
+    """dpft.h promises DPFT_EINVAL for flag mixes no kernel serves (checked at the C ABI, not only in Python)."""
+    import ctypes
+    from deep_prob_feature_track_b200 import _lib
+    L = _lib.lib()
+    B, C, H, W = 2, 8, 24, 32
+    data = make_frame_pairs(B, C, H, W, seed=1, n_levels=1)
+    lv = levels_to(data["levels"], DEV)[0]
+    arr = (_lib.DpftLevel * 1)()
+    a = arr[0]
+    a.x0, a.x1, a.sigma0, a.sigma1 = (lv[k].data_ptr() for k in ("x0", "x1", "s0", "s1"))
+    a.invd0, a.invd1, a.K = lv["invD0"].data_ptr(), lv["invD1"].data_ptr(), lv["K"].data_ptr()
+    a.depth0, a.depth1 = lv["invD0"].data_ptr(), lv["invD1"].data_ptr()
+    a.H, a.W = H, W
+    F = _lib
+    bad = [F.DPFT_SHARED_KEYFRAME,                                               # without FUSED_SOBEL
+           F.DPFT_PAIRWISE_EXTREMES | F.DPFT_REMOVE_TRU_SIGMA,                   # without FUSED_SOBEL
+           F.DPFT_SHARED_KEYFRAME | F.DPFT_FUSED_SOBEL | F.DPFT_COMBINE_ICP,
+           F.DPFT_PAIRWISE_EXTREMES | F.DPFT_FUSED_SOBEL | F.DPFT_COMBINE_ICP,
+           F.DPFT_SIGMA_BROADCAST]                                               # without FUSED_SOBEL
+    for flags in bad:
+        assert L.dpft_uic_workspace_bytes(arr, 1, B, C, 3, flags) == 0, hex(flags)
+        buf = torch.zeros(1 << 20, dtype=torch.uint8, device=DEV)
+        ph = torch.zeros((4, B, 12), device=DEV)
+        sh = torch.zeros((3, B, 27), device=DEV)
+        st = torch.zeros(1, dtype=torch.int32, device=DEV)
+        code = L.dpft_uic_forward(arr, 1, B, C, 3, flags, ctypes.c_float(0.01), ph.data_ptr(), ph.data_ptr(), sh.data_ptr(),
+                                  None, st.data_ptr(), buf.data_ptr(), buf.numel(), None)
+        assert code == -1, (hex(flags), code)
+    # a group that does not divide B
+    opt = _lib.DpftUicOptions(group=3)
+    flags = F.DPFT_FUSED_SOBEL | F.DPFT_QUEUE | F.DPFT_REMOVE_TRU_SIGMA
+    assert L.dpft_uic_workspace_bytes_ex(arr, 1, 4, C, 3, flags, ctypes.byref(opt)) == 0
