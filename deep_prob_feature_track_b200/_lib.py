@@ -16,7 +16,8 @@ from typing import List, Optional
 PKG_DIR = os.path.dirname(os.path.abspath(__file__))
 REPO_DIR = os.path.dirname(PKG_DIR)
 CSRC = os.path.join(PKG_DIR, "csrc")
-LIB_PATH = os.path.join(PKG_DIR, "libdpft.so")
+# DPFT_LIB_PATH points at another build of the SAME library (tuning sweeps build several); nothing else is ever loaded
+LIB_PATH = os.environ.get("DPFT_LIB_PATH") or os.path.join(PKG_DIR, "libdpft.so")
 SOURCES = ["dpft_abi.cu", "uic_forward.cu", "uic_queue.cu", "uic_backward.cu", "icp_term.cu", "uic_residual.cu",
            "ic_path.cu", "ic_backward.cu", "uic_persistent.cu", "preprocess.cu", "pose_loss.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
@@ -60,7 +61,8 @@ class DpftUicOptions(ctypes.Structure):
     _fields_ = [
         ("struct_bytes", ctypes.c_uint32), ("group", ctypes.c_int32),
         ("tile_rows", ctypes.c_int32 * DPFT_MAX_LEVELS),
-        ("queue_ctas", ctypes.c_int32), ("cta_slots", ctypes.c_int32), ("tiling", ctypes.c_int32),
+        ("queue_ctas", ctypes.c_int32), ("queue_levels", ctypes.c_int32), ("cta_slots", ctypes.c_int32),
+        ("tiling", ctypes.c_int32),
         ("generic_geometry", ctypes.c_int32),
         ("launch_ms", ctypes.POINTER(ctypes.c_float)),
     ]

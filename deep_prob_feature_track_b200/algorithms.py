@@ -97,7 +97,8 @@ def uic_solve(levels: Sequence[Dict[str, torch.Tensor]], pose: Pose, *, iters: i
               want_occ: bool = False, pdl: bool = True, timed: bool = False, fused_sobel: bool = True, single_launch: bool = False, staged_footprint: bool = True,
               shared_keyframe: bool = False, pairwise_extremes: bool = False,
               obj_mask0: Optional[Sequence] = None, obj_mask1: Optional[Sequence] = None,
-              queue: bool = True, group: int = 0, tile_rows: Optional[Sequence[int]] = None, queue_ctas: int = 0,
+              queue: Optional[bool] = None, group: int = 0, tile_rows: Optional[Sequence[int]] = None, queue_ctas: int = 0,
+              queue_levels: int = 0,
               tuning: Optional[Dict[str, int]] = None) -> SolveResult:
     """Coarse-to-fine U_IC solve of a batch of frame pairs on the current CUDA stream.
 
@@ -108,12 +109,14 @@ def uic_solve(levels: Sequence[Dict[str, torch.Tensor]], pose: Pose, *, iters: i
     it to C channels (algorithms.py:1425-1427).  The fused launch-per-iteration kernels then read it once per
     pixel (DPFT_SIGMA_BROADCAST); every other path gets the repeated tensor, so results never depend on it.
 
-    ``queue`` (default): the whole solve is ONE launch whose warps take tiles from a work queue with per-pair
-    dependencies (csrc/uic_queue.cu) whenever the problem qualifies (C == 8, fused Sobel, no ICP term, no
-    ``want_occ``); otherwise -- and with ``queue=False`` -- one launch per Gauss-Newton iteration.  ``group``: the B
-    pairs are B / group independent batches of ``group`` consecutive pairs, each with its own batch-global sigma
-    extremes (what B / group separate calls would give, from one launch; queue path only).  ``tile_rows`` (per level,
-    coarse first), ``queue_ctas`` and ``tuning`` (cta_slots, tiling, generic_geometry) are measurement knobs.
+    ``group``: the B pairs are B / group independent batches of ``group`` consecutive pairs, each with its own
+    batch-global sigma extremes (alg:1976-1979) -- the results of B / group separate calls, from one call.  0 = one
+    batch.  ``queue``: the finest level runs as ONE launch whose warps take tiles from a work queue with per-pair
+    dependencies (csrc/uic_queue.cu) instead of one launch per iteration; it needs C == 8, fused Sobel, no ICP term
+    and no ``want_occ``.  ``None`` (default) picks it when it pays: more than one group, or pairs that nothing
+    couples, and at least two waves of tiles at the finest level.  ``queue_levels``: how many of the finest levels
+    take that path (default 1).  ``tile_rows`` (per level, coarse first), ``queue_ctas`` and ``tuning`` (cta_slots,
+    tiling, generic_geometry) are measurement knobs.
     """
     L = _lib.lib()
     n_levels = len(levels)
@@ -122,13 +125,19 @@ def uic_solve(levels: Sequence[Dict[str, torch.Tensor]], pose: Pose, *, iters: i
     Bk = 1 if shared_keyframe else B     # batch size of the keyframe-side tensors
     one_sigma = C > 1 and all(int(lv[k].shape[1]) == 1 for lv in levels for k in ("s0", "s1"))
     sigma_broadcast = one_sigma and fused_sobel and not single_launch
-    use_queue = queue and fused_sobel and not single_launch and not combine_icp and not want_occ and C == 8 and iters >= 1
-    if group not in (0, B) and not use_queue and not (group == 1 and pairwise_extremes):
-        raise NotImplementedError("sigma-extreme groups other than the whole batch need the work-queue path")
     eff_group = group if group > 0 else (1 if pairwise_extremes else B)
     if B % eff_group:
         raise ValueError(f"group ({eff_group}) must divide the batch size ({B})")
-    n_groups = B // eff_group if use_queue else 1
+    n_groups = B // eff_group
+    pairwise_extremes = pairwise_extremes or (eff_group == 1 and B > 1)
+    if n_groups > 1 and (combine_icp or want_occ or not fused_sobel or single_launch):
+        raise NotImplementedError("sigma-extreme groups are served by the fused launch-per-iteration and work-queue kernels only")
+    queue_ok = fused_sobel and not single_launch and not combine_icp and not want_occ and C == 8 and iters >= 1
+    if queue is None:
+        Hf, Wf = int(levels[-1]["x1"].shape[2]), int(levels[-1]["x1"].shape[3])
+        coupled = remove_tru_sigma and n_groups == 1 and B > 1
+        queue = (not coupled) and B * ((Wf + 29) // 30) * Hf >= 2 * 1776 * 12
+    use_queue = bool(queue) and queue_ok
     SC = 1 if sigma_broadcast else C
     dev = x0.device
     keep = []   # keep converted tensors alive until the launches are queued
@@ -183,7 +192,7 @@ def uic_solve(levels: Sequence[Dict[str, torch.Tensor]], pose: Pose, *, iters: i
     aux_hist = torch.zeros(aux_shape, dtype=torch.float32, device=dev)
     status = torch.zeros((1,), dtype=torch.int32, device=dev)
     buf = (ctypes.c_float * max(n_it, 1))() if timed else None
-    opt = _lib.DpftUicOptions(group=(eff_group if use_queue else 0), tile_rows=tile_rows, queue_ctas=queue_ctas,
+    opt = _lib.DpftUicOptions(group=eff_group, tile_rows=tile_rows, queue_ctas=queue_ctas, queue_levels=queue_levels,
                               **(tuning or {}))
     if timed:   # measurement aid (bench.py): per-iteration device times, synchronises the stream
         opt.launch_ms = ctypes.cast(buf, ctypes.POINTER(ctypes.c_float))

@@ -48,35 +48,38 @@ struct PersistParams {
 int persistent_grid(int C, bool tru);   // CTAs that can be co-resident on the current device
 cudaError_t launch_persistent(const PersistParams& prm, int grid, bool tru, cudaStream_t stream);
 
-// ---- queue-driven single launch (uic_queue.cu): per-pair dependencies, any number of sigma-extreme groups
+// ---- work-queue launch of one pyramid level (uic_queue.cu): per-pair dependencies, any number of sigma-extreme groups
 struct QLevel {
   const float *x0, *x1, *s0, *s1, *d0, *d1, *K;
   const uint8_t *m0, *m1;
   int H, W, nseg, TR, nrt, tpp;      // TR rows per tile, tpp = tiles per pair
-  int kind;                          // tile routine: 0 plain, 1 staged footprint (2: its geometry-specialised copy)
+  int kind;                          // tile routine: 0 plain, 1 staged footprint
 };
 struct QueueParams {
-  QLevel lv[8];
-  int n_levels, iters, B, C, SC;
+  QLevel L;
+  int iters, B, C, SC;
   int group, n_groups;               // pairs per sigma-extreme group (the reference's batch), groups in this call
-  int n_mm_groups;                   // groups of the sigma0 extremes per level (1 with a shared keyframe)
-  int max_tiles, kf_shared;
+  int n_mm_groups;                   // groups of the sigma0 extremes (1 with a shared keyframe)
+  int kf_shared;
   unsigned total_items;
-  float *pose_hist, *sys_hist, *aux; // aux: (n_it, n_groups, 4) or nullptr
-  float* records;                    // (B, max_tiles, PS)
+  float *pose_hist, *sys_hist, *aux; // rows of THIS level: (iters + 1, B, 12), (iters, B, 27), (iters, n_groups, 4) or nullptr
+  float* records;                    // (B, tpp, PS)
   double* pairrec;                   // (B, PS) parked sums of the candidates
   unsigned long long* fifo;          // (total_items)
   unsigned* qctl;                    // [0] head (claims), [1] tail (reservations)
   int *tiles_done, *cand;            // (B)
-  int *pairs_done, *groups_done;     // (n_it, n_groups), (n_it)
-  uint32_t* gext;                    // (n_it, n_groups, 2) running extremes of the warped sigma, order-encoded
-  const uint32_t* s0mm;              // (n_levels, n_mm_groups, 2) extremes of sigma0, order-encoded
-  uint32_t* s0mm_rw;                 // the same buffer (written by the launcher's helper kernels)
+  int *pairs_done, *groups_done;     // (iters, n_groups), (iters)
+  uint32_t* gext;                    // (iters, n_groups, 2) running extremes of the warped sigma, order-encoded
+  const uint32_t* s0mm;              // (n_mm_groups, 2) extremes of this level's sigma0, order-encoded
   int32_t* status;
-  unsigned long long* t_done;        // optional (n_it + 1) %globaltimer stamps: start, then every iteration complete
+  unsigned long long* t_done;        // optional (iters + 1) %globaltimer stamps: start, then every iteration complete
 };
 int queue_tiles_per_sm();            // resident workers (warps) per SM
 cudaError_t launch_queue(const QueueParams& prm, const float* pose_in, bool tru, int grid, cudaStream_t stream,
                          bool allow_fixed_geometry);
+// order-encoded [min, max] of v[l][g * per_group[l] .. (g + 1) * per_group[l]) into mm[(l * n_groups + g) * 2 ..]
+// (atomicMin / atomicMax: mm must hold 0xffffffff, 0 on entry)
+void launch_minmax_levels(const float* const* v, const size_t* per_group, int n_levels, int n_groups, uint32_t* mm,
+                          cudaStream_t stream);
 
 }  // namespace dpft

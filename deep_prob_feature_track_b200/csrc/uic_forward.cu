@@ -77,14 +77,15 @@ struct UicIterParams {
   float* sys_out;        // (B,27)
   float* partials;       // (B, ctas_per_pair, PS)
   double* pairrec;       // (B, PS)
-  int* counters;         // [B] per pair, [B] = pairs done
+  int* counters;         // [B] per pair, then [n_groups] pairs done per sigma-extreme group
   int SC;                // channels of sigma0 / sigma1: C, or 1 (DPFT_SIGMA_BROADCAST)
-  const uint32_t* s0mm;  // order-encoded min, max of sigma0 over the whole level tensor
-  float* gmm;            // [4] batch-global min/max of the warped sigma of this iteration, min/max of sigma0
+  const uint32_t* s0mm;  // order-encoded min, max of sigma0 over the level tensor of every group: (n_mm_groups, 2)
+  float* gmm;            // (n_groups, 4) group-wide min/max of the warped sigma of this iteration, min/max of sigma0
   int32_t* status;
   uint32_t flags;
   int kf_shared;         // keyframe-side tensors (x0, sigma0, invd0, obj_mask0) have batch size 1
-  int pairwise;          // sigma extremes per pair instead of per batch (each pair its own batch of one)
+  int pairwise;          // sigma extremes per pair instead of per batch (each pair its own batch of one: group == 1)
+  int group, n_mm_groups; // pairs per sigma-extreme group (B: the whole call is one batch); groups of the sigma0 extremes
   const float* icp_rec;  // (B,28) sums of the point-to-plane term of this iteration, or nullptr
   float icp_w2;          // its weight squared (w_icp scales both J and r)
   TileTab tab;           // staged kernel only
@@ -304,19 +305,26 @@ __device__ __forceinline__ void reduce_and_finish(const UicIterParams& p, const 
   }
   if (p.pairwise) {
     // every pair is its own batch: its extremes are "the batch extremes", nothing couples the pairs
-    if (threadIdx.x == 0) finalize_pair<true>(p, b, pair_min, pair_max);
+    if (threadIdx.x == 0) {
+      finalize_pair<true>(p, b, pair_min, pair_max);
+      const uint32_t* mm = p.s0mm + (p.n_mm_groups > 1 ? 2 * b : 0);
+      float* gm = p.gmm + 4 * b;
+      gm[0] = pair_min; gm[1] = pair_max; gm[2] = ord2f(__ldcg(mm)); gm[3] = ord2f(__ldcg(mm + 1));
+    }
     return;
   }
 
-  // ---------------------------------------------------------------- last CTA of the grid: batch extremes + all solves
+  // ---------------------------------------------------------------- last CTA of the group: its extremes + its solves
+  // (a group is one batch of the reference: `group` consecutive pairs; usually the whole call)
   DPFT_STAMP(5, threadIdx.x == 0 && b == 0);                      // pair 0 reduced
-  if (threadIdx.x == 0) s_flag = (atomicAdd(p.counters + p.B, 1) == p.B - 1);
+  const int grp = b / p.group, g_lo = grp * p.group, g_hi = g_lo + p.group;
+  if (threadIdx.x == 0) s_flag = (atomicAdd(p.counters + p.B + grp, 1) == p.group - 1);
   __syncthreads();
   if (!s_flag) return;
   __threadfence();
   {
     float a = CUDART_INF_F, c = -CUDART_INF_F;
-    for (int i = threadIdx.x; i < p.B; i += (NW * 32)) {
+    for (int i = g_lo + threadIdx.x; i < g_hi; i += (NW * 32)) {
       a = fminf(a, (float)__ldcg(p.pairrec + (size_t)i * PS + E_VMIN));
       c = fmaxf(c, (float)__ldcg(p.pairrec + (size_t)i * PS + E_VMAX));
     }
@@ -336,16 +344,18 @@ __device__ __forceinline__ void reduce_and_finish(const UicIterParams& p, const 
       }
       s_pair_mm[0] = g0;
       s_pair_mm[1] = g1;
-      p.gmm[0] = g0;
-      p.gmm[1] = g1;
-      p.gmm[2] = ord2f(__ldcg(p.s0mm));
-      p.gmm[3] = ord2f(__ldcg(p.s0mm + 1));
-      p.counters[p.B] = 0;
+      const uint32_t* mm = p.s0mm + (p.n_mm_groups > 1 ? 2 * grp : 0);
+      float* gm = p.gmm + 4 * grp;
+      gm[0] = g0;
+      gm[1] = g1;
+      gm[2] = ord2f(__ldcg(mm));
+      gm[3] = ord2f(__ldcg(mm + 1));
+      p.counters[p.B + grp] = 0;
     }
     __syncthreads();
   }
-  DPFT_STAMP(6, threadIdx.x == 0);                                // grid-last CTA: extremes known
-  for (int i = threadIdx.x; i < p.B; i += (NW * 32)) finalize_pair<true>(p, i, s_pair_mm[0], s_pair_mm[1]);
+  DPFT_STAMP(6, threadIdx.x == 0);                                // group-last CTA: extremes known
+  for (int i = g_lo + threadIdx.x; i < g_hi; i += (NW * 32)) finalize_pair<true>(p, i, s_pair_mm[0], s_pair_mm[1]);
   DPFT_STAMP(7, threadIdx.x == 0);                                // all solves written
 }
 
@@ -386,7 +396,7 @@ __global__ void __launch_bounds__(kThreads, DPFT_MIN_CTAS) uic_iter_kernel(const
   DPFT_STAMP(1, threadIdx.x == 0 && blockIdx.x == 0 && b == 0);
   if (threadIdx.x < 12) s_pose[threadIdx.x] = __ldcg(p.pose + (size_t)b * 12 + threadIdx.x);
   if (TRU) {
-    const uint32_t* mm = p.s0mm + ((p.pairwise && !p.kf_shared) ? 2 * b : 0);
+    const uint32_t* mm = p.s0mm + (p.n_mm_groups > 1 ? 2 * (b / p.group) : 0);
     g.s0lo = ord2f(__ldcg(mm));
     g.s0hi = ord2f(__ldcg(mm + 1));
 #pragma unroll
@@ -465,7 +475,7 @@ __global__ void __launch_bounds__(kSThreads, DPFT_STAGED_CTAS) uic_iter_staged_k
   DPFT_STAMP(1, threadIdx.x == 0 && blockIdx.x == 0 && b == 0);   // previous launch complete
   if (threadIdx.x < 12) s_pose[threadIdx.x] = __ldcg(p.pose + (size_t)b * 12 + threadIdx.x);
   if (TRU) {
-    const uint32_t* mm = p.s0mm + ((p.pairwise && !p.kf_shared) ? 2 * b : 0);
+    const uint32_t* mm = p.s0mm + (p.n_mm_groups > 1 ? 2 * (b / p.group) : 0);
     g.s0lo = ord2f(__ldcg(mm));
     g.s0hi = ord2f(__ldcg(mm + 1));
 #pragma unroll
@@ -767,6 +777,7 @@ struct Tuning {
   int group = 0;                          // pairs per sigma-extreme group (queue path); 0 = B
   int tile_rows[DPFT_MAX_LEVELS] = {};    // queue path: rows per tile, 0 = chosen
   int queue_ctas = 0;
+  int queue_levels = 0;                   // finest levels that run as work-queue launches; 0 = 1
   long cta_slots = 0;                     // 0 = 148 x resident CTAs
   int tiling = 0;                         // 0 dealt, 1 rectangular, 2 linear
   bool generic_geometry = false;
@@ -779,6 +790,7 @@ static Tuning tuning_of(const dpft_uic_options_t* o) {
   t.group = o->group;
   for (int l = 0; l < DPFT_MAX_LEVELS; ++l) t.tile_rows[l] = o->tile_rows[l];
   t.queue_ctas = o->queue_ctas;
+  t.queue_levels = o->queue_levels;
   t.cta_slots = o->cta_slots;
   t.tiling = o->tiling;
   t.generic_geometry = o->generic_geometry != 0;
@@ -907,7 +919,7 @@ static bool make_tile_tab(int H, int nseg, int B, TileTab& tab, const Tuning& tu
 }
 
 static Plan make_plan(const dpft_level_t* lv, int n_levels, int B, int C, uint32_t flags, bool any_occ,
-                      int p_grid, const Tuning& tun) {
+                      int p_grid, const Tuning& tun, int n_groups, int n_mm_groups) {
   Plan pl{};
   pl.max_ctas = 1;
   pl.max_plane = 0;
@@ -943,9 +955,9 @@ static Plan make_plan(const dpft_level_t* lv, int n_levels, int B, int C, uint32
   };
   pl.off_partials = take((size_t)B * pl.max_ctas * PS * sizeof(float));
   pl.off_pairrec = take((size_t)B * PS * sizeof(double));
-  pl.off_counters = take((size_t)(B + 1) * sizeof(int));
-  pl.off_mm = take((size_t)2 * DPFT_MAX_LEVELS * sizeof(uint32_t) * ((flags & DPFT_PAIRWISE_EXTREMES) ? B : 1));
-  pl.off_gmm = take(4 * sizeof(float) * DPFT_MAX_LEVELS * 64);
+  pl.off_counters = take((size_t)(B + n_groups) * sizeof(int));
+  pl.off_mm = take((size_t)2 * DPFT_MAX_LEVELS * sizeof(uint32_t) * n_mm_groups);
+  pl.off_gmm = take(4 * sizeof(float) * DPFT_MAX_LEVELS * 64 * n_groups);
   pl.off_sr0 = take(((flags & DPFT_REMOVE_TRU_SIGMA) && any_occ) ? (size_t)B * pl.max_plane * sizeof(float) : 0);
   pl.grad_elems = (flags & DPFT_FUSED_SOBEL) ? 0 : (size_t)B * C * pl.max_plane;
   pl.off_grad = take(4 * pl.grad_elems * sizeof(float));
@@ -1002,12 +1014,17 @@ static int check_args(const dpft_level_t* lv, int n_levels, int B, int C, int it
   return 0;
 }
 
-// the sigma-extreme group of the options: a divisor of B, and only the queue path knows groups other than B and 1
-static int check_group(int B, uint32_t flags, const Tuning& tun, bool queue) {
+// the sigma-extreme group of the options: a divisor of B; groups other than the whole batch are served by the fused
+// U_IC kernels only (the ICP term's normals and the per-iteration mask output know batch-global extremes only)
+static int check_group(const dpft_level_t* lv, int n_levels, int B, uint32_t flags, const Tuning& tun) {
   if (tun.group < 0 || (tun.group > 0 && B % tun.group != 0))
     return set_error(DPFT_EINVAL, "options.group (%d) must divide B (%d)", tun.group, B);
-  if (tun.group > 0 && tun.group != B && !queue && !(tun.group == 1 && (flags & DPFT_PAIRWISE_EXTREMES)))
-    return set_error(DPFT_EINVAL, "options.group = %d needs the work-queue path (DPFT_QUEUE, C == 8, fused, no ICP, no occ_out)", tun.group);
+  if (tun.group > 0 && tun.group != B) {
+    bool any_occ = false;
+    for (int l = 0; l < n_levels; ++l) any_occ = any_occ || lv[l].occ_out;
+    if (!(flags & DPFT_FUSED_SOBEL) || (flags & DPFT_COMBINE_ICP) || any_occ)
+      return set_error(DPFT_EINVAL, "options.group = %d needs DPFT_FUSED_SOBEL and excludes DPFT_COMBINE_ICP and occ_out", tun.group);
+  }
   return 0;
 }
 
@@ -1151,13 +1168,12 @@ static int persistent_grid_cached(int C, bool tru) {
 }
 
 // ------------------------------------------------------------------------------------------- queue path (uic_queue.cu)
+// The finest level of a solve as one work-queue launch (all its iterations, per-pair dependencies).
 struct QPlan {
-  bool on = false;
-  int nseg[DPFT_MAX_LEVELS], TR[DPFT_MAX_LEVELS], nrt[DPFT_MAX_LEVELS], tpp[DPFT_MAX_LEVELS], kind[DPFT_MAX_LEVELS];
-  int group = 0, n_groups = 0, n_mm_groups = 0, max_tiles = 0, grid = 0;
-  size_t total_items = 0;
+  int nseg, TR, nrt, tpp, kind, grid;
+  size_t total_items;
   size_t off_fifo, off_qctl, off_tiles_done, off_cand, off_pairs_done, off_groups_done, off_gext, off_mm, off_records,
-      off_pairrec, off_tdone, off_aux, total = 0;
+      off_pairrec, off_tdone, off_aux, total;
 };
 
 static int device_sms() {
@@ -1168,53 +1184,58 @@ static int device_sms() {
   return sms;
 }
 
-// Rows per tile of the queue path.  Workers are warps; an iteration of a level offers B * nseg * ceil(H / TR) tiles.
-// A tile costs its rows plus ~3 rows of fixed work (claim, pose, window and ring priming, record, counters) and a
-// pair's iteration is over when its last tile is, so: as few waves of tiles as possible, and within that small tiles.
+// Rows per tile of the queue path.  Workers are warps; an iteration of the level offers B * nseg * ceil(H / TR) tiles.
+// A tile costs its rows plus ~2 rows of fixed work (claim, pose, window and ring priming, record, counters).  With
+// several waves of tiles per iteration the pairs drift apart and only the fixed work counts, so tall tiles win; with
+// a wave or two the last tile of a pair IS its iteration, so the count of waves counts.
 static int queue_tile_rows(int H, int nseg, int B, long workers) {
   int best_tr = 1;
   double best = 1e30;
-  for (int tr = 1; tr <= std::min(H, 64); ++tr) {
+  for (int tr = 4; tr <= std::min(H, 48); ++tr) {
     const long nrt = (H + tr - 1) / tr;
     const int tr_eff = (int)((H + nrt - 1) / nrt);          // equal tiles: ceil(H / nrt) rows
     const long tiles = nrt * nseg * B;
-    const long waves = (tiles + workers - 1) / workers;
-    const double cost = (double)waves * (tr_eff + 3.0) + 0.25 * (double)((nrt * nseg + 7) / 8);
+    const double waves = (double)tiles / (double)workers;
+    const double quant = waves >= 3.0 ? waves + 0.5 : (double)((tiles + workers - 1) / workers);
+    const double cost = quant * (tr_eff + 2.0);
     if (cost < best - 1e-9) { best = cost; best_tr = tr_eff; }
   }
   return best_tr;
+}
+
+// sigma-extreme groups of a call: `group` consecutive pairs are one batch of the reference
+struct Groups {
+  int group, n_groups, n_mm_groups;
+};
+static Groups groups_of(int B, uint32_t flags, const Tuning& tun) {
+  Groups g;
+  g.group = tun.group > 0 ? tun.group : ((flags & DPFT_PAIRWISE_EXTREMES) ? 1 : B);
+  g.n_groups = B / g.group;
+  g.n_mm_groups = (flags & DPFT_SHARED_KEYFRAME) ? 1 : g.n_groups;
+  return g;
 }
 
 static bool queue_wanted(int C, int iters, uint32_t flags, bool any_occ) {
   return (flags & DPFT_QUEUE) && (flags & DPFT_FUSED_SOBEL) && !(flags & DPFT_COMBINE_ICP) && !any_occ && C == 8 && iters >= 1;
 }
 
-static QPlan make_qplan(const dpft_level_t* lv, int n_levels, int B, int C, int iters, uint32_t flags, const Tuning& tun) {
-  QPlan q;
-  q.on = true;
-  q.group = tun.group > 0 ? tun.group : ((flags & DPFT_PAIRWISE_EXTREMES) ? 1 : B);
-  q.n_groups = B / q.group;
-  q.n_mm_groups = (flags & DPFT_SHARED_KEYFRAME) ? 1 : q.n_groups;
+static QPlan make_qplan(const dpft_level_t& lv, int level_index, int B, int C, int iters, uint32_t flags, const Tuning& tun) {
+  QPlan q{};
+  const Groups G = groups_of(B, flags, tun);
   const int sms = device_sms();
   const long workers = (long)sms * queue_tiles_per_sm();
-  long widest = 1;
-  for (int l = 0; l < n_levels; ++l) {
-    const bool staged = (flags & DPFT_STAGED_FOOTPRINT) && staged_ok(lv[l], C);
-    q.kind[l] = staged ? 1 : 0;
-    q.nseg[l] = (lv[l].W + kCols - 1) / kCols;
-    int tr = tun.tile_rows[l] > 0 ? std::min(tun.tile_rows[l], (int)lv[l].H) : queue_tile_rows(lv[l].H, q.nseg[l], B, workers);
-    if (staged) tr = std::max(tr, 1);
-    q.nrt[l] = (lv[l].H + tr - 1) / tr;
-    q.TR[l] = (lv[l].H + q.nrt[l] - 1) / q.nrt[l];
-    q.nrt[l] = (lv[l].H + q.TR[l] - 1) / q.TR[l];
-    q.tpp[l] = q.nseg[l] * q.nrt[l];
-    q.max_tiles = std::max(q.max_tiles, q.tpp[l]);
-    q.total_items += (size_t)iters * B * q.tpp[l];
-    widest = std::max(widest, (long)B * q.tpp[l]);
-  }
+  const bool staged = (flags & DPFT_STAGED_FOOTPRINT) && staged_ok(lv, C);
+  q.kind = staged ? 1 : 0;
+  q.nseg = (lv.W + kCols - 1) / kCols;
+  const int want = tun.tile_rows[level_index];
+  const int tr = want > 0 ? std::min(want, (int)lv.H) : queue_tile_rows(lv.H, q.nseg, B, workers);
+  q.nrt = (lv.H + tr - 1) / tr;
+  q.TR = (lv.H + q.nrt - 1) / q.nrt;
+  q.nrt = (lv.H + q.TR - 1) / q.TR;
+  q.tpp = q.nseg * q.nrt;
+  q.total_items = (size_t)iters * B * q.tpp;
   const int full = sms * 3;
-  q.grid = tun.queue_ctas > 0 ? tun.queue_ctas : (int)std::min<long>(full, (widest + 3) / 4);
-  const int n_it = n_levels * iters;
+  q.grid = tun.queue_ctas > 0 ? tun.queue_ctas : (int)std::min<long>(full, ((long)B * q.tpp + 3) / 4);
   size_t off = 0;
   auto take = [&](size_t bytes) {
     const size_t o = off;
@@ -1225,38 +1246,38 @@ static QPlan make_qplan(const dpft_level_t* lv, int n_levels, int B, int C, int 
   q.off_qctl = take(2 * sizeof(unsigned));
   q.off_tiles_done = take((size_t)B * sizeof(int));
   q.off_cand = take((size_t)B * sizeof(int));
-  q.off_pairs_done = take((size_t)n_it * q.n_groups * sizeof(int));
-  q.off_groups_done = take((size_t)n_it * sizeof(int));
-  q.off_gext = take((size_t)n_it * q.n_groups * 2 * sizeof(uint32_t));
-  q.off_mm = take((size_t)n_levels * q.n_mm_groups * 2 * sizeof(uint32_t));
-  q.off_records = take((size_t)B * q.max_tiles * PS * sizeof(float));
+  q.off_pairs_done = take((size_t)iters * G.n_groups * sizeof(int));
+  q.off_groups_done = take((size_t)iters * sizeof(int));
+  q.off_gext = take((size_t)iters * G.n_groups * 2 * sizeof(uint32_t));
+  q.off_mm = take((size_t)G.n_mm_groups * 2 * sizeof(uint32_t));
+  q.off_records = take((size_t)B * q.tpp * PS * sizeof(float));
   q.off_pairrec = take((size_t)B * PS * sizeof(double));
-  q.off_tdone = take((size_t)(n_it + 1) * sizeof(unsigned long long));
-  q.off_aux = take((size_t)n_it * q.n_groups * 4 * sizeof(float));
+  q.off_tdone = take((size_t)(iters + 1) * sizeof(unsigned long long));
+  q.off_aux = take((size_t)iters * G.n_groups * 4 * sizeof(float));
   q.total = off;
   return q;
 }
 
-static int run_queue(const dpft_level_t* levels, int n_levels, int B, int C, int iters, uint32_t flags,
-                     const float* pose_in, float* pose_hist, float* sys_hist, float* aux_hist, int32_t* status,
-                     void* workspace, size_t workspace_bytes, cudaStream_t stream, const Tuning& tun) {
-  const QPlan q = make_qplan(levels, n_levels, B, C, iters, flags, tun);
+// One level through the work queue.  pose_hist / sys_hist / aux_hist point at THIS level's rows; pose_in may be
+// pose_hist (the coarser levels already left the level's starting pose there).  launch_ms (host, iters) optional.
+static int run_queue(const dpft_level_t& L, int level_index, int B, int C, int iters, uint32_t flags, const float* pose_in,
+                     float* pose_hist, float* sys_hist, float* aux_hist, int32_t* status, void* workspace,
+                     size_t workspace_bytes, cudaStream_t stream, const Tuning& tun, float* launch_ms) {
+  const QPlan q = make_qplan(L, level_index, B, C, iters, flags, tun);
+  const Groups G = groups_of(B, flags, tun);
   if (workspace_bytes < q.total) return set_error(DPFT_ENOSPACE, "workspace has %zu bytes, %zu needed", workspace_bytes, q.total);
-  if (q.total_items >= (1ull << 32) || q.max_tiles >= (1 << 20) || n_levels * iters >= (1 << 19))
+  if (q.total_items >= (1ull << 32) || q.tpp >= (1 << 20) || iters >= (1 << 19) || B >= (1 << 24))
     return set_error(DPFT_EINVAL, "problem too large for the work queue's item encoding");
   char* ws = (char*)workspace;
   QueueParams prm{};
-  for (int l = 0; l < n_levels; ++l) {
-    const dpft_level_t& L = levels[l];
-    QLevel& v = prm.lv[l];
-    v.x0 = L.x0; v.x1 = L.x1; v.s0 = L.sigma0; v.s1 = L.sigma1; v.d0 = L.invd0; v.d1 = L.invd1; v.K = L.K;
-    v.m0 = L.obj_mask0; v.m1 = L.obj_mask1;
-    v.H = L.H; v.W = L.W; v.nseg = q.nseg[l]; v.TR = q.TR[l]; v.nrt = q.nrt[l]; v.tpp = q.tpp[l]; v.kind = q.kind[l];
-  }
-  prm.n_levels = n_levels; prm.iters = iters; prm.B = B; prm.C = C;
+  QLevel& v = prm.L;
+  v.x0 = L.x0; v.x1 = L.x1; v.s0 = L.sigma0; v.s1 = L.sigma1; v.d0 = L.invd0; v.d1 = L.invd1; v.K = L.K;
+  v.m0 = L.obj_mask0; v.m1 = L.obj_mask1;
+  v.H = L.H; v.W = L.W; v.nseg = q.nseg; v.TR = q.TR; v.nrt = q.nrt; v.tpp = q.tpp; v.kind = q.kind;
+  prm.iters = iters; prm.B = B; prm.C = C;
   prm.SC = (flags & DPFT_SIGMA_BROADCAST) ? 1 : C;
-  prm.group = q.group; prm.n_groups = q.n_groups; prm.n_mm_groups = q.n_mm_groups;
-  prm.max_tiles = q.max_tiles; prm.kf_shared = (flags & DPFT_SHARED_KEYFRAME) ? 1 : 0;
+  prm.group = G.group; prm.n_groups = G.n_groups; prm.n_mm_groups = G.n_mm_groups;
+  prm.kf_shared = (flags & DPFT_SHARED_KEYFRAME) ? 1 : 0;
   prm.total_items = (unsigned)q.total_items;
   prm.pose_hist = pose_hist; prm.sys_hist = sys_hist;
   prm.aux = aux_hist ? aux_hist : (float*)(ws + q.off_aux);
@@ -1269,35 +1290,53 @@ static int run_queue(const dpft_level_t* levels, int n_levels, int B, int C, int
   prm.pairs_done = (int*)(ws + q.off_pairs_done);
   prm.groups_done = (int*)(ws + q.off_groups_done);
   prm.gext = (uint32_t*)(ws + q.off_gext);
-  prm.s0mm = prm.s0mm_rw = (uint32_t*)(ws + q.off_mm);
+  uint32_t* mm = (uint32_t*)(ws + q.off_mm);
+  prm.s0mm = mm;
   prm.status = status;
-  prm.t_done = tun.launch_ms ? (unsigned long long*)(ws + q.off_tdone) : nullptr;
-  if (tun.generic_geometry)
-    for (int l = 0; l < n_levels; ++l) prm.lv[l].kind = std::min(prm.lv[l].kind, 1);
-  cudaError_t err = launch_queue(prm, pose_in, flags & DPFT_REMOVE_TRU_SIGMA, q.grid, stream, !tun.generic_geometry);
+  prm.t_done = launch_ms ? (unsigned long long*)(ws + q.off_tdone) : nullptr;
+  const bool tru = flags & DPFT_REMOVE_TRU_SIGMA;
+  if (tru) {
+    init_kernel<<<1, 256, 0, stream>>>(nullptr, nullptr, 0, nullptr, 0, mm, std::min(G.n_mm_groups, 256));
+    if (G.n_mm_groups > 256) init_kernel<<<(G.n_mm_groups + 255) / 256, 256, 0, stream>>>(nullptr, nullptr, 0, nullptr, 0, mm, G.n_mm_groups);
+    const float* src[1] = {L.sigma0};
+    const size_t per_pair = (size_t)prm.SC * L.H * L.W;
+    const size_t per_group[1] = {G.n_mm_groups > 1 ? per_pair * G.group : per_pair * (prm.kf_shared ? 1 : B)};
+    launch_minmax_levels(src, per_group, 1, G.n_mm_groups, mm, stream);
+  }
+  cudaError_t err = launch_queue(prm, pose_in, tru, q.grid, stream, !tun.generic_geometry);
   if (err != cudaSuccess) return set_error((int)err, "work-queue launch: %s", cudaGetErrorString(err));
-  if (tun.launch_ms) {
-    const int n = n_levels * iters;
-    unsigned long long stamps[DPFT_MAX_LEVELS * 64 + 1];
-    err = cudaMemcpyAsync(stamps, prm.t_done, (n + 1) * sizeof(unsigned long long), cudaMemcpyDeviceToHost, stream);
+  if (launch_ms) {
+    unsigned long long stamps[64 + 1];
+    err = cudaMemcpyAsync(stamps, prm.t_done, (iters + 1) * sizeof(unsigned long long), cudaMemcpyDeviceToHost, stream);
     if (err == cudaSuccess) err = cudaStreamSynchronize(stream);
     if (err != cudaSuccess) return set_error((int)err, "stamp read-back: %s", cudaGetErrorString(err));
-    for (int i = 0; i < n; ++i) tun.launch_ms[i] = (float)((double)(stamps[i + 1] - stamps[i]) * 1e-6);
+    for (int i = 0; i < iters; ++i) launch_ms[i] = (float)((double)(stamps[i + 1] - stamps[i]) * 1e-6);
   }
   return 0;
+}
+
+// Workspace of a call: [launch-per-iteration plan of the levels it serves | work-queue plan of the finest level].
+static size_t lpi_bytes(const dpft_level_t* levels, int n_levels, int B, int C, uint32_t flags, bool any_occ, const Tuning& tun) {
+  if (n_levels < 1) return 0;
+  const Groups G = groups_of(B, flags, tun);
+  const int pg = (persistent_ok(flags, any_occ) && G.n_groups == 1) ? persistent_grid_cached(C, flags & DPFT_REMOVE_TRU_SIGMA) : 0;
+  return make_plan(levels, n_levels, B, C, flags, any_occ, std::max(pg, 0), tun, G.n_groups, G.n_mm_groups).total;
 }
 
 extern "C" size_t dpft_uic_workspace_bytes_ex(const dpft_level_t* levels, int n_levels, int B, int C, int iters,
                                               uint32_t flags, const dpft_uic_options_t* opt) {
   if (check_args(levels, n_levels, B, C, iters, flags)) return 0;
   const Tuning tun = tuning_of(opt);
+  if (check_group(levels, n_levels, B, flags, tun)) return 0;
   bool any_occ = false;
   for (int l = 0; l < n_levels; ++l) any_occ = any_occ || levels[l].occ_out;
-  const bool queue = queue_wanted(C, iters, flags, any_occ);
-  if (check_group(B, flags, tun, queue)) return 0;
-  if (queue) return make_qplan(levels, n_levels, B, C, iters, flags, tun).total;
-  const int pg = persistent_ok(flags, any_occ) ? persistent_grid_cached(C, flags & DPFT_REMOVE_TRU_SIGMA) : 0;
-  return make_plan(levels, n_levels, B, C, flags, any_occ, std::max(pg, 0), tun).total;
+  if (queue_wanted(C, iters, flags, any_occ)) {
+    const int nc = n_levels - std::min(n_levels, std::max(1, tun.queue_levels));
+    size_t q = 0;                                     // the queue launches run one after the other: one region
+    for (int l = nc; l < n_levels; ++l) q = std::max(q, make_qplan(levels[l], l, B, C, iters, flags, tun).total);
+    return lpi_bytes(levels, nc, B, C, flags, any_occ, tun) + q;
+  }
+  return lpi_bytes(levels, n_levels, B, C, flags, any_occ, tun);
 }
 
 extern "C" size_t dpft_uic_workspace_bytes(const dpft_level_t* levels, int n_levels, int B, int C, int iters,
@@ -1305,25 +1344,20 @@ extern "C" size_t dpft_uic_workspace_bytes(const dpft_level_t* levels, int n_lev
   return dpft_uic_workspace_bytes_ex(levels, n_levels, B, C, iters, flags, nullptr);
 }
 
-static int run_uic(const dpft_level_t* levels, int n_levels, int B, int C, int iters, uint32_t flags,
+// Launch-per-iteration kernels (or the single cooperative launch) over `n_levels` levels; arguments already checked.
+static int run_lpi(const dpft_level_t* levels, int n_levels, int B, int C, int iters, uint32_t flags,
                    float w_icp, const float* pose_in, float* pose_hist, float* sys_hist, float* aux_hist,
                    int32_t* status, void* workspace, size_t workspace_bytes, void* stream_, cudaEvent_t* ev,
                    unsigned long long* clock_host, const Tuning& tun) {
-  if (iters > 64) return set_error(DPFT_EINVAL, "iters must be <= 64");
-  if (int e = check_args(levels, n_levels, B, C, iters, flags)) return e;
-  if (!pose_in || !pose_hist || !status || (iters > 0 && !sys_hist) || !workspace)
-    return set_error(DPFT_EINVAL, "pose_in, pose_hist, sys_hist, status and workspace are required");
   bool any_occ = false;
   for (int l = 0; l < n_levels; ++l) any_occ = any_occ || levels[l].occ_out;
-  const bool queue = queue_wanted(C, iters, flags, any_occ);
-  if (int e = check_group(B, flags, tun, queue)) return e;
-  if (queue)
-    return run_queue(levels, n_levels, B, C, iters, flags, pose_in, pose_hist, sys_hist, aux_hist, status, workspace,
-                     workspace_bytes, (cudaStream_t)stream_, tun);
+  const Groups G = groups_of(B, flags, tun);
   if (ev && !clock_host) flags |= DPFT_LAUNCH_PER_ITERATION;   // event timing needs separate launches
-  const bool persist = persistent_ok(flags, any_occ) && persistent_grid_cached(C, flags & DPFT_REMOVE_TRU_SIGMA) > 0;
+  const bool persist = persistent_ok(flags, any_occ) && G.n_groups == 1 &&
+                       persistent_grid_cached(C, flags & DPFT_REMOVE_TRU_SIGMA) > 0;
   const Plan pl = make_plan(levels, n_levels, B, C, flags, any_occ,
-                            persist ? persistent_grid_cached(C, flags & DPFT_REMOVE_TRU_SIGMA) : 0, tun);
+                            persist ? persistent_grid_cached(C, flags & DPFT_REMOVE_TRU_SIGMA) : 0, tun, G.n_groups,
+                            G.n_mm_groups);
   if (workspace_bytes < pl.total) return set_error(DPFT_ENOSPACE, "workspace has %zu bytes, %zu needed", workspace_bytes, pl.total);
   cudaStream_t stream = (cudaStream_t)stream_;
   char* ws = (char*)workspace;
@@ -1331,7 +1365,7 @@ static int run_uic(const dpft_level_t* levels, int n_levels, int B, int C, int i
   double* pairrec = (double*)(ws + pl.off_pairrec);
   int* counters = (int*)(ws + pl.off_counters);
   uint32_t* mm = (uint32_t*)(ws + pl.off_mm);
-  float* gmm = aux_hist ? aux_hist : (float*)(ws + pl.off_gmm);   // 4 floats per iteration
+  float* gmm = aux_hist ? aux_hist : (float*)(ws + pl.off_gmm);   // 4 floats per iteration and group
   float* sr0 = (float*)(ws + pl.off_sr0);
   const bool tru = flags & DPFT_REMOVE_TRU_SIGMA;
   const bool pdl = !(flags & DPFT_NO_PDL);
@@ -1344,25 +1378,24 @@ static int run_uic(const dpft_level_t* levels, int n_levels, int B, int C, int i
   uint32_t* dmm = (uint32_t*)(ws + pl.off_dmm);
 
   {
-    const int n_mm = n_levels * (((flags & DPFT_PAIRWISE_EXTREMES) && !(flags & DPFT_SHARED_KEYFRAME)) ? B : 1);
-    const int n = std::max(std::max(B * 12, B + 1), n_mm);
-    init_kernel<<<(n + 255) / 256, 256, 0, stream>>>(pose_in, pose_hist, B * 12, counters, B + 1, mm, n_mm);
+    const int n_mm = n_levels * G.n_mm_groups;
+    const int n = std::max(std::max(B * 12, B + G.n_groups), n_mm);
+    init_kernel<<<(n + 255) / 256, 256, 0, stream>>>(pose_in, pose_hist, pose_in == pose_hist ? 0 : B * 12, counters,
+                                                     B + G.n_groups, mm, n_mm);
     if (icp) init_kernel<<<1, 32, 0, stream>>>(pose_in, pose_hist, 0, counters, 0, dmm, n_levels);
   }
-  const bool shared_kf = flags & DPFT_SHARED_KEYFRAME, pairwise = flags & DPFT_PAIRWISE_EXTREMES;
-  const int mm_per_level = (pairwise && !shared_kf) ? B : 1;
+  const bool shared_kf = flags & DPFT_SHARED_KEYFRAME, pairwise = G.group == 1;
+  const int mm_per_level = G.n_mm_groups;
   if (tru) {
+    // extremes of sigma0 per level and group, all levels in one launch
+    const float* src[DPFT_MAX_LEVELS];
+    size_t per_group[DPFT_MAX_LEVELS];
     for (int l = 0; l < n_levels; ++l) {
       const size_t per_pair = (size_t)SC * levels[l].H * levels[l].W;
-      const size_t n = per_pair * (shared_kf ? 1 : B);
-      if (mm_per_level == 1) {
-        const int blocks = (int)std::min<size_t>((n / 4 + 255) / 256 + 1, 148 * 8);
-        minmax_kernel<<<blocks, 256, 0, stream>>>(levels[l].sigma0, n, mm + 2 * l);
-      } else {
-        const dim3 g((unsigned)std::min<size_t>((per_pair + 255) / 256, 64), B);
-        minmax_pairs_kernel<<<g, 256, 0, stream>>>(levels[l].sigma0, per_pair, mm + 2 * (size_t)l * B);
-      }
+      src[l] = levels[l].sigma0;
+      per_group[l] = G.n_mm_groups > 1 ? per_pair * G.group : per_pair * (shared_kf ? 1 : B);
     }
+    launch_minmax_levels(src, per_group, n_levels, G.n_mm_groups, mm, stream);
   }
   if (persist) {
     PersistParams pp{};
@@ -1428,8 +1461,9 @@ static int run_uic(const dpft_level_t* levels, int n_levels, int B, int C, int i
       prm.pose_next = pose_hist + (size_t)(k + 1) * B * 12;
       prm.sys_out = sys_hist + (size_t)k * B * 27;
       prm.partials = partials; prm.pairrec = pairrec; prm.counters = counters;
-      prm.s0mm = mm + 2 * (size_t)l * mm_per_level; prm.gmm = gmm + 4 * k;
+      prm.s0mm = mm + 2 * (size_t)l * mm_per_level; prm.gmm = gmm + 4 * (size_t)k * G.n_groups;
       prm.kf_shared = shared_kf; prm.pairwise = pairwise; prm.status = status; prm.flags = flags;
+      prm.group = G.group; prm.n_mm_groups = G.n_mm_groups;
       if (icp) {
         launch_icp_term(L.depth0, L.K, vn, vn + 3 * (size_t)B * plane, prm.pose, L.obj_mask0, L.obj_mask1, icp_rec,
                         nullptr, nullptr, B, L.H, L.W, stream);
@@ -1470,32 +1504,26 @@ static int run_uic(const dpft_level_t* levels, int n_levels, int B, int C, int i
   return 0;
 }
 
-static int forward_timed(const dpft_level_t* levels, int n_levels, int B, int C, int iters, uint32_t flags, float w_icp,
-                         const float* pose_in, float* pose_hist, float* sys_hist, float* aux_hist, int32_t* status,
-                         void* workspace, size_t workspace_bytes, void* stream, const Tuning& tun) {
-  float* launch_ms = tun.launch_ms;
-  if (n_levels < 1 || n_levels > DPFT_MAX_LEVELS || iters < 1 || iters > 64)
-    return set_error(DPFT_EINVAL, "timing needs 1..%d levels and 1..64 iterations", DPFT_MAX_LEVELS);
+// launch-per-iteration levels with the device time of every iteration (events, or stamps of the cooperative launch)
+static int lpi_timed(const dpft_level_t* levels, int n_levels, int B, int C, int iters, uint32_t flags, float w_icp,
+                     const float* pose_in, float* pose_hist, float* sys_hist, float* aux_hist, int32_t* status,
+                     void* workspace, size_t workspace_bytes, void* stream, const Tuning& tun, float* launch_ms) {
   const int n = n_levels * iters;
   bool any_occ = false;
   for (int l = 0; l < n_levels; ++l) any_occ = any_occ || levels[l].occ_out;
-  if (queue_wanted(C, iters, flags, any_occ))   // one launch: iteration completions are stamped on the device
-    return run_uic(levels, n_levels, B, C, iters, flags, w_icp, pose_in, pose_hist, sys_hist, aux_hist, status, workspace,
-                   workspace_bytes, stream, nullptr, nullptr, tun);
-  Tuning plain = tun;
-  plain.launch_ms = nullptr;
-  if (persistent_ok(flags, any_occ) && persistent_grid_cached(C, flags & DPFT_REMOVE_TRU_SIGMA) > 0) {
+  if (persistent_ok(flags, any_occ) && groups_of(B, flags, tun).n_groups == 1 &&
+      persistent_grid_cached(C, flags & DPFT_REMOVE_TRU_SIGMA) > 0) {
     // single cooperative launch: iteration boundaries are stamped on the device with %globaltimer
     unsigned long long stamps[DPFT_MAX_LEVELS * 64 + 1];
-    const int rc = run_uic(levels, n_levels, B, C, iters, flags, w_icp, pose_in, pose_hist, sys_hist, aux_hist, status,
-                           workspace, workspace_bytes, stream, nullptr, stamps, plain);
+    const int rc = run_lpi(levels, n_levels, B, C, iters, flags, w_icp, pose_in, pose_hist, sys_hist, aux_hist, status,
+                           workspace, workspace_bytes, stream, nullptr, stamps, tun);
     for (int i = 0; i < n && rc == 0; ++i) launch_ms[i] = (float)((double)(stamps[i + 1] - stamps[i]) * 1e-6);
     return rc;
   }
   cudaEvent_t ev[DPFT_MAX_LEVELS * 64 + 1];
   for (int i = 0; i <= n; ++i) cudaEventCreate(&ev[i]);
-  int rc = run_uic(levels, n_levels, B, C, iters, flags, w_icp, pose_in, pose_hist, sys_hist, aux_hist, status,
-                   workspace, workspace_bytes, stream, ev, nullptr, plain);
+  int rc = run_lpi(levels, n_levels, B, C, iters, flags, w_icp, pose_in, pose_hist, sys_hist, aux_hist, status,
+                   workspace, workspace_bytes, stream, ev, nullptr, tun);
   if (rc == 0) {
     const cudaError_t err = cudaStreamSynchronize((cudaStream_t)stream);
     if (err != cudaSuccess) rc = set_error((int)err, "sync: %s", cudaGetErrorString(err));
@@ -1505,16 +1533,59 @@ static int forward_timed(const dpft_level_t* levels, int n_levels, int B, int C,
   return rc;
 }
 
+// Every dpft_uic_forward* entry point ends here: checks, then the levels either all through the launch-per-iteration
+// kernels or -- DPFT_QUEUE on a problem that qualifies -- the coarse ones through them and the finest through the
+// work queue.
+static int run_uic(const dpft_level_t* levels, int n_levels, int B, int C, int iters, uint32_t flags, float w_icp,
+                   const float* pose_in, float* pose_hist, float* sys_hist, float* aux_hist, int32_t* status,
+                   void* workspace, size_t workspace_bytes, void* stream, const Tuning& tun) {
+  if (iters > 64) return set_error(DPFT_EINVAL, "iters must be <= 64");
+  if (int e = check_args(levels, n_levels, B, C, iters, flags)) return e;
+  if (int e = check_group(levels, n_levels, B, flags, tun)) return e;
+  if (!pose_in || !pose_hist || !status || (iters > 0 && !sys_hist) || !workspace)
+    return set_error(DPFT_EINVAL, "pose_in, pose_hist, sys_hist, status and workspace are required");
+  if (tun.launch_ms && iters < 1) return set_error(DPFT_EINVAL, "timing needs at least one iteration");
+  bool any_occ = false;
+  for (int l = 0; l < n_levels; ++l) any_occ = any_occ || levels[l].occ_out;
+  float* ms = tun.launch_ms;
+  if (!queue_wanted(C, iters, flags, any_occ)) {
+    if (ms)
+      return lpi_timed(levels, n_levels, B, C, iters, flags, w_icp, pose_in, pose_hist, sys_hist, aux_hist, status,
+                       workspace, workspace_bytes, stream, tun, ms);
+    return run_lpi(levels, n_levels, B, C, iters, flags, w_icp, pose_in, pose_hist, sys_hist, aux_hist, status, workspace,
+                   workspace_bytes, stream, nullptr, nullptr, tun);
+  }
+  const int nc = n_levels - std::min(n_levels, std::max(1, tun.queue_levels));   // coarse levels
+  const Groups G = groups_of(B, flags, tun);
+  const size_t coarse_bytes = lpi_bytes(levels, nc, B, C, flags, any_occ, tun);
+  size_t qbytes = 0;
+  for (int l = nc; l < n_levels; ++l) qbytes = std::max(qbytes, make_qplan(levels[l], l, B, C, iters, flags, tun).total);
+  if (workspace_bytes < coarse_bytes + qbytes)
+    return set_error(DPFT_ENOSPACE, "workspace has %zu bytes, %zu needed", workspace_bytes, coarse_bytes + qbytes);
+  if (nc > 0) {
+    const int rc = ms ? lpi_timed(levels, nc, B, C, iters, flags, w_icp, pose_in, pose_hist, sys_hist, aux_hist, status,
+                                  workspace, coarse_bytes, stream, tun, ms)
+                      : run_lpi(levels, nc, B, C, iters, flags, w_icp, pose_in, pose_hist, sys_hist, aux_hist, status,
+                                workspace, coarse_bytes, stream, nullptr, nullptr, tun);
+    if (rc) return rc;
+  }
+  for (int l = nc; l < n_levels; ++l) {
+    const size_t k0 = (size_t)l * iters;
+    float* ph = pose_hist + k0 * B * 12;
+    const int rc = run_queue(levels[l], l, B, C, iters, flags, l > 0 ? ph : pose_in, ph, sys_hist + k0 * B * 27,
+                             aux_hist ? aux_hist + k0 * G.n_groups * 4 : nullptr, status, (char*)workspace + coarse_bytes,
+                             qbytes, (cudaStream_t)stream, tun, ms ? ms + k0 : nullptr);
+    if (rc) return rc;
+  }
+  return 0;
+}
+
 extern "C" int dpft_uic_forward_ex(const dpft_level_t* levels, int n_levels, int B, int C, int iters, uint32_t flags,
                                    float w_icp, const float* pose_in, float* pose_hist, float* sys_hist,
                                    float* aux_hist, int32_t* status, void* workspace, size_t workspace_bytes,
                                    void* stream, const dpft_uic_options_t* opt) {
-  const Tuning tun = tuning_of(opt);
-  if (tun.launch_ms)
-    return forward_timed(levels, n_levels, B, C, iters, flags, w_icp, pose_in, pose_hist, sys_hist, aux_hist, status,
-                         workspace, workspace_bytes, stream, tun);
   return run_uic(levels, n_levels, B, C, iters, flags, w_icp, pose_in, pose_hist, sys_hist, aux_hist, status,
-                 workspace, workspace_bytes, stream, nullptr, nullptr, tun);
+                 workspace, workspace_bytes, stream, tuning_of(opt));
 }
 
 extern "C" int dpft_uic_forward(const dpft_level_t* levels, int n_levels, int B, int C, int iters, uint32_t flags,
@@ -1532,8 +1603,8 @@ extern "C" int dpft_uic_forward_timed(const dpft_level_t* levels, int n_levels, 
   if (!launch_ms) return set_error(DPFT_EINVAL, "launch_ms is required");
   Tuning tun;
   tun.launch_ms = launch_ms;
-  return forward_timed(levels, n_levels, B, C, iters, flags, w_icp, pose_in, pose_hist, sys_hist, aux_hist, status,
-                       workspace, workspace_bytes, stream, tun);
+  return run_uic(levels, n_levels, B, C, iters, flags, w_icp, pose_in, pose_hist, sys_hist, aux_hist, status, workspace,
+                 workspace_bytes, stream, tun);
 }
 
 // Host-side view of the balanced tile table of one level (test hook, not part of the ABI): returns 1 and fills

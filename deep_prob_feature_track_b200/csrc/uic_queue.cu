@@ -1,21 +1,23 @@
-// U_IC forward as ONE launch driven by a work queue: every pyramid level and every Gauss-Newton iteration of every
-// frame pair, with the dependencies of the algorithm expressed per PAIR instead of per launch.
+// The finest pyramid level of the U_IC solve as ONE launch driven by a work queue: all Gauss-Newton iterations of all
+// frame pairs of the call, with the dependencies of the algorithm expressed per PAIR instead of per launch.
 //
-// Why.  With one launch per iteration (uic_forward.cu) every iteration of every level ends in a drain: the launch is as
-// long as its slowest warp, then a chain of hand-offs (CTA sums -> pair sums -> batch extremes -> 64 solves) runs on a
-// nearly idle machine, then the next launch starts.  The in-kernel timeline of round 1 put a third of a finest-level
-// launch into that drain, and a coarse-level launch is little else.  But the algorithm only orders the iterations of ONE
-// pair (iteration k+1 of a pair needs the pose iteration k gave it); pairs do not wait for each other -- with one
-// exception, the batch-global sigma extremes of remove_tru_sigma (algorithms.py:1976-1979), handled below.
+// Why.  With one launch per iteration (uic_forward.cu) every iteration ends in a drain: the launch is as long as its
+// slowest warp, then a chain of hand-offs (CTA sums -> pair sums -> batch extremes -> the solves) runs on a nearly idle
+// machine, then the next launch starts.  The in-kernel timeline of round 1 put a third of a finest-level launch into
+// that drain (profiles/r1h_timeline_*.txt).  But the algorithm only orders the iterations of ONE pair (iteration k+1
+// of a pair needs the pose iteration k gave it); pairs do not wait for each other -- with one exception, the
+// batch-global sigma extremes of remove_tru_sigma (algorithms.py:1976-1979), handled below.
 //
-// How.  A unit of work is a warp tile (30 columns x TR rows of one pair at one iteration), the same tile routines as
-// the launch-per-iteration kernels walk it (uic_tile.cuh / uic_tile_staged.cuh).  Warps are workers: a worker takes
-// the next slot of a FIFO in global memory (one atomicAdd), waits until the slot holds an item, walks the tile and
-// writes one record.  The worker that completes the LAST tile of a pair-iteration folds the pair's records in tile
+// How.  A unit of work is a warp tile (30 columns x TR rows of one pair at one iteration), walked by the same tile
+// routines as the launch-per-iteration kernels (uic_tile.cuh / uic_tile_staged.cuh).  Warps are workers: a worker
+// takes the next slot of a FIFO in global memory (one atomicAdd), waits until the slot holds an item, walks the tile
+// and writes one record.  The worker that completes the LAST tile of a pair-iteration folds the pair's records in tile
 // order (fp64, deterministic whoever ran which tile), damps and solves the 6x6 system, writes the pose of iteration
-// k+1 and appends that iteration's tiles to the FIFO.  Nothing ever waits for a launch boundary; pairs drift apart and
-// the drain of one is hidden behind the tiles of the others.  Several independent batches ("groups") may share a
-// launch, which is what keeps the machine full while a batch is in its small coarse levels.
+// k+1 and appends that iteration's tiles to the FIFO.  Nothing waits for a launch boundary; pairs drift apart and the
+// drain of one is hidden behind the tiles of the others.  It pays when the call holds more work than one wave of
+// tiles: several independent batches ("groups") per call, or pairs that nothing couples.  The coarse levels stay
+// with the launch-per-iteration kernels: their iterations are latency chains (measured, profiles/r2/) that a whole
+// grid walks faster in lockstep than pair by pair.
 //
 // Batch-global sigma extremes without a barrier.  A pixel is masked when its warped sigma equals the minimum or the
 // maximum over the whole batch (group).  The mask only moves J^T r, and every record carries what its extreme pixels
@@ -70,11 +72,26 @@ __device__ __forceinline__ unsigned long long ld_acquire_u64(const unsigned long
 __device__ __forceinline__ void st_release_u64(unsigned long long* q, unsigned long long v) {
   asm volatile("st.release.gpu.global.u64 [%0], %1;" ::"l"(q), "l"(v) : "memory");
 }
+__device__ __forceinline__ void st_relaxed_u64(unsigned long long* q, unsigned long long v) {
+  asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(q), "l"(v) : "memory");
+}
 __device__ __forceinline__ unsigned long long q_now_ns() {
   unsigned long long t;
   asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
   return t;
 }
+
+// Optional phase stamps of pair 0 (compile with -DDPFT_QUEUE_STAMPS; read back with dpft_debug_queue_stamps): per
+// iteration k the %globaltimer at [0] first tile dequeued, [1] walk start / [2] walk end / [3] record flushed /
+// [4] counted of the pair's LAST tile, [5] folded, [6] solved or parked, [7] next tiles pushed, [8] group resolved.
+#ifdef DPFT_QUEUE_STAMPS
+__device__ unsigned long long g_qstamps[512 * 16];
+#define DPFT_QSTAMP(k, b, i) do { if ((b) == 0 && (threadIdx.x & 31) == 0 && (k) < 512) g_qstamps[(k) * 16 + (i)] = q_now_ns(); } while (0)
+#define DPFT_QSTAMP_MIN(k, b, i) do { if ((b) == 0 && (threadIdx.x & 31) == 0 && (k) < 512) atomicMin(&g_qstamps[(k) * 16 + (i)], q_now_ns()); } while (0)
+#else
+#define DPFT_QSTAMP(k, b, i) do { } while (0)
+#define DPFT_QSTAMP_MIN(k, b, i) do { } while (0)
+#endif
 
 // lane 0: wait until the slot holds an item (the producer may still be folding the pair that feeds it)
 __device__ __forceinline__ unsigned long long q_wait_item(const unsigned long long* slot) {
@@ -131,32 +148,27 @@ __device__ __forceinline__ void q_finalize(const QueueParams& p, const int k, co
 
 // Append the tiles of iteration k+1 of pair b (its pose has been written by this warp's lane 0).
 __device__ __forceinline__ void q_push_next(const QueueParams& p, const int k, const int b, const int lane) {
-  if (k + 1 >= p.n_levels * p.iters) return;
-  const int n = p.lv[(k + 1) / p.iters].tpp;
+  if (k + 1 >= p.iters) return;
+  const int n = p.L.tpp;
   __threadfence();                       // the pose (lane 0) and everything before it, ahead of the items
   __syncwarp();
   unsigned pos = 0;
   if (lane == 0) pos = atomicAdd(p.qctl + 1, (unsigned)n);
   pos = __shfl_sync(0xffffffffu, pos, 0);
-  for (int i = lane; i < n; i += 32) st_release_u64(p.fifo + pos + i, q_encode(k + 1, b, i));
+  // (the fence above orders the pose before the items; a release per store would fence 32 more times)
+  for (int i = lane; i < n; i += 32) st_relaxed_u64(p.fifo + pos + i, q_encode(k + 1, b, i));
 }
 
 // One item: walk the tile, write its record, count it.  Returns true for the worker that completed the pair-iteration.
-// Not inlined on purpose: the tile routines want every register the launch bounds allow, and inside the worker loop
-// the loop's own state (item, level, queue pointers) pushed accumulators of the row loop out to local memory.
-template <bool TRU, bool SB, bool AUX, int GW, int GH>
-__device__ __noinline__ bool q_walk_item(const QueueParams& p, float* area, const unsigned long long item) {
+// The level lives in the kernel parameters (constant bank): nothing of it occupies a register across the row loop.
+template <bool TRU, bool SB, bool AUX, int GW, int GH, int KIND>
+__device__ __forceinline__ bool q_walk_item(const QueueParams& p, float* area, const unsigned long long item) {
   const int lane = threadIdx.x & 31;
   float (*redw)[33] = reinterpret_cast<float (*)[33]>(area + kStageWarpFloats - 27 * 33);   // rows 27.. follow the ring
   float* spose = area + kStageAreaFloats;
-  // what the epilogue needs is parked in shared memory for the length of the tile walk (registers are what the row
-  // loop is short of) and decoded again afterwards
-  volatile unsigned long long* sitem = reinterpret_cast<volatile unsigned long long*>(spose + 16);
-  if (lane == 0) *sitem = item;
   const int k = q_item_k(item), b = q_item_b(item), t = q_item_t(item);
   const int B = p.B, C = p.C;
-  const int l = k / p.iters;
-  const QLevel& L = p.lv[l];
+  const QLevel& L = p.L;
   const int plane = L.H * L.W;
 
   PairView g;
@@ -175,11 +187,13 @@ __device__ __noinline__ bool q_walk_item(const QueueParams& p, float* area, cons
     g.b = b;
     g.tm_x1 = g.tm_s1 = g.tm_d1 = nullptr;
     if (TRU) {
-      const uint32_t* mm = p.s0mm + 2 * ((size_t)l * p.n_mm_groups + (p.n_mm_groups > 1 ? b / p.group : 0));
+      const uint32_t* mm = p.s0mm + 2 * (p.n_mm_groups > 1 ? b / p.group : 0);
       g.s0lo = ord2f(__ldcg(mm));
       g.s0hi = ord2f(__ldcg(mm + 1));
     }
   }
+  DPFT_QSTAMP_MIN(k, b, 0);
+  DPFT_QSTAMP(k, b, 1);
   __syncwarp();
   if (lane < 12) spose[lane] = __ldcg(p.pose_hist + ((size_t)k * B + b) * 12 + lane);
   if (TRU) {
@@ -193,24 +207,22 @@ __device__ __noinline__ bool q_walk_item(const QueueParams& p, float* area, cons
   {
     const int seg = t % L.nseg, rt = t / L.nseg;
     const int y0 = rt * L.TR, y1 = min(y0 + L.TR, L.H);
-    const int kind = L.kind;
     float* outl = area + kStageWarpFloats + 12 * 33;
-    if (GW > 0 && kind == 2)
+    if (KIND == 1)
       process_tile_staged<TRU, SB, GW, GH, AUX>(g, spose, redw + 27, area, outl, seg, y0, y1, lane, S);
-    else if (kind >= 1)
-      process_tile_staged<TRU, SB, 0, 0, AUX>(g, spose, redw + 27, area, outl, seg, y0, y1, lane, S);
     else
       process_tile<8, TRU>(g, spose, redw + 27, seg, y0, y1, lane, S);
   }
   __syncwarp();
-  const unsigned long long it2 = *sitem;
-  const int b2 = q_item_b(it2);
-  flush_warp<TRU>(S, redw, p.records + ((size_t)b2 * p.max_tiles + q_item_t(it2)) * PS, lane);
+  DPFT_QSTAMP(k, b, 2);
+  flush_warp<TRU>(S, redw, p.records + ((size_t)b * L.tpp + t) * PS, lane);
+  DPFT_QSTAMP(k, b, 3);
 
   __threadfence();
   __syncwarp();
   int last = 0;
-  if (lane == 0) last = (atomicAdd(p.tiles_done + b2, 1) == p.lv[q_item_k(it2) / p.iters].tpp - 1);
+  if (lane == 0) last = (atomicAdd(p.tiles_done + b, 1) == L.tpp - 1);
+  DPFT_QSTAMP(k, b, 4);
   return __shfl_sync(0xffffffffu, last, 0) != 0;
 }
 
@@ -221,13 +233,16 @@ __device__ __noinline__ void q_finish_pair(const QueueParams& p, float* area, co
   constexpr int NE = TRU ? NSUM : 27;
   double* sdbl = reinterpret_cast<double*>(area);        // PS doubles, free between two tile walks
   const int B = p.B;
-  const QLevel& L = p.lv[k / p.iters];
+  const QLevel& L = p.L;
   const int grp = b / p.group;
   __threadfence();
 
   // ---------------------------------------------------------------- fold the pair's records in tile order
-  const float* recs = p.records + (size_t)b * p.max_tiles * PS;
+  const float* recs = p.records + (size_t)b * L.tpp * PS;
   const int n = L.tpp;
+  // Lane e sums entry e of the records (and entry e + 32: the six corrections of the maximum and one of the minimum
+  // live past 32), sixteen loads in flight per lane, always in record order.  A correction only counts when its
+  // record sits on the pair's extreme, which is itself folded from the records first.
   float pair_min = CUDART_INF_F, pair_max = -CUDART_INF_F;
   if (TRU) {
     for (int i = lane; i < n; i += 32) {
@@ -237,35 +252,44 @@ __device__ __noinline__ void q_finish_pair(const QueueParams& p, float* area, co
     pair_min = warp_min(pair_min);
     pair_max = warp_max(pair_max);
   }
-#pragma unroll 1
-  for (int e = lane; e < NE; e += 32) {
-    const int sl = e < 27 ? e : e + 2;
-    // eight records in flight at a time (L2 round trips), summed in record order
-    const bool corr = TRU && e >= 27;
-    const int key_at = e < 33 ? E_VMIN : E_VMAX;
-    const float key_want = e < 33 ? pair_min : pair_max;
-    double s = 0.0;
+  {
+    const int e0 = lane, e1 = lane + 32;
+    const bool two = e1 < NE;
+    const int sl0 = e0 < 27 ? e0 : e0 + 2, sl1 = two ? e1 + 2 : sl0;
+    const bool corr0 = TRU && e0 >= 27;
+    const int key0_at = E_VMIN;                       // entries 27..31 belong to the minimum
+    const int key1_at = e1 < 33 ? E_VMIN : E_VMAX;    // entry 32 is the last of the minimum's, 33..38 the maximum's
+    const float want1 = e1 < 33 ? pair_min : pair_max;
+    double s0 = 0.0, s1 = 0.0;
     for (int i0 = 0; i0 < n; i0 += 8) {
-      float v[8], key[8];
+      float v0[8], v1[8], k0[8], k1[8];
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
         const float* q = recs + (size_t)min(i0 + j, n - 1) * PS;
-        v[j] = __ldcg(q + sl);
-        key[j] = corr ? __ldcg(q + key_at) : 0.f;
+        v0[j] = __ldcg(q + sl0);
+        k0[j] = corr0 ? __ldcg(q + key0_at) : 0.f;
+        v1[j] = two ? __ldcg(q + sl1) : 0.f;
+        k1[j] = (TRU && two) ? __ldcg(q + key1_at) : 0.f;
       }
 #pragma unroll
-      for (int j = 0; j < 8; ++j)
-        if (i0 + j < n && (!corr || key[j] == key_want)) s += (double)v[j];
+      for (int j = 0; j < 8; ++j) {
+        if (i0 + j < n) {
+          if (!corr0 || k0[j] == pair_min) s0 += (double)v0[j];
+          if (two && k1[j] == want1) s1 += (double)v1[j];
+        }
+      }
     }
-    sdbl[sl] = s;
+    if (e0 < NE) sdbl[sl0] = s0;
+    if (two) sdbl[sl1] = s1;
   }
+  DPFT_QSTAMP(k, b, 5);
   float s0lo = 0.f, s0hi = 0.f;
   if (lane == 0) {
     sdbl[E_VMIN] = (double)pair_min;
     sdbl[E_VMAX] = (double)pair_max;
     p.tiles_done[b] = 0;               // ready for the pair's next iteration
     if (TRU && p.aux) {
-      const uint32_t* mm = p.s0mm + 2 * ((size_t)(k / p.iters) * p.n_mm_groups + (p.n_mm_groups > 1 ? grp : 0));
+      const uint32_t* mm = p.s0mm + 2 * (p.n_mm_groups > 1 ? grp : 0);
       s0lo = ord2f(__ldcg(mm));
       s0hi = ord2f(__ldcg(mm + 1));
     }
@@ -303,7 +327,9 @@ __device__ __noinline__ void q_finish_pair(const QueueParams& p, float* area, co
     if (lane == 0) p.cand[b] = k + 1;
   } else {
     if (lane == 0) q_finalize<TRU, false>(p, k, b, sdbl, false, false);
+    DPFT_QSTAMP(k, b, 6);
     q_push_next(p, k, b, lane);
+    DPFT_QSTAMP(k, b, 7);
   }
   __threadfence();
   __syncwarp();
@@ -336,16 +362,20 @@ __device__ __noinline__ void q_finish_pair(const QueueParams& p, float* area, co
       q_push_next(p, k, base + j, lane);
     }
   }
+  DPFT_QSTAMP(k, 0, 8);
   if (p.t_done && lane == 0) {
     if (atomicAdd(p.groups_done + k, 1) == p.n_groups - 1) p.t_done[k + 1] = q_now_ns();
   }
 }
 
-template <bool TRU, bool SB, bool AUX, int GW, int GH>
+template <bool TRU, bool SB, bool AUX, int GW, int GH, int KIND>
 __global__ void __launch_bounds__(kQThreads, kQCtasPerSm) uic_queue_kernel(const __grid_constant__ QueueParams p) {
   extern __shared__ __align__(128) float q_dyn[];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   float* area = q_dyn + warp * kQAreaFloats;
+  // Workers stay until the queue is exhausted (one CTA per resident slot).  Workers that leave after a few items, so
+  // that retiring CTAs let the kernels of other streams in between, were measured and bought nothing
+  // (profiles/r2/stream_probe_items.txt).
   while (true) {
     unsigned slot = 0;
     if (lane == 0) slot = atomicAdd(p.qctl, 1u);
@@ -357,40 +387,34 @@ __global__ void __launch_bounds__(kQThreads, kQCtasPerSm) uic_queue_kernel(const
       if (p.t_done && slot == 0) p.t_done[0] = q_now_ns();
     }
     item = __shfl_sync(0xffffffffu, item, 0);
-    if (q_walk_item<TRU, SB, AUX, GW, GH>(p, area, item)) q_finish_pair<TRU>(p, area, q_item_k(item), q_item_b(item));
+    if (q_walk_item<TRU, SB, AUX, GW, GH, KIND>(p, area, item)) q_finish_pair<TRU>(p, area, q_item_k(item), q_item_b(item));
   }
 }
 
-// head / tail, counters, running extremes, candidate marks, the FIFO with the coarsest level's first iteration in it
-__global__ void __launch_bounds__(256) queue_init_kernel(const QueueParams p, const float* __restrict__ pose_in,
-                                                         const int n_mm) {
+// head / tail, counters, running extremes, candidate marks, the FIFO with the first iteration of every pair in it
+__global__ void __launch_bounds__(256) queue_init_kernel(const QueueParams p, const float* __restrict__ pose_in) {
   const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  const int n_it = p.n_levels * p.iters;
-  const unsigned n0 = (unsigned)p.B * (unsigned)p.lv[0].tpp;
+  const unsigned n0 = (unsigned)p.B * (unsigned)p.L.tpp;
   if (i < p.total_items) {
     unsigned long long v = 0;
-    if (i < n0) v = q_encode(0, (int)(i / p.lv[0].tpp), (int)(i % p.lv[0].tpp));
+    if (i < n0) v = q_encode(0, (int)(i / p.L.tpp), (int)(i % p.L.tpp));
     p.fifo[i] = v;
   }
   if (i == 0) {
     p.qctl[0] = 0u;
     p.qctl[1] = n0;
   }
-  if (i < (size_t)p.B * 12) p.pose_hist[i] = pose_in[i];
+  if (i < (size_t)p.B * 12 && pose_in != p.pose_hist) p.pose_hist[i] = pose_in[i];
   if (i < (size_t)p.B) {
     p.tiles_done[i] = 0;
     p.cand[i] = 0;
   }
-  if (i < (size_t)n_it * p.n_groups) {
+  if (i < (size_t)p.iters * p.n_groups) {
     p.pairs_done[i] = 0;
     p.gext[2 * i] = 0xffffffffu;
     p.gext[2 * i + 1] = 0u;
   }
-  if (i < (size_t)n_it) p.groups_done[i] = 0;
-  if (i < (size_t)n_mm) {
-    p.s0mm_rw[2 * i] = 0xffffffffu;
-    p.s0mm_rw[2 * i + 1] = 0u;
-  }
+  if (i < (size_t)p.iters) p.groups_done[i] = 0;
 }
 
 // extremes of sigma0 per (level, group): blockIdx.z = level, blockIdx.y = group
@@ -438,16 +462,29 @@ __global__ void __launch_bounds__(256) minmax_levels_kernel(const MmLevels q, ui
       lo = fminf(lo, s_lo[w]);
       hi = fmaxf(hi, s_hi[w]);
     }
-    uint32_t* out = mm + 2 * ((size_t)l * n_groups + grp);
+    uint32_t* out = mm + 2 * ((size_t)l * n_groups + grp);   // (level, group)
     atomicMin(out, f2ord(lo));
     atomicMax(out + 1, f2ord(hi));
   }
 }
 
-template <bool TRU, bool SB, bool AUX, int GW, int GH>
+void launch_minmax_levels(const float* const* v, const size_t* per_group, int n_levels, int n_groups, uint32_t* mm,
+                          cudaStream_t stream) {
+  MmLevels q{};
+  size_t widest = 0;
+  for (int l = 0; l < n_levels; ++l) {
+    q.v[l] = v[l];
+    q.per_group[l] = per_group[l];
+    widest = std::max(widest, per_group[l]);
+  }
+  const unsigned bx = (unsigned)std::max<size_t>(1, std::min<size_t>((widest / 4 + 255) / 256, (148 * 8) / std::max(1, n_groups) + 1));
+  minmax_levels_kernel<<<dim3(bx, n_groups, n_levels), 256, 0, stream>>>(q, mm, n_groups);
+}
+
+template <bool TRU, bool SB, bool AUX, int GW, int GH, int KIND>
 static cudaError_t launch_q(const QueueParams& prm, int grid, cudaStream_t stream) {
   constexpr int smem = kQW * kQAreaFloats * (int)sizeof(float);
-  auto* fn = uic_queue_kernel<TRU, SB, AUX, GW, GH>;
+  auto* fn = uic_queue_kernel<TRU, SB, AUX, GW, GH, KIND>;
   // (cudaFuncSetAttribute is per device and cheap: set it on every launch rather than caching per process)
   cudaError_t err = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
   if (err != cudaSuccess) return err;
@@ -457,46 +494,43 @@ static cudaError_t launch_q(const QueueParams& prm, int grid, cudaStream_t strea
 
 int queue_tiles_per_sm() { return kQCtasPerSm * kQW; }
 
-cudaError_t launch_queue(const QueueParams& prm_in, const float* pose_in, bool tru, int grid, cudaStream_t stream,
+// `prm.s0mm` must already hold the level's sigma0 extremes (launch_minmax_levels); pose_in may be prm.pose_hist.
+cudaError_t launch_queue(const QueueParams& prm, const float* pose_in, bool tru, int grid, cudaStream_t stream,
                          bool allow_fixed_geometry) {
-  QueueParams prm = prm_in;
-  const int n_it = prm.n_levels * prm.iters;
-  const int n_mm = prm.n_levels * prm.n_mm_groups;
   {
-    const size_t n = std::max<size_t>(std::max<size_t>(prm.total_items, (size_t)prm.B * 12),
-                                      std::max<size_t>((size_t)n_it * prm.n_groups, (size_t)n_mm));
-    queue_init_kernel<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(prm, pose_in, n_mm);
-  }
-  if (tru) {
-    MmLevels q{};
-    size_t widest = 0;
-    for (int l = 0; l < prm.n_levels; ++l) {
-      const size_t per_pair = (size_t)prm.SC * prm.lv[l].H * prm.lv[l].W;
-      q.v[l] = prm.lv[l].s0;
-      q.per_group[l] = prm.n_mm_groups > 1 ? per_pair * prm.group : per_pair * (prm.kf_shared ? 1 : prm.B);
-      widest = std::max(widest, q.per_group[l]);
-    }
-    const unsigned bx = (unsigned)std::max<size_t>(1, std::min<size_t>((widest / 4 + 255) / 256, (148 * 8) / std::max(1, prm.n_mm_groups) + 1));
-    minmax_levels_kernel<<<dim3(bx, prm.n_mm_groups, prm.n_levels), 256, 0, stream>>>(q, prm.s0mm_rw, prm.n_mm_groups);
+    const size_t n = std::max<size_t>(std::max<size_t>(prm.total_items, (size_t)prm.B * 12), (size_t)prm.iters * prm.n_groups);
+    queue_init_kernel<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(prm, pose_in);
   }
   const bool sb = prm.SC != prm.C;
-  bool aux = false;
-  for (int l = 0; l < prm.n_levels; ++l) aux = aux || prm.lv[l].m0 || prm.lv[l].m1;
-  // the reference's TUM pyramid (160x120 at the finest level) runs a geometry-specialised tile routine there
-  const QLevel& fine = prm.lv[prm.n_levels - 1];
-  if (allow_fixed_geometry && !sb && !aux && fine.kind >= 1 && fine.W == 160 && fine.H == 120) {
-    for (int l = 0; l < prm.n_levels; ++l)
-      if (prm.lv[l].kind >= 1 && prm.lv[l].W == 160 && prm.lv[l].H == 120) prm.lv[l].kind = 2;
-    return tru ? launch_q<true, false, false, 160, 120>(prm, grid, stream) : launch_q<false, false, false, 160, 120>(prm, grid, stream);
+  const bool aux = prm.L.m0 || prm.L.m1;
+  const bool staged = prm.L.kind >= 1;
+#define DPFT_Q(TRUV, SBV, AUXV, w, h, KINDV) launch_q<TRUV, SBV, AUXV, w, h, KINDV>(prm, grid, stream)
+  if (!staged) {   // levels the staged routine does not take (narrow, unaligned): the plain tile routine
+    if (tru) return aux ? DPFT_Q(true, false, true, 0, 0, 0) : DPFT_Q(true, false, false, 0, 0, 0);
+    return aux ? DPFT_Q(false, false, true, 0, 0, 0) : DPFT_Q(false, false, false, 0, 0, 0);
   }
-#define DPFT_Q(TRUV, SBV, AUXV) launch_q<TRUV, SBV, AUXV, 0, 0>(prm, grid, stream)
+  // the reference's TUM level 0 (160x120) runs a geometry-specialised tile routine
+  if (allow_fixed_geometry && !sb && !aux && prm.L.W == 160 && prm.L.H == 120)
+    return tru ? DPFT_Q(true, false, false, 160, 120, 1) : DPFT_Q(false, false, false, 160, 120, 1);
   if (tru) {
-    if (sb) return aux ? DPFT_Q(true, true, true) : DPFT_Q(true, true, false);
-    return aux ? DPFT_Q(true, false, true) : DPFT_Q(true, false, false);
+    if (sb) return aux ? DPFT_Q(true, true, true, 0, 0, 1) : DPFT_Q(true, true, false, 0, 0, 1);
+    return aux ? DPFT_Q(true, false, true, 0, 0, 1) : DPFT_Q(true, false, false, 0, 0, 1);
   }
-  if (sb) return aux ? DPFT_Q(false, true, true) : DPFT_Q(false, true, false);
-  return aux ? DPFT_Q(false, false, true) : DPFT_Q(false, false, false);
+  if (sb) return aux ? DPFT_Q(false, true, true, 0, 0, 1) : DPFT_Q(false, true, false, 0, 0, 1);
+  return aux ? DPFT_Q(false, false, true, 0, 0, 1) : DPFT_Q(false, false, false, 0, 0, 1);
 #undef DPFT_Q
 }
 
 }  // namespace dpft
+
+#ifdef DPFT_QUEUE_STAMPS
+// debug builds only: reset (fill with ~0) or read the phase stamps of pair 0
+extern "C" int dpft_debug_queue_stamps(unsigned long long* host, int n_it, int reset) {
+  if (reset) {
+    static unsigned long long ones[512 * 16];
+    for (auto& v : ones) v = ~0ull;
+    return (int)cudaMemcpyToSymbol(dpft::g_qstamps, ones, sizeof(ones));
+  }
+  return (int)cudaMemcpyFromSymbol(host, dpft::g_qstamps, sizeof(unsigned long long) * 16 * (size_t)n_it);
+}
+#endif

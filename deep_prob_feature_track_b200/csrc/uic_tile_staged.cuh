@@ -496,6 +496,7 @@ __device__ __forceinline__ void process_tile_staged(const PairView& g, const flo
     if (TRU) occ = occ || (sm[0].x == g.s0lo) || (sm[0].x == g.s0hi);
 
     const float2 zero2 = make_float2(0.f, 0.f), two2 = make_float2(2.f, 2.f), neg1 = make_float2(-1.f, -1.f);
+    const float2 rt_zero2 = make_float2(late0, late0);        // (0, 0), opaque to the compiler
     const float2 wa2 = make_float2(tap.wa, tap.wa), wb2 = make_float2(tap.wb, tap.wb);
     const float2 wc2 = make_float2(tap.wc, tap.wc), wd2 = make_float2(tap.wd, tap.wd);
     float2 saa2 = zero2, sab2 = zero2, sbb2 = zero2, sar2 = zero2, sbr2 = zero2, sca2 = zero2, scb2 = zero2;
@@ -587,9 +588,13 @@ __device__ __forceinline__ void process_tile_staged(const PairView& g, const flo
           k3 = sb_k;
         } else {
           // sigma is compared for equality against its batch extremes -> every product and sum rounded on its own,
-          // in blend_exact's order
-          sr = TRU ? __fadd2_rn(__fadd2_rn(__fadd2_rn(__fmul2_rn(za[j], wa2), __fmul2_rn(zb[j], wb2)),
-                                           __fmul2_rn(zc[j], wc2)), __fmul2_rn(zd[j], wd2))
+          // in blend_exact's order.  ptxas contracts mul.rn.f32x2 + add.rn.f32x2 into FFMA2 although both carry .rn
+          // (it honours the scalar forms); a saturated map then loses its one-ulp dips and the WRONG pixels tie with
+          // the extreme (tests/test_uic_queue_gpu.py: saturated sigma).  So the products are formed as x * w + 0 with
+          // a zero only known at run time -- an FFMA2 that is exactly the rounded product (sigma and the weights are
+          // non-negative, so no -0 can turn into +0) and that ptxas cannot merge into the sums.
+          sr = TRU ? __fadd2_rn(__fadd2_rn(__fadd2_rn(__ffma2_rn(za[j], wa2, rt_zero2), __ffma2_rn(zb[j], wb2, rt_zero2)),
+                                           __ffma2_rn(zc[j], wc2, rt_zero2)), __ffma2_rn(zd[j], wd2, rt_zero2))
                    : __ffma2_rn(zd[j], wd2, __ffma2_rn(zc[j], wc2, __ffma2_rn(zb[j], wb2, __fmul2_rn(za[j], wa2))));
           const float2 s0v = sm[SB ? 0 : p];
           const float2 ss = __ffma2_rn(sr, sr, __fmul2_rn(s0v, s0v));

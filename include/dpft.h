@@ -62,11 +62,14 @@ extern "C" {
                                        batch tracks against the same keyframe (kf_vo.py keyframe mode); forward only */
 #define DPFT_PAIRWISE_EXTREMES 0x80u /* with DPFT_REMOVE_TRU_SIGMA: sigma extremes per pair, i.e. the semantics of
                                         calling the reference once per pair with B = 1 (kf_vo.py:156-166); forward only */
-#define DPFT_QUEUE            0x200u /* dpft_uic_forward: the whole solve (every level, every iteration) as ONE launch
-                                        whose warps take warp tiles from a work queue; dependencies are per frame pair,
-                                        not per launch (csrc/uic_queue.cu).  Taken when the problem qualifies (C == 8,
-                                        DPFT_FUSED_SOBEL, no DPFT_COMBINE_ICP, no occ_out, iters >= 1), ignored otherwise.
-                                        Same results as the launch-per-iteration path up to summation order.          */
+#define DPFT_QUEUE            0x200u /* dpft_uic_forward: the finest level (all its iterations) as ONE launch whose warps
+                                        take warp tiles from a work queue; dependencies are per frame pair, not per
+                                        launch (csrc/uic_queue.cu).  It pays when the call holds several waves of tiles
+                                        and the pairs are not all coupled: several groups (dpft_uic_options.group), or
+                                        no DPFT_REMOVE_TRU_SIGMA, or pairwise extremes.  Taken when the problem
+                                        qualifies (C == 8, DPFT_FUSED_SOBEL, no DPFT_COMBINE_ICP, no occ_out,
+                                        iters >= 1), ignored otherwise.  Same results as the launch-per-iteration path
+                                        up to summation order.                                                        */
 #define DPFT_FUSED_SOBEL      0x08u /* recompute the unit Sobel gradients inside every iteration (sliding register
                                        window) instead of materialising them once per level                    */
 
@@ -94,13 +97,16 @@ typedef struct dpft_level {
  */
 typedef struct dpft_uic_options {
   uint32_t struct_bytes;
-  int32_t group;          /* DPFT_QUEUE + DPFT_REMOVE_TRU_SIGMA: pairs per sigma-extreme group.  The B pairs of the
-                             call are `B / group` independent batches of `group` consecutive pairs, each with the
-                             reference's batch-global extremes (alg:1976-1979) -- the results of B / group separate
-                             calls, from one launch.  0 = B (one batch); 1 = DPFT_PAIRWISE_EXTREMES.  B % group == 0.
+  int32_t group;          /* DPFT_REMOVE_TRU_SIGMA: pairs per sigma-extreme group.  The B pairs of the call are
+                             `B / group` independent batches of `group` consecutive pairs, each with the reference's
+                             batch-global extremes (alg:1976-1979) -- the results of B / group separate calls, from
+                             one call.  0 = B (one batch); 1 = DPFT_PAIRWISE_EXTREMES.  B % group == 0; groups other
+                             than B need DPFT_FUSED_SOBEL and exclude DPFT_COMBINE_ICP and occ_out.
                              aux_hist then has (n_levels*iters, B / group, 4) entries.                            */
   int32_t tile_rows[DPFT_MAX_LEVELS]; /* DPFT_QUEUE: rows per warp tile at level l (coarse first); 0 = chosen   */
   int32_t queue_ctas;     /* DPFT_QUEUE: CTAs (4 worker warps each) to launch; 0 = what the device holds        */
+  int32_t queue_levels;   /* DPFT_QUEUE: how many of the finest levels run as work-queue launches (one launch per
+                             level); 0 = 1.  The coarser levels keep one launch per iteration.                   */
   int32_t cta_slots;      /* launch-per-iteration kernels: resident CTA slots the tile heights are planned for  */
   int32_t tiling;         /* staged kernel: 0 balanced dealt tiles, 1 rectangular, 2 balanced linear ranges     */
   int32_t generic_geometry; /* 1: never pick the instantiations specialised for 160x120 / 80x60 levels          */
