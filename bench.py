@@ -1,29 +1,36 @@
 #!/usr/bin/env python
 """Benchmark of the trust-region inverse-compositional solver path (BASELINE.json metric).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload tum|vga]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload tum|vga|train]
 
-A *step* is one coarse-to-fine solve (4 pyramid levels x 3 Gauss-Newton iterations, U_IC with
---remove_tru_sigma as in every script the reference ships) of one batch of synthetic frame pairs.
-The metric is frame-pair GN solves per second; rank 0 prints ONE JSON line.
+A *step* is one coarse-to-fine solve (4 pyramid levels x 3 Gauss-Newton iterations, U_IC with --remove_tru_sigma as
+in every script the reference ships) of ONE batch of synthetic frame pairs -- 64 pairs at 120x160 (BASELINE config 2,
+the default), 16 live frames at 480x640 against a resident keyframe (config 3, --workload vga), or one training step
+of the patched reference tracker (config 4, --workload train).  The metric is frame-pair GN solves per second;
+rank 0 prints ONE JSON line.
 
-  value      whole-job throughput with the inputs already in HBM (CUDA events, max over ranks); independent
-             batches are issued round-robin on --streams CUDA streams (default 8) so the latency-bound coarse
-             levels of one batch overlap the finest level of another; --streams 1 gives the latency of one solve
-  e2e        same call made with HOST (pinned) buffers: host->device copy of the step's inputs and
-             device->host read of the poses inside the timed region
-  roofline   dominant kernel = the finest-level Gauss-Newton launch; algorithmic bytes per launch
-             (4C+2)*4*H*W*B  /  its average device time (events around every launch, separate pass)
-  cpu_baseline  the CPU port of the reference (oracle/) on this box's host cores, bounded sample
+  value      whole-job throughput with the inputs already in HBM, through the package's public BatchedSolver: calls
+             of `batches_per_call` batches (each batch keeps its own batch-global sigma extremes, i.e. the results
+             of separate reference calls) rotate over `streams` CUDA streams; K steps = K batches exactly.
+             `latency_ms` next to it is ONE batch alone on one stream.
+  e2e        same metric with HOST (pinned) buffers: every step uploads its batch and reads its poses back inside
+             the timed region (HostStreamSolver, 3 device buffers).  The host holds what the reference's encoder
+             emits: ONE uncertainty map per frame (alg:1425-1427 repeats it on the device).
+  roofline   dominant kernel = the finest-level work-queue launch (uic_queue_kernel: 3 iterations of
+             8 batches per launch); achieved = algorithmic bytes (4C+2)*4*H*W*B per iteration / CUDA-event time
+  parity     this run's own results against the CPU oracle on the step's first batch (twist, J^T W J, mask flips)
+  cpu_baseline  the reference itself (baseline/_ref, installed from /root/reference) on the host cores, full batches
 
-N > 1 is launched by torchrun (one rank per GPU); frame pairs are independent, so every rank solves
-its own batch and there is no collective on the data path (weak scaling).
+N > 1 is launched by torchrun (one rank per GPU); frame pairs are independent, so every rank solves its own
+batches and there is no collective on the data path (weak scaling).  --workload train adds the one collective of
+this code base: the NCCL all-reduce of the encoder gradients (deep_prob_feature_track_b200/ddp.py).
 """
 from __future__ import annotations
 
 import argparse
 import json
 import os
+import re
 import statistics
 import sys
 import threading
@@ -37,11 +44,14 @@ import torch  # noqa: E402
 WORKLOADS = {
     # BASELINE.json configs[1]: TUM-shape 120x160, batch 64, C=8 features, 4 levels x 3 iterations
     "tum": dict(name="tum120x160_b64_c8_uic_4lvl_x3it", B=64, C=8, H=120, W=160),
-    # BASELINE.json configs[2] per-GPU shard: 480x640, 128 pairs per GPU, processed 16 at a time
-    "vga": dict(name="vga480x640_b16_c8_uic_4lvl_x3it", B=16, C=8, H=480, W=640),
+    # BASELINE.json configs[2]: 480x640 keyframe VO; a step = 16 live frames tracked against the resident keyframe
+    "vga": dict(name="vga480x640_kf_b16_c8_uic_4lvl_x3it", B=16, C=8, H=480, W=640),
+    # BASELINE.json configs[3]: training step (forward + backward + all-reduce + optimizer) at 120x160, batch 64 per GPU
+    "train": dict(name="tum120x160_b64_c8_uic_trainstep", B=64, C=8, H=120, W=160),
 }
 N_LEVELS, ITERS = 4, 3
-N_SETS = 4           # distinct input sets rotated between steps so no step finds its inputs in L2
+ROOFLINE_BATCHES = 8          # batches per launch of the roofline pass (what the committed ncu capture ran)
+NCU_SUMMARY = os.path.join(ROOT, "profiles", "r2", "r2_uic_queue_kernel_level0_G8.txt")
 
 
 def algorithmic_bytes(B, C, H, W, levels=N_LEVELS, iters=ITERS):
@@ -104,407 +114,629 @@ class ClockSampler:
                 "reasons": sorted(self.reasons), "samples": len(self.samples)}
 
 
-def cpu_sample(levels, R0, t0, n_pairs, min_seconds=10.0, max_reps=500):
-    """Time the oracle port (reference op chain: grid_sample + permute/bmm/sum) on the host cores."""
-    from oracle import ic_oracle as O
+def base_config(wl):
+    """The part of `config` both arms print (the driver compares it)."""
+    return {"workload": wl["name"], "pairs_per_gpu_per_step": wl["B"], "feature_channels": wl["C"],
+            "resolution": f"{wl['H']}x{wl['W']}", "levels": N_LEVELS, "iters_per_level": ITERS, "variant": "U_IC",
+            "remove_tru_sigma": True}
+
+
+# ----------------------------------------------------------------------------------------------- CPU reference
+def cpu_reference_runner(wl, workload, seed):
+    """(step(), pairs_per_step, kind, description): the reference's own implementation of the path on the host cores.
+    baseline/_ref (the installed reference) when it is there, else the oracle port."""
+    from deep_prob_feature_track_b200.synthetic import make_frame_pairs
     threads = os.cpu_count() or 1
     torch.set_num_threads(threads)
-    sub = [{k: v[:n_pairs].contiguous() for k, v in lv.items()} for lv in levels]
-    pose = (R0[:n_pairs].contiguous(), t0[:n_pairs].contiguous())
+    B, C, H, W = wl["B"], wl["C"], wl["H"], wl["W"]
+    try:
+        from baseline import reference as REF
+        have_ref = REF.available()
+    except Exception:
+        have_ref = False
+    if workload == "train":
+        n = 8
+        if not have_ref:
+            raise SystemExit("--workload train --impl reference needs baseline/_ref (python baseline/install_reference.py)")
+        REF.modules()                         # puts baseline/_ref/code on the import path
+        import models.criterions as crit
+        net = REF.make_tracker(REF.EVAL_TUM_FLAGS).train()
+        img0, img1, d0, d1, K = REF.synthetic_rgbd(n, H, W, seed=seed)
+        R_gt = torch.eye(3).repeat(n, 1, 1)
+        t_gt = torch.tensor([[0.01, -0.005, 0.002]]).repeat(n, 1)
+        opt = torch.optim.Adam(net.parameters(), lr=1e-5, weight_decay=4e-4)
 
-    def once():
+        def step():
+            opt.zero_grad()
+            Rs, ts = net(img0, img1, d0, d1, K)
+            loss = crit.compute_RT_EPE_loss(Rs, ts, R_gt, t_gt, d0, K, invalid=(d0 < 0.1)).mean() * 1e2
+            loss.backward()
+            torch.nn.utils.clip_grad_norm_(net.parameters(), 5.0)
+            opt.step()
+        return step, n, "reference", (f"training step of the reference's LeastSquareTracking (train.py:117-192) on {n} of the "
+                                      f"{B} pairs of a step")
+    n = B if workload == "tum" else 1
+    data = make_frame_pairs(n, C, H, W, seed=seed, n_levels=N_LEVELS)
+    pose = [data["R0"], data["t0"].view(n, 3, 1)]
+    if have_ref:
+        net = REF.make_tracker().eval()
+
+        def step():
+            with torch.no_grad():
+                REF.solver_chain(net, data["levels"], pose)
+        return step, n, "reference", (f"tr_update3..0 of the reference's LeastSquareTracking (LeastSquareTracking.py:345-446) on "
+                                      f"{n} of the {B} pairs of a step")
+    from oracle import ic_oracle as O
+
+    def step():
         with torch.no_grad():
-            return O.track_pyramid(sub, pose, iters=ITERS, remove_tru_sigma=True, sampler="grid_sample",
-                                   reduction="bmm")
+            O.track_pyramid(data["levels"], (data["R0"], data["t0"]), iters=ITERS, remove_tru_sigma=True,
+                            sampler="grid_sample", reduction="bmm")
+    return step, n, "port", f"oracle port of the reference op chain on {n} of the {B} pairs of a step (baseline/_ref missing)"
 
-    small = [{k: v[:2].contiguous() for k, v in lv.items()} for lv in levels]
-    with torch.no_grad():
-        O.track_pyramid(small, (R0[:2], t0[:2]), iters=ITERS, remove_tru_sigma=True, sampler="grid_sample",
-                        reduction="bmm")
+
+def cpu_sample(wl, workload, seed, min_seconds=10.0):
+    """Mean throughput of full steps of the CPU reference over >= min_seconds (the statistic of the reference arm)."""
+    step, n, kind, what = cpu_reference_runner(wl, workload, seed)
+    step()
     times = []
     t_begin = time.perf_counter()
-    while len(times) < max_reps and (not times or time.perf_counter() - t_begin < min_seconds):
+    while len(times) < 2 or time.perf_counter() - t_begin < min_seconds:
         t = time.perf_counter()
-        once()
+        step()
         times.append(time.perf_counter() - t)
-    return n_pairs / min(times), threads, times
+    return {"value": n * len(times) / sum(times), "unit": "pairs/s", "cores": os.cpu_count() or 1, "kind": kind,
+            "sample": f"{what}; mean of {len(times)} steps after 1 warm-up ({sum(times):.1f} s of CPU work)"}
 
 
-def train_step_leg(A, dev_sets, pose0, B, steps, dev):
-    """Solver part of a training step (BASELINE config 4): forward + backward through all 12 iterations, loss =
-    a linear functional of every level's pose (what criterions.py:101-136 feeds back)."""
-    import torch
+def reference_arm(args, wl):
+    step, n, kind, what = cpu_reference_runner(wl, args.workload, 1234)
+    for _ in range(args.warmup):
+        step()
+    t = time.perf_counter()
+    for _ in range(args.steps):
+        step()
+    dt = time.perf_counter() - t
+    v = n * args.steps / dt
+    print(json.dumps({
+        "impl": "reference", "metric": "frame-pair GN solves/sec", "value": v, "unit": "pairs/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": base_config(wl),
+        "cpu_baseline": {"value": v, "unit": "pairs/s", "cores": os.cpu_count() or 1, "kind": kind,
+                         "sample": f"{what}; mean of {args.steps} steps after {args.warmup} warm-up"},
+        "e2e": {"value": v, "unit": "pairs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }))
+
+
+# ----------------------------------------------------------------------------------------------- helpers (GPU)
+def event_time_ms(fn, main):
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(main)
+    fn()
+    e1.record(main)
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1)
+
+
+def stacked_sets(gen_dev, n_sets, n_batches):
+    """n_sets distinct allocations of n_batches batches each, composed from the generated batches rolled along the
+    batch axis (distinct addresses and pair orders: no step finds another step's inputs in L2)."""
+    sets = []
+    for s in range(n_sets):
+        parts = [(gen_dev[(s + j) % len(gen_dev)], (5 * j + 3 * s) % 64) for j in range(n_batches)]
+        levels = [{k: torch.cat([torch.roll(p["levels"][l][k], sh, 0) if (sh and k != "K") else p["levels"][l][k]
+                                 for p, sh in parts]).contiguous() for k in parts[0][0]["levels"][l]}
+                  for l in range(N_LEVELS)]
+        pose = (torch.cat([p["R0"] for p, _ in parts]), torch.cat([p["t0"] for p, _ in parts]))
+        sets.append((levels, pose))
+    return sets
+
+
+def take(levels, pose, n):
+    return [{k: v[:n] for k, v in lv.items()} for lv in levels], (pose[0][:n], pose[1][:n])
+
+
+def ncu_traffic(path):
+    """dram bytes read + written of the committed ncu --set full capture of the roofline kernel (per launch)."""
+    try:
+        txt = open(path).read()
+        rd = re.search(r"dram__bytes_read\.sum\s+(\S+)\s+([0-9.]+)", txt)
+        wr = re.search(r"dram__bytes_write\.sum\s+(\S+)\s+([0-9.]+)", txt)
+        scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+        return float(rd.group(2)) * scale[rd.group(1)] + float(wr.group(2)) * scale[wr.group(1)]
+    except Exception:
+        return None
+
+
+def parity_block(A, batch_cpu, res_rows, lpi_occ):
+    """This run's results on one batch against the CPU oracle: twist, J^T W J of every iteration, mask flips."""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from helpers import frob_rel, twist_rel_err
+    from oracle import ic_oracle as O
+    trace = []
+    with torch.no_grad():
+        pose, _ = O.track_pyramid(batch_cpu["levels"], (batch_cpu["R0"], batch_cpu["t0"]), iters=ITERS, remove_tru_sigma=True,
+                                  trace=trace, reduction="einsum")
+    R, t = A.unpack_pose(res_rows["pose_hist"][-1].cpu())
+    relA, relb, flips, pixels = 0.0, 0.0, 0, 0
+    for i, tr in enumerate(trace):
+        for it, rec in enumerate(tr):
+            k = i * ITERS + it
+            Ac, bc = A.unpack_system(res_rows["sys_hist"][k].cpu())
+            relA, relb = max(relA, frob_rel(Ac, rec["A"])), max(relb, frob_rel(bc, rec["b"]))
+            occ = lpi_occ[i][it].cpu()
+            flips += int((occ != rec["occ"][:, 0].to(torch.uint8)).sum())
+            pixels += occ.numel()
+    n4 = 4
+    return {"against": "oracle/ic_oracle.py (CPU restatement of the reference, pinned to reference-generated fixtures)",
+            "pairs": int(R.shape[0]), "twist_rel_err_max": twist_rel_err(R, t, pose[0], pose[1]),
+            "twist_rel_err_max_first4": twist_rel_err(R[:n4], t[:n4], pose[0][:n4], pose[1][:n4]),
+            "pose_abs_err_max": max((R - pose[0]).abs().max().item(), (t - pose[1]).abs().max().item()),
+            "JtWJ_frob_rel_max": relA, "JtWr_frob_rel_max": relb, "mask_flips": flips, "mask_pixels": pixels,
+            "note": "masks of the first iteration are bit-exact (tests); later iterations start from poses that differ in "
+                    "the last bits, so threshold-adjacent pixels may flip"}
+
+
+# ----------------------------------------------------------------------------------------------- workloads (GPU)
+def run_tum(args, wl, rank, world, dev, barrier, max_over_ranks):
+    from deep_prob_feature_track_b200 import algorithms as A
+    from deep_prob_feature_track_b200.batched import BatchedSolver, HostStreamSolver, pack_levels
+    from deep_prob_feature_track_b200.synthetic import make_frame_pairs
+    B, C, H, W = wl["B"], wl["C"], wl["H"], wl["W"]
+    K, S = args.steps, max(1, args.streams)
+    G = max(1, min(args.batches_per_call, K))
+    bytes_step, bytes_lvl0 = algorithmic_bytes(B, C, H, W)
+    main = torch.cuda.current_stream(dev)
+
+    gen = [make_frame_pairs(B, C, H, W, seed=1234 + 100 * rank + i, n_levels=N_LEVELS) for i in range(4)]
+    gen_dev = [{"levels": [{k: v.to(dev) for k, v in lv.items()} for lv in g["levels"]], "R0": g["R0"].to(dev),
+                "t0": g["t0"].to(dev)} for g in gen]
+    n_stack = max(G, ROOFLINE_BATCHES)
+    sets = stacked_sets(gen_dev, S, n_stack)               # one stacked set per stream
+    set_bytes = sum(v.numel() * 4 for lv in sets[0][0] for v in lv.values()) // n_stack
+    solver = BatchedSolver(B, iters=ITERS, remove_tru_sigma=True, streams=S, device=dev)
+
+    calls = [G] * (K // G) + ([K % G] if K % G else [])     # K steps exactly
+
+    def run(call_sizes):
+        out = None
+        for i, g in enumerate(call_sizes):
+            out = solver.submit(*take(*sets[i % S], B * g))
+        return out
+
+    # ---- value
+    warm = [G] * max(1, (args.warmup + G - 1) // G)
+    res = run(warm + [1])                                   # every call size once (allocator, function attributes)
+    if calls[-1] != G:
+        run([calls[-1]])
+    solver.synchronize()
+    res.raise_if_bad()
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(main)
+    solver.wait_for(e0)
+    res = run(calls)
+    solver.join(main)
+    e1.record(main)
+    barrier()
+    ms = max_over_ranks(e0.elapsed_time(e1), dev)
+    res.raise_if_bad()
+    launches_per_call = 2 + 3 * ITERS + 4          # init, sigma0 extremes, 9 coarse iterations; extremes init + extremes, queue init, queue kernel
+
+    # ---- latency of ONE batch alone (launch-per-iteration kernels, one stream)
+    one = [take(*s, B) for s in sets]
+    lat = []
+    for i in range(3 + 10):
+        t = event_time_ms(lambda: A.uic_solve(*one[i % S], iters=ITERS, remove_tru_sigma=True), main)
+        if i >= 3:
+            lat.append(t)
+    latency_ms = statistics.median(lat)
+
+    # ---- roofline: the finest-level work-queue launch, ROOFLINE_BATCHES batches per launch, CUDA events around it
+    full = A.uic_solve(*take(*sets[0], B * ROOFLINE_BATCHES), iters=ITERS, remove_tru_sigma=True, group=B, queue=True)
+    pose_l0 = A.unpack_pose(full.pose_hist[(N_LEVELS - 1) * ITERS])
+    fine = [take(*s, B * ROOFLINE_BATCHES)[0][-1] for s in sets]
+
+    def fine_launch(i):
+        return A.uic_solve([fine[i % S]], pose_l0, iters=ITERS, remove_tru_sigma=True, group=B, queue=True)
+    for i in range(3):
+        fine_launch(i)
+    torch.cuda.synchronize()
+    call_ms = statistics.mean(event_time_ms(lambda i=i: fine_launch(i), main) for i in range(max(3, min(K, 10))))
+    # the kernel alone: CUDA events recorded by the library right before / after the work-queue kernel's launch
+    timed = [A.uic_solve([fine[i % S]], pose_l0, iters=ITERS, remove_tru_sigma=True, group=B, queue=True, timed=True)
+             for i in range(max(3, min(K, 10)))]
+    ev = [r.queue_kernel_ms[0] for r in timed]
+    launch_ms = statistics.mean(ev)
+    stamps = timed[0].launch_ms
+    assert (fine_launch(0).pose_hist[-1] - full.pose_hist[-1]).abs().max().item() < 1e-5   # the timed launch does the real work
+
+    # ---- parity of this very run (first batch of the first set) against the CPU oracle
+    parity = None
+    if rank == 0 and not args.no_parity:
+        first = A.uic_solve(*take(*sets[0], B * G), iters=ITERS, remove_tru_sigma=True, group=B, **solver.solve_kw)
+        lpi = A.uic_solve(*one[0], iters=ITERS, remove_tru_sigma=True, queue=False, want_occ=True)
+        torch.cuda.synchronize()
+        parity = parity_block(A, gen[0], {"pose_hist": first.pose_hist[:, :B], "sys_hist": first.sys_hist[:, :B]}, lpi.occ)
+
+    # ---- e2e: every step's batch comes from pinned host memory and its poses go back
+    host_levels = [dict(lv, s0=lv["s0"][:, :1].contiguous(), s1=lv["s1"][:, :1].contiguous()) for lv in gen[0]["levels"]]
+    assert all(torch.equal(lv["s0"], h["s0"].expand_as(lv["s0"])) for lv, h in zip(gen[0]["levels"], host_levels))
+    host_flat, layout = pack_levels(host_levels, pin=True)
+    host_flats = [host_flat] + [host_flat.clone().pin_memory() for _ in range(2)]
+    pose0 = (gen_dev[0]["R0"], gen_dev[0]["t0"])
+    streamer = HostStreamSolver(layout, host_flat.numel(), N_LEVELS, B, dev,
+                                lambda lv: A.uic_solve(lv, pose0, iters=ITERS, remove_tru_sigma=True), depth=3)
+    n_e2e = K
+    streamer.run([host_flats[i % 3] for i in range(3)])
+    barrier()
+    e0.record(main)
+    out_host = streamer.run([host_flats[i % 3] for i in range(n_e2e)])
+    e1.record(main)
+    barrier()
+    ms_e2e = max_over_ranks(e0.elapsed_time(e1), dev)
+    torch.cuda.synchronize()
+    e2e_ok = (out_host.to(dev) - A.uic_solve(gen_dev[0]["levels"], pose0, iters=ITERS, remove_tru_sigma=True).pose_hist[-1]).abs().max().item()
+
+    extras = {}
+    if not args.no_extras and rank == 0:
+        # the same solve with the uncertainty passed as the ONE map per frame the reference's encoder emits
+        one_sigma = [([dict(lv, s0=lv["s0"][:, :1].contiguous(), s1=lv["s1"][:, :1].contiguous()) for lv in s[0]], s[1]) for s in sets[:1]]
+        tmp = BatchedSolver(B, iters=ITERS, remove_tru_sigma=True, streams=1, device=dev)
+        for _ in range(2):
+            tmp.submit(*take(*one_sigma[0], B * G))
+        tmp.synchronize()
+        e0.record(main)
+        tmp.wait_for(e0)
+        n_sb = max(2, min(4, K // G))
+        for _ in range(n_sb):
+            tmp.submit(*take(*one_sigma[0], B * G))
+        tmp.join(main)
+        e1.record(main)
+        torch.cuda.synchronize()
+        extras["single_sigma_map"] = {"what": "sigma0 / sigma1 given as (B,1,h,w) instead of repeated to C channels "
+                                              "(DPFT_SIGMA_BROADCAST); same results, one stream",
+                                      "pairs_per_s": B * G * n_sb / (e0.elapsed_time(e1) * 1e-3)}
+        del one_sigma, tmp
+        extras["train_step_solver_only"] = train_solver_leg(A, one, B, dev, main)
+
+    peak, peak_src = measured_peak()
+    achieved = ITERS * bytes_lvl0 * ROOFLINE_BATCHES / (launch_ms * 1e-3) / 1e9
+    traffic = ncu_traffic(NCU_SUMMARY)
+    return {
+        "value": world * B * K / (ms * 1e-3), "ms_per_step": ms / K,
+        "config": dict(base_config(wl), batches_per_call=G, streams=S, call_sizes=calls,
+                       api="deep_prob_feature_track_b200.batched.BatchedSolver.submit",
+                       coarse_levels="one launch per Gauss-Newton iteration (uic_iter_staged_kernel / uic_iter_kernel), all batches of a call in one grid",
+                       finest_level="one work-queue launch for its 3 iterations (uic_queue_kernel, per-pair dependencies)",
+                       sigma_extremes="per batch of 64 (options.group): the results of separate reference calls",
+                       l2=f"every stream owns a set of {n_stack} batches ({set_bytes / 1e6:.0f} MB each, > 126 MB L2 per call); "
+                          f"sets differ in addresses and pair order",
+                       algorithmic_bytes_per_step=bytes_step),
+        "latency_ms": latency_ms,
+        "latency_note": "one batch of 64 pairs alone on one stream (launch-per-iteration kernels): ms per solve",
+        "step_hbm_frac": bytes_step / (ms / K * 1e-3) / 1e9 / peak,
+        "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                     "traffic": traffic,
+                     "traffic_source": "ncu --set full dram__bytes_read.sum + dram__bytes_write.sum of the same launch "
+                                       "(8 batches): profiles/r2/r2_uic_queue_kernel_level0_G8.txt",
+                     "kernel": "uic_queue_kernel<true,false,false,160,120,1>: the finest level (120x160) of "
+                               f"{ROOFLINE_BATCHES} batches of {B} pairs, its {ITERS} Gauss-Newton iterations in one launch",
+                     "algorithmic_bytes_per_launch": ITERS * bytes_lvl0 * ROOFLINE_BATCHES, "launch_ms": launch_ms,
+                     "launch_ms_all": [round(x, 4) for x in ev],
+                     "iteration_ms_device_stamps": [round(x, 4) for x in stamps],
+                     "per_batch_iteration_us": launch_ms * 1e3 / (ITERS * ROOFLINE_BATCHES),
+                     "peak_source": peak_src,
+                     "call_ms_with_helper_launches": call_ms,
+                     "how": "CUDA events recorded on the launching stream right before and right after the kernel's launch "
+                            "(dpft_uic_options.queue_kernel_ms), separate pass after the timed region; call_ms adds the "
+                            "launches around it (sigma0 extremes of the level, queue init); iteration_ms_device_stamps are "
+                            "%globaltimer stamps of the iteration completions inside the kernel"},
+        "parity": parity,
+        "e2e": {"value": world * B * n_e2e / (ms_e2e * 1e-3), "unit": "pairs/s",
+                "h2d_bytes_per_step": streamer.h2d_bytes_per_step, "d2h_bytes_per_step": streamer.d2h_bytes_per_step,
+                "steps": n_e2e, "ms_per_step": ms_e2e / n_e2e,
+                "what": "pinned host batch (x0, x1 with 8 channels, ONE sigma map per frame as the reference's encoder emits it, "
+                        "inverse depths, K) -> 3 device buffers -> solve -> poses in pinned memory, every step",
+                "pose_check_max_abs": e2e_ok},
+        "gpu_launches": launches_per_call * len(calls),
+        "extra": extras,
+    }
+
+
+def train_solver_leg(A, one, B, dev, main):
+    """Solver part of a training step alone (forward + backward through all 12 iterations, linear loss)."""
     leaves = [[{k: (v.clone().requires_grad_(True) if k in ("x0", "x1", "s0", "s1") else v) for k, v in lv.items()}
-               for lv in s] for s in dev_sets[:2]]
-    R = pose0[0].clone().requires_grad_(True)
-    t = pose0[1].clone().requires_grad_(True)
+               for lv in s[0]] for s in one[:2]]
+    R = one[0][1][0].clone().requires_grad_(True)
+    t = one[0][1][1].clone().requires_grad_(True)
 
     def step(i):
-        for lv in leaves[i % 2]:
+        for lv in leaves[i % len(leaves)]:
             for k in ("x0", "x1", "s0", "s1"):
                 lv[k].grad = None
-        outs = A.uic_track(leaves[i % 2], (R, t), iters=ITERS, remove_tru_sigma=True, check=False)
-        loss = sum(Rl.sum() + tl.sum() for Rl, tl, _ in outs)
-        loss.backward()
-
+        outs = A.uic_track(leaves[i % len(leaves)], (R, t), iters=ITERS, remove_tru_sigma=True, check=False)
+        sum(Rl.sum() + tl.sum() for Rl, tl, _ in outs).backward()
     for i in range(3):
         step(i)
-    torch.cuda.synchronize()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for i in range(steps):
-        step(i)
-    e1.record()
-    torch.cuda.synchronize()
-    ms = e0.elapsed_time(e1) / steps
-    return {"what": "solver forward+backward (autograd through 4 levels x 3 iterations), per GPU", "ms_per_step": ms,
-            "pairs_per_s": B / (ms * 1e-3), "steps": steps}
-
-
-def vga_leg(A, rank, dev, args):
-    """BASELINE config 3 shape: 480x640 pairs, 16 per call (a 128-pair shard is 8 such calls)."""
-    import torch
-    from deep_prob_feature_track_b200.synthetic import make_frame_pairs
-    wl = WORKLOADS["vga"]
-    B, C, H, W = wl["B"], wl["C"], wl["H"], wl["W"]
-    data = make_frame_pairs(B, C, H, W, seed=99 + rank, n_levels=N_LEVELS)
-    sets = []
-    for s in range(2):
-        sets.append([{k: torch.roll(v, s, 0).to(dev) for k, v in lv.items()} for lv in data["levels"]])
-    pose0 = (data["R0"].to(dev), data["t0"].to(dev))
-
-    def solve(i, **kw):
-        return A.uic_solve(sets[i % 2], pose0, iters=ITERS, remove_tru_sigma=True, pdl=not args.no_pdl,
-                           fused_sobel=args.fused_sobel, single_launch=args.single_launch, staged_footprint=not args.no_staged, **kw)
-
-    for i in range(3):
-        solve(i)
     torch.cuda.synchronize()
     n = 10
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for i in range(n):
-        solve(i)
-    e1.record()
-    torch.cuda.synchronize()
-    ms = e0.elapsed_time(e1) / n
-    r = solve(0, timed=True)
+    ms = event_time_ms(lambda: [step(i) for i in range(n)], main) / n
+    return {"what": "solver forward+backward alone (autograd through 4 levels x 3 iterations), one GPU", "ms_per_step": ms,
+            "pairs_per_s": B / (ms * 1e-3)}
+
+
+def run_vga(args, wl, rank, world, dev, barrier, max_over_ranks):
+    """BASELINE config 3: keyframe VO at 480x640.  A sequence's keyframe stays resident; a step tracks 16 live frames
+    against it (per-frame sigma extremes = the semantics of kf_vo.py's B = 1 calls)."""
+    from deep_prob_feature_track_b200 import algorithms as A
+    from deep_prob_feature_track_b200.batched import HostStreamSolver, pack_levels
+    from deep_prob_feature_track_b200.synthetic import make_frame_pairs
+    B, C, H, W = wl["B"], wl["C"], wl["H"], wl["W"]
+    K, S = args.steps, max(1, args.streams)
     bytes_step, bytes_lvl0 = algorithmic_bytes(B, C, H, W)
-    lvl0 = sum(r.launch_ms[-ITERS:]) / ITERS
-    out = {"workload": wl["name"], "ms_per_step": ms, "pairs_per_s": B / (ms * 1e-3),
-           "lvl0_launch_ms": lvl0, "lvl0_algorithmic_GBps": bytes_lvl0 / (lvl0 * 1e-3) / 1e9,
-           "step_algorithmic_GBps": bytes_step / (ms * 1e-3) / 1e9}
-    # keyframe mode (kf_vo.py --vo_type keyframe): the same live frames against ONE keyframe uploaded once
-    key = [{k: lv[k][:1].contiguous() for k in ("x0", "s0", "invD0")} for lv in sets[0]]
+    main = torch.cuda.current_stream(dev)
+    data = make_frame_pairs(B, C, H, W, seed=99 + rank, n_levels=N_LEVELS, motion=0.05)
+    key = [{k: lv[k][:1].to(dev).contiguous() for k in ("x0", "s0", "invD0")} for lv in data["levels"]]
+    live_cpu = [{k: lv[k] for k in ("x1", "s1", "invD1", "K")} for lv in data["levels"]]
+    lives = [[{k: (torch.roll(v, s, 0) if k != "K" else v).to(dev).contiguous() for k, v in lv.items()} for lv in live_cpu]
+             for s in range(max(2, S))]
+    pose0 = (data["R0"].to(dev), data["t0"].to(dev))
     tracker = A.KeyframeTracker(key, iters=ITERS, remove_tru_sigma=True)
-    live = [[{k: lv[k] for k in ("x1", "s1", "invD1", "K")} for lv in s] for s in sets]
+    streams = [torch.cuda.Stream(device=dev) for _ in range(S)]
+
+    def run(n):
+        out = None
+        for i in range(n):
+            with torch.cuda.stream(streams[i % S]):
+                out = tracker.track(lives[i % len(lives)], pose0)
+        return out
+    res = run(max(args.warmup, S))
+    torch.cuda.synchronize()
+    res.raise_if_bad()
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(main)
+    for st in streams:
+        st.wait_event(e0)
+    res = run(K)
+    for st in streams:
+        evd = torch.cuda.Event()
+        evd.record(st)
+        main.wait_event(evd)
+    e1.record(main)
+    barrier()
+    ms = max_over_ranks(e0.elapsed_time(e1), dev)
+    res.raise_if_bad()
+
+    # latency of ONE live frame (kf_vo.py's callback: B = 1 per call)
+    live1 = [{k: v[:1] for k, v in lv.items()} for lv in lives[0]]
+    p1 = (pose0[0][:1], pose0[1][:1])
+    for _ in range(3):
+        tracker.track(live1, p1)
+    torch.cuda.synchronize()
+    lat1 = statistics.median(event_time_ms(lambda: tracker.track(live1, p1), main) for _ in range(10))
+
+    # roofline: the finest-level work-queue launch of one step
+    full = tracker.track(lives[0], pose0)
+    pose_l0 = A.unpack_pose(full.pose_hist[(N_LEVELS - 1) * ITERS])
+    kfine = A.KeyframeTracker(key[-1:], iters=ITERS, remove_tru_sigma=True)
     for i in range(3):
-        tracker.track(live[i % 2], pose0)
+        kfine.track([lives[i % len(lives)][-1]], pose_l0)
     torch.cuda.synchronize()
-    e0.record()
-    for i in range(n):
-        tracker.track(live[i % 2], pose0)
-    e1.record()
+    ev = [event_time_ms(lambda i=i: kfine.track([lives[i % len(lives)][-1]], pose_l0), main) for i in range(max(3, min(K, 10)))]
+    launch_ms = statistics.mean(ev)
+
+    # parity against the oracle, frame by frame (B = 1 semantics), first 2 live frames
+    parity = None
+    if rank == 0 and not args.no_parity:
+        sys.path.insert(0, os.path.join(ROOT, "tests"))
+        from helpers import twist_rel_err
+        from oracle import ic_oracle as O
+        errs = []
+        Rc, tc = (x.cpu() for x in full.pose)
+        for b in range(2):
+            lv1 = [dict(x0=lv["x0"][:1], s0=lv["s0"][:1], invD0=lv["invD0"][:1], **{k: v[b:b + 1] for k, v in lc.items()})
+                   for lv, lc in zip(data["levels"], live_cpu)]
+            with torch.no_grad():
+                (R, t), _ = O.track_pyramid(lv1, (data["R0"][b:b + 1], data["t0"][b:b + 1]), iters=ITERS, remove_tru_sigma=True)
+            errs.append((twist_rel_err(Rc[b:b + 1], tc[b:b + 1], R, t), max((Rc[b] - R[0]).abs().max().item(), (tc[b] - t[0]).abs().max().item())))
+        parity = {"against": "oracle/ic_oracle.py, one B = 1 call per live frame (kf_vo.py:156-166)", "pairs": 2,
+                  "twist_rel_err_max": max(e[0] for e in errs), "pose_abs_err_max": max(e[1] for e in errs)}
+
+    # e2e: the live frames of every step come from pinned host memory (the keyframe side stays resident)
+    host_live = [dict(lv, s1=lv["s1"][:, :1].contiguous()) for lv in live_cpu]
+    key_sb = [dict(kf, s0=kf["s0"][:, :1].contiguous()) for kf in key]
+    tracker_sb = A.KeyframeTracker(key_sb, iters=ITERS, remove_tru_sigma=True)
+    host_flat, layout = pack_levels(host_live, pin=True)
+    host_flats = [host_flat, host_flat.clone().pin_memory()]
+    streamer = HostStreamSolver(layout, host_flat.numel(), N_LEVELS, B, dev, lambda lv: tracker_sb.track(lv, pose0), depth=3)
+    streamer.run(host_flats)
+    barrier()
+    e0.record(main)
+    streamer.run([host_flats[i % 2] for i in range(K)])
+    e1.record(main)
+    barrier()
+    ms_e2e = max_over_ranks(e0.elapsed_time(e1), dev)
+
+    peak, peak_src = measured_peak()
+    achieved = ITERS * bytes_lvl0 / (launch_ms * 1e-3) / 1e9
+    return {
+        "value": world * B * K / (ms * 1e-3), "ms_per_step": ms / K,
+        "config": dict(base_config(wl), streams=S, keyframe="one resident keyframe per sequence (x0, sigma0, invD0 with batch size 1), "
+                       "16 live frames per step, sigma extremes per frame (DPFT_SHARED_KEYFRAME | DPFT_PAIRWISE_EXTREMES)",
+                       api="deep_prob_feature_track_b200.algorithms.KeyframeTracker.track",
+                       l2=f"live frames rotate over {len(lives)} resident sets of {sum(v.numel() * 4 for lv in lives[0] for v in lv.values()) / 1e6:.0f} MB (> 126 MB L2)",
+                       algorithmic_bytes_per_step=bytes_step),
+        "latency_ms": lat1, "latency_note": "ONE live frame against the keyframe (B = 1, kf_vo.py's per-frame call): ms per solve",
+        "step_hbm_frac": bytes_step / (ms / K * 1e-3) / 1e9 / peak,
+        "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+                     "kernel": f"uic_queue_kernel<true,false,false,0,0,1>: the finest level (480x640) of {B} live frames, {ITERS} iterations in one launch",
+                     "algorithmic_bytes_per_launch": ITERS * bytes_lvl0, "launch_ms": launch_ms, "peak_source": peak_src,
+                     "note": "algorithmic bytes count the keyframe side once per pair (SURVEY 8d); it is shared by the 16 frames, so DRAM reads less",
+                     "how": "CUDA events on the launching stream around the call that launches it, separate pass"},
+        "parity": parity,
+        "e2e": {"value": world * B * K / (ms_e2e * 1e-3), "unit": "pairs/s", "h2d_bytes_per_step": streamer.h2d_bytes_per_step,
+                "d2h_bytes_per_step": streamer.d2h_bytes_per_step, "steps": K, "ms_per_step": ms_e2e / K,
+                "what": "pinned host live frames (x1 with 8 channels, one sigma map, inverse depth, K) -> device -> track against the "
+                        "resident keyframe -> poses in pinned memory, every step"},
+        "gpu_launches": (2 + 3 * ITERS + 4) * K,
+        "extra": {},
+    }
+
+
+def run_train(args, wl, rank, world, dev, barrier, max_over_ranks):
+    """BASELINE config 4: one data-parallel training step per batch of 64 pairs per GPU (train.py:117-192): the
+    reference's LeastSquareTracking with its tr_update0..3 swapped for the CUDA-backed solver (patch_tracker), the
+    CUDA pose-pyramid loss, backward, bucketed NCCL all-reduce of the gradients overlapped with the backward, gradient
+    clipping and the Adam step."""
+    import torch.distributed as dist
+    from deep_prob_feature_track_b200 import algorithms as A, criterions
+    from deep_prob_feature_track_b200.ddp import FlatBucketReducer, broadcast_parameters
+    from baseline import reference as REF
+    if not REF.available():
+        raise SystemExit("--workload train needs the reference's encoder: baseline/_ref is missing (python baseline/install_reference.py)")
+    B, H, W = wl["B"], wl["H"], wl["W"]
+    K = args.steps
+    main = torch.cuda.current_stream(dev)
+    torch.backends.cudnn.benchmark = True
+    net = A.patch_tracker(REF.make_tracker(REF.EVAL_TUM_FLAGS, seed=0)).to(dev).train()
+    broadcast_parameters(net)
+    reducer = FlatBucketReducer(net.parameters(), n_buckets=4)
+    opt = torch.optim.Adam(net.parameters(), lr=1e-5, weight_decay=4e-4)
+    batches = [REF.synthetic_rgbd(B, H, W, seed=50 + 10 * rank + i, device=dev) for i in range(2)]
+    R_gt = torch.eye(3, device=dev).repeat(B, 1, 1)
+    t_gt = torch.tensor([[0.01, -0.005, 0.002]], device=dev).repeat(B, 1)
+    parts = {}
+
+    def step(i, timed=False):
+        img0, img1, d0, d1, Kc = batches[i % 2]
+        reducer.zero_grad()
+        if timed:
+            marks = [torch.cuda.Event(enable_timing=True) for _ in range(5)]
+            marks[0].record(main)
+        Rs, ts = net(img0, img1, d0, d1, Kc)
+        loss = criterions.compute_RT_EPE_loss(Rs, ts, R_gt, t_gt, d0, Kc, invalid=(d0 == d0.min()) | (d0 == d0.max())).mean() * 1e2
+        if timed:
+            marks[1].record(main)
+        loss.backward()
+        if timed:
+            marks[2].record(main)
+        reducer.finish()
+        if timed:
+            marks[3].record(main)
+        torch.nn.utils.clip_grad_norm_(net.parameters(), 5.0)
+        opt.step()
+        if timed:
+            marks[4].record(main)
+            torch.cuda.synchronize()
+            for name, a, b in (("forward_loss_ms", 0, 1), ("backward_ms", 1, 2), ("allreduce_wait_ms", 2, 3), ("clip_adam_ms", 3, 4)):
+                parts.setdefault(name, []).append(marks[a].elapsed_time(marks[b]))
+        return loss
+
+    for i in range(max(3, args.warmup)):
+        step(i)
     torch.cuda.synchronize()
-    ms_kf = e0.elapsed_time(e1) / n
-    out["keyframe_mode"] = {"what": f"{B} live frames per call against one resident keyframe, B=1 semantics per frame",
-                            "ms_per_step": ms_kf, "pairs_per_s": B / (ms_kf * 1e-3)}
-    return out
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(main)
+    for i in range(K):
+        loss = step(i)
+    e1.record(main)
+    barrier()
+    ms = max_over_ranks(e0.elapsed_time(e1), dev)
+    loss_value = float(loss.item())
+    for i in range(5):
+        step(i, timed=True)
+    # the collective alone: one all-reduce of the whole flat gradient buffer
+    ar_ms = None
+    if world > 1:
+        for _ in range(3):
+            dist.all_reduce(reducer.flat)
+        torch.cuda.synchronize()
+        ar_ms = event_time_ms(lambda: [dist.all_reduce(reducer.flat) for _ in range(10)], main) / 10
+    return {
+        "value": world * B * K / (ms * 1e-3), "ms_per_step": ms / K,
+        "config": dict(base_config(wl), step="forward (reference FeaturePyramid + pose predictor on cuDNN, CUDA solver 4 levels x 3 iterations) "
+                       "+ compute_RT_EPE_loss (CUDA) + backward + bucketed all-reduce + clip_grad_norm + Adam",
+                       api="patch_tracker(LeastSquareTracking) + criterions.compute_RT_EPE_loss + ddp.FlatBucketReducer",
+                       gradient_bytes=reducer.nbytes, buckets=len(reducer.bounds), collective="NCCL all-reduce" if world > 1 else "none (1 rank)"),
+        "latency_ms": ms / K, "latency_note": "a training step IS the latency",
+        "step_hbm_frac": None,
+        "roofline": None,
+        "parity": {"against": "tests/test_reference_dropin_gpu.py (poses and encoder gradients of this step vs the unpatched reference on CUDA)"},
+        "e2e": None,
+        "gpu_launches": None,
+        "extra": {"step_parts_ms": {k: statistics.median(v) for k, v in parts.items()}, "loss": loss_value,
+                  "allreduce_alone_ms": ar_ms, "allreduce_bytes": reducer.nbytes,
+                  "note": "allreduce_wait_ms is what the step still waits for after backward: the buckets were started from "
+                          "autograd hooks while backward ran"},
+    }
+
+
+def measured_peak():
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        return float(peaks["hbm_gbs"]), "MEASURED_PEAKS.json hbm_gbs (measured copy bandwidth)"
+    except Exception:
+        return 6650.0, "fallback 6650 GB/s (B200_PROFILING.md)"
 
 
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=200)
-    ap.add_argument("--warmup", type=int, default=10)
+    ap.add_argument("--steps", type=int, default=64)
+    ap.add_argument("--warmup", type=int, default=8)
     ap.add_argument("--impl", default="ours", choices=("ours", "reference"))
     ap.add_argument("--workload", default="tum", choices=tuple(WORKLOADS))
+    ap.add_argument("--batches-per-call", type=int, default=20, help="batches stacked into one solver call (tum)")
+    ap.add_argument("--streams", type=int, default=2, help="CUDA streams the calls rotate over")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--no-pdl", action="store_true")
-    ap.add_argument("--materialised", action="store_true",
-                    help="materialise the unit Sobel gradients once per level instead of the fused sliding-window kernel")
-    ap.add_argument("--single-launch", action="store_true",
-                    help="all levels and iterations in ONE cooperative launch instead of one launch per iteration")
-    ap.add_argument("--no-staged", action="store_true", help="plain fused kernel instead of the staged-footprint one (DPFT_STAGED_FOOTPRINT off)")
-    ap.add_argument("--streams", type=int, default=8, help="CUDA streams the timed steps are spread over")
-    ap.add_argument("--no-extras", action="store_true", help="skip the training-step and 480x640 side measurements")
-    ap.add_argument("--no-graphs", action="store_true",
-                    help="issue every launch from the host instead of replaying one CUDA graph per solve")
+    ap.add_argument("--no-extras", action="store_true")
+    ap.add_argument("--no-parity", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
-    args.fused_sobel = not args.materialised
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     wl = WORKLOADS[args.workload]
-    B, C, H, W = wl["B"], wl["C"], wl["H"], wl["W"]
-    bytes_step, bytes_lvl0 = algorithmic_bytes(B, C, H, W)
 
-    from deep_prob_feature_track_b200.synthetic import make_frame_pairs
-
-    # ------------------------------------------------------------------ reference arm: CPU port, rank 0 only
     if args.impl == "reference":
-        if rank != 0:
-            return
-        n_cpu = min(B, 16 if args.workload == "tum" else 1)
-        data = make_frame_pairs(n_cpu, C, H, W, seed=1234, n_levels=N_LEVELS)
-        from oracle import ic_oracle as O
-        threads = os.cpu_count() or 1
-        torch.set_num_threads(threads)
-
-        def step():
-            with torch.no_grad():
-                O.track_pyramid(data["levels"], (data["R0"], data["t0"]), iters=ITERS, remove_tru_sigma=True,
-                                sampler="grid_sample", reduction="bmm")
-
-        for _ in range(args.warmup):
-            step()
-        t = time.perf_counter()
-        for _ in range(args.steps):
-            step()
-        dt = time.perf_counter() - t
-        v = n_cpu * args.steps / dt
-        sample = f"{n_cpu} of the {B} pairs of a step, {args.steps} steps after {args.warmup} warm-up"
-        print(json.dumps({
-            "impl": "reference", "metric": "frame-pair GN solves/sec", "value": v, "unit": "pairs/s",
-            "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3,
-            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": wl["name"], "levels": N_LEVELS, "iters_per_level": ITERS, "variant": "U_IC",
-                       "remove_tru_sigma": True},
-            "cpu_baseline": {"value": v, "unit": "pairs/s", "cores": threads, "kind": "port", "sample": sample},
-            "e2e": {"value": v, "unit": "pairs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-            "gpu_launches": 0,
-        }))
+        if rank == 0:
+            reference_arm(args, wl)
         return
 
-    # ------------------------------------------------------------------ our arm
     if not torch.cuda.is_available():
         raise SystemExit("bench.py --impl ours needs a CUDA device (no CPU fallback exists)")
+    from deep_prob_feature_track_b200.batched import bind_to_gpu_numa_node
+    numa_cpus = bind_to_gpu_numa_node(local_rank)     # before any pinned allocation: first touch on the GPU's node
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=dev)
-    from deep_prob_feature_track_b200 import algorithms as A
     from deep_prob_feature_track_b200.sharding import max_over_ranks
-    from deep_prob_feature_track_b200.streaming import StreamingSolver, pack_levels, views
-
-    data = make_frame_pairs(B, C, H, W, seed=1234 + rank, n_levels=N_LEVELS)
-    host_flat, layout = pack_levels(data["levels"], pin=True)
-    dev_sets = []
-    for s in range(N_SETS):
-        # distinct allocations (distinct addresses) with the batch rolled by s: L2 can not serve step k+1 from step k
-        rolled = [{k: torch.roll(v, s, 0) for k, v in lv.items()} for lv in data["levels"]]
-        f, _ = pack_levels(rolled, pin=False)
-        dev_sets.append(views(f.to(dev), layout, N_LEVELS))
-    pose0 = (data["R0"].to(dev), data["t0"].to(dev))
-    set_bytes = host_flat.numel() * 4
-
-    def solve(levels, **kw):
-        return A.uic_solve(levels, pose0, iters=ITERS, remove_tru_sigma=True, pdl=not args.no_pdl, fused_sobel=args.fused_sobel,
-                           single_launch=args.single_launch, staged_footprint=not args.no_staged, **kw)
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
-    # init + sigma0 min/max per level, then either ONE cooperative launch for all 12 iterations (+ its init) or
-    # one launch per iteration (+ 2 Sobel launches per level when gradients are materialised)
-    single = args.fused_sobel and args.single_launch
-    launches_per_step = 1 + N_LEVELS + (2 if single else N_LEVELS * ITERS + (0 if args.fused_sobel else 2 * N_LEVELS))
-
     with ClockSampler(local_rank) as clocks:
-        # ---- value: inputs resident in HBM.  Batches are independent, so consecutive steps are issued round-robin
-        # on `--streams` CUDA streams: the latency-bound coarse levels of one batch overlap the bandwidth-heavy
-        # finest level of another.  Timed with events on the launching (default) stream, which every worker
-        # stream waits for at the start and which waits for every worker stream at the end.
-        main_stream = torch.cuda.current_stream(dev)
-        workers = [torch.cuda.Stream(device=dev) for _ in range(max(1, args.streams))]
+        body = {"tum": run_tum, "vga": run_vga, "train": run_train}[args.workload](args, wl, rank, world, dev, barrier, max_over_ranks)
 
-        # One solve is 17 launches (~0.18 ms of host time) for ~0.3 ms of device time; with several ranks on one host
-        # the issue rate, not the GPU, set the pace (4 GPUs: 0.56 ms per step).  So a solve is captured ONCE per
-        # (worker stream, input set) into a CUDA graph -- same C-ABI call, same launches, PDL edges included -- and the
-        # timed steps replay the graphs.  --no-graphs restores host-issued launches; a failed capture falls back to them.
-        graphs = {}
-        if not args.no_graphs and not args.single_launch:
-            try:
-                combos = sorted({(i % len(workers), i % N_SETS) for i in range(len(workers) * N_SETS)})
-                for w, k in combos:
-                    with torch.cuda.stream(workers[w]):
-                        solve(dev_sets[k])                      # scratch pools, function attributes
-                torch.cuda.synchronize()
-                for w, k in combos:
-                    g = torch.cuda.CUDAGraph()
-                    with torch.cuda.graph(g, stream=workers[w]):
-                        out = solve(dev_sets[k])
-                    graphs[(w, k)] = (g, out)
-                torch.cuda.synchronize()
-            except Exception as exc:   # pragma: no cover - depends on the driver
-                print(f"[bench] CUDA graph capture failed ({exc!r}); issuing launches from the host", file=sys.stderr)
-                graphs = {}
-                torch.cuda.synchronize()
-
-        def run_steps(n):
-            last = None
-            for i in range(n):
-                w, k = i % len(workers), i % N_SETS
-                with torch.cuda.stream(workers[w]):
-                    if graphs:
-                        graphs[(w, k)][0].replay()
-                        last = graphs[(w, k)][1]
-                    else:
-                        last = solve(dev_sets[k])
-            return last
-
-        def timed(n):
-            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            e0.record(main_stream)
-            for w in workers:
-                w.wait_event(e0)
-            out = run_steps(n)
-            for w in workers:
-                done = torch.cuda.Event()
-                done.record(w)
-                main_stream.wait_event(done)
-            e1.record(main_stream)
-            return out, e0, e1
-
-        use_graphs = bool(graphs)
-        res, _, _ = timed(args.warmup)
-        res.raise_if_bad()
-        barrier()
-        res, e0, e1 = timed(args.steps)
-        barrier()
-        ms = e0.elapsed_time(e1)
-        res.raise_if_bad()
-        ms = max_over_ranks(ms, dev)
-
-        # ---- roofline: device time of every GN launch (events around each launch; separate pass)
-        lvl0 = []
-        per_launch = None
-        for i in range(max(3, min(args.steps, 20))):
-            r = solve(dev_sets[i % N_SETS], timed=True)
-            lvl0 += r.launch_ms[-ITERS:]
-            per_launch = r.launch_ms if per_launch is None else [a + b for a, b in zip(per_launch, r.launch_ms)]
-        n_timed = max(3, min(args.steps, 20))
-        per_launch = [x / n_timed for x in per_launch]
-        lvl0_ms = sum(lvl0) / len(lvl0)
-
-        # ---- e2e: host buffers in, poses out, every step.  Two device buffers and a copy stream: the upload of
-        # step k+1 runs while step k is solved (the upload is ~5x the solve, so the link sets the pace); every
-        # step still uploads all of its inputs from pinned memory and reads its poses back.
-        streamer = StreamingSolver(layout, host_flat.numel(), N_LEVELS, B, dev, solve)
-
-        def e2e_run(n):
-            streamer.run([host_flat] * n)
-
-        n_e2e = max(3, min(args.steps, 30))
-        e2e_run(3)
-        barrier()
-        e0.record()
-        e2e_run(n_e2e)
-        e1.record()
-        barrier()
-        ms_e2e = e0.elapsed_time(e1)
-        ms_e2e = max_over_ranks(ms_e2e, dev)
-
-        # ---- side measurements (not the headline): training step of the same workload, 480x640 pairs
-        extras = {}
-        if not args.no_extras:
-            # the same workload with the uncertainty passed as the ONE map per frame the reference's encoder emits
-            # (it repeats it to C channels, alg:1425-1427; the headline above moves and reads the repeated tensors)
-            one_sets = [[dict(lv, s0=lv["s0"][:, :1].contiguous(), s1=lv["s1"][:, :1].contiguous()) for lv in st]
-                        for st in dev_sets]
-
-            def run_one(n):
-                for i in range(n):
-                    with torch.cuda.stream(workers[i % len(workers)]):
-                        solve(one_sets[i % N_SETS])
-
-            e0.record(main_stream)
-            for w in workers:
-                w.wait_event(e0)
-            run_one(args.warmup)
-            torch.cuda.synchronize()
-            e0.record(main_stream)
-            for w in workers:
-                w.wait_event(e0)
-            run_one(args.steps)
-            for w in workers:
-                done = torch.cuda.Event()
-                done.record(w)
-                main_stream.wait_event(done)
-            e1.record(main_stream)
-            torch.cuda.synchronize()
-            ms_one = e0.elapsed_time(e1) / args.steps
-            r = solve(one_sets[0], timed=True)
-            lvl0_one = sum(r.launch_ms[-ITERS:]) / ITERS
-            bytes_lvl0_one = (2 * C + 4) * 4 * H * W * B
-            extras["single_sigma_map"] = {
-                "what": "sigma0 / sigma1 given as (B,1,h,w) instead of repeated to C channels (DPFT_SIGMA_BROADCAST); "
-                        "same results", "ms_per_step": ms_one, "pairs_per_s": B / (ms_one * 1e-3),
-                "lvl0_launch_ms": lvl0_one, "lvl0_bytes_read_per_launch": bytes_lvl0_one,
-                "lvl0_GBps_of_bytes_read": bytes_lvl0_one / (lvl0_one * 1e-3) / 1e9}
-            del one_sets
-            extras["train_step"] = train_step_leg(A, dev_sets, pose0, B, max(3, min(args.steps, 20)), dev)
-            if args.workload == "tum":
-                del streamer
-                extras["vga480x640"] = vga_leg(A, rank, dev, args)
-
-    if rank != 0:
-        if world > 1:
-            dist.destroy_process_group()
-        return
-
-    peaks = {}
-    try:
-        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
-    except Exception:
-        pass
-    peak = float(peaks.get("hbm_gbs", 6650.0))
-    peak_src = "MEASURED_PEAKS.json hbm_gbs (measured copy bandwidth)" if peaks else "fallback 6650 GB/s"
-    achieved = bytes_lvl0 / (lvl0_ms * 1e-3) / 1e9
-    value = world * B * args.steps / (ms * 1e-3)
-    out = {
-        "metric": "frame-pair GN solves/sec", "value": value, "unit": "pairs/s", "n_gpus": world,
-        "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps,
-        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": wl["name"], "pairs_per_gpu_per_step": B, "feature_channels": C,
-                   "resolution": f"{H}x{W}", "levels": N_LEVELS, "iters_per_level": ITERS, "variant": "U_IC",
-                   "remove_tru_sigma": True, "pdl": not args.no_pdl, "streams": max(1, args.streams),
-                   "sobel": "fused" if args.fused_sobel else "materialised once per level",
-                   "lookups": "plain loads" if (args.no_staged or not args.fused_sobel) else "footprint staged in shared memory (cp.async ring)",
-                   "launch": "single cooperative launch for all levels and iterations" if single else
-                             ("one launch per iteration, each solve replayed from a CUDA graph" if use_graphs else "one launch per iteration"),
-                   "l2": f"inputs rotate over {N_SETS} resident sets of {set_bytes / 1e6:.0f} MB each (> 126 MB L2)",
-                   "algorithmic_bytes_per_step": bytes_step},
-        "step_hbm_frac": bytes_step / (ms / args.steps * 1e-3) / 1e9 / peak,
-        "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                     "traffic": (328.3e6 if not args.fused_sobel else 184.0e6 if args.no_staged else 187.6e6)
-                     if args.workload == "tum" else None,
-                     "traffic_source": "ncu --set full dram__bytes_read+write per launch: profiles/r1h_uic_iter_staged_kernel_level0.txt "
-                                       "(staged, default) / r1_uic_iter_kernel_level0.txt (--no-staged) / r1c_* (--materialised)",
-                     "kernel": ("uic_iter_px_kernel<8,true>" if not args.fused_sobel else "uic_iter_kernel<8,true>" if args.no_staged
-                                else "uic_iter_staged_kernel<true,false,160,120,false>") + " at the finest level",
-                     "algorithmic_bytes_per_launch": bytes_lvl0, "launch_ms": lvl0_ms,
-                     "all_launch_ms": [round(x, 4) for x in per_launch], "peak_source": peak_src,
-                     "how": ("%globaltimer stamps at the iteration boundaries inside the single cooperative launch"
-                             if single else "CUDA events around every launch") + " (dpft_uic_forward_timed), separate pass after the timed region"},
-        "e2e": {"value": world * B * n_e2e / (ms_e2e * 1e-3), "unit": "pairs/s", "h2d_bytes_per_step": set_bytes,
-                "d2h_bytes_per_step": B * 12 * 4, "steps": n_e2e, "ms_per_step": ms_e2e / n_e2e},
-        "gpu_launches": launches_per_step * args.steps,
-        "clocks": clocks.summary(),
-        "extra": extras,
-    }
-    if not args.no_cpu_baseline:
-        n_cpu = min(B, 16 if args.workload == "tum" else 1)
-        v, threads, times = cpu_sample(data["levels"], data["R0"], data["t0"], n_cpu)
-        out["cpu_baseline"] = {"value": v, "unit": "pairs/s", "cores": threads, "kind": "port",
-                               "sample": f"first {n_cpu} pairs of the step's batch, best of {len(times)} runs "
-                                         f"({sum(times):.1f} s of CPU work)"}
-    print(json.dumps(out))
+    if rank == 0:
+        out = {"metric": "frame-pair GN solves/sec", "value": body.pop("value"), "unit": "pairs/s", "n_gpus": world,
+               "steps": args.steps, "warmup": args.warmup, "ms_per_step": body.pop("ms_per_step"), "higher_is_better": True,
+               "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic"}
+        out.update(body)
+        out["clocks"] = clocks.summary()
+        out["numa"] = {"cpus_bound": numa_cpus}
+        if not args.no_cpu_baseline:
+            out["cpu_baseline"] = cpu_sample(wl, args.workload, 1234)
+        print(json.dumps(out))
     if world > 1:
         dist.destroy_process_group()
 

@@ -65,6 +65,7 @@ class DpftUicOptions(ctypes.Structure):
         ("tiling", ctypes.c_int32),
         ("generic_geometry", ctypes.c_int32),
         ("launch_ms", ctypes.POINTER(ctypes.c_float)),
+        ("queue_kernel_ms", ctypes.POINTER(ctypes.c_float)),
     ]
 
     def __init__(self, **kw):

@@ -68,12 +68,13 @@ def unpack_system(sys_rows: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
 
 class SolveResult:
     """What one call into the library hands back (all device tensors, nothing synchronised)."""
-    __slots__ = ("pose_hist", "sys_hist", "aux_hist", "status", "occ", "n_levels", "iters", "launch_ms")
+    __slots__ = ("pose_hist", "sys_hist", "aux_hist", "status", "occ", "n_levels", "iters", "launch_ms", "queue_kernel_ms")
 
-    def __init__(self, pose_hist, sys_hist, aux_hist, status, occ, n_levels, iters, launch_ms=None):
+    def __init__(self, pose_hist, sys_hist, aux_hist, status, occ, n_levels, iters, launch_ms=None, queue_kernel_ms=None):
         self.pose_hist, self.sys_hist, self.aux_hist = pose_hist, sys_hist, aux_hist
         self.status, self.occ = status, occ
         self.n_levels, self.iters, self.launch_ms = n_levels, iters, launch_ms
+        self.queue_kernel_ms = queue_kernel_ms     # timed=True on the work-queue path: event time of each queue kernel alone
 
     @property
     def pose(self) -> Pose:
@@ -194,8 +195,11 @@ def uic_solve(levels: Sequence[Dict[str, torch.Tensor]], pose: Pose, *, iters: i
     buf = (ctypes.c_float * max(n_it, 1))() if timed else None
     opt = _lib.DpftUicOptions(group=eff_group, tile_rows=tile_rows, queue_ctas=queue_ctas, queue_levels=queue_levels,
                               **(tuning or {}))
+    qbuf = (ctypes.c_float * max(1, queue_levels))() if (timed and use_queue) else None
     if timed:   # measurement aid (bench.py): per-iteration device times, synchronises the stream
         opt.launch_ms = ctypes.cast(buf, ctypes.POINTER(ctypes.c_float))
+        if qbuf is not None:
+            opt.queue_kernel_ms = ctypes.cast(qbuf, ctypes.POINTER(ctypes.c_float))
     ws_bytes = L.dpft_uic_workspace_bytes_ex(arr, n_levels, B, C, iters, flags, ctypes.byref(opt))
     if ws_bytes == 0:
         raise RuntimeError("dpft_uic_workspace_bytes: " + L.dpft_last_error().decode())
@@ -208,7 +212,8 @@ def uic_solve(levels: Sequence[Dict[str, torch.Tensor]], pose: Pose, *, iters: i
     _lib.check(code, "dpft_uic_forward")
     launch_ms = list(buf) if timed else None
     del keep   # launches are queued on the allocating stream; the caching allocator orders reuse after them
-    return SolveResult(pose_hist, sys_hist[:n_it], aux_hist[:n_it], status, occ, n_levels, iters, launch_ms)
+    return SolveResult(pose_hist, sys_hist[:n_it], aux_hist[:n_it], status, occ, n_levels, iters, launch_ms,
+                       list(qbuf) if qbuf is not None else None)
 
 
 def depth_pyramids(depth: torch.Tensor, n_levels: int = 4, with_depth: bool = False):

@@ -75,8 +75,9 @@ struct QueueParams {
   unsigned long long* t_done;        // optional (iters + 1) %globaltimer stamps: start, then every iteration complete
 };
 int queue_tiles_per_sm();            // resident workers (warps) per SM
+// ev0 / ev1 (optional): events recorded on `stream` right before / after the work-queue kernel itself
 cudaError_t launch_queue(const QueueParams& prm, const float* pose_in, bool tru, int grid, cudaStream_t stream,
-                         bool allow_fixed_geometry);
+                         bool allow_fixed_geometry, cudaEvent_t ev0 = nullptr, cudaEvent_t ev1 = nullptr);
 // order-encoded [min, max] of v[l][g * per_group[l] .. (g + 1) * per_group[l]) into mm[(l * n_groups + g) * 2 ..]
 // (atomicMin / atomicMax: mm must hold 0xffffffff, 0 on entry)
 void launch_minmax_levels(const float* const* v, const size_t* per_group, int n_levels, int n_groups, uint32_t* mm,

@@ -782,6 +782,7 @@ struct Tuning {
   int tiling = 0;                         // 0 dealt, 1 rectangular, 2 linear
   bool generic_geometry = false;
   float* launch_ms = nullptr;
+  float* queue_kernel_ms = nullptr;
 };
 
 static Tuning tuning_of(const dpft_uic_options_t* o) {
@@ -795,6 +796,7 @@ static Tuning tuning_of(const dpft_uic_options_t* o) {
   t.tiling = o->tiling;
   t.generic_geometry = o->generic_geometry != 0;
   t.launch_ms = o->launch_ms;
+  t.queue_kernel_ms = o->launch_ms ? o->queue_kernel_ms : nullptr;
   return t;
 }
 
@@ -1185,9 +1187,10 @@ static int device_sms() {
 }
 
 // Rows per tile of the queue path.  Workers are warps; an iteration of the level offers B * nseg * ceil(H / TR) tiles.
-// A tile costs its rows plus ~2 rows of fixed work (claim, pose, window and ring priming, record, counters).  With
-// several waves of tiles per iteration the pairs drift apart and only the fixed work counts, so tall tiles win; with
-// a wave or two the last tile of a pair IS its iteration, so the count of waves counts.
+// A tile costs its rows plus ~3.5 rows of fixed work (claim, pose, window and ring priming, record, counters; measured:
+// 40-row tiles beat 30-row ones by 2 % at 8 batches of 64 pairs, profiles/r2/).  With several waves of tiles per
+// iteration the pairs drift apart and only the fixed work counts, so tall tiles win; with a wave or two the last tile
+// of a pair IS its iteration, so the count of waves counts.
 static int queue_tile_rows(int H, int nseg, int B, long workers) {
   int best_tr = 1;
   double best = 1e30;
@@ -1197,7 +1200,7 @@ static int queue_tile_rows(int H, int nseg, int B, long workers) {
     const long tiles = nrt * nseg * B;
     const double waves = (double)tiles / (double)workers;
     const double quant = waves >= 3.0 ? waves + 0.5 : (double)((tiles + workers - 1) / workers);
-    const double cost = quant * (tr_eff + 2.0);
+    const double cost = quant * (tr_eff + 3.5);
     if (cost < best - 1e-9) { best = cost; best_tr = tr_eff; }
   }
   return best_tr;
@@ -1262,7 +1265,8 @@ static QPlan make_qplan(const dpft_level_t& lv, int level_index, int B, int C, i
 // pose_hist (the coarser levels already left the level's starting pose there).  launch_ms (host, iters) optional.
 static int run_queue(const dpft_level_t& L, int level_index, int B, int C, int iters, uint32_t flags, const float* pose_in,
                      float* pose_hist, float* sys_hist, float* aux_hist, int32_t* status, void* workspace,
-                     size_t workspace_bytes, cudaStream_t stream, const Tuning& tun, float* launch_ms) {
+                     size_t workspace_bytes, cudaStream_t stream, const Tuning& tun, float* launch_ms,
+                     const uint32_t* s0mm_ready /* this level's sigma0 extremes if already computed */, float* kernel_ms) {
   const QPlan q = make_qplan(L, level_index, B, C, iters, flags, tun);
   const Groups G = groups_of(B, flags, tun);
   if (workspace_bytes < q.total) return set_error(DPFT_ENOSPACE, "workspace has %zu bytes, %zu needed", workspace_bytes, q.total);
@@ -1291,11 +1295,11 @@ static int run_queue(const dpft_level_t& L, int level_index, int B, int C, int i
   prm.groups_done = (int*)(ws + q.off_groups_done);
   prm.gext = (uint32_t*)(ws + q.off_gext);
   uint32_t* mm = (uint32_t*)(ws + q.off_mm);
-  prm.s0mm = mm;
+  prm.s0mm = s0mm_ready ? s0mm_ready : mm;
   prm.status = status;
   prm.t_done = launch_ms ? (unsigned long long*)(ws + q.off_tdone) : nullptr;
   const bool tru = flags & DPFT_REMOVE_TRU_SIGMA;
-  if (tru) {
+  if (tru && !s0mm_ready) {
     init_kernel<<<1, 256, 0, stream>>>(nullptr, nullptr, 0, nullptr, 0, mm, std::min(G.n_mm_groups, 256));
     if (G.n_mm_groups > 256) init_kernel<<<(G.n_mm_groups + 255) / 256, 256, 0, stream>>>(nullptr, nullptr, 0, nullptr, 0, mm, G.n_mm_groups);
     const float* src[1] = {L.sigma0};
@@ -1303,8 +1307,20 @@ static int run_queue(const dpft_level_t& L, int level_index, int B, int C, int i
     const size_t per_group[1] = {G.n_mm_groups > 1 ? per_pair * G.group : per_pair * (prm.kf_shared ? 1 : B)};
     launch_minmax_levels(src, per_group, 1, G.n_mm_groups, mm, stream);
   }
-  cudaError_t err = launch_queue(prm, pose_in, tru, q.grid, stream, !tun.generic_geometry);
+  cudaEvent_t ev[2] = {nullptr, nullptr};
+  if (kernel_ms) {
+    cudaEventCreate(&ev[0]);
+    cudaEventCreate(&ev[1]);
+  }
+  cudaError_t err = launch_queue(prm, pose_in, tru, q.grid, stream, !tun.generic_geometry, ev[0], ev[1]);
   if (err != cudaSuccess) return set_error((int)err, "work-queue launch: %s", cudaGetErrorString(err));
+  if (kernel_ms) {
+    err = cudaEventSynchronize(ev[1]);
+    if (err == cudaSuccess) err = cudaEventElapsedTime(kernel_ms, ev[0], ev[1]);
+    cudaEventDestroy(ev[0]);
+    cudaEventDestroy(ev[1]);
+    if (err != cudaSuccess) return set_error((int)err, "kernel timing: %s", cudaGetErrorString(err));
+  }
   if (launch_ms) {
     unsigned long long stamps[64 + 1];
     err = cudaMemcpyAsync(stamps, prm.t_done, (iters + 1) * sizeof(unsigned long long), cudaMemcpyDeviceToHost, stream);
@@ -1345,10 +1361,14 @@ extern "C" size_t dpft_uic_workspace_bytes(const dpft_level_t* levels, int n_lev
 }
 
 // Launch-per-iteration kernels (or the single cooperative launch) over `n_levels` levels; arguments already checked.
+// `n_mm_levels` >= n_levels: levels whose sigma0 extremes are computed here (the ones past n_levels belong to work-queue
+// launches that follow; `mm_out` receives where they are).
 static int run_lpi(const dpft_level_t* levels, int n_levels, int B, int C, int iters, uint32_t flags,
                    float w_icp, const float* pose_in, float* pose_hist, float* sys_hist, float* aux_hist,
                    int32_t* status, void* workspace, size_t workspace_bytes, void* stream_, cudaEvent_t* ev,
-                   unsigned long long* clock_host, const Tuning& tun) {
+                   unsigned long long* clock_host, const Tuning& tun, int n_mm_levels = 0,
+                   const uint32_t** mm_out = nullptr) {
+  n_mm_levels = std::max(n_mm_levels, n_levels);
   bool any_occ = false;
   for (int l = 0; l < n_levels; ++l) any_occ = any_occ || levels[l].occ_out;
   const Groups G = groups_of(B, flags, tun);
@@ -1377,8 +1397,9 @@ static int run_lpi(const dpft_level_t* levels, int n_levels, int B, int C, int i
   float* icp_rec = (float*)(ws + pl.off_icp);
   uint32_t* dmm = (uint32_t*)(ws + pl.off_dmm);
 
+  if (mm_out) *mm_out = mm;
   {
-    const int n_mm = n_levels * G.n_mm_groups;
+    const int n_mm = n_mm_levels * G.n_mm_groups;
     const int n = std::max(std::max(B * 12, B + G.n_groups), n_mm);
     init_kernel<<<(n + 255) / 256, 256, 0, stream>>>(pose_in, pose_hist, pose_in == pose_hist ? 0 : B * 12, counters,
                                                      B + G.n_groups, mm, n_mm);
@@ -1390,12 +1411,12 @@ static int run_lpi(const dpft_level_t* levels, int n_levels, int B, int C, int i
     // extremes of sigma0 per level and group, all levels in one launch
     const float* src[DPFT_MAX_LEVELS];
     size_t per_group[DPFT_MAX_LEVELS];
-    for (int l = 0; l < n_levels; ++l) {
+    for (int l = 0; l < n_mm_levels; ++l) {
       const size_t per_pair = (size_t)SC * levels[l].H * levels[l].W;
       src[l] = levels[l].sigma0;
       per_group[l] = G.n_mm_groups > 1 ? per_pair * G.group : per_pair * (shared_kf ? 1 : B);
     }
-    launch_minmax_levels(src, per_group, n_levels, G.n_mm_groups, mm, stream);
+    launch_minmax_levels(src, per_group, n_mm_levels, G.n_mm_groups, mm, stream);
   }
   if (persist) {
     PersistParams pp{};
@@ -1507,7 +1528,8 @@ static int run_lpi(const dpft_level_t* levels, int n_levels, int B, int C, int i
 // launch-per-iteration levels with the device time of every iteration (events, or stamps of the cooperative launch)
 static int lpi_timed(const dpft_level_t* levels, int n_levels, int B, int C, int iters, uint32_t flags, float w_icp,
                      const float* pose_in, float* pose_hist, float* sys_hist, float* aux_hist, int32_t* status,
-                     void* workspace, size_t workspace_bytes, void* stream, const Tuning& tun, float* launch_ms) {
+                     void* workspace, size_t workspace_bytes, void* stream, const Tuning& tun, float* launch_ms,
+                     int n_mm_levels = 0, const uint32_t** mm_out = nullptr) {
   const int n = n_levels * iters;
   bool any_occ = false;
   for (int l = 0; l < n_levels; ++l) any_occ = any_occ || levels[l].occ_out;
@@ -1516,14 +1538,14 @@ static int lpi_timed(const dpft_level_t* levels, int n_levels, int B, int C, int
     // single cooperative launch: iteration boundaries are stamped on the device with %globaltimer
     unsigned long long stamps[DPFT_MAX_LEVELS * 64 + 1];
     const int rc = run_lpi(levels, n_levels, B, C, iters, flags, w_icp, pose_in, pose_hist, sys_hist, aux_hist, status,
-                           workspace, workspace_bytes, stream, nullptr, stamps, tun);
+                           workspace, workspace_bytes, stream, nullptr, stamps, tun, n_mm_levels, mm_out);
     for (int i = 0; i < n && rc == 0; ++i) launch_ms[i] = (float)((double)(stamps[i + 1] - stamps[i]) * 1e-6);
     return rc;
   }
   cudaEvent_t ev[DPFT_MAX_LEVELS * 64 + 1];
   for (int i = 0; i <= n; ++i) cudaEventCreate(&ev[i]);
   int rc = run_lpi(levels, n_levels, B, C, iters, flags, w_icp, pose_in, pose_hist, sys_hist, aux_hist, status,
-                   workspace, workspace_bytes, stream, ev, nullptr, tun);
+                   workspace, workspace_bytes, stream, ev, nullptr, tun, n_mm_levels, mm_out);
   if (rc == 0) {
     const cudaError_t err = cudaStreamSynchronize((cudaStream_t)stream);
     if (err != cudaSuccess) rc = set_error((int)err, "sync: %s", cudaGetErrorString(err));
@@ -1562,19 +1584,24 @@ static int run_uic(const dpft_level_t* levels, int n_levels, int B, int C, int i
   for (int l = nc; l < n_levels; ++l) qbytes = std::max(qbytes, make_qplan(levels[l], l, B, C, iters, flags, tun).total);
   if (workspace_bytes < coarse_bytes + qbytes)
     return set_error(DPFT_ENOSPACE, "workspace has %zu bytes, %zu needed", workspace_bytes, coarse_bytes + qbytes);
+  // the coarse levels' launch computes the sigma0 extremes of EVERY level in its one reduction launch
+  const uint32_t* mm_all = nullptr;
   if (nc > 0) {
     const int rc = ms ? lpi_timed(levels, nc, B, C, iters, flags, w_icp, pose_in, pose_hist, sys_hist, aux_hist, status,
-                                  workspace, coarse_bytes, stream, tun, ms)
+                                  workspace, coarse_bytes, stream, tun, ms, n_levels, &mm_all)
                       : run_lpi(levels, nc, B, C, iters, flags, w_icp, pose_in, pose_hist, sys_hist, aux_hist, status,
-                                workspace, coarse_bytes, stream, nullptr, nullptr, tun);
+                                workspace, coarse_bytes, stream, nullptr, nullptr, tun, n_levels, &mm_all);
     if (rc) return rc;
   }
   for (int l = nc; l < n_levels; ++l) {
     const size_t k0 = (size_t)l * iters;
     float* ph = pose_hist + k0 * B * 12;
+    const bool tru = flags & DPFT_REMOVE_TRU_SIGMA;
     const int rc = run_queue(levels[l], l, B, C, iters, flags, l > 0 ? ph : pose_in, ph, sys_hist + k0 * B * 27,
                              aux_hist ? aux_hist + k0 * G.n_groups * 4 : nullptr, status, (char*)workspace + coarse_bytes,
-                             qbytes, (cudaStream_t)stream, tun, ms ? ms + k0 : nullptr);
+                             qbytes, (cudaStream_t)stream, tun, ms ? ms + k0 : nullptr,
+                             (tru && mm_all) ? mm_all + 2 * (size_t)l * G.n_mm_groups : nullptr,
+                             tun.queue_kernel_ms ? tun.queue_kernel_ms + (l - nc) : nullptr);
     if (rc) return rc;
   }
   return 0;

@@ -482,13 +482,15 @@ void launch_minmax_levels(const float* const* v, const size_t* per_group, int n_
 }
 
 template <bool TRU, bool SB, bool AUX, int GW, int GH, int KIND>
-static cudaError_t launch_q(const QueueParams& prm, int grid, cudaStream_t stream) {
+static cudaError_t launch_q(const QueueParams& prm, int grid, cudaStream_t stream, cudaEvent_t ev0, cudaEvent_t ev1) {
   constexpr int smem = kQW * kQAreaFloats * (int)sizeof(float);
   auto* fn = uic_queue_kernel<TRU, SB, AUX, GW, GH, KIND>;
   // (cudaFuncSetAttribute is per device and cheap: set it on every launch rather than caching per process)
   cudaError_t err = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
   if (err != cudaSuccess) return err;
+  if (ev0) cudaEventRecord(ev0, stream);
   fn<<<grid, kQThreads, smem, stream>>>(prm);
+  if (ev1) cudaEventRecord(ev1, stream);
   return cudaGetLastError();
 }
 
@@ -496,7 +498,7 @@ int queue_tiles_per_sm() { return kQCtasPerSm * kQW; }
 
 // `prm.s0mm` must already hold the level's sigma0 extremes (launch_minmax_levels); pose_in may be prm.pose_hist.
 cudaError_t launch_queue(const QueueParams& prm, const float* pose_in, bool tru, int grid, cudaStream_t stream,
-                         bool allow_fixed_geometry) {
+                         bool allow_fixed_geometry, cudaEvent_t ev0, cudaEvent_t ev1) {
   {
     const size_t n = std::max<size_t>(std::max<size_t>(prm.total_items, (size_t)prm.B * 12), (size_t)prm.iters * prm.n_groups);
     queue_init_kernel<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(prm, pose_in);
@@ -504,7 +506,7 @@ cudaError_t launch_queue(const QueueParams& prm, const float* pose_in, bool tru,
   const bool sb = prm.SC != prm.C;
   const bool aux = prm.L.m0 || prm.L.m1;
   const bool staged = prm.L.kind >= 1;
-#define DPFT_Q(TRUV, SBV, AUXV, w, h, KINDV) launch_q<TRUV, SBV, AUXV, w, h, KINDV>(prm, grid, stream)
+#define DPFT_Q(TRUV, SBV, AUXV, w, h, KINDV) launch_q<TRUV, SBV, AUXV, w, h, KINDV>(prm, grid, stream, ev0, ev1)
   if (!staged) {   // levels the staged routine does not take (narrow, unaligned): the plain tile routine
     if (tru) return aux ? DPFT_Q(true, false, true, 0, 0, 0) : DPFT_Q(true, false, false, 0, 0, 0);
     return aux ? DPFT_Q(false, false, true, 0, 0, 0) : DPFT_Q(false, false, false, 0, 0, 0);

@@ -37,7 +37,10 @@ static_assert(kStagedCols == 30 || kStagedCols == 32, "30 or 32 output columns p
 constexpr int kHaloFloats = kStagedCols == 32 ? 128 : 0;        // [row parity][side][16 maps: vs, vs, vd, vd per pair]
 constexpr int kStageWidth = DPFT_STAGE_WIDTH;      // texels per staged row segment (30 output columns + margin)
 constexpr int kStageMaps = 17;       // x1[0..7], sigma1[0..7], invd1
-constexpr int kStageLookahead = 2;   // source rows requested ahead of the row being computed
+#ifndef DPFT_STAGE_LOOKAHEAD
+#define DPFT_STAGE_LOOKAHEAD 2
+#endif
+constexpr int kStageLookahead = DPFT_STAGE_LOOKAHEAD;   // source rows requested ahead of the row being computed
 // slot stride = 0 mod 32 banks: lanes of one warp row that sit on different source rows (same map, distinct
 // columns) then never share a bank
 constexpr int kStageSlotFloats = (kStageMaps * kStageWidth + 31) / 32 * 32;
@@ -320,6 +323,10 @@ __device__ __forceinline__ void process_tile_staged(const PairView& g, const flo
   int top = -0x40000000, base = 0x40000000;
   float d0_next = (y0 < y1) ? __ldg(D0 + (unsigned)(y0 * W + xc)) : 0.f;
 
+#ifdef DPFT_HOIST_PX
+  // the lane's column is fixed for the whole tile: its three products with the first column of R are, too
+  const float rpx0 = xmul(spose[0], px), rpx1 = xmul(spose[3], px), rpx2 = xmul(spose[6], px);
+#endif
   for (int y = y0; y < y1; ++y) {
 #ifdef DPFT_DEBUG_STAMPS
     const long long ck0 = clock64();
@@ -345,9 +352,15 @@ __device__ __forceinline__ void process_tile_staged(const PairView& g, const flo
     float u, v, inv_z;
     {
       const float4 ra = lds_v4(spose), rb = lds_v4(spose + 4), rc = lds_v4(spose + 8);
+#ifdef DPFT_HOIST_PX
+      const float wx = xadd(xadd(xadd(rpx0, xmul(ra.y, py)), ra.z), xmul(rc.y, d0));
+      const float wy = xadd(xadd(xadd(rpx1, xmul(rb.x, py)), rb.y), xmul(rc.z, d0));
+      const float wz = xadd(xadd(xadd(rpx2, xmul(rb.w, py)), rc.x), xmul(rc.w, d0));
+#else
       const float wx = xadd(xadd(xadd(xmul(ra.x, px), xmul(ra.y, py)), ra.z), xmul(rc.y, d0));
       const float wy = xadd(xadd(xadd(xmul(ra.w, px), xmul(rb.x, py)), rb.y), xmul(rc.z, d0));
       const float wz = xadd(xadd(xadd(xmul(rb.z, px), xmul(rb.w, py)), rc.x), xmul(rc.w, d0));
+#endif
       const float rz = __frcp_rn(wz);
       u = xadd(xmul(div_by(wx, wz, rz), fx), cx);
       v = xadd(xmul(div_by(wy, wz, rz), fy), cy);
@@ -412,10 +425,12 @@ __device__ __forceinline__ void process_tile_staged(const PairView& g, const flo
     // first r1h capture).  Adding a zero that is only known after the ring logic turns each copy into an FADD that
     // cannot be scheduled before this point, by which time the loads have landed.
     const float late0 = (top == 0x7ffffff0) ? 1.f : 0.f;       // always 0.f (top is a row index), opaque to the compiler
+#ifndef DPFT_NO_LATE0
 #pragma unroll
     for (int p = 0; p < NP; ++p) { fb[p].x += late0; fb[p].y += late0; }
 #pragma unroll
     for (int p = 0; p < NSP; ++p) { sb[p].x += late0; if (!SB) sb[p].y += late0; }
+#endif
     const int lowest = max(base, top - (kStageRows - 1));
     const int s0i = txy.yi & (kStageRows - 1), s1i = (txy.yi + 1) & (kStageRows - 1);
     const int xs0 = slot_xs[s0i], xs1 = slot_xs[s1i];

@@ -114,6 +114,10 @@ typedef struct dpft_uic_options {
                              Gauss-Newton iteration (CUDA events around every launch, or %globaltimer stamps of the
                              iteration completions inside a single launch), WAITS for the stream and fills the array:
                              a measurement aid, not a way to run the solver.                                      */
+  float *queue_kernel_ms; /* HOST array (queue_levels entries, coarse level first) or NULL; only read together with
+                             launch_ms.  Receives the device time of each work-queue KERNEL alone: CUDA events recorded on
+                             `stream` right before and right after its launch (its helper launches -- queue init, sigma0
+                             extremes -- stay outside).                                                          */
 } dpft_uic_options_t;
 
 /* ABI version of the loaded library (== DPFT_ABI_VERSION). */

@@ -1,4 +1,5 @@
-"""Round 2 probe: S streams x calls of G batches each, persistent vs retiring queue workers."""
+"""Round 2 probe: S streams x calls of G batches each (stream_probe_items.txt is the log of the version that also
+tried queue workers that leave after 1 / 2 / 4 items: no gain, option removed)."""
 import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 import torch
@@ -43,7 +44,6 @@ def run(G, S, n_calls, **kw):
 
 for G in (2, 4, 8):
     for S in (1, 2, 3, 4):
-        for items in (0, 1, 2, 4):
-            for tr in (30, 40):
-                t = run(G, S, max(8, 48 // G), tile_rows=[0, 0, 0, tr])
-                print(f"G={G} streams={S} items/worker={items} tile_rows={tr}: {t:7.1f} us per batch", flush=True)
+        for tr in (30, 40):
+            t = run(G, S, max(8, 48 // G), tile_rows=[0, 0, 0, tr])
+            print(f"G={G} streams={S} tile_rows={tr}: {t:7.1f} us per batch", flush=True)

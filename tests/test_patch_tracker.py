@@ -64,3 +64,17 @@ def test_direct_solver_net_mirrors_the_reference_layout():
     assert A.DirectSolverNet("Direct-Nodamping").net is None
     with pytest.raises(NotImplementedError):
         A.DirectSolverNet("something-else")
+
+
+def test_real_reference_tracker_is_patched():
+    """The same swap on a LeastSquareTracking built by the reference's own constructor (baseline/_ref)."""
+    from baseline import reference as REF
+    if not REF.available():
+        pytest.skip("baseline/_ref not installed (python baseline/install_reference.py)")
+    net = REF.make_tracker()
+    before = set(net.state_dict().keys())
+    A.patch_tracker(net)
+    for i in range(4):
+        m = getattr(net, f"tr_update{i}")
+        assert isinstance(m, A.TrustRegionInverseWUncertainty) and m.remove_tru_sigma and m.max_iterations == 3
+    assert set(net.state_dict().keys()) == before
