@@ -24,6 +24,10 @@ EVAL_TUM_FLAGS = ["--encoder_name", "ConvRGBD2", "--mestimator", "None", "--solv
                   "--uncertainty", "laplacian", "--remove_tru_sigma", "--scaler", "None"]
 
 
+# scripts/train_tum_rgbd.sh: the same tracker with the learned initial pose (SFMPoseNet) trained jointly
+TRAIN_TUM_FLAGS = EVAL_TUM_FLAGS + ["--init_pose", "sfm_net", "--train_init_pose", "--multi_hypo", "prob_fuse"]
+
+
 def available() -> bool:
     return os.path.isdir(CODE)
 
@@ -34,6 +38,8 @@ def modules():
         raise RuntimeError("baseline/_ref is missing: run `python baseline/install_reference.py` in the build container")
     if CODE not in sys.path:
         sys.path.insert(0, CODE)
+    import warnings
+    warnings.filterwarnings("ignore", category=SyntaxWarning)     # 2019 docstrings with LaTeX backslashes
     alg = importlib.import_module("models.algorithms")
     geo = importlib.import_module("models.geometry")
     lst = importlib.import_module("models.LeastSquareTracking")

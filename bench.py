@@ -140,7 +140,7 @@ def cpu_reference_runner(wl, workload, seed):
             raise SystemExit("--workload train --impl reference needs baseline/_ref (python baseline/install_reference.py)")
         REF.modules()                         # puts baseline/_ref/code on the import path
         import models.criterions as crit
-        net = REF.make_tracker(REF.EVAL_TUM_FLAGS).train()
+        net = REF.make_tracker(REF.TRAIN_TUM_FLAGS).train()
         img0, img1, d0, d1, K = REF.synthetic_rgbd(n, H, W, seed=seed)
         R_gt = torch.eye(3).repeat(n, 1, 1)
         t_gt = torch.tensor([[0.01, -0.005, 0.002]]).repeat(n, 1)
@@ -601,7 +601,7 @@ def run_train(args, wl, rank, world, dev, barrier, max_over_ranks):
     K = args.steps
     main = torch.cuda.current_stream(dev)
     torch.backends.cudnn.benchmark = True
-    net = A.patch_tracker(REF.make_tracker(REF.EVAL_TUM_FLAGS, seed=0)).to(dev).train()
+    net = A.patch_tracker(REF.make_tracker(REF.TRAIN_TUM_FLAGS, seed=0)).to(dev).train()
     broadcast_parameters(net)
     reducer = FlatBucketReducer(net.parameters(), n_buckets=4)
     opt = torch.optim.Adam(net.parameters(), lr=1e-5, weight_decay=4e-4)
