@@ -18,7 +18,7 @@ REPO_DIR = os.path.dirname(PKG_DIR)
 CSRC = os.path.join(PKG_DIR, "csrc")
 # DPFT_LIB_PATH points at another build of the SAME library (tuning sweeps build several); nothing else is ever loaded
 LIB_PATH = os.environ.get("DPFT_LIB_PATH") or os.path.join(PKG_DIR, "libdpft.so")
-SOURCES = ["dpft_abi.cu", "uic_forward.cu", "uic_queue.cu", "uic_backward.cu", "icp_term.cu", "uic_residual.cu",
+SOURCES = ["dpft_abi.cu", "uic_forward.cu", "uic_queue.cu", "uic_backward.cu", "icp_term.cu", "uic_residual.cu", "context.cu",
            "ic_path.cu", "ic_backward.cu", "uic_persistent.cu", "preprocess.cu", "pose_loss.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "-Xcompiler", "-fPIC"]
@@ -65,6 +65,7 @@ class DpftUicOptions(ctypes.Structure):
         ("tiling", ctypes.c_int32),
         ("generic_geometry", ctypes.c_int32),
         ("launch_ms", ctypes.POINTER(ctypes.c_float)),
+        ("icp_weight", ctypes.c_void_p * DPFT_MAX_LEVELS),
         ("queue_kernel_ms", ctypes.POINTER(ctypes.c_float)),
     ]
 
@@ -74,6 +75,8 @@ class DpftUicOptions(ctypes.Structure):
         tile_rows = kw.pop("tile_rows", None)
         for i, v in enumerate(tile_rows or ()):
             self.tile_rows[i] = int(v)
+        for i, v in enumerate(kw.pop("icp_weight", None) or ()):
+            self.icp_weight[i] = v
         for k, v in kw.items():
             setattr(self, k, v)
 
@@ -208,6 +211,10 @@ def lib() -> ctypes.CDLL:
         fn = getattr(L, name)
         fn.restype = ctypes.c_int
         fn.argtypes = args
+    L.dpft_ic_context.restype = ctypes.c_int
+    L.dpft_ic_context.argtypes = [lp, ci, vp, vp, ci, ci, vp, vp, vp]
+    L.dpft_uic_icp_context.restype = ctypes.c_int
+    L.dpft_uic_icp_context.argtypes = [lp, ci, ci, ctypes.c_uint32, vp, vp, vp, vp, ctypes.c_size_t, vp]
     L.dpft_pose_epe_loss.restype = ctypes.c_int
     L.dpft_pose_epe_loss.argtypes = [vp] * 7 + [ci] * 4 + [vp, vp]
     L.dpft_pose_epe_loss_backward.restype = ctypes.c_int
@@ -225,7 +232,8 @@ def exported_symbols() -> List[str]:
     """Entry points include/dpft.h declares (kept in sync by tests/test_abi.py)."""
     return ["dpft_abi_version", "dpft_last_error", "dpft_uic_workspace_bytes", "dpft_uic_forward",
             "dpft_uic_workspace_bytes_ex", "dpft_uic_forward_ex", "dpft_uic_forward_timed", "dpft_uic_backward_workspace_bytes", "dpft_uic_backward",
-            "dpft_uic_residual_workspace_bytes", "dpft_uic_residual_loss", "dpft_ic_gradients", "dpft_ic_residual",
+            "dpft_uic_residual_workspace_bytes", "dpft_uic_residual_loss", "dpft_ic_context", "dpft_uic_icp_context",
+            "dpft_ic_gradients", "dpft_ic_residual",
             "dpft_ic_normal_matrix", "dpft_ic_rhs", "dpft_ic_update", "dpft_ic_gradients_backward",
             "dpft_ic_residual_backward", "dpft_ic_normal_matrix_backward", "dpft_ic_rhs_backward",
             "dpft_ic_update_backward", "dpft_preprocess_depth", "dpft_pose_epe_loss", "dpft_pose_epe_loss_backward"]

@@ -99,7 +99,7 @@ def uic_solve(levels: Sequence[Dict[str, torch.Tensor]], pose: Pose, *, iters: i
               shared_keyframe: bool = False, pairwise_extremes: bool = False,
               obj_mask0: Optional[Sequence] = None, obj_mask1: Optional[Sequence] = None,
               queue: Optional[bool] = None, group: int = 0, tile_rows: Optional[Sequence[int]] = None, queue_ctas: int = 0,
-              queue_levels: int = 0,
+              queue_levels: int = 0, icp_weight: Optional[Sequence[Optional[torch.Tensor]]] = None,
               tuning: Optional[Dict[str, int]] = None) -> SolveResult:
     """Coarse-to-fine U_IC solve of a batch of frame pairs on the current CUDA stream.
 
@@ -117,7 +117,8 @@ def uic_solve(levels: Sequence[Dict[str, torch.Tensor]], pose: Pose, *, iters: i
     and no ``want_occ``.  ``None`` (default) picks it when it pays: more than one group, or pairs that nothing
     couples, and at least two waves of tiles at the finest level.  ``queue_levels``: how many of the finest levels
     take that path (default 1).  ``tile_rows`` (per level, coarse first), ``queue_ctas`` and ``tuning`` (cta_slots,
-    tiling, generic_geometry) are measurement knobs.
+    tiling, generic_geometry) are measurement knobs.  ``icp_weight``: with ``combine_icp``, per level a (B,1,h,w) map
+    that scales the point-to-plane term pixel by pixel (a learned ScaleNet's output, alg:677-682) instead of ``w_icp``.
     """
     L = _lib.lib()
     n_levels = len(levels)
@@ -193,7 +194,17 @@ def uic_solve(levels: Sequence[Dict[str, torch.Tensor]], pose: Pose, *, iters: i
     aux_hist = torch.zeros(aux_shape, dtype=torch.float32, device=dev)
     status = torch.zeros((1,), dtype=torch.int32, device=dev)
     buf = (ctypes.c_float * max(n_it, 1))() if timed else None
+    wmaps = None
+    if icp_weight is not None:
+        if not combine_icp or len(icp_weight) != n_levels:
+            raise ValueError("icp_weight needs combine_icp and one entry per level")
+        wmaps = [None if w is None else _dev_f32(w, "icp_weight") for w in icp_weight]
+        for w, lv in zip(wmaps, levels):
+            if w is not None and w.numel() != B * int(lv["x0"].shape[2]) * int(lv["x0"].shape[3]):
+                raise ValueError("icp_weight maps must be (B,1,h,w)")
+        keep.append(wmaps)
     opt = _lib.DpftUicOptions(group=eff_group, tile_rows=tile_rows, queue_ctas=queue_ctas, queue_levels=queue_levels,
+                              icp_weight=None if wmaps is None else [None if w is None else w.data_ptr() for w in wmaps],
                               **(tuning or {}))
     qbuf = (ctypes.c_float * max(1, queue_levels))() if (timed and use_queue) else None
     if timed:   # measurement aid (bench.py): per-iteration device times, synchronises the stream
@@ -279,6 +290,32 @@ def uic_residual_loss(level: Dict[str, torch.Tensor], pose: Pose, *, remove_tru_
     _lib.check(code, "dpft_uic_residual_loss")
     del keep
     return loss
+
+
+def uic_icp_context(level: Dict[str, torch.Tensor], pose: Pose, *, remove_tru_sigma: bool = False, obj_mask0=None,
+                    obj_mask1=None) -> Tuple[torch.Tensor, torch.Tensor]:
+    """What a learned ScaleNet reads at the first iteration of a level (reference alg:677-680, 1535-1567):
+    ``icp_r`` (B,1,H,W), the point-to-plane residual with 1e-6 where its mask is set, and ``feat_norm`` (B,1,H,W) =
+    sqrt(sum_c wres_c^2) of the masked uncertainty-weighted feature residual -- written by the residual kernels, the
+    (B,C,H,W) residual map is never formed.  ``ScaleNet.compute_rtr`` of them gives exactly its two inputs."""
+    L = _lib.lib()
+    x0 = level["x0"]
+    B, C, H, W, dev = int(x0.shape[0]), int(x0.shape[1]), int(x0.shape[2]), int(x0.shape[3]), x0.device
+    level = dict(level, s0=level["s0"].expand(-1, C, -1, -1), s1=level["s1"].expand(-1, C, -1, -1))
+    arr, keep = _level_array([level], B, C, None if obj_mask0 is None else [obj_mask0],
+                             None if obj_mask1 is None else [obj_mask1], with_depth=True)
+    flags = (_lib.DPFT_REMOVE_TRU_SIGMA if remove_tru_sigma else 0) | _lib.DPFT_COMBINE_ICP
+    pose_in = pack_pose(pose).to(dev)
+    icp_r = torch.empty((B, 1, H, W), dtype=torch.float32, device=dev)
+    feat_norm = torch.empty((B, 1, H, W), dtype=torch.float32, device=dev)
+    ws_bytes = L.dpft_uic_residual_workspace_bytes(arr, B, C, flags)
+    ws = torch.empty((max(ws_bytes, 1),), dtype=torch.uint8, device=dev)
+    with torch.cuda.device(dev):
+        code = L.dpft_uic_icp_context(arr, B, C, flags, pose_in.data_ptr(), icp_r.data_ptr(), feat_norm.data_ptr(),
+                                      ws.data_ptr(), ws_bytes, torch.cuda.current_stream(dev).cuda_stream)
+    _lib.check(code, "dpft_uic_icp_context")
+    del keep
+    return icp_r, feat_norm
 
 
 class _UicSolveFn(torch.autograd.Function):
@@ -397,17 +434,40 @@ class TrustRegionInverseWUncertainty(nn.Module):
     def forward(self, pose10, x0, x1, invD0, invD1, K, sigma0, sigma1, wPrior=None, depth0=None, depth1=None,
                 vis_res=True, obj_mask0=None, obj_mask1=None):
         assert sigma0 is not None and sigma1 is not None
-        w_icp = self._icp_weight()
+        learned = self.combine_icp and self._learned_scaler()
+        w_icp = 0.01 if learned else self._icp_weight()
         if self.combine_icp:
             assert depth0 is not None and depth1 is not None
         if self.timers: self.timers.tic('trust-region level solve (fused CUDA)')
         lv = dict(x0=x0, x1=x1, s0=sigma0, s1=sigma1, invD0=invD0, invD1=invD1, K=K)
         weights = torch.ones((1, 1, 1, 1), dtype=x0.dtype, device=x0.device).expand(x0.shape)
+        needs_grad = torch.is_grad_enabled() and any(t.requires_grad for t in (x0, x1, sigma0, sigma1, pose10[0], pose10[1]))
         if self.combine_icp:
             lv.update(depth0=depth0, depth1=depth1)
             weights = torch.full((1, 1, 1, 1), w_icp, dtype=x0.dtype, device=x0.device).expand(
                 x0.shape[0], 1, x0.shape[2], x0.shape[3])
-        if torch.is_grad_enabled() and any(t.requires_grad for t in (x0, x1, sigma0, sigma1, pose10[0], pose10[1])):
+        if learned:
+            # A ScaleNet with a CNN (alg:1501-1568): evaluated once, at the level's first iteration, on the two residual
+            # maps; its (B,1,H,W) output scales the ICP term pixel by pixel.  The kernels write what it reads
+            # (uic_icp_context); the CNN itself stays the reference's module on cuDNN.
+            if needs_grad or any(p.requires_grad and torch.is_grad_enabled() for p in self.scale_func.parameters()):
+                raise NotImplementedError("training through a learned ICP scaler is not built (no script of the reference uses one)")
+            icp_r, feat_norm = uic_icp_context(lv, pose10, remove_tru_sigma=self.remove_tru_sigma, obj_mask0=obj_mask0,
+                                               obj_mask1=obj_mask1)
+            with torch.no_grad():
+                weights = self.scale_func(icp_r, feat_norm, wPrior).float().contiguous()
+            res = uic_solve([lv], pose10, iters=self.max_iterations, remove_tru_sigma=self.remove_tru_sigma,
+                            combine_icp=True, icp_weight=[weights],
+                            obj_mask0=None if obj_mask0 is None else [obj_mask0],
+                            obj_mask1=None if obj_mask1 is None else [obj_mask1])
+            if self.check_nan:
+                res.raise_if_bad()
+            if self.timers: self.timers.toc('trust-region level solve (fused CUDA)')
+            if self.uncer_prop:
+                A, _ = unpack_system(res.sys_hist[-1])
+                return res.pose, weights, A
+            return res.pose, weights
+        if needs_grad:
             # training: same kernels, recorded for autograd (backward = dpft_uic_backward)
             (R, t, A), = uic_track([lv], (pose10[0], pose10[1]), iters=self.max_iterations,
                                    remove_tru_sigma=self.remove_tru_sigma, combine_icp=self.combine_icp, w_icp=w_icp,
@@ -428,17 +488,14 @@ class TrustRegionInverseWUncertainty(nn.Module):
         return res.pose, weights
 
 
+    def _learned_scaler(self) -> bool:
+        return self.scale_func is not None and getattr(self.scale_func, "D", -1) > 0
+
     def _icp_weight(self) -> float:
-        """ScaleNet('None') is a constant (ones * scale, alg:1535,1563-1567); that is what every shipped
-        script uses.  A learned scaler would need the residual maps materialised for its CNN."""
-        if not self.combine_icp:
+        """ScaleNet('None') is a constant (ones * scale, alg:1535,1563-1567); that is what every shipped script uses."""
+        if not self.combine_icp or self.scale_func is None:
             return 0.01
-        sf = self.scale_func
-        if sf is None:
-            return 0.01
-        if getattr(sf, "D", -1) > 0:
-            raise NotImplementedError("learned ICP scalers (ScaleNet with a CNN) are not built (DESIGN.md)")
-        return float(getattr(sf, "scale", 0.01))
+        return float(getattr(self.scale_func, "scale", 0.01))
 
     def forward_residuals(self, pose10, x0, x1, invD0, invD1, K, sigma0, sigma1, wPrior=None, depth0=None,
                           depth1=None, vis_res=True, obj_mask0=None, obj_mask1=None):
@@ -447,6 +504,8 @@ class TrustRegionInverseWUncertainty(nn.Module):
         if self.combine_icp:
             assert depth0 is not None and depth1 is not None
             lv.update(depth0=depth0, depth1=depth1)
+        if self.combine_icp and self._learned_scaler():
+            raise NotImplementedError("forward_residuals with a learned ICP scaler is not built")
         return uic_residual_loss(lv, pose10, remove_tru_sigma=self.remove_tru_sigma, combine_icp=self.combine_icp,
                                  w_icp=self._icp_weight(), obj_mask0=obj_mask0, obj_mask1=obj_mask1)
 
@@ -480,8 +539,33 @@ class DirectSolverNet(nn.Module):
         else:
             raise NotImplementedError()
 
-    def forward(self, *args, **kwargs):
-        raise NotImplementedError("called through TrustRegionBase, which never materialises the dense Jacobian")
+    def forward(self, JtJ, Jt, weights, R, pose0, invD0, invD1, x0, x1, K, obj_mask1=None):
+        """Reference signature (alg:1604): ``JtJ (B,6,6)``, the dense ``Jt (B,6,C*H*W)``, ``weights`` and the residual
+        ``R (B,C,H,W)``, ``pose0 = [R, t]`` -> updated pose.  TrustRegionBase above never calls this (it never forms
+        ``Jt``); it exists for callers that hold the dense Jacobian already.  The products with ``Jt`` are torch's bmm
+        as in the reference; damping, solve, pose update and the re-warped residuals of the residual volume are the
+        library's (dpft_ic_update, dpft_ic_residual)."""
+        if self.direction != 'inverse':
+            raise NotImplementedError("pose updated should be inverse for this tracker")
+        lvl = _IcLevel(x0, x1, invD0, invD1, K, None, obj_mask1)
+        B = lvl.B
+        Jt = Jt.float()
+        w = weights.expand(B, lvl.C, lvl.H, lvl.W).float()
+        rows = pack_pose(pose0).to(lvl.dev)
+        A21 = JtJ.reshape(B, 36).float().index_select(1, torch.tensor([i * 6 + j for i, j in _TRI], device=lvl.dev)).contiguous()
+        b0 = torch.bmm(Jt, (w * R).reshape(B, -1, 1)).reshape(B, 6).contiguous()
+        if self.type == self.SOLVER_NO_DAMPING:
+            return unpack_pose(lvl.update(0, A21, b0, rows)[0])
+        S = int(self.samples)
+        lambdas = torch.logspace(-5, 5, S).to(device=lvl.dev, dtype=torch.float32)
+        trial = lvl.update(1, A21, b0, rows, lambdas=lambdas)                      # (S,B,12)
+        vol = []
+        for s in range(S):                                                         # alg:1676-1683
+            r_s, _ = lvl.residual(trial[s].contiguous(), first=False)
+            vol.append(torch.bmm(Jt, (w * r_s).reshape(B, -1, 1)).reshape(B, 6))
+        feat = torch.cat((torch.stack(vol, dim=2).reshape(B, 6 * S), JtJ.reshape(B, 36).float()), dim=1)
+        damp = self.net(feat).float().contiguous()
+        return unpack_pose(lvl.update(2, A21, b0, rows, damp=damp)[0])
 
 
 class _IcLevel:
@@ -516,6 +600,19 @@ class _IcLevel:
         """(r (B,C,H,W), occ bool (B,1,H,W)); the keyframe object mask only counts on the first call (alg:65-66, 86-87)."""
         r, occ = _IcResidualFn.apply(self, first, pose_rows, self.t["x0"], self.t["x1"])
         return r, occ.bool()
+
+    def context(self, pose_rows, w_prior):
+        """(B,4,H,W) input of DeepRobustEstimator('MultiScale2w') at ``pose_rows`` (first evaluation of a level: the
+        keyframe object mask counts)."""
+        wp = _dev_f32(w_prior, "wPrior")
+        ctx = torch.empty((self.B, 4, self.H, self.W), dtype=torch.float32, device=self.dev)
+        rows = pose_rows.contiguous()
+        with torch.cuda.device(self.dev):
+            code = self.L.dpft_ic_context(self._arr(True), self.B, rows.data_ptr(), wp.data_ptr(), int(wp.shape[-2]),
+                                          int(wp.shape[-1]), ctx.data_ptr(), None,
+                                          torch.cuda.current_stream(self.dev).cuda_stream)
+        _lib.check(code, "dpft_ic_context")
+        return ctx
 
     def _w(self, weights):
         if weights is None:
@@ -706,6 +803,16 @@ class TrustRegionBase(nn.Module):
             return None
         return self.mEstimator(r, x0, x1, wPrior)
 
+    def _fused_context_ok(self, lvl, wPrior, tensors) -> bool:
+        """The convolutional M-estimator's input can come straight from the residual kernel (dpft_ic_context) when the
+        estimator is the reference's 4-channel one on a one-channel level and nothing needs a gradient."""
+        m = self.mEstimator
+        if m is None or getattr(m, "D", None) != 4 or getattr(m, "net", None) is None or lvl.C != 1 or wPrior is None:
+            return False
+        if torch.is_grad_enabled() and (any(t.requires_grad for t in tensors) or any(p.requires_grad for p in m.parameters())):
+            return False
+        return True
+
     def forward(self, pose, x0, x1, invD0, invD1, K, wPrior=None, vis_res=False, obj_mask0=None, obj_mask1=None):
         solver = self.directSolver
         if solver is not None and getattr(solver, "direction", "inverse") != "inverse":
@@ -713,9 +820,14 @@ class TrustRegionBase(nn.Module):
         lvl = _IcLevel(x0, x1, invD0, invD1, K, obj_mask0, obj_mask1)
         rows = pack_pose(pose).to(lvl.dev)
         if self.timers: self.timers.tic('compute warping residuals')
-        r, occ = lvl.residual(rows, first=True)
+        if self._fused_context_ok(lvl, wPrior, (x0, x1, pose[0], pose[1], wPrior)):
+            # [ |r|, x0, x1, up(wPrior) ] written once by the residual kernel (alg:1471-1474 builds it from four tensors)
+            with torch.no_grad():
+                weights = self.mEstimator.net(lvl.context(rows, wPrior))
+        else:
+            r, occ = lvl.residual(rows, first=True)
+            weights = self._weights(r, lvl.t["x0"], lvl.t["x1"], wPrior)
         if self.timers: self.timers.toc('compute warping residuals')
-        weights = self._weights(r, lvl.t["x0"], lvl.t["x1"], wPrior)
         A21 = lvl.normal_matrix(weights)
         kind = getattr(solver, "type", 0) if solver is not None else 0
         for it in range(self.max_iterations):

@@ -65,6 +65,7 @@ struct IcpParams {
   float* rec;         // (B,28): 21 + 6 sums (atomically accumulated; zero before the launch)
   uint8_t* occ_out;   // optional (B,H,W)
   float* r_out;       // optional (B,H,W) weighted-by-sigma residual (1e-6 where masked)
+  const float* wmap;  // optional (B,H,W) per-pixel scale of residual and Jacobian (learned ScaleNet, alg:677-682)
   int H, W, B, ppt;
 };
 
@@ -123,7 +124,13 @@ __global__ void __launch_bounds__(128, 4) icp_term_kernel(const IcpParams p) {
     J[3] = nr[0] * inv;
     J[4] = nr[1] * inv;
     J[5] = nr[2] * inv;
-    const float rm = occ ? 1e-6f : r;
+    float rm = occ ? 1e-6f : r;
+    if (p.wmap) {   // w scales r and J alike: sum (w J)(w J)^T, sum (w J)(w r)
+      const float w = __ldg(p.wmap + (size_t)b * plane + pix);
+      rm *= w;
+#pragma unroll
+      for (int a = 0; a < 6; ++a) J[a] *= w;
+    }
 #pragma unroll
     for (int a = 0; a < 6; ++a) {
 #pragma unroll
@@ -131,7 +138,7 @@ __global__ void __launch_bounds__(128, 4) icp_term_kernel(const IcpParams p) {
       acc[21 + a] = fmaf(J[a], rm, acc[21 + a]);
     }
     if (p.occ_out) p.occ_out[(size_t)b * plane + pix] = occ ? 1 : 0;
-    if (p.r_out) p.r_out[(size_t)b * plane + pix] = rm;
+    if (p.r_out) p.r_out[(size_t)b * plane + pix] = occ ? 1e-6f : r;
   }
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 #pragma unroll
@@ -324,11 +331,11 @@ void launch_vertex_normal(const float* depth, const float* K, const uint32_t* dm
 }
 
 void launch_icp_term(const float* depth0, const float* K, const float* V1, const float* N1, const float* pose,
-                     const uint8_t* m0, const uint8_t* m1, float* rec, uint8_t* occ_out, float* r_out, int B, int H,
-                     int W, cudaStream_t stream) {
+                     const uint8_t* m0, const uint8_t* m1, float* rec, uint8_t* occ_out, float* r_out, const float* wmap,
+                     int B, int H, int W, cudaStream_t stream) {
   IcpParams p{};
   p.depth0 = depth0; p.K = K; p.V1 = V1; p.N1 = N1; p.pose = pose; p.m0 = m0; p.m1 = m1;
-  p.rec = rec; p.occ_out = occ_out; p.r_out = r_out; p.H = H; p.W = W; p.B = B;
+  p.rec = rec; p.occ_out = occ_out; p.r_out = r_out; p.wmap = wmap; p.H = H; p.W = W; p.B = B;
   const long plane = (long)H * W;
   const long want_threads = 148L * 2048 * 2;
   long ppt = ((long)B * plane + want_threads - 1) / want_threads;

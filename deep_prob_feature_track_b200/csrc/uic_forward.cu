@@ -783,6 +783,7 @@ struct Tuning {
   bool generic_geometry = false;
   float* launch_ms = nullptr;
   float* queue_kernel_ms = nullptr;
+  const float* icp_weight[DPFT_MAX_LEVELS] = {};   // per level: (B,1,H,W) scale of the ICP term, or nullptr (scalar w_icp)
 };
 
 static Tuning tuning_of(const dpft_uic_options_t* o) {
@@ -797,6 +798,7 @@ static Tuning tuning_of(const dpft_uic_options_t* o) {
   t.generic_geometry = o->generic_geometry != 0;
   t.launch_ms = o->launch_ms;
   t.queue_kernel_ms = o->launch_ms ? o->queue_kernel_ms : nullptr;
+  for (int l = 0; l < DPFT_MAX_LEVELS; ++l) t.icp_weight[l] = o->icp_weight[l];
   return t;
 }
 
@@ -1486,10 +1488,11 @@ static int run_lpi(const dpft_level_t* levels, int n_levels, int B, int C, int i
       prm.kf_shared = shared_kf; prm.pairwise = pairwise; prm.status = status; prm.flags = flags;
       prm.group = G.group; prm.n_mm_groups = G.n_mm_groups;
       if (icp) {
+        const float* wmap = tun.icp_weight[l];      // a learned scaler's per-pixel map replaces the scalar weight
         launch_icp_term(L.depth0, L.K, vn, vn + 3 * (size_t)B * plane, prm.pose, L.obj_mask0, L.obj_mask1, icp_rec,
-                        nullptr, nullptr, B, L.H, L.W, stream);
+                        nullptr, nullptr, wmap, B, L.H, L.W, stream);
         prm.icp_rec = icp_rec;
-        prm.icp_w2 = w_icp * w_icp;
+        prm.icp_w2 = wmap ? 1.f : w_icp * w_icp;
       }
       const dim3 grid(prm.ctas_per_pair, B);
       // the debug mask pass reads what this launch wrote, so keep plain stream order around it

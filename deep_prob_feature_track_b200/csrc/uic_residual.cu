@@ -23,6 +23,7 @@ struct ResParams {
   const uint8_t* icp_occ;    // (B,H,W)
   uint32_t* mm;              // [0..1] sigma0 min/max, [2..3] warped sigma min/max (order-encoded)
   float* sums;               // (B,2): sum of squares, number of masked pixels
+  float* norm_out;           // optional (B,H,W): sqrt(sum_c wm_c^2), wm = 1e-6 where masked (ScaleNet's view of the residual)
   float w_icp;
   int H, W, B, C;
 };
@@ -62,6 +63,7 @@ __global__ void __launch_bounds__(128) uic_residual_kernel(const ResParams p) {
         occ = occ || (s0c0 == ord2f(p.mm[0])) || (s0c0 == ord2f(p.mm[1])) || (sr0 == ord2f(p.mm[2])) || (sr0 == ord2f(p.mm[3]));
       }
       if (p.icp_occ) occ = occ || (__ldg(p.icp_occ + (size_t)b * plane + pix) != 0);
+      if (p.norm_out && occ) p.norm_out[(size_t)b * plane + pix] = sqrtf((float)C * 1e-12f);
       if (!occ) {
         for (int c = 0; c < C; ++c) {
           const size_t k0 = pair_off + (size_t)c * plane;
@@ -73,6 +75,7 @@ __global__ void __launch_bounds__(128) uic_residual_kernel(const ResParams p) {
           const float wres = res * rsqrtf(fmaf(sr, sr, s0v * s0v));
           ssq = fmaf(wres, wres, ssq);
         }
+        if (p.norm_out) p.norm_out[(size_t)b * plane + pix] = sqrtf(ssq);
         if (p.icp_r) {
           const float r = p.w_icp * __ldg(p.icp_r + (size_t)b * plane + pix);
           ssq = fmaf(r, r, ssq);
@@ -149,6 +152,51 @@ static ResPlan make_res_plan(const dpft_level_t& L, int B, uint32_t flags) {
 
 using namespace dpft;
 
+// ScaleNet's inputs at `pose` (see context.cu): icp_r (B,1,H,W) and feat_norm (B,1,H,W).  Same passes as
+// dpft_uic_residual_loss, with the two maps as outputs; the feature mask does NOT include the ICP mask here
+// (compose_residuals, alg:1960-1989, knows nothing of the ICP term).  Workspace: dpft_uic_residual_workspace_bytes
+// with DPFT_COMBINE_ICP.
+extern "C" int dpft_uic_icp_context(const dpft_level_t* level, int B, int C, uint32_t flags, const float* pose,
+                                    float* icp_r, float* feat_norm, void* workspace, size_t workspace_bytes,
+                                    void* stream_) {
+  if (!level || B < 1 || B > 65535 || C < 1 || !pose || !icp_r || !feat_norm || !workspace)
+    return set_error(DPFT_EINVAL, "level, pose, icp_r, feat_norm and workspace are required");
+  const dpft_level_t& L = *level;
+  if (!L.x0 || !L.x1 || !L.sigma0 || !L.sigma1 || !L.invd0 || !L.invd1 || !L.K || !L.depth0 || !L.depth1 || L.H < 2 || L.W < 2)
+    return set_error(DPFT_EINVAL, "x0, x1, sigma0, sigma1, invd0, invd1, depth0, depth1 and K are required");
+  const bool tru = flags & DPFT_REMOVE_TRU_SIGMA;
+  const ResPlan pl = make_res_plan(L, B, flags | DPFT_COMBINE_ICP);
+  if (workspace_bytes < pl.total) return set_error(DPFT_ENOSPACE, "workspace has %zu bytes, %zu needed", workspace_bytes, pl.total);
+  cudaStream_t stream = (cudaStream_t)stream_;
+  char* ws = (char*)workspace;
+  const size_t plane = (size_t)L.H * L.W;
+  ResParams p{};
+  p.x0 = L.x0; p.x1 = L.x1; p.s0 = L.sigma0; p.s1 = L.sigma1; p.d0 = L.invd0; p.d1 = L.invd1; p.K = L.K; p.pose = pose;
+  p.m0 = L.obj_mask0; p.m1 = L.obj_mask1;
+  p.mm = (uint32_t*)(ws + pl.off_mm);
+  p.sums = (float*)(ws + pl.off_sums);
+  p.norm_out = feat_norm;
+  p.H = L.H; p.W = L.W; p.B = B; p.C = C;
+  residual_prepare_kernel<<<(2 * B + 255) / 256, 256, 0, stream>>>(p.mm, p.sums, 2 * B);
+  float* vn = (float*)(ws + pl.off_vn);
+  launch_minmax(L.depth1, (size_t)B * plane, p.mm + 4, stream);
+  launch_vertex_normal(L.depth1, L.K, p.mm + 4, vn, vn + 3 * (size_t)B * plane, B, L.H, L.W, stream);
+  // inside the solver loop the ICP term honours the object masks (alg:668-672)
+  launch_icp_term(L.depth0, L.K, vn, vn + 3 * (size_t)B * plane, pose, L.obj_mask0, L.obj_mask1, (float*)(ws + pl.off_rec),
+                  nullptr, icp_r, nullptr, B, L.H, L.W, stream);
+  const dim3 grid((unsigned)((plane + 127) / 128), B);
+  if (tru) {
+    launch_minmax(L.sigma0, (size_t)B * C * plane, p.mm, stream);
+    uic_residual_kernel<0, true><<<grid, 128, 0, stream>>>(p);
+    uic_residual_kernel<1, true><<<grid, 128, 0, stream>>>(p);
+  } else {
+    uic_residual_kernel<1, false><<<grid, 128, 0, stream>>>(p);
+  }
+  const cudaError_t err = cudaGetLastError();
+  if (err != cudaSuccess) return set_error((int)err, "context launch: %s", cudaGetErrorString(err));
+  return 0;
+}
+
 extern "C" size_t dpft_uic_residual_workspace_bytes(const dpft_level_t* level, int B, int C, uint32_t flags) {
   (void)C;
   if (!level || B < 1) {
@@ -188,7 +236,7 @@ extern "C" int dpft_uic_residual_loss(const dpft_level_t* level, int B, int C, u
     launch_vertex_normal(L.depth1, L.K, p.mm + 4, vn, vn + 3 * (size_t)B * plane, B, L.H, L.W, stream);
     // the reference leaves the object masks out of this ICP evaluation (algorithms.py:768-769)
     launch_icp_term(L.depth0, L.K, vn, vn + 3 * (size_t)B * plane, pose, nullptr, nullptr, (float*)(ws + pl.off_rec),
-                    icp_occ, icp_r, B, L.H, L.W, stream);
+                    icp_occ, icp_r, nullptr, B, L.H, L.W, stream);
     p.icp_r = icp_r;
     p.icp_occ = icp_occ;
   }

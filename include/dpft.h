@@ -114,6 +114,9 @@ typedef struct dpft_uic_options {
                              Gauss-Newton iteration (CUDA events around every launch, or %globaltimer stamps of the
                              iteration completions inside a single launch), WAITS for the stream and fills the array:
                              a measurement aid, not a way to run the solver.                                      */
+  const float *icp_weight[DPFT_MAX_LEVELS]; /* DPFT_COMBINE_ICP: per level (coarse first) a DEVICE map (B,1,H,W) that
+                             scales the point-to-plane residual and Jacobian pixel by pixel -- the output of a learned
+                             ScaleNet evaluated at the level's first iteration (alg:677-682) -- or NULL: the scalar w_icp. */
   float *queue_kernel_ms; /* HOST array (queue_levels entries, coarse level first) or NULL; only read together with
                              launch_ms.  Receives the device time of each work-queue KERNEL alone: CUDA events recorded on
                              `stream` right before and right after its launch (its helper launches -- queue init, sigma0
@@ -221,6 +224,22 @@ int dpft_ic_rhs_backward(const dpft_level_t *level, int B, int C, const float *g
 int dpft_ic_update_backward(int B, int S, int mode, const float *A21, const float *rhs, const float *lambdas,
                             const float *damp, const float *pose_in, const float *g_pose_out, float *g_A21,
                             float *g_rhs, float *g_damp, float *g_pose_in, void *stream);
+
+/*
+ * Context tensors of the learned networks the reference calls inside the loop, written by the kernels
+ * that evaluate the residual:
+ *   dpft_ic_context       context (B,4,H,W) = [ |r|, x0, x1, bilinear_up(w_prior) ]: the input of
+ *                         DeepRobustEstimator('MultiScale2w') (alg:1471-1474) for a ONE-channel IC level at `pose` (B,12);
+ *                         w_prior (B,1,hp,wp) or NULL (ones); occ_out (B,H,W) optional.
+ *   dpft_uic_icp_context  icp_r (B,1,H,W): point-to-plane residual / sigma_icp, 1e-6 where its mask is set, and
+ *                         feat_norm (B,1,H,W) = sqrt(sum_c wres_c^2) of the masked uncertainty-weighted feature residual:
+ *                         all ScaleNet (alg:1535-1567) reads of its two residual inputs.  Needs depth0 / depth1.
+ *                         Workspace: dpft_uic_residual_workspace_bytes with DPFT_COMBINE_ICP.
+ */
+int dpft_ic_context(const dpft_level_t *level, int B, const float *pose, const float *w_prior, int hp, int wp,
+                    float *context, uint8_t *occ_out, void *stream);
+int dpft_uic_icp_context(const dpft_level_t *level, int B, int C, uint32_t flags, const float *pose, float *icp_r,
+                         float *feat_norm, void *workspace, size_t workspace_bytes, void *stream);
 
 /*
  * forward_residuals of the U_IC tracker (alg:725-786 with compute_avg_loss alg:2119-2137): per frame pair the

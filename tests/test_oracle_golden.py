@@ -158,3 +158,29 @@ def test_pose_epe_loss_matches_reference():
         ev = O.pose_epe_loss(g["R_est"][:, :1], g["t_est"][:, :1], g["R_gt"], g["t_gt"], g["depth"], g["K"],
                              g["invalid"].float())
     assert frob_rel(ev, g["loss_eval"]) < 1e-5
+
+
+@pytest.mark.parametrize("kind", ["twoResidual", "MultiScale2w"])
+def test_uic_level_with_a_learned_scaler_matches_the_installed_reference(kind):
+    """The oracle's scale_func branch (alg:677-682) against the reference's own TrustRegionInverseWUncertainty with
+    its ScaleNet, both on the CPU (baseline/_ref: the reference installed by recipe)."""
+    from baseline import reference as REF
+    if not REF.available():
+        pytest.skip("baseline/_ref not installed")
+    alg, _, _, _ = REF.modules()
+    from deep_prob_feature_track_b200.synthetic import make_frame_pairs
+    torch.manual_seed(5)
+    net = alg.ScaleNet(kind, scale=0.05).eval()
+    data = make_frame_pairs(2, 4, 48, 64, seed=13, n_levels=1, with_depth=True)
+    lv = data["levels"][0]
+    s0, s1 = lv["s0"].expand(-1, 4, -1, -1).contiguous(), lv["s1"].expand(-1, 4, -1, -1).contiguous()
+    prior = torch.rand((2, 1, 24, 32), generator=torch.Generator().manual_seed(1))
+    tr = alg.TrustRegionInverseWUncertainty(3, combine_icp=True, scale_func=net, remove_tru_sigma=True).eval()
+    with torch.no_grad():
+        (R_ref, t_ref), w_ref = tr([data["R0"], data["t0"]], lv["x0"], lv["x1"], lv["invD0"], lv["invD1"], lv["K"], s0, s1,
+                                   wPrior=prior, depth0=lv["depth0"], depth1=lv["depth1"], vis_res=False)
+        (R, t), w = O.uic_level((data["R0"], data["t0"]), lv["x0"], lv["x1"], lv["invD0"], lv["invD1"], lv["K"], s0, s1,
+                                iters=3, remove_tru_sigma=True, combine_icp=True, depth0=lv["depth0"], depth1=lv["depth1"],
+                                scale_func=net, wPrior=prior, sampler="grid_sample")
+    assert frob_rel(w, w_ref) < 1e-5
+    assert (R - R_ref).abs().max() < 1e-6 and (t - t_ref.reshape(-1, 3)).abs().max() < 1e-6
