@@ -84,8 +84,8 @@ def test_deepic_level_through_the_fused_context_matches_the_reference_fixture():
         solver.net[i][0].bias.data = ref[2 * i].bias.data.clone()
     mod = A.TrustRegionBase(max_iter=int(g["flags"][3]), mEst_func=mest, solver_func=solver).to(DEV).eval()
     pose = [g["R0"].to(DEV), g["t0"].to(DEV)]
-    assert mod._fused_context_ok(A._IcLevel(lv["x0"], lv["x1"], lv["invD0"], lv["invD1"], lv["K"]), g["wprior"], ())
     with torch.no_grad():
+        assert mod._fused_context_ok(A._IcLevel(lv["x0"], lv["x1"], lv["invD0"], lv["invD1"], lv["K"]), g["wprior"], ())
         (R, t), w = mod(pose, lv["x0"], lv["x1"], lv["invD0"], lv["invD1"], lv["K"], wPrior=g["wprior"].to(DEV))
     assert (R.cpu() - g["R_out"]).abs().max() < TOL_POSE
     assert (t.cpu() - g["t_out"]).abs().max() < TOL_POSE
