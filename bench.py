@@ -50,7 +50,8 @@ WORKLOADS = {
     "train": dict(name="tum120x160_b64_c8_uic_trainstep", B=64, C=8, H=120, W=160),
 }
 N_LEVELS, ITERS = 4, 3
-ROOFLINE_BATCHES = 8          # batches per launch of the roofline pass (what the committed ncu capture ran)
+ROOFLINE_BATCHES = 8          # batches per launch of the roofline pass (what the committed ncu capture ran; 20 per launch measure
+                              # 55.7 us per batch-iteration under ncu and 58 us back to back under the power cap, profiles/r2/r2b_*)
 NCU_SUMMARY = os.path.join(ROOT, "profiles", "r2", "r2_uic_queue_kernel_level0_G8.txt")
 
 
@@ -295,7 +296,7 @@ def run_tum(args, wl, rank, world, dev, barrier, max_over_ranks):
     n_stack = max(G, ROOFLINE_BATCHES)
     sets = stacked_sets(gen_dev, S, n_stack)               # one stacked set per stream
     set_bytes = sum(v.numel() * 4 for lv in sets[0][0] for v in lv.values()) // n_stack
-    solver = BatchedSolver(B, iters=ITERS, remove_tru_sigma=True, streams=S, device=dev)
+    solver = BatchedSolver(B, iters=ITERS, remove_tru_sigma=True, streams=S, device=dev, graphs=not args.no_graphs)
 
     calls = [G] * (K // G) + ([K % G] if K % G else [])     # K steps exactly
 
@@ -306,10 +307,15 @@ def run_tum(args, wl, rank, world, dev, barrier, max_over_ranks):
         return out
 
     # ---- value
-    warm = [G] * max(1, (args.warmup + G - 1) // G)
-    res = run(warm + [1])                                   # every call size once (allocator, function attributes)
-    if calls[-1] != G:
-        run([calls[-1]])
+    # warm-up: every call size of the timed region on every input set (function attributes, allocator, and the graph
+    # of that set and size is captured here, not in the timed region), then whole calls up to at least W steps
+    res = None
+    for g in sorted(set(calls + [1]), reverse=True):
+        for si in range(S):
+            res = solver.submit(*take(*sets[si], B * g))
+    done = S * sum(set(calls))
+    if done < args.warmup:
+        run([G] * ((args.warmup - done + G - 1) // G))
     solver.synchronize()
     res.raise_if_bad()
     barrier()
@@ -408,6 +414,8 @@ def run_tum(args, wl, rank, world, dev, barrier, max_over_ranks):
         "value": world * B * K / (ms * 1e-3), "ms_per_step": ms / K,
         "config": dict(base_config(wl), batches_per_call=G, streams=S, call_sizes=calls,
                        api="deep_prob_feature_track_b200.batched.BatchedSolver.submit",
+                       cuda_graphs=f"{solver.replays} of {solver.calls} calls replayed from a captured graph (BatchedSolver(graphs=True): "
+                                   "one graph per input set, captured during warm-up)",
                        coarse_levels="one launch per Gauss-Newton iteration (uic_iter_staged_kernel / uic_iter_kernel), all batches of a call in one grid",
                        finest_level="one work-queue launch for its 3 iterations (uic_queue_kernel, per-pair dependencies)",
                        sigma_extremes="per batch of 64 (options.group): the results of separate reference calls",
@@ -692,6 +700,7 @@ def main():
     ap.add_argument("--workload", default="tum", choices=tuple(WORKLOADS))
     ap.add_argument("--batches-per-call", type=int, default=20, help="batches stacked into one solver call (tum)")
     ap.add_argument("--streams", type=int, default=2, help="CUDA streams the calls rotate over")
+    ap.add_argument("--no-graphs", action="store_true", help="submit every call launch by launch instead of replaying its CUDA graph")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-extras", action="store_true")
     ap.add_argument("--no-parity", action="store_true")

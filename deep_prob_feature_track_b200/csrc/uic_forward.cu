@@ -359,8 +359,17 @@ __device__ __forceinline__ void reduce_and_finish(const UicIterParams& p, const 
   DPFT_STAMP(7, threadIdx.x == 0);                                // all solves written
 }
 
-template <int CH, bool TRU, int GW = 0, int GH = 0>
-__global__ void __launch_bounds__(kThreads, DPFT_MIN_CTAS) uic_iter_kernel(const __grid_constant__ UicIterParams p) {
+//
+// RES: the "resident" variant for SMALL levels (the coarse end of the pyramid).  There a level of one pair is a few
+// tens of KB, so every CTA first copies the pair's whole live frame (x1, sigma1, invd1) into shared memory -- with
+// cp.async, BEFORE the dependency sync, i.e. under the tail of the previous iteration's launch, because nothing a
+// launch writes is read by that copy -- and the 68 footprint taps of a pixel become LDS instead of L1/L2 round trips.
+constexpr int kResMinCtas = 3;     // shared memory, not registers, bounds the resident CTAs: 170 registers, no spills
+__device__ __forceinline__ bool cta_has_tiles(const UicIterParams& p, unsigned cta) { return (int)(cta * kWarps) < p.nseg * p.nrt; }
+
+template <int CH, bool TRU, int GW = 0, int GH = 0, bool RES = false>
+__global__ void __launch_bounds__(kThreads, RES ? kResMinCtas : DPFT_MIN_CTAS) uic_iter_kernel(const __grid_constant__ UicIterParams p) {
+  extern __shared__ __align__(16) float dyn_live[];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int b = blockIdx.y;
   const int plane = (GW > 0) ? GW * GH : p.H * p.W;
@@ -391,9 +400,30 @@ __global__ void __launch_bounds__(kThreads, DPFT_MIN_CTAS) uic_iter_kernel(const
   __shared__ float red[kWarps][NSUM][33];
   __shared__ __align__(16) float s_pose[12];
   DPFT_STAMP(0, threadIdx.x == 0 && blockIdx.x == 0 && b == 0);
+  if (RES && cta_has_tiles(p, blockIdx.x)) {
+    // x1 | sigma1 | invd1 of this pair, contiguous in that order: 16-byte copies when the planes allow it
+    const unsigned dst0 = (unsigned)__cvta_generic_to_shared(dyn_live);
+    const float* src[3] = {g.x1, g.s1, g.d1};
+    const int cnt[3] = {p.C * plane, p.SC * plane, plane};
+    const bool v16 = (plane % 4 == 0) && ((((uintptr_t)g.x1 | (uintptr_t)g.s1 | (uintptr_t)g.d1) & 15u) == 0);
+    int off = 0;
+#pragma unroll
+    for (int r = 0; r < 3; ++r) {
+      if (v16) {
+        for (int i = 4 * threadIdx.x; i < cnt[r]; i += 4 * kThreads)
+          asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst0 + 4u * (unsigned)(off + i)), "l"(src[r] + i) : "memory");
+      } else {
+        for (int i = threadIdx.x; i < cnt[r]; i += kThreads)
+          asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dst0 + 4u * (unsigned)(off + i)), "l"(src[r] + i) : "memory");
+      }
+      off += cnt[r];
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  }
   cudaTriggerProgrammaticLaunchCompletion();
   cudaGridDependencySynchronize();
   DPFT_STAMP(1, threadIdx.x == 0 && blockIdx.x == 0 && b == 0);
+  if (RES) asm volatile("cp.async.wait_group 0;" ::: "memory");
   if (threadIdx.x < 12) s_pose[threadIdx.x] = __ldcg(p.pose + (size_t)b * 12 + threadIdx.x);
   if (TRU) {
     const uint32_t* mm = p.s0mm + (p.n_mm_groups > 1 ? 2 * (b / p.group) : 0);
@@ -405,7 +435,7 @@ __global__ void __launch_bounds__(kThreads, DPFT_MIN_CTAS) uic_iter_kernel(const
   __syncthreads();
   TileSums S;
   S.reset();
-  process_tile<CH, TRU, GW, GH>(g, s_pose, &red[warp][27], seg, y0, y1, lane, S);
+  process_tile<CH, TRU, GW, GH, RES>(g, s_pose, &red[warp][27], seg, y0, y1, lane, S, dyn_live);
   DPFT_STAMP(2, threadIdx.x == 0 && blockIdx.x == 0 && b == 0);
   reduce_and_finish<TRU>(p, b, red[warp], S.acc, S.vmin, S.vmax, p.ctas_per_pair);
 }
@@ -781,6 +811,7 @@ struct Tuning {
   long cta_slots = 0;                     // 0 = 148 x resident CTAs
   int tiling = 0;                         // 0 dealt, 1 rectangular, 2 linear
   bool generic_geometry = false;
+  bool no_resident = false;       // measurement knob: small levels on the plain (global-memory lookup) kernel
   float* launch_ms = nullptr;
   float* queue_kernel_ms = nullptr;
   const float* icp_weight[DPFT_MAX_LEVELS] = {};   // per level: (B,1,H,W) scale of the ICP term, or nullptr (scalar w_icp)
@@ -799,6 +830,7 @@ static Tuning tuning_of(const dpft_uic_options_t* o) {
   t.launch_ms = o->launch_ms;
   t.queue_kernel_ms = o->launch_ms ? o->queue_kernel_ms : nullptr;
   for (int l = 0; l < DPFT_MAX_LEVELS; ++l) t.icp_weight[l] = o->icp_weight[l];
+  t.no_resident = o->small_levels == 1;
   return t;
 }
 
@@ -807,6 +839,7 @@ struct Plan {
   int ppt[DPFT_MAX_LEVELS], px_ctas[DPFT_MAX_LEVELS];   // materialised-gradient path: pixels per thread, CTAs per pair
   int max_ctas;
   TileTab tab[DPFT_MAX_LEVELS];   // balanced tiling of the levels the staged kernel takes
+  int res_smem[DPFT_MAX_LEVELS];  // > 0: the level runs the resident variant with this many bytes of dynamic shared memory
   size_t max_plane;
   size_t off_partials, off_pairrec, off_counters, off_mm, off_gmm, off_sr0, off_grad, grad_elems;
   size_t off_vn, off_icp, off_dmm, total;
@@ -818,7 +851,7 @@ struct Plan {
 // Rows per warp tile.  A tile is walked row by row by one warp, so the time of a launch is about
 // (waves of CTAs) x (rows per tile + ~1.5 rows of window priming and reduction tail): pick the height that
 // minimises that, i.e. fill whole waves of the 148 x DPFT_MIN_CTAS resident CTAs.
-static int pick_tile_rows(int H, int nseg, int B, int ctas_per_sm, int warps, const Tuning& tun) {
+static int pick_tile_rows(int H, int nseg, int B, int ctas_per_sm, int warps, const Tuning& tun, double fixed_rows = 1.5) {
   long slots = 148L * ctas_per_sm;
   if (tun.cta_slots > 0) slots = tun.cta_slots;
   int best_tr = 1;
@@ -827,7 +860,7 @@ static int pick_tile_rows(int H, int nseg, int B, int ctas_per_sm, int warps, co
     const long nrt = (H + tr - 1) / tr;
     const long ctas = ((nrt * nseg + warps - 1) / warps) * B;
     const long waves = (ctas + slots - 1) / slots;
-    const double cost = (double)waves * (tr + 1.5);
+    const double cost = (double)waves * (tr + fixed_rows);
     if (cost < best - 1e-9) { best = cost; best_tr = tr; }
   }
   return best_tr;
@@ -837,6 +870,14 @@ static int pick_tile_rows(int H, int nseg, int B, int ctas_per_sm, int warps, co
 static bool staged_ok(const dpft_level_t& L, int C) {
   auto al = [](const void* q) { return ((uintptr_t)q & 15u) == 0; };
   return C == 8 && L.W % 4 == 0 && L.W >= 2 * kTileCols && L.H >= kStageRows && al(L.x1) && al(L.sigma1) && al(L.invd1);
+}
+
+// Small levels: the whole live frame of a pair (x1, sigma1, invd1) in the shared memory of every CTA that works on the
+// pair (uic_iter_kernel<.., RES>).  Taken when the staged kernel does not apply and at least two CTAs fit an SM.
+constexpr int kResStaticSmem = (kWarps * NSUM * 33 + 16) * 4 + kWarps * (NSUM + 1) * 8 + 64;   // red, s_pose, wsum, flags
+static int resident_smem(const dpft_level_t& L, int C, int SC) {
+  const size_t bytes = (size_t)(C + SC + 1) * L.H * L.W * sizeof(float);
+  return bytes + kResStaticSmem <= 110 * 1024 ? (int)bytes : 0;
 }
 
 // Linear variant of the balanced tile table (DPFT_LINEAR_TILES=1; see TileTab).  Returns false when the rectangular tiling should stay (the
@@ -932,7 +973,13 @@ static Plan make_plan(const dpft_level_t* lv, int n_levels, int B, int C, uint32
     const int cols = staged ? kStagedCols : kCols;
     pl.nseg[l] = (lv[l].W + cols - 1) / cols;
     const int cta_warps = staged ? kSW : kWarps;
-    pl.TR[l] = pick_tile_rows(lv[l].H, pl.nseg[l], B, staged ? DPFT_STAGED_CTAS : DPFT_MIN_CTAS, cta_warps, tun);
+    const int SC = (flags & DPFT_SIGMA_BROADCAST) ? 1 : C;
+    pl.res_smem[l] = (!staged && (flags & DPFT_FUSED_SOBEL) && !tun.no_resident) ? resident_smem(lv[l], C, SC) : 0;
+    int ctas_per_sm = staged ? DPFT_STAGED_CTAS : DPFT_MIN_CTAS;
+    if (pl.res_smem[l]) ctas_per_sm = std::max(1, std::min(kResMinCtas, (227 * 1024) / (pl.res_smem[l] + kResStaticSmem + 1024)));
+    // (a resident CTA pays for its copy of the live frame first: about two tile rows' worth of time, which the cost
+    // model of pick_tile_rows sees as taller tiles being cheaper)
+    pl.TR[l] = pick_tile_rows(lv[l].H, pl.nseg[l], B, ctas_per_sm, cta_warps, tun, pl.res_smem[l] ? 3.5 : 1.5);
     pl.nrt[l] = (lv[l].H + pl.TR[l] - 1) / pl.TR[l];
     pl.ctas[l] = (pl.nseg[l] * pl.nrt[l] + cta_warps - 1) / cta_warps;
     pl.tab[l].on = 0;
@@ -1034,11 +1081,11 @@ static int check_group(const dpft_level_t* lv, int n_levels, int B, uint32_t fla
 
 template <int CH>
 static cudaError_t launch_iter(const UicIterParams& prm, dim3 grid, bool tru, bool pdl, cudaStream_t stream,
-                               const Tuning& tun) {
+                               const Tuning& tun, int res_smem = 0) {
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = grid;
   cfg.blockDim = dim3(kThreads);
-  cfg.dynamicSmemBytes = 0;
+  cfg.dynamicSmemBytes = (size_t)res_smem;
   cfg.stream = stream;
   cudaLaunchAttribute attr[1];
   attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
@@ -1046,7 +1093,7 @@ static cudaError_t launch_iter(const UicIterParams& prm, dim3 grid, bool tru, bo
   cfg.attrs = attr;
   cfg.numAttrs = pdl ? 1 : 0;
   // the reference's pyramid sizes (TUM 160x120 ... and 640x480 ...) run geometry-specialised instantiations
-  if (CH == 8 && !tun.generic_geometry) {
+  if (CH == 8 && !tun.generic_geometry && res_smem == 0) {
 #define DPFT_FIXED(w, h)                                                                     \
     if (prm.W == w && prm.H == h)                                                            \
       return tru ? cudaLaunchKernelEx(&cfg, uic_iter_kernel<8, true, w, h>, prm)             \
@@ -1054,6 +1101,11 @@ static cudaError_t launch_iter(const UicIterParams& prm, dim3 grid, bool tru, bo
     DPFT_FIXED(160, 120)
     DPFT_FIXED(80, 60)
 #undef DPFT_FIXED
+  }
+  if (res_smem > 0) {
+    auto* fn = tru ? uic_iter_kernel<CH, true, 0, 0, true> : uic_iter_kernel<CH, false, 0, 0, true>;
+    cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, res_smem);
+    return cudaLaunchKernelEx(&cfg, fn, prm);
   }
   if (tru) return cudaLaunchKernelEx(&cfg, uic_iter_kernel<CH, true>, prm);
   return cudaLaunchKernelEx(&cfg, uic_iter_kernel<CH, false>, prm);
@@ -1510,10 +1562,10 @@ static int run_lpi(const dpft_level_t* levels, int n_levels, int B, int C, int i
         err = launch_staged(prm, grid, tru, use_pdl, stream, tun);
       } else
       switch (CH) {
-        case 8: err = launch_iter<8>(prm, grid, tru, use_pdl, stream, tun); break;
-        case 4: err = launch_iter<4>(prm, grid, tru, use_pdl, stream, tun); break;
-        case 2: err = launch_iter<2>(prm, grid, tru, use_pdl, stream, tun); break;
-        default: err = launch_iter<1>(prm, grid, tru, use_pdl, stream, tun); break;
+        case 8: err = launch_iter<8>(prm, grid, tru, use_pdl, stream, tun, pl.res_smem[l]); break;
+        case 4: err = launch_iter<4>(prm, grid, tru, use_pdl, stream, tun, pl.res_smem[l]); break;
+        case 2: err = launch_iter<2>(prm, grid, tru, use_pdl, stream, tun, pl.res_smem[l]); break;
+        default: err = launch_iter<1>(prm, grid, tru, use_pdl, stream, tun, pl.res_smem[l]); break;
       }
       if (err != cudaSuccess) return set_error((int)err, "uic_iter_kernel launch: %s", cudaGetErrorString(err));
       if (tru && prm.occ_out) {

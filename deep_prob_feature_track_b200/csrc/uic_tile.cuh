@@ -82,10 +82,16 @@ __device__ __forceinline__ float4 lds_v4(const float* p) {
 // GW, GH > 0: the level's width and height are compile-time constants (the reference's pyramid sizes get their
 // own instantiations).  Every channel plane and footprint tap is then an immediate offset from ONE address
 // register per map and row, instead of a 64-bit multiply-add per load; GW = GH = 0 is the generic routine.
-template <int CH, bool TRU, int GW = 0, int GH = 0>
+//
+// RES ("resident"): `live` is a SHARED-memory copy of the live frame of this pair -- x1 (C planes), sigma1 (C planes, or
+// one with a single uncertainty map), invd1 -- which the CTA staged before the walk; every footprint tap is then an
+// LDS, whatever the warp field does.  What the small pyramid levels run (a 30x40 level is 82 KB), see
+// uic_iter_kernel.
+template <int CH, bool TRU, int GW = 0, int GH = 0, bool RES = false>
 __device__ __forceinline__ void process_tile(const PairView& g, const float* spose, float (*scorr)[33],
                                              const int seg, const int y0, const int y1, const int lane,
-                                             TileSums& S) {
+                                             TileSums& S, const float* live = nullptr) {
+  static_assert(!RES || (GW == 0 && GH == 0), "the resident routine is generic in the level size");
   constexpr bool FIXED = GW > 0 && GH > 0;
   constexpr int PLANE = GW * GH;
   const int H = FIXED ? GH : g.H, W = FIXED ? GW : g.W, C = g.C;
@@ -103,9 +109,11 @@ __device__ __forceinline__ void process_tile(const PairView& g, const float* spo
     const float* X0 = g.x0 + (size_t)c0 * iplane;
     const unsigned splane = g.splane;
     const float* S0 = g.s0 + (size_t)c0 * splane;
-    const float* X1 = g.x1 + (size_t)c0 * iplane;
-    const float* S1 = g.s1 + (size_t)c0 * splane;
-    if (!FIXED) { X0 = opaque(X0); S0 = opaque(S0); X1 = opaque(X1); S1 = opaque(S1); }
+    const float* X1 = RES ? live + (unsigned)c0 * iplane : g.x1 + (size_t)c0 * iplane;
+    const float* S1 = RES ? live + (unsigned)C * iplane + (unsigned)c0 * splane : g.s1 + (size_t)c0 * splane;
+    const float* D1 = RES ? live + (unsigned)(splane ? 2 * C : C + 1) * iplane : g.d1;
+    if (!FIXED) { X0 = opaque(X0); S0 = opaque(S0); }
+    if (!FIXED && !RES) { X1 = opaque(X1); S1 = opaque(S1); }
 
     // 3-row sliding windows of the keyframe maps (own column): top / mid / (bot loaded per row)
     float ft[CH], fm[CH], st[CH], sm[CH];
@@ -164,7 +172,13 @@ __device__ __forceinline__ void process_tile(const PairView& g, const float* spo
         inv_z = div_by(d0, wz, rz);
       }
       const Tap tap = make_tap_r(u, v, H, W, rcp_hw, rcp_hh);
-      const float d1w = sample_exact(g.d1, tap, W);
+      float d1w;
+      if (RES) {
+        const float* q = D1 + tap.o;
+        d1w = blend_exact(q[0], q[1], q[Wu], q[Wu + 1], tap);
+      } else {
+        d1w = sample_exact(D1, tap, W);
+      }
       bool occ = occluded(u, v, inv_z, d1w, H, W);
       if (g.m0) occ = occ || (__ldg(g.m0 + o) == 0);
       if (g.m1) occ = occ || !(sample_mask(g.m1, tap, W) > 0.f);
@@ -190,6 +204,14 @@ __device__ __forceinline__ void process_tile(const PairView& g, const float* spo
             const unsigned kz = (unsigned)(g0 + c) * splane;
             xa[c] = __ldg(xq + k); xb[c] = __ldg(xq + k + 1); xc_[c] = __ldg(xq + k + GW); xd[c] = __ldg(xq + k + GW + 1);
             za[c] = __ldg(zq + kz); zb[c] = __ldg(zq + kz + 1); zc[c] = __ldg(zq + kz + GW); zd[c] = __ldg(zq + kz + GW + 1);
+          }
+        } else if (RES) {
+          const float *xq = X1 + tap.o, *zq = S1 + tap.o;
+#pragma unroll
+          for (int c = 0; c < G; ++c) {
+            const unsigned k = (unsigned)(g0 + c) * iplane, kz = (unsigned)(g0 + c) * splane;
+            xa[c] = xq[k]; xb[c] = xq[k + 1]; xc_[c] = xq[k + Wu]; xd[c] = xq[k + Wu + 1];
+            za[c] = zq[kz]; zb[c] = zq[kz + 1]; zc[c] = zq[kz + Wu]; zd[c] = zq[kz + Wu + 1];
           }
         } else {
 #pragma unroll
@@ -248,7 +270,12 @@ __device__ __forceinline__ void process_tile(const PairView& g, const float* spo
       }
       if (TRU && c0 != 0) {
         // channel 0 decides the mask; seeing it in every pass keeps the running extremes comparable
-        sr0 = sample_exact(g.s1, tap, W);
+        if (RES) {
+          const float* q = live + (unsigned)C * iplane + tap.o;
+          sr0 = blend_exact(q[0], q[1], q[Wu], q[Wu + 1], tap);
+        } else {
+          sr0 = sample_exact(g.s1, tap, W);
+        }
         pmin = fminf(pmin, sr0);
         pmax = fmaxf(pmax, sr0);
       }

@@ -121,6 +121,11 @@ typedef struct dpft_uic_options {
                              launch_ms.  Receives the device time of each work-queue KERNEL alone: CUDA events recorded on
                              `stream` right before and right after its launch (its helper launches -- queue init, sigma0
                              extremes -- stay outside).                                                          */
+  int32_t small_levels;   /* launch-per-iteration kernels, levels whose live frame (x1, sigma1, invd1 of one pair) fits
+                             the shared memory of a CTA twice per SM: 0 = stage it there and look the footprint up on
+                             chip (the default), 1 = global-memory lookups as on any other level (a measurement knob;
+                             same masks bit for bit, same sums up to the order of the fp32 partial sums).        */
+  int32_t reserved_;
 } dpft_uic_options_t;
 
 /* ABI version of the loaded library (== DPFT_ABI_VERSION). */

@@ -271,3 +271,38 @@ def test_abi_rejects_unsupported_flag_mixes():
     # groups with the ICP term
     opt = _lib.DpftUicOptions(group=1)
     assert L.dpft_uic_workspace_bytes_ex(arr, 1, 2, C, 3, F.DPFT_FUSED_SOBEL | F.DPFT_COMBINE_ICP, ctypes.byref(opt)) == 0
+
+
+def test_batched_solver_graph_replay_equals_eager_calls():
+    """BatchedSolver(graphs=True): the first call on a set of buffers captures, later ones replay; the
+    results are those of plain calls, and refilling the input buffers in place is seen by the next replay."""
+    from deep_prob_feature_track_b200.batched import BatchedSolver
+    B, G = 8, 3
+    parts = [make_frame_pairs(B, 8, 120, 160, seed=70 + g, n_levels=4) for g in range(2 * G)]
+
+    def stack(ps):
+        lv = [{k: torch.cat([p["levels"][l][k] for p in ps]).to(DEV) for k in ps[0]["levels"][l]} for l in range(4)]
+        return lv, (torch.cat([p["R0"] for p in ps]).to(DEV), torch.cat([p["t0"] for p in ps]).to(DEV))
+
+    lv_a, pose = stack(parts[:G])
+    lv_b, _ = stack(parts[G:])
+    eager_a = A.uic_solve(lv_a, pose, iters=3, remove_tru_sigma=True, group=B, queue=True)
+    eager_b = A.uic_solve(lv_b, pose, iters=3, remove_tru_sigma=True, group=B, queue=True)
+    solver = BatchedSolver(B, iters=3, remove_tru_sigma=True, streams=2, device=torch.device(DEV), graphs=True, queue=True)
+    buf = [{k: v.clone() for k, v in lv.items()} for lv in lv_a]
+    outs = []
+    for i in range(4):                      # one graph for these buffers, replayed on either stream
+        r = solver.submit(buf, pose)
+        solver.synchronize()
+        outs.append(r.pose_hist.clone())
+    assert solver.replays == 4 and len(solver._graphs) == 1
+    for o in outs:
+        assert torch.equal(o, eager_a.pose_hist)
+    for lv, src in zip(buf, lv_b):          # new frames in the same buffers
+        for k in lv:
+            lv[k].copy_(src[k])
+    r = solver.submit(buf, pose)
+    solver.synchronize()
+    r.raise_if_bad()
+    assert torch.equal(r.pose_hist, eager_b.pose_hist)
+    assert torch.equal(r.sys_hist, eager_b.sys_hist)
