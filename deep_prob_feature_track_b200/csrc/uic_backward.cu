@@ -276,36 +276,58 @@ __global__ void pose_bwd_kernel(const float* __restrict__ sys, const float* __re
   for (int i = 0; i < 12; ++i) gpose_k[(size_t)b * 12 + i] += (float)gk[i];
 }
 
-// Adjoint of g = S / sqrt(|S|^2 + 1e-8), S = replicate-padded Sobel of img: scatters into g_img.
+// Adjoint of g = S / sqrt(|S|^2 + 1e-8), S = replicate-padded Sobel of img, ADDED to g_img.  Gather form: a CTA owns
+// 32 x 8 pixels of one plane, evaluates bs = n gg - (S . gg) n^3 S on the tile plus a one-pixel halo in shared memory
+// and every thread sums the transposed stencil for its own pixel -- one plain read-modify-write per element instead
+// of eight scattered atomicAdd per pixel.  With D_r[x] = bsx_r[x-1] - bsx_r[x+1], T_r[x] = bsy_r[x-1] + 2 bsy_r[x] +
+// bsy_r[x+1]:  g[y][x] += (D_{y-1} + T_{y-1}) + 2 D_y + (D_{y+1} - T_{y+1}).  The replicate padding folds what would
+// leave the image back onto the border, which is the same as extending bs by reflection: bsx odd / bsy even across a
+// vertical border, bsx even / bsy odd across a horizontal one.
 __global__ void __launch_bounds__(256) sobel_unit_bwd_kernel(const float* __restrict__ img, const float* __restrict__ ggx,
                                                              const float* __restrict__ ggy, float* __restrict__ g_img,
                                                              int planes, int H, int W) {
-  const int x = blockIdx.x * 32 + (threadIdx.x & 31);
-  const int y = blockIdx.y * 8 + (threadIdx.x >> 5);
-  if (x >= W || y >= H) return;
-  const int xl = max(x - 1, 0), xr = min(x + 1, W - 1), yt = max(y - 1, 0) * W, ym = y * W, yb = min(y + 1, H - 1) * W;
+  __shared__ float sbx[10][35], sby[10][35];
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const int x0 = blockIdx.x * 32, y0 = blockIdx.y * 8;
+  const int x = x0 + tx, y = y0 + ty;
   for (int pl = blockIdx.z; pl < planes; pl += gridDim.z) {
     const size_t base = (size_t)pl * H * W;
     const float* q = img + base;
-    const float a = __ldg(q + yt + xl), b = __ldg(q + yt + x), c = __ldg(q + yt + xr);
-    const float d = __ldg(q + ym + xl), f = __ldg(q + ym + xr);
-    const float g = __ldg(q + yb + xl), h = __ldg(q + yb + x), i = __ldg(q + yb + xr);
-    const float sx = (c - a) + 2.f * (f - d) + (i - g);
-    const float sy = (g - a) + 2.f * (h - b) + (i - c);
-    const float n = rsqrtf(fmaf(sx, sx, fmaf(sy, sy, 1e-8f)));
-    const float gx = __ldg(ggx + base + ym + x), gy = __ldg(ggy + base + ym + x);
-    const float dot = (sx * gx + sy * gy) * n * n * n;
-    const float bsx = fmaf(-dot, sx, n * gx), bsy = fmaf(-dot, sy, n * gy);
-    if (bsx == 0.f && bsy == 0.f) continue;
-    float* o = g_img + base;
-    atomicAdd(o + yt + xl, -bsx - bsy);
-    atomicAdd(o + yt + x, -2.f * bsy);
-    atomicAdd(o + yt + xr, bsx - bsy);
-    atomicAdd(o + ym + xl, -2.f * bsx);
-    atomicAdd(o + ym + xr, 2.f * bsx);
-    atomicAdd(o + yb + xl, -bsx + bsy);
-    atomicAdd(o + yb + x, 2.f * bsy);
-    atomicAdd(o + yb + xr, bsx + bsy);
+    for (int i = threadIdx.x; i < 10 * 34; i += 256) {
+      const int hy = i / 34, hx = i - hy * 34;
+      const int gy = y0 - 1 + hy, gx = x0 - 1 + hx;
+      const int cy = min(max(gy, 0), H - 1), cx = min(max(gx, 0), W - 1);
+      float bx = 0.f, by = 0.f;
+      if (gy <= H && gx <= W) {      // (positions further out than the one-pixel fold feed no pixel of the image)
+        const int xl = max(cx - 1, 0), xr = min(cx + 1, W - 1), yt = max(cy - 1, 0) * W, ym = cy * W, yb = min(cy + 1, H - 1) * W;
+        const float a = __ldg(q + yt + xl), b = __ldg(q + yt + cx), c = __ldg(q + yt + xr);
+        const float d = __ldg(q + ym + xl), f = __ldg(q + ym + xr);
+        const float g = __ldg(q + yb + xl), h = __ldg(q + yb + cx), k = __ldg(q + yb + xr);
+        const float sx = (c - a) + 2.f * (f - d) + (k - g);
+        const float sy = (g - a) + 2.f * (h - b) + (k - c);
+        const float n = rsqrtf(fmaf(sx, sx, fmaf(sy, sy, 1e-8f)));
+        const float gx_ = __ldg(ggx + base + ym + cx), gy_ = __ldg(ggy + base + ym + cx);
+        const float dot = (sx * gx_ + sy * gy_) * n * n * n;
+        bx = fmaf(-dot, sx, n * gx_);
+        by = fmaf(-dot, sy, n * gy_);
+        if (gx != cx) bx = -bx;      // reflection across a vertical border
+        if (gy != cy) by = -by;      // ... across a horizontal border
+      }
+      sbx[hy][hx] = bx;
+      sby[hy][hx] = by;
+    }
+    __syncthreads();
+    if (x < W && y < H) {
+      float acc = 0.f;
+#pragma unroll
+      for (int r = 0; r < 3; ++r) {
+        const float D = sbx[ty + r][tx] - sbx[ty + r][tx + 2];
+        const float T = sby[ty + r][tx] + 2.f * sby[ty + r][tx + 1] + sby[ty + r][tx + 2];
+        acc += (r == 0) ? (D + T) : (r == 1) ? 2.f * D : (D - T);
+      }
+      g_img[base + (size_t)y * W + x] += acc;
+    }
+    __syncthreads();
   }
 }
 
