@@ -52,7 +52,7 @@ WORKLOADS = {
 N_LEVELS, ITERS = 4, 3
 ROOFLINE_BATCHES = 8          # batches per launch of the roofline pass (what the committed ncu capture ran; 20 per launch measure
                               # 55.7 us per batch-iteration under ncu and 58 us back to back under the power cap, profiles/r2/r2b_*)
-NCU_SUMMARY = os.path.join(ROOT, "profiles", "r2", "r2_uic_queue_kernel_level0_G8.txt")
+NCU_SUMMARY = os.path.join(ROOT, "profiles", "r2", "r2b_uic_queue_kernel_onemap_level0_G8.txt")
 
 
 def algorithmic_bytes(B, C, H, W, levels=N_LEVELS, iters=ITERS):
@@ -328,7 +328,9 @@ def run_tum(args, wl, rank, world, dev, barrier, max_over_ranks):
     barrier()
     ms = max_over_ranks(e0.elapsed_time(e1), dev)
     res.raise_if_bad()
-    launches_per_call = 2 + 3 * ITERS + 4          # init, sigma0 extremes, 9 coarse iterations; extremes init + extremes, queue init, queue kernel
+    # kernels of one call: sigma replication check, init, sigma0 extremes of all levels, 3 + 3 iterations of the two coarsest
+    # levels, 3 x 2 twin launches of the 60x80 level, queue init and the two twins of the work-queue kernel
+    launches_per_call = 1 + 2 + 2 * ITERS + 2 * ITERS + 1 + 2
 
     # ---- latency of ONE batch alone (launch-per-iteration kernels, one stream)
     one = [take(*s, B) for s in sets]
@@ -344,19 +346,23 @@ def run_tum(args, wl, rank, world, dev, barrier, max_over_ranks):
     pose_l0 = A.unpack_pose(full.pose_hist[(N_LEVELS - 1) * ITERS])
     fine = [take(*s, B * ROOFLINE_BATCHES)[0][-1] for s in sets]
 
-    def fine_launch(i):
-        return A.uic_solve([fine[i % S]], pose_l0, iters=ITERS, remove_tru_sigma=True, group=B, queue=True)
+    def fine_launch(i, **kw):
+        return A.uic_solve([fine[i % S]], pose_l0, iters=ITERS, remove_tru_sigma=True, group=B, queue=True, **kw)
     for i in range(3):
         fine_launch(i)
     torch.cuda.synchronize()
     call_ms = statistics.mean(event_time_ms(lambda i=i: fine_launch(i), main) for i in range(max(3, min(K, 10))))
-    # the kernel alone: CUDA events recorded by the library right before / after the work-queue kernel's launch
-    timed = [A.uic_solve([fine[i % S]], pose_l0, iters=ITERS, remove_tru_sigma=True, group=B, queue=True, timed=True)
-             for i in range(max(3, min(K, 10)))]
+    # the kernel alone: CUDA events recorded by the library right before / after the work-queue kernel's launch (with the
+    # replication check on, around its two twin launches, of which the one that does not apply returns at once)
+    timed = [fine_launch(i, timed=True) for i in range(max(3, min(K, 10)))]
     ev = [r.queue_kernel_ms[0] for r in timed]
     launch_ms = statistics.mean(ev)
     stamps = timed[0].launch_ms
     assert (fine_launch(0).pose_hist[-1] - full.pose_hist[-1]).abs().max().item() < 1e-5   # the timed launch does the real work
+    # the same level with the check off: the C-map tile routine (what sigma tensors with independent channels run)
+    cmap = [fine_launch(i, timed=True, tuning=dict(sigma_detect=1)) for i in range(max(3, min(K, 10)))]
+    cmap_ms = statistics.mean(r.queue_kernel_ms[0] for r in cmap)
+    assert (cmap[0].pose_hist[-1] - full.pose_hist[-1]).abs().max().item() < 1e-5
 
     # ---- parity of this very run (first batch of the first set) against the CPU oracle
     parity = None
@@ -409,6 +415,10 @@ def run_tum(args, wl, rank, world, dev, barrier, max_over_ranks):
 
     peak, peak_src = measured_peak()
     achieved = ITERS * bytes_lvl0 * ROOFLINE_BATCHES / (launch_ms * 1e-3) / 1e9
+    # what the one-map routine reads per pixel: x0, x1 (C channels), ONE sigma0 / sigma1 map, both inverse depths
+    bytes_read_lvl0 = (2 * C + 4) * 4 * H * W * B
+    achieved_read = ITERS * bytes_read_lvl0 * ROOFLINE_BATCHES / (launch_ms * 1e-3) / 1e9
+    achieved_cmap = ITERS * bytes_lvl0 * ROOFLINE_BATCHES / (cmap_ms * 1e-3) / 1e9
     traffic = ncu_traffic(NCU_SUMMARY)
     return {
         "value": world * B * K / (ms * 1e-3), "ms_per_step": ms / K,
@@ -418,6 +428,9 @@ def run_tum(args, wl, rank, world, dev, barrier, max_over_ranks):
                                    "one graph per input set, captured during warm-up)",
                        coarse_levels="one launch per Gauss-Newton iteration (uic_iter_staged_kernel / uic_iter_kernel), all batches of a call in one grid",
                        finest_level="one work-queue launch for its 3 iterations (uic_queue_kernel, per-pair dependencies)",
+                       sigma="(B,C,H,W) tensors holding C copies of one map per frame, as the reference's encoder emits them; a device-side "
+                             "check per call finds that (one read of the sigma tensors, inside the timed region) and the one-map tile "
+                             "routines run (options.sigma_detect)",
                        sigma_extremes="per batch of 64 (options.group): the results of separate reference calls",
                        l2=f"every stream owns a set of {n_stack} batches ({set_bytes / 1e6:.0f} MB each, > 126 MB L2 per call); "
                           f"sets differ in addresses and pair order",
@@ -428,10 +441,20 @@ def run_tum(args, wl, rank, world, dev, barrier, max_over_ranks):
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                      "traffic": traffic,
                      "traffic_source": "ncu --set full dram__bytes_read.sum + dram__bytes_write.sum of the same launch "
-                                       "(8 batches): profiles/r2/r2_uic_queue_kernel_level0_G8.txt",
-                     "kernel": "uic_queue_kernel<true,false,false,160,120,1>: the finest level (120x160) of "
-                               f"{ROOFLINE_BATCHES} batches of {B} pairs, its {ITERS} Gauss-Newton iterations in one launch",
+                                       f"(8 batches): {os.path.relpath(NCU_SUMMARY, ROOT)}",
+                     "kernel": "uic_queue_kernel<true,true,false,0,0,1>: the finest level (120x160) of "
+                               f"{ROOFLINE_BATCHES} batches of {B} pairs, its {ITERS} Gauss-Newton iterations in one launch, ONE-MAP tile "
+                               "routine: the (B,C,H,W) sigma tensors of the workload are C copies of one map (as the reference's encoder "
+                               "emits them, SURVEY 8d), sigma_replication_kernel finds that on the device and this twin of the launch runs",
                      "algorithmic_bytes_per_launch": ITERS * bytes_lvl0 * ROOFLINE_BATCHES, "launch_ms": launch_ms,
+                     "algorithmic_note": "achieved / frac use SURVEY 8(d)'s (4C+2)*4 bytes per pixel and iteration; this kernel reads "
+                                         "(2C+4)*4 of them (x0, x1, one sigma0 / sigma1 map, inverse depths): see bytes_read_*",
+                     "bytes_read_per_launch": ITERS * bytes_read_lvl0 * ROOFLINE_BATCHES,
+                     "bytes_read_GBps": achieved_read, "bytes_read_frac": achieved_read / peak,
+                     "c_map_kernel": {"kernel": "uic_queue_kernel<true,false,false,160,120,1> (options.sigma_detect = 1: every sigma "
+                                                "channel read, what tensors with independent channels run)",
+                                      "launch_ms": cmap_ms, "achieved": achieved_cmap, "frac": achieved_cmap / peak,
+                                      "ncu": "profiles/r2/r2_uic_queue_kernel_level0_G8.txt"},
                      "launch_ms_all": [round(x, 4) for x in ev],
                      "iteration_ms_device_stamps": [round(x, 4) for x in stamps],
                      "per_batch_iteration_us": launch_ms * 1e3 / (ITERS * ROOFLINE_BATCHES),

@@ -67,7 +67,7 @@ class DpftUicOptions(ctypes.Structure):
         ("launch_ms", ctypes.POINTER(ctypes.c_float)),
         ("icp_weight", ctypes.c_void_p * DPFT_MAX_LEVELS),
         ("queue_kernel_ms", ctypes.POINTER(ctypes.c_float)),
-        ("small_levels", ctypes.c_int32), ("reserved_", ctypes.c_int32),
+        ("small_levels", ctypes.c_int32), ("sigma_detect", ctypes.c_int32),
     ]
 
     def __init__(self, **kw):

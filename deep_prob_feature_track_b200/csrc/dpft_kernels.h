@@ -59,6 +59,9 @@ struct QLevel {
 struct QueueParams {
   QLevel L;
   int iters, B, C, SC;
+  int SCm;                           // channels of sigma0 / sigma1 in memory (C or 1); SC == 1 with SCm == C: read channel 0
+  const int* mism;                   // device flag written by sigma_replication_kernel (0: every channel of sigma0 and
+  int rep_role;                      //  sigma1 equals channel 0); role 1 runs only if it is 0, role 2 only if not, 0 always
   int group, n_groups;               // pairs per sigma-extreme group (the reference's batch), groups in this call
   int n_mm_groups;                   // groups of the sigma0 extremes (1 with a shared keyframe)
   int kf_shared;

@@ -78,7 +78,10 @@ struct UicIterParams {
   float* partials;       // (B, ctas_per_pair, PS)
   double* pairrec;       // (B, PS)
   int* counters;         // [B] per pair, then [n_groups] pairs done per sigma-extreme group
-  int SC;                // channels of sigma0 / sigma1: C, or 1 (DPFT_SIGMA_BROADCAST)
+  int SC;                // channels of sigma0 / sigma1 the kernel works with: C, or 1 (one map per frame)
+  int SCm;               // channels of sigma0 / sigma1 in MEMORY: SC, or C when SC == 1 reads channel 0 of full tensors
+  const int* mism;       // device flag of sigma_replication_kernel: 0 = every channel of sigma0 / sigma1 equals channel 0
+  int rep_role;          // 0: no twin launches; 1: this launch works only if *mism == 0; 2: only if *mism != 0
   const uint32_t* s0mm;  // order-encoded min, max of sigma0 over the level tensor of every group: (n_mm_groups, 2)
   float* gmm;            // (n_groups, 4) group-wide min/max of the warped sigma of this iteration, min/max of sigma0
   int32_t* status;
@@ -384,7 +387,8 @@ __global__ void __launch_bounds__(kThreads, RES ? kResMinCtas : DPFT_MIN_CTAS) u
   const size_t po = (size_t)b * p.C * plane;
   const size_t b0 = p.kf_shared ? 0 : (size_t)b;      // one keyframe for the whole batch (kf_vo-style tracking)
   g.x0 = p.x0 + b0 * p.C * plane; g.x1 = p.x1 + po;
-  g.s0 = p.s0 + b0 * p.SC * plane; g.s1 = p.s1 + (size_t)b * p.SC * plane;
+  g.s0 = p.s0 + b0 * p.SCm * plane; g.s1 = p.s1 + (size_t)b * p.SCm * plane;
+  g.scm = p.SCm;
   g.splane = (p.SC == p.C) ? (unsigned)plane : 0u;
   g.d0 = p.d0 + b0 * plane; g.d1 = p.d1 + (size_t)b * plane;
   g.m0 = p.m0 ? p.m0 + b0 * plane : nullptr;
@@ -404,7 +408,7 @@ __global__ void __launch_bounds__(kThreads, RES ? kResMinCtas : DPFT_MIN_CTAS) u
     // x1 | sigma1 | invd1 of this pair, contiguous in that order: 16-byte copies when the planes allow it
     const unsigned dst0 = (unsigned)__cvta_generic_to_shared(dyn_live);
     const float* src[3] = {g.x1, g.s1, g.d1};
-    const int cnt[3] = {p.C * plane, p.SC * plane, plane};
+    const int cnt[3] = {p.C * plane, p.SCm * plane, plane};
     const bool v16 = (plane % 4 == 0) && ((((uintptr_t)g.x1 | (uintptr_t)g.s1 | (uintptr_t)g.d1) & 15u) == 0);
     int off = 0;
 #pragma unroll
@@ -424,6 +428,8 @@ __global__ void __launch_bounds__(kThreads, RES ? kResMinCtas : DPFT_MIN_CTAS) u
   cudaGridDependencySynchronize();
   DPFT_STAMP(1, threadIdx.x == 0 && blockIdx.x == 0 && b == 0);
   if (RES) asm volatile("cp.async.wait_group 0;" ::: "memory");
+  // full sigma tensors whose channels are copies of channel 0 (found on the device): read the one map, C times less
+  if (p.mism && p.rep_role == 0 && __ldcg(p.mism) == 0) g.splane = 0u;
   if (threadIdx.x < 12) s_pose[threadIdx.x] = __ldcg(p.pose + (size_t)b * 12 + threadIdx.x);
   if (TRU) {
     const uint32_t* mm = p.s0mm + (p.n_mm_groups > 1 ? 2 * (b / p.group) : 0);
@@ -479,7 +485,8 @@ __global__ void __launch_bounds__(kSThreads, DPFT_STAGED_CTAS) uic_iter_staged_k
   const size_t po = (size_t)b * p.C * plane;
   const size_t b0 = p.kf_shared ? 0 : (size_t)b;      // one keyframe for the whole batch (kf_vo-style tracking)
   g.x0 = p.x0 + b0 * p.C * plane; g.x1 = p.x1 + po;
-  g.s0 = p.s0 + b0 * p.SC * plane; g.s1 = p.s1 + (size_t)b * p.SC * plane;
+  g.s0 = p.s0 + b0 * p.SCm * plane; g.s1 = p.s1 + (size_t)b * p.SCm * plane;
+  g.scm = p.SCm;
   g.splane = (p.SC == p.C) ? (unsigned)plane : 0u;
   g.d0 = p.d0 + b0 * plane; g.d1 = p.d1 + (size_t)b * plane;
   g.m0 = p.m0 ? p.m0 + b0 * plane : nullptr;
@@ -503,6 +510,10 @@ __global__ void __launch_bounds__(kSThreads, DPFT_STAGED_CTAS) uic_iter_staged_k
   cudaTriggerProgrammaticLaunchCompletion();
   cudaGridDependencySynchronize();
   DPFT_STAMP(1, threadIdx.x == 0 && blockIdx.x == 0 && b == 0);   // previous launch complete
+  // twin launches (one uncertainty map / C maps) for full sigma tensors: only the twin that matches what
+  // sigma_replication_kernel found works; the other one has waited for its predecessor (so the chain of
+  // programmatic dependencies stays transitive) and leaves
+  if (p.rep_role && ((__ldcg(p.mism) == 0) != (p.rep_role == 1))) return;
   if (threadIdx.x < 12) s_pose[threadIdx.x] = __ldcg(p.pose + (size_t)b * 12 + threadIdx.x);
   if (TRU) {
     const uint32_t* mm = p.s0mm + (p.n_mm_groups > 1 ? 2 * (b / p.group) : 0);
@@ -803,6 +814,61 @@ __global__ void occ_fixup_kernel(uint8_t* __restrict__ occ, const float* __restr
 
 // --------------------------------------------------------------------------- host side
 // What dpft_uic_options_t carries, with the defaults filled in (no environment variables, no process state).
+// Are the C channels of every sigma0 / sigma1 tensor of the call copies of channel 0?  That is what the reference's
+// encoder produces: ONE uncertainty map per frame, repeated to C channels before the tracker sees it
+// (algorithms.py:1425-1427, uncertainty_channel = 1 in every shipped configuration).  The kernels then read the one map
+// (the DPFT_SIGMA_BROADCAST tile routines with the full tensors' pair stride): same values, C times fewer loads,
+// blends, Sobel responses and normalisations of sigma.  Decided on the device -- no host synchronisation, and a CUDA
+// graph of the call stays valid when its buffers are refilled with other data: *mism is 0 on entry and set to 1 by any
+// thread that finds a channel differing (bitwise) from channel 0.
+struct RepTensors {
+  const float* p[2 * DPFT_MAX_LEVELS];
+  unsigned plane[2 * DPFT_MAX_LEVELS];             // elements per channel plane
+  unsigned units[2 * DPFT_MAX_LEVELS];             // work units of the tensor: pairs * ceil(plane / 4)
+  unsigned first[2 * DPFT_MAX_LEVELS + 1];         // prefix sums of `units`
+  int n;
+};
+// One unit = four consecutive pixels of one pair: all C channels are loaded (16 bytes each when the plane allows it)
+// before anything is compared, so a thread keeps C independent loads in flight.
+template <int CT>
+__global__ void __launch_bounds__(256) sigma_replication_kernel(const RepTensors t, const int C, int* __restrict__ mism) {
+  const unsigned total = t.first[t.n];
+  unsigned diff = 0u;
+  int round = 0;
+  for (unsigned u = blockIdx.x * 256u + threadIdx.x; u < total; u += gridDim.x * 256u) {
+    int ti = 0;
+#pragma unroll
+    for (int k = 1; k < 2 * DPFT_MAX_LEVELS; ++k) ti += (k < t.n && u >= t.first[k]) ? 1 : 0;
+    const unsigned plane = t.plane[ti], cpp = (plane + 3u) / 4u;
+    const unsigned w = u - t.first[ti];
+    const unsigned pair = w / cpp, ch = w - pair * cpp;
+    const float* r = t.p[ti] + (size_t)pair * C * plane + 4u * ch;
+    if ((plane & 3u) == 0u && ((uintptr_t)t.p[ti] & 15u) == 0u) {
+      const uint4 v0 = __ldg(reinterpret_cast<const uint4*>(r));
+      if (CT > 0) {
+        uint4 v[CT > 0 ? CT : 1];
+#pragma unroll
+        for (int c = 1; c < CT; ++c) v[c] = __ldg(reinterpret_cast<const uint4*>(r + (size_t)c * plane));
+#pragma unroll
+        for (int c = 1; c < CT; ++c) diff |= (v[c].x ^ v0.x) | (v[c].y ^ v0.y) | (v[c].z ^ v0.z) | (v[c].w ^ v0.w);
+      } else {
+        for (int c = 1; c < C; ++c) {
+          const uint4 a = __ldg(reinterpret_cast<const uint4*>(r + (size_t)c * plane));
+          diff |= (a.x ^ v0.x) | (a.y ^ v0.y) | (a.z ^ v0.z) | (a.w ^ v0.w);
+        }
+      }
+    } else {
+      const unsigned left = min(4u, plane - 4u * ch);
+      for (unsigned e = 0; e < left; ++e) {
+        const unsigned v0 = __float_as_uint(__ldg(r + e));
+        for (int c = 1; c < C; ++c) diff |= __float_as_uint(__ldg(r + (size_t)c * plane + e)) ^ v0;
+      }
+    }
+    if (((++round) & 7) == 0 && (diff || *(volatile int*)mism)) break;      // somebody found a difference: no need to go on
+  }
+  if (diff) *mism = 1;
+}
+
 struct Tuning {
   int group = 0;                          // pairs per sigma-extreme group (queue path); 0 = B
   int tile_rows[DPFT_MAX_LEVELS] = {};    // queue path: rows per tile, 0 = chosen
@@ -812,6 +878,8 @@ struct Tuning {
   int tiling = 0;                         // 0 dealt, 1 rectangular, 2 linear
   bool generic_geometry = false;
   bool no_resident = false;       // measurement knob: small levels on the plain (global-memory lookup) kernel
+  bool no_sigma_detect = false;   // do not look for full sigma tensors whose channels are copies of channel 0
+  const int* mism = nullptr;      // internal: device flag of sigma_replication_kernel for this call (run_uic sets it)
   float* launch_ms = nullptr;
   float* queue_kernel_ms = nullptr;
   const float* icp_weight[DPFT_MAX_LEVELS] = {};   // per level: (B,1,H,W) scale of the ICP term, or nullptr (scalar w_icp)
@@ -831,6 +899,7 @@ static Tuning tuning_of(const dpft_uic_options_t* o) {
   t.queue_kernel_ms = o->launch_ms ? o->queue_kernel_ms : nullptr;
   for (int l = 0; l < DPFT_MAX_LEVELS; ++l) t.icp_weight[l] = o->icp_weight[l];
   t.no_resident = o->small_levels == 1;
+  t.no_sigma_detect = o->sigma_detect == 1;
   return t;
 }
 
@@ -1334,6 +1403,7 @@ static int run_queue(const dpft_level_t& L, int level_index, int B, int C, int i
   v.H = L.H; v.W = L.W; v.nseg = q.nseg; v.TR = q.TR; v.nrt = q.nrt; v.tpp = q.tpp; v.kind = q.kind;
   prm.iters = iters; prm.B = B; prm.C = C;
   prm.SC = (flags & DPFT_SIGMA_BROADCAST) ? 1 : C;
+  prm.SCm = prm.SC; prm.mism = (prm.SC == C) ? tun.mism : nullptr; prm.rep_role = 0;
   prm.group = G.group; prm.n_groups = G.n_groups; prm.n_mm_groups = G.n_mm_groups;
   prm.kf_shared = (flags & DPFT_SHARED_KEYFRAME) ? 1 : 0;
   prm.total_items = (unsigned)q.total_items;
@@ -1385,7 +1455,9 @@ static int run_queue(const dpft_level_t& L, int level_index, int B, int C, int i
   return 0;
 }
 
-// Workspace of a call: [launch-per-iteration plan of the levels it serves | work-queue plan of the finest level].
+// Workspace of a call: [launch-per-iteration plan of the levels it serves | work-queue plan of the finest level | the
+// flag of sigma_replication_kernel].
+constexpr size_t kRepFlagBytes = 256;
 static size_t lpi_bytes(const dpft_level_t* levels, int n_levels, int B, int C, uint32_t flags, bool any_occ, const Tuning& tun) {
   if (n_levels < 1) return 0;
   const Groups G = groups_of(B, flags, tun);
@@ -1404,9 +1476,9 @@ extern "C" size_t dpft_uic_workspace_bytes_ex(const dpft_level_t* levels, int n_
     const int nc = n_levels - std::min(n_levels, std::max(1, tun.queue_levels));
     size_t q = 0;                                     // the queue launches run one after the other: one region
     for (int l = nc; l < n_levels; ++l) q = std::max(q, make_qplan(levels[l], l, B, C, iters, flags, tun).total);
-    return lpi_bytes(levels, nc, B, C, flags, any_occ, tun) + q;
+    return lpi_bytes(levels, nc, B, C, flags, any_occ, tun) + q + kRepFlagBytes;
   }
-  return lpi_bytes(levels, n_levels, B, C, flags, any_occ, tun);
+  return lpi_bytes(levels, n_levels, B, C, flags, any_occ, tun) + kRepFlagBytes;
 }
 
 extern "C" size_t dpft_uic_workspace_bytes(const dpft_level_t* levels, int n_levels, int B, int C, int iters,
@@ -1529,6 +1601,7 @@ static int run_lpi(const dpft_level_t* levels, int n_levels, int B, int C, int i
       prm.occ_out = L.occ_out ? L.occ_out + (size_t)it * B * plane : nullptr;
       prm.sr0_dbg = sr0;
       prm.H = L.H; prm.W = L.W; prm.B = B; prm.C = C; prm.SC = SC;
+      prm.SCm = SC; prm.mism = (fused && SC == C) ? tun.mism : nullptr; prm.rep_role = 0;
       prm.nseg = pl.nseg[l]; prm.nrt = pl.nrt[l]; prm.TR = pl.TR[l];
       prm.ctas_per_pair = fused ? pl.ctas[l] : pl.px_ctas[l];
       prm.tab = pl.tab[l];
@@ -1559,7 +1632,16 @@ static int run_lpi(const dpft_level_t* levels, int n_levels, int B, int C, int i
           default: err = launch_px<1>(prm, ex, grid, tru, use_pdl, stream); break;
         }
       } else if ((flags & DPFT_STAGED_FOOTPRINT) && staged_ok(L, C)) {
-        err = launch_staged(prm, grid, tru, use_pdl, stream, tun);
+        if (prm.mism) {
+          // full sigma tensors, replication decided on the device: the one-map twin, then the C-map twin
+          UicIterParams one = prm;
+          one.SC = 1; one.rep_role = 1;
+          err = launch_staged(one, grid, tru, use_pdl, stream, tun);
+          prm.rep_role = 2;
+          if (err == cudaSuccess) err = launch_staged(prm, grid, tru, use_pdl, stream, tun);
+        } else {
+          err = launch_staged(prm, grid, tru, use_pdl, stream, tun);
+        }
       } else
       switch (CH) {
         case 8: err = launch_iter<8>(prm, grid, tru, use_pdl, stream, tun, pl.res_smem[l]); break;
@@ -1615,7 +1697,9 @@ static int lpi_timed(const dpft_level_t* levels, int n_levels, int B, int C, int
 // work queue.
 static int run_uic(const dpft_level_t* levels, int n_levels, int B, int C, int iters, uint32_t flags, float w_icp,
                    const float* pose_in, float* pose_hist, float* sys_hist, float* aux_hist, int32_t* status,
-                   void* workspace, size_t workspace_bytes, void* stream, const Tuning& tun) {
+                   void* workspace, size_t workspace_bytes, void* stream, const Tuning& tun_in) {
+  Tuning tun = tun_in;
+  tun.mism = nullptr;
   if (iters > 64) return set_error(DPFT_EINVAL, "iters must be <= 64");
   if (int e = check_args(levels, n_levels, B, C, iters, flags)) return e;
   if (int e = check_group(levels, n_levels, B, flags, tun)) return e;
@@ -1625,7 +1709,46 @@ static int run_uic(const dpft_level_t* levels, int n_levels, int B, int C, int i
   bool any_occ = false;
   for (int l = 0; l < n_levels; ++l) any_occ = any_occ || levels[l].occ_out;
   float* ms = tun.launch_ms;
-  if (!queue_wanted(C, iters, flags, any_occ)) {
+  const bool use_queue = queue_wanted(C, iters, flags, any_occ);
+  if ((flags & DPFT_FUSED_SOBEL) && ((flags & DPFT_LAUNCH_PER_ITERATION) || use_queue) && C > 1 && iters >= 1 &&
+      !(flags & (DPFT_SIGMA_BROADCAST | DPFT_COMBINE_ICP)) && !any_occ && !tun.no_sigma_detect) {
+    // where the flag lives: behind everything else the call uses
+    size_t used;
+    if (use_queue) {
+      const int nc0 = n_levels - std::min(n_levels, std::max(1, tun.queue_levels));
+      size_t q = 0;
+      for (int l = nc0; l < n_levels; ++l) q = std::max(q, make_qplan(levels[l], l, B, C, iters, flags, tun).total);
+      used = lpi_bytes(levels, nc0, B, C, flags, any_occ, tun) + q;
+    } else {
+      used = lpi_bytes(levels, n_levels, B, C, flags, any_occ, tun);
+    }
+    if (workspace_bytes < used + kRepFlagBytes)
+      return set_error(DPFT_ENOSPACE, "workspace has %zu bytes, %zu needed", workspace_bytes, used + kRepFlagBytes);
+    int* mism = (int*)((char*)workspace + used);
+    RepTensors rt{};
+    const size_t Bk = (flags & DPFT_SHARED_KEYFRAME) ? 1 : (size_t)B;
+    unsigned long long units = 0;
+    for (int l = 0; l < n_levels; ++l) {
+      const unsigned plane = (unsigned)(levels[l].H * levels[l].W), cpp = (plane + 3) / 4;
+      const float* tp[2] = {levels[l].sigma0, levels[l].sigma1};
+      const size_t np[2] = {Bk, (size_t)B};
+      for (int k = 0; k < 2; ++k) {
+        rt.p[rt.n] = tp[k]; rt.plane[rt.n] = plane; rt.units[rt.n] = (unsigned)(np[k] * cpp);
+        rt.first[rt.n] = (unsigned)units;
+        units += np[k] * cpp;
+        ++rt.n;
+      }
+    }
+    rt.first[rt.n] = (unsigned)units;
+    if (units < (1ull << 32)) {     // (larger calls simply go without the check)
+      cudaMemsetAsync(mism, 0, sizeof(int), (cudaStream_t)stream);
+      const unsigned gx = (unsigned)std::min<unsigned long long>((units + 255) / 256, 148ull * 16);
+      if (C == 8) sigma_replication_kernel<8><<<gx, 256, 0, (cudaStream_t)stream>>>(rt, C, mism);
+      else sigma_replication_kernel<0><<<gx, 256, 0, (cudaStream_t)stream>>>(rt, C, mism);
+      tun.mism = mism;
+    }
+  }
+  if (!use_queue) {
     if (ms)
       return lpi_timed(levels, n_levels, B, C, iters, flags, w_icp, pose_in, pose_hist, sys_hist, aux_hist, status,
                        workspace, workspace_bytes, stream, tun, ms);

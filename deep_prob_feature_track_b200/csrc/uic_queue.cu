@@ -175,7 +175,8 @@ __device__ __forceinline__ bool q_walk_item(const QueueParams& p, float* area, c
   {
     const size_t b0 = p.kf_shared ? 0 : (size_t)b;      // one keyframe for every pair (kf_vo-style tracking)
     g.x0 = L.x0 + b0 * C * plane; g.x1 = L.x1 + (size_t)b * C * plane;
-    g.s0 = L.s0 + b0 * p.SC * plane; g.s1 = L.s1 + (size_t)b * p.SC * plane;
+    g.s0 = L.s0 + b0 * p.SCm * plane; g.s1 = L.s1 + (size_t)b * p.SCm * plane;
+    g.scm = p.SCm;
     g.splane = (p.SC == C) ? (unsigned)plane : 0u;
     g.d0 = L.d0 + b0 * plane; g.d1 = L.d1 + (size_t)b * plane;
     g.m0 = (AUX && L.m0) ? L.m0 + b0 * plane : nullptr;
@@ -373,6 +374,9 @@ __global__ void __launch_bounds__(kQThreads, kQCtasPerSm) uic_queue_kernel(const
   extern __shared__ __align__(128) float q_dyn[];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   float* area = q_dyn + warp * kQAreaFloats;
+  // Twin launches for full sigma tensors whose channels may be copies of channel 0 (QueueParams::mism): only the twin
+  // whose tile routine matches what sigma_replication_kernel found does the work, the other leaves the queue alone.
+  if (p.rep_role && ((__ldcg(p.mism) == 0) != (p.rep_role == 1))) return;
   // Workers stay until the queue is exhausted (one CTA per resident slot).  Workers that leave after a few items, so
   // that retiring CTAs let the kernels of other streams in between, were measured and bought nothing
   // (profiles/r2/stream_probe_items.txt).
@@ -496,6 +500,9 @@ static cudaError_t launch_q(const QueueParams& prm, int grid, cudaStream_t strea
 
 int queue_tiles_per_sm() { return kQCtasPerSm * kQW; }
 
+static cudaError_t launch_queue_variant(const QueueParams& prm, bool tru, int grid, cudaStream_t stream, bool allow_fixed_geometry,
+                                        cudaEvent_t ev0, cudaEvent_t ev1);
+
 // `prm.s0mm` must already hold the level's sigma0 extremes (launch_minmax_levels); pose_in may be prm.pose_hist.
 cudaError_t launch_queue(const QueueParams& prm, const float* pose_in, bool tru, int grid, cudaStream_t stream,
                          bool allow_fixed_geometry, cudaEvent_t ev0, cudaEvent_t ev1) {
@@ -503,6 +510,24 @@ cudaError_t launch_queue(const QueueParams& prm, const float* pose_in, bool tru,
     const size_t n = std::max<size_t>(std::max<size_t>(prm.total_items, (size_t)prm.B * 12), (size_t)prm.iters * prm.n_groups);
     queue_init_kernel<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(prm, pose_in);
   }
+  const bool aux = prm.L.m0 || prm.L.m1;
+  const bool staged = prm.L.kind >= 1;
+  if (staged && prm.mism && prm.SC == prm.C && prm.rep_role == 0) {
+    // full sigma tensors, replication decided on the device: the one-map twin, then the C-map twin (one of them
+    // returns at once); the events bracket both
+    QueueParams one = prm, full = prm;
+    one.SC = 1; one.rep_role = 1;
+    full.rep_role = 2;
+    cudaError_t err = launch_queue_variant(one, tru, grid, stream, allow_fixed_geometry, ev0, nullptr);
+    if (err != cudaSuccess) return err;
+    return launch_queue_variant(full, tru, grid, stream, allow_fixed_geometry, nullptr, ev1);
+  }
+  return launch_queue_variant(prm, tru, grid, stream, allow_fixed_geometry, ev0, ev1);
+}
+
+// one launch of the kernel instantiation that serves prm (prm.SC == 1: one uncertainty map per frame)
+static cudaError_t launch_queue_variant(const QueueParams& prm, bool tru, int grid, cudaStream_t stream, bool allow_fixed_geometry,
+                                 cudaEvent_t ev0, cudaEvent_t ev1) {
   const bool sb = prm.SC != prm.C;
   const bool aux = prm.L.m0 || prm.L.m1;
   const bool staged = prm.L.kind >= 1;
@@ -514,6 +539,8 @@ cudaError_t launch_queue(const QueueParams& prm, const float* pose_in, bool tru,
   // the reference's TUM level 0 (160x120) runs a geometry-specialised tile routine
   if (allow_fixed_geometry && !sb && !aux && prm.L.W == 160 && prm.L.H == 120)
     return tru ? DPFT_Q(true, false, false, 160, 120, 1) : DPFT_Q(false, false, false, 160, 120, 1);
+  // (the one-map routine specialised for 160x120 measured 4 % SLOWER than its generic instantiation: 2760 against 2654 us
+  // for 20 batches, profiles/r2/r2b_sigma_detect_fixedgeo.txt -- not instantiated)
   if (tru) {
     if (sb) return aux ? DPFT_Q(true, true, true, 0, 0, 1) : DPFT_Q(true, true, false, 0, 0, 1);
     return aux ? DPFT_Q(true, false, true, 0, 0, 1) : DPFT_Q(true, false, false, 0, 0, 1);

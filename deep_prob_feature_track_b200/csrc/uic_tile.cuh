@@ -23,6 +23,8 @@ struct PairView {               // one frame pair of one level, pointers already
   int H, W, C;
   unsigned splane;              // channel stride of sigma0 / sigma1 in elements: H*W, or 0 when the uncertainty is ONE
                                 // map per frame that the reference would have repeated to C channels (alg:1425-1427)
+  int scm;                      // channels of sigma0 / sigma1 IN MEMORY (C, or 1): with splane == 0 and scm == C the
+                                // tensors are full but their channels were found to be copies of channel 0
   float fx, fy, cx, cy;
   float s0lo, s0hi;             // extremes of sigma0 over the whole level tensor (remove_tru_sigma)
   const void *tm_x1, *tm_s1, *tm_d1;   // tensor maps of the live frame's level tensors (TMA ring staging only)
@@ -111,7 +113,7 @@ __device__ __forceinline__ void process_tile(const PairView& g, const float* spo
     const float* S0 = g.s0 + (size_t)c0 * splane;
     const float* X1 = RES ? live + (unsigned)c0 * iplane : g.x1 + (size_t)c0 * iplane;
     const float* S1 = RES ? live + (unsigned)C * iplane + (unsigned)c0 * splane : g.s1 + (size_t)c0 * splane;
-    const float* D1 = RES ? live + (unsigned)(splane ? 2 * C : C + 1) * iplane : g.d1;
+    const float* D1 = RES ? live + (unsigned)(C + g.scm) * iplane : g.d1;
     if (!FIXED) { X0 = opaque(X0); S0 = opaque(S0); }
     if (!FIXED && !RES) { X1 = opaque(X1); S1 = opaque(S1); }
 

@@ -125,7 +125,12 @@ typedef struct dpft_uic_options {
                              the shared memory of a CTA twice per SM: 0 = stage it there and look the footprint up on
                              chip (the default), 1 = global-memory lookups as on any other level (a measurement knob;
                              same masks bit for bit, same sums up to the order of the fp32 partial sums).        */
-  int32_t reserved_;
+  int32_t sigma_detect;   /* full (B,C,H,W) sigma tensors whose C channels are copies of channel 0 -- what the reference's
+                             encoder hands over (alg:1425-1427) -- are found by a device-side check at the start of the call
+                             and served by the one-map tile routines (same results; no host synchronisation: kernels for
+                             both cases are enqueued and the ones that do not apply return at once).  0 = check (default;
+                             costs one read of the sigma tensors), 1 = do not check.  Fused kernels without
+                             DPFT_COMBINE_ICP and occ_out only.                                                   */
 } dpft_uic_options_t;
 
 /* ABI version of the loaded library (== DPFT_ABI_VERSION). */
