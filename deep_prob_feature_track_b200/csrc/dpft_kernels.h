@@ -78,7 +78,8 @@ struct QueueParams {
   int32_t* status;
   unsigned long long* t_done;        // optional (iters + 1) %globaltimer stamps: start, then every iteration complete
 };
-int queue_tiles_per_sm();            // resident workers (warps) per SM
+int queue_tiles_per_sm(bool one_map);   // resident workers (warps) per SM of the staged routine (one sigma map: a 4th CTA)
+// grid <= 0: as many CTAs as the device holds of the variant that runs
 // ev0 / ev1 (optional): events recorded on `stream` right before / after the work-queue kernel itself
 cudaError_t launch_queue(const QueueParams& prm, const float* pose_in, bool tru, int grid, cudaStream_t stream,
                          bool allow_fixed_geometry, cudaEvent_t ev0 = nullptr, cudaEvent_t ev1 = nullptr);

@@ -1349,7 +1349,9 @@ static QPlan make_qplan(const dpft_level_t& lv, int level_index, int B, int C, i
   QPlan q{};
   const Groups G = groups_of(B, flags, tun);
   const int sms = device_sms();
-  const long workers = (long)sms * queue_tiles_per_sm();
+  // (full sigma tensors whose channels turn out to be copies run the one-map twin: the tile height is shared by the
+  // twins, so it is chosen for the variant the flags announce)
+  const long workers = (long)sms * queue_tiles_per_sm((flags & DPFT_SIGMA_BROADCAST) != 0);
   const bool staged = (flags & DPFT_STAGED_FOOTPRINT) && staged_ok(lv, C);
   q.kind = staged ? 1 : 0;
   q.nseg = (lv.W + kCols - 1) / kCols;
@@ -1360,8 +1362,7 @@ static QPlan make_qplan(const dpft_level_t& lv, int level_index, int B, int C, i
   q.nrt = (lv.H + q.TR - 1) / q.TR;
   q.tpp = q.nseg * q.nrt;
   q.total_items = (size_t)iters * B * q.tpp;
-  const int full = sms * 3;
-  q.grid = tun.queue_ctas > 0 ? tun.queue_ctas : (int)std::min<long>(full, ((long)B * q.tpp + 3) / 4);
+  q.grid = tun.queue_ctas > 0 ? tun.queue_ctas : 0;      // 0: launch_queue sizes the grid per kernel variant
   size_t off = 0;
   auto take = [&](size_t bytes) {
     const size_t o = off;

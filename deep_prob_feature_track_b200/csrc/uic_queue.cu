@@ -49,14 +49,27 @@
 namespace dpft {
 
 constexpr int kQW = 4;                 // warps (workers) per CTA
-constexpr int kQThreads = kQW * 32;
+#ifndef DPFT_QW_SB
+#define DPFT_QW_SB 4                   // ... of the one-map staged routine (tuning hook)
+#endif
+__host__ __device__ constexpr int q_warps(bool sb, int kind) { return (sb && kind == 1) ? DPFT_QW_SB : kQW; }
+// Resident CTAs per SM: 3 (168 registers, 12 workers).  The one-map routine's 10-map ring would let a fourth CTA fit
+// by shared memory, and DPFT_Q_CTAS_SB=4 / DPFT_QW_SB / DPFT_Q_MAXNREG_SB build such variants -- all measured SLOWER
+// (profiles/r2/r2c_occupancy.txt): the register file is 16 K per scheduler, so between 12 and 16 workers per SM there is
+// nothing (144 registers still hold 3 warps per scheduler), and at 128 registers the row body spills ~30 accesses per
+// row whose lines no longer fit the 28-60 KB of L1 that 16 workers' shared memory leaves (3.60 against 2.66 ms).
+#ifndef DPFT_Q_CTAS_SB
+#define DPFT_Q_CTAS_SB 3
+#endif
 constexpr int kQCtasPerSm = 3;
+__host__ __device__ constexpr int q_ctas_per_sm(bool sb, int kind) { return (sb && kind == 1) ? DPFT_Q_CTAS_SB : kQCtasPerSm; }
 // per-worker shared memory: the staged routine's area (ring | corrections | outlier taps | halo sums), then the pose
-constexpr int kQAreaFloats = kStageAreaFloats + 32;
+__host__ __device__ constexpr int q_area_floats(bool sb) { return stage_area_floats(sb) + 32; }
 constexpr unsigned long long kWaitLimitNs = 4000000000ull;   // a worker that waits this long for an item traps
 constexpr unsigned long long kItemValid = 1ull << 63;
 
-static_assert(kStageWarpFloats - 27 * 33 >= 2 * PS, "the fold's fp64 scratch sits in front of the reduction rows");
+static_assert(stage_warp_floats(true) - 27 * 33 >= 2 * PS, "the fold's fp64 scratch sits in front of the reduction rows");
+static_assert(DPFT_QW_SB * q_area_floats(true) * 4 * DPFT_Q_CTAS_SB + 1024 * DPFT_Q_CTAS_SB <= 227 * 1024, "one-map CTAs per SM by shared memory");
 
 __device__ __forceinline__ unsigned long long q_encode(int k, int b, int t) {
   return kItemValid | ((unsigned long long)k << 44) | ((unsigned long long)b << 20) | (unsigned long long)t;
@@ -164,8 +177,9 @@ __device__ __forceinline__ void q_push_next(const QueueParams& p, const int k, c
 template <bool TRU, bool SB, bool AUX, int GW, int GH, int KIND>
 __device__ __forceinline__ bool q_walk_item(const QueueParams& p, float* area, const unsigned long long item) {
   const int lane = threadIdx.x & 31;
-  float (*redw)[33] = reinterpret_cast<float (*)[33]>(area + kStageWarpFloats - 27 * 33);   // rows 27.. follow the ring
-  float* spose = area + kStageAreaFloats;
+  constexpr int WF = stage_warp_floats(SB && KIND == 1);
+  float (*redw)[33] = reinterpret_cast<float (*)[33]>(area + WF - 27 * 33);   // rows 27.. follow the ring
+  float* spose = area + stage_area_floats(SB && KIND == 1);
   const int k = q_item_k(item), b = q_item_b(item), t = q_item_t(item);
   const int B = p.B, C = p.C;
   const QLevel& L = p.L;
@@ -208,7 +222,7 @@ __device__ __forceinline__ bool q_walk_item(const QueueParams& p, float* area, c
   {
     const int seg = t % L.nseg, rt = t / L.nseg;
     const int y0 = rt * L.TR, y1 = min(y0 + L.TR, L.H);
-    float* outl = area + kStageWarpFloats + 12 * 33;
+    float* outl = area + WF + 12 * 33;
     if (KIND == 1)
       process_tile_staged<TRU, SB, GW, GH, AUX>(g, spose, redw + 27, area, outl, seg, y0, y1, lane, S);
     else
@@ -370,10 +384,15 @@ __device__ __noinline__ void q_finish_pair(const QueueParams& p, float* area, co
 }
 
 template <bool TRU, bool SB, bool AUX, int GW, int GH, int KIND>
-__global__ void __launch_bounds__(kQThreads, kQCtasPerSm) uic_queue_kernel(const __grid_constant__ QueueParams p) {
+#ifdef DPFT_Q_MAXNREG_SB
+__global__ void __maxnreg__((SB && KIND == 1) ? DPFT_Q_MAXNREG_SB : 168) uic_queue_kernel(
+#else
+__global__ void __launch_bounds__(q_warps(SB, KIND) * 32, q_ctas_per_sm(SB, KIND)) uic_queue_kernel(
+#endif
+    const __grid_constant__ QueueParams p) {
   extern __shared__ __align__(128) float q_dyn[];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  float* area = q_dyn + warp * kQAreaFloats;
+  float* area = q_dyn + warp * q_area_floats(SB && KIND == 1);
   // Twin launches for full sigma tensors whose channels may be copies of channel 0 (QueueParams::mism): only the twin
   // whose tile routine matches what sigma_replication_kernel found does the work, the other leaves the queue alone.
   if (p.rep_role && ((__ldcg(p.mism) == 0) != (p.rep_role == 1))) return;
@@ -487,18 +506,23 @@ void launch_minmax_levels(const float* const* v, const size_t* per_group, int n_
 
 template <bool TRU, bool SB, bool AUX, int GW, int GH, int KIND>
 static cudaError_t launch_q(const QueueParams& prm, int grid, cudaStream_t stream, cudaEvent_t ev0, cudaEvent_t ev1) {
-  constexpr int smem = kQW * kQAreaFloats * (int)sizeof(float);
+  constexpr int smem = q_warps(SB, KIND) * q_area_floats(SB && KIND == 1) * (int)sizeof(float);
   auto* fn = uic_queue_kernel<TRU, SB, AUX, GW, GH, KIND>;
   // (cudaFuncSetAttribute is per device and cheap: set it on every launch rather than caching per process)
   cudaError_t err = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
   if (err != cudaSuccess) return err;
+#ifdef DPFT_Q_CARVEOUT_MAX
+  // (tuning hook: by default the driver picks the carve-out, which may hold fewer CTAs than the launch bounds name)
+  err = cudaFuncSetAttribute(fn, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+  if (err != cudaSuccess) return err;
+#endif
   if (ev0) cudaEventRecord(ev0, stream);
-  fn<<<grid, kQThreads, smem, stream>>>(prm);
+  fn<<<grid, q_warps(SB, KIND) * 32, smem, stream>>>(prm);
   if (ev1) cudaEventRecord(ev1, stream);
   return cudaGetLastError();
 }
 
-int queue_tiles_per_sm() { return kQCtasPerSm * kQW; }
+int queue_tiles_per_sm(bool one_map) { return q_ctas_per_sm(one_map, 1) * q_warps(one_map, 1); }
 
 static cudaError_t launch_queue_variant(const QueueParams& prm, bool tru, int grid, cudaStream_t stream, bool allow_fixed_geometry,
                                         cudaEvent_t ev0, cudaEvent_t ev1);
@@ -510,7 +534,6 @@ cudaError_t launch_queue(const QueueParams& prm, const float* pose_in, bool tru,
     const size_t n = std::max<size_t>(std::max<size_t>(prm.total_items, (size_t)prm.B * 12), (size_t)prm.iters * prm.n_groups);
     queue_init_kernel<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(prm, pose_in);
   }
-  const bool aux = prm.L.m0 || prm.L.m1;
   const bool staged = prm.L.kind >= 1;
   if (staged && prm.mism && prm.SC == prm.C && prm.rep_role == 0) {
     // full sigma tensors, replication decided on the device: the one-map twin, then the C-map twin (one of them
@@ -531,6 +554,14 @@ static cudaError_t launch_queue_variant(const QueueParams& prm, bool tru, int gr
   const bool sb = prm.SC != prm.C;
   const bool aux = prm.L.m0 || prm.L.m1;
   const bool staged = prm.L.kind >= 1;
+  if (grid <= 0) {     // what the device holds of THIS variant (the one-map routine fits a fourth CTA per SM)
+    int dev = 0, sms = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms < 1)
+      sms = 148;
+    const int qw = q_warps(sb, staged ? 1 : 0);
+    const long want = ((long)prm.B * prm.L.tpp + qw - 1) / qw;
+    grid = (int)std::max<long>(1, std::min<long>((long)sms * q_ctas_per_sm(sb, staged ? 1 : 0), want));
+  }
 #define DPFT_Q(TRUV, SBV, AUXV, w, h, KINDV) launch_q<TRUV, SBV, AUXV, w, h, KINDV>(prm, grid, stream, ev0, ev1)
   if (!staged) {   // levels the staged routine does not take (narrow, unaligned): the plain tile routine
     if (tru) return aux ? DPFT_Q(true, false, true, 0, 0, 0) : DPFT_Q(true, false, false, 0, 0, 0);

@@ -55,10 +55,17 @@ __device__ __forceinline__ const float* opaque(const float* p) {
   asm volatile("" : "+l"(p));
   return p;
 }
+// keyframe-side window loads: every element is read once per tile, so there is nothing for L1 to keep
+// (-DDPFT_WINDOW_LDCG: ld.global.cg, no L1 line allocated; a tuning hook, see profiles/r2/)
+#ifdef DPFT_WINDOW_LDCG
+#define DPFT_LDW(p) __ldcg(p)
+#else
+#define DPFT_LDW(p) __ldg(p)
+#endif
 __device__ __forceinline__ float ldf(const float* __restrict__ base, unsigned idx) {
   const float* q;
   asm("mad.wide.u32 %0, %1, 4, %2;" : "=l"(q) : "r"(idx), "l"(base));
-  return __ldg(q);
+  return DPFT_LDW(q);
 }
 __device__ __forceinline__ void ldf2(const float* __restrict__ base, unsigned idx, float& a, float& b) {
   const float* q;

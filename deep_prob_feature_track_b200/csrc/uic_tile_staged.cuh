@@ -45,6 +45,13 @@ constexpr int kStageLookahead = DPFT_STAGE_LOOKAHEAD;   // source rows requested
 // columns) then never share a bank
 constexpr int kStageSlotFloats = (kStageMaps * kStageWidth + 31) / 32 * 32;
 constexpr int kStageWarpFloats = kStageRows * kStageSlotFloats + 32;   // + x origin of each slot (as int)
+// One uncertainty map per frame (SB): a staged source row holds 10 maps (x1[0..7], sigma1, invd1) instead of 17, and a
+// worker's ring shrinks from 12 to 7 KB -- what lets a fourth CTA of the work-queue kernel fit an SM.  The routine
+// always lays its ring out by stage_maps(SB); callers that size their areas with the 17-map constants simply leave the
+// tail unused.
+__host__ __device__ constexpr int stage_maps(bool sb) { return sb ? 8 + 2 : kStageMaps; }
+__host__ __device__ constexpr int stage_slot_floats(bool sb) { return (stage_maps(sb) * kStageWidth + 31) / 32 * 32; }
+__host__ __device__ constexpr int stage_warp_floats(bool sb) { return kStageRows * stage_slot_floats(sb) + 32; }
 // lanes of a row whose footprint is not resident park their own 17 x 4 taps here (see the direct-load body)
 #ifndef DPFT_OUT_LANES
 #define DPFT_OUT_LANES 4
@@ -55,6 +62,11 @@ constexpr int kOutFloats = kOutLanes * kStageMaps * 4;
 // bytes so that every ring slot is 128-byte aligned (what the tensor-map copies of DPFT_STAGED_TMA=1 require of their
 // destination).  The 27 rows of the final reduction overlay the tail of the ring once the tile is done.
 constexpr int kStageAreaFloats = (kStageWarpFloats + 12 * 33 + kOutFloats + kHaloFloats + 31) / 32 * 32;
+__host__ __device__ constexpr int stage_area_floats(bool sb) {
+  return (stage_warp_floats(sb) + 12 * 33 + kOutFloats + kHaloFloats + 31) / 32 * 32;
+}
+static_assert(stage_warp_floats(true) >= 27 * 33 && stage_warp_floats(true) % 4 == 0, "the reduction rows overlay the ring");
+static_assert(stage_warp_floats(false) == kStageWarpFloats && stage_area_floats(false) == kStageAreaFloats, "17-map layout");
 static_assert((kStageWarpFloats + 12 * 33 + kOutFloats) % 4 == 0, "the halo sums are read as float4");
 static_assert(kStageWarpFloats >= 27 * 33, "the reduction rows overlay the ring");
 
@@ -150,6 +162,8 @@ __device__ __forceinline__ void process_tile_staged(const PairView& g, const flo
   constexpr bool FIXED = GW > 0 && GH > 0;
   constexpr int PLANE = GW * GH;
   constexpr int SW = kStageWidth, CPR = SW / 4;   // 16-byte chunks per staged map row
+  constexpr int NM = stage_maps(SB), SLOT = stage_slot_floats(SB);   // maps and floats of one staged source row
+  constexpr int DMAP = NM - 1;                    // map slot of the inverse depth (sigma1: slots CH.. or the one slot CH)
   const int H = FIXED ? GH : g.H, W = FIXED ? GW : g.W;
   const unsigned iplane = (unsigned)(H * W), Wu = (unsigned)W;
   constexpr bool WIDE = kStagedCols == 32;
@@ -161,11 +175,11 @@ __device__ __forceinline__ void process_tile_staged(const PairView& g, const flo
   const float rcp_fy = __frcp_rn(fy);
   const float rcp_hw = __frcp_rn(0.5f * (float)(W - 1)), rcp_hh = __frcp_rn(0.5f * (float)(H - 1));
   const unsigned ring_s = (unsigned)__cvta_generic_to_shared(ring);
-  int* slot_xs = reinterpret_cast<int*>(ring + kStageRows * kStageSlotFloats);
+  int* slot_xs = reinterpret_cast<int*>(ring + kStageRows * SLOT);
   // TMA variant: four mbarriers behind the slot origins; `par` holds the phase parity to wait for per slot,
   // `inflight` the slots whose copy has not been confirmed yet (both warp-uniform)
 #if DPFT_STAGED_TMA
-  const unsigned mbar0 = ring_s + (unsigned)(kStageRows * kStageSlotFloats + 8) * 4u;
+  const unsigned mbar0 = ring_s + (unsigned)(kStageRows * SLOT + 8) * 4u;
   unsigned par = 0u, inflight = 0u;
 #endif
 
@@ -191,7 +205,7 @@ __device__ __forceinline__ void process_tile_staged(const PairView& g, const flo
 #if DPFT_STAGED_TMA
   // map rows per staged source row: x1 channels in map slots 0..7, sigma1 in 8..15 (one map in slot 8 with SB),
   // the inverse depth in slot 16
-  constexpr int kBulkMaps = SB ? CH + 2 : kStageMaps;
+  constexpr int kBulkMaps = NM;
   auto wait_slot = [&](const int sl) {
     const unsigned mb = mbar0 + 8u * (unsigned)sl;
     int spins = 0;
@@ -216,10 +230,10 @@ __device__ __forceinline__ void process_tile_staged(const PairView& g, const flo
     if (lane == 0) {
       slot_xs[sl] = xs;
       mbar_expect_tx(mb, (unsigned)(kBulkMaps * SW * 4));
-      const unsigned dst = ring_s + (unsigned)(sl * kStageSlotFloats) * 4u;
+      const unsigned dst = ring_s + (unsigned)(sl * SLOT) * 4u;
       tma_row_g2s(dst, g.tm_x1, xs, row, g.b, mb);
       tma_row_g2s(dst + 4u * (CH * SW), g.tm_s1, xs, row, g.b, mb);
-      tma_row_g2s(dst + 4u * (2 * CH * SW), g.tm_d1, xs, row, g.b, mb);
+      tma_row_g2s(dst + 4u * (DMAP * SW), g.tm_d1, xs, row, g.b, mb);
     }
     inflight |= 1u << sl;
   };
@@ -231,7 +245,7 @@ __device__ __forceinline__ void process_tile_staged(const PairView& g, const flo
     soff[k] = (unsigned)m * iplane + 4u * (unsigned)ch;
   }
   auto stage_row = [&](const int row, const int xs) {
-    const unsigned dst = ring_s + (unsigned)((row & (kStageRows - 1)) * kStageSlotFloats) * 4u + 16u * (unsigned)lane;
+    const unsigned dst = ring_s + (unsigned)((row & (kStageRows - 1)) * SLOT) * 4u + 16u * (unsigned)lane;
     const unsigned row_off = (unsigned)(row * W + xs);
 #pragma unroll
     for (int k = 0; k < 3; ++k) {
@@ -247,7 +261,7 @@ __device__ __forceinline__ void process_tile_staged(const PairView& g, const flo
       }
     }
     if (lane < CPR) {
-      cp_async16(dst + 4u * (2 * CH * SW), D1 + row_off + 4 * lane);
+      cp_async16(dst + 4u * (DMAP * SW), D1 + row_off + 4 * lane);
       if (SB) cp_async16(dst + 4u * (CH * SW), S1 + row_off + 4 * lane);     // the one sigma map, in map slot CH
     }
     if (lane == 0) slot_xs[row & (kStageRows - 1)] = xs;
@@ -263,8 +277,8 @@ __device__ __forceinline__ void process_tile_staged(const PairView& g, const flo
     float2 r;
     if (FIXED) {
       const float* q = base + idx;
-      r.x = __ldg(q + (2 * p) * PLANE);
-      r.y = __ldg(q + (2 * p + 1) * PLANE);
+      r.x = DPFT_LDW(q + (2 * p) * PLANE);
+      r.y = DPFT_LDW(q + (2 * p + 1) * PLANE);
     } else {
       r.x = ldf(base, idx + (2 * p) * iplane);
       r.y = ldf(base, idx + (2 * p + 1) * iplane);
@@ -279,8 +293,8 @@ __device__ __forceinline__ void process_tile_staged(const PairView& g, const flo
       fm[p] = load_pair(X0, om, p);
     }
     if (SB) {
-      st[0] = make_float2(__ldg(S0 + ot), 0.f);
-      sm[0] = make_float2(__ldg(S0 + om), 0.f);
+      st[0] = make_float2(DPFT_LDW(S0 + ot), 0.f);
+      sm[0] = make_float2(DPFT_LDW(S0 + om), 0.f);
     } else {
 #pragma unroll
       for (int p = 0; p < NSP; ++p) {
@@ -321,7 +335,7 @@ __device__ __forceinline__ void process_tile_staged(const PairView& g, const flo
   }
   // the ring holds source rows max(base, top - 3) .. top; base = first row requested since the last restart
   int top = -0x40000000, base = 0x40000000;
-  float d0_next = (y0 < y1) ? __ldg(D0 + (unsigned)(y0 * W + xc)) : 0.f;
+  float d0_next = (y0 < y1) ? DPFT_LDW(D0 + (unsigned)(y0 * W + xc)) : 0.f;
 
 #ifdef DPFT_HOIST_PX
   // the lane's column is fixed for the whole tile: its three products with the first column of R are, too
@@ -337,7 +351,7 @@ __device__ __forceinline__ void process_tile_staged(const PairView& g, const flo
 #pragma unroll
     for (int p = 0; p < NP; ++p) fb[p] = load_pair(X0, ob, p);
     if (SB) {
-      sb[0] = make_float2(__ldg(S0 + ob), 0.f);
+      sb[0] = make_float2(DPFT_LDW(S0 + ob), 0.f);
     } else {
 #pragma unroll
       for (int p = 0; p < NSP; ++p) sb[p] = load_pair(S0, ob, p);
@@ -346,7 +360,7 @@ __device__ __forceinline__ void process_tile_staged(const PairView& g, const flo
     if (WIDE) hnext = __ldg(hsrc + min(y + 2, H - 1) * W);
     const unsigned o = (unsigned)(y * W + xc);
     const float d0 = d0_next;
-    if (y + 1 < y1) d0_next = __ldg(D0 + o + Wu);
+    if (y + 1 < y1) d0_next = DPFT_LDW(D0 + o + Wu);
     const float py = div_by(xsub((float)y, cy), fy, rcp_fy);
 
     float u, v, inv_z;
@@ -442,8 +456,8 @@ __device__ __forceinline__ void process_tile_staged(const PairView& g, const flo
     S.nlanes += __popc(__ballot_sync(0xffffffffu, col_out && !resident));
 #endif
     // north-west / south-west texel of map 0 in the ring (kept in range for lanes that are not resident)
-    const float* a0 = ring + s0i * kStageSlotFloats + min(max(txy.xi - xs0, 0), SW - 2);
-    const float* a1 = ring + s1i * kStageSlotFloats + min(max(txy.xi - xs1, 0), SW - 2);
+    const float* a0 = ring + s0i * SLOT + min(max(txy.xi - xs0, 0), SW - 2);
+    const float* a1 = ring + s1i * SLOT + min(max(txy.xi - xs1, 0), SW - 2);
 
     // The rest of the row exists twice: the copy that runs when every lane's footprint is resident has no
     // lane-divergent code at all (one basic block from the first tap to the accumulation, which is what lets the
@@ -477,11 +491,10 @@ __device__ __forceinline__ void process_tile_staged(const PairView& g, const flo
         float* sc = outl + rank * (kStageMaps * 4);
         const unsigned sc_s = (unsigned)__cvta_generic_to_shared(sc);
 #pragma unroll
-        for (int m = 0; m < kStageMaps; ++m) {
-          if (SB && m > CH && m < 2 * CH) continue;      // one sigma map: slot CH
+        for (int m = 0; m < NM; ++m) {
           const float* src = (m < CH) ? X1 + (unsigned)tap.o + (unsigned)m * iplane
-                           : (m < 2 * CH) ? S1 + (unsigned)tap.o + (SB ? 0u : (unsigned)(m - CH) * iplane)
-                                          : D1 + tap.o;
+                           : (m < DMAP) ? S1 + (unsigned)tap.o + (SB ? 0u : (unsigned)(m - CH) * iplane)
+                                        : D1 + tap.o;
           cp_async4(sc_s + 16u * m, src);
           cp_async4(sc_s + 16u * m + 4u, src + 1);
           cp_async4(sc_s + 16u * m + 8u, src + W);
@@ -497,8 +510,8 @@ __device__ __forceinline__ void process_tile_staged(const PairView& g, const flo
     }
     float d1w;
     {
-      float da = b0[2 * CH * ms], db = b0[2 * CH * ms + 1];
-      float dc = b1[2 * CH * ms], dd = b1[2 * CH * ms + 1];
+      float da = b0[DMAP * ms], db = b0[DMAP * ms + 1];
+      float dc = b1[DMAP * ms], dd = b1[DMAP * ms + 1];
       if (DIRECT && slow) {
         const float* q = D1 + tap.o;
         da = __ldg(q); db = __ldg(q + 1); dc = __ldg(q + W); dd = __ldg(q + W + 1);
@@ -558,7 +571,10 @@ __device__ __forceinline__ void process_tile_staged(const PairView& g, const flo
       sb_rs = make_float2(rs, rs); sb_k = make_float2(k3, k3);
       pmin = pmax = sr0 = sr;
     }
-    constexpr int GP = SB ? NP : DPFT_GATHER_GROUP / 2;      // channel pairs whose lookups are in flight together
+#ifndef DPFT_GATHER_PAIRS_SB
+#define DPFT_GATHER_PAIRS_SB 4
+#endif
+    constexpr int GP = SB ? DPFT_GATHER_PAIRS_SB : DPFT_GATHER_GROUP / 2;      // channel pairs whose lookups are in flight together
 #pragma unroll
     for (int p0 = 0; p0 < NP; p0 += GP) {
       float2 xa[GP], xb[GP], xc_[GP], xd[GP], za[GP], zb[GP], zc[GP], zd[GP];
