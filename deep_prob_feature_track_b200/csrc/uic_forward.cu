@@ -388,7 +388,7 @@ __global__ void __launch_bounds__(kThreads, RES ? kResMinCtas : DPFT_MIN_CTAS) u
   const size_t b0 = p.kf_shared ? 0 : (size_t)b;      // one keyframe for the whole batch (kf_vo-style tracking)
   g.x0 = p.x0 + b0 * p.C * plane; g.x1 = p.x1 + po;
   g.s0 = p.s0 + b0 * p.SCm * plane; g.s1 = p.s1 + (size_t)b * p.SCm * plane;
-  g.scm = p.SCm;
+  g.scm = RES ? p.SC : p.SCm;           // sigma1 planes of the shared-memory copy (RES) / of the tensor in memory
   g.splane = (p.SC == p.C) ? (unsigned)plane : 0u;
   g.d0 = p.d0 + b0 * plane; g.d1 = p.d1 + (size_t)b * plane;
   g.m0 = p.m0 ? p.m0 + b0 * plane : nullptr;
@@ -404,11 +404,17 @@ __global__ void __launch_bounds__(kThreads, RES ? kResMinCtas : DPFT_MIN_CTAS) u
   __shared__ float red[kWarps][NSUM][33];
   __shared__ __align__(16) float s_pose[12];
   DPFT_STAMP(0, threadIdx.x == 0 && blockIdx.x == 0 && b == 0);
-  if (RES && cta_has_tiles(p, blockIdx.x)) {
+  // Twin launches (one uncertainty map / C maps) for full sigma tensors: only the twin that matches what
+  // sigma_replication_kernel found works.  The flag is final before any iteration launch can be resident (ordinary
+  // launches -- init, sigma0 extremes -- sit between that kernel and the first programmatic launch), so the twin
+  // that will not work skips its copy of the live frame as well.
+  const bool idle_twin = p.rep_role && ((__ldcg(p.mism) == 0) != (p.rep_role == 1));
+  if (RES && !idle_twin && cta_has_tiles(p, blockIdx.x)) {
     // x1 | sigma1 | invd1 of this pair, contiguous in that order: 16-byte copies when the planes allow it
+    // (SC == 1 on full tensors: the pair's channel 0 is the one map)
     const unsigned dst0 = (unsigned)__cvta_generic_to_shared(dyn_live);
     const float* src[3] = {g.x1, g.s1, g.d1};
-    const int cnt[3] = {p.C * plane, p.SCm * plane, plane};
+    const int cnt[3] = {p.C * plane, p.SC * plane, plane};
     const bool v16 = (plane % 4 == 0) && ((((uintptr_t)g.x1 | (uintptr_t)g.s1 | (uintptr_t)g.d1) & 15u) == 0);
     int off = 0;
 #pragma unroll
@@ -427,6 +433,7 @@ __global__ void __launch_bounds__(kThreads, RES ? kResMinCtas : DPFT_MIN_CTAS) u
   cudaTriggerProgrammaticLaunchCompletion();
   cudaGridDependencySynchronize();
   DPFT_STAMP(1, threadIdx.x == 0 && blockIdx.x == 0 && b == 0);
+  if (idle_twin) return;        // (after the dependency sync: the chain of programmatic dependencies stays transitive)
   if (RES) asm volatile("cp.async.wait_group 0;" ::: "memory");
   // full sigma tensors whose channels are copies of channel 0 (found on the device): read the one map, C times less
   if (p.mism && p.rep_role == 0 && __ldcg(p.mism) == 0) g.splane = 0u;
@@ -949,6 +956,11 @@ static int resident_smem(const dpft_level_t& L, int C, int SC) {
   return bytes + kResStaticSmem <= 110 * 1024 ? (int)bytes : 0;
 }
 
+// CTAs of the resident variant an SM holds (what make_plan assumes when it picks the tile height)
+static int resident_ctas(int res_smem) {
+  return res_smem > 0 ? std::max(1, std::min(kResMinCtas, (227 * 1024) / (res_smem + kResStaticSmem + 1024))) : 0;
+}
+
 // Linear variant of the balanced tile table (DPFT_LINEAR_TILES=1; see TileTab).  Returns false when the rectangular tiling should stay (the
 // table holds at most kTabWarps warps per pair, and a warp's range may cross one segment boundary at most).
 static bool make_tile_tab_linear(int H, int nseg, int B, TileTab& tab, const Tuning& tun) {
@@ -1045,7 +1057,7 @@ static Plan make_plan(const dpft_level_t* lv, int n_levels, int B, int C, uint32
     const int SC = (flags & DPFT_SIGMA_BROADCAST) ? 1 : C;
     pl.res_smem[l] = (!staged && (flags & DPFT_FUSED_SOBEL) && !tun.no_resident) ? resident_smem(lv[l], C, SC) : 0;
     int ctas_per_sm = staged ? DPFT_STAGED_CTAS : DPFT_MIN_CTAS;
-    if (pl.res_smem[l]) ctas_per_sm = std::max(1, std::min(kResMinCtas, (227 * 1024) / (pl.res_smem[l] + kResStaticSmem + 1024)));
+    if (pl.res_smem[l]) ctas_per_sm = resident_ctas(pl.res_smem[l]);
     // (a resident CTA pays for its copy of the live frame first: about two tile rows' worth of time, which the cost
     // model of pick_tile_rows sees as taller tiles being cheaper)
     pl.TR[l] = pick_tile_rows(lv[l].H, pl.nseg[l], B, ctas_per_sm, cta_warps, tun, pl.res_smem[l] ? 3.5 : 1.5);
@@ -1643,6 +1655,16 @@ static int run_lpi(const dpft_level_t* levels, int n_levels, int B, int C, int i
         } else {
           err = launch_staged(prm, grid, tru, use_pdl, stream, tun);
         }
+      } else if (prm.mism && pl.res_smem[l] > 0 && CH == 8 && resident_ctas(resident_smem(L, C, 1)) > resident_ctas(pl.res_smem[l])) {
+        // resident level, replication decided on the device: the one-map twin holds C + 2 instead of 2 C + 1 planes
+        // of the live frame, then the C-map twin; one of them returns at once.  Only where the smaller copy lets more
+        // CTAs share an SM (30x40: 4 against 2, 476 against 628 us per level at 20 batches); a 15x20 level would
+        // only pay the extra launches (+5 us each)
+        UicIterParams one = prm;
+        one.SC = 1; one.rep_role = 1;
+        err = launch_iter<8>(one, grid, tru, use_pdl, stream, tun, resident_smem(L, C, 1));
+        prm.rep_role = 2;
+        if (err == cudaSuccess) err = launch_iter<8>(prm, grid, tru, use_pdl, stream, tun, pl.res_smem[l]);
       } else
       switch (CH) {
         case 8: err = launch_iter<8>(prm, grid, tru, use_pdl, stream, tun, pl.res_smem[l]); break;
