@@ -85,7 +85,9 @@ cudaError_t launch_queue(const QueueParams& prm, const float* pose_in, bool tru,
                          bool allow_fixed_geometry, cudaEvent_t ev0 = nullptr, cudaEvent_t ev1 = nullptr);
 // order-encoded [min, max] of v[l][g * per_group[l] .. (g + 1) * per_group[l]) into mm[(l * n_groups + g) * 2 ..]
 // (atomicMin / atomicMax: mm must hold 0xffffffff, 0 on entry)
+// plane / C / mism (optional): elements per channel plane of every level, channels per pair and the device flag of
+// sigma_replication_kernel -- when the flag says the channels are copies, only channel 0 of every pair is read
 void launch_minmax_levels(const float* const* v, const size_t* per_group, int n_levels, int n_groups, uint32_t* mm,
-                          cudaStream_t stream);
+                          cudaStream_t stream, const unsigned* plane = nullptr, int C = 1, const int* mism = nullptr);
 
 }  // namespace dpft

@@ -1442,7 +1442,8 @@ static int run_queue(const dpft_level_t& L, int level_index, int B, int C, int i
     const float* src[1] = {L.sigma0};
     const size_t per_pair = (size_t)prm.SC * L.H * L.W;
     const size_t per_group[1] = {G.n_mm_groups > 1 ? per_pair * G.group : per_pair * (prm.kf_shared ? 1 : B)};
-    launch_minmax_levels(src, per_group, 1, G.n_mm_groups, mm, stream);
+    const unsigned plane1[1] = {(unsigned)(L.H * L.W)};
+    launch_minmax_levels(src, per_group, 1, G.n_mm_groups, mm, stream, plane1, prm.SC, prm.mism);
   }
   cudaEvent_t ev[2] = {nullptr, nullptr};
   if (kernel_ms) {
@@ -1550,12 +1551,15 @@ static int run_lpi(const dpft_level_t* levels, int n_levels, int B, int C, int i
     // extremes of sigma0 per level and group, all levels in one launch
     const float* src[DPFT_MAX_LEVELS];
     size_t per_group[DPFT_MAX_LEVELS];
+    unsigned planes[DPFT_MAX_LEVELS];
     for (int l = 0; l < n_mm_levels; ++l) {
       const size_t per_pair = (size_t)SC * levels[l].H * levels[l].W;
       src[l] = levels[l].sigma0;
       per_group[l] = G.n_mm_groups > 1 ? per_pair * G.group : per_pair * (shared_kf ? 1 : B);
+      planes[l] = (unsigned)(levels[l].H * levels[l].W);
     }
-    launch_minmax_levels(src, per_group, n_mm_levels, G.n_mm_groups, mm, stream);
+    // (full sigma tensors found to be C copies of one map: the extremes of channel 0 are the tensor's)
+    launch_minmax_levels(src, per_group, n_mm_levels, G.n_mm_groups, mm, stream, planes, SC, (fused && SC == C) ? tun.mism : nullptr);
   }
   if (persist) {
     PersistParams pp{};

@@ -444,6 +444,9 @@ __global__ void __launch_bounds__(256) queue_init_kernel(const QueueParams p, co
 struct MmLevels {
   const float* v[DPFT_MAX_LEVELS];
   size_t per_group[DPFT_MAX_LEVELS];     // elements of one group's slice
+  unsigned plane[DPFT_MAX_LEVELS];       // elements of one channel plane (0: unknown, never the channel-0 walk)
+  const int* mism;                       // device flag of sigma_replication_kernel (nullptr: none); 0 = the C channels of
+  int C;                                 //   a pair are copies of channel 0, whose extremes are the tensor's
 };
 __global__ void __launch_bounds__(256) minmax_levels_kernel(const MmLevels q, uint32_t* __restrict__ mm, const int n_groups) {
   __shared__ float s_lo[8], s_hi[8];
@@ -452,6 +455,21 @@ __global__ void __launch_bounds__(256) minmax_levels_kernel(const MmLevels q, ui
   const float* v = q.v[l] + (size_t)grp * n;
   float lo = CUDART_INF_F, hi = -CUDART_INF_F;
   const size_t stride = (size_t)gridDim.x * blockDim.x;
+  const unsigned plane = q.plane[l];
+  if (q.mism && q.C > 1 && plane >= 4u && (plane & 3u) == 0u && n % ((size_t)q.C * plane) == 0 &&
+      (reinterpret_cast<uintptr_t>(v) & 15) == 0 && __ldcg(q.mism) == 0) {
+    // replicated channels: walk channel 0 of every pair of the slice, a C-th of the bytes
+    const unsigned p4 = plane / 4u;
+    const size_t n4 = n / q.C / 4u;                  // 16-byte chunks of the channel-0 planes
+    const size_t pair_stride4 = (size_t)q.C * p4;
+    const float4* v4 = reinterpret_cast<const float4*>(v);
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
+      const size_t pair = i / p4;
+      const float4 a = __ldg(v4 + pair * pair_stride4 + (i - pair * p4));
+      lo = fminf(fminf(lo, a.x), fminf(a.y, fminf(a.z, a.w)));
+      hi = fmaxf(fmaxf(hi, a.x), fmaxf(a.y, fmaxf(a.z, a.w)));
+    }
+  } else {
   const size_t n4 = ((reinterpret_cast<uintptr_t>(v) & 15) == 0) ? n / 4 : 0;
   const float4* v4 = reinterpret_cast<const float4*>(v);
   size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -471,6 +489,7 @@ __global__ void __launch_bounds__(256) minmax_levels_kernel(const MmLevels q, ui
     const float a = __ldg(v + j);
     lo = fminf(lo, a);
     hi = fmaxf(hi, a);
+  }
   }
   lo = warp_min(lo);
   hi = warp_max(hi);
@@ -492,14 +511,17 @@ __global__ void __launch_bounds__(256) minmax_levels_kernel(const MmLevels q, ui
 }
 
 void launch_minmax_levels(const float* const* v, const size_t* per_group, int n_levels, int n_groups, uint32_t* mm,
-                          cudaStream_t stream) {
+                          cudaStream_t stream, const unsigned* plane, int C, const int* mism) {
   MmLevels q{};
   size_t widest = 0;
   for (int l = 0; l < n_levels; ++l) {
     q.v[l] = v[l];
     q.per_group[l] = per_group[l];
+    q.plane[l] = (plane && mism) ? plane[l] : 0u;
     widest = std::max(widest, per_group[l]);
   }
+  q.mism = (plane && C > 1) ? mism : nullptr;
+  q.C = C;
   const unsigned bx = (unsigned)std::max<size_t>(1, std::min<size_t>((widest / 4 + 255) / 256, (148 * 8) / std::max(1, n_groups) + 1));
   minmax_levels_kernel<<<dim3(bx, n_groups, n_levels), 256, 0, stream>>>(q, mm, n_groups);
 }
