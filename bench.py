@@ -52,7 +52,7 @@ WORKLOADS = {
 N_LEVELS, ITERS = 4, 3
 ROOFLINE_BATCHES = 8          # batches per launch of the roofline pass (what the committed ncu capture ran; 20 per launch measure
                               # 55.7 us per batch-iteration under ncu and 58 us back to back under the power cap, profiles/r2/r2b_*)
-NCU_SUMMARY = os.path.join(ROOT, "profiles", "r2", "r2b_uic_queue_kernel_onemap_level0_G8.txt")
+NCU_SUMMARY = os.path.join(ROOT, "profiles", "r2", "r2d_uic_queue_kernel_onemap_level0_G8.txt")
 
 
 def algorithmic_bytes(B, C, H, W, levels=N_LEVELS, iters=ITERS):
@@ -603,7 +603,9 @@ def run_vga(args, wl, rank, world, dev, barrier, max_over_ranks):
         "latency_ms": lat1, "latency_note": "ONE live frame against the keyframe (B = 1, kf_vo.py's per-frame call): ms per solve",
         "step_hbm_frac": bytes_step / (ms / K * 1e-3) / 1e9 / peak,
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
-                     "kernel": f"uic_queue_kernel<true,false,false,0,0,1>: the finest level (480x640) of {B} live frames, {ITERS} iterations in one launch",
+                     "kernel": f"uic_queue_kernel<true,true,false,0,0,1>: the finest level (480x640) of {B} live frames, {ITERS} iterations in one launch "
+                               "(the one-map twin: the sigma tensors are C copies of one map, found on the device; the time brackets the "
+                               "call -- replication check, sigma0 extremes, queue init and both twins)",
                      "algorithmic_bytes_per_launch": ITERS * bytes_lvl0, "launch_ms": launch_ms, "peak_source": peak_src,
                      "note": "algorithmic bytes count the keyframe side once per pair (SURVEY 8d); it is shared by the 16 frames, so DRAM reads less",
                      "how": "CUDA events on the launching stream around the call that launches it, separate pass"},

@@ -36,3 +36,12 @@ def test_bad_arguments_are_rejected_without_a_gpu():
     assert b"required" in L.dpft_last_error()
     assert L.dpft_uic_workspace_bytes(arr, 0, 2, 4, 3, 0) == 0
     assert b"n_levels" in L.dpft_last_error()
+
+
+def test_package_exports_resolve():
+    """Every name the package advertises resolves to an object of the module it is said to live in."""
+    import deep_prob_feature_track_b200 as pkg
+    for name in pkg.__all__:
+        assert getattr(pkg, name) is not None, name
+    assert pkg.patch_tracker.__module__.endswith("algorithms")
+    assert pkg.BatchedSolver.__module__.endswith("batched")
