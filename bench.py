@@ -494,8 +494,32 @@ def train_solver_leg(A, one, B, dev, main):
     torch.cuda.synchronize()
     n = 10
     ms = event_time_ms(lambda: [step(i) for i in range(n)], main) / n
+
+    # the backward of the finest level alone (its 3 iterations): what uic_bwd_px_kernel and the kernels around it cost
+    C, H, W = (int(v) for v in leaves[0][-1]["x0"].shape[1:])
+    bwd = []
+    for i in range(3 + 5):
+        lv = leaves[i % len(leaves)][-1]
+        for k in ("x0", "x1", "s0", "s1"):
+            lv[k].grad = None
+        outs = A.uic_track([lv], (R, t), iters=ITERS, remove_tru_sigma=True, check=False)
+        loss = sum(Rl.sum() + tl.sum() for Rl, tl, _ in outs)
+        t_b = event_time_ms(loss.backward, main)
+        if i >= 3:
+            bwd.append(t_b)
+    bwd_ms = statistics.median(bwd)
+    bwd_bytes = ITERS * (12 * C + 2) * 4 * H * W * B
+    peak, _ = measured_peak()
     return {"what": "solver forward+backward alone (autograd through 4 levels x 3 iterations), one GPU", "ms_per_step": ms,
-            "pairs_per_s": B / (ms * 1e-3)}
+            "pairs_per_s": B / (ms * 1e-3),
+            "backward_finest_level": {
+                "what": "dpft_uic_backward of the 120x160 level alone (3 iterations: unit Sobel maps, 3 x uic_bwd_px_kernel, 3 x pose_bwd, "
+                        "the Sobel adjoint, zero fills), CUDA events around autograd's backward",
+                "ms": bwd_ms, "algorithmic_bytes": bwd_bytes,
+                "algorithmic_note": "(12C+2)*4 bytes per pixel and iteration: x0, sigma0, their unit Sobel maps, x1 / sigma1 lookups and "
+                                    "the gradient maps written once; the kernel moves 1.9x that (each iteration reads and rewrites the six "
+                                    "accumulated maps per channel, profiles/r2/r2b_bwd_variants.txt)",
+                "achieved_GBps": bwd_bytes / (bwd_ms * 1e-3) / 1e9, "frac": bwd_bytes / (bwd_ms * 1e-3) / 1e9 / peak}}
 
 
 def run_vga(args, wl, rank, world, dev, barrier, max_over_ranks):
