@@ -596,6 +596,16 @@ class _IcLevel:
             code = getattr(self.L, name)(*args, torch.cuda.current_stream(self.dev).cuda_stream)
         _lib.check(code, name)
 
+    def raise_if_bad(self) -> None:
+        """Host check of the level's status word (one sync), as SolveResult.raise_if_bad does for the U_IC path:
+        dpft_ic_update factors the damped system by Cholesky, so a system that is not positive definite (negative
+        learned weights or damping) would otherwise travel on as NaN poses; the reference's torch.inverse
+        (alg:2085-2092) raises on a singular one."""
+        st = int(self.status.item())
+        assert not (st & _lib.DPFT_ST_NONFINITE), "non-finite weighted residual / normal equations"
+        if st & _lib.DPFT_ST_SINGULAR:
+            raise RuntimeError("damped Gauss-Newton system of the IC tracker is not positive definite")
+
     def residual(self, pose_rows, first):
         """(r (B,C,H,W), occ bool (B,1,H,W)); the keyframe object mask only counts on the first call (alg:65-66, 86-87)."""
         r, occ = _IcResidualFn.apply(self, first, pose_rows, self.t["x0"], self.t["x1"])
@@ -844,6 +854,7 @@ class TrustRegionBase(nn.Module):
                 damp = solver.net(feat).float().contiguous()
                 rows = lvl.update(2, A21, b0, rows, damp=damp)[0]
             if self.timers: self.timers.toc('solve x=A^{-1}b')
+        lvl.raise_if_bad()
         if weights is None:
             weights = torch.ones((1, 1, 1, 1), dtype=torch.float32, device=lvl.dev).expand(x0.shape)
         return unpack_pose(rows), weights

@@ -172,11 +172,17 @@ static IcParams ic_params(const dpft_level_t& L, int B, int C, long work_items) 
 
 using namespace dpft;
 
+// a launch that failed (bad configuration, a sticky error of an earlier call) must not read as success
+static int launched(const char* what) {
+  const cudaError_t err = cudaGetLastError();
+  return err == cudaSuccess ? 0 : dpft::set_error((int)err, "%s launch: %s", what, cudaGetErrorString(err));
+}
+
 extern "C" int dpft_ic_gradients(const dpft_level_t* level, int B, int C, float* gx, float* gy, void* stream) {
   if (int e = ic_check(level, B, C)) return e;
   if (!gx || !gy) return set_error(DPFT_EINVAL, "gx and gy are required");
   launch_sobel_unit(level->x0, gx, gy, B * C, level->H, level->W, (cudaStream_t)stream);
-  return 0;
+  return launched("ic_gradients");
 }
 
 extern "C" int dpft_ic_residual(const dpft_level_t* level, int B, int C, const float* pose, float* r_out,
@@ -188,7 +194,7 @@ extern "C" int dpft_ic_residual(const dpft_level_t* level, int B, int C, const f
   p.pose = pose; p.r_out = r_out; p.occ_out = occ_out;
   const dim3 grid((unsigned)((plane + 128L * p.ppt - 1) / (128L * p.ppt)), B, 1);
   ic_kernel<0><<<grid, 128, 0, (cudaStream_t)stream>>>(p);
-  return 0;
+  return launched("ic_residual");
 }
 
 extern "C" int dpft_ic_normal_matrix(const dpft_level_t* level, int B, int C, const float* gx, const float* gy,
@@ -202,7 +208,7 @@ extern "C" int dpft_ic_normal_matrix(const dpft_level_t* level, int B, int C, co
   cudaMemsetAsync(A21, 0, (size_t)B * 21 * sizeof(float), stream);
   const dim3 grid((unsigned)((plane + 128L * p.ppt - 1) / (128L * p.ppt)), B, 1);
   ic_kernel<1><<<grid, 128, 0, stream>>>(p);
-  return 0;
+  return launched("ic_normal_matrix");
 }
 
 extern "C" int dpft_ic_rhs(const dpft_level_t* level, int B, int C, const float* gx, const float* gy,
@@ -216,7 +222,7 @@ extern "C" int dpft_ic_rhs(const dpft_level_t* level, int B, int C, const float*
   cudaMemsetAsync(rhs, 0, (size_t)S * B * 6 * sizeof(float), stream);
   const dim3 grid((unsigned)((plane + 128L * p.ppt - 1) / (128L * p.ppt)), B, S);
   ic_kernel<2><<<grid, 128, 0, stream>>>(p);
-  return 0;
+  return launched("ic_rhs");
 }
 
 extern "C" int dpft_ic_update(int B, int S, int mode, const float* A21, const float* rhs, const float* lambdas,

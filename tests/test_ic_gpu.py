@@ -62,3 +62,19 @@ def test_ic_pieces_against_oracle():
     b_c = lvl.rhs(w.to(DEV), rows.unsqueeze(0))[0].cpu()
     assert frob_rel(A_c, A_o) < 1e-4
     assert frob_rel(b_c.unsqueeze(2), b_o) < 1e-4
+
+
+def test_ic_forward_raises_on_a_system_that_is_not_positive_definite():
+    """Negative M-estimator weights make J^T W J negative definite: Cholesky has no pivot, the device status word says
+    so and forward raises instead of returning NaN poses (the U_IC path's raise_if_bad; the reference's torch.inverse
+    raises on a singular system, alg:2085-2092)."""
+    g = load_golden("ic_plain")
+    lv = {k: v.to(DEV) for k, v in level_inputs(g).items()}
+
+    class Negative(nn.Module):
+        def forward(self, r, x0, x1, wPrior):
+            return -torch.ones_like(r)
+
+    mod = A.TrustRegionBase(max_iter=1, mEst_func=Negative(), solver_func=A.DirectSolverNet("Direct-Nodamping")).to(DEV).eval()
+    with torch.no_grad(), pytest.raises(RuntimeError, match="not positive definite"):
+        mod([g["R0"].to(DEV), g["t0"].to(DEV)], lv["x0"], lv["x1"], lv["invD0"], lv["invD1"], lv["K"])
