@@ -620,7 +620,7 @@ def run_vga(args, wl, rank, world, dev, barrier, max_over_ranks):
     return {
         "value": world * B * K / (ms * 1e-3), "ms_per_step": ms / K,
         "config": dict(base_config(wl), streams=S, keyframe="one resident keyframe per sequence (x0, sigma0, invD0 with batch size 1), "
-                       "16 live frames per step, sigma extremes per frame (DPFT_SHARED_KEYFRAME | DPFT_PAIRWISE_EXTREMES)",
+                       f"{B} live frames per step, sigma extremes per frame (DPFT_SHARED_KEYFRAME | DPFT_PAIRWISE_EXTREMES)",
                        api="deep_prob_feature_track_b200.algorithms.KeyframeTracker.track",
                        l2=f"live frames rotate over {len(lives)} resident sets of {sum(v.numel() * 4 for lv in lives[0] for v in lv.values()) / 1e6:.0f} MB (> 126 MB L2)",
                        algorithmic_bytes_per_step=bytes_step),
@@ -750,6 +750,8 @@ def main():
     ap.add_argument("--batches-per-call", type=int, default=20, help="batches stacked into one solver call (tum)")
     ap.add_argument("--streams", type=int, default=2, help="CUDA streams the calls rotate over")
     ap.add_argument("--no-graphs", action="store_true", help="submit every call launch by launch instead of replaying its CUDA graph")
+    ap.add_argument("--frames-per-step", type=int, default=0,
+                    help="vga: live frames tracked against the keyframe per step / call (default 16; BASELINE's 1024 pairs over 8 GPUs are 128 per GPU)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-extras", action="store_true")
     ap.add_argument("--no-parity", action="store_true")
@@ -760,6 +762,8 @@ def main():
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     wl = WORKLOADS[args.workload]
+    if args.workload == "vga" and args.frames_per_step > 0:
+        wl = dict(wl, B=args.frames_per_step, name=wl["name"].replace("_b16_", f"_b{args.frames_per_step}_"))
 
     if args.impl == "reference":
         if rank == 0:
