@@ -664,6 +664,9 @@ __device__ __forceinline__ void process_tile_staged(const PairView& g, const flo
       // running extremes of the warped sigma over the WARP's pixels and what the pixels sitting on them added to
       // J^T r.  A new extreme of the warp is rare after the first rows (~ log of the pixels seen), so the
       // bookkeeping sits behind one warp-uniform branch; ties (saturated sigma maps) take it every time.
+      // one vote decides the common case (three rows of four): no pixel of this row reaches the warp's running extremes,
+      // nothing below would change anything (-0.6 % / -2.9 % on the one-map / C-map level-0 launch)
+      if (__any_sync(0xffffffffu, col_out && (pmin <= S.vmin || pmax >= S.vmax))) {
       const float wmin = ord2f(__reduce_min_sync(0xffffffffu, f2ord(col_out ? pmin : CUDART_INF_F)));
       const float wmax = ord2f(__reduce_max_sync(0xffffffffu, f2ord(col_out ? pmax : -CUDART_INF_F)));
       const bool lo = wmin < S.vmin, hi = wmax > S.vmax;
@@ -692,6 +695,7 @@ __device__ __forceinline__ void process_tile_staged(const PairView& g, const flo
 #pragma unroll
           for (int i = 0; i < 6; ++i) scorr[6 + i][lane] = (hi ? 0.f : scorr[6 + i][lane]) + (tmax ? cc[i] : 0.f);
         }
+      }
       }
     }
     if (AUX && g.occ_out && col_out) {
