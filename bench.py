@@ -296,7 +296,8 @@ def run_tum(args, wl, rank, world, dev, barrier, max_over_ranks):
     n_stack = max(G, ROOFLINE_BATCHES)
     sets = stacked_sets(gen_dev, S, n_stack)               # one stacked set per stream
     set_bytes = sum(v.numel() * 4 for lv in sets[0][0] for v in lv.values()) // n_stack
-    solver = BatchedSolver(B, iters=ITERS, remove_tru_sigma=True, streams=S, device=dev, graphs=not args.no_graphs)
+    solver = BatchedSolver(B, iters=ITERS, remove_tru_sigma=True, streams=S, device=dev, graphs=not args.no_graphs,
+                           **({"queue_ctas": args.queue_ctas} if args.queue_ctas > 0 else {}))
 
     calls = [G] * (K // G) + ([K % G] if K % G else [])     # K steps exactly
 
@@ -752,6 +753,7 @@ def main():
     ap.add_argument("--no-graphs", action="store_true", help="submit every call launch by launch instead of replaying its CUDA graph")
     ap.add_argument("--frames-per-step", type=int, default=0,
                     help="vga: live frames tracked against the keyframe per step / call (default 16; BASELINE's 1024 pairs over 8 GPUs are 128 per GPU)")
+    ap.add_argument("--queue-ctas", type=int, default=0, help="tum: CTAs of the work-queue launch (0 = what the device holds)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-extras", action="store_true")
     ap.add_argument("--no-parity", action="store_true")
