@@ -1,13 +1,15 @@
 #!/usr/bin/env python
 """Benchmark of the trust-region inverse-compositional solver path (BASELINE.json metric).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload tum|vga|train]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload tum|vga|train|deepic|icp]
 
 A *step* is one coarse-to-fine solve (4 pyramid levels x 3 Gauss-Newton iterations, U_IC with --remove_tru_sigma as
 in every script the reference ships) of ONE batch of synthetic frame pairs -- 64 pairs at 120x160 (BASELINE config 2,
 the default), 16 live frames at 480x640 against a resident keyframe (config 3, --workload vga), or one training step
-of the patched reference tracker (config 4, --workload train).  The metric is frame-pair GN solves per second;
-rank 0 prints ONE JSON line.
+of the patched reference tracker (config 4, --workload train).  --workload deepic (config 1: run_example.py's DeepIC
+tracker, one pair per call) and --workload icp (config 5: --combine_ICP, batch 64) time the whole LeastSquareTracking
+forward with the solver levels swapped by patch_tracker, next to the unpatched reference on the same GPU and on the
+host cores.  The metric is frame-pair GN solves per second; rank 0 prints ONE JSON line.
 
   value      whole-job throughput with the inputs already in HBM, through the package's public BatchedSolver: calls
              of `batches_per_call` batches (each batch keeps its own batch-global sigma extremes, i.e. the results
@@ -48,7 +50,22 @@ WORKLOADS = {
     "vga": dict(name="vga480x640_kf_b16_c8_uic_4lvl_x3it", B=16, C=8, H=480, W=640),
     # BASELINE.json configs[3]: training step (forward + backward + all-reduce + optimizer) at 120x160, batch 64 per GPU
     "train": dict(name="tum120x160_b64_c8_uic_trainstep", B=64, C=8, H=120, W=160),
+    # BASELINE.json configs[0]: run_example.py's DeepIC tracker (IC solver, convolutional M-estimator, residual-volume
+    # damping, run_example.py:84-92), one 120x160 RGB-D pair per call; the whole LeastSquareTracking forward
+    "deepic": dict(name="tum120x160_b1_deepic_run_example", B=1, C=1, H=120, W=160,
+                   flags=["--encoder_name", "ConvRGBD2", "--mestimator", "MultiScale2w", "--solver", "Direct-ResVol", "--uncertainty", "None"],
+                   variant="IC (DeepIC: MultiScale2w M-estimator, Direct-ResVol)"),
+    # BASELINE.json configs[4]: joint feature-metric + ICP refinement (scripts/train_tum_feature_icp.sh / eval_tum_feature_icp.sh),
+    # batch 64; the whole LeastSquareTracking forward
+    "icp": dict(name="tum120x160_b64_c8_uic_icp", B=64, C=8, H=120, W=160, flags="EVAL_TUM+combine_ICP",
+                variant="U_IC + point-to-plane ICP term (--combine_ICP, constant scaler)"),
 }
+TRACKER_WORKLOADS = ("deepic", "icp")
+
+
+def tracker_flags(wl):
+    from baseline import reference as REF
+    return REF.EVAL_TUM_FLAGS + ["--combine_ICP"] if wl["flags"] == "EVAL_TUM+combine_ICP" else list(wl["flags"])
 N_LEVELS, ITERS = 4, 3
 ROOFLINE_BATCHES = 8          # batches per launch of the roofline pass (what the committed ncu capture ran; 20 per launch measure
                               # 55.7 us per batch-iteration under ncu and 58 us back to back under the power cap, profiles/r2/r2b_*)
@@ -118,8 +135,8 @@ class ClockSampler:
 def base_config(wl):
     """The part of `config` both arms print (the driver compares it)."""
     return {"workload": wl["name"], "pairs_per_gpu_per_step": wl["B"], "feature_channels": wl["C"],
-            "resolution": f"{wl['H']}x{wl['W']}", "levels": N_LEVELS, "iters_per_level": ITERS, "variant": "U_IC",
-            "remove_tru_sigma": True}
+            "resolution": f"{wl['H']}x{wl['W']}", "levels": N_LEVELS, "iters_per_level": ITERS, "variant": wl.get("variant", "U_IC"),
+            "remove_tru_sigma": "flags" not in wl or wl["flags"] == "EVAL_TUM+combine_ICP"}
 
 
 # ----------------------------------------------------------------------------------------------- CPU reference
@@ -156,6 +173,17 @@ def cpu_reference_runner(wl, workload, seed):
             opt.step()
         return step, n, "reference", (f"training step of the reference's LeastSquareTracking (train.py:117-192) on {n} of the "
                                       f"{B} pairs of a step")
+    if workload in TRACKER_WORKLOADS:
+        if not have_ref:
+            raise SystemExit(f"--workload {workload} needs the reference's networks: baseline/_ref is missing (python baseline/install_reference.py)")
+        n = min(B, 16)
+        net = REF.make_tracker(tracker_flags(wl)).eval()
+        rgbd = REF.synthetic_rgbd(n, H, W, seed=seed)
+
+        def step():
+            with torch.no_grad():
+                net(*rgbd)
+        return step, n, "reference", (f"forward of the reference's LeastSquareTracking ({' '.join(tracker_flags(wl))}) on {n} of the {B} pairs of a step")
     n = B if workload == "tum" else 1
     data = make_frame_pairs(n, C, H, W, seed=seed, n_levels=N_LEVELS)
     pose = [data["R0"], data["t0"].view(n, 3, 1)]
@@ -644,6 +672,97 @@ def run_vga(args, wl, rank, world, dev, barrier, max_over_ranks):
     }
 
 
+def run_tracker(args, wl, rank, world, dev, barrier, max_over_ranks):
+    """BASELINE configs 1 and 5: the whole LeastSquareTracking forward (the reference's encoder and in-loop networks on
+    cuDNN, its tr_update0..3 swapped by patch_tracker) on device-resident RGB-D batches, next to the unpatched
+    reference on the same GPU and on the host cores."""
+    import copy
+    from deep_prob_feature_track_b200 import algorithms as A
+    from baseline import reference as REF
+    if not REF.available():
+        raise SystemExit(f"--workload {args.workload} needs the reference's networks: baseline/_ref is missing (python baseline/install_reference.py)")
+    B, H, W = wl["B"], wl["H"], wl["W"]
+    K = args.steps
+    main = torch.cuda.current_stream(dev)
+    torch.backends.cudnn.benchmark = True
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    ref = REF.make_tracker(tracker_flags(wl), seed=0).to(dev).eval()
+    ours = A.patch_tracker(copy.deepcopy(ref)).eval()
+    n_sets = max(4, -(-140_000_000 // (B * 8 * H * W * 4)))      # inputs of the rotation exceed the 126 MB L2 ... where B allows
+    n_sets = min(n_sets, 64)
+    host = [tuple(x.pin_memory() for x in REF.synthetic_rgbd(B, H, W, seed=70 + 100 * rank + i)) for i in range(n_sets)]
+    batches = [tuple(x.to(dev) for x in hb) for hb in host]
+
+    def run(net, n):
+        out = None
+        with torch.no_grad():
+            for i in range(n):
+                out = net(*batches[i % n_sets])
+        return out
+
+    def timed(net, n):
+        run(net, max(3, args.warmup))
+        torch.cuda.synchronize()
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(main)
+        run(net, n)
+        e1.record(main)
+        barrier()
+        return max_over_ranks(e0.elapsed_time(e1), dev)
+
+    ms = timed(ours, K)
+    ms_ref = timed(ref, max(3, min(K, 10))) / max(3, min(K, 10)) * K if rank == 0 else None
+    with torch.no_grad():
+        R, t = ours(*batches[0])
+        R_ref, t_ref = ref(*batches[0])
+    parity = {"against": "the unpatched reference on the same GPU, same weights and inputs (TF32 off)",
+              "R_abs_err_max": (R - R_ref).abs().max().item(), "t_abs_err_max": (t - t_ref).abs().max().item(),
+              "t_abs_max": t_ref.abs().max().item()}
+
+    # e2e: RGB-D from pinned host memory every step, poses back
+    pose_host = [torch.empty((B, 3, 3)).pin_memory(), torch.empty((B, 3)).pin_memory()]
+
+    def e2e_step(i):
+        dev_in = tuple(x.to(dev, non_blocking=True) for x in host[i % n_sets])
+        with torch.no_grad():
+            Ro, to = ours(*dev_in)
+        pose_host[0].copy_(Ro, non_blocking=True)
+        pose_host[1].copy_(to.reshape(B, 3), non_blocking=True)
+    for i in range(3):
+        e2e_step(i)
+    torch.cuda.synchronize()
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(main)
+    for i in range(K):
+        e2e_step(i)
+    e1.record(main)
+    barrier()
+    ms_e2e = max_over_ranks(e0.elapsed_time(e1), dev)
+    torch.cuda.synchronize()
+    h2d = sum(x.numel() * x.element_size() for x in host[0])
+    return {
+        "value": world * B * K / (ms * 1e-3), "ms_per_step": ms / K,
+        "config": dict(base_config(wl), flags=" ".join(tracker_flags(wl)),
+                       step="forward of LeastSquareTracking in eval mode: the reference's feature encoder (and M-estimator CNN / damping MLP) "
+                            "on cuDNN, the solver levels on this repository's CUDA kernels",
+                       api="patch_tracker(LeastSquareTracking)(img0, img1, depth0, depth1, K)",
+                       l2=f"RGB-D batches rotate over {n_sets} resident sets ({n_sets * h2d / 1e6:.0f} MB); every step's features are new tensors"),
+        "latency_ms": ms / K, "latency_note": "a step is one forward call: its time IS the latency",
+        "step_hbm_frac": None, "roofline": None, "parity": parity,
+        "e2e": {"value": world * B * K / (ms_e2e * 1e-3), "unit": "pairs/s", "h2d_bytes_per_step": h2d,
+                "d2h_bytes_per_step": B * 12 * 4, "steps": K, "ms_per_step": ms_e2e / K,
+                "what": "RGB-D batch in pinned host memory -> device -> forward -> poses in pinned memory, every step"},
+        "gpu_launches": None,
+        "extra": {"reference_on_this_gpu": {"what": "the UNPATCHED reference (its own PyTorch op chain for the solver levels) on the same GPU, "
+                                                     "same weights and inputs", "ms_per_step": ms_ref / K if ms_ref else None,
+                                            "pairs_per_s": B * K / (ms_ref * 1e-3) if ms_ref else None,
+                                            "speedup": ms_ref / ms if ms_ref else None}},
+    }
+
+
 def run_train(args, wl, rank, world, dev, barrier, max_over_ranks):
     """BASELINE config 4: one data-parallel training step per batch of 64 pairs per GPU (train.py:117-192): the
     reference's LeastSquareTracking with its tr_update0..3 swapped for the CUDA-backed solver (patch_tracker), the
@@ -789,7 +908,8 @@ def main():
         torch.cuda.synchronize()
 
     with ClockSampler(local_rank) as clocks:
-        body = {"tum": run_tum, "vga": run_vga, "train": run_train}[args.workload](args, wl, rank, world, dev, barrier, max_over_ranks)
+        body = {"tum": run_tum, "vga": run_vga, "train": run_train, "deepic": run_tracker, "icp": run_tracker}[args.workload](
+            args, wl, rank, world, dev, barrier, max_over_ranks)
 
     if rank == 0:
         out = {"metric": "frame-pair GN solves/sec", "value": body.pop("value"), "unit": "pairs/s", "n_gpus": world,

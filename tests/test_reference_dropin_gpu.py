@@ -90,3 +90,50 @@ def test_training_step_gradients_match_the_reference():
     assert worst < 2e-3, worst
     total = frob_rel(torch.cat([go[n].flatten() for n in sorted(gr)]), torch.cat([gr[n].flatten() for n in sorted(gr)]))
     assert total < 5e-4, total
+
+
+# run_example.py:84-92 (BASELINE config 1): the DeepIC tracker -- IC solver, convolutional M-estimator, residual-volume damping
+DEEPIC_FLAGS = ["--encoder_name", "ConvRGBD2", "--mestimator", "MultiScale2w", "--solver", "Direct-ResVol", "--uncertainty", "None"]
+
+
+def test_deepic_run_example_configuration_matches_the_reference_on_cuda():
+    ref, ours = trackers(DEEPIC_FLAGS)
+    ref.eval(), ours.eval()
+    for i in range(4):
+        assert type(getattr(ours, f"tr_update{i}")).__name__ == "TrustRegionBase"
+        assert type(getattr(ours, f"tr_update{i}")).__module__.startswith("deep_prob_feature_track_b200")
+    for B, seed in ((1, 11), (3, 12)):                    # run_example.py feeds one pair at a time
+        img0, img1, d0, d1, K = REF.synthetic_rgbd(B, 120, 160, seed=seed, device=DEV)
+        with torch.no_grad():
+            R_ref, t_ref = ref(img0, img1, d0, d1, K)
+            R, t = ours(img0, img1, d0, d1, K)
+        assert t_ref.abs().max() > 1e-6
+        assert (R - R_ref).abs().max() < 2e-5, (R - R_ref).abs().max()
+        assert (t - t_ref).abs().max() < 2e-5, (t - t_ref).abs().max()
+
+
+def test_deepic_training_step_gradients_match_the_reference():
+    """One training step of the DeepIC tracker: autograd chains the dpft_ic_* functions around the reference's own
+    M-estimator CNN and damping MLP; gradients of every parameter (encoder, M-estimator, solver MLP) agree."""
+    import models.criterions as crit
+    ref, ours = trackers(DEEPIC_FLAGS)
+    ref.train(), ours.train()
+    B = 2
+    img0, img1, d0, d1, K = REF.synthetic_rgbd(B, 120, 160, seed=13, device=DEV)
+    R_gt = torch.eye(3, device=DEV).repeat(B, 1, 1)
+    t_gt = torch.tensor([[0.01, -0.005, 0.002]], device=DEV).repeat(B, 1)
+    invalid = (d0 < 0.1)
+
+    def step(net):
+        net.zero_grad()
+        Rs, ts = net(img0, img1, d0, d1, K)
+        loss = crit.compute_RT_EPE_loss(Rs, ts, R_gt, t_gt, d0, K, invalid=invalid).mean() * 1e2
+        loss.backward()
+        return Rs.detach(), ts.detach(), {n: p.grad.detach().clone() for n, p in net.named_parameters() if p.grad is not None}
+
+    Rr, tr_, gr = step(ref)
+    Ro, to, go = step(ours)
+    assert (Ro - Rr).abs().max() < 2e-5 and (to - tr_).abs().max() < 2e-5
+    assert set(go) == set(gr) and len(gr) > 20
+    total = frob_rel(torch.cat([go[n].flatten() for n in sorted(gr)]), torch.cat([gr[n].flatten() for n in sorted(gr)]))
+    assert total < 2e-3, total
