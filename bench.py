@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """Benchmark of the trust-region inverse-compositional solver path (BASELINE.json metric).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload tum|vga|train|deepic|icp]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload tum|vga|train|deepic|icp|tracker]
 
 A *step* is one coarse-to-fine solve (4 pyramid levels x 3 Gauss-Newton iterations, U_IC with --remove_tru_sigma as
 in every script the reference ships) of ONE batch of synthetic frame pairs -- 64 pairs at 120x160 (BASELINE config 2,
@@ -59,12 +59,18 @@ WORKLOADS = {
     # batch 64; the whole LeastSquareTracking forward
     "icp": dict(name="tum120x160_b64_c8_uic_icp", B=64, C=8, H=120, W=160, flags="EVAL_TUM+combine_ICP",
                 variant="U_IC + point-to-plane ICP term (--combine_ICP, constant scaler)"),
+    # BASELINE.json configs[1] read literally ("feature pyramid + uncertainty-weighted trust-region IC solve"): the whole
+    # LeastSquareTracking eval forward of scripts/eval_tum_rgbd.sh at batch 64, encoder included
+    "tracker": dict(name="tum120x160_b64_c8_uic_tracker", B=64, C=8, H=120, W=160, flags="EVAL_TUM",
+                    variant="U_IC, whole LeastSquareTracking forward (eval_tum_rgbd.sh)"),
 }
-TRACKER_WORKLOADS = ("deepic", "icp")
+TRACKER_WORKLOADS = ("deepic", "icp", "tracker")
 
 
 def tracker_flags(wl):
     from baseline import reference as REF
+    if wl["flags"] == "EVAL_TUM":
+        return list(REF.EVAL_TUM_FLAGS)
     return REF.EVAL_TUM_FLAGS + ["--combine_ICP"] if wl["flags"] == "EVAL_TUM+combine_ICP" else list(wl["flags"])
 N_LEVELS, ITERS = 4, 3
 ROOFLINE_BATCHES = 8          # batches per launch of the roofline pass (what the committed ncu capture ran; 20 per launch measure
@@ -136,7 +142,7 @@ def base_config(wl):
     """The part of `config` both arms print (the driver compares it)."""
     return {"workload": wl["name"], "pairs_per_gpu_per_step": wl["B"], "feature_channels": wl["C"],
             "resolution": f"{wl['H']}x{wl['W']}", "levels": N_LEVELS, "iters_per_level": ITERS, "variant": wl.get("variant", "U_IC"),
-            "remove_tru_sigma": "flags" not in wl or wl["flags"] == "EVAL_TUM+combine_ICP"}
+            "remove_tru_sigma": "flags" not in wl or str(wl["flags"]).startswith("EVAL_TUM")}
 
 
 # ----------------------------------------------------------------------------------------------- CPU reference
@@ -688,7 +694,8 @@ def run_tracker(args, wl, rank, world, dev, barrier, max_over_ranks):
     torch.backends.cudnn.allow_tf32 = False
     torch.backends.cuda.matmul.allow_tf32 = False
     ref = REF.make_tracker(tracker_flags(wl), seed=0).to(dev).eval()
-    ours = A.patch_tracker(copy.deepcopy(ref)).eval()
+    # (U_IC without the ICP term: all four levels in one solver call; the other trackers level by level)
+    ours = A.patch_tracker(copy.deepcopy(ref), fused_forward=(args.workload == "tracker" and not args.level_by_level)).eval()
     n_sets = max(4, -(-140_000_000 // (B * 8 * H * W * 4)))      # inputs of the rotation exceed the 126 MB L2 ... where B allows
     n_sets = min(n_sets, 64)
     host = [tuple(x.pin_memory() for x in REF.synthetic_rgbd(B, H, W, seed=70 + 100 * rank + i)) for i in range(n_sets)]
@@ -748,7 +755,8 @@ def run_tracker(args, wl, rank, world, dev, barrier, max_over_ranks):
         "config": dict(base_config(wl), flags=" ".join(tracker_flags(wl)),
                        step="forward of LeastSquareTracking in eval mode: the reference's feature encoder (and M-estimator CNN / damping MLP) "
                             "on cuDNN, the solver levels on this repository's CUDA kernels",
-                       api="patch_tracker(LeastSquareTracking)(img0, img1, depth0, depth1, K)",
+                       api="patch_tracker(LeastSquareTracking" + (", fused_forward=True" if (args.workload == "tracker" and not args.level_by_level) else "")
+                           + ")(img0, img1, depth0, depth1, K)",
                        l2=f"RGB-D batches rotate over {n_sets} resident sets ({n_sets * h2d / 1e6:.0f} MB); every step's features are new tensors"),
         "latency_ms": ms / K, "latency_note": "a step is one forward call: its time IS the latency",
         "step_hbm_frac": None, "roofline": None, "parity": parity,
@@ -873,6 +881,7 @@ def main():
     ap.add_argument("--frames-per-step", type=int, default=0,
                     help="vga: live frames tracked against the keyframe per step / call (default 16; BASELINE's 1024 pairs over 8 GPUs are 128 per GPU)")
     ap.add_argument("--queue-ctas", type=int, default=0, help="tum: CTAs of the work-queue launch (0 = what the device holds)")
+    ap.add_argument("--level-by-level", action="store_true", help="tracker: keep LeastSquareTracking.forward's four module calls")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-extras", action="store_true")
     ap.add_argument("--no-parity", action="store_true")
@@ -908,7 +917,8 @@ def main():
         torch.cuda.synchronize()
 
     with ClockSampler(local_rank) as clocks:
-        body = {"tum": run_tum, "vga": run_vga, "train": run_train, "deepic": run_tracker, "icp": run_tracker}[args.workload](
+        body = {"tum": run_tum, "vga": run_vga, "train": run_train, "deepic": run_tracker, "icp": run_tracker,
+                "tracker": run_tracker}[args.workload](
             args, wl, rank, world, dev, barrier, max_over_ranks)
 
     if rank == 0:

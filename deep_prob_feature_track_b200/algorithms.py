@@ -887,9 +887,48 @@ class KeyframeTracker:
                          pairwise_extremes=True)
 
 
-def patch_tracker(net: nn.Module) -> nn.Module:
+def _fused_eval_forward(net: nn.Module):
+    """``forward`` for a patched U_IC tracker in eval mode: the reference's own ``_preprocess`` (feature encoder, depth
+    pyramids, initial pose) and then ALL pyramid levels in ONE solver call -- what ``LeastSquareTracking.forward``
+    (LeastSquareTracking.py:345-446) does through four module calls with Python, a status read and a dozen small
+    tensor ops between them.  Anything the one call does not serve (training, ICP term, object masks, uncertainty
+    propagation, logging / visualisation, timers) goes to the original forward."""
+    original = net.forward
+
+    def forward(img0, img1, depth0, depth1, K, init_only=False, logger=None, iteration=0, vis=False, obj_mask0=None,
+                obj_mask1=None, index=None):
+        trs = [getattr(net, f"tr_update{i}") for i in (3, 2, 1, 0)]
+        tr0 = trs[-1]
+        fused = (not net.training and not init_only and logger is None and not vis and obj_mask0 is None
+                 and obj_mask1 is None and getattr(net, "track_type", None) == "U_IC" and img0.is_cuda
+                 and not getattr(net, "vis_feat_uncer", False) and not getattr(net, "timers", None)
+                 and all(isinstance(t, TrustRegionInverseWUncertainty) and not t.combine_icp and not t.uncer_prop
+                         and t.max_iterations == tr0.max_iterations and t.remove_tru_sigma == tr0.remove_tru_sigma
+                         for t in trs))
+        if not fused:
+            return original(img0, img1, depth0, depth1, K, init_only=init_only, logger=logger, iteration=iteration,
+                            vis=vis, obj_mask0=obj_mask0, obj_mask1=obj_mask1, index=index)
+        pre = net._preprocess(img0, img1, depth0, depth1, poseI=None, obj_mask0=None, obj_mask1=None)
+        x0, x1, sigma0, sigma1, inv_d0, inv_d1, poseI = pre[2], pre[3], pre[4], pre[5], pre[8], pre[9], pre[12]
+        levels = [dict(x0=x0[l], x1=x1[l], s0=sigma0[l], s1=sigma1[l], invD0=inv_d0[l], invD1=inv_d1[l],
+                       K=K / float(1 << l)) for l in (3, 2, 1, 0)]
+        res = uic_solve(levels, poseI, iters=tr0.max_iterations, remove_tru_sigma=tr0.remove_tru_sigma)
+        if all(t.check_nan for t in trs):
+            res.raise_if_bad()
+        return res.pose
+
+    return forward
+
+
+def patch_tracker(net: nn.Module, fused_forward: bool = False) -> nn.Module:
     """Swap the ``tr_update0..3`` children of a reference ``LeastSquareTracking`` (U_IC or IC) for the CUDA-backed
-    modules, keeping their learned sub-modules so ``state_dict`` keys are unchanged."""
+    modules, keeping their learned sub-modules so ``state_dict`` keys are unchanged.  ``fused_forward=True``
+    additionally lets an eval-mode U_IC forward run all four levels in one solver call (same results; see
+    ``_fused_eval_forward``)."""
+    if fused_forward:
+        net = patch_tracker(net)
+        net.forward = _fused_eval_forward(net)
+        return net
     for i in range(4):
         name = f"tr_update{i}"
         old = getattr(net, name)

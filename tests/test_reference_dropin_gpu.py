@@ -137,3 +137,24 @@ def test_deepic_training_step_gradients_match_the_reference():
     assert set(go) == set(gr) and len(gr) > 20
     total = frob_rel(torch.cat([go[n].flatten() for n in sorted(gr)]), torch.cat([gr[n].flatten() for n in sorted(gr)]))
     assert total < 2e-3, total
+
+
+def test_fused_eval_forward_equals_the_level_by_level_forward():
+    """patch_tracker(net, fused_forward=True): the reference's _preprocess, then all four levels in ONE solver call.
+    Same kernels on the same tensors as the four module calls, so the poses are the same floats; whatever the one call
+    does not serve (here: train mode) takes the original forward."""
+    ref, ours = trackers()
+    fused = A.patch_tracker(copy.deepcopy(ref), fused_forward=True)
+    ref.eval(), ours.eval(), fused.eval()
+    img0, img1, d0, d1, K = REF.synthetic_rgbd(4, 120, 160, seed=21, device=DEV)
+    with torch.no_grad():
+        R_ref, t_ref = ref(img0, img1, d0, d1, K)
+        R_a, t_a = ours(img0, img1, d0, d1, K)
+        R_b, t_b = fused(img0, img1, d0, d1, K)
+    assert R_b.shape == R_a.shape and t_b.shape == t_a.shape
+    assert torch.equal(R_a, R_b) and torch.equal(t_a, t_b)
+    assert (R_b - R_ref).abs().max() < 1e-5 and (t_b - t_ref).abs().max() < 1e-5
+    fused.train(), ours.train()
+    Rs_a, ts_a = ours(img0, img1, d0, d1, K)
+    Rs_b, ts_b = fused(img0, img1, d0, d1, K)                # falls back: the pose pyramid of train.py
+    assert Rs_b.shape == Rs_a.shape and torch.allclose(Rs_a, Rs_b, atol=1e-6) and torch.allclose(ts_a, ts_b, atol=1e-6)
