@@ -11,6 +11,8 @@ tracker, one pair per call) and --workload icp (config 5: --combine_ICP, batch 6
 forward with the solver levels swapped by patch_tracker, next to the unpatched reference on the same GPU and on the
 host cores.  The metric is frame-pair GN solves per second; rank 0 prints ONE JSON line.
 
+  config     WHAT is measured (workload, sizes, the L2 rule): the same dict in both arms (the driver compares them)
+  how        how this arm runs it (call sizes, streams, graph replay, which kernels, the uncertainty format)
   value      whole-job throughput with the inputs already in HBM, through the package's public BatchedSolver: calls
              of `batches_per_call` batches (each batch keeps its own batch-global sigma extremes, i.e. the results
              of separate reference calls) rotate over `streams` CUDA streams; K steps = K batches exactly.
@@ -145,6 +147,31 @@ def base_config(wl):
             "remove_tru_sigma": "flags" not in wl or str(wl["flags"]).startswith("EVAL_TUM")}
 
 
+def l2_note(wl, workload, args):
+    """How the timed region keeps a step from finding its inputs in the 126 MB L2 (same text in both arms: it is part
+    of `config`, which the driver compares)."""
+    B, C, H, W = wl["B"], wl["C"], wl["H"], wl["W"]
+    S = max(1, args.streams)
+    if workload == "tum":
+        n_stack = max(max(1, args.batches_per_call), ROOFLINE_BATCHES)
+        per_batch = sum(((4 * C + 2) * (H >> l) * (W >> l) + 4) * 4 * B for l in range(N_LEVELS))
+        return (f"every stream owns a set of {n_stack} batches ({per_batch / 1e6:.0f} MB each, > 126 MB L2 per call); "
+                f"sets differ in addresses and pair order")
+    if workload == "vga":
+        per_set = sum(((2 * C + 1) * (H >> l) * (W >> l) + 4) * 4 * B for l in range(N_LEVELS))
+        return f"live frames rotate over {max(2, S)} resident sets of {per_set / 1e6:.0f} MB (> 126 MB L2)"
+    per_batch = B * 8 * H * W * 4 + 16 * B
+    if workload == "train":
+        return f"2 RGB-D batches of {per_batch / 1e6:.0f} MB; every step's features, gradients and workspaces are new tensors"
+    n_sets = min(max(4, -(-140_000_000 // (B * 8 * H * W * 4))), 64)
+    return f"RGB-D batches rotate over {n_sets} resident sets ({n_sets * per_batch / 1e6:.0f} MB); every step's features are new tensors"
+
+
+def workload_config(wl, workload, args):
+    """`config` of the JSON line: what is measured -- identical in both arms.  How this arm runs it goes to `how`."""
+    return dict(base_config(wl), l2=l2_note(wl, workload, args))
+
+
 # ----------------------------------------------------------------------------------------------- CPU reference
 def cpu_reference_runner(wl, workload, seed):
     """(step(), pairs_per_step, kind, description): the reference's own implementation of the path on the host cores.
@@ -236,7 +263,8 @@ def reference_arm(args, wl):
     print(json.dumps({
         "impl": "reference", "metric": "frame-pair GN solves/sec", "value": v, "unit": "pairs/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True,
-        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": base_config(wl),
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": workload_config(wl, args.workload, args),
         "cpu_baseline": {"value": v, "unit": "pairs/s", "cores": os.cpu_count() or 1, "kind": kind,
                          "sample": f"{what}; mean of {args.steps} steps after {args.warmup} warm-up"},
         "e2e": {"value": v, "unit": "pairs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -467,8 +495,7 @@ def run_tum(args, wl, rank, world, dev, barrier, max_over_ranks):
                              "check per call finds that (one read of the sigma tensors, inside the timed region) and the one-map tile "
                              "routines run (options.sigma_detect)",
                        sigma_extremes="per batch of 64 (options.group): the results of separate reference calls",
-                       l2=f"every stream owns a set of {n_stack} batches ({set_bytes / 1e6:.0f} MB each, > 126 MB L2 per call); "
-                          f"sets differ in addresses and pair order",
+                       l2=l2_note(wl, "tum", args),
                        algorithmic_bytes_per_step=bytes_step),
         "latency_ms": latency_ms,
         "latency_note": "one batch of 64 pairs alone on one stream (launch-per-iteration kernels): ms per solve",
@@ -657,7 +684,7 @@ def run_vga(args, wl, rank, world, dev, barrier, max_over_ranks):
         "config": dict(base_config(wl), streams=S, keyframe="one resident keyframe per sequence (x0, sigma0, invD0 with batch size 1), "
                        f"{B} live frames per step, sigma extremes per frame (DPFT_SHARED_KEYFRAME | DPFT_PAIRWISE_EXTREMES)",
                        api="deep_prob_feature_track_b200.algorithms.KeyframeTracker.track",
-                       l2=f"live frames rotate over {len(lives)} resident sets of {sum(v.numel() * 4 for lv in lives[0] for v in lv.values()) / 1e6:.0f} MB (> 126 MB L2)",
+                       l2=l2_note(wl, "vga", args),
                        algorithmic_bytes_per_step=bytes_step),
         "latency_ms": lat1, "latency_note": "ONE live frame against the keyframe (B = 1, kf_vo.py's per-frame call): ms per solve",
         "step_hbm_frac": bytes_step / (ms / K * 1e-3) / 1e9 / peak,
@@ -757,7 +784,7 @@ def run_tracker(args, wl, rank, world, dev, barrier, max_over_ranks):
                             "on cuDNN, the solver levels on this repository's CUDA kernels",
                        api="patch_tracker(LeastSquareTracking" + (", fused_forward=True" if (args.workload == "tracker" and not args.level_by_level) else "")
                            + ")(img0, img1, depth0, depth1, K)",
-                       l2=f"RGB-D batches rotate over {n_sets} resident sets ({n_sets * h2d / 1e6:.0f} MB); every step's features are new tensors"),
+                       l2=l2_note(wl, args.workload, args)),
         "latency_ms": ms / K, "latency_note": "a step is one forward call: its time IS the latency",
         "step_hbm_frac": None, "roofline": None, "parity": parity,
         "e2e": {"value": world * B * K / (ms_e2e * 1e-3), "unit": "pairs/s", "h2d_bytes_per_step": h2d,
@@ -846,7 +873,8 @@ def run_train(args, wl, rank, world, dev, barrier, max_over_ranks):
         "config": dict(base_config(wl), step="forward (reference FeaturePyramid + pose predictor on cuDNN, CUDA solver 4 levels x 3 iterations) "
                        "+ compute_RT_EPE_loss (CUDA) + backward + bucketed all-reduce + clip_grad_norm + Adam",
                        api="patch_tracker(LeastSquareTracking) + criterions.compute_RT_EPE_loss + ddp.FlatBucketReducer",
-                       gradient_bytes=reducer.nbytes, buckets=len(reducer.bounds), collective="NCCL all-reduce" if world > 1 else "none (1 rank)"),
+                       gradient_bytes=reducer.nbytes, buckets=len(reducer.bounds), collective="NCCL all-reduce" if world > 1 else "none (1 rank)",
+                       l2=l2_note(wl, "train", args)),
         "latency_ms": ms / K, "latency_note": "a training step IS the latency",
         "step_hbm_frac": None,
         "roofline": None,
@@ -925,6 +953,13 @@ def main():
         out = {"metric": "frame-pair GN solves/sec", "value": body.pop("value"), "unit": "pairs/s", "n_gpus": world,
                "steps": args.steps, "warmup": args.warmup, "ms_per_step": body.pop("ms_per_step"), "higher_is_better": True,
                "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic"}
+        # `config` = what is measured (the reference arm prints the same dict); `how` = how this arm runs it
+        full = body.pop("config")
+        out["config"] = workload_config(wl, args.workload, args)
+        out["how"] = {k: v for k, v in full.items() if k not in out["config"]}
+        for k in out["config"]:                       # (the run's own value wins should the two ever disagree)
+            if k in full and full[k] != out["config"][k]:
+                out["config"][k] = full[k]
         out.update(body)
         out["clocks"] = clocks.summary()
         out["numa"] = {"cpus_bound": numa_cpus}
