@@ -60,6 +60,19 @@ def _tri_gather(device) -> torch.Tensor:
     return g
 
 
+_LAMBDAS: Dict[tuple, torch.Tensor] = {}
+
+
+def _resvol_lambdas(device, samples: int) -> torch.Tensor:
+    """The residual volume's trial dampings, logspace(-5, 5, S) (alg:1664): built once per device (the reference builds
+    them on the host in every iteration -- a pageable host-to-device copy, i.e. a stream synchronisation, each time)."""
+    key = (device, int(samples))
+    lam = _LAMBDAS.get(key)
+    if lam is None:
+        lam = _LAMBDAS[key] = torch.logspace(-5, 5, int(samples)).to(device=device, dtype=torch.float32)
+    return lam
+
+
 def unpack_system(sys_rows: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
     """(...,27) -> symmetric J^T W J (...,6,6) and J^T W r (...,6,1); one gather, no per-entry launches."""
     A = sys_rows.index_select(-1, _tri_gather(sys_rows.device)).reshape(sys_rows.shape[:-1] + (6, 6))
@@ -557,7 +570,7 @@ class DirectSolverNet(nn.Module):
         if self.type == self.SOLVER_NO_DAMPING:
             return unpack_pose(lvl.update(0, A21, b0, rows)[0])
         S = int(self.samples)
-        lambdas = torch.logspace(-5, 5, S).to(device=lvl.dev, dtype=torch.float32)
+        lambdas = _resvol_lambdas(lvl.dev, S)
         trial = lvl.update(1, A21, b0, rows, lambdas=lambdas)                      # (S,B,12)
         vol = []
         for s in range(S):                                                         # alg:1676-1683
@@ -807,6 +820,7 @@ class TrustRegionBase(nn.Module):
         self.mEstimator = mEst_func
         self.directSolver = solver_func
         self.timers = timers
+        self.check_nan = True   # one read of the level's status word per call (a host sync); False turns it off
 
     def _weights(self, r, x0, x1, wPrior):
         if self.mEstimator is None:
@@ -847,14 +861,15 @@ class TrustRegionBase(nn.Module):
                 rows = lvl.update(0, A21, b0, rows)[0]
             else:
                 S = int(solver.samples)
-                lambdas = torch.logspace(-5, 5, S).to(device=lvl.dev, dtype=torch.float32)
+                lambdas = _resvol_lambdas(lvl.dev, S)
                 trial = lvl.update(1, A21, b0, rows, lambdas=lambdas)              # (S,B,12)
                 vol = lvl.rhs(weights, trial)                                      # (S,B,6)
                 feat = torch.cat((vol.permute(1, 2, 0).reshape(lvl.B, 6 * S), _tri_to_full(A21).reshape(lvl.B, 36)), dim=1)
                 damp = solver.net(feat).float().contiguous()
                 rows = lvl.update(2, A21, b0, rows, damp=damp)[0]
             if self.timers: self.timers.toc('solve x=A^{-1}b')
-        lvl.raise_if_bad()
+        if self.check_nan:
+            lvl.raise_if_bad()
         if weights is None:
             weights = torch.ones((1, 1, 1, 1), dtype=torch.float32, device=lvl.dev).expand(x0.shape)
         return unpack_pose(rows), weights
