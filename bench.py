@@ -963,7 +963,7 @@ def main():
         out.update(body)
         out["clocks"] = clocks.summary()
         out["numa"] = {"cpus_bound": numa_cpus}
-        if not args.no_cpu_baseline:
+        if not args.no_cpu_baseline and world == 1:        # (the contract: on rank 0 at N = 1 only)
             out["cpu_baseline"] = cpu_sample(wl, args.workload, 1234)
         print(json.dumps(out))
     if world > 1:
