@@ -128,7 +128,8 @@ def uic_solve(levels: Sequence[Dict[str, torch.Tensor]], pose: Pose, *, iters: i
     batch.  ``queue``: the finest level runs as ONE launch whose warps take tiles from a work queue with per-pair
     dependencies (csrc/uic_queue.cu) instead of one launch per iteration; it needs C == 8, fused Sobel, no ICP term
     and no ``want_occ``.  ``None`` (default) picks it when it pays: more than one group, or pairs that nothing
-    couples, and at least two waves of tiles at the finest level.  ``queue_levels``: how many of the finest levels
+    couples, and at least two waves of tiles at the finest level.  ``queue_levels``: how many of the finest levels (0: one,
+    or two when the call is large enough for the second-finest level to fill the queue as well)
     take that path (default 1).  ``tile_rows`` (per level, coarse first), ``queue_ctas`` and ``tuning`` (cta_slots,
     tiling, generic_geometry) are measurement knobs.  ``icp_weight``: with ``combine_icp``, per level a (B,1,h,w) map
     that scales the point-to-plane term pixel by pixel (a learned ScaleNet's output, alg:677-682) instead of ``w_icp``.
@@ -153,6 +154,13 @@ def uic_solve(levels: Sequence[Dict[str, torch.Tensor]], pose: Pose, *, iters: i
         coupled = remove_tru_sigma and n_groups == 1 and B > 1
         queue = (not coupled) and B * ((Wf + 29) // 30) * Hf >= 2 * 1776 * 12
     use_queue = bool(queue) and queue_ok
+    if use_queue and queue_levels == 0 and n_levels >= 2:
+        # The second-finest level joins the queue when a call offers it several waves of warp rows and it qualifies for the
+        # staged routine (measured with the one-map routines: 60x80 at 20 batches of 64 pairs 841 -> 698 us per call,
+        # neutral at 8 batches; a third level on the queue is slower than its resident launch-per-iteration kernel)
+        H1, W1 = int(levels[-2]["x1"].shape[2]), int(levels[-2]["x1"].shape[3])
+        if W1 % 4 == 0 and W1 >= 60 and B * ((W1 + 29) // 30) * H1 >= 8 * 1776 * 12:
+            queue_levels = 2
     SC = 1 if sigma_broadcast else C
     dev = x0.device
     keep = []   # keep converted tensors alive until the launches are queued

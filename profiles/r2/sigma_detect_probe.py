@@ -34,6 +34,8 @@ def timeit(fn, n=6, warm=3):
 
 
 kw = dict(iters=3, remove_tru_sigma=True, group=B)
+if len(sys.argv) > 2:
+    kw["queue_levels"] = int(sys.argv[2])          # how many of the finest levels run as work-queue launches
 for name, data, tun in (("check on (default)", sets, None), ("check off          ", sets, dict(sigma_detect=1)), ("one map passed in  ", one, None),
                         ("check off, generic geometry", sets, dict(sigma_detect=1, generic_geometry=1))):
     t = timeit(lambda i: A.uic_solve(*data[i % 2], tuning=tun, **kw))
