@@ -692,7 +692,9 @@ def run_vga(args, wl, rank, world, dev, barrier, max_over_ranks):
                        algorithmic_bytes_per_step=bytes_step),
         "latency_ms": lat1, "latency_note": "ONE live frame against the keyframe (B = 1, kf_vo.py's per-frame call): ms per solve",
         "step_hbm_frac": bytes_step / (ms / K * 1e-3) / 1e9 / peak,
-        "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+        "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                     "traffic": ncu_traffic(os.path.join(ROOT, "profiles", "r2", "r2d_uic_queue_kernel_vga_level0.txt")) if B == 16 else None,
+                     "traffic_source": "ncu --set full of the same launch at 16 frames: profiles/r2/r2d_uic_queue_kernel_vga_level0.txt",
                      "kernel": f"uic_queue_kernel<true,true,false,0,0,1>: the finest level (480x640) of {B} live frames, {ITERS} iterations in one launch "
                                "(the one-map twin: the sigma tensors are C copies of one map, found on the device; the time brackets the "
                                "call -- replication check, sigma0 extremes, queue init and both twins)",
