@@ -21,7 +21,7 @@ host cores.  The metric is frame-pair GN solves per second; rank 0 prints ONE JS
              the timed region (HostStreamSolver, 3 device buffers).  The host holds what the reference's encoder
              emits: ONE uncertainty map per frame (alg:1425-1427 repeats it on the device).
   roofline   dominant kernel = the finest-level work-queue launch (uic_queue_kernel: 3 iterations of
-             8 batches per launch); achieved = algorithmic bytes (4C+2)*4*H*W*B per iteration / CUDA-event time
+             20 batches per launch, what a call of the timed region launches); achieved = algorithmic bytes (4C+2)*4*H*W*B per iteration / CUDA-event time
   parity     this run's own results against the CPU oracle on the step's first batch (twist, J^T W J, mask flips)
   cpu_baseline  the reference itself (baseline/_ref, installed from /root/reference) on the host cores, full batches
 
@@ -75,9 +75,10 @@ def tracker_flags(wl):
         return list(REF.EVAL_TUM_FLAGS)
     return REF.EVAL_TUM_FLAGS + ["--combine_ICP"] if wl["flags"] == "EVAL_TUM+combine_ICP" else list(wl["flags"])
 N_LEVELS, ITERS = 4, 3
-ROOFLINE_BATCHES = 8          # batches per launch of the roofline pass (what the committed ncu capture ran; 20 per launch measure
-                              # 55.7 us per batch-iteration under ncu and 58 us back to back under the power cap, profiles/r2/r2b_*)
-NCU_SUMMARY = os.path.join(ROOT, "profiles", "r2", "r2d_uic_queue_kernel_onemap_level0_G8.txt")
+ROOFLINE_BATCHES = 20         # batches per launch of the roofline pass: what a call of the timed region launches (and what the
+                              # committed ncu capture ran; at 8 per launch the tail of the launch weighs more: 45.9 against 44 us
+                              # per batch-iteration, profiles/r2/r2d_uic_queue_kernel_onemap_level0_G8.txt)
+NCU_SUMMARY = os.path.join(ROOT, "profiles", "r2", "r2d_uic_queue_kernel_onemap_level0_G20.txt")
 
 
 def algorithmic_bytes(B, C, H, W, levels=N_LEVELS, iters=ITERS):
@@ -507,7 +508,7 @@ def run_tum(args, wl, rank, world, dev, barrier, max_over_ranks):
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                      "traffic": traffic,
                      "traffic_source": "ncu --set full dram__bytes_read.sum + dram__bytes_write.sum of the same launch "
-                                       f"(8 batches): {os.path.relpath(NCU_SUMMARY, ROOT)}",
+                                       f"({ROOFLINE_BATCHES} batches): {os.path.relpath(NCU_SUMMARY, ROOT)}",
                      "kernel": "uic_queue_kernel<true,true,false,0,0,1>: the finest level (120x160) of "
                                f"{ROOFLINE_BATCHES} batches of {B} pairs, its {ITERS} Gauss-Newton iterations in one launch, ONE-MAP tile "
                                "routine: the (B,C,H,W) sigma tensors of the workload are C copies of one map (as the reference's encoder "
@@ -520,7 +521,7 @@ def run_tum(args, wl, rank, world, dev, barrier, max_over_ranks):
                      "c_map_kernel": {"kernel": "uic_queue_kernel<true,false,false,160,120,1> (options.sigma_detect = 1: every sigma "
                                                 "channel read, what tensors with independent channels run)",
                                       "launch_ms": cmap_ms, "achieved": achieved_cmap, "frac": achieved_cmap / peak,
-                                      "ncu": "profiles/r2/r2_uic_queue_kernel_level0_G8.txt"},
+                                      "ncu": "profiles/r2/r2b_uic_queue_kernel_level0_G20.txt"},
                      "launch_ms_all": [round(x, 4) for x in ev],
                      "iteration_ms_device_stamps": [round(x, 4) for x in stamps],
                      "per_batch_iteration_us": launch_ms * 1e3 / (ITERS * ROOFLINE_BATCHES),
