@@ -317,7 +317,10 @@ void launch_icp_bwd(const float* depth0, const float* K, const float* V1, const 
   p.depth0 = depth0; p.K = K; p.V1 = V1; p.N1 = N1; p.pose = pose; p.mlam = mlam; p.m0 = m0; p.m1 = m1;
   p.gpose = gpose; p.w2 = w2; p.H = H; p.W = W; p.B = B;
   const long plane = (long)H * W;
-  const long want_threads = 148L * 2048 * 2;
+#ifndef DPFT_ICP_WANT_THREADS
+#define DPFT_ICP_WANT_THREADS (148L * 2048 * 2)
+#endif
+  const long want_threads = DPFT_ICP_WANT_THREADS;
   long ppt = ((long)B * plane + want_threads - 1) / want_threads;
   p.ppt = (int)std::max(1L, std::min(ppt, 8L));
   const dim3 grid((unsigned)((plane + 128L * p.ppt - 1) / (128L * p.ppt)), B);

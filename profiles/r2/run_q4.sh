@@ -1,4 +1,3 @@
-# round 2d: row loop of the staged routine unrolled by two (independent rows for the scheduler to interleave)
-for v in unroll2 unroll2c2; do
-  echo "== $v"; DPFT_LIB_PATH=profiles/r2/variants/$v.so python profiles/r2/sigma_detect_probe.py 20 2>&1 | grep -E "passed in|Error|error"
-done
+# round 2d: pixels per thread of icp_term_kernel (its 27-sum epilogue is amortised over them)
+python profiles/r2/icp_launch_target.py 2>&1 | tail -2
+for v in icp_t1 icp_t05 icp_t025; do echo "== $v"; DPFT_LIB_PATH=profiles/r2/variants/$v.so python profiles/r2/icp_launch_target.py 2>&1 | tail -2 | head -1; done
