@@ -19,9 +19,12 @@ void launch_vertex_normal(const float* depth, const float* K, const uint32_t* dm
 
 // Point-to-plane sums of one iteration into rec (B,28); zeroes rec first (algorithms.py:916-973).  wmap: optional
 // (B,H,W) per-pixel scale applied to residual and Jacobian (a learned ScaleNet's output)
+// scratch (optional, icp_scratch_bytes): per-CTA sums and per-pair counters -- with it the sums are folded in CTA order by
+// the pair's last CTA (bitwise reproducible); without it they are added with float atomics
+size_t icp_scratch_bytes(int B, int H, int W);
 void launch_icp_term(const float* depth0, const float* K, const float* V1, const float* N1, const float* pose,
                      const uint8_t* m0, const uint8_t* m1, float* rec, uint8_t* occ_out, float* r_out, const float* wmap,
-                     int B, int H, int W, cudaStream_t stream);
+                     int B, int H, int W, cudaStream_t stream, void* scratch = nullptr);
 
 // Pose gradient of the point-to-plane term of one iteration, accumulated into gpose (B,12)
 void launch_icp_bwd(const float* depth0, const float* K, const float* V1, const float* N1, const float* pose,

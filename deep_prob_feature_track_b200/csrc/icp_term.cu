@@ -66,6 +66,8 @@ struct IcpParams {
   uint8_t* occ_out;   // optional (B,H,W)
   float* r_out;       // optional (B,H,W) weighted-by-sigma residual (1e-6 where masked)
   const float* wmap;  // optional (B,H,W) per-pixel scale of residual and Jacobian (learned ScaleNet, alg:677-682)
+  float* part;        // optional (B, gridDim.x, 28) per-CTA sums: the pair's last CTA folds them in CTA order into rec
+  int* done;          //   (B) CTAs of the pair finished (zero before the launch, zero again after it)
   int H, W, B, ppt;
 };
 
@@ -149,10 +151,35 @@ __global__ void __launch_bounds__(128, 4) icp_term_kernel(const IcpParams p) {
     if (lane == 0) s_red[warp][i] = s;
   }
   __syncthreads();
-  if (threadIdx.x < 27) {
-    const float s = s_red[0][threadIdx.x] + s_red[1][threadIdx.x] + s_red[2][threadIdx.x] + s_red[3][threadIdx.x];
-    atomicAdd(p.rec + (size_t)b * 28 + threadIdx.x, s);
+  float s = 0.f;
+  if (threadIdx.x < 27) s = s_red[0][threadIdx.x] + s_red[1][threadIdx.x] + s_red[2][threadIdx.x] + s_red[3][threadIdx.x];
+  if (!p.part) {      // callers that only want the per-pixel outputs: the order of the sums does not matter to them
+    if (threadIdx.x < 27) atomicAdd(p.rec + (size_t)b * 28 + threadIdx.x, s);
+    return;
   }
+  // the solver's sums: fixed-order fold by the pair's last CTA (bitwise the same whatever the CTAs' timing)
+  __shared__ int s_last;
+  float* mine = p.part + ((size_t)b * gridDim.x + blockIdx.x) * 28;
+  if (threadIdx.x < 27) mine[threadIdx.x] = s;
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) s_last = (atomicAdd(p.done + b, 1) == (int)gridDim.x - 1);
+  __syncthreads();
+  if (!s_last) return;
+  __threadfence();
+  if (threadIdx.x < 27) {
+    double acc = 0.0;
+    const float* q = p.part + (size_t)b * gridDim.x * 28 + threadIdx.x;
+    for (unsigned c0 = 0; c0 < gridDim.x; c0 += 8) {       // eight loads in flight, added in CTA order
+      float v[8];
+#pragma unroll
+      for (unsigned j = 0; j < 8; ++j) v[j] = (c0 + j < gridDim.x) ? __ldcg(q + (size_t)(c0 + j) * 28) : 0.f;
+#pragma unroll
+      for (unsigned j = 0; j < 8; ++j) acc += (double)v[j];
+    }
+    p.rec[(size_t)b * 28 + threadIdx.x] = (float)acc;
+  }
+  if (threadIdx.x == 0) p.done[b] = 0;
 }
 
 // Reverse mode of icp_term_kernel for one iteration: only the pose receives a gradient (the depth maps are
@@ -317,10 +344,7 @@ void launch_icp_bwd(const float* depth0, const float* K, const float* V1, const 
   p.depth0 = depth0; p.K = K; p.V1 = V1; p.N1 = N1; p.pose = pose; p.mlam = mlam; p.m0 = m0; p.m1 = m1;
   p.gpose = gpose; p.w2 = w2; p.H = H; p.W = W; p.B = B;
   const long plane = (long)H * W;
-#ifndef DPFT_ICP_WANT_THREADS
-#define DPFT_ICP_WANT_THREADS (148L * 2048 * 2)
-#endif
-  const long want_threads = DPFT_ICP_WANT_THREADS;
+  const long want_threads = 148L * 2048 * 2;
   long ppt = ((long)B * plane + want_threads - 1) / want_threads;
   p.ppt = (int)std::max(1L, std::min(ppt, 8L));
   const dim3 grid((unsigned)((plane + 128L * p.ppt - 1) / (128L * p.ppt)), B);
@@ -333,18 +357,41 @@ void launch_vertex_normal(const float* depth, const float* K, const uint32_t* dm
   vertex_normal_kernel<<<grid, 256, 0, stream>>>(depth, K, dmm, V, N, B, H, W);
 }
 
+#ifndef DPFT_ICP_WANT_THREADS
+#define DPFT_ICP_WANT_THREADS (148L * 2048 * 2)      // tuning hook: resident threads the launch is sized for
+#endif
+static int icp_pixels_per_thread(int B, long plane) {
+  const long want_threads = DPFT_ICP_WANT_THREADS;
+  const long ppt = ((long)B * plane + want_threads - 1) / want_threads;
+  return (int)std::max(1L, std::min(ppt, 8L));
+}
+static unsigned icp_ctas_per_pair(int B, long plane) {
+  const long per_cta = 128L * icp_pixels_per_thread(B, plane);
+  return (unsigned)((plane + per_cta - 1) / per_cta);
+}
+
+size_t icp_scratch_bytes(int B, int H, int W) {
+  const size_t part = (size_t)B * icp_ctas_per_pair(B, (long)H * W) * 28 * sizeof(float);
+  return ((part + 255) & ~(size_t)255) + (size_t)B * sizeof(int);
+}
+
 void launch_icp_term(const float* depth0, const float* K, const float* V1, const float* N1, const float* pose,
                      const uint8_t* m0, const uint8_t* m1, float* rec, uint8_t* occ_out, float* r_out, const float* wmap,
-                     int B, int H, int W, cudaStream_t stream) {
+                     int B, int H, int W, cudaStream_t stream, void* scratch) {
   IcpParams p{};
   p.depth0 = depth0; p.K = K; p.V1 = V1; p.N1 = N1; p.pose = pose; p.m0 = m0; p.m1 = m1;
   p.rec = rec; p.occ_out = occ_out; p.r_out = r_out; p.wmap = wmap; p.H = H; p.W = W; p.B = B;
   const long plane = (long)H * W;
-  const long want_threads = 148L * 2048 * 2;
-  long ppt = ((long)B * plane + want_threads - 1) / want_threads;
-  p.ppt = (int)std::max(1L, std::min(ppt, 8L));
-  const dim3 grid((unsigned)((plane + 128L * p.ppt - 1) / (128L * p.ppt)), B);
-  cudaMemsetAsync(rec, 0, (size_t)B * 28 * sizeof(float), stream);
+  p.ppt = icp_pixels_per_thread(B, plane);
+  const dim3 grid(icp_ctas_per_pair(B, plane), B);
+  if (scratch) {
+    const size_t part = ((size_t)B * grid.x * 28 * sizeof(float) + 255) & ~(size_t)255;
+    p.part = (float*)scratch;
+    p.done = (int*)((char*)scratch + part);
+    cudaMemsetAsync(p.done, 0, (size_t)B * sizeof(int), stream);
+  } else {
+    cudaMemsetAsync(rec, 0, (size_t)B * 28 * sizeof(float), stream);
+  }
   icp_term_kernel<<<grid, 128, 0, stream>>>(p);
 }
 

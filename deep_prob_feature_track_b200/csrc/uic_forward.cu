@@ -918,7 +918,7 @@ struct Plan {
   int res_smem[DPFT_MAX_LEVELS];  // > 0: the level runs the resident variant with this many bytes of dynamic shared memory
   size_t max_plane;
   size_t off_partials, off_pairrec, off_counters, off_mm, off_gmm, off_sr0, off_grad, grad_elems;
-  size_t off_vn, off_icp, off_dmm, total;
+  size_t off_vn, off_icp, off_icp_scratch, off_dmm, total;
   // persistent (single cooperative launch) path
   int p_grid, p_TR[DPFT_MAX_LEVELS], p_nrt[DPFT_MAX_LEVELS], p_rcap;
   size_t off_records, off_gext, off_clock;
@@ -1096,6 +1096,11 @@ static Plan make_plan(const dpft_level_t* lv, int n_levels, int B, int C, uint32
   const bool icp = flags & DPFT_COMBINE_ICP;
   pl.off_vn = take(icp ? 6 * (size_t)B * pl.max_plane * sizeof(float) : 0);
   pl.off_icp = take(icp ? (size_t)B * 28 * sizeof(float) : 0);
+  {
+    size_t scratch = 0;
+    for (int l = 0; l < n_levels && icp; ++l) scratch = std::max(scratch, icp_scratch_bytes(B, lv[l].H, lv[l].W));
+    pl.off_icp_scratch = take(scratch);
+  }
   pl.off_dmm = take(2 * DPFT_MAX_LEVELS * sizeof(uint32_t));
   // persistent path: tile height per level that minimises the rows the busiest warp walks (a tile costs its
   // rows plus about one row of window priming), record slots per pair
@@ -1632,7 +1637,7 @@ static int run_lpi(const dpft_level_t* levels, int n_levels, int B, int C, int i
       if (icp) {
         const float* wmap = tun.icp_weight[l];      // a learned scaler's per-pixel map replaces the scalar weight
         launch_icp_term(L.depth0, L.K, vn, vn + 3 * (size_t)B * plane, prm.pose, L.obj_mask0, L.obj_mask1, icp_rec,
-                        nullptr, nullptr, wmap, B, L.H, L.W, stream);
+                        nullptr, nullptr, wmap, B, L.H, L.W, stream, ws + pl.off_icp_scratch);
         prm.icp_rec = icp_rec;
         prm.icp_w2 = wmap ? 1.f : w_icp * w_icp;
       }

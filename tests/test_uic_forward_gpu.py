@@ -311,3 +311,16 @@ def test_single_uncertainty_map_equals_the_repeated_tensor(shape):
     O.uic_level(pose, lv["x0"], lv["x1"], lv["invD0"], lv["invD1"], lv["K"], lv["s0"], lv["s1"], iters=3,
                 remove_tru_sigma=True, trace=trace)
     compare_level(bc, trace, 0, 0, 3, exact_pose_inputs=True)
+
+
+def test_icp_variant_is_bitwise_reproducible():
+    """The point-to-plane sums are folded in CTA order by each pair's last CTA (no float atomics on the solver's path):
+    repeated solves give the same floats."""
+    from deep_prob_feature_track_b200.synthetic import make_frame_pairs
+    d = make_frame_pairs(8, 8, 120, 160, seed=31, n_levels=4, with_depth=True)
+    levels = [{k: v.to(DEV) for k, v in lv.items()} for lv in d["levels"]]
+    pose = (d["R0"].to(DEV), d["t0"].to(DEV))
+    runs = [A.uic_solve(levels, pose, iters=3, remove_tru_sigma=True, combine_icp=True, w_icp=0.01) for _ in range(6)]
+    for r in runs[1:]:
+        assert torch.equal(r.pose_hist, runs[0].pose_hist) and torch.equal(r.sys_hist, runs[0].sys_hist)
+    runs[0].raise_if_bad()
