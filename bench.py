@@ -392,12 +392,12 @@ def run_tum(args, wl, rank, world, dev, barrier, max_over_ranks):
     barrier()
     ms = max_over_ranks(e0.elapsed_time(e1), dev)
     res.raise_if_bad()
-    # kernels of one call: sigma replication check, init, sigma0 extremes of all levels, 3 iterations of the 15x20 level,
-    # 3 x 2 twin launches of the resident 30x40 level, then per work-queue level queue init + its two twins -- the 60x80 level
-    # joins the queue when the call is large enough (uic_solve's rule), else it runs 3 x 2 staged twin launches
+    # kernels of one call: sigma replication check, init, sigma0 extremes of all levels, 3 iterations of the 15x20 level; then
+    # per level either 3 x 2 twin launches (resident 30x40 / staged 60x80 launch-per-iteration kernels) or, for the levels
+    # that join the queue when the call is large enough (algorithms.default_queue_levels), queue init + its two twins
     def launches_per_call(g):
-        two_queue_levels = g * B * ((W // 2 + 29) // 30) * (H // 2) >= 8 * 1776 * 12
-        return 1 + 2 + ITERS + 2 * ITERS + (3 if two_queue_levels else 2 * ITERS) + 3
+        ql = A.default_queue_levels([(H >> l, W >> l) for l in (3, 2, 1, 0)], g * B)
+        return 1 + 2 + ITERS + (3 if ql >= 3 else 2 * ITERS) + (3 if ql >= 2 else 2 * ITERS) + 3
 
     # ---- latency of ONE batch alone (launch-per-iteration kernels, one stream)
     one = [take(*s, B) for s in sets]
@@ -495,7 +495,8 @@ def run_tum(args, wl, rank, world, dev, barrier, max_over_ranks):
                                    "one graph per input set, captured during warm-up)",
                        coarse_levels="one launch per Gauss-Newton iteration (uic_iter_staged_kernel / uic_iter_kernel), all batches of a call in one grid",
                        finest_level="one work-queue launch for its 3 iterations (uic_queue_kernel, per-pair dependencies); in calls of "
-                                    "15 batches or more the 60x80 level runs as a work-queue launch of its own as well (uic_solve's rule)",
+                                    "4 / 6 batches or more the 60x80 / 30x40 levels run as work-queue launches of their own as well "
+                                    "(algorithms.default_queue_levels; the 30x40 level on the staged routine's narrow form)",
                        sigma="(B,C,H,W) tensors holding C copies of one map per frame, as the reference's encoder emits them; a device-side "
                              "check per call finds that (one read of the sigma tensors, inside the timed region) and the one-map tile "
                              "routines run (options.sigma_detect)",

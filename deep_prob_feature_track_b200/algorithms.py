@@ -106,6 +106,32 @@ class SolveResult:
             raise RuntimeError("damped Gauss-Newton system is not positive definite")
 
 
+def default_queue_levels(shapes: Sequence[Tuple[int, int]], B: int, masks: bool = False) -> int:
+    """How many of the finest pyramid levels of a work-queue solve run as work-queue launches (``uic_solve``'s rule when
+    ``queue_levels`` is 0).  ``shapes``: (H, W) per level, coarse first; ``B``: pairs of the call; ``masks``: object masks.
+
+    More levels join the queue when a call offers them enough warp rows AND enough pairs to hide a pair's iteration
+    boundary (fold, solve, append) behind the tiles of the others.  A level must qualify for the staged routine
+    (W >= 60) or its narrow form (W < 44, no object masks); the plain routine on the queue loses to the
+    launch-per-iteration kernels.  Measured on one B200, us per call (profiles/r2/r2e_narrow_probe.txt,
+    r2e_vga_levels_probe.txt), levels on the queue 1 / 2 / 3 / 4:
+      120x160, batches of 64:  2 batches 716 / 765 / 790 / 851,  4: 1205 / 1152 / 1151 / 1204,  8: 2050 / - / 1875 / 1915,
+                               12: 2838 / 2724 / 2667 / 2706,  20: - / 4371 / 4203 / 4222
+      480x640, one keyframe:   16 frames 1018 / 1060 / 1087 / 1124,  64 frames 3212 / 3126 / 3152 / 3172
+    """
+    rows = 1776 * 12     # warp rows one wave of workers walks in a 12-row tile
+
+    def offers(i):
+        h, w = shapes[i]
+        return B * ((w + 29) // 30) * h if (w % 4 == 0 and (w >= 60 or (8 <= w < 44 and not masks))) else 0
+
+    if len(shapes) >= 2 and B >= 64 and offers(-2) >= 2 * rows:
+        if len(shapes) >= 3 and B >= 256 and offers(-3) >= rows:
+            return 3
+        return 2
+    return 1
+
+
 def uic_solve(levels: Sequence[Dict[str, torch.Tensor]], pose: Pose, *, iters: int = 3,
               remove_tru_sigma: bool = False, combine_icp: bool = False, w_icp: float = 0.01,
               want_occ: bool = False, pdl: bool = True, timed: bool = False, fused_sobel: bool = True, single_launch: bool = False, staged_footprint: bool = True,
@@ -128,9 +154,9 @@ def uic_solve(levels: Sequence[Dict[str, torch.Tensor]], pose: Pose, *, iters: i
     batch.  ``queue``: the finest level runs as ONE launch whose warps take tiles from a work queue with per-pair
     dependencies (csrc/uic_queue.cu) instead of one launch per iteration; it needs C == 8, fused Sobel, no ICP term
     and no ``want_occ``.  ``None`` (default) picks it when it pays: more than one group, or pairs that nothing
-    couples, and at least two waves of tiles at the finest level.  ``queue_levels``: how many of the finest levels (0: one,
-    or two when the call is large enough for the second-finest level to fill the queue as well)
-    take that path (default 1).  ``tile_rows`` (per level, coarse first), ``queue_ctas`` and ``tuning`` (cta_slots,
+    couples, and at least two waves of tiles at the finest level.  ``queue_levels``: how many of the finest levels take
+    that path (0: one, or two / three when the call holds enough pairs and warp rows for the coarser levels to fill the
+    queue as well -- levels narrower than 44 columns then run the staged routine's narrow form).  ``tile_rows`` (per level, coarse first), ``queue_ctas`` and ``tuning`` (cta_slots,
     tiling, generic_geometry) are measurement knobs.  ``icp_weight``: with ``combine_icp``, per level a (B,1,h,w) map
     that scales the point-to-plane term pixel by pixel (a learned ScaleNet's output, alg:677-682) instead of ``w_icp``.
     """
@@ -154,13 +180,9 @@ def uic_solve(levels: Sequence[Dict[str, torch.Tensor]], pose: Pose, *, iters: i
         coupled = remove_tru_sigma and n_groups == 1 and B > 1
         queue = (not coupled) and B * ((Wf + 29) // 30) * Hf >= 2 * 1776 * 12
     use_queue = bool(queue) and queue_ok
-    if use_queue and queue_levels == 0 and n_levels >= 2:
-        # The second-finest level joins the queue when a call offers it several waves of warp rows and it qualifies for the
-        # staged routine (measured with the one-map routines: 60x80 at 20 batches of 64 pairs 841 -> 698 us per call,
-        # neutral at 8 batches; a third level on the queue is slower than its resident launch-per-iteration kernel)
-        H1, W1 = int(levels[-2]["x1"].shape[2]), int(levels[-2]["x1"].shape[3])
-        if W1 % 4 == 0 and W1 >= 60 and B * ((W1 + 29) // 30) * H1 >= 8 * 1776 * 12:
-            queue_levels = 2
+    if use_queue and queue_levels == 0:
+        queue_levels = default_queue_levels([(int(lv["x1"].shape[2]), int(lv["x1"].shape[3])) for lv in levels], B,
+                                            obj_mask0 is not None or obj_mask1 is not None)
     SC = 1 if sigma_broadcast else C
     dev = x0.device
     keep = []   # keep converted tensors alive until the launches are queued

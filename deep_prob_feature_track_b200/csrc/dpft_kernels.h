@@ -57,7 +57,7 @@ struct QLevel {
   const float *x0, *x1, *s0, *s1, *d0, *d1, *K;
   const uint8_t *m0, *m1;
   int H, W, nseg, TR, nrt, tpp;      // TR rows per tile, tpp = tiles per pair
-  int kind;                          // tile routine: 0 plain, 1 staged footprint
+  int kind;                          // tile routine: 0 plain, 1 staged footprint, 2 staged, maps narrower than the ring
 };
 struct QueueParams {
   QLevel L;

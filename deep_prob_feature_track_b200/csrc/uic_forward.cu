@@ -885,6 +885,7 @@ struct Tuning {
   int tiling = 0;                         // 0 dealt, 1 rectangular, 2 linear
   bool generic_geometry = false;
   bool no_resident = false;       // measurement knob: small levels on the plain (global-memory lookup) kernel
+  bool no_narrow = false;         // measurement knob: narrow levels on the work queue keep the plain tile routine
   bool no_sigma_detect = false;   // do not look for full sigma tensors whose channels are copies of channel 0
   const int* mism = nullptr;      // internal: device flag of sigma_replication_kernel for this call (run_uic sets it)
   float* launch_ms = nullptr;
@@ -906,6 +907,7 @@ static Tuning tuning_of(const dpft_uic_options_t* o) {
   t.queue_kernel_ms = o->launch_ms ? o->queue_kernel_ms : nullptr;
   for (int l = 0; l < DPFT_MAX_LEVELS; ++l) t.icp_weight[l] = o->icp_weight[l];
   t.no_resident = o->small_levels == 1;
+  t.no_narrow = o->small_levels == 2;
   t.no_sigma_detect = o->sigma_detect == 1;
   return t;
 }
@@ -946,6 +948,14 @@ static int pick_tile_rows(int H, int nseg, int B, int ctas_per_sm, int warps, co
 static bool staged_ok(const dpft_level_t& L, int C) {
   auto al = [](const void* q) { return ((uintptr_t)q & 15u) == 0; };
   return C == 8 && L.W % 4 == 0 && L.W >= 2 * kTileCols && L.H >= kStageRows && al(L.x1) && al(L.sigma1) && al(L.invd1);
+}
+
+// Levels narrower than the staged routine's ring (the 30x40 and 15x20 levels of a 120x160 pyramid) on the work queue: the
+// routine's NARROW form stages whole map rows.  No object masks (that instantiation is not built).
+static bool staged_narrow_ok(const dpft_level_t& L, int C) {
+  auto al = [](const void* q) { return ((uintptr_t)q & 15u) == 0; };
+  return C == 8 && L.W % 4 == 0 && L.W >= 8 && L.W < kStageWidth && L.H >= kStageRows && al(L.x1) && al(L.sigma1) &&
+         al(L.invd1) && !L.obj_mask0 && !L.obj_mask1;
 }
 
 // Small levels: the whole live frame of a pair (x1, sigma1, invd1) in the shared memory of every CTA that works on the
@@ -1370,7 +1380,7 @@ static QPlan make_qplan(const dpft_level_t& lv, int level_index, int B, int C, i
   // twins, so it is chosen for the variant the flags announce)
   const long workers = (long)sms * queue_tiles_per_sm((flags & DPFT_SIGMA_BROADCAST) != 0);
   const bool staged = (flags & DPFT_STAGED_FOOTPRINT) && staged_ok(lv, C);
-  q.kind = staged ? 1 : 0;
+  q.kind = staged ? 1 : ((flags & DPFT_STAGED_FOOTPRINT) && !tun.no_narrow && staged_narrow_ok(lv, C)) ? 2 : 0;
   q.nseg = (lv.W + kCols - 1) / kCols;
   const int want = tun.tile_rows[level_index];
   const int tr = want > 0 ? std::min(want, (int)lv.H) : queue_tile_rows(lv.H, q.nseg, B, workers);

@@ -52,7 +52,7 @@ constexpr int kQW = 4;                 // warps (workers) per CTA
 #ifndef DPFT_QW_SB
 #define DPFT_QW_SB 4                   // ... of the one-map staged routine (tuning hook)
 #endif
-__host__ __device__ constexpr int q_warps(bool sb, int kind) { return (sb && kind == 1) ? DPFT_QW_SB : kQW; }
+__host__ __device__ constexpr int q_warps(bool sb, int kind) { return (sb && kind >= 1) ? DPFT_QW_SB : kQW; }
 // Resident CTAs per SM: 3 (168 registers, 12 workers).  The one-map routine's 10-map ring would let a fourth CTA fit
 // by shared memory, and DPFT_Q_CTAS_SB=4 / DPFT_QW_SB / DPFT_Q_MAXNREG_SB build such variants -- all measured SLOWER
 // (profiles/r2/r2c_occupancy.txt): the register file is 16 K per scheduler, so between 12 and 16 workers per SM there is
@@ -62,7 +62,7 @@ __host__ __device__ constexpr int q_warps(bool sb, int kind) { return (sb && kin
 #define DPFT_Q_CTAS_SB 3
 #endif
 constexpr int kQCtasPerSm = 3;
-__host__ __device__ constexpr int q_ctas_per_sm(bool sb, int kind) { return (sb && kind == 1) ? DPFT_Q_CTAS_SB : kQCtasPerSm; }
+__host__ __device__ constexpr int q_ctas_per_sm(bool sb, int kind) { return (sb && kind >= 1) ? DPFT_Q_CTAS_SB : kQCtasPerSm; }
 // per-worker shared memory: the staged routine's area (ring | corrections | outlier taps | halo sums), then the pose
 __host__ __device__ constexpr int q_area_floats(bool sb) { return stage_area_floats(sb) + 32; }
 constexpr unsigned long long kWaitLimitNs = 4000000000ull;   // a worker that waits this long for an item traps
@@ -177,9 +177,9 @@ __device__ __forceinline__ void q_push_next(const QueueParams& p, const int k, c
 template <bool TRU, bool SB, bool AUX, int GW, int GH, int KIND>
 __device__ __forceinline__ bool q_walk_item(const QueueParams& p, float* area, const unsigned long long item) {
   const int lane = threadIdx.x & 31;
-  constexpr int WF = stage_warp_floats(SB && KIND == 1);
+  constexpr int WF = stage_warp_floats(SB && KIND >= 1);
   float (*redw)[33] = reinterpret_cast<float (*)[33]>(area + WF - 27 * 33);   // rows 27.. follow the ring
-  float* spose = area + stage_area_floats(SB && KIND == 1);
+  float* spose = area + stage_area_floats(SB && KIND >= 1);
   const int k = q_item_k(item), b = q_item_b(item), t = q_item_t(item);
   const int B = p.B, C = p.C;
   const QLevel& L = p.L;
@@ -223,8 +223,8 @@ __device__ __forceinline__ bool q_walk_item(const QueueParams& p, float* area, c
     const int seg = t % L.nseg, rt = t / L.nseg;
     const int y0 = rt * L.TR, y1 = min(y0 + L.TR, L.H);
     float* outl = area + WF + 12 * 33;
-    if (KIND == 1)
-      process_tile_staged<TRU, SB, GW, GH, AUX>(g, spose, redw + 27, area, outl, seg, y0, y1, lane, S);
+    if (KIND >= 1)      // 2: the staged routine's form for maps narrower than its ring
+      process_tile_staged<TRU, SB, GW, GH, AUX, KIND == 2>(g, spose, redw + 27, area, outl, seg, y0, y1, lane, S);
     else
       process_tile<8, TRU>(g, spose, redw + 27, seg, y0, y1, lane, S);
   }
@@ -385,14 +385,14 @@ __device__ __noinline__ void q_finish_pair(const QueueParams& p, float* area, co
 
 template <bool TRU, bool SB, bool AUX, int GW, int GH, int KIND>
 #ifdef DPFT_Q_MAXNREG_SB
-__global__ void __maxnreg__((SB && KIND == 1) ? DPFT_Q_MAXNREG_SB : 168) uic_queue_kernel(
+__global__ void __maxnreg__((SB && KIND >= 1) ? DPFT_Q_MAXNREG_SB : 168) uic_queue_kernel(
 #else
 __global__ void __launch_bounds__(q_warps(SB, KIND) * 32, q_ctas_per_sm(SB, KIND)) uic_queue_kernel(
 #endif
     const __grid_constant__ QueueParams p) {
   extern __shared__ __align__(128) float q_dyn[];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  float* area = q_dyn + warp * q_area_floats(SB && KIND == 1);
+  float* area = q_dyn + warp * q_area_floats(SB && KIND >= 1);
   // Twin launches for full sigma tensors whose channels may be copies of channel 0 (QueueParams::mism): only the twin
   // whose tile routine matches what sigma_replication_kernel found does the work, the other leaves the queue alone.
   if (p.rep_role && ((__ldcg(p.mism) == 0) != (p.rep_role == 1))) return;
@@ -528,7 +528,7 @@ void launch_minmax_levels(const float* const* v, const size_t* per_group, int n_
 
 template <bool TRU, bool SB, bool AUX, int GW, int GH, int KIND>
 static cudaError_t launch_q(const QueueParams& prm, int grid, cudaStream_t stream, cudaEvent_t ev0, cudaEvent_t ev1) {
-  constexpr int smem = q_warps(SB, KIND) * q_area_floats(SB && KIND == 1) * (int)sizeof(float);
+  constexpr int smem = q_warps(SB, KIND) * q_area_floats(SB && KIND >= 1) * (int)sizeof(float);
   auto* fn = uic_queue_kernel<TRU, SB, AUX, GW, GH, KIND>;
   // (cudaFuncSetAttribute is per device and cheap: set it on every launch rather than caching per process)
   cudaError_t err = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
@@ -588,6 +588,10 @@ static cudaError_t launch_queue_variant(const QueueParams& prm, bool tru, int gr
   if (!staged) {   // levels the staged routine does not take (narrow, unaligned): the plain tile routine
     if (tru) return aux ? DPFT_Q(true, false, true, 0, 0, 0) : DPFT_Q(true, false, false, 0, 0, 0);
     return aux ? DPFT_Q(false, false, true, 0, 0, 0) : DPFT_Q(false, false, false, 0, 0, 0);
+  }
+  if (prm.L.kind == 2) {   // narrow maps (make_qplan only plans them without object masks)
+    if (tru) return sb ? DPFT_Q(true, true, false, 0, 0, 2) : DPFT_Q(true, false, false, 0, 0, 2);
+    return sb ? DPFT_Q(false, true, false, 0, 0, 2) : DPFT_Q(false, false, false, 0, 0, 2);
   }
   // the reference's TUM level 0 (160x120) runs a geometry-specialised tile routine
   if (allow_fixed_geometry && !sb && !aux && prm.L.W == 160 && prm.L.H == 120)

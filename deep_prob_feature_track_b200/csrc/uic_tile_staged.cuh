@@ -153,7 +153,10 @@ __device__ __forceinline__ TapXY make_tap_xy(float u, float v, int H, int W, flo
 // map is staged, looked up, blended and differentiated once per pixel instead of once per channel; the results
 // are those of the repeated tensor.
 // AUX: object masks and / or the per-pixel debug outputs may be present (their tests are compiled out otherwise).
-template <bool TRU, bool SB = false, int GW = 0, int GH = 0, bool AUX = true>
+// NARROW: maps narrower than the ring (W < kStageWidth, W % 4 == 0 -- the 30x40 and 15x20 levels of a 120x160 pyramid):
+// a staged source row is the WHOLE map row at column origin 0; the chunks of a ring row past the map row re-read its
+// last chunk (never looked up), so nothing is fetched from beyond a row.
+template <bool TRU, bool SB = false, int GW = 0, int GH = 0, bool AUX = true, bool NARROW = false>
 __device__ __forceinline__ void process_tile_staged(const PairView& g, const float* spose, float (*scorr)[33],
                                                     float* ring /* kStageWarpFloats of this warp */,
                                                     float* outl /* kOutFloats (+ kHaloFloats) of this warp */, const int seg,
@@ -179,6 +182,7 @@ __device__ __forceinline__ void process_tile_staged(const PairView& g, const flo
   // TMA variant: four mbarriers behind the slot origins; `par` holds the phase parity to wait for per slot,
   // `inflight` the slots whose copy has not been confirmed yet (both warp-uniform)
 #if DPFT_STAGED_TMA
+  static_assert(!NARROW, "the tensor-map ring has no narrow form");
   const unsigned mbar0 = ring_s + (unsigned)(kStageRows * SLOT + 8) * 4u;
   unsigned par = 0u, inflight = 0u;
 #endif
@@ -242,8 +246,9 @@ __device__ __forceinline__ void process_tile_staged(const PairView& g, const flo
 #pragma unroll
   for (int k = 0; k < 3; ++k) {
     const int i = lane + 32 * k, m = i / CPR, ch = i - m * CPR;
-    soff[k] = (unsigned)m * iplane + 4u * (unsigned)ch;
+    soff[k] = (unsigned)m * iplane + 4u * (unsigned)(NARROW ? min(ch, (W >> 2) - 1) : ch);
   }
+  const int dchunk = NARROW ? 4 * min(lane, (W >> 2) - 1) : 0;   // NARROW: this lane's chunk of a one-map row
   auto stage_row = [&](const int row, const int xs) {
     const unsigned dst = ring_s + (unsigned)((row & (kStageRows - 1)) * SLOT) * 4u + 16u * (unsigned)lane;
     const unsigned row_off = (unsigned)(row * W + xs);
@@ -261,8 +266,9 @@ __device__ __forceinline__ void process_tile_staged(const PairView& g, const flo
       }
     }
     if (lane < CPR) {
-      cp_async16(dst + 4u * (DMAP * SW), D1 + row_off + 4 * lane);
-      if (SB) cp_async16(dst + 4u * (CH * SW), S1 + row_off + 4 * lane);     // the one sigma map, in map slot CH
+      const int dc = NARROW ? dchunk : 4 * lane;
+      cp_async16(dst + 4u * (DMAP * SW), D1 + row_off + dc);
+      if (SB) cp_async16(dst + 4u * (CH * SW), S1 + row_off + dc);           // the one sigma map, in map slot CH
     }
     if (lane == 0) slot_xs[row & (kStageRows - 1)] = xs;
     stage_commit();
@@ -386,7 +392,7 @@ __device__ __forceinline__ void process_tile_staged(const PairView& g, const flo
     // ---- footprint of this warp row and the ring ----------------------------------------------------------
     const int ylo = __reduce_min_sync(0xffffffffu, col_out ? txy.yi : 0x3fffffff);
     const int yhi = __reduce_max_sync(0xffffffffu, col_out ? txy.yi + 1 : -1);
-    const int xlo = __reduce_min_sync(0xffffffffu, col_out ? txy.xi : 0x3fffffff);
+    const int xlo = NARROW ? 0 : __reduce_min_sync(0xffffffffu, col_out ? txy.xi : 0x3fffffff);
     int ready_top = top;
     if (yhi >= 0) {
       if (ylo > top + 1 || ylo < base - 2) {            // a jump in the warp field: restart the ring at ylo
@@ -398,7 +404,7 @@ __device__ __forceinline__ void process_tile_staged(const PairView& g, const flo
       }
       const int keep = max(max(base, top - (kStageRows - 1)), ylo);      // lowest row this warp row still needs
       const int target = min(min(yhi + kStageLookahead, keep + kStageRows - 1), H - 1);
-      const int xs = min(max((xlo - (SW - 32) / 2) & ~3, 0), W - SW);
+      const int xs = NARROW ? 0 : min(max((xlo - (SW - 32) / 2) & ~3, 0), W - SW);
       __syncwarp();                                                      // every lane is done with the old slots
       if (WIDE) {                                                        // ... and with the halo sums of row y - 1
         halo_store(y + 1, hnext);

@@ -124,7 +124,9 @@ typedef struct dpft_uic_options {
   int32_t small_levels;   /* launch-per-iteration kernels, levels whose live frame (x1, sigma1, invd1 of one pair) fits
                              the shared memory of a CTA twice per SM: 0 = stage it there and look the footprint up on
                              chip (the default), 1 = global-memory lookups as on any other level (a measurement knob;
-                             same masks bit for bit, same sums up to the order of the fp32 partial sums).        */
+                             same masks bit for bit, same sums up to the order of the fp32 partial sums).
+                             2 = levels narrower than 44 columns that run as work-queue launches (queue_levels) keep the
+                             plain tile routine instead of the staged routine's narrow form (a measurement knob too). */
   int32_t sigma_detect;   /* full (B,C,H,W) sigma tensors whose C channels are copies of channel 0 -- what the reference's
                              encoder hands over (alg:1425-1427) -- are found by a device-side check at the start of the call
                              and served by the one-map tile routines (same results; no host synchronisation: kernels for
