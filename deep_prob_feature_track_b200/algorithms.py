@@ -925,11 +925,12 @@ class KeyframeTracker:
                 raise ValueError("a keyframe has batch size 1")
         self.iters, self.tru = iters, remove_tru_sigma
 
-    def track(self, live_levels: Sequence[Dict[str, torch.Tensor]], pose: Pose) -> SolveResult:
-        """live_levels: per level x1, s1 (B,C,h,w), invD1 (B,1,h,w), K (B,4); pose: starting poses of the B frames."""
+    def track(self, live_levels: Sequence[Dict[str, torch.Tensor]], pose: Pose, **solve_kw) -> SolveResult:
+        """live_levels: per level x1, s1 (B,C,h,w), invD1 (B,1,h,w), K (B,4); pose: starting poses of the B frames;
+        ``solve_kw``: measurement knobs of ``uic_solve`` (timed, tile_rows, ...)."""
         levels = [dict(kf, x1=lv["x1"], s1=lv["s1"], invD1=lv["invD1"], K=lv["K"]) for kf, lv in zip(self.key, live_levels)]
         return uic_solve(levels, pose, iters=self.iters, remove_tru_sigma=self.tru, shared_keyframe=True,
-                         pairwise_extremes=True)
+                         pairwise_extremes=True, **solve_kw)
 
 
 def _fused_eval_forward(net: nn.Module):
