@@ -133,6 +133,35 @@ def test_all_levels_on_the_queue_narrow_form(tru, one_map):
     assert torch.equal(again.pose_hist, res.pose_hist) and torch.equal(again.sys_hist, res.sys_hist)
 
 
+def test_narrow_form_on_small_and_odd_widths():
+    """Forced queue_levels on a tiny pyramid: widths 8, 16 and 32 run the narrow form (2, 4 and 8 chunks of a ring row
+    hold the map row, the rest re-read its last chunk), 64 the wide one -- against the launch-per-iteration kernels and
+    the oracle; also one pair alone (pairwise extremes) and a width that is not a multiple of 4 (plain routine)."""
+    B, C = 6, 8
+    data = make_frame_pairs(B, C, 48, 64, seed=21, n_levels=4)
+    pose0 = (data["R0"], data["t0"])
+    assert [tuple(lv["x1"].shape[2:]) for lv in data["levels"]] == [(6, 8), (12, 16), (24, 32), (48, 64)]
+    for tru in (True, False):
+        kw = dict(iters=3, remove_tru_sigma=tru)
+        q = solve(data["levels"], pose0, queue=True, queue_levels=4, **kw)
+        lp = solve(data["levels"], pose0, queue=False, **kw)
+        assert int(q.status.item()) == 0
+        assert (q.pose_hist - lp.pose_hist).abs().max() < 2e-6
+        assert frob_rel(q.sys_hist.cpu(), lp.sys_hist.cpu()) < 1e-5
+        trace = []
+        with torch.no_grad():
+            O.track_pyramid(data["levels"], pose0, iters=3, remove_tru_sigma=tru, trace=trace, reduction="einsum")
+        check_against_trace(q, trace, 3)
+    one = [{k: v[:1] for k, v in lv.items()} for lv in data["levels"]]
+    q1 = solve(one, (pose0[0][:1], pose0[1][:1]), iters=3, remove_tru_sigma=True, queue=True, queue_levels=4)
+    l1 = solve(one, (pose0[0][:1], pose0[1][:1]), iters=3, remove_tru_sigma=True, queue=False)
+    assert (q1.pose_hist - l1.pose_hist).abs().max() < 2e-6
+    odd = make_frame_pairs(B, C, 40, 52, seed=22, n_levels=2)      # 20x26: W % 4 != 0 -> the plain tile routine on the queue
+    qo = solve(odd["levels"], (odd["R0"], odd["t0"]), iters=3, remove_tru_sigma=True, queue=True, queue_levels=2)
+    lo = solve(odd["levels"], (odd["R0"], odd["t0"]), iters=3, remove_tru_sigma=True, queue=False)
+    assert (qo.pose_hist - lo.pose_hist).abs().max() < 2e-6
+
+
 @pytest.mark.parametrize("queue", [True, False], ids=["queue", "launch-per-iteration"])
 @pytest.mark.parametrize("tru", [True, False])
 def test_groups_equal_separate_calls(tru, queue):
