@@ -1353,6 +1353,16 @@ static int queue_tile_rows(int H, int nseg, int B, long workers) {
     const double cost = quant * (tr_eff + 3.5);
     if (cost < best - 1e-9) { best = cost; best_tr = tr_eff; }
   }
+  // Throughput regime: while an iteration still offers 2.5 waves of tiles or more, the pairs drift apart, the workers never
+  // run dry, and only the fixed work per tile counts -- the tallest such tile wins, up to whole columns (measured, one-map
+  // routine, profiles/r2/r2e_fine_tile_rows_probe.txt: 120x160 at 20 batches 40 / 60 / 120 rows 2636 / 2577 / 2543 us, at 12
+  // batches 1601 / 1565 / 1546; 480x640 with 64 frames 48 / 120 rows 2190 / 2140 us, with 16 frames -- 1.6 waves at 60
+  // rows -- 48 rows stay best; below 2.5 waves taller tiles lose, e.g. 60x80 at 12 batches).
+  for (long nrt = 1; nrt <= H; ++nrt) {
+    const int tr_eff = (int)((H + nrt - 1) / nrt);
+    if (tr_eff <= best_tr) break;
+    if ((double)(nrt * nseg * B) / (double)workers >= 2.5) return tr_eff;
+  }
   return best_tr;
 }
 

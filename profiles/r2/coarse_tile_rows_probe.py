@@ -33,6 +33,12 @@ def run(tr):
     return e0.elapsed_time(e1) / 6 * 1e3, [round(sum(r.launch_ms[3 * l:3 * l + 3]) * 1e3) for l in range(4)]
 
 
+for t0 in ((0, 30, 40, 60, 120) if "fine" in sys.argv else ()):
+    for t1 in (0, 60):
+        t, lv = run([0, 0, t1, t0])
+        print(f"G={G} 120x160 tile rows {t0:3d}, 60x80 tile rows {t1:2d}: {t:7.0f} us per call, levels {lv}", flush=True)
+if "fine" in sys.argv:
+    sys.exit(0)
 for t2 in (0, 6, 8, 10, 15, 30):
     t, lv = run([0, t2, 0, 0])
     print(f"G={G} 30x40 tile rows {t2:2d}: {t:7.0f} us per call, levels {lv}", flush=True)
