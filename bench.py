@@ -78,7 +78,7 @@ N_LEVELS, ITERS = 4, 3
 ROOFLINE_BATCHES = 20         # batches per launch of the roofline pass: what a call of the timed region launches (and what the
                               # committed ncu capture ran; at 8 per launch the tail of the launch weighs more: 45.9 against 44 us
                               # per batch-iteration, profiles/r2/r2d_uic_queue_kernel_onemap_level0_G8.txt)
-NCU_SUMMARY = os.path.join(ROOT, "profiles", "r2", "r2d_uic_queue_kernel_onemap_level0_G20.txt")
+NCU_SUMMARY = os.path.join(ROOT, "profiles", "r2", "r2f_uic_queue_kernel_onemap_level0_G20.txt")
 
 
 def algorithmic_bytes(B, C, H, W, levels=N_LEVELS, iters=ITERS):
