@@ -17,7 +17,7 @@ _EXPORTS = {
     "TrustRegionInverseWUncertainty": "algorithms", "TrustRegionBase": "algorithms", "DirectSolverNet": "algorithms",
     "patch_tracker": "algorithms", "uic_solve": "algorithms", "uic_track": "algorithms", "uic_residual_loss": "algorithms",
     "depth_pyramids": "algorithms", "KeyframeTracker": "algorithms", "SolveResult": "algorithms",
-    "pack_pose": "algorithms", "unpack_pose": "algorithms",
+    "pack_pose": "algorithms", "unpack_pose": "algorithms", "default_queue_levels": "algorithms",
     "compute_RT_EPE_loss": "criterions",
     "BatchedSolver": "batched", "HostStreamSolver": "batched", "bind_to_gpu_numa_node": "batched",
     "FlatBucketReducer": "ddp", "broadcast_parameters": "ddp",
