@@ -834,44 +834,107 @@ struct RepTensors {
   unsigned units[2 * DPFT_MAX_LEVELS];             // work units of the tensor: pairs * ceil(plane / 4)
   unsigned first[2 * DPFT_MAX_LEVELS + 1];         // prefix sums of `units`
   int n;
+  // extremes on the way (sigma0 tensors of a remove_tru_sigma call): slot of the tensor's first group in `mm` (-1: none) and
+  // work units per sigma-extreme group.  The check loads every channel of every sigma0 element anyway, so the per-level,
+  // per-group minimum / maximum the solve needs (algorithms.py:1976-1977) cost no further pass over the tensors.
+  int mm_base[2 * DPFT_MAX_LEVELS];
+  unsigned upg[2 * DPFT_MAX_LEVELS];
 };
 // One unit = four consecutive pixels of one pair: all C channels are loaded (16 bytes each when the plane allows it)
 // before anything is compared, so a thread keeps C independent loads in flight.
 template <int CT>
-__global__ void __launch_bounds__(256) sigma_replication_kernel(const RepTensors t, const int C, int* __restrict__ mism) {
+__global__ void __launch_bounds__(256) sigma_replication_kernel(const RepTensors t, const int C, int* __restrict__ mism,
+                                                                uint32_t* __restrict__ mm) {
   const unsigned total = t.first[t.n];
   unsigned diff = 0u;
   int round = 0;
-  for (unsigned u = blockIdx.x * 256u + threadIdx.x; u < total; u += gridDim.x * 256u) {
+  bool stop = false;                    // a difference is known: units without extremes to collect are skipped from here on
+  int key = -1;                         // mm slot the running extremes belong to
+  float lo = CUDART_INF_F, hi = -CUDART_INF_F;
+  auto flush = [&]() {
+    if (key >= 0 && lo <= hi) {
+      atomicMin(mm + 2 * key, f2ord(lo));
+      atomicMax(mm + 2 * key + 1, f2ord(hi));
+    }
+    lo = CUDART_INF_F;
+    hi = -CUDART_INF_F;
+  };
+  // a CTA walks one contiguous share of the units (not a grid-stride loop): a thread then stays inside one tensor and one
+  // sigma-extreme group for nearly all of its units, and its running extremes are flushed a handful of times
+  const unsigned per_cta = (total + gridDim.x - 1u) / gridDim.x;
+  const unsigned u_begin = min(total, blockIdx.x * per_cta), u_end = min(total, u_begin + per_cta);
+  for (unsigned u = u_begin + threadIdx.x; u < u_end; u += 256u) {
     int ti = 0;
 #pragma unroll
     for (int k = 1; k < 2 * DPFT_MAX_LEVELS; ++k) ti += (k < t.n && u >= t.first[k]) ? 1 : 0;
     const unsigned plane = t.plane[ti], cpp = (plane + 3u) / 4u;
     const unsigned w = u - t.first[ti];
+    const bool ext = mm != nullptr && t.mm_base[ti] >= 0;
+    if (stop && !ext) continue;
+    if (ext) {
+      const int nk = t.mm_base[ti] + (int)(w / t.upg[ti]);
+      if (nk != key) {
+        flush();
+        key = nk;
+      }
+    }
     const unsigned pair = w / cpp, ch = w - pair * cpp;
     const float* r = t.p[ti] + (size_t)pair * C * plane + 4u * ch;
     if ((plane & 3u) == 0u && ((uintptr_t)t.p[ti] & 15u) == 0u) {
       const uint4 v0 = __ldg(reinterpret_cast<const uint4*>(r));
+      auto fold = [&](const uint4 a) {
+        const float x = __uint_as_float(a.x), y = __uint_as_float(a.y), z = __uint_as_float(a.z), q = __uint_as_float(a.w);
+        lo = fminf(fminf(lo, fminf(x, y)), fminf(z, q));
+        hi = fmaxf(fmaxf(hi, fmaxf(x, y)), fmaxf(z, q));
+      };
+      if (ext) fold(v0);
       if (CT > 0) {
         uint4 v[CT > 0 ? CT : 1];
 #pragma unroll
         for (int c = 1; c < CT; ++c) v[c] = __ldg(reinterpret_cast<const uint4*>(r + (size_t)c * plane));
 #pragma unroll
-        for (int c = 1; c < CT; ++c) diff |= (v[c].x ^ v0.x) | (v[c].y ^ v0.y) | (v[c].z ^ v0.z) | (v[c].w ^ v0.w);
+        for (int c = 1; c < CT; ++c) {
+          diff |= (v[c].x ^ v0.x) | (v[c].y ^ v0.y) | (v[c].z ^ v0.z) | (v[c].w ^ v0.w);
+          if (ext) fold(v[c]);
+        }
       } else {
         for (int c = 1; c < C; ++c) {
           const uint4 a = __ldg(reinterpret_cast<const uint4*>(r + (size_t)c * plane));
           diff |= (a.x ^ v0.x) | (a.y ^ v0.y) | (a.z ^ v0.z) | (a.w ^ v0.w);
+          if (ext) fold(a);
         }
       }
     } else {
       const unsigned left = min(4u, plane - 4u * ch);
       for (unsigned e = 0; e < left; ++e) {
         const unsigned v0 = __float_as_uint(__ldg(r + e));
-        for (int c = 1; c < C; ++c) diff |= __float_as_uint(__ldg(r + (size_t)c * plane + e)) ^ v0;
+        if (ext) { lo = fminf(lo, __uint_as_float(v0)); hi = fmaxf(hi, __uint_as_float(v0)); }
+        for (int c = 1; c < C; ++c) {
+          const unsigned a = __float_as_uint(__ldg(r + (size_t)c * plane + e));
+          diff |= a ^ v0;
+          if (ext) { lo = fminf(lo, __uint_as_float(a)); hi = fmaxf(hi, __uint_as_float(a)); }
+        }
       }
     }
-    if (((++round) & 7) == 0 && (diff || *(volatile int*)mism)) break;      // somebody found a difference: no need to go on
+    // somebody found a difference: without extremes to collect there is no need to go on
+    if (((++round) & 7) == 0 && (diff || *(volatile int*)mism)) {
+      if (!mm) break;
+      stop = true;
+    }
+  }
+  if (mm) {
+    // the last flush goes through the warp when its lanes ended on the same slot (they nearly always do: a warp's units are
+    // neighbours), so an address takes a few hundred atomics per launch instead of one per thread
+    const int key0 = __shfl_sync(0xffffffffu, key, 0);
+    if (__all_sync(0xffffffffu, key == key0)) {
+      const uint32_t wlo = __reduce_min_sync(0xffffffffu, f2ord(lo)), whi = __reduce_max_sync(0xffffffffu, f2ord(hi));
+      if ((threadIdx.x & 31) == 0 && key0 >= 0 && wlo <= whi) {
+        atomicMin(mm + 2 * key0, wlo);
+        atomicMax(mm + 2 * key0 + 1, whi);
+      }
+    } else {
+      flush();
+    }
   }
   if (diff) *mism = 1;
 }
@@ -888,6 +951,7 @@ struct Tuning {
   bool no_narrow = false;         // measurement knob: narrow levels on the work queue keep the plain tile routine
   bool no_sigma_detect = false;   // do not look for full sigma tensors whose channels are copies of channel 0
   const int* mism = nullptr;      // internal: device flag of sigma_replication_kernel for this call (run_uic sets it)
+  uint32_t* mm_ready = nullptr;   // internal: sigma0 extremes of every level, collected by that kernel on the way (level, group, 2)
   float* launch_ms = nullptr;
   float* queue_kernel_ms = nullptr;
   const float* icp_weight[DPFT_MAX_LEVELS] = {};   // per level: (B,1,H,W) scale of the ICP term, or nullptr (scalar w_icp)
@@ -1497,6 +1561,10 @@ static int run_queue(const dpft_level_t& L, int level_index, int B, int C, int i
 // Workspace of a call: [launch-per-iteration plan of the levels it serves | work-queue plan of the finest level | the
 // flag of sigma_replication_kernel].
 constexpr size_t kRepFlagBytes = 256;
+// ... and behind the flag the sigma0 extremes that kernel collects on the way: (level, group, 2) order-encoded floats
+static size_t rep_mm_bytes(int n_levels, int n_mm_groups) {
+  return (((size_t)n_levels * n_mm_groups * 2 * sizeof(uint32_t)) + 255) & ~(size_t)255;
+}
 static size_t lpi_bytes(const dpft_level_t* levels, int n_levels, int B, int C, uint32_t flags, bool any_occ, const Tuning& tun) {
   if (n_levels < 1) return 0;
   const Groups G = groups_of(B, flags, tun);
@@ -1515,9 +1583,9 @@ extern "C" size_t dpft_uic_workspace_bytes_ex(const dpft_level_t* levels, int n_
     const int nc = n_levels - std::min(n_levels, std::max(1, tun.queue_levels));
     size_t q = 0;                                     // the queue launches run one after the other: one region
     for (int l = nc; l < n_levels; ++l) q = std::max(q, make_qplan(levels[l], l, B, C, iters, flags, tun).total);
-    return lpi_bytes(levels, nc, B, C, flags, any_occ, tun) + q + kRepFlagBytes;
+    return lpi_bytes(levels, nc, B, C, flags, any_occ, tun) + q + kRepFlagBytes + rep_mm_bytes(n_levels, groups_of(B, flags, tun).n_mm_groups);
   }
-  return lpi_bytes(levels, n_levels, B, C, flags, any_occ, tun) + kRepFlagBytes;
+  return lpi_bytes(levels, n_levels, B, C, flags, any_occ, tun) + kRepFlagBytes + rep_mm_bytes(n_levels, groups_of(B, flags, tun).n_mm_groups);
 }
 
 extern "C" size_t dpft_uic_workspace_bytes(const dpft_level_t* levels, int n_levels, int B, int C, int iters,
@@ -1549,7 +1617,8 @@ static int run_lpi(const dpft_level_t* levels, int n_levels, int B, int C, int i
   float* partials = (float*)(ws + pl.off_partials);
   double* pairrec = (double*)(ws + pl.off_pairrec);
   int* counters = (int*)(ws + pl.off_counters);
-  uint32_t* mm = (uint32_t*)(ws + pl.off_mm);
+  // (sigma0 extremes: already collected by the replication check of this call, or found below)
+  uint32_t* mm = tun.mm_ready ? tun.mm_ready : (uint32_t*)(ws + pl.off_mm);
   float* gmm = aux_hist ? aux_hist : (float*)(ws + pl.off_gmm);   // 4 floats per iteration and group
   float* sr0 = (float*)(ws + pl.off_sr0);
   const bool tru = flags & DPFT_REMOVE_TRU_SIGMA;
@@ -1564,7 +1633,7 @@ static int run_lpi(const dpft_level_t* levels, int n_levels, int B, int C, int i
 
   if (mm_out) *mm_out = mm;
   {
-    const int n_mm = n_mm_levels * G.n_mm_groups;
+    const int n_mm = tun.mm_ready ? 0 : n_mm_levels * G.n_mm_groups;
     const int n = std::max(std::max(B * 12, B + G.n_groups), n_mm);
     init_kernel<<<(n + 255) / 256, 256, 0, stream>>>(pose_in, pose_hist, pose_in == pose_hist ? 0 : B * 12, counters,
                                                      B + G.n_groups, mm, n_mm);
@@ -1572,7 +1641,7 @@ static int run_lpi(const dpft_level_t* levels, int n_levels, int B, int C, int i
   }
   const bool shared_kf = flags & DPFT_SHARED_KEYFRAME, pairwise = G.group == 1;
   const int mm_per_level = G.n_mm_groups;
-  if (tru) {
+  if (tru && !tun.mm_ready) {
     // extremes of sigma0 per level and group, all levels in one launch
     const float* src[DPFT_MAX_LEVELS];
     size_t per_group[DPFT_MAX_LEVELS];
@@ -1774,9 +1843,15 @@ static int run_uic(const dpft_level_t* levels, int n_levels, int B, int C, int i
     } else {
       used = lpi_bytes(levels, n_levels, B, C, flags, any_occ, tun);
     }
-    if (workspace_bytes < used + kRepFlagBytes)
-      return set_error(DPFT_ENOSPACE, "workspace has %zu bytes, %zu needed", workspace_bytes, used + kRepFlagBytes);
     int* mism = (int*)((char*)workspace + used);
+    const Groups Gd = groups_of(B, flags, tun);
+    // behind the flag: the sigma0 extremes the check collects on the way, (level, group, 2) -- what launch_minmax_levels
+    // would otherwise compute in a pass of its own
+    const bool fuse_mm = (flags & DPFT_REMOVE_TRU_SIGMA) != 0;
+    uint32_t* mm_fused = (uint32_t*)((char*)workspace + used + kRepFlagBytes);
+    const size_t mm_bytes = rep_mm_bytes(n_levels, Gd.n_mm_groups);
+    if (workspace_bytes < used + kRepFlagBytes + mm_bytes)
+      return set_error(DPFT_ENOSPACE, "workspace has %zu bytes, %zu needed", workspace_bytes, used + kRepFlagBytes + mm_bytes);
     RepTensors rt{};
     const size_t Bk = (flags & DPFT_SHARED_KEYFRAME) ? 1 : (size_t)B;
     unsigned long long units = 0;
@@ -1787,17 +1862,23 @@ static int run_uic(const dpft_level_t* levels, int n_levels, int B, int C, int i
       for (int k = 0; k < 2; ++k) {
         rt.p[rt.n] = tp[k]; rt.plane[rt.n] = plane; rt.units[rt.n] = (unsigned)(np[k] * cpp);
         rt.first[rt.n] = (unsigned)units;
+        // sigma0: one slot per sigma-extreme group (one for a shared keyframe or a single batch)
+        rt.mm_base[rt.n] = (k == 0 && fuse_mm) ? l * Gd.n_mm_groups : -1;
+        rt.upg[rt.n] = (unsigned)((Gd.n_mm_groups > 1 ? (size_t)Gd.group : np[k]) * cpp);
         units += np[k] * cpp;
         ++rt.n;
       }
     }
     rt.first[rt.n] = (unsigned)units;
     if (units < (1ull << 32)) {     // (larger calls simply go without the check)
-      cudaMemsetAsync(mism, 0, sizeof(int), (cudaStream_t)stream);
+      // flag <- 0, extremes <- (+inf, -inf) in their order encoding: one small launch
+      const int n_mm = fuse_mm ? n_levels * Gd.n_mm_groups : 0;
+      init_kernel<<<(std::max(n_mm, 1) + 255) / 256, 256, 0, (cudaStream_t)stream>>>(nullptr, nullptr, 0, mism, 1, mm_fused, n_mm);
       const unsigned gx = (unsigned)std::min<unsigned long long>((units + 255) / 256, 148ull * 16);
-      if (C == 8) sigma_replication_kernel<8><<<gx, 256, 0, (cudaStream_t)stream>>>(rt, C, mism);
-      else sigma_replication_kernel<0><<<gx, 256, 0, (cudaStream_t)stream>>>(rt, C, mism);
+      if (C == 8) sigma_replication_kernel<8><<<gx, 256, 0, (cudaStream_t)stream>>>(rt, C, mism, fuse_mm ? mm_fused : nullptr);
+      else sigma_replication_kernel<0><<<gx, 256, 0, (cudaStream_t)stream>>>(rt, C, mism, fuse_mm ? mm_fused : nullptr);
       tun.mism = mism;
+      tun.mm_ready = fuse_mm ? mm_fused : nullptr;
     }
   }
   if (!use_queue) {
@@ -1814,8 +1895,9 @@ static int run_uic(const dpft_level_t* levels, int n_levels, int B, int C, int i
   for (int l = nc; l < n_levels; ++l) qbytes = std::max(qbytes, make_qplan(levels[l], l, B, C, iters, flags, tun).total);
   if (workspace_bytes < coarse_bytes + qbytes)
     return set_error(DPFT_ENOSPACE, "workspace has %zu bytes, %zu needed", workspace_bytes, coarse_bytes + qbytes);
-  // the coarse levels' launch computes the sigma0 extremes of EVERY level in its one reduction launch
-  const uint32_t* mm_all = nullptr;
+  // the coarse levels' launch computes the sigma0 extremes of EVERY level in its one reduction launch (unless the
+  // replication check already collected them)
+  const uint32_t* mm_all = tun.mm_ready;
   if (nc > 0) {
     const int rc = ms ? lpi_timed(levels, nc, B, C, iters, flags, w_icp, pose_in, pose_hist, sys_hist, aux_hist, status,
                                   workspace, coarse_bytes, stream, tun, ms, n_levels, &mm_all)
