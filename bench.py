@@ -407,7 +407,8 @@ def run_tum(args, wl, rank, world, dev, barrier, max_over_ranks):
     barrier()
     ms = max_over_ranks(e0.elapsed_time(e1), dev)
     res.raise_if_bad()
-    # kernels of one call: sigma replication check, init, sigma0 extremes of all levels, 3 iterations of the 15x20 level; then
+    # kernels of one call: init of the replication flag and the sigma0 extremes, the replication check (which collects those
+    # extremes on its way), init of poses and counters, 3 iterations of the 15x20 level; then
     # per level either 3 x 2 twin launches (resident 30x40 / staged 60x80 launch-per-iteration kernels) or, for the levels
     # that join the queue when the call is large enough (algorithms.default_queue_levels), queue init + its two twins
     def launches_per_call(g):
