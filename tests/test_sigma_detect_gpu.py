@@ -27,6 +27,19 @@ def stacked(B, G, seed, sigma_channels=1, H=120, W=160, n_levels=4):
     return parts, levels, pose
 
 
+def check_sigma0_extremes(res, levels, B, iters=3):
+    """aux_hist[k, g, 2:4] = min / max of sigma0 of the level of iteration k over the pairs of group g (alg:1976-1977).  With
+    the check on, the replication kernel collects them on its way; they must be torch's, bit for bit."""
+    for l, lv in enumerate(levels):
+        s0 = lv["s0"]
+        G = s0.shape[0] // B
+        lo = s0.reshape(G, -1).amin(dim=1)
+        hi = s0.reshape(G, -1).amax(dim=1)
+        for it in range(iters):
+            a = res.aux_hist[l * iters + it]
+            assert torch.equal(a[:, 2], lo) and torch.equal(a[:, 3], hi), (l, it)
+
+
 @pytest.mark.parametrize("queue", [False, True])
 def test_replicated_tensors_equal_the_c_map_routines_and_the_one_map_call(queue):
     B, G = 8, 3
@@ -41,6 +54,8 @@ def test_replicated_tensors_equal_the_c_map_routines_and_the_one_map_call(queue)
     assert (a.pose_hist - b.pose_hist).abs().max() < 1e-6
     assert frob_rel(a.sys_hist, b.sys_hist) < 2e-6
     assert (a.pose_hist - c.pose_hist).abs().max() < 1e-6 and frob_rel(a.sys_hist, c.sys_hist) < 2e-6
+    check_sigma0_extremes(a, levels, B)
+    check_sigma0_extremes(b, levels, B)
     # ... and the oracle, first batch
     trace = []
     with torch.no_grad():
@@ -60,6 +75,7 @@ def test_tensors_that_are_not_replicated_take_the_c_map_routines(queue):
     b = A.uic_solve(levels, pose, tuning=OFF, **kw)
     torch.cuda.synchronize()
     assert torch.equal(a.pose_hist, b.pose_hist) and torch.equal(a.sys_hist, b.sys_hist)
+    check_sigma0_extremes(a, levels, B)     # extremes over ALL channels, collected by the check although it found differences
 
 
 @pytest.mark.parametrize("where", ["s1_finest_last", "s0_coarsest_first", "s1_level1_middle"])
