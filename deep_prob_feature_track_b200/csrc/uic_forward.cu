@@ -1870,7 +1870,9 @@ static int run_uic(const dpft_level_t* levels, int n_levels, int B, int C, int i
       }
     }
     rt.first[rt.n] = (unsigned)units;
-    if (units < (1ull << 32)) {     // (larger calls simply go without the check)
+    // (larger calls simply go without the check; the margin keeps the kernel's 32-bit share bounds, begin + ceil(units / CTAs),
+    // from wrapping)
+    if (units < (1ull << 32) - (1ull << 16)) {
       // flag <- 0, extremes <- (+inf, -inf) in their order encoding: one small launch
       const int n_mm = fuse_mm ? n_levels * Gd.n_mm_groups : 0;
       init_kernel<<<(std::max(n_mm, 1) + 255) / 256, 256, 0, (cudaStream_t)stream>>>(nullptr, nullptr, 0, mism, 1, mm_fused, n_mm);
