@@ -15,9 +15,12 @@
 // order (fp64, deterministic whoever ran which tile), damps and solves the 6x6 system, writes the pose of iteration
 // k+1 and appends that iteration's tiles to the FIFO.  Nothing waits for a launch boundary; pairs drift apart and the
 // drain of one is hidden behind the tiles of the others.  It pays when the call holds more work than one wave of
-// tiles: several independent batches ("groups") per call, or pairs that nothing couples.  The coarse levels stay
-// with the launch-per-iteration kernels: their iterations are latency chains (measured, profiles/r2/) that a whole
-// grid walks faster in lockstep than pair by pair.
+// tiles: several independent batches ("groups") per call, or pairs that nothing couples.  Small calls keep the coarse
+// levels on the launch-per-iteration kernels: their iterations are latency chains (measured, profiles/r2/) that a whole
+// grid walks faster in lockstep than pair by pair.  Large calls give the second- and third-finest level a work-queue
+// launch of their own (algorithms.default_queue_levels; levels narrower than the staged routine's ring run its narrow
+// form, tile routine kind 2), and tiles grow to whole columns once an iteration offers 2.5 waves of them
+// (queue_tile_rows, uic_forward.cu).
 //
 // Batch-global sigma extremes without a barrier.  A pixel is masked when its warped sigma equals the minimum or the
 // maximum over the whole batch (group).  The mask only moves J^T r, and every record carries what its extreme pixels
