@@ -16,12 +16,16 @@ host cores.  The metric is frame-pair GN solves per second; rank 0 prints ONE JS
   value      whole-job throughput with the inputs already in HBM, through the package's public BatchedSolver: calls
              of `batches_per_call` batches (each batch keeps its own batch-global sigma extremes, i.e. the results
              of separate reference calls) rotate over `streams` CUDA streams; K steps = K batches exactly.
-             `latency_ms` next to it is ONE batch alone on one stream.
+             `latency_ms` next to it is ONE batch alone on one stream.  The device-timed region is bracketed by CUDA events
+             on the main stream around exactly K steps; a 0.4 ms spin kernel is enqueued right before the start event, so
+             the first call is already queued when the region starts (at 20 steps the region is one 4 ms call, and the
+             host's submission latency would otherwise sit inside it; `how.timed_region`).
   e2e        same metric with HOST (pinned) buffers: every step uploads its batch and reads its poses back inside
              the timed region (HostStreamSolver, 3 device buffers).  The host holds what the reference's encoder
              emits: ONE uncertainty map per frame (alg:1425-1427 repeats it on the device).
   roofline   dominant kernel = the finest-level work-queue launch (uic_queue_kernel: 3 iterations of
-             20 batches per launch, what a call of the timed region launches); achieved = algorithmic bytes (4C+2)*4*H*W*B per iteration / CUDA-event time
+             20 batches per launch, what a call of the timed region launches; in such calls the 60x80 and 30x40 levels run
+             as work-queue launches of their own as well, algorithms.default_queue_levels); achieved = algorithmic bytes (4C+2)*4*H*W*B per iteration / CUDA-event time
   parity     this run's own results against the CPU oracle on the step's first batch (twist, J^T W J, mask flips)
   cpu_baseline  the reference itself (baseline/_ref, installed from /root/reference) on the host cores, full batches
 
