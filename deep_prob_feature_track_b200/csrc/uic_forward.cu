@@ -1948,6 +1948,14 @@ extern "C" int dpft_uic_forward_timed(const dpft_level_t* levels, int n_levels, 
                  workspace_bytes, stream, tun);
 }
 
+// Rows per work-queue tile the planner picks for a level of H x W with B pairs in the call (test hook, not part of the ABI;
+// `workers` <= 0: what the device -- or, without one, a B200 -- holds of the one-map routine).
+extern "C" int dpft_debug_queue_tile_rows(int H, int W, int B, long workers) {
+  if (H < 1 || W < 1 || B < 1) return 0;
+  if (workers <= 0) workers = (long)device_sms() * queue_tiles_per_sm(true);
+  return queue_tile_rows(H, (W + kCols - 1) / kCols, B, workers);
+}
+
 // Host-side view of the balanced tile table of one level (test hook, not part of the ABI): returns 1 and fills
 // `tiles` ([2 kinds][max_warps][2 sub-tiles][seg, y0, y1]), `ctas` (CTAs per pair of kind 0 / 1), `n_more` (pairs of
 // kind 1), `nseg` and `warps_per_cta` when a table is used for (H, W, B), 0 when the rectangular tiling stays.
